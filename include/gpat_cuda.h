@@ -1,0 +1,287 @@
+/*
+ * gpat_cuda.h -- C ABI of the B200-native pseudo-particle SDE integrator for
+ * GPAT (xiaocanli/stochastic-parker).
+ *
+ * This is the drop-in boundary for ONE hot path of the reference: the Parker
+ * transport particle push + RNG + split/compaction + histogram diagnostics
+ * (SURVEY.md section 8).  The reference has no FFI of its own; the boundary sits
+ * where `program stochastic` (src/programs/stochastic-mhd.f90:12-33) `use`s
+ * particle_module / diagnostics / random_number_generator.  Every entry point
+ * below names the reference procedure it replaces (file:line under
+ * /root/reference/src).  fortran/gpat_cuda_iface.f90 holds the matching
+ * ISO_C_BINDING interface block; INTEGRATION.md shows the call-site patch.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all host arrays are owned by the caller
+ *    and are never retained past the call;
+ *  - arrays are column-major with the reference's index order (first index
+ *    fastest), so a Fortran array can be passed with c_loc();
+ *  - every function returns 0 (GPAT_OK) or a GPAT_ERR_* code; the message is
+ *    available from gpat_last_error().  The reference's own error style is
+ *    "print on rank 0; MPI_FINALIZE; stop" (simulation_setup.f90:78-87,
+ *    diagnostics.f90:1989-2014): the Fortran shim does that on non-zero;
+ *  - capacity overflow is SILENT, exactly as in the reference
+ *    (particle_module.f90:491-492, 5444-5447);
+ *  - there is no CPU fallback: without a CUDA device gpat_init fails.
+ */
+#ifndef GPAT_CUDA_H
+#define GPAT_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPAT_OK 0
+#define GPAT_ERR_INVALID 1 /* bad argument, or a reference feature outside the GPU path */
+#define GPAT_ERR_CUDA 2    /* CUDA runtime error (no device, OOM, launch failure) */
+#define GPAT_ERR_STATE 3   /* call sequence error (e.g. mover before fields) */
+#define GPAT_ERR_NCCL 4    /* NCCL not loadable or a collective failed */
+
+/* count_flag values, particle_module.f90:55-62 */
+#define GPAT_COUNT_FLAG_INBOX 1
+#define GPAT_COUNT_FLAG_OTHERS 0
+#define GPAT_COUNT_FLAG_ESCAPE_LX (-1)
+#define GPAT_COUNT_FLAG_ESCAPE_HX (-2)
+#define GPAT_COUNT_FLAG_ESCAPE_LY (-3)
+#define GPAT_COUNT_FLAG_ESCAPE_HY (-4)
+#define GPAT_COUNT_FLAG_ESCAPE_LZ (-5)
+#define GPAT_COUNT_FLAG_ESCAPE_HZ (-6)
+
+/* AoS particle record == `particle_type`, particle_module.f90:38-50 (104 B with
+ * natural padding).  Device storage is SoA; this layout is used only for
+ * upload/download (restart files, particle dumps: diagnostics.f90:1811-1888).
+ * `padding` carries the 64-bit per-particle RNG step counter (bit pattern),
+ * which the reference's mt_stream state has no equivalent of. */
+typedef struct gpat_particle {
+    int8_t split_times;
+    int8_t count_flag;
+    int8_t pad_[2];
+    int32_t origin;
+    int32_t nsteps_tracked;
+    int32_t nsteps_pushed;
+    int32_t tag_injected;
+    int32_t tag_splitted;
+    double x, y, z, p;
+    double v, mu;
+    double weight, t, dt;
+    double padding;
+} gpat_particle;
+
+/* One set of local-distribution parameters, diagnostics.f90:53-65, 2118-2140 */
+typedef struct gpat_hist_spec {
+    int32_t enabled; /* dump_local_distK */
+    int32_t npbins;  /* npbinsK */
+    int32_t nmu;     /* nmuK (forced to 1 for Parker, diagnostics.f90:2124-2128) */
+    int32_t rx, ry, rz;
+    double pmin, pmax; /* pminK, pmaxK */
+} gpat_hist_spec;
+
+#define GPAT_RNG_PHILOX 0 /* on-device Philox4x32-10, one stream per particle */
+#define GPAT_RNG_TABLE 1  /* replay pre-generated uniforms (gpat_set_rng_table) */
+
+/* Everything the reference keeps in module variables for this path.
+ * Sources: read_particle_params (particle_module.f90:2778-2878), set_dpp_params /
+ * set_flags_params / set_drift_parameters / set_flag_check_drift_2d
+ * (particle_module.f90:260-335), read_diagnostics_params (diagnostics.f90:2049-2200),
+ * mhd_config (mhd_config.f90:16-27), fconfig for a 1x1x1 topology
+ * (simulation_setup.f90:171-253), particle BCs (simulation_setup.f90:107-123). */
+typedef struct gpat_params {
+    /* grid */
+    int32_t ndim;        /* ndim_field: 2 or 3 (1-D is not on the GPU path) */
+    int32_t nx, ny, nz;  /* mhd_config%nx.. without ghost cells (nz=1 in 2-D) */
+    int32_t time_interp; /* time_interp_flag */
+    int32_t pbc[3];      /* pbcx,pbcy,pbcz: 0 periodic, 1 open */
+    double dx, dy, dz;
+    double xmin, ymin, zmin;
+    double xmax, ymax, zmax;
+    double lx, ly, lz;
+    /* particle parameters */
+    double b0, p0, pmin, pmax;
+    double gamma_turb, pindex; /* pindex = 3 - gamma_turb in the reference */
+    double kpara0, kret;
+    double dt_min_rel, dt_max_rel;
+    int32_t momentum_dependency, mag_dependency;
+    int32_t acc_region_flag;
+    int32_t pad0_;
+    double acc_region[6]; /* xmin,xmax,ymin,ymax,zmin,zmax in [0,1] */
+    /* momentum diffusion */
+    int32_t dpp_wave, dpp_shear, weak_scattering;
+    int32_t pad1_;
+    double tau0;
+    /* drift */
+    double drift1, drift2;
+    int32_t pcharge;
+    int32_t check_drift_2d;
+    /* model switches */
+    int32_t include_3rd_dim; /* include_3rd_dim_in2d_flag */
+    int32_t nlgc;
+    double kperp_kpara;
+    /* switches that must be 0/false on the GPU path (error otherwise) */
+    int32_t focused_transport, spherical_coord, nonuniform_grid;
+    int32_t deltab_flag, correlation_flag, acc_by_surface;
+    /* diagnostics */
+    int32_t npp_global, nmu_global;
+    gpat_hist_spec local[4];
+    /* RNG */
+    uint64_t seed;
+    int32_t rng_mode; /* GPAT_RNG_* */
+    /* rank identity (particle `origin`, particle_module.f90:428) */
+    int32_t mpi_rank;
+    /* arithmetic: 0 = fast (FMA contraction, fused time-blend), 1 = strict
+     * (no contraction, reference operation order; used by the parity tests) */
+    int32_t strict_math;
+    int32_t pad2_;
+} gpat_params;
+
+typedef struct gpat_sim* gpat_handle;
+
+/* ---- life cycle ------------------------------------------------------- */
+
+/* Replaces init_particles (particle_module.f90:171), init_prng
+ * (random_number_generator.f90:28), init_field_data (mhd_data_parallel.f90:66),
+ * init_particle_distributions (diagnostics.f90:178).  Allocates device SoA
+ * particle storage (capacity nptl_max), the field store and the histograms. */
+int gpat_init(gpat_handle* h, int device, int64_t nptl_max, const gpat_params* params);
+
+/* Re-reads the physics/diagnostics parameters (not the grid shape). */
+int gpat_set_params(gpat_handle h, const gpat_params* params);
+
+/* Replaces free_particles / delete_prng / free_field_data. */
+int gpat_finalize(gpat_handle h);
+
+/* Last error text for this handle (h may be NULL for init failures). */
+const char* gpat_last_error(gpat_handle h);
+
+/* ---- fields ------------------------------------------------------------ */
+
+/* Consumer side of read_field_data_parallel (mhd_data_parallel.f90:224) +
+ * calc_fields_gradients (mhd_data_parallel.f90:504).  `f` points at the first
+ * element of an array (nvar, nx+4, ny+4[, nz+4]) column-major, nvar = 8 (the
+ * on-disk mhd_data_NNNN record) or 32 (the reference's farray1/farray2).
+ * with_grad = 0: only the 8 primaries are read and the device computes the
+ * gradients with the reference's FP32/FP64 arithmetic; with_grad = 1 (nvar must
+ * be 32): slots 9..32 are taken as computed by the host.
+ * slot = 0 -> farray1 (frame at t0), 1 -> farray2 (frame at t0 + dtf). */
+int gpat_upload_fields(gpat_handle h, int slot, const float* f, int nvar, int with_grad);
+
+/* Replaces copy_fields (mhd_data_parallel.f90:1920): farray1 = farray2. O(1). */
+int gpat_swap_fields(gpat_handle h);
+
+/* ---- particles --------------------------------------------------------- */
+
+/* Replaces inject_particles_spatial_uniform (particle_module.f90:454-530, whole-field
+ * branch) + inject_one_particle (particle_module.f90:385-441).  t_frame =
+ * tstamps_mhd(ct_mhd), dt_mhd = tstamps_mhd(ct_mhd+1) - tstamps_mhd(ct_mhd).
+ * part_box = xmin,ymin,zmin,xmax,ymax,zmax (stochastic-mhd.f90:375-391). */
+int gpat_inject_uniform(gpat_handle h, int64_t nptl, double dt, int dist_flag,
+                        double particle_v0, double t_frame, double dt_mhd,
+                        const double part_box[6], double power_index);
+
+/* Replaces particle_mover (particle_module.f90:1846-1974) including both
+ * remove_particles passes (particle_module.f90:5365-5403).  t0 = tstamps_mhd(frame),
+ * dtf = tstamps_mhd(frame+1) - t0.  Blocking.  steps_done (may be NULL) receives
+ * the number of push_particle_* calls executed (the unit of the headline
+ * metric). */
+int gpat_particle_mover(gpat_handle h, double t0, double dtf, int nsteps_interval,
+                        int num_fine_steps, int dump_escaped_dist, uint64_t* steps_done);
+
+/* Replaces split_particle (particle_module.f90:5430-5480). */
+int gpat_split(gpat_handle h, double split_ratio, double pmin_split, int nsteps_interval);
+
+/* ptls(1:n) access for dump_particles (diagnostics.f90:1811), read_particles
+ * (particle_module.f90:5744) and the module state (particle_module.f90:5532-5664). */
+int gpat_download_particles(gpat_handle h, gpat_particle* out, int64_t nmax, int64_t* n);
+int gpat_upload_particles(gpat_handle h, const gpat_particle* in, int64_t n);
+
+/* Escaped particles of the current interval (escaped_ptls, particle_module.f90:134-135)
+ * and reset_escaped_particles (diagnostics.f90, called at stochastic-mhd.f90:533). */
+int gpat_download_escaped(gpat_handle h, gpat_particle* out, int64_t nmax, int64_t* n);
+int gpat_reset_escaped(gpat_handle h);
+
+/* Module counters: nptl_current, nptl_split, nptl_escaped, tag_max, leak,
+ * leak_negp (particle_module.f90:73-82). */
+typedef struct gpat_counters {
+    int64_t nptl_current, nptl_split, nptl_escaped, nptl_max;
+    int64_t tag_max;
+    double leak, leak_negp;
+} gpat_counters;
+int gpat_get_counters(gpat_handle h, gpat_counters* c);
+int gpat_set_counters(gpat_handle h, const gpat_counters* c);
+
+/* ---- diagnostics -------------------------------------------------------- */
+
+/* Replaces calc_particle_distributions (diagnostics.f90:738-906) + quick_check
+ * (diagnostics.f90:116-170) + get_pmax_global (diagnostics.f90:1691-1719) in one
+ * pass over the particles.  Outputs are ALREADY reduced over the ranks of the
+ * communicator set by gpat_comm_init (the MPI_REDUCE calls at diagnostics.f90:
+ * 881-905, 143-151, 1707); with no communicator they are the local values.
+ *   fglobal   : (nmu_global, npp_global) doubles
+ *   flocal[k] : (nmuK, npbinsK, nrxK, nryK, nrzK) doubles, or NULL to skip
+ *   quick[8]  : var_global(1:6) of quick_check = nptl_current, nptl_split,
+ *               sum(weight), leak, leak_negp, sum(dt); then pdt_min, pdt_max
+ *   pmax      : max particle momentum
+ * Any pointer may be NULL. */
+int gpat_diagnostics(gpat_handle h, int local_dist, double* fglobal, double* const flocal[4],
+                     double quick[8], double* pmax);
+
+/* calc_escaped_distributions (diagnostics.f90:913-1232), global part:
+ * fescaped (nmu_global, npp_global, 2*ndim), reduced like fglobal. */
+int gpat_escaped_diagnostics(gpat_handle h, double* fescaped);
+
+/* Bin edges, init_particle_distributions (diagnostics.f90:196-209, 270-283).
+ * which = 0 global, 1..4 local set.  pedges has npbins+1, muedges nmu+1 values. */
+int gpat_hist_edges(gpat_handle h, int which, double* pedges, double* muedges);
+
+/* ---- multi-GPU (one process per GPU) ------------------------------------ */
+
+/* NCCL communicator for the diagnostics all-reduce.  The 128-byte id is created
+ * on one rank and distributed by the caller (MPI_Bcast in the Fortran driver,
+ * torch.distributed in bench.py). */
+int gpat_comm_unique_id(char id[128]);
+int gpat_comm_init(gpat_handle h, const char id[128], int nranks, int rank);
+int gpat_comm_destroy(gpat_handle h);
+
+/* ---- instrumentation ---------------------------------------------------- */
+
+/* Device times (CUDA events on the library's stream) of the last calls, ms. */
+typedef struct gpat_timings {
+    float mover_ms;      /* whole gpat_particle_mover */
+    float push_ms;       /* push kernel only */
+    float compact_ms;    /* remove_particles passes */
+    float upload_ms;     /* last gpat_upload_fields: H2D + gradient/pack kernel */
+    float grad_ms;       /* gradient/pack kernel only */
+    float inject_ms, split_ms, diag_ms;
+    uint64_t push_steps; /* steps of the last mover call */
+    uint32_t push_launches;
+    uint32_t total_launches; /* kernels launched by this handle since init */
+} gpat_timings;
+int gpat_get_timings(gpat_handle h, gpat_timings* t);
+
+/* ---- test hooks ---------------------------------------------------------- */
+
+/* Uniform table for GPAT_RNG_TABLE: u[(slot*max_steps + step)*4 + j], where
+ * slot = tag_injected and step = the particle's RNG step counter. */
+int gpat_set_rng_table(gpat_handle h, const double* u, int64_t nslots, int64_t max_steps);
+
+/* All 24 gradients of an 8-variable frame with the device gradient arithmetic,
+ * returned in the reference's 32-slot layout (parity check of
+ * calc_fields_gradients, mhd_data_parallel.f90:533-566). */
+int gpat_debug_gradients(gpat_handle h, const float* f8, float* out32);
+
+/* Push every in-box particle exactly nsteps adaptive steps (inner loop body of
+ * particle_mover_one_cycle, particle_module.f90:1600-1704, without the end-of-interval
+ * fix-up).  Used for per-step parity and steady-state throughput. */
+int gpat_debug_push_n(gpat_handle h, double t0, double dtf, int nsteps, uint64_t* steps_done);
+
+/* Interpolated fields(1:32) at given positions/times for the current field
+ * store (interp_fields, mhd_data_parallel.f90:1751-1793); slots the push does not
+ * use on this configuration are returned as 0. */
+int gpat_debug_interp(gpat_handle h, int64_t n, const double* x, const double* y,
+                      const double* z, const double* rt, double* fields32);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPAT_CUDA_H */

@@ -1,0 +1,1305 @@
+/*
+ * gpat_oracle.c -- CPU restatement of GPAT's Parker-transport particle path.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may build, load or call it.  The product (stochastic_parker_b200/) never does.
+ *
+ * PARITY UNPINNED: the reference (xiaocanli/stochastic-parker) ships no tests,
+ * golden vectors or known-answer files for this path, and it cannot be built in
+ * this image (needs gfortran + MPI + HDF5 + FoBiS/FLAP + mt_stream_f90-1.11, none
+ * present).  This file restates the cited Fortran line by line: FP64 throughout,
+ * the same operation order (Fortran left-to-right association), the same
+ * default-real (FP32) literals.  Build the parity copy with
+ * `-O2 -ffp-contract=off` so the compiler keeps that order.
+ *
+ * Third-party arithmetic that is NOT restated: mt_stream_f90-1.11 (multiple-stream
+ * MT19937, random_number_generator.f90:9,35-44,100).  north_star defines parity
+ * as "fed the same pre-generated random increments", so uniforms are an INPUT
+ * here: either a table, or Philox4x32-10 keyed per particle (the stream the GPU
+ * library defines; specification in DESIGN.md "RNG").
+ *
+ * All file:line citations are relative to /root/reference/src/modules/ with
+ * PM = particle_module.f90, MD = mhd_data_parallel.f90, DG = diagnostics.f90.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../include/gpat_cuda.h" /* POD structs only (gpat_params, gpat_particle) */
+
+#define NFIELDS 8
+#define NGRADS 24
+#define NVAR (NFIELDS + NGRADS)
+
+typedef struct orc_sim {
+    gpat_params P;
+    int nxg, nyg, nzg;        /* array extents with ghosts: nx+4, ny+4, nz+4 | 1 */
+    float* farray1;           /* (32, nxg, nyg, nzg), MD:35,82-102 */
+    float* farray2;
+    gpat_particle* ptls;      /* PM:65 */
+    gpat_particle* escaped;   /* PM:134 */
+    int64_t nptl_current, nptl_old, nptl_max, nptl_split, nptl_inject;
+    int64_t nptl_escaped, nptl_escaped_max;
+    int64_t tag_max;
+    double leak, leak_negp;
+    double dt_min, dt_max;
+    int neighbors[6];         /* SS:299-342 for a 1x1x1 topology */
+    const double* rng_table;  /* optional uniform table */
+    int64_t rng_slots, rng_max_steps;
+    uint64_t steps;           /* push_particle_* calls */
+} orc_sim;
+
+static inline double sq(double x) { return x * x; }
+
+/* ------------------------------------------------------------------------ */
+/* Philox4x32-10 (Salmon et al., SC'11), written from the published algorithm. */
+/* ------------------------------------------------------------------------ */
+static void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    uint32_t k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    philox4x32_10(ctr, key, out);
+}
+
+/* u32 -> [0,1] with 32-bit resolution (the genrand_real1 convention) */
+static inline double u01(uint32_t w) { return (double)w / 4294967295.0; }
+
+static inline uint64_t get_rng_step(const gpat_particle* p)
+{
+    uint64_t s;
+    memcpy(&s, &p->padding, 8);
+    return s;
+}
+static inline void set_rng_step(gpat_particle* p, uint64_t s) { memcpy(&p->padding, &s, 8); }
+
+/* Four uniforms of one push step: ran1, ran2, ran3, ran_p (PM:3548-3550,3589). */
+static void step_uniforms(const orc_sim* S, const gpat_particle* ptl, double u[4])
+{
+    uint64_t step = get_rng_step(ptl);
+    if (S->P.rng_mode == GPAT_RNG_TABLE && S->rng_table) {
+        int64_t slot = ptl->tag_injected;
+        if (slot < 0 || slot >= S->rng_slots || (int64_t)step >= S->rng_max_steps) {
+            u[0] = u[1] = u[2] = u[3] = 0.5;
+            return;
+        }
+        const double* t = S->rng_table + ((size_t)slot * S->rng_max_steps + step) * 4;
+        u[0] = t[0]; u[1] = t[1]; u[2] = t[2]; u[3] = t[3];
+        return;
+    }
+    uint32_t ctr[4] = {(uint32_t)step, (uint32_t)(step >> 32), (uint32_t)ptl->tag_injected,
+                       (uint32_t)ptl->tag_splitted};
+    uint32_t key[2] = {(uint32_t)S->P.seed, (uint32_t)(S->P.seed >> 32) + (uint32_t)ptl->origin};
+    uint32_t o[4];
+    philox4x32_10(ctr, key, o);
+    for (int j = 0; j < 4; ++j) u[j] = u01(o[j]);
+}
+
+/* Sequential uniform reader for injection: word k of the stream
+ * ctr = (k/4, 0, tag_injected, 0), same key as above. */
+typedef struct inj_stream {
+    const orc_sim* S;
+    uint32_t tag, origin;
+    uint32_t k;
+    uint32_t buf[4];
+} inj_stream;
+
+static double inj_next(inj_stream* s)
+{
+    if ((s->k & 3u) == 0) {
+        uint32_t ctr[4] = {s->k >> 2, 0u, s->tag, 0u};
+        uint32_t key[2] = {(uint32_t)s->S->P.seed, (uint32_t)(s->S->P.seed >> 32) + s->origin};
+        philox4x32_10(ctr, key, s->buf);
+    }
+    double u = u01(s->buf[s->k & 3u]);
+    s->k++;
+    return u;
+}
+
+/* ------------------------------------------------------------------------ */
+/* life cycle                                                                */
+/* ------------------------------------------------------------------------ */
+static void set_neighbors(orc_sim* S)
+{
+    /* SS:267-272 (msize == 1): periodic -> self (rank 0), open -> -1 */
+    for (int d = 0; d < 3; ++d) {
+        int n = (S->P.pbc[d] == 0) ? 0 : -1;
+        S->neighbors[2 * d] = n;
+        S->neighbors[2 * d + 1] = n;
+    }
+}
+
+orc_sim* orc_create(const gpat_params* p, int64_t nptl_max)
+{
+    orc_sim* S = (orc_sim*)calloc(1, sizeof(orc_sim));
+    S->P = *p;
+    S->nxg = p->nx + 4;
+    S->nyg = (p->ndim > 1) ? p->ny + 4 : p->ny;
+    S->nzg = (p->ndim > 2) ? p->nz + 4 : p->nz;
+    size_t n = (size_t)NVAR * S->nxg * S->nyg * S->nzg;
+    S->farray1 = (float*)calloc(n, sizeof(float));
+    S->farray2 = (float*)calloc(n, sizeof(float));
+    S->nptl_max = nptl_max;
+    S->ptls = (gpat_particle*)calloc((size_t)nptl_max + 1, sizeof(gpat_particle)); /* PM:171-194 */
+    S->nptl_escaped_max = nptl_max;
+    S->escaped = (gpat_particle*)calloc((size_t)nptl_max + 1, sizeof(gpat_particle));
+    set_neighbors(S);
+    return S;
+}
+
+void orc_set_params(orc_sim* S, const gpat_params* p)
+{
+    S->P = *p;
+    set_neighbors(S);
+}
+
+void orc_destroy(orc_sim* S)
+{
+    if (!S) return;
+    free(S->farray1); free(S->farray2); free(S->ptls); free(S->escaped);
+    free(S);
+}
+
+void orc_set_rng_table(orc_sim* S, const double* u, int64_t nslots, int64_t max_steps)
+{
+    S->rng_table = u; S->rng_slots = nslots; S->rng_max_steps = max_steps;
+}
+
+/* ------------------------------------------------------------------------ */
+/* fields: load, gradients (MD:504-605), copy (MD:1920)                      */
+/* ------------------------------------------------------------------------ */
+#define FIDX(S, v, i, j, k) ((size_t)(v) + (size_t)NVAR * ((size_t)(i) + (size_t)(S)->nxg * ((size_t)(j) + (size_t)(S)->nyg * (size_t)(k))))
+
+/* f: (nvar, nxg, nyg, nzg); copies the 8 primaries (and 24 gradients if with_grad) */
+void orc_set_fields(orc_sim* S, int slot, const float* f, int nvar, int with_grad)
+{
+    float* fa = slot ? S->farray2 : S->farray1;
+    size_t ncell = (size_t)S->nxg * S->nyg * S->nzg;
+    int ncopy = (with_grad && nvar == NVAR) ? NVAR : NFIELDS;
+    for (size_t c = 0; c < ncell; ++c)
+        for (int v = 0; v < ncopy; ++v) fa[c * NVAR + v] = f[c * nvar + v];
+}
+
+void orc_calc_gradients(orc_sim* S, int slot)
+{
+    float* fa = slot ? S->farray2 : S->farray1;
+    const double idxh = 0.5 / S->P.dx; /* MD:512-514 */
+    const double idyh = 0.5 / S->P.dy;
+    const double idzh = 0.5 / S->P.dz;
+    const int nxg = S->nxg, nyg = S->nyg, nzg = S->nzg;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int k = 0; k < nzg; ++k)
+        for (int j = 0; j < nyg; ++j)
+            for (int i = 0; i < nxg; ++i)
+                for (int v = 0; v < NFIELDS; ++v) {
+                    float g;
+                    /* d/dx -> slot nfields+1+3v, MD:535-542 */
+                    if (i == 0) {
+                        float a = -3.0f * fa[FIDX(S, v, 0, j, k)];
+                        float b = 4.0f * fa[FIDX(S, v, 1, j, k)];
+                        float s = a + b;
+                        g = s - fa[FIDX(S, v, 2, j, k)];
+                    } else if (i == nxg - 1) {
+                        float a = 3.0f * fa[FIDX(S, v, nxg - 1, j, k)];
+                        float b = 4.0f * fa[FIDX(S, v, nxg - 2, j, k)];
+                        float s = a - b;
+                        g = s + fa[FIDX(S, v, nxg - 3, j, k)];
+                    } else {
+                        g = fa[FIDX(S, v, i + 1, j, k)] - fa[FIDX(S, v, i - 1, j, k)];
+                    }
+                    fa[FIDX(S, NFIELDS + 3 * v + 0, i, j, k)] = (float)((double)g * idxh);
+                    /* d/dy, MD:545-554 (only if the y extent > 1) */
+                    if (nyg > 1) {
+                        if (j == 0) {
+                            float a = -3.0f * fa[FIDX(S, v, i, 0, k)];
+                            float b = 4.0f * fa[FIDX(S, v, i, 1, k)];
+                            float s = a + b;
+                            g = s - fa[FIDX(S, v, i, 2, k)];
+                        } else if (j == nyg - 1) {
+                            float a = 3.0f * fa[FIDX(S, v, i, nyg - 1, k)];
+                            float b = 4.0f * fa[FIDX(S, v, i, nyg - 2, k)];
+                            float s = a - b;
+                            g = s + fa[FIDX(S, v, i, nyg - 3, k)];
+                        } else {
+                            g = fa[FIDX(S, v, i, j + 1, k)] - fa[FIDX(S, v, i, j - 1, k)];
+                        }
+                        fa[FIDX(S, NFIELDS + 3 * v + 1, i, j, k)] = (float)((double)g * idyh);
+                    }
+                    /* d/dz, MD:557-566 */
+                    if (nzg > 1) {
+                        if (k == 0) {
+                            float a = -3.0f * fa[FIDX(S, v, i, j, 0)];
+                            float b = 4.0f * fa[FIDX(S, v, i, j, 1)];
+                            float s = a + b;
+                            g = s - fa[FIDX(S, v, i, j, 2)];
+                        } else if (k == nzg - 1) {
+                            float a = 3.0f * fa[FIDX(S, v, i, j, nzg - 1)];
+                            float b = 4.0f * fa[FIDX(S, v, i, j, nzg - 2)];
+                            float s = a - b;
+                            g = s + fa[FIDX(S, v, i, j, nzg - 3)];
+                        } else {
+                            g = fa[FIDX(S, v, i, j, k + 1)] - fa[FIDX(S, v, i, j, k - 1)];
+                        }
+                        fa[FIDX(S, NFIELDS + 3 * v + 2, i, j, k)] = (float)((double)g * idzh);
+                    }
+                }
+}
+
+void orc_get_fields(const orc_sim* S, int slot, float* out32)
+{
+    const float* fa = slot ? S->farray2 : S->farray1;
+    memcpy(out32, fa, sizeof(float) * (size_t)NVAR * S->nxg * S->nyg * S->nzg);
+}
+
+void orc_copy_fields(orc_sim* S) /* MD:1920-1923 */
+{
+    memcpy(S->farray1, S->farray2, sizeof(float) * (size_t)NVAR * S->nxg * S->nyg * S->nzg);
+}
+
+/* ------------------------------------------------------------------------ */
+/* interpolation: get_interp_paramters (PM:642-674), interp_fields (MD:1751)  */
+/* ------------------------------------------------------------------------ */
+static void get_interp_parameters(const orc_sim* S, double px, double py, double pz, int pos[3],
+                                  double w[8])
+{
+    double rx, ry, rz;
+    if (S->P.ndim == 2) {
+        pos[0] = (int)floor(px) + 1; pos[1] = (int)floor(py) + 1; pos[2] = 1;
+        ry = py - pos[1] + 1;
+        rz = 0.0;
+    } else {
+        pos[0] = (int)floor(px) + 1; pos[1] = (int)floor(py) + 1; pos[2] = (int)floor(pz) + 1;
+        ry = py - pos[1] + 1;
+        rz = pz - pos[2] + 1;
+    }
+    rx = px - pos[0] + 1;
+    double rx1 = 1.0 - rx, ry1 = 1.0 - ry, rz1 = 1.0 - rz;
+    w[0] = rx1 * ry1 * rz1;
+    w[1] = rx * ry1 * rz1;
+    w[2] = rx1 * ry * rz1;
+    w[3] = rx * ry * rz1;
+    w[4] = rx1 * ry1 * rz;
+    w[5] = rx * ry1 * rz;
+    w[6] = rx1 * ry * rz;
+    w[7] = rx * ry * rz;
+}
+
+/* Fortran index ix in -1..nx+2 -> C index ix+1; iz: 1-based (extent 1) in 2-D */
+static void interp_fields(const orc_sim* S, const int pos[3], const double w[8], double rt,
+                          double fields[NVAR])
+{
+    double fields2[NVAR];
+    const int ze = (S->P.ndim > 2) ? 1 : 0;
+    const int ye = (S->P.ndim > 1) ? 1 : 0;
+    for (int v = 0; v < NVAR; ++v) { fields[v] = 0.0; fields2[v] = 0.0; }
+    for (int k = 0; k <= ze; ++k)
+        for (int j = 0; j <= ye; ++j)
+            for (int i = 0; i <= 1; ++i) {
+                int idx = k * 4 + j * 2 + i;
+                /* A runaway particle indexes outside farray in the reference (undefined
+                 * behaviour); here, as in the GPU library, the cell index is clamped. */
+                int c0 = pos[0] + 1, c1 = pos[1] + 1, c2 = pos[2] + 1;
+                if (c0 < 0) c0 = 0;
+                if (c0 > S->nxg - 2) c0 = S->nxg - 2;
+                if (c1 < 0) c1 = 0;
+                if (c1 > S->nyg - 2) c1 = S->nyg - 2;
+                if (c2 < 0) c2 = 0;
+                if (c2 > S->nzg - 2) c2 = S->nzg - 2;
+                int ci = c0 + i;
+                int cj = (S->P.ndim > 1) ? c1 + j : 0;
+                int ck = (S->P.ndim > 2) ? c2 + k : 0;
+                const float* f1 = S->farray1 + FIDX(S, 0, ci, cj, ck);
+                for (int v = 0; v < NVAR; ++v) fields[v] = fields[v] + (double)f1[v] * w[idx];
+                if (S->P.time_interp) {
+                    const float* f2 = S->farray2 + FIDX(S, 0, ci, cj, ck);
+                    for (int v = 0; v < NVAR; ++v) fields2[v] = fields2[v] + (double)f2[v] * w[idx];
+                }
+            }
+    if (S->P.time_interp) {
+        double rt1 = 1.0 - rt;
+        for (int v = 0; v < NVAR; ++v) fields[v] = fields[v] * rt1 + fields2[v] * rt;
+    }
+}
+
+void orc_interp(const orc_sim* S, int64_t n, const double* x, const double* y, const double* z,
+                const double* rt, double* fields32)
+{
+    for (int64_t i = 0; i < n; ++i) {
+        double px = (x[i] - S->P.xmin) / S->P.dx;
+        double py = (y[i] - S->P.ymin) / S->P.dy;
+        double pz = (z[i] - S->P.zmin) / S->P.dz;
+        int pos[3];
+        double w[8];
+        get_interp_parameters(S, px, py, pz, pos, w);
+        interp_fields(S, pos, w, rt[i], fields32 + (size_t)i * NVAR);
+    }
+}
+
+/* ------------------------------------------------------------------------ */
+/* kappa: PM:93-104, PM:2208-2450, PM:2464-2771                               */
+/* ------------------------------------------------------------------------ */
+typedef struct kappa_type {
+    double knorm_para, knorm_perp, kpara, kperp, skpara, skperp, skpara_perp;
+    double kxx, kyy, kzz, kxy, kxz, kyz;
+    double dkxx_dx, dkyy_dy, dkzz_dz, dkxy_dx, dkxy_dy, dkxz_dx, dkxz_dz, dkyz_dy, dkyz_dz;
+} kappa_type;
+
+#define F(n) fields[(n) - 1]           /* fields(n), 1-based */
+#define FG(n) fields[NFIELDS + (n) - 1] /* fields(nfields+n) */
+
+static void calc_kappa(const orc_sim* S, const gpat_particle* ptl, const double* fields,
+                       kappa_type* kp)
+{
+    const gpat_params* P = &S->P;
+    double bx = F(5), by = F(6), bz = F(7);
+    double b = sqrt(sq(bx) + sq(by) + sq(bz));
+    double ib1 = (b < 2.220446049250313e-16) ? 1.0 : 1.0 / b; /* EPSILON(b), PM:2230-2234 */
+    double ib2 = ib1 * ib1;
+    double ib3 = ib1 * ib2;
+    memset(kp, 0, sizeof(*kp));
+
+    kp->knorm_para = 1.0;
+    kp->knorm_perp = 1.0;
+    if (P->mag_dependency == 1) kp->knorm_para = kp->knorm_para * pow(b, P->gamma_turb - 2.0);
+    double knorm;
+    if (P->momentum_dependency == 1)
+        knorm = kp->knorm_para * pow(ptl->p / P->p0, P->pindex);
+    else
+        knorm = kp->knorm_para;
+    kp->knorm_perp = kp->knorm_para;
+    kp->kpara = P->kpara0 * knorm;
+    kp->kperp = kp->kpara * P->kret;
+    kp->skpara = sqrt(2.0 * kp->kpara);
+    kp->skperp = sqrt(2.0 * kp->kperp);
+    kp->skpara_perp = sqrt(2.0 * (kp->kpara - kp->kperp));
+
+    int three = (P->ndim == 3) || (P->ndim == 2 && P->include_3rd_dim);
+    double dbx_dx = FG(13), dbx_dy = FG(14), dby_dx = FG(16), dby_dy = FG(17);
+    double db_dx = FG(22), db_dy = FG(23);
+    double dbx_dz = 0.0, dby_dz = 0.0, dbz_dx = 0.0, dbz_dy = 0.0, dbz_dz = 0.0, db_dz = 0.0;
+    if (three) { dbz_dx = FG(19); dbz_dy = FG(20); }
+    if (P->ndim == 3) { dbx_dz = FG(15); dby_dz = FG(18); dbz_dz = FG(21); db_dz = FG(24); }
+    double dkdx = 0.0, dkdy = 0.0, dkdz = 0.0;
+    if (P->mag_dependency == 1) {
+        if (P->ndim == 3) { /* PM:2405-2409: no ib1 in 3-D */
+            dkdx = db_dx * (P->gamma_turb - 2.0);
+            dkdy = db_dy * (P->gamma_turb - 2.0);
+            dkdz = db_dz * (P->gamma_turb - 2.0);
+        } else { /* PM:2310-2313, 2360-2363 */
+            dkdx = db_dx * ib1 * (P->gamma_turb - 2.0);
+            dkdy = db_dy * ib1 * (P->gamma_turb - 2.0);
+        }
+    }
+    double kpp = kp->kpara - kp->kperp; /* not focused transport */
+    kp->dkxx_dx = kp->kperp * dkdx + kpp * dkdx * sq(bx) * ib2 +
+                  2.0 * kpp * bx * (dbx_dx * b - bx * db_dx) * ib3;
+    kp->dkyy_dy = kp->kperp * dkdy + kpp * dkdy * sq(by) * ib2 +
+                  2.0 * kpp * by * (dby_dy * b - by * db_dy) * ib3;
+    kp->dkxy_dx = kpp * dkdx * bx * by * ib2 +
+                  kpp * ((dbx_dx * by + bx * dby_dx) * ib2 - 2.0 * bx * by * db_dx * ib3);
+    kp->dkxy_dy = kpp * dkdy * bx * by * ib2 +
+                  kpp * ((dbx_dy * by + bx * dby_dy) * ib2 - 2.0 * bx * by * db_dy * ib3);
+    kp->kxx = kp->kperp + kpp * bx * bx * ib2;
+    kp->kyy = kp->kperp + kpp * by * by * ib2;
+    kp->kxy = kpp * bx * by * ib2;
+    if (three) {
+        kp->dkzz_dz = kp->kperp * dkdz + kpp * dkdz * sq(bz) * ib2 +
+                      2.0 * kpp * bz * (dbz_dz * b - bz * db_dz) * ib3;
+        kp->dkxz_dx = kpp * dkdx * bx * bz * ib2 +
+                      kpp * ((dbx_dx * bz + bx * dbz_dx) * ib2 - 2.0 * bx * bz * db_dx * ib3);
+        kp->dkxz_dz = kpp * dkdz * bx * bz * ib2 +
+                      kpp * ((dbx_dz * bz + bx * dbz_dz) * ib2 - 2.0 * bx * bz * db_dz * ib3);
+        kp->dkyz_dy = kpp * dkdy * by * bz * ib2 +
+                      kpp * ((dby_dy * bz + by * dbz_dy) * ib2 - 2.0 * by * bz * db_dy * ib3);
+        kp->dkyz_dz = kpp * dkdz * by * bz * ib2 +
+                      kpp * ((dby_dz * bz + by * dbz_dz) * ib2 - 2.0 * by * bz * db_dz * ib3);
+        kp->kzz = kp->kperp + kpp * bz * bz * ib2;
+        kp->kxz = kpp * bx * bz * ib2;
+        kp->kyz = kpp * by * bz * ib2;
+    }
+}
+
+/* NLGC variant, PM:2464-2771 (deltab/correlation flags off) */
+static void calc_kappa_nlgc(const orc_sim* S, const gpat_particle* ptl, const double* fields,
+                            kappa_type* kp)
+{
+    const gpat_params* P = &S->P;
+    double bx = F(5), by = F(6), bz = F(7);
+    double b = sqrt(sq(bx) + sq(by) + sq(bz));
+    double ib1 = (b < 2.220446049250313e-16) ? 1.0 : 1.0 / b;
+    double ib2 = ib1 * ib1;
+    double ib3 = ib1 * ib2;
+    memset(kp, 0, sizeof(*kp));
+    kp->knorm_para = 1.0;
+    kp->knorm_perp = 1.0;
+    if (P->mag_dependency == 1) {
+        kp->knorm_para = kp->knorm_para * pow(b, P->gamma_turb - 2.0);
+        kp->knorm_perp = kp->knorm_perp * pow(b, (P->gamma_turb - 2.0) / 3.0);
+    }
+    double knorm_para, knorm_perp;
+    if (P->momentum_dependency == 1) {
+        knorm_para = kp->knorm_para * pow(ptl->p / P->p0, P->pindex);
+        knorm_perp = kp->knorm_perp * pow(ptl->p / P->p0, (5.0 - P->gamma_turb) / 3.0);
+    } else {
+        knorm_para = kp->knorm_para;
+        knorm_perp = kp->knorm_perp;
+    }
+    kp->kpara = P->kpara0 * knorm_para;
+    kp->kperp = P->kpara0 * P->kperp_kpara * knorm_perp * sq(ptl->mu);
+    kp->skpara = sqrt(2.0 * kp->kpara);
+    kp->skperp = sqrt(2.0 * kp->kperp);
+    kp->skpara_perp = sqrt(2.0 * (kp->kpara - kp->kperp));
+
+    int three = (P->ndim == 3) || (P->ndim == 2 && P->include_3rd_dim);
+    double dbx_dx = FG(13), dbx_dy = FG(14), dby_dx = FG(16), dby_dy = FG(17);
+    double db_dx = FG(22), db_dy = FG(23);
+    double dbx_dz = 0.0, dby_dz = 0.0, dbz_dx = 0.0, dbz_dy = 0.0, dbz_dz = 0.0, db_dz = 0.0;
+    if (three) { dbz_dx = FG(19); dbz_dy = FG(20); }
+    if (P->ndim == 3) { dbx_dz = FG(15); dby_dz = FG(18); dbz_dz = FG(21); db_dz = FG(24); }
+    double dkpara_dx = 0.0, dkpara_dy = 0.0, dkpara_dz = 0.0;
+    double dkperp_dx = 0.0, dkperp_dy = 0.0, dkperp_dz = 0.0;
+    if (P->mag_dependency == 1) {
+        dkpara_dx = db_dx * ib1 * (P->gamma_turb - 2.0);
+        dkpara_dy = db_dy * ib1 * (P->gamma_turb - 2.0);
+        dkperp_dx = db_dx * ib1 * (P->gamma_turb - 2.0) / 3.0;
+        dkperp_dy = db_dy * ib1 * (P->gamma_turb - 2.0) / 3.0;
+        if (P->ndim == 3) {
+            dkpara_dz = db_dz * ib1 * (P->gamma_turb - 2.0);
+            dkperp_dz = db_dz * ib1 * (P->gamma_turb - 2.0) / 3.0;
+        }
+    }
+    double kpp = kp->kpara - kp->kperp;
+    double kpa = kp->kpara, kpe = kp->kperp;
+    kp->dkxx_dx = kpe * dkperp_dx + (kpa * dkpara_dx - kpe * dkperp_dx) * sq(bx) * ib2 +
+                  2.0 * kpp * bx * (dbx_dx * b - bx * db_dx) * ib3;
+    kp->dkyy_dy = kpe * dkperp_dy + (kpa * dkpara_dy - kpe * dkperp_dy) * sq(by) * ib2 +
+                  2.0 * kpp * by * (dby_dy * b - by * db_dy) * ib3;
+    kp->dkxy_dx = (kpa * dkpara_dx - kpe * dkperp_dx) * bx * by * ib2 +
+                  kpp * ((dbx_dx * by + bx * dby_dx) * ib2 - 2.0 * bx * by * db_dx * ib3);
+    kp->dkxy_dy = (kpa * dkpara_dy - kpe * dkperp_dy) * bx * by * ib2 +
+                  kpp * ((dbx_dy * by + bx * dby_dy) * ib2 - 2.0 * bx * by * db_dy * ib3);
+    kp->kxx = kpe + kpp * bx * bx * ib2;
+    kp->kyy = kpe + kpp * by * by * ib2;
+    kp->kxy = kpp * bx * by * ib2;
+    if (three) {
+        kp->dkzz_dz = kpe * dkperp_dz + (kpa * dkpara_dz - kpe * dkperp_dz) * sq(bz) * ib2 +
+                      2.0 * kpp * bz * (dbz_dz * b - bz * db_dz) * ib3;
+        kp->dkxz_dx = (kpa * dkpara_dx - kpe * dkperp_dx) * bx * bz * ib2 +
+                      kpp * ((dbx_dx * bz + bx * dbz_dx) * ib2 - 2.0 * bx * bz * db_dx * ib3);
+        kp->dkxz_dz = (kpa * dkpara_dz - kpe * dkperp_dz) * bx * bz * ib2 +
+                      kpp * ((dbx_dz * bz + bx * dbz_dz) * ib2 - 2.0 * bx * bz * db_dz * ib3);
+        kp->dkyz_dy = (kpa * dkpara_dy - kpe * dkperp_dy) * by * bz * ib2 +
+                      kpp * ((dby_dy * bz + by * dbz_dy) * ib2 - 2.0 * by * bz * db_dy * ib3);
+        kp->dkyz_dz = (kpa * dkpara_dz - kpe * dkperp_dz) * by * bz * ib2 +
+                      kpp * ((dby_dz * bz + by * dbz_dz) * ib2 - 2.0 * by * bz * db_dz * ib3);
+        kp->kzz = kpe + kpp * bz * bz * ib2;
+        kp->kxz = kpp * bx * bz * ib2;
+        kp->kyz = kpp * by * bz * ib2;
+    }
+}
+
+/* ------------------------------------------------------------------------ */
+/* acceleration region (PM:2885-2906), D_pp (PM:2918-2979)                    */
+/* ------------------------------------------------------------------------ */
+static int particle_in_acceleration_region(const orc_sim* S, const gpat_particle* ptl)
+{
+    const gpat_params* P = &S->P;
+    int inx, iny = 1, inz = 1;
+    double xnorm = (ptl->x - P->xmin) / P->lx;
+    inx = (xnorm >= P->acc_region[0]) && (xnorm <= P->acc_region[1]);
+    if (P->ndim > 1) {
+        double ynorm = (ptl->y - P->ymin) / P->ly;
+        iny = (ynorm >= P->acc_region[2]) && (ynorm <= P->acc_region[3]);
+    }
+    if (P->ndim == 3) {
+        double znorm = (ptl->z - P->zmin) / P->lz;
+        inz = (znorm >= P->acc_region[4]) && (znorm <= P->acc_region[5]);
+    }
+    return inx && iny && inz;
+}
+
+static void calc_dpp_wave_scattering(const orc_sim* S, double rho, double b, double kpara,
+                                     const gpat_particle* ptl, double* dp_dt, double* dpp)
+{
+    double va = b / sqrt(rho);
+    if (S->P.momentum_dependency == 1)
+        *dp_dt = *dp_dt + (8.0 * ptl->p / (27.0 * kpara)) * sq(va);
+    else
+        *dp_dt = *dp_dt + (4.0 * ptl->p / (9.0 * kpara)) * sq(va);
+    *dpp = *dpp + sq(ptl->p * va) / (9.0 * kpara);
+}
+
+static void calc_dpp_flow_shear(const orc_sim* S, double b, double bx, double by, double bz,
+                                double knorm_para, double sxx, double syy, double szz, double sxy,
+                                double sxz, double syz, const gpat_particle* ptl, double* dp_dt,
+                                double* dpp)
+{
+    const gpat_params* P = &S->P;
+    double gshear;
+    if (P->weak_scattering) {
+        double ib = (b < 2.220446049250313e-16) ? 0.0 : 1.0 / b;
+        double bbsigma = sxx * sq(bx) + syy * sq(by) + szz * sq(bz) +
+                         2.0 * (sxy * bx * by + sxz * bx * bz + syz * by * bz);
+        bbsigma = bbsigma * ib * ib;
+        gshear = sq(bbsigma) / 5.0;
+    } else {
+        gshear = 2.0 * (sq(sxx) + sq(syy) + sq(szz) + 2.0 * (sq(sxy) + sq(sxz) + sq(syz))) / 15.0;
+    }
+    if (gshear > 0.0) {
+        *dp_dt = *dp_dt + (2.0 + P->pindex) * gshear * P->tau0 * knorm_para *
+                              pow(ptl->p, P->pindex - 1.0) * pow(P->p0, 2.0 - P->pindex);
+        *dpp = *dpp + gshear * P->tau0 * knorm_para * pow(ptl->p, P->pindex) *
+                          pow(P->p0, 2.0 - P->pindex);
+    }
+}
+
+static inline double min2(double a, double b) { return (b < a) ? b : a; }
+
+/* common tail of every pusher: momentum update, PM:3589-3605 */
+static void update_momentum(const orc_sim* S, gpat_particle* ptl, double dp_dt, double dpp,
+                            double sdt, double ranp, double* deltap)
+{
+    const gpat_params* P = &S->P;
+    *deltap = dp_dt * ptl->dt + ranp * sqrt(2.0 * dpp) * sdt;
+    if (P->acc_region_flag == 1) {
+        if (particle_in_acceleration_region(S, ptl))
+            ptl->p = ptl->p + *deltap;
+        else
+            *deltap = 0.0;
+    } else {
+        ptl->p = ptl->p + *deltap;
+    }
+    if (ptl->p < 0.25 * P->p0) {
+        ptl->p = ptl->p - *deltap;
+        *deltap = 0.25 * P->p0 - ptl->p;
+        ptl->p = 0.25 * P->p0;
+    }
+}
+
+static double drift_vdp(const orc_sim* S, const gpat_particle* ptl)
+{
+    const gpat_params* P = &S->P;
+    /* `1.0 / (3 * pcharge)` is a default-real division, PM:3436 */
+    float q = 1.0f / (float)(3 * P->pcharge);
+    return (double)q / sqrt(sq(P->drift1 * P->p0 / ptl->p) + sq(P->drift2 * sq(P->p0) / sq(ptl->p)));
+}
+
+/* ------------------------------------------------------------------------ */
+/* push_particle_2d, PM:3358-3606 (Cartesian, uniform grid)                   */
+/* ------------------------------------------------------------------------ */
+static void push_particle_2d(orc_sim* S, gpat_particle* ptl, const double* fields,
+                             const kappa_type* kp, int fixed_dt, const double u[4], double* deltax,
+                             double* deltay, double* deltap)
+{
+    const gpat_params* P = &S->P;
+    double vx = F(1), vy = F(2), bx = F(5), by = F(6), bz = F(7);
+    double b = sqrt(sq(bx) + sq(by) + sq(bz));
+    double dvx_dx = FG(1), dvy_dy = FG(5);
+    double dxm = P->dx, dym = P->dy;
+    double ib = (b < 2.220446049250313e-16) ? 0.0 : 1.0 / b; /* PM:3414-3418 */
+    double dbz_dx = FG(19), dbz_dy = FG(20), db_dx = FG(22), db_dy = FG(23);
+    double ib2 = ib * ib;
+    double ib3 = ib * ib2;
+    double vdp = drift_vdp(S, ptl);
+    double vdx = vdp * (dbz_dy * ib2 - 2.0 * bz * db_dy * ib3);
+    double vdy = vdp * (-dbz_dx * ib2 + 2.0 * bz * db_dx * ib3);
+    double vdz;
+    if (P->check_drift_2d) {
+        double dbx_dy = FG(14), dby_dx = FG(16);
+        vdz = vdp * ((dby_dx - dbx_dy) * ib2 - 2.0 * (by * db_dx - bx * db_dy) * ib3);
+    } else {
+        vdz = 0.0;
+    }
+    double dx_dt = vx + vdx + kp->dkxx_dx + kp->dkxy_dy;
+    double dy_dt = vy + vdy + kp->dkxy_dx + kp->dkyy_dy;
+    double dz_dt = vdz;
+    double divv = dvx_dx + dvy_dy;
+    double dp_dt = -ptl->p * divv / 3.0;
+    double dpp = 0.0;
+    if (P->dpp_wave) calc_dpp_wave_scattering(S, F(4), b, kp->kpara, ptl, &dp_dt, &dpp);
+    if (P->dpp_shear) {
+        double dvx_dy = FG(2), dvy_dx = FG(4);
+        double sxx = dvx_dx - divv / 3.0, syy = dvy_dy - divv / 3.0, szz = -divv / 3.0;
+        double sxy = (dvx_dy + dvy_dx) / 2.0;
+        calc_dpp_flow_shear(S, b, bx, by, bz, kp->knorm_para, sxx, syy, szz, sxy, 0.0, 0.0, ptl,
+                            &dp_dt, &dpp);
+    }
+    if (!fixed_dt) {
+        if (dx_dt != 0.0 && dy_dt != 0.0 && dp_dt != 0.0) {
+            double s = (kp->skperp > 0.0) ? kp->skperp : kp->skpara; /* PM:3518-3530 */
+            double d = sq(0.5 * dxm / kp->skpara);
+            d = min2(d, sq(0.5 * dym / kp->skpara));
+            d = min2(d, sq(s / dx_dt));
+            d = min2(d, sq(s / dy_dt));
+            d = min2(d, (double)0.1f * ptl->p / fabs(dp_dt));
+            ptl->dt = d;
+        } else {
+            ptl->dt = S->dt_min;
+        }
+        if (ptl->dt < S->dt_min) ptl->dt = S->dt_min;
+        if (ptl->dt > S->dt_max) ptl->dt = S->dt_max;
+    }
+    double sdt = sqrt(ptl->dt);
+    double sqrt3 = sqrt(3.0);
+    double ran1 = (2.0 * u[0] - 1.0) * sqrt3;
+    double ran2 = (2.0 * u[1] - 1.0) * sqrt3;
+    double ran3 = (2.0 * u[2] - 1.0) * sqrt3;
+    *deltax = dx_dt * ptl->dt + ran1 * kp->skperp * sdt + ran3 * kp->skpara_perp * sdt * bx * ib;
+    *deltay = dy_dt * ptl->dt + ran2 * kp->skperp * sdt + ran3 * kp->skpara_perp * sdt * by * ib;
+    double deltaz = dz_dt * ptl->dt;
+    ptl->x = ptl->x + *deltax;
+    ptl->y = ptl->y + *deltay;
+    ptl->z = ptl->z + deltaz;
+    ptl->t = ptl->t + ptl->dt;
+    double ranp = (2.0 * u[3] - 1.0) * sqrt3;
+    update_momentum(S, ptl, dp_dt, dpp, sdt, ranp, deltap);
+}
+
+/* ------------------------------------------------------------------------ */
+/* push_particle_2d_include_3rd (PM:3979-4245) and push_particle_3d           */
+/* (PM:4625-4907): identical structure; 2-D sets every d/dz to zero.          */
+/* ------------------------------------------------------------------------ */
+static void push_particle_3d_like(orc_sim* S, gpat_particle* ptl, const double* fields,
+                                  kappa_type* kp, int fixed_dt, const double u[4], double* deltax,
+                                  double* deltay, double* deltaz, double* deltap)
+{
+    const gpat_params* P = &S->P;
+    const int full3d = (P->ndim == 3);
+    double vx = F(1), vy = F(2), vz = F(3), bx = F(5), by = F(6), bz = F(7);
+    double b = sqrt(sq(bx) + sq(by) + sq(bz));
+    double ib = (b < 2.220446049250313e-16) ? 0.0 : 1.0 / b;
+    double bxn = bx * ib, byn = by * ib, bzn = bz * ib;
+    double bxyn = sqrt(sq(bxn) + sq(byn));
+    double ibxyn = (bxyn < 2.220446049250313e-16) ? 0.0 : 1.0 / bxyn;
+    double dvx_dx = FG(1), dvy_dy = FG(5);
+    double dvz_dz = full3d ? FG(9) : 0.0;
+    double dxm = P->dx, dym = P->dy, dzm = P->dz;
+    double dbx_dy = FG(14), dby_dx = FG(16), dbz_dx = FG(19), dbz_dy = FG(20);
+    double db_dx = FG(22), db_dy = FG(23);
+    double dbx_dz = full3d ? FG(15) : 0.0;
+    double dby_dz = full3d ? FG(18) : 0.0;
+    double db_dz = full3d ? FG(24) : 0.0;
+    double ib2 = ib * ib;
+    double ib3 = ib * ib2;
+    double vdp = drift_vdp(S, ptl);
+    double vdx = vdp * ((dbz_dy - dby_dz) * ib2 - 2.0 * (bz * db_dy - by * db_dz) * ib3);
+    double vdy = vdp * ((dbx_dz - dbz_dx) * ib2 - 2.0 * (bx * db_dz - bz * db_dx) * ib3);
+    double vdz = vdp * ((dby_dx - dbx_dy) * ib2 - 2.0 * (by * db_dx - bx * db_dy) * ib3);
+    if (!full3d) { /* PM:4094-4096 */
+        kp->dkxz_dz = 0.0; kp->dkyz_dz = 0.0; kp->dkzz_dz = 0.0;
+    }
+    double dx_dt = vx + vdx + kp->dkxx_dx + kp->dkxy_dy + kp->dkxz_dz;
+    double dy_dt = vy + vdy + kp->dkxy_dx + kp->dkyy_dy + kp->dkyz_dz;
+    double dz_dt = vz + vdz + kp->dkxz_dx + kp->dkyz_dy + kp->dkzz_dz;
+    double divv = dvx_dx + dvy_dy + dvz_dz;
+    double dp_dt = -ptl->p * divv / 3.0;
+    double dpp = 0.0;
+    if (P->dpp_wave) calc_dpp_wave_scattering(S, F(4), b, kp->kpara, ptl, &dp_dt, &dpp);
+    if (P->dpp_shear) {
+        double dvx_dy = FG(2), dvy_dx = FG(4), dvz_dx = FG(7), dvz_dy = FG(8);
+        double dvx_dz = full3d ? FG(3) : 0.0;
+        double dvy_dz = full3d ? FG(6) : 0.0;
+        double sxx = dvx_dx - divv / 3.0, syy = dvy_dy - divv / 3.0, szz = dvz_dz - divv / 3.0;
+        double sxy = (dvx_dy + dvy_dx) / 2.0;
+        double sxz = (dvx_dz + dvz_dx) / 2.0;
+        double syz = (dvy_dz + dvz_dy) / 2.0;
+        calc_dpp_flow_shear(S, b, bx, by, bz, kp->knorm_para, sxx, syy, szz, sxy, sxz, syz, ptl,
+                            &dp_dt, &dpp);
+    }
+    if (!fixed_dt) {
+        if (dx_dt != 0.0 && dy_dt != 0.0 && dp_dt != 0.0) {
+            double s = (kp->skperp > 0.0) ? kp->skperp : kp->skpara;
+            double d = sq(0.5 * dxm / kp->skpara);
+            d = min2(d, sq(0.5 * dym / kp->skpara));
+            if (full3d) d = min2(d, sq(0.5 * dzm / kp->skpara)); /* PM:4815-4821 */
+            d = min2(d, sq(s / dx_dt));
+            d = min2(d, sq(s / dy_dt));
+            if (full3d) d = min2(d, sq(s / dz_dt));
+            d = min2(d, (double)0.1f * ptl->p / fabs(dp_dt));
+            ptl->dt = d;
+        } else {
+            ptl->dt = S->dt_min;
+        }
+        if (ptl->dt < S->dt_min) ptl->dt = S->dt_min;
+        if (ptl->dt > S->dt_max) ptl->dt = S->dt_max;
+    }
+    double sdt = sqrt(ptl->dt);
+    double sqrt3 = sqrt(3.0);
+    double ran1 = (2.0 * u[0] - 1.0) * sqrt3;
+    double ran2 = (2.0 * u[1] - 1.0) * sqrt3;
+    double ran3 = (2.0 * u[2] - 1.0) * sqrt3;
+    *deltax = dx_dt * ptl->dt + (bxn * kp->skpara * ran1 - bxn * bzn * kp->skperp * ibxyn * ran2 -
+                                 byn * kp->skperp * ibxyn * ran3) * sdt;
+    *deltay = dy_dt * ptl->dt + (byn * kp->skpara * ran1 - byn * bzn * kp->skperp * ibxyn * ran2 +
+                                 bxn * kp->skperp * ibxyn * ran3) * sdt;
+    *deltaz = dz_dt * ptl->dt + (bzn * kp->skpara * ran1 + bxyn * kp->skperp * ran2) * sdt;
+    ptl->x = ptl->x + *deltax;
+    ptl->y = ptl->y + *deltay;
+    ptl->z = ptl->z + *deltaz;
+    ptl->t = ptl->t + ptl->dt;
+    double ranp = (2.0 * u[3] - 1.0) * sqrt3;
+    update_momentum(S, ptl, dp_dt, dpp, sdt, ranp, deltap);
+}
+
+/* ------------------------------------------------------------------------ */
+/* particle_boundary_condition, PM:1984-2129 (single-rank branches)           */
+/* ------------------------------------------------------------------------ */
+static void particle_boundary_condition(orc_sim* S, gpat_particle* ptl, double xmin, double xmax,
+                                        double ymin, double ymax, double zmin, double zmax)
+{
+    const gpat_params* P = &S->P;
+    if (ptl->x < xmin && ptl->count_flag == GPAT_COUNT_FLAG_INBOX) {
+        if (S->neighbors[0] < 0) {
+#pragma omp atomic update
+            S->leak += ptl->weight;
+            ptl->count_flag = GPAT_COUNT_FLAG_ESCAPE_LX;
+        } else {
+            ptl->x = ptl->x - xmin + xmax;
+        }
+    } else if (ptl->x > xmax && ptl->count_flag == GPAT_COUNT_FLAG_INBOX) {
+        if (S->neighbors[1] < 0) {
+#pragma omp atomic update
+            S->leak += ptl->weight;
+            ptl->count_flag = GPAT_COUNT_FLAG_ESCAPE_HX;
+        } else {
+            ptl->x = ptl->x - xmax + xmin;
+        }
+    }
+    if (P->ndim > 1) {
+        if (ptl->y < ymin && ptl->count_flag == GPAT_COUNT_FLAG_INBOX) {
+            if (S->neighbors[2] < 0) {
+#pragma omp atomic update
+                S->leak += ptl->weight;
+                ptl->count_flag = GPAT_COUNT_FLAG_ESCAPE_LY;
+            } else {
+                ptl->y = ptl->y - ymin + ymax;
+            }
+        } else if (ptl->y > ymax && ptl->count_flag == GPAT_COUNT_FLAG_INBOX) {
+            if (S->neighbors[3] < 0) {
+#pragma omp atomic update
+                S->leak += ptl->weight;
+                ptl->count_flag = GPAT_COUNT_FLAG_ESCAPE_HY;
+            } else {
+                ptl->y = ptl->y - ymax + ymin;
+            }
+        }
+    }
+    if (P->ndim == 3 || (P->ndim == 2 && P->include_3rd_dim)) {
+        if (ptl->z < zmin && ptl->count_flag == GPAT_COUNT_FLAG_INBOX) {
+            if (S->neighbors[4] < 0) {
+#pragma omp atomic update
+                S->leak += ptl->weight;
+                ptl->count_flag = GPAT_COUNT_FLAG_ESCAPE_LZ;
+            } else {
+                ptl->z = ptl->z - zmin + zmax;
+            }
+        } else if (ptl->z > zmax && ptl->count_flag == GPAT_COUNT_FLAG_INBOX) {
+            if (S->neighbors[5] < 0) {
+#pragma omp atomic update
+                S->leak += ptl->weight;
+                ptl->count_flag = GPAT_COUNT_FLAG_ESCAPE_HZ;
+            } else {
+                ptl->z = ptl->z - zmax + zmin;
+            }
+        }
+    }
+}
+
+static void negp_or_bc(orc_sim* S, gpat_particle* ptl, const double e[6])
+{
+    if (ptl->p < 0.0) { /* PM:1602-1609 */
+        ptl->count_flag = GPAT_COUNT_FLAG_OTHERS;
+#pragma omp atomic update
+        S->leak_negp += ptl->weight;
+    } else {
+        particle_boundary_condition(S, ptl, e[0], e[1], e[2], e[3], e[4], e[5]);
+    }
+}
+
+/* one call of interp + kappa + push_particle_* (PM:1614-1691 / 1726-1802) */
+static void one_push(orc_sim* S, gpat_particle* ptl, double t0, double dtf, int fixed_dt,
+                     double* deltax, double* deltay, double* deltaz, double* deltap)
+{
+    const gpat_params* P = &S->P;
+    double px = (ptl->x - P->xmin) / P->dx;
+    double py = (ptl->y - P->ymin) / P->dy;
+    double pz = (ptl->z - P->zmin) / P->dz;
+    double rt = (ptl->t - t0) / dtf;
+    int pos[3];
+    double w[8], fields[NVAR], u[4];
+    kappa_type kp;
+    get_interp_parameters(S, px, py, pz, pos, w);
+    interp_fields(S, pos, w, rt, fields);
+    if (P->nlgc)
+        calc_kappa_nlgc(S, ptl, fields, &kp);
+    else
+        calc_kappa(S, ptl, fields, &kp);
+    step_uniforms(S, ptl, u);
+    if (P->ndim == 2 && !P->include_3rd_dim)
+        push_particle_2d(S, ptl, fields, &kp, fixed_dt, u, deltax, deltay, deltap);
+    else
+        push_particle_3d_like(S, ptl, fields, &kp, fixed_dt, u, deltax, deltay, deltaz, deltap);
+    set_rng_step(ptl, get_rng_step(ptl) + 1);
+}
+
+/* ------------------------------------------------------------------------ */
+/* particle_mover_one_cycle, PM:1481-1833                                     */
+/* ------------------------------------------------------------------------ */
+static void particle_mover_one_cycle(orc_sim* S, double t0, double dtf, int nsteps_interval,
+                                     int num_fine_steps)
+{
+    const gpat_params* P = &S->P;
+    const double dt_fine = dtf / num_fine_steps;
+    const double e[6] = {P->xmin - P->dx * 0.5, P->xmax + P->dx * 0.5, P->ymin - P->dy * 0.5,
+                         P->ymax + P->dy * 0.5, P->zmin - P->dz * 0.5, P->zmax + P->dz * 0.5};
+    uint64_t steps = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : steps)
+    for (int64_t i = S->nptl_old; i < S->nptl_current; ++i) {
+        gpat_particle ptl = S->ptls[i];
+        double deltax = 0.0, deltay = 0.0, deltaz = 0.0, deltap = 0.0;
+        double dt_target;
+        int step = (int)ceil((ptl.t - t0) / dt_fine); /* PM:1570 */
+        if (step <= 0)
+            dt_target = dt_fine;
+        else
+            dt_target = step * dt_fine;
+        if (dt_target > dtf) dt_target = dtf;
+
+        /* safe check, PM:1581-1592 */
+        if (ptl.p < 0.0 && ptl.count_flag == GPAT_COUNT_FLAG_INBOX) {
+            ptl.count_flag = GPAT_COUNT_FLAG_OTHERS;
+#pragma omp atomic update
+            S->leak_negp += ptl.weight;
+        } else {
+            particle_boundary_condition(S, &ptl, e[0], e[1], e[2], e[3], e[4], e[5]);
+        }
+        if (ptl.count_flag != GPAT_COUNT_FLAG_INBOX) {
+            S->ptls[i] = ptl;
+            continue;
+        }
+        while (dt_target < (dtf + dt_fine * (double)0.1f)) { /* PM:1596 */
+            if (ptl.count_flag != GPAT_COUNT_FLAG_INBOX) break;
+            while ((ptl.t - t0) < dt_target && ptl.count_flag == GPAT_COUNT_FLAG_INBOX) {
+                negp_or_bc(S, &ptl, e);
+                if (ptl.count_flag != GPAT_COUNT_FLAG_INBOX) break;
+                one_push(S, &ptl, t0, dtf, 0, &deltax, &deltay, &deltaz, &deltap);
+                steps++;
+                ptl.nsteps_pushed = (ptl.nsteps_pushed + 1) % nsteps_interval; /* PM:1694 */
+            }
+            /* make sure ptl%t reaches the target exactly, PM:1707-1826 */
+            if ((ptl.t - t0) > dt_target && ptl.count_flag == GPAT_COUNT_FLAG_INBOX) {
+                ptl.x = ptl.x - deltax;
+                ptl.y = ptl.y - deltay;
+                ptl.z = ptl.z - deltaz;
+                ptl.p = ptl.p - deltap;
+                ptl.t = ptl.t - ptl.dt;
+                double dt_old = ptl.dt;
+                ptl.dt = t0 + dt_target - ptl.t;
+                if (ptl.dt > 0) {
+                    ptl.nsteps_pushed = ptl.nsteps_pushed - 1; /* PM:1723 (untracked) */
+                    one_push(S, &ptl, t0, dtf, 1, &deltax, &deltay, &deltaz, &deltap);
+                    steps++;
+                    /* Fortran mod keeps the sign of the dividend, like C's % */
+                    ptl.nsteps_pushed = (ptl.nsteps_pushed + 1) % nsteps_interval;
+                }
+                ptl.dt = dt_old;
+                negp_or_bc(S, &ptl, e);
+            }
+            dt_target = dt_target + dt_fine;
+        }
+        S->ptls[i] = ptl;
+    }
+    S->steps += steps;
+}
+
+/* remove_particles, PM:5365-5403 (serial swap-with-tail) */
+static void remove_particles(orc_sim* S, int dump_escaped_dist)
+{
+    if (S->nptl_current > 0) {
+        int64_t nremoved = 0;
+        int64_t i = 1; /* 1-based like the reference */
+        while (i <= S->nptl_current) {
+            if ((S->nptl_current - i) == (nremoved - 1)) break;
+            gpat_particle* pi = &S->ptls[i - 1];
+            if (pi->count_flag == GPAT_COUNT_FLAG_INBOX) {
+                i = i + 1;
+            } else {
+                if (pi->count_flag < 0) {
+                    S->nptl_escaped++;
+                    if (dump_escaped_dist && S->nptl_escaped <= S->nptl_escaped_max)
+                        S->escaped[S->nptl_escaped - 1] = *pi;
+                }
+                gpat_particle ptl1 = S->ptls[S->nptl_current - nremoved - 1];
+                S->ptls[S->nptl_current - nremoved - 1] = *pi;
+                *pi = ptl1;
+                nremoved++;
+            }
+        }
+        S->nptl_current -= nremoved;
+    }
+}
+
+static void set_dt_min_max(orc_sim* S, double dtf) /* PM:5519-5524 */
+{
+    S->dt_min = S->P.dt_min_rel * dtf;
+    S->dt_max = S->P.dt_max_rel * dtf;
+}
+
+/* particle_mover, PM:1846-1974, for a 1x1x1 topology (one cycle, no exchange) */
+void orc_particle_mover(orc_sim* S, double t0, double dtf, int nsteps_interval, int num_fine_steps,
+                        int dump_escaped_dist, uint64_t* steps_done)
+{
+    const gpat_params* P = &S->P;
+    uint64_t s0 = S->steps;
+    S->nptl_old = 0;
+    set_dt_min_max(S, dtf);
+    for (int64_t i = 0; i < S->nptl_current; ++i) S->ptls[i].nsteps_tracked = 1; /* PM:1913 */
+    if (S->nptl_old < S->nptl_current)
+        particle_mover_one_cycle(S, t0, dtf, nsteps_interval, num_fine_steps);
+    remove_particles(S, dump_escaped_dist);
+    S->nptl_old = S->nptl_current; /* add_neighbor_particles, PM:5411 */
+    /* final pass with the un-extended box, PM:1959-1971 */
+    for (int64_t i = 0; i < S->nptl_current; ++i) {
+        gpat_particle ptl = S->ptls[i];
+        if (ptl.p < 0.0 && ptl.count_flag != GPAT_COUNT_FLAG_INBOX) {
+            ptl.count_flag = GPAT_COUNT_FLAG_OTHERS;
+            S->leak_negp += ptl.weight;
+        } else {
+            particle_boundary_condition(S, &ptl, P->xmin, P->xmax, P->ymin, P->ymax, P->zmin,
+                                        P->zmax);
+        }
+        S->ptls[i] = ptl;
+    }
+    remove_particles(S, dump_escaped_dist);
+    if (steps_done) *steps_done = S->steps - s0;
+}
+
+/* test hook mirrored by gpat_debug_push_n: exactly nsteps adaptive pushes */
+void orc_debug_push_n(orc_sim* S, double t0, double dtf, int nsteps, uint64_t* steps_done)
+{
+    const gpat_params* P = &S->P;
+    const double e[6] = {P->xmin - P->dx * 0.5, P->xmax + P->dx * 0.5, P->ymin - P->dy * 0.5,
+                         P->ymax + P->dy * 0.5, P->zmin - P->dz * 0.5, P->zmax + P->dz * 0.5};
+    set_dt_min_max(S, dtf);
+    uint64_t steps = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : steps)
+    for (int64_t i = 0; i < S->nptl_current; ++i) {
+        gpat_particle ptl = S->ptls[i];
+        double dx_, dy_, dz_ = 0.0, dp_;
+        for (int n = 0; n < nsteps && ptl.count_flag == GPAT_COUNT_FLAG_INBOX; ++n) {
+            negp_or_bc(S, &ptl, e);
+            if (ptl.count_flag != GPAT_COUNT_FLAG_INBOX) break;
+            one_push(S, &ptl, t0, dtf, 0, &dx_, &dy_, &dz_, &dp_);
+            steps++;
+        }
+        S->ptls[i] = ptl;
+    }
+    S->steps += steps;
+    if (steps_done) *steps_done = steps;
+}
+
+/* ------------------------------------------------------------------------ */
+/* injection: PM:454-530 (whole-field branch) + PM:385-441                     */
+/* ------------------------------------------------------------------------ */
+void orc_inject_uniform(orc_sim* S, int64_t nptl, double dt, int dist_flag, double particle_v0,
+                        double t_frame, double dt_mhd, const double part_box[6],
+                        double power_index)
+{
+    const gpat_params* P = &S->P;
+    const double mu_max = (double)0.99f; /* PM:121 */
+    double xmin_box = part_box[0], ymin_box = part_box[1], zmin_box = part_box[2];
+    double xmax_box = part_box[3], ymax_box = part_box[4], zmax_box = part_box[5];
+    S->nptl_inject = nptl;
+    for (int64_t i = 0; i < nptl; ++i) {
+        S->nptl_current++;
+        if (S->nptl_current > S->nptl_max) S->nptl_current = S->nptl_max; /* PM:491-492 */
+        gpat_particle* q = &S->ptls[S->nptl_current - 1];
+        inj_stream st = {S, (uint32_t)S->tag_max, (uint32_t)P->mpi_rank, 0, {0, 0, 0, 0}};
+        double xtmp = inj_next(&st) * (xmax_box - xmin_box) + xmin_box;
+        double ytmp = inj_next(&st) * (ymax_box - ymin_box) + ymin_box;
+        double ztmp = inj_next(&st) * (zmax_box - zmin_box) + zmin_box;
+        double mu_tmp = mu_max * (2.0 * inj_next(&st) - 1.0);
+        memset(q, 0, sizeof(*q));
+        q->x = xtmp; q->y = ytmp; q->z = ztmp;
+        if (dist_flag == 0) { /* PM:399-407 */
+            double ftest = 1.0, fxp = 0.5, ptmp = 0.0;
+            while (ftest > fxp) {
+                ptmp = (inj_next(&st) * (P->pmax - P->pmin) + P->pmin) / P->p0;
+                fxp = sq(ptmp) * exp(-sq(ptmp));
+                ftest = inj_next(&st) * (double)0.37f;
+            }
+            q->p = ptmp * P->p0;
+        } else if (dist_flag == 1) {
+            q->p = P->p0;
+        } else if (dist_flag == 2) { /* PM:410-418 */
+            double r01 = inj_next(&st);
+            if ((int)power_index == 1) {
+                q->p = pow(P->pmax / P->p0, r01) * P->p0;
+            } else {
+                double norm = pow(P->pmax, -power_index + 1) - pow(P->p0, -power_index + 1);
+                q->p = pow(r01 * norm + pow(P->p0, -power_index + 1), 1.0 / (-power_index + 1));
+            }
+        }
+        q->v = particle_v0 * q->p / P->p0;
+        q->mu = mu_tmp;
+        q->weight = 1.0;
+        q->t = t_frame + inj_next(&st) * dt_mhd;
+        q->dt = dt;
+        q->split_times = 0;
+        q->count_flag = GPAT_COUNT_FLAG_INBOX;
+        q->origin = P->mpi_rank;
+        q->nsteps_tracked = 0;
+        q->nsteps_pushed = 0;
+        q->tag_injected = (int32_t)S->tag_max;
+        S->tag_max++;
+        q->tag_splitted = 1;
+        set_rng_step(q, 0);
+    }
+}
+
+/* ------------------------------------------------------------------------ */
+/* split_particle, PM:5430-5480 (untracked particles)                         */
+/* ------------------------------------------------------------------------ */
+static double powi(double x, int m) /* libgcc __powidf2: what gfortran emits for dp**integer */
+{
+    unsigned int n = (m < 0) ? -(unsigned int)m : (unsigned int)m;
+    double y = (n % 2) ? x : 1.0;
+    while (n >>= 1) {
+        x = x * x;
+        if (n % 2) y *= x;
+    }
+    return (m < 0) ? 1.0 / y : y;
+}
+
+void orc_split(orc_sim* S, double split_ratio, double pmin_split, int nsteps_interval)
+{
+    (void)nsteps_interval;
+    const gpat_params* P = &S->P;
+    int64_t nptl = S->nptl_current;
+    for (int64_t i = 0; i < nptl; ++i) {
+        gpat_particle ptl = S->ptls[i];
+        double p_threshold = pmin_split * P->p0 * powi(split_ratio, ptl.split_times);
+        if (ptl.p > p_threshold && ptl.p <= P->pmax) {
+            S->nptl_current++;
+            if (S->nptl_current > S->nptl_max) {
+                S->nptl_current = S->nptl_max;
+                return;
+            }
+            S->nptl_split++;
+            ptl.weight = (double)powf(0.5f, 1.0f + (float)ptl.split_times); /* PM:5449 */
+            ptl.split_times = (int8_t)(ptl.split_times + 1);
+            S->ptls[S->nptl_current - 1] = ptl;
+            S->ptls[S->nptl_current - 1].tag_splitted =
+                ptl.tag_splitted + (1 << (ptl.split_times - 1)); /* PM:5475 */
+            S->ptls[i] = ptl;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------ */
+/* diagnostics: DG:196-209 (edges), DG:738-879 (binning), DG:116-170, 1691    */
+/* ------------------------------------------------------------------------ */
+static int64_t ifloor(double v, int* ok)
+{
+    if (!(v > -2.0e9 && v < 2.0e9)) { *ok = 0; return 0; } /* NaN/Inf: never a valid bin */
+    return (int64_t)floor(v);
+}
+
+void orc_hist_edges(const orc_sim* S, int which, double* pedges, double* muedges)
+{
+    const gpat_params* P = &S->P;
+    double pmin = which ? P->local[which - 1].pmin : P->pmin;
+    double pmax = which ? P->local[which - 1].pmax : P->pmax;
+    int np = which ? P->local[which - 1].npbins : P->npp_global;
+    int nmu = which ? P->local[which - 1].nmu : P->nmu_global;
+    double pmin_log = log10(pmin), pmax_log = log10(pmax);
+    double dp_log = (pmax_log - pmin_log) / np;
+    for (int i = 1; i <= np + 1; ++i) pedges[i - 1] = pow(10.0, pmin_log + (i - 1) * dp_log);
+    double dmu = (double)(2.0f / (float)nmu); /* DG:206: default-real division */
+    for (int i = 1; i <= nmu + 1; ++i) muedges[i - 1] = -1.0 + (i - 1) * dmu;
+}
+
+/* fglobal: (nmu_global, npp_global); flocal[k]: (nmu, npbins, nrx, nry, nrz), all
+ * column-major and zeroed here.  quick[8] and pmax as in gpat_diagnostics. */
+void orc_diagnostics(const orc_sim* S, int local_dist, double* fglobal, double* const flocal[4],
+                     double quick[8], double* pmax_out)
+{
+    const gpat_params* P = &S->P;
+    const int nmu_g = P->nmu_global, npp = P->npp_global;
+    double pmin_log = log10(P->pmin), pmax_log = log10(P->pmax);
+    double dp_log = (pmax_log - pmin_log) / npp;
+    double dmu = (double)(2.0f / (float)nmu_g);
+    if (fglobal) memset(fglobal, 0, sizeof(double) * (size_t)nmu_g * npp);
+    int nrx[4], nry[4], nrz[4];
+    double dxd[4], dyd[4], dzd[4], pminl[4], dpl[4], dmul[4];
+    for (int k = 0; k < 4; ++k) {
+        const gpat_hist_spec* h = &P->local[k];
+        if (!h->enabled) continue;
+        nrx[k] = (P->nx + h->rx - 1) / h->rx; /* DG:2135-2137 */
+        nry[k] = (P->ny + h->ry - 1) / h->ry;
+        nrz[k] = (P->nz + h->rz - 1) / h->rz;
+        dxd[k] = P->lx / nrx[k]; /* DG:271-276 (nrx_mhd == nrx for 1x1x1) */
+        dyd[k] = P->ly / nry[k];
+        dzd[k] = P->lz / nrz[k];
+        pminl[k] = log10(h->pmin);
+        dpl[k] = (log10(h->pmax) - pminl[k]) / h->npbins;
+        dmul[k] = (double)(2.0f / (float)h->nmu);
+        if (local_dist && flocal && flocal[k])
+            memset(flocal[k], 0, sizeof(double) * (size_t)h->nmu * h->npbins * nrx[k] * nry[k] * nrz[k]);
+    }
+    double q3 = 0.0, q6 = 0.0, pdt_min = 1.0, pdt_max = 0.0, pmx = 0.0;
+    for (int64_t n = 0; n < S->nptl_current; ++n) {
+        const gpat_particle* ptl = &S->ptls[n];
+        double x = ptl->x, y = ptl->y, z = ptl->z, p = ptl->p, mu = ptl->mu, weight = ptl->weight;
+        if (fglobal && p > P->pmin && p <= P->pmax && mu >= -1.0 && mu <= 1.0) {
+            int ok = 1;
+            int64_t ip = ifloor((log10(p) - pmin_log) / dp_log, &ok) + 1;
+            int64_t imu = ifloor((mu + 1.0) / dmu, &ok) + 1;
+            /* Column-major address like fglobal(imu,ip); an index past the array is
+             * undefined behaviour in the reference (DG:775-779) and is dropped here. */
+            int64_t lin = (imu - 1) + (ip - 1) * (int64_t)nmu_g;
+            if (ok && ip >= 1 && imu >= 1 && lin >= 0 && lin < (int64_t)nmu_g * npp)
+                fglobal[lin] += ptl->weight;
+        }
+        if (local_dist && flocal) {
+            for (int k = 0; k < 4; ++k) {
+                const gpat_hist_spec* h = &P->local[k];
+                if (!h->enabled || !flocal[k]) continue;
+                int ok = 1;
+                int64_t ix = ifloor((x - P->xmin) / dxd[k], &ok) + 1;
+                int64_t iy = ifloor((y - P->ymin) / dyd[k], &ok) + 1;
+                int64_t iz = ifloor((z - P->zmin) / dzd[k], &ok) + 1;
+                int64_t ip = ifloor((log10(p) - pminl[k]) / dpl[k], &ok) + 1;
+                int64_t imu = ifloor((mu + 1.0) / dmul[k], &ok) + 1;
+                int condx = ix >= 1 && ix <= nrx[k];
+                int condy = iy >= 1 && iy <= nry[k];
+                int condz = iz >= 1 && iz <= nrz[k];
+                int condp = ip > 0 && ip < h->npbins; /* top bin never filled, DG:799 */
+                int condmu = imu >= 1 && imu <= h->nmu;
+                if (ok && condx && condy && condz && condp && condmu) {
+                    size_t lin = (size_t)(imu - 1) +
+                                 (size_t)h->nmu * ((size_t)(ip - 1) +
+                                 (size_t)h->npbins * ((size_t)(ix - 1) +
+                                 (size_t)nrx[k] * ((size_t)(iy - 1) + (size_t)nry[k] * (size_t)(iz - 1))));
+                    flocal[k][lin] += weight;
+                }
+            }
+        }
+        q3 += ptl->weight;
+        if (ptl->dt < pdt_min) pdt_min = ptl->dt;
+        if (ptl->dt > pdt_max) pdt_max = ptl->dt;
+        q6 += ptl->dt;
+        if (ptl->p > pmx) pmx = ptl->p;
+    }
+    if (quick) {
+        quick[0] = (double)S->nptl_current;
+        quick[1] = (double)S->nptl_split;
+        quick[2] = q3;
+        quick[3] = S->leak;
+        quick[4] = S->leak_negp;
+        quick[5] = q6;
+        quick[6] = pdt_min;
+        quick[7] = pdt_max;
+    }
+    if (pmax_out) *pmax_out = pmx;
+}
+
+/* global part of calc_escaped_distributions, DG:913-1000: fescaped(nmu,npp,2*ndim),
+ * face index = -count_flag */
+void orc_escaped_diagnostics(const orc_sim* S, double* fescaped)
+{
+    const gpat_params* P = &S->P;
+    const int nmu_g = P->nmu_global, npp = P->npp_global, nface = 2 * P->ndim;
+    double pmin_log = log10(P->pmin), pmax_log = log10(P->pmax);
+    double dp_log = (pmax_log - pmin_log) / npp;
+    double dmu = (double)(2.0f / (float)nmu_g);
+    memset(fescaped, 0, sizeof(double) * (size_t)nmu_g * npp * nface);
+    int64_t n_esc = S->nptl_escaped < S->nptl_escaped_max ? S->nptl_escaped : S->nptl_escaped_max;
+    for (int64_t n = 0; n < n_esc; ++n) {
+        const gpat_particle* ptl = &S->escaped[n];
+        double p = ptl->p, mu = ptl->mu;
+        int face = -ptl->count_flag;
+        if (face < 1 || face > nface) continue;
+        if (p > P->pmin && p <= P->pmax && mu >= -1.0 && mu <= 1.0) {
+            int ok = 1;
+            int64_t ip = ifloor((log10(p) - pmin_log) / dp_log, &ok) + 1;
+            int64_t imu = ifloor((mu + 1.0) / dmu, &ok) + 1;
+            int64_t lin = (imu - 1) + (ip - 1) * (int64_t)nmu_g;
+            if (ok && ip >= 1 && imu >= 1 && lin >= 0 && lin < (int64_t)nmu_g * npp)
+                fescaped[lin + (size_t)(face - 1) * nmu_g * npp] += ptl->weight;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------ */
+/* accessors                                                                  */
+/* ------------------------------------------------------------------------ */
+int64_t orc_get_particles(const orc_sim* S, gpat_particle* out, int64_t nmax)
+{
+    int64_t n = S->nptl_current < nmax ? S->nptl_current : nmax;
+    memcpy(out, S->ptls, sizeof(gpat_particle) * (size_t)n);
+    return S->nptl_current;
+}
+
+void orc_set_particles(orc_sim* S, const gpat_particle* in, int64_t n)
+{
+    if (n > S->nptl_max) n = S->nptl_max;
+    memcpy(S->ptls, in, sizeof(gpat_particle) * (size_t)n);
+    S->nptl_current = n;
+}
+
+int64_t orc_get_escaped(const orc_sim* S, gpat_particle* out, int64_t nmax)
+{
+    int64_t n = S->nptl_escaped < nmax ? S->nptl_escaped : nmax;
+    if (n > S->nptl_escaped_max) n = S->nptl_escaped_max;
+    memcpy(out, S->escaped, sizeof(gpat_particle) * (size_t)n);
+    return S->nptl_escaped;
+}
+
+void orc_reset_escaped(orc_sim* S) { S->nptl_escaped = 0; }
+
+void orc_get_counters(const orc_sim* S, gpat_counters* c)
+{
+    c->nptl_current = S->nptl_current; c->nptl_split = S->nptl_split;
+    c->nptl_escaped = S->nptl_escaped; c->nptl_max = S->nptl_max; c->tag_max = S->tag_max;
+    c->leak = S->leak; c->leak_negp = S->leak_negp;
+}
+
+void orc_set_counters(orc_sim* S, const gpat_counters* c)
+{
+    S->nptl_current = c->nptl_current; S->nptl_split = c->nptl_split;
+    S->nptl_escaped = c->nptl_escaped; S->tag_max = c->tag_max;
+    S->leak = c->leak; S->leak_negp = c->leak_negp;
+}
+
+uint64_t orc_total_steps(const orc_sim* S) { return S->steps; }
+
+int orc_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}

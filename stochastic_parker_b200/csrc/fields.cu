@@ -1,0 +1,114 @@
+// fields.cu -- field store: gradient pre-pass + packing into the push kernel's records.
+//
+// Replaces calc_fields_gradients (mhd_data_parallel.f90:504-605) for uniform Cartesian
+// grids and the consumer side of read_field_data_parallel (mhd_data_parallel.f90:224).
+// The arithmetic is the reference's: FP32 difference, times 0.5/dx in FP64, rounded back
+// to FP32 on store; one-sided 3-point formula at the two ends of each array axis.  Only the
+// slots the configured pusher reads are materialised (gpat_internal.cuh, Rec<L>).
+#include "gpat_internal.cuh"
+
+namespace gpat {
+
+struct SlotMap {
+    int nrec;
+    int slot[32];  // reference slot (1-based) for each packed position, 0 = padding
+};
+
+struct GridDims {
+    int nxg, nyg, nzg;
+    double idxh, idyh, idzh;  // 0.5/dx, 0.5/dy, 0.5/dz (mhd_data_parallel.f90:512-514)
+};
+
+// gradient of primary v along direction d (0,1,2) at storage cell (i,j,k); src has `nvar`
+// floats per cell with the primaries first.
+__device__ __forceinline__ float grad_one(const float* __restrict__ src, int nvar, const GridDims& g,
+                                          int v, int d, int i, int j, int k)
+{
+    const long long sx = nvar, sy = (long long)nvar * g.nxg, sz = (long long)nvar * g.nxg * g.nyg;
+    const float* c = src + (long long)i * sx + (long long)j * sy + (long long)k * sz + v;
+    long long s;
+    int pos, n;
+    double idh;
+    if (d == 0) { s = sx; pos = i; n = g.nxg; idh = g.idxh; }
+    else if (d == 1) { s = sy; pos = j; n = g.nyg; idh = g.idyh; }
+    else { s = sz; pos = k; n = g.nzg; idh = g.idzh; }
+    if (n <= 1) return 0.0f;  // unresolved dimension: the reference leaves the zero fill
+    float diff;
+    if (pos == 0) {  // mhd_data_parallel.f90:537-539
+        float a = __fmul_rn(-3.0f, c[0]);
+        float b = __fmul_rn(4.0f, c[s]);
+        diff = __fsub_rn(__fadd_rn(a, b), c[2 * s]);
+    } else if (pos == n - 1) {  // mhd_data_parallel.f90:540-542
+        float a = __fmul_rn(3.0f, c[0]);
+        float b = __fmul_rn(4.0f, c[-s]);
+        diff = __fadd_rn(__fsub_rn(a, b), c[-2 * s]);
+    } else {  // mhd_data_parallel.f90:535-536
+        diff = __fsub_rn(c[s], c[-s]);
+    }
+    return __double2float_rn(__dmul_rn((double)diff, idh));
+}
+
+// One thread per grid point: fills its record (one frame half) in the packed store.
+__global__ void pack_kernel(const float* __restrict__ src, int nvar, int with_grad, GridDims g,
+                            SlotMap map, float* __restrict__ dst, long long stride, int half_off)
+{
+    const long long ncell = (long long)g.nxg * g.nyg * g.nzg;
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < ncell;
+         c += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(c % g.nxg);
+        const int j = (int)((c / g.nxg) % g.nyg);
+        const int k = (int)(c / ((long long)g.nxg * g.nyg));
+        float* out = dst + c * stride + half_off;
+        for (int q = 0; q < map.nrec; q += 4) {
+            float v4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int s = map.slot[q + e];
+                float val = 0.0f;
+                if (s >= 1 && s <= 8) val = src[c * nvar + (s - 1)];
+                else if (s > 8) {
+                    if (with_grad) val = src[c * nvar + (s - 1)];
+                    else val = grad_one(src, nvar, g, (s - 9) / 3, (s - 9) % 3, i, j, k);
+                }
+                v4[e] = val;
+            }
+            *reinterpret_cast<float4*>(out + q) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+        }
+    }
+}
+
+// debug: the full 32-slot reference layout from an 8-variable frame
+__global__ void grad32_kernel(const float* __restrict__ src, GridDims g, float* __restrict__ out32)
+{
+    const long long ncell = (long long)g.nxg * g.nyg * g.nzg;
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < ncell;
+         c += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(c % g.nxg);
+        const int j = (int)((c / g.nxg) % g.nyg);
+        const int k = (int)(c / ((long long)g.nxg * g.nyg));
+        for (int v = 0; v < 8; ++v) out32[c * 32 + v] = src[c * 8 + v];
+        for (int s = 9; s <= 32; ++s)
+            out32[c * 32 + s - 1] = grad_one(src, 8, g, (s - 9) / 3, (s - 9) % 3, i, j, k);
+    }
+}
+
+void launch_pack(const float* src, int nvar, int with_grad, const DevParams& prm, int layout,
+                 float* dst, int half, int sm_count, cudaStream_t st)
+{
+    GridDims g{prm.nxg, prm.nyg, prm.nzg, 0.5 / prm.dx, 0.5 / prm.dy, 0.5 / prm.dz};
+    SlotMap map;
+    map.nrec = nrec_of(layout);
+    for (int k = 0; k < 32; ++k) map.slot[k] = (k < map.nrec) ? slot_of(layout, k) : 0;
+    const long long stride = (long long)map.nrec * (prm.time_interp ? 2 : 1);
+    const int half_off = (prm.time_interp ? half : 0) * map.nrec;
+    pack_kernel<<<sm_count * 8, 256, 0, st>>>(src, nvar, with_grad, g, map, dst, stride, half_off);
+}
+
+void launch_grad32(const float* src8, const DevParams& prm, float* out32, int sm_count,
+                   cudaStream_t st)
+{
+    GridDims g{prm.nxg, prm.nyg, prm.nzg, 0.5 / prm.dx, 0.5 / prm.dy, 0.5 / prm.dz};
+    grad32_kernel<<<sm_count * 8, 256, 0, st>>>(src8, g, out32);
+}
+
+}  // namespace gpat

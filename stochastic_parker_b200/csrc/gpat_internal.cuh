@@ -1,0 +1,182 @@
+// gpat_internal.cuh -- device-side data layout shared by the kernels of libgpat_cuda.so.
+//
+// HBM layout (DESIGN.md "Data layout"):
+//  * particles: structure-of-arrays, one contiguous device allocation, capacity nptl_max
+//    (the reference's AoS particle_type, particle_module.f90:38-50, exists only at the
+//    upload/download boundary);
+//  * fields: one packed record per grid point holding ONLY the slots the configured
+//    pusher reads (15 of the reference's 32 for 2-D Parker), FP32 exactly as the
+//    reference stores them (mhd_data_parallel.f90:35), the two time frames of a grid
+//    point interleaved so that one 128-byte line holds both frames of a 2-D cell.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/gpat_cuda.h"
+
+namespace gpat {
+
+// ---- packed field record layouts ---------------------------------------------------
+// Reference slot numbers (1-based, mhd_data_parallel.f90:77-81): 1 vx 2 vy 3 vz 4 rho 5 bx
+// 6 by 7 bz 8 |B|; gradient of primary k along d (1..3) is slot 8 + 3(k-1) + d.
+enum Layout : int { L2B = 0, L2E = 1, L3B = 2, L3E = 3 };
+
+template <int L> struct Rec;
+// 2-D Parker without momentum diffusion: 15 slots (particle_module.f90:3392-3399, 3430-3433,
+// 2352-2357) + 1 pad = 64 B per frame
+template <> struct Rec<L2B> {
+    static constexpr int NREC = 16, NUSED = 15, NDIM = 2;
+    static constexpr bool EXT = false;
+};
+// + vz (include_3rd_dim), rho (D_pp wave), dvx_dy dvy_dx dvz_dx dvz_dy (D_pp shear)
+template <> struct Rec<L2E> {
+    static constexpr int NREC = 24, NUSED = 21, NDIM = 2;
+    static constexpr bool EXT = true;
+};
+// 3-D Parker: 21 slots (particle_module.f90:4665-4670, 4686-4688, 2390-2401)
+template <> struct Rec<L3B> {
+    static constexpr int NREC = 24, NUSED = 21, NDIM = 3;
+    static constexpr bool EXT = false;
+};
+template <> struct Rec<L3E> {
+    static constexpr int NREC = 32, NUSED = 28, NDIM = 3;
+    static constexpr bool EXT = true;
+};
+
+// packed position -> reference slot (1-based); 0 marks padding
+__host__ __device__ constexpr int slot_of(int layout, int k)
+{
+    constexpr int l2[24] = {1, 2, 5, 6, 7, 9, 13, 21, 22, 24, 25, 27, 28, 30, 31, /*15*/ 3,
+                            4, 10, 12, 15, 16, 0, 0, 0};
+    constexpr int l3[32] = {1, 2, 3, 5, 6, 7, 9, 13, 17, 21, 22, 23, 24, 25, 26, 27, 28, 29,
+                            30, 31, 32, /*21*/ 4, 10, 11, 12, 14, 15, 16, 0, 0, 0, 0};
+    return (layout == L2B) ? (k < 15 ? l2[k] : 0)
+         : (layout == L2E) ? l2[k]
+         : (layout == L3B) ? (k < 21 ? l3[k] : 0)
+                           : l3[k];
+}
+__host__ __device__ constexpr int nrec_of(int layout)
+{
+    return layout == L2B ? 16 : layout == L3E ? 32 : 24;
+}
+
+// named positions inside a record
+namespace s2 {  // 2-D layouts
+enum { vx = 0, vy, bx, by, bz, dvx_dx, dvy_dy, dbx_dx, dbx_dy, dby_dx, dby_dy, dbz_dx, dbz_dy,
+       db_dx, db_dy, vz, rho, dvx_dy, dvy_dx, dvz_dx, dvz_dy };
+}
+namespace s3 {  // 3-D layouts
+enum { vx = 0, vy, vz, bx, by, bz, dvx_dx, dvy_dy, dvz_dz, dbx_dx, dbx_dy, dbx_dz, dby_dx, dby_dy,
+       dby_dz, dbz_dx, dbz_dy, dbz_dz, db_dx, db_dy, db_dz, rho, dvx_dy, dvx_dz, dvy_dx, dvy_dz,
+       dvz_dx, dvz_dy };
+}
+
+// ---- particles (SoA) ---------------------------------------------------------------
+struct PtlSoA {
+    double *x, *y, *z, *p, *v, *mu, *weight, *t, *dt;
+    unsigned long long* rng;  // per-particle Philox step counter
+    int *origin, *nsteps_tracked, *nsteps_pushed, *tag_injected, *tag_splitted;
+    signed char *split_times, *count_flag;
+};
+
+// ---- parameters as the kernels see them ----------------------------------------------
+struct DevParams {
+    // grid
+    int ndim, nx, ny, nz, nxg, nyg, nzg;
+    int time_interp;
+    int pbc[3];
+    double dx, dy, dz, xmin, ymin, zmin, xmax, ymax, zmax, lx, ly, lz;
+    double ext[6];  // extended box xmin1,xmax1,ymin1,ymax1,zmin1,zmax1 (particle_module.f90:1528-1533)
+    // physics
+    double p0, pmin, pmax, gamma_turb, pindex, kpara0, kret, kperp_kpara;
+    double gm2;      // gamma_turb - 2
+    double gm2_3;    // (gamma_turb - 2) / 3
+    double pidx_perp;  // (5 - gamma_turb) / 3
+    double qdrift;   // dble(1.0 / (3*pcharge)) evaluated in FP32 (particle_module.f90:3436)
+    double drift1, drift2, tau0;
+    double p0_pow;   // p0**(2 - pindex)
+    double acc_region[6];
+    int momentum_dependency, mag_dependency, acc_region_flag;
+    int dpp_wave, dpp_shear, weak_scattering, check_drift_2d, include_3rd_dim, nlgc;
+    // rng
+    unsigned int key0, key1;  // Philox key = (seed_lo, seed_hi + origin)
+    int rng_mode;
+    int mpi_rank;
+};
+
+struct PushArgs {
+    double t0, dtf, dt_fine, dt_min, dt_max;
+    double dt_target_limit;  // dtf + dt_fine*0.1 (particle_module.f90:1596)
+    int nsteps_interval;
+    int debug_nsteps;        // >0: gpat_debug_push_n mode
+    int sel;                 // which half of a record pair holds farray1
+    long long nptl;
+    unsigned long long* queue;   // work counter
+    unsigned long long* steps;   // push_particle_* calls
+    double* leak;                // [0] leak, [1] leak_negp
+    const double* rng_table;
+    long long rng_slots, rng_max_steps;
+};
+
+// ---- stream-compaction scratch (particles.cu) ---------------------------------------------
+struct ScanWork {
+    unsigned* tile_counts;
+    long long* tile_offsets;
+};
+
+// ---- histogram pass (diag.cu) ---------------------------------------------------------------
+struct HistDev {
+    int enabled, npbins, nmu, nrx, nry, nrz;
+    double pmin_log, dp_log, dmu, dx_diag, dy_diag, dz_diag;
+    double* data;
+};
+
+struct DiagArgs {
+    long long n;
+    int local_dist;
+    int nmu_g, npp_g;
+    double pmin, pmax, pmin_log, dp_log, dmu;
+    double xmin, ymin, zmin;
+    double* fglobal;  // (nmu_g, npp_g) column-major
+    HistDev loc[4];
+    double* sums;                // [0] sum weight [1] sum dt
+    unsigned long long* minmax;  // [0] min dt bits [1] max dt bits [2] max p bits
+};
+
+// device counters (long long): [0] nptl_current [1] nptl_escaped [2] alive m [3] nholes
+// [4] nfillers [5] escaped in this pass [6] split candidates
+constexpr int kNumCounters = 8;
+
+void launch_pack(const float* src, int nvar, int with_grad, const DevParams& prm, int layout,
+                 float* dst, int half, int sm_count, cudaStream_t st);
+void launch_grad32(const float* src8, const DevParams& prm, float* out32, int sm_count,
+                   cudaStream_t st);
+void launch_inject(const DevParams& prm, const PtlSoA& P, long long n, long long start,
+                   long long nptl_max, long long tag0, double dt, int dist_flag, double particle_v0,
+                   double t_frame, double dt_mhd, const double box[6], double power_index,
+                   cudaStream_t st);
+void launch_remove(const PtlSoA& P, const PtlSoA& E, long long ecap, long long n, long long* counters,
+                   const ScanWork& w, long long* idx_a, long long* idx_b, int dump_escaped,
+                   cudaStream_t st);
+void launch_final_bc(const DevParams& prm, const PtlSoA& P, long long nmax, const long long* n_dev,
+                     double* leak, cudaStream_t st);
+void launch_split(const DevParams& prm, const PtlSoA& P, long long n, long long nptl_max,
+                  double split_ratio, double pmin_split, long long* counters, long long* nptl_split,
+                  const ScanWork& w, long long* idx_a, cudaStream_t st);
+void launch_to_aos(const PtlSoA& P, gpat_particle* out, long long n, cudaStream_t st);
+void launch_from_aos(const PtlSoA& P, const gpat_particle* in, long long n, cudaStream_t st);
+void launch_diag(const PtlSoA& P, const DiagArgs& a, int sm_count, cudaStream_t st);
+void launch_escaped_diag(const PtlSoA& E, long long n, const DiagArgs& a, int nface, double* fesc,
+                         cudaStream_t st);
+void launch_finalize_quick(const double* sums, const unsigned long long* minmax, const double* leak,
+                           double nptl_current, double nptl_split, double* q9, cudaStream_t st);
+
+void launch_push_fast(int layout, const DevParams& prm, const PtlSoA& P, const float* fld,
+                      const PushArgs& a, int sm_count, cudaStream_t st);
+void launch_push_strict(int layout, const DevParams& prm, const PtlSoA& P, const float* fld,
+                        const PushArgs& a, int sm_count, cudaStream_t st);
+void launch_interp_debug(int layout, const DevParams& prm, const float* fld, int sel, long long n,
+                         const double* x, const double* y, const double* z, const double* rt,
+                         double* out32, cudaStream_t st);
+
+}  // namespace gpat

@@ -1,0 +1,434 @@
+// particles.cu -- injection, splitting, dead-particle compaction, AoS<->SoA conversion.
+//
+//  * inject_kernel   : inject_particles_spatial_uniform + inject_one_particle
+//                      (particle_module.f90:454-530, 385-441), one thread per new particle
+//  * split           : split_particle (particle_module.f90:5430-5480) as flag -> scan -> append
+//  * remove          : remove_particles (particle_module.f90:5365-5403) as stream compaction
+//                      that reproduces the reference's swap-with-tail ORDER exactly
+//  * to_aos/from_aos : particle_type records for dumps and restart
+//
+// The scans are hand-written "warp ballot + block scan" stream compaction: pass A counts
+// selected items per 1024-item tile (__syncthreads_count), pass B scans the tile counts in
+// one block, pass C recomputes the predicate and writes each selected index at
+// tile offset + warp offset + popc(ballot below lane).
+#include "gpat_internal.cuh"
+
+namespace gpat {
+
+constexpr int kTile = 1024;
+
+// ---- Philox (same algorithm as push.cu; injection stream) -----------------------------------
+__device__ __forceinline__ uint4 philox_inj(uint4 c, unsigned k0, unsigned k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+
+struct InjStream {  // word k of ctr = (k/4, 0, tag_injected, 0)
+    unsigned tag, k0, k1, k;
+    uint4 buf;
+    __device__ double next()
+    {
+        if ((k & 3u) == 0) buf = philox_inj(make_uint4(k >> 2, 0u, tag, 0u), k0, k1);
+        unsigned w = (k & 3u) == 0 ? buf.x : (k & 3u) == 1 ? buf.y : (k & 3u) == 2 ? buf.z : buf.w;
+        k++;
+        return __ddiv_rn((double)w, 4294967295.0);
+    }
+};
+
+struct InjectArgs {
+    long long n, start, nptl_max;
+    long long tag0;
+    double dt, particle_v0, t_frame, dt_mhd, power_index;
+    double box[6];
+    int dist_flag;
+};
+
+__global__ void inject_kernel(const __grid_constant__ DevParams prm, const PtlSoA P,
+                              const __grid_constant__ InjectArgs a)
+{
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    // particle_module.f90:491-492: past capacity every particle lands in slot nptl_max; the
+    // serial loop leaves the LAST one there.
+    long long slot = a.start + i;
+    if (slot >= a.nptl_max) {
+        if (i != a.n - 1) return;
+        slot = a.nptl_max - 1;
+    }
+    InjStream s{(unsigned)(a.tag0 + i), prm.key0, prm.key1 + (unsigned)prm.mpi_rank, 0u, make_uint4(0, 0, 0, 0)};
+    const double mu_max = (double)0.99f;  // particle_module.f90:121
+    // no contraction here: these are parity-checked bit for bit against the oracle
+    double x = __dadd_rn(__dmul_rn(s.next(), a.box[3] - a.box[0]), a.box[0]);
+    double y = __dadd_rn(__dmul_rn(s.next(), a.box[4] - a.box[1]), a.box[1]);
+    double z = __dadd_rn(__dmul_rn(s.next(), a.box[5] - a.box[2]), a.box[2]);
+    double mu = __dmul_rn(mu_max, __dsub_rn(__dmul_rn(2.0, s.next()), 1.0));
+    double p;
+    if (a.dist_flag == 0) {  // particle_module.f90:399-407
+        double ftest = 1.0, fxp = 0.5, ptmp = 0.0;
+        while (ftest > fxp) {
+            ptmp = __ddiv_rn(__dadd_rn(__dmul_rn(s.next(), prm.pmax - prm.pmin), prm.pmin), prm.p0);
+            double p2 = __dmul_rn(ptmp, ptmp);
+            fxp = __dmul_rn(p2, exp(-p2));
+            ftest = __dmul_rn(s.next(), (double)0.37f);
+        }
+        p = __dmul_rn(ptmp, prm.p0);
+    } else if (a.dist_flag == 2) {  // particle_module.f90:410-418
+        double r01 = s.next();
+        if ((int)a.power_index == 1) {
+            p = __dmul_rn(pow(prm.pmax / prm.p0, r01), prm.p0);
+        } else {
+            double e = -a.power_index + 1;
+            double norm = pow(prm.pmax, e) - pow(prm.p0, e);
+            p = pow(__dadd_rn(__dmul_rn(r01, norm), pow(prm.p0, e)), 1.0 / e);
+        }
+    } else {
+        p = prm.p0;
+    }
+    P.x[slot] = x; P.y[slot] = y; P.z[slot] = z; P.p[slot] = p;
+    P.v[slot] = __ddiv_rn(__dmul_rn(a.particle_v0, p), prm.p0);
+    P.mu[slot] = mu;
+    P.weight[slot] = 1.0;
+    P.t[slot] = __dadd_rn(a.t_frame, __dmul_rn(s.next(), a.dt_mhd));
+    P.dt[slot] = a.dt;
+    P.rng[slot] = 0ull;
+    P.split_times[slot] = 0;
+    P.count_flag[slot] = GPAT_COUNT_FLAG_INBOX;
+    P.origin[slot] = prm.mpi_rank;
+    P.nsteps_tracked[slot] = 0;
+    P.nsteps_pushed[slot] = 0;
+    P.tag_injected[slot] = (int)(a.tag0 + i);
+    P.tag_splitted[slot] = 1;
+}
+
+void launch_inject(const DevParams& prm, const PtlSoA& P, long long n, long long start,
+                   long long nptl_max, long long tag0, double dt, int dist_flag, double particle_v0,
+                   double t_frame, double dt_mhd, const double box[6], double power_index,
+                   cudaStream_t st)
+{
+    if (n <= 0) return;
+    InjectArgs a;
+    a.n = n; a.start = start; a.nptl_max = nptl_max; a.tag0 = tag0; a.dt = dt;
+    a.particle_v0 = particle_v0; a.t_frame = t_frame; a.dt_mhd = dt_mhd;
+    a.power_index = power_index; a.dist_flag = dist_flag;
+    for (int i = 0; i < 6; ++i) a.box[i] = box[i];
+    inject_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(prm, P, a);
+}
+
+// ---- stream compaction primitives --------------------------------------------------------
+enum Pred : int { PRED_ALIVE = 0, PRED_HOLE, PRED_FILLER, PRED_ESCAPED, PRED_SPLIT };
+
+struct PredArgs {
+    const signed char* count_flag;
+    const signed char* split_times;
+    const double* p;
+    const long long* m;  // device: number of alive particles (for HOLE / FILLER)
+    double thr0, split_ratio, pmax;  // SPLIT: p > thr0 * split_ratio**split_times, p <= pmax
+};
+
+// libgcc's __powidf2, which is what gfortran emits for real(dp)**integer
+__device__ __forceinline__ double powi(double x, int mexp)
+{
+    unsigned n = (mexp < 0) ? (unsigned)(-mexp) : (unsigned)mexp;
+    double y = (n & 1u) ? x : 1.0;
+    while (n >>= 1) {
+        x = __dmul_rn(x, x);
+        if (n & 1u) y = __dmul_rn(y, x);
+    }
+    return (mexp < 0) ? 1.0 / y : y;
+}
+
+template <int PRED>
+__device__ __forceinline__ bool pred(const PredArgs& a, long long i)
+{
+    if (PRED == PRED_ALIVE) return a.count_flag[i] == GPAT_COUNT_FLAG_INBOX;
+    if (PRED == PRED_HOLE) return i < *a.m && a.count_flag[i] != GPAT_COUNT_FLAG_INBOX;
+    if (PRED == PRED_FILLER) return i >= *a.m && a.count_flag[i] == GPAT_COUNT_FLAG_INBOX;
+    if (PRED == PRED_ESCAPED) return a.count_flag[i] < 0;
+    // particle_module.f90:5441-5442
+    double thr = __dmul_rn(a.thr0, powi(a.split_ratio, (int)a.split_times[i]));
+    return a.p[i] > thr && a.p[i] <= a.pmax;
+}
+
+template <int PRED>
+__global__ void __launch_bounds__(kTile) tile_count_kernel(PredArgs a, long long n, unsigned* tile_counts)
+{
+    long long i = blockIdx.x * (long long)kTile + threadIdx.x;
+    int f = (i < n) ? (int)pred<PRED>(a, i) : 0;
+    int c = __syncthreads_count(f);
+    if (threadIdx.x == 0) tile_counts[blockIdx.x] = (unsigned)c;
+}
+
+// exclusive scan of the tile counts by one block; total -> *total
+__global__ void __launch_bounds__(1024) tile_scan_kernel(unsigned* tile_counts, long long ntiles,
+                                                          long long* tile_offsets, long long* total)
+{
+    __shared__ long long warp_sums[32];
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    for (long long base = 0; base < ntiles; base += 1024) {
+        long long i = base + threadIdx.x;
+        long long v = (i < ntiles) ? (long long)tile_counts[i] : 0;
+        long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += t;
+        }
+        if (lane == 31) warp_sums[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            long long ws = warp_sums[lane];
+            long long wi = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                long long t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= (unsigned)o) wi += t;
+            }
+            warp_sums[lane] = wi - ws;  // exclusive warp offsets
+        }
+        __syncthreads();
+        long long excl = carry + warp_sums[wid] + incl - v;
+        if (i < ntiles) tile_offsets[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+// writes the index of every selected item, in ascending order, to out[]
+template <int PRED>
+__global__ void __launch_bounds__(kTile) tile_scatter_kernel(PredArgs a, long long n,
+                                                             const long long* tile_offsets,
+                                                             long long* out)
+{
+    __shared__ unsigned warp_cnt[32];
+    long long i = blockIdx.x * (long long)kTile + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    bool f = (i < n) && pred<PRED>(a, i);
+    unsigned b = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) warp_cnt[wid] = __popc(b);
+    __syncthreads();
+    if (wid == 0) {
+        unsigned c = warp_cnt[lane], incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (unsigned)o) incl += t;
+        }
+        warp_cnt[lane] = incl - c;
+    }
+    __syncthreads();
+    if (f) out[tile_offsets[blockIdx.x] + warp_cnt[wid] + __popc(b & ((1u << lane) - 1u))] = i;
+}
+
+template <int PRED>
+static void select_indices(const PredArgs& a, long long n, const ScanWork& w, long long* out,
+                           long long* total, cudaStream_t st)
+{
+    long long ntiles = (n + kTile - 1) / kTile;
+    if (ntiles == 0) {
+        cudaMemsetAsync(total, 0, sizeof(long long), st);
+        return;
+    }
+    tile_count_kernel<PRED><<<(unsigned)ntiles, kTile, 0, st>>>(a, n, w.tile_counts);
+    tile_scan_kernel<<<1, 1024, 0, st>>>(w.tile_counts, ntiles, w.tile_offsets, total);
+    if (out) tile_scatter_kernel<PRED><<<(unsigned)ntiles, kTile, 0, st>>>(a, n, w.tile_offsets, out);
+}
+
+__device__ __forceinline__ void copy_particle(const PtlSoA& D, long long d, const PtlSoA& S, long long s)
+{
+    D.x[d] = S.x[s]; D.y[d] = S.y[s]; D.z[d] = S.z[s]; D.p[d] = S.p[s]; D.v[d] = S.v[s];
+    D.mu[d] = S.mu[s]; D.weight[d] = S.weight[s]; D.t[d] = S.t[s]; D.dt[d] = S.dt[s];
+    D.rng[d] = S.rng[s]; D.origin[d] = S.origin[s]; D.nsteps_tracked[d] = S.nsteps_tracked[s];
+    D.nsteps_pushed[d] = S.nsteps_pushed[s]; D.tag_injected[d] = S.tag_injected[s];
+    D.tag_splitted[d] = S.tag_splitted[s]; D.split_times[d] = S.split_times[s];
+    D.count_flag[d] = S.count_flag[s];
+}
+
+// ---- remove_particles --------------------------------------------------------------------
+// The serial reference walks i upward and swaps every non-INBOX particle with the current
+// tail.  Net effect: the k-th hole (ascending) among the first m = #alive slots receives the
+// k-th alive particle counted DOWN from the end.  Reproduced here with two index lists.
+__global__ void fill_holes_kernel(PtlSoA P, const long long* holes, const long long* fillers,
+                                  const long long* nholes)
+{
+    long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long nh = *nholes;
+    if (k >= nh) return;
+    copy_particle(P, holes[k], P, fillers[nh - 1 - k]);
+}
+
+__global__ void save_escaped_kernel(PtlSoA E, long long ebase_cap, const long long* ebase,
+                                    PtlSoA P, const long long* idx, const long long* nesc)
+{
+    long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (k >= *nesc) return;
+    long long d = *ebase + k;
+    if (d < ebase_cap) copy_particle(E, d, P, idx[k]);
+}
+
+// counters layout (device, long long): [0] nptl_current [1] nptl_escaped [2] scratch alive m
+// [3] nholes [4] nfillers [5] nesc_this_pass [6] nsplit_this_pass
+__global__ void after_remove_kernel(long long* c)
+{
+    c[1] += c[5];
+    c[0] = c[2];
+}
+
+void launch_remove(const PtlSoA& P, const PtlSoA& E, long long ecap, long long n, long long* counters,
+                   const ScanWork& w, long long* idx_a, long long* idx_b, int dump_escaped,
+                   cudaStream_t st)
+{
+    if (n <= 0) return;
+    PredArgs a{P.count_flag, P.split_times, P.p, counters + 2, 0.0, 0.0, 0.0};
+    // escaped particles first (they are overwritten by the hole filling)
+    select_indices<PRED_ESCAPED>(a, n, w, dump_escaped ? idx_a : nullptr, counters + 5, st);
+    if (dump_escaped)
+        save_escaped_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(E, ecap, counters + 1, P, idx_a,
+                                                                         counters + 5);
+    select_indices<PRED_ALIVE>(a, n, w, nullptr, counters + 2, st);
+    select_indices<PRED_HOLE>(a, n, w, idx_a, counters + 3, st);
+    select_indices<PRED_FILLER>(a, n, w, idx_b, counters + 4, st);
+    fill_holes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, idx_a, idx_b, counters + 3);
+    after_remove_kernel<<<1, 1, 0, st>>>(counters);
+}
+
+// final BC pass with the un-extended box, particle_module.f90:1959-1970
+__global__ void final_bc_kernel(const __grid_constant__ DevParams prm, PtlSoA P, const long long* n,
+                                double* leak)
+{
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= *n) return;
+    int flag = P.count_flag[i];
+    double x = P.x[i], y = P.y[i], z = P.z[i], w = P.weight[i];
+    if (P.p[i] < 0.0 && flag != GPAT_COUNT_FLAG_INBOX) {
+        flag = GPAT_COUNT_FLAG_OTHERS;
+        atomicAdd(leak + 1, w);
+    } else {
+        if (x < prm.xmin && flag == GPAT_COUNT_FLAG_INBOX) {
+            if (prm.pbc[0]) { atomicAdd(leak, w); flag = GPAT_COUNT_FLAG_ESCAPE_LX; }
+            else x = x - prm.xmin + prm.xmax;
+        } else if (x > prm.xmax && flag == GPAT_COUNT_FLAG_INBOX) {
+            if (prm.pbc[0]) { atomicAdd(leak, w); flag = GPAT_COUNT_FLAG_ESCAPE_HX; }
+            else x = x - prm.xmax + prm.xmin;
+        }
+        if (y < prm.ymin && flag == GPAT_COUNT_FLAG_INBOX) {
+            if (prm.pbc[1]) { atomicAdd(leak, w); flag = GPAT_COUNT_FLAG_ESCAPE_LY; }
+            else y = y - prm.ymin + prm.ymax;
+        } else if (y > prm.ymax && flag == GPAT_COUNT_FLAG_INBOX) {
+            if (prm.pbc[1]) { atomicAdd(leak, w); flag = GPAT_COUNT_FLAG_ESCAPE_HY; }
+            else y = y - prm.ymax + prm.ymin;
+        }
+        if (prm.ndim == 3 || prm.include_3rd_dim) {
+            if (z < prm.zmin && flag == GPAT_COUNT_FLAG_INBOX) {
+                if (prm.pbc[2]) { atomicAdd(leak, w); flag = GPAT_COUNT_FLAG_ESCAPE_LZ; }
+                else z = z - prm.zmin + prm.zmax;
+            } else if (z > prm.zmax && flag == GPAT_COUNT_FLAG_INBOX) {
+                if (prm.pbc[2]) { atomicAdd(leak, w); flag = GPAT_COUNT_FLAG_ESCAPE_HZ; }
+                else z = z - prm.zmax + prm.zmin;
+            }
+        }
+    }
+    P.x[i] = x; P.y[i] = y; P.z[i] = z;
+    P.count_flag[i] = (signed char)flag;
+}
+
+void launch_final_bc(const DevParams& prm, const PtlSoA& P, long long nmax, const long long* n_dev,
+                     double* leak, cudaStream_t st)
+{
+    if (nmax <= 0) return;
+    final_bc_kernel<<<(unsigned)((nmax + 255) / 256), 256, 0, st>>>(prm, P, n_dev, leak);
+}
+
+// ---- split_particle ----------------------------------------------------------------------
+__global__ void split_apply_kernel(PtlSoA P, const long long* idx, long long* counters, long long n,
+                                   long long nptl_max)
+{
+    long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    long long total = counters[6];
+    long long room = nptl_max - n;  // the serial loop stops at the first child that does not fit
+    long long nsplit = total < room ? total : room;
+    if (k >= nsplit) return;
+    long long i = idx[k];
+    long long child = n + k;
+    int st = P.split_times[i];
+    // particle_module.f90:5449: 0.5**(1.0 + split_times) in default real -- exact power of two
+    double wgt = (double)exp2f(-(1.0f + (float)st));
+    P.weight[i] = wgt;
+    P.split_times[i] = (signed char)(st + 1);
+    copy_particle(P, child, P, i);
+    P.tag_splitted[child] = P.tag_splitted[i] + (1 << st);  // 2**(split_times_new - 1)
+}
+
+__global__ void after_split_kernel(long long* c, long long n, long long nptl_max, long long* nptl_split)
+{
+    long long total = c[6];
+    long long room = nptl_max - n;
+    long long nsplit = total < room ? total : room;
+    // overflow: nptl_current = nptl_max (particle_module.f90:5444-5447)
+    c[0] = (total > room) ? nptl_max : n + nsplit;
+    *nptl_split += nsplit;
+}
+
+void launch_split(const DevParams& prm, const PtlSoA& P, long long n, long long nptl_max,
+                  double split_ratio, double pmin_split, long long* counters, long long* nptl_split,
+                  const ScanWork& w, long long* idx_a, cudaStream_t st)
+{
+    if (n <= 0) return;
+    PredArgs a{P.count_flag, P.split_times, P.p, counters + 2, pmin_split * prm.p0, split_ratio, prm.pmax};
+    select_indices<PRED_SPLIT>(a, n, w, idx_a, counters + 6, st);
+    split_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, idx_a, counters, n, nptl_max);
+    after_split_kernel<<<1, 1, 0, st>>>(counters, n, nptl_max, nptl_split);
+}
+
+// ---- AoS <-> SoA ----------------------------------------------------------------------------
+__global__ void to_aos_kernel(PtlSoA P, gpat_particle* out, long long n)
+{
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    gpat_particle q;
+    q.split_times = P.split_times[i]; q.count_flag = P.count_flag[i]; q.pad_[0] = q.pad_[1] = 0;
+    q.origin = P.origin[i]; q.nsteps_tracked = P.nsteps_tracked[i];
+    q.nsteps_pushed = P.nsteps_pushed[i]; q.tag_injected = P.tag_injected[i];
+    q.tag_splitted = P.tag_splitted[i];
+    q.x = P.x[i]; q.y = P.y[i]; q.z = P.z[i]; q.p = P.p[i]; q.v = P.v[i]; q.mu = P.mu[i];
+    q.weight = P.weight[i]; q.t = P.t[i]; q.dt = P.dt[i];
+    q.padding = __longlong_as_double((long long)P.rng[i]);
+    out[i] = q;
+}
+
+__global__ void from_aos_kernel(PtlSoA P, const gpat_particle* in, long long n)
+{
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    gpat_particle q = in[i];
+    P.split_times[i] = q.split_times; P.count_flag[i] = q.count_flag;
+    P.origin[i] = q.origin; P.nsteps_tracked[i] = q.nsteps_tracked;
+    P.nsteps_pushed[i] = q.nsteps_pushed; P.tag_injected[i] = q.tag_injected;
+    P.tag_splitted[i] = q.tag_splitted;
+    P.x[i] = q.x; P.y[i] = q.y; P.z[i] = q.z; P.p[i] = q.p; P.v[i] = q.v; P.mu[i] = q.mu;
+    P.weight[i] = q.weight; P.t[i] = q.t; P.dt[i] = q.dt;
+    P.rng[i] = (unsigned long long)__double_as_longlong(q.padding);
+}
+
+void launch_to_aos(const PtlSoA& P, gpat_particle* out, long long n, cudaStream_t st)
+{
+    if (n > 0) to_aos_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, out, n);
+}
+void launch_from_aos(const PtlSoA& P, const gpat_particle* in, long long n, cudaStream_t st)
+{
+    if (n > 0) from_aos_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, in, n);
+}
+
+}  // namespace gpat

@@ -1,0 +1,723 @@
+// push.cu -- the pseudo-particle SDE push (the hot path).
+//
+// One launch moves every particle through one MHD interval: it replaces the particle loop
+// of particle_mover_one_cycle (particle_module.f90:1560-1831) with get_interp_paramters
+// (particle_module.f90:642-674), interp_fields (mhd_data_parallel.f90:1751-1793),
+// calc_spatial_diffusion_coefficients[_nlgc] (particle_module.f90:2208-2771),
+// push_particle_2d / _2d_include_3rd / _3d (particle_module.f90:3358-3606, 3979-4245,
+// 4625-4907), particle_boundary_condition (particle_module.f90:1984-2129) and unif_01
+// (random_number_generator.f90:97-101 -> Philox4x32-10 per particle) fused.
+//
+// Execution model: persistent grid, one lane per particle, lanes refill from a global
+// work counter with a warp-aggregated atomic when their particle reaches the end of the
+// interval.  The reference's nested while loops are flattened into a per-lane state
+// machine so that every loop iteration of a warp executes the expensive body (gather +
+// kappa + step) exactly once, converged, whatever the per-particle step counts are.
+//
+// This translation unit is compiled twice:
+//   GPAT_STRICT=1, -fmad=false : reference operation order, no contraction (parity build)
+//   GPAT_STRICT=0              : FMA contraction, time-blend folded into the weights
+#include "gpat_internal.cuh"
+
+#ifndef GPAT_STRICT
+#define GPAT_STRICT 0
+#endif
+
+namespace gpat {
+namespace {
+
+constexpr double kEps = 2.220446049250313e-16;  // EPSILON(1.0d0)
+constexpr int kBlock = 128;
+
+__device__ __forceinline__ double sq(double v) { return v * v; }
+__device__ __forceinline__ double min2(double a, double b) { return (b < a) ? b : a; }
+
+// ---- Philox4x32-10 (Salmon et al. 2011) -------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, unsigned k0, unsigned k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+
+__device__ __forceinline__ double u01(unsigned w)
+{
+#if GPAT_STRICT
+    return (double)w / 4294967295.0;
+#else
+    return (double)w * (1.0 / 4294967295.0);
+#endif
+}
+
+// ---- per-lane particle state ---------------------------------------------------------
+struct Lane {
+    double x, y, z, p, t, dt, weight, mu;
+    double dxl, dyl, dzl, dpl;  // last step's deltas (roll-back, particle_module.f90:1708-1714)
+    double dt_target, dt_old;
+    unsigned long long rng;
+    int tag_inj, tag_spl, origin;
+    int nsteps_pushed;
+    int count_flag;
+};
+
+// particle_boundary_condition for a single rank (neighbours are self or -1)
+__device__ __forceinline__ void boundary(const DevParams& prm, Lane& q, const double* e,
+                                         double* leak)
+{
+    if (q.x < e[0] && q.count_flag == GPAT_COUNT_FLAG_INBOX) {
+        if (prm.pbc[0]) { atomicAdd(leak, q.weight); q.count_flag = GPAT_COUNT_FLAG_ESCAPE_LX; }
+        else q.x = q.x - e[0] + e[1];
+    } else if (q.x > e[1] && q.count_flag == GPAT_COUNT_FLAG_INBOX) {
+        if (prm.pbc[0]) { atomicAdd(leak, q.weight); q.count_flag = GPAT_COUNT_FLAG_ESCAPE_HX; }
+        else q.x = q.x - e[1] + e[0];
+    }
+    if (q.y < e[2] && q.count_flag == GPAT_COUNT_FLAG_INBOX) {
+        if (prm.pbc[1]) { atomicAdd(leak, q.weight); q.count_flag = GPAT_COUNT_FLAG_ESCAPE_LY; }
+        else q.y = q.y - e[2] + e[3];
+    } else if (q.y > e[3] && q.count_flag == GPAT_COUNT_FLAG_INBOX) {
+        if (prm.pbc[1]) { atomicAdd(leak, q.weight); q.count_flag = GPAT_COUNT_FLAG_ESCAPE_HY; }
+        else q.y = q.y - e[3] + e[2];
+    }
+    if (prm.ndim == 3 || prm.include_3rd_dim) {
+        if (q.z < e[4] && q.count_flag == GPAT_COUNT_FLAG_INBOX) {
+            if (prm.pbc[2]) { atomicAdd(leak, q.weight); q.count_flag = GPAT_COUNT_FLAG_ESCAPE_LZ; }
+            else q.z = q.z - e[4] + e[5];
+        } else if (q.z > e[5] && q.count_flag == GPAT_COUNT_FLAG_INBOX) {
+            if (prm.pbc[2]) { atomicAdd(leak, q.weight); q.count_flag = GPAT_COUNT_FLAG_ESCAPE_HZ; }
+            else q.z = q.z - e[5] + e[4];
+        }
+    }
+}
+
+// particle_module.f90:1602-1609
+__device__ __forceinline__ void negp_or_bc(const DevParams& prm, Lane& q, double* leak)
+{
+    if (q.p < 0.0) {
+        q.count_flag = GPAT_COUNT_FLAG_OTHERS;
+        atomicAdd(leak + 1, q.weight);
+    } else {
+        boundary(prm, q, prm.ext, leak);
+    }
+}
+
+// ---- gather: get_interp_paramters + interp_fields -------------------------------------
+template <int L>
+__device__ __forceinline__ void gather(const DevParams& prm, const float* __restrict__ fld,
+                                       int sel, double x, double y, double z, double rt,
+                                       double (&F)[Rec<L>::NREC])
+{
+    constexpr int NREC = Rec<L>::NREC;
+    constexpr int NQ = (Rec<L>::NUSED + 3) / 4;
+    constexpr int NC = (Rec<L>::NDIM == 3) ? 8 : 4;
+    const int nfr = prm.time_interp ? 2 : 1;
+    const long long stride = (long long)NREC * nfr;  // floats per grid point
+
+    double px = (x - prm.xmin) / prm.dx;
+    double py = (y - prm.ymin) / prm.dy;
+    int ix = (int)floor(px) + 1;  // Fortran pos(1)
+    int iy = (int)floor(py) + 1;
+    double rx = px - (double)ix + 1.0;
+    double ry = py - (double)iy + 1.0;
+    double rx1 = 1.0 - rx, ry1 = 1.0 - ry;
+    // Fortran index -> storage index is +1; clamp so a runaway particle cannot fault
+    int cx = min(max(ix + 1, 0), prm.nxg - 2);
+    int cy = min(max(iy + 1, 0), prm.nyg - 2);
+    long long cell = (long long)cy * prm.nxg + cx;
+    double w[NC];
+    long long off[NC];
+    if (NC == 4) {
+        w[0] = rx1 * ry1; w[1] = rx * ry1; w[2] = rx1 * ry; w[3] = rx * ry;
+    } else {
+        double pz = (z - prm.zmin) / prm.dz;
+        int iz = (int)floor(pz) + 1;
+        double rz = pz - (double)iz + 1.0;
+        double rz1 = 1.0 - rz;
+        int cz = min(max(iz + 1, 0), prm.nzg - 2);
+        cell += (long long)cz * prm.nxg * prm.nyg;
+        w[0] = rx1 * ry1 * rz1; w[1] = rx * ry1 * rz1; w[2] = rx1 * ry * rz1; w[3] = rx * ry * rz1;
+        w[4] = rx1 * ry1 * rz;  w[5] = rx * ry1 * rz;  w[6] = rx1 * ry * rz;  w[7] = rx * ry * rz;
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+        off[c] = (cell + (c & 1) + (long long)((c >> 1) & 1) * prm.nxg +
+                  (long long)(c >> 2) * prm.nxg * prm.nyg) * stride;
+    const int hA = (prm.time_interp ? sel : 0) * NREC;
+    const int hB = (sel ^ 1) * NREC;
+
+#if GPAT_STRICT
+    // reference order: per frame, sum over corners starting from 0, then blend
+    const double rt1 = 1.0 - rt;
+#pragma unroll
+    for (int qd = 0; qd < NQ; ++qd) {
+        double a[4] = {0.0, 0.0, 0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            float4 fa = __ldg(reinterpret_cast<const float4*>(fld + off[c] + hA) + qd);
+            a[0] = a[0] + (double)fa.x * w[c]; a[1] = a[1] + (double)fa.y * w[c];
+            a[2] = a[2] + (double)fa.z * w[c]; a[3] = a[3] + (double)fa.w * w[c];
+            if (prm.time_interp) {
+                float4 fb = __ldg(reinterpret_cast<const float4*>(fld + off[c] + hB) + qd);
+                b[0] = b[0] + (double)fb.x * w[c]; b[1] = b[1] + (double)fb.y * w[c];
+                b[2] = b[2] + (double)fb.z * w[c]; b[3] = b[3] + (double)fb.w * w[c];
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            F[4 * qd + e] = prm.time_interp ? (a[e] * rt1 + b[e] * rt) : a[e];
+    }
+#else
+    // fast: fold the time blend into the corner weights, one FMA per loaded value
+    double wa[NC], wb[NC];
+    const double rt1 = 1.0 - rt;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        wa[c] = prm.time_interp ? w[c] * rt1 : w[c];
+        wb[c] = w[c] * rt;
+    }
+#pragma unroll
+    for (int qd = 0; qd < NQ; ++qd) {
+        double a[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            float4 fa = __ldg(reinterpret_cast<const float4*>(fld + off[c] + hA) + qd);
+            a[0] = fma((double)fa.x, wa[c], a[0]); a[1] = fma((double)fa.y, wa[c], a[1]);
+            a[2] = fma((double)fa.z, wa[c], a[2]); a[3] = fma((double)fa.w, wa[c], a[3]);
+            if (prm.time_interp) {
+                float4 fb = __ldg(reinterpret_cast<const float4*>(fld + off[c] + hB) + qd);
+                a[0] = fma((double)fb.x, wb[c], a[0]); a[1] = fma((double)fb.y, wb[c], a[1]);
+                a[2] = fma((double)fb.z, wb[c], a[2]); a[3] = fma((double)fb.w, wb[c], a[3]);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) F[4 * qd + e] = a[e];
+    }
+#endif
+}
+
+// ---- kappa (particle_module.f90:93-104) --------------------------------------------
+struct Kappa {
+    double knorm_para, kpara, kperp, skpara, skperp, skpara_perp;
+    double dkxx_dx, dkyy_dy, dkzz_dz, dkxy_dx, dkxy_dy, dkxz_dx, dkxz_dz, dkyz_dy, dkyz_dz;
+};
+
+struct BField {  // B and its gradients at the particle
+    double bx, by, bz, b;
+    double dbx_dx, dbx_dy, dbx_dz, dby_dx, dby_dy, dby_dz, dbz_dx, dbz_dy, dbz_dz;
+    double db_dx, db_dy, db_dz;
+};
+
+// THREE: z-components needed (3-D or 2-D with include_3rd_dim); FULL3D: ndim == 3
+template <bool THREE, bool FULL3D>
+__device__ __forceinline__ void calc_kappa(const DevParams& prm, const BField& B, double p,
+                                           double mu, Kappa& k)
+{
+    const double bx = B.bx, by = B.by, bz = B.bz, b = B.b;
+    const double ib1 = (b < kEps) ? 1.0 : 1.0 / b;  // particle_module.f90:2230-2234
+    const double ib2 = ib1 * ib1;
+    const double ib3 = ib1 * ib2;
+    double knp = 1.0, knperp = 1.0;
+    if (prm.mag_dependency == 1) {
+        knp = knp * pow(b, prm.gm2);
+        if (prm.nlgc) knperp = knperp * pow(b, prm.gm2_3);
+    }
+    k.knorm_para = knp;
+    double ax = 0.0, ay = 0.0, az = 0.0;  // coefficients multiplying the b_i b_j terms
+    if (!prm.nlgc) {
+        double knorm = (prm.momentum_dependency == 1) ? knp * pow(p / prm.p0, prm.pindex) : knp;
+        k.kpara = prm.kpara0 * knorm;
+        k.kperp = k.kpara * prm.kret;
+    } else {
+        double kn_para = knp, kn_perp = knperp;
+        if (prm.momentum_dependency == 1) {
+            kn_para = knp * pow(p / prm.p0, prm.pindex);
+            kn_perp = knperp * pow(p / prm.p0, prm.pidx_perp);
+        }
+        k.kpara = prm.kpara0 * kn_para;
+        k.kperp = prm.kpara0 * prm.kperp_kpara * kn_perp * sq(mu);
+    }
+    k.skpara = sqrt(2.0 * k.kpara);
+    k.skperp = sqrt(2.0 * k.kperp);
+    k.skpara_perp = sqrt(2.0 * (k.kpara - k.kperp));
+    const double kpp = k.kpara - k.kperp;
+    double px_, py_, pz_ = 0.0;  // the "kperp*dkdx" leading terms
+    if (!prm.nlgc) {
+        double dkdx = 0.0, dkdy = 0.0, dkdz = 0.0;
+        if (prm.mag_dependency == 1) {
+            if (FULL3D) {  // particle_module.f90:2405-2409: no 1/B in 3-D
+                dkdx = B.db_dx * prm.gm2; dkdy = B.db_dy * prm.gm2; dkdz = B.db_dz * prm.gm2;
+            } else {
+                dkdx = B.db_dx * ib1 * prm.gm2; dkdy = B.db_dy * ib1 * prm.gm2;
+            }
+        }
+        px_ = k.kperp * dkdx; py_ = k.kperp * dkdy; pz_ = k.kperp * dkdz;
+        ax = kpp * dkdx; ay = kpp * dkdy; az = kpp * dkdz;
+    } else {
+        double dpa_x = 0.0, dpa_y = 0.0, dpa_z = 0.0, dpe_x = 0.0, dpe_y = 0.0, dpe_z = 0.0;
+        if (prm.mag_dependency == 1) {
+            dpa_x = B.db_dx * ib1 * prm.gm2; dpa_y = B.db_dy * ib1 * prm.gm2;
+            dpe_x = B.db_dx * ib1 * prm.gm2 / 3.0; dpe_y = B.db_dy * ib1 * prm.gm2 / 3.0;
+            if (FULL3D) { dpa_z = B.db_dz * ib1 * prm.gm2; dpe_z = B.db_dz * ib1 * prm.gm2 / 3.0; }
+        }
+        px_ = k.kperp * dpe_x; py_ = k.kperp * dpe_y; pz_ = k.kperp * dpe_z;
+        ax = k.kpara * dpa_x - k.kperp * dpe_x;
+        ay = k.kpara * dpa_y - k.kperp * dpe_y;
+        az = k.kpara * dpa_z - k.kperp * dpe_z;
+    }
+    k.dkxx_dx = px_ + ax * sq(bx) * ib2 + 2.0 * kpp * bx * (B.dbx_dx * b - bx * B.db_dx) * ib3;
+    k.dkyy_dy = py_ + ay * sq(by) * ib2 + 2.0 * kpp * by * (B.dby_dy * b - by * B.db_dy) * ib3;
+    k.dkxy_dx = ax * bx * by * ib2 +
+                kpp * ((B.dbx_dx * by + bx * B.dby_dx) * ib2 - 2.0 * bx * by * B.db_dx * ib3);
+    k.dkxy_dy = ay * bx * by * ib2 +
+                kpp * ((B.dbx_dy * by + bx * B.dby_dy) * ib2 - 2.0 * bx * by * B.db_dy * ib3);
+    if (THREE) {
+        k.dkzz_dz = pz_ + az * sq(bz) * ib2 + 2.0 * kpp * bz * (B.dbz_dz * b - bz * B.db_dz) * ib3;
+        k.dkxz_dx = ax * bx * bz * ib2 +
+                    kpp * ((B.dbx_dx * bz + bx * B.dbz_dx) * ib2 - 2.0 * bx * bz * B.db_dx * ib3);
+        k.dkxz_dz = az * bx * bz * ib2 +
+                    kpp * ((B.dbx_dz * bz + bx * B.dbz_dz) * ib2 - 2.0 * bx * bz * B.db_dz * ib3);
+        k.dkyz_dy = ay * by * bz * ib2 +
+                    kpp * ((B.dby_dy * bz + by * B.dbz_dy) * ib2 - 2.0 * by * bz * B.db_dy * ib3);
+        k.dkyz_dz = az * by * bz * ib2 +
+                    kpp * ((B.dby_dz * bz + by * B.dbz_dz) * ib2 - 2.0 * by * bz * B.db_dz * ib3);
+    } else {
+        k.dkzz_dz = k.dkxz_dx = k.dkxz_dz = k.dkyz_dy = k.dkyz_dz = 0.0;
+    }
+}
+
+// velocity gradients needed by D_pp
+struct VGrad { double dvx_dx, dvy_dy, dvz_dz, dvx_dy, dvx_dz, dvy_dx, dvy_dz, dvz_dx, dvz_dy; };
+
+// calc_dpp_wave_scattering + calc_dpp_flow_shear (particle_module.f90:2918-2979)
+__device__ __forceinline__ void momentum_diffusion(const DevParams& prm, const BField& B,
+                                                   const VGrad& V, double rho, double divv,
+                                                   const Kappa& k, double p, double& dp_dt,
+                                                   double& dpp)
+{
+    if (prm.dpp_wave) {
+        double va = B.b / sqrt(rho);
+        if (prm.momentum_dependency == 1) dp_dt = dp_dt + (8.0 * p / (27.0 * k.kpara)) * sq(va);
+        else dp_dt = dp_dt + (4.0 * p / (9.0 * k.kpara)) * sq(va);
+        dpp = dpp + sq(p * va) / (9.0 * k.kpara);
+    }
+    if (prm.dpp_shear) {
+        double sxx = V.dvx_dx - divv / 3.0, syy = V.dvy_dy - divv / 3.0, szz = V.dvz_dz - divv / 3.0;
+        double sxy = (V.dvx_dy + V.dvy_dx) / 2.0;
+        double sxz = (V.dvx_dz + V.dvz_dx) / 2.0;
+        double syz = (V.dvy_dz + V.dvz_dy) / 2.0;
+        double gshear;
+        if (prm.weak_scattering) {
+            double ib = (B.b < kEps) ? 0.0 : 1.0 / B.b;
+            double bbs = sxx * sq(B.bx) + syy * sq(B.by) + szz * sq(B.bz) +
+                         2.0 * (sxy * B.bx * B.by + sxz * B.bx * B.bz + syz * B.by * B.bz);
+            bbs = bbs * ib * ib;
+            gshear = sq(bbs) / 5.0;
+        } else {
+            gshear = 2.0 * (sq(sxx) + sq(syy) + sq(szz) + 2.0 * (sq(sxy) + sq(sxz) + sq(syz))) / 15.0;
+        }
+        if (gshear > 0.0) {
+            dp_dt = dp_dt + (2.0 + prm.pindex) * gshear * prm.tau0 * k.knorm_para *
+                                pow(p, prm.pindex - 1.0) * prm.p0_pow;
+            dpp = dpp + gshear * prm.tau0 * k.knorm_para * pow(p, prm.pindex) * prm.p0_pow;
+        }
+    }
+}
+
+__device__ __forceinline__ bool in_acc_region(const DevParams& prm, const Lane& q)
+{
+    double xn = (q.x - prm.xmin) / prm.lx;
+    bool in = (xn >= prm.acc_region[0]) && (xn <= prm.acc_region[1]);
+    double yn = (q.y - prm.ymin) / prm.ly;
+    in = in && (yn >= prm.acc_region[2]) && (yn <= prm.acc_region[3]);
+    if (prm.ndim == 3) {
+        double zn = (q.z - prm.zmin) / prm.lz;
+        in = in && (zn >= prm.acc_region[4]) && (zn <= prm.acc_region[5]);
+    }
+    return in;
+}
+
+// One call of push_particle_*: everything between the BC test and the step counter.
+template <int L>
+__device__ __forceinline__ void push_once(const DevParams& prm, const PushArgs& a,
+                                          const float* __restrict__ fld, Lane& q, bool fixed_dt)
+{
+    constexpr bool D3 = (Rec<L>::NDIM == 3);
+    constexpr bool EXT = Rec<L>::EXT;
+    double F[Rec<L>::NREC];
+    const double rt = (q.t - a.t0) / a.dtf;
+    gather<L>(prm, fld, a.sel, q.x, q.y, q.z, rt, F);
+
+    // uniforms of this step: ran1, ran2, ran3, ran_p
+    double u0, u1, u2, u3;
+    if (prm.rng_mode == GPAT_RNG_TABLE) {
+        long long slot = q.tag_inj;
+        if (a.rng_table && slot >= 0 && slot < a.rng_slots && (long long)q.rng < a.rng_max_steps) {
+            const double* tb = a.rng_table + ((size_t)slot * a.rng_max_steps + q.rng) * 4;
+            u0 = tb[0]; u1 = tb[1]; u2 = tb[2]; u3 = tb[3];
+        } else {
+            u0 = u1 = u2 = u3 = 0.5;
+        }
+    } else {
+        uint4 r = philox4x32_10(make_uint4((unsigned)q.rng, (unsigned)(q.rng >> 32),
+                                           (unsigned)q.tag_inj, (unsigned)q.tag_spl),
+                                prm.key0, prm.key1 + (unsigned)q.origin);
+        u0 = u01(r.x); u1 = u01(r.y); u2 = u01(r.z); u3 = u01(r.w);
+    }
+    q.rng += 1;
+
+    BField B;
+    VGrad V;
+    double vx, vy, vz = 0.0, rho = 1.0;
+    if constexpr (!D3) {
+        vx = F[s2::vx]; vy = F[s2::vy];
+        B.bx = F[s2::bx]; B.by = F[s2::by]; B.bz = F[s2::bz];
+        B.dbx_dx = F[s2::dbx_dx]; B.dbx_dy = F[s2::dbx_dy]; B.dby_dx = F[s2::dby_dx];
+        B.dby_dy = F[s2::dby_dy]; B.dbz_dx = F[s2::dbz_dx]; B.dbz_dy = F[s2::dbz_dy];
+        B.db_dx = F[s2::db_dx]; B.db_dy = F[s2::db_dy];
+        B.dbx_dz = B.dby_dz = B.dbz_dz = B.db_dz = 0.0;
+        V.dvx_dx = F[s2::dvx_dx]; V.dvy_dy = F[s2::dvy_dy]; V.dvz_dz = 0.0;
+        V.dvx_dz = V.dvy_dz = 0.0;
+        if constexpr (EXT) {
+            vz = F[s2::vz]; rho = F[s2::rho];
+            V.dvx_dy = F[s2::dvx_dy]; V.dvy_dx = F[s2::dvy_dx];
+            V.dvz_dx = F[s2::dvz_dx]; V.dvz_dy = F[s2::dvz_dy];
+        } else {
+            V.dvx_dy = V.dvy_dx = V.dvz_dx = V.dvz_dy = 0.0;
+        }
+    } else {
+        vx = F[s3::vx]; vy = F[s3::vy]; vz = F[s3::vz];
+        B.bx = F[s3::bx]; B.by = F[s3::by]; B.bz = F[s3::bz];
+        B.dbx_dx = F[s3::dbx_dx]; B.dbx_dy = F[s3::dbx_dy]; B.dbx_dz = F[s3::dbx_dz];
+        B.dby_dx = F[s3::dby_dx]; B.dby_dy = F[s3::dby_dy]; B.dby_dz = F[s3::dby_dz];
+        B.dbz_dx = F[s3::dbz_dx]; B.dbz_dy = F[s3::dbz_dy]; B.dbz_dz = F[s3::dbz_dz];
+        B.db_dx = F[s3::db_dx]; B.db_dy = F[s3::db_dy]; B.db_dz = F[s3::db_dz];
+        V.dvx_dx = F[s3::dvx_dx]; V.dvy_dy = F[s3::dvy_dy]; V.dvz_dz = F[s3::dvz_dz];
+        if constexpr (EXT) {
+            rho = F[s3::rho];
+            V.dvx_dy = F[s3::dvx_dy]; V.dvx_dz = F[s3::dvx_dz]; V.dvy_dx = F[s3::dvy_dx];
+            V.dvy_dz = F[s3::dvy_dz]; V.dvz_dx = F[s3::dvz_dx]; V.dvz_dy = F[s3::dvz_dy];
+        } else {
+            V.dvx_dy = V.dvx_dz = V.dvy_dx = V.dvy_dz = V.dvz_dx = V.dvz_dy = 0.0;
+        }
+    }
+    B.b = sqrt(sq(B.bx) + sq(B.by) + sq(B.bz));
+    const bool third = D3 || (EXT && prm.include_3rd_dim);  // push_particle_3d-like path
+
+    Kappa k;
+    if (D3) calc_kappa<true, true>(prm, B, q.p, q.mu, k);
+    else if (EXT && prm.include_3rd_dim) calc_kappa<true, false>(prm, B, q.p, q.mu, k);
+    else calc_kappa<false, false>(prm, B, q.p, q.mu, k);
+
+    const double ib = (B.b < kEps) ? 0.0 : 1.0 / B.b;  // particle_module.f90:3414-3418
+    const double ib2 = ib * ib;
+    const double ib3 = ib * ib2;
+    // particle_module.f90:3436: 1.0/(3*pcharge) is an FP32 quotient
+    const double vdp = prm.qdrift / sqrt(sq(prm.drift1 * prm.p0 / q.p) +
+                                         sq(prm.drift2 * sq(prm.p0) / sq(q.p)));
+    double vdx, vdy, vdz;
+    if (!third) {
+        vdx = vdp * (B.dbz_dy * ib2 - 2.0 * B.bz * B.db_dy * ib3);
+        vdy = vdp * (-B.dbz_dx * ib2 + 2.0 * B.bz * B.db_dx * ib3);
+        vdz = prm.check_drift_2d
+                  ? vdp * ((B.dby_dx - B.dbx_dy) * ib2 - 2.0 * (B.by * B.db_dx - B.bx * B.db_dy) * ib3)
+                  : 0.0;
+    } else {
+        vdx = vdp * ((B.dbz_dy - B.dby_dz) * ib2 - 2.0 * (B.bz * B.db_dy - B.by * B.db_dz) * ib3);
+        vdy = vdp * ((B.dbx_dz - B.dbz_dx) * ib2 - 2.0 * (B.bx * B.db_dz - B.bz * B.db_dx) * ib3);
+        vdz = vdp * ((B.dby_dx - B.dbx_dy) * ib2 - 2.0 * (B.by * B.db_dx - B.bx * B.db_dy) * ib3);
+    }
+    double dx_dt, dy_dt, dz_dt, divv;
+    if (!third) {
+        dx_dt = vx + vdx + k.dkxx_dx + k.dkxy_dy;
+        dy_dt = vy + vdy + k.dkxy_dx + k.dkyy_dy;
+        dz_dt = vdz;
+        divv = V.dvx_dx + V.dvy_dy;
+    } else {
+        if (!D3) { k.dkxz_dz = 0.0; k.dkyz_dz = 0.0; k.dkzz_dz = 0.0; }  // particle_module.f90:4094-4096
+        dx_dt = vx + vdx + k.dkxx_dx + k.dkxy_dy + k.dkxz_dz;
+        dy_dt = vy + vdy + k.dkxy_dx + k.dkyy_dy + k.dkyz_dz;
+        dz_dt = vz + vdz + k.dkxz_dx + k.dkyz_dy + k.dkzz_dz;
+        divv = V.dvx_dx + V.dvy_dy + V.dvz_dz;
+    }
+    double dp_dt = -q.p * divv / 3.0;
+    double dpp = 0.0;
+    if (EXT) {
+        if (!third) { V.dvz_dx = 0.0; V.dvz_dy = 0.0; }  // push_particle_2d: sigma_xz = sigma_yz = 0
+        momentum_diffusion(prm, B, V, rho, divv, k, q.p, dp_dt, dpp);
+    }
+
+    if (!fixed_dt) {
+        double d;
+        if (dx_dt != 0.0 && dy_dt != 0.0 && dp_dt != 0.0) {
+            const double s = (k.skperp > 0.0) ? k.skperp : k.skpara;
+            d = sq(0.5 * prm.dx / k.skpara);
+            d = min2(d, sq(0.5 * prm.dy / k.skpara));
+            if (D3) d = min2(d, sq(0.5 * prm.dz / k.skpara));
+            d = min2(d, sq(s / dx_dt));
+            d = min2(d, sq(s / dy_dt));
+            if (D3) d = min2(d, sq(s / dz_dt));
+            d = min2(d, (double)0.1f * q.p / fabs(dp_dt));
+        } else {
+            d = a.dt_min;
+        }
+        if (d < a.dt_min) d = a.dt_min;
+        if (d > a.dt_max) d = a.dt_max;
+        q.dt = d;
+    }
+    const double sdt = sqrt(q.dt);
+    const double sqrt3 = 1.7320508075688772;  // dsqrt(3.0d0), correctly rounded
+    const double ran1 = (2.0 * u0 - 1.0) * sqrt3;
+    const double ran2 = (2.0 * u1 - 1.0) * sqrt3;
+    const double ran3 = (2.0 * u2 - 1.0) * sqrt3;
+    double ddx, ddy, ddz;
+    if (!third) {
+        ddx = dx_dt * q.dt + ran1 * k.skperp * sdt + ran3 * k.skpara_perp * sdt * B.bx * ib;
+        ddy = dy_dt * q.dt + ran2 * k.skperp * sdt + ran3 * k.skpara_perp * sdt * B.by * ib;
+        ddz = dz_dt * q.dt;
+        q.dzl = 0.0;  // the mover's own deltaz stays 0 in plain 2-D (particle_module.f90:1564)
+    } else {
+        const double bxn = B.bx * ib, byn = B.by * ib, bzn = B.bz * ib;
+        const double bxyn = sqrt(sq(bxn) + sq(byn));
+        const double ibxyn = (bxyn < kEps) ? 0.0 : 1.0 / bxyn;
+        ddx = dx_dt * q.dt + (bxn * k.skpara * ran1 - bxn * bzn * k.skperp * ibxyn * ran2 -
+                              byn * k.skperp * ibxyn * ran3) * sdt;
+        ddy = dy_dt * q.dt + (byn * k.skpara * ran1 - byn * bzn * k.skperp * ibxyn * ran2 +
+                              bxn * k.skperp * ibxyn * ran3) * sdt;
+        ddz = dz_dt * q.dt + (bzn * k.skpara * ran1 + bxyn * k.skperp * ran2) * sdt;
+        q.dzl = ddz;
+    }
+    q.x = q.x + ddx;
+    q.y = q.y + ddy;
+    q.z = q.z + ddz;
+    q.t = q.t + q.dt;
+    q.dxl = ddx;
+    q.dyl = ddy;
+
+    const double ranp = (2.0 * u3 - 1.0) * sqrt3;
+    double ddp = dp_dt * q.dt + ranp * sqrt(2.0 * dpp) * sdt;
+    if (prm.acc_region_flag == 1) {
+        if (in_acc_region(prm, q)) q.p = q.p + ddp;
+        else ddp = 0.0;
+    } else {
+        q.p = q.p + ddp;
+    }
+    const double pfloor = 0.25 * prm.p0;
+    if (q.p < pfloor) {  // particle_module.f90:3601-3605
+        q.p = q.p - ddp;
+        ddp = pfloor - q.p;
+        q.p = pfloor;
+    }
+    q.dpl = ddp;
+}
+
+// ---- the kernel -------------------------------------------------------------------------
+enum : int { ST_IDLE = 0, ST_ADAPT = 1, ST_FIX = 2 };
+enum : int { AT_OUTER_HEAD = 0, AT_INNER_HEAD = 1, AFTER_FIXED_PUSH = 2 };
+
+// The reference's loop nest (particle_module.f90:1596-1829) as a resumable state machine:
+//   do while (dt_target < dtf + 0.1 dt_fine)            <- AT_OUTER_HEAD
+//     if (.not. inbox) exit
+//     do while (t - t0 < dt_target .and. inbox)          <- AT_INNER_HEAD
+//        [BC; adaptive push]                              -> returns ST_ADAPT
+//     if (t - t0 > dt_target .and. inbox) roll back, [fixed push] -> returns ST_FIX,
+//        then dt = dt_old; BC                             <- AFTER_FIXED_PUSH
+//     dt_target += dt_fine
+// Returns ST_IDLE when the particle is done for this interval.
+__device__ __forceinline__ int next_state(const DevParams& prm, const PushArgs& a, Lane& q,
+                                          int entry)
+{
+    for (;;) {
+        if (entry == AT_INNER_HEAD) {
+            const bool inbox = (q.count_flag == GPAT_COUNT_FLAG_INBOX);
+            if ((q.t - a.t0) < q.dt_target && inbox) return ST_ADAPT;
+            if ((q.t - a.t0) > q.dt_target && inbox) {  // particle_module.f90:1707-1716
+                q.x = q.x - q.dxl; q.y = q.y - q.dyl; q.z = q.z - q.dzl;
+                q.p = q.p - q.dpl;
+                q.t = q.t - q.dt;
+                q.dt_old = q.dt;
+                q.dt = a.t0 + q.dt_target - q.t;
+                if (q.dt > 0) {
+                    q.nsteps_pushed = q.nsteps_pushed - 1;  // particle_module.f90:1723
+                    return ST_FIX;
+                }
+                q.dt = q.dt_old;  // particle_module.f90:1816-1825
+                negp_or_bc(prm, q, a.leak);
+            }
+            q.dt_target = q.dt_target + a.dt_fine;
+        } else if (entry == AFTER_FIXED_PUSH) {
+            q.dt = q.dt_old;
+            negp_or_bc(prm, q, a.leak);
+            q.dt_target = q.dt_target + a.dt_fine;
+        }
+        if (!(q.dt_target < a.dt_target_limit) || q.count_flag != GPAT_COUNT_FLAG_INBOX)
+            return ST_IDLE;
+        entry = AT_INNER_HEAD;
+    }
+}
+
+template <int L>
+__global__ void __launch_bounds__(kBlock)
+push_kernel(const __grid_constant__ DevParams prm, const PtlSoA P, const float* __restrict__ fld,
+            const __grid_constant__ PushArgs a)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    Lane q;
+    int state = ST_IDLE;
+    long long idx = -1;
+    bool exhausted = false;
+    int remaining = 0;
+    unsigned long long nsteps = 0;
+
+    auto store = [&]() {
+        P.x[idx] = q.x; P.y[idx] = q.y; P.z[idx] = q.z; P.p[idx] = q.p;
+        P.t[idx] = q.t; P.dt[idx] = q.dt; P.rng[idx] = q.rng;
+        P.nsteps_pushed[idx] = q.nsteps_pushed;
+        P.count_flag[idx] = (signed char)q.count_flag;
+        if (a.debug_nsteps == 0) P.nsteps_tracked[idx] = 1;  // particle_module.f90:1913
+    };
+
+    for (;;) {
+        // ---- refill idle lanes from the work counter (warp-aggregated atomic) ----
+        __syncwarp();
+        const bool want = (state == ST_IDLE) && !exhausted;
+        const unsigned m = __ballot_sync(0xffffffffu, want);
+        if (m) {
+            unsigned long long base = 0;
+            const int leader = __ffs(m) - 1;
+            if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (want) {
+                idx = (long long)(base + __popc(m & ((1u << lane) - 1u)));
+                if (idx >= a.nptl) {
+                    exhausted = true;
+                } else {
+                    q.x = P.x[idx]; q.y = P.y[idx]; q.z = P.z[idx]; q.p = P.p[idx];
+                    q.t = P.t[idx]; q.dt = P.dt[idx]; q.weight = P.weight[idx]; q.mu = P.mu[idx];
+                    q.rng = P.rng[idx]; q.tag_inj = P.tag_injected[idx];
+                    q.tag_spl = P.tag_splitted[idx]; q.origin = P.origin[idx];
+                    q.nsteps_pushed = P.nsteps_pushed[idx]; q.count_flag = P.count_flag[idx];
+                    q.dxl = q.dyl = q.dzl = q.dpl = 0.0;
+                    q.dt_old = q.dt;
+                    if (a.debug_nsteps > 0) {
+                        remaining = a.debug_nsteps;
+                        q.dt_target = a.dtf;
+                        state = (q.count_flag == GPAT_COUNT_FLAG_INBOX) ? ST_ADAPT : ST_IDLE;
+                    } else {
+                        // target time of the first fine step, particle_module.f90:1570-1578
+                        int step = (int)ceil((q.t - a.t0) / a.dt_fine);
+                        q.dt_target = (step <= 0) ? a.dt_fine : step * a.dt_fine;
+                        if (q.dt_target > a.dtf) q.dt_target = a.dtf;
+                        // safe check, particle_module.f90:1581-1592
+                        if (q.p < 0.0 && q.count_flag == GPAT_COUNT_FLAG_INBOX) {
+                            q.count_flag = GPAT_COUNT_FLAG_OTHERS;
+                            atomicAdd(a.leak + 1, q.weight);
+                        } else {
+                            boundary(prm, q, prm.ext, a.leak);
+                        }
+                        state = (q.count_flag == GPAT_COUNT_FLAG_INBOX)
+                                    ? next_state(prm, a, q, AT_OUTER_HEAD)
+                                    : ST_IDLE;
+                        if (state == ST_IDLE) store();
+                    }
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, state == ST_IDLE)) {
+            if (__all_sync(0xffffffffu, exhausted)) break;
+            continue;
+        }
+
+        // ---- one push for every busy lane ----
+        if (state == ST_ADAPT) {  // top of the inner while body, particle_module.f90:1602-1612
+            negp_or_bc(prm, q, a.leak);
+            if (q.count_flag != GPAT_COUNT_FLAG_INBOX) {
+                store();
+                state = ST_IDLE;
+            }
+        }
+        if (state != ST_IDLE) {
+            push_once<L>(prm, a, fld, q, state == ST_FIX);
+            nsteps++;
+            q.nsteps_pushed = (q.nsteps_pushed + 1) % a.nsteps_interval;  // particle_module.f90:1694
+            if (a.debug_nsteps > 0)
+                state = (--remaining == 0) ? ST_IDLE : ST_ADAPT;
+            else
+                state = next_state(prm, a, q, state == ST_FIX ? AFTER_FIXED_PUSH : AT_INNER_HEAD);
+            if (state == ST_IDLE) store();
+        }
+    }
+    // warp-aggregated step count
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nsteps += __shfl_down_sync(0xffffffffu, nsteps, o);
+    if (lane == 0 && nsteps) atomicAdd(a.steps, nsteps);
+}
+
+// debug: interpolated fields in the reference's 32-slot order
+template <int L>
+__global__ void interp_kernel(const __grid_constant__ DevParams prm, const float* __restrict__ fld,
+                              int sel, long long n, const double* x, const double* y,
+                              const double* z, const double* rt, double* out32)
+{
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double F[Rec<L>::NREC];
+    gather<L>(prm, fld, sel, x[i], y[i], z[i], rt[i], F);
+    for (int s = 0; s < 32; ++s) out32[i * 32 + s] = 0.0;
+#pragma unroll
+    for (int k = 0; k < Rec<L>::NUSED; ++k) out32[i * 32 + slot_of(L, k) - 1] = F[k];
+}
+
+template <int L>
+void launch_one(const DevParams& prm, const PtlSoA& P, const float* fld, const PushArgs& a,
+                int sm_count, cudaStream_t st)
+{
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel<L>, kBlock, 0);
+    if (per_sm < 1) per_sm = 1;
+    long long want = (a.nptl + kBlock - 1) / kBlock;
+    long long grid = (long long)sm_count * per_sm;  // persistent: a multiple of the SM count
+    if (want < grid) grid = want > 0 ? want : 1;
+    push_kernel<L><<<(unsigned)grid, kBlock, 0, st>>>(prm, P, fld, a);
+}
+
+}  // namespace
+
+#if GPAT_STRICT
+#define GPAT_LAUNCH launch_push_strict
+#else
+#define GPAT_LAUNCH launch_push_fast
+#endif
+
+void GPAT_LAUNCH(int layout, const DevParams& prm, const PtlSoA& P, const float* fld,
+                 const PushArgs& a, int sm_count, cudaStream_t st)
+{
+    switch (layout) {
+        case L2B: launch_one<L2B>(prm, P, fld, a, sm_count, st); break;
+        case L2E: launch_one<L2E>(prm, P, fld, a, sm_count, st); break;
+        case L3B: launch_one<L3B>(prm, P, fld, a, sm_count, st); break;
+        default: launch_one<L3E>(prm, P, fld, a, sm_count, st); break;
+    }
+}
+
+#if GPAT_STRICT
+void launch_interp_debug(int layout, const DevParams& prm, const float* fld, int sel, long long n,
+                         const double* x, const double* y, const double* z, const double* rt,
+                         double* out32, cudaStream_t st)
+{
+    unsigned grid = (unsigned)((n + 127) / 128);
+    if (grid == 0) return;
+    switch (layout) {
+        case L2B: interp_kernel<L2B><<<grid, 128, 0, st>>>(prm, fld, sel, n, x, y, z, rt, out32); break;
+        case L2E: interp_kernel<L2E><<<grid, 128, 0, st>>>(prm, fld, sel, n, x, y, z, rt, out32); break;
+        case L3B: interp_kernel<L3B><<<grid, 128, 0, st>>>(prm, fld, sel, n, x, y, z, rt, out32); break;
+        default: interp_kernel<L3E><<<grid, 128, 0, st>>>(prm, fld, sel, n, x, y, z, rt, out32); break;
+    }
+}
+#endif
+
+}  // namespace gpat

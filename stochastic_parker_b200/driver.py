@@ -1,0 +1,255 @@
+"""Host-side mirror of the reference driver for the GPU path.
+
+`GpatSim` is a one-to-one wrapper of the C ABI (include/gpat_cuda.h): the method names are
+the reference procedure names (particle_module / diagnostics public lists,
+particle_module.f90:16-36, diagnostics.f90:24-30).  `run_intervals` reproduces the order
+of calls of solve_transport_equation (stochastic-mhd.f90:312-567) for one rank.
+
+Everything numerical happens inside libgpat_cuda.so; this file only sequences calls
+and owns the host buffers, exactly like the Fortran driver would.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from .abi import PARTICLE_DTYPE, Counters, Params, Timings, ptr
+
+
+class GpatError(RuntimeError):
+    pass
+
+
+class GpatSim:
+    def __init__(self, params: Params, nptl_max: int, device: int = 0, lib_path: str | None = None):
+        self.lib = abi.load_library(lib_path)
+        self.P = params.copy()
+        self.nptl_max = int(nptl_max)
+        self.h = C.c_void_p()
+        rc = self.lib.gpat_init(C.byref(self.h), device, self.nptl_max, C.byref(self.P))
+        if rc != abi.GPAT_OK:
+            msg = self.lib.gpat_last_error(None)
+            self.h = None
+            raise GpatError(f"gpat_init failed ({rc}): {msg.decode() if msg else ''}")
+
+    # ---- plumbing -----------------------------------------------------------
+    def _ck(self, rc: int, what: str):
+        if rc != abi.GPAT_OK:
+            msg = self.lib.gpat_last_error(self.h)
+            raise GpatError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gpat_finalize(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def grid_shape(self):
+        P = self.P
+        nzg = P.nz + 4 if P.ndim > 2 else 1
+        return nzg, P.ny + 4, P.nx + 4
+
+    def set_params(self, params: Params):
+        self._ck(self.lib.gpat_set_params(self.h, C.byref(params)), "gpat_set_params")
+        self.P = params.copy()
+
+    # ---- fields -------------------------------------------------------------
+    def upload_fields(self, slot: int, f: np.ndarray, with_grad: int = 0):
+        f = np.ascontiguousarray(f, dtype=np.float32)
+        nvar = f.shape[-1]
+        if f.size != int(np.prod(self.grid_shape)) * nvar:
+            raise ValueError(f"field array has {f.size} floats, grid {self.grid_shape} x {nvar} expected")
+        self._ck(self.lib.gpat_upload_fields(self.h, slot, ptr(f), nvar, with_grad), "gpat_upload_fields")
+
+    def swap_fields(self):
+        self._ck(self.lib.gpat_swap_fields(self.h), "gpat_swap_fields")
+
+    def debug_gradients(self, f8: np.ndarray) -> np.ndarray:
+        f8 = np.ascontiguousarray(f8, dtype=np.float32)
+        out = np.empty(f8.shape[:-1] + (32,), dtype=np.float32)
+        self._ck(self.lib.gpat_debug_gradients(self.h, ptr(f8), ptr(out)), "gpat_debug_gradients")
+        return out
+
+    def interp(self, x, y, z, rt) -> np.ndarray:
+        x, y, z, rt = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, z, rt))
+        out = np.empty((len(x), 32), dtype=np.float64)
+        self._ck(self.lib.gpat_debug_interp(self.h, len(x), ptr(x), ptr(y), ptr(z), ptr(rt), ptr(out)),
+                 "gpat_debug_interp")
+        return out
+
+    # ---- particles ----------------------------------------------------------
+    def inject_uniform(self, nptl, dt, dist_flag, particle_v0, t_frame, dt_mhd, part_box, power_index):
+        box = (C.c_double * 6)(*part_box)
+        self._ck(self.lib.gpat_inject_uniform(self.h, nptl, dt, dist_flag, particle_v0, t_frame, dt_mhd,
+                                              box, power_index), "gpat_inject_uniform")
+
+    def particle_mover(self, t0, dtf, nsteps_interval=100, num_fine_steps=1, dump_escaped_dist=0) -> int:
+        steps = C.c_uint64(0)
+        self._ck(self.lib.gpat_particle_mover(self.h, t0, dtf, nsteps_interval, num_fine_steps,
+                                              dump_escaped_dist, C.byref(steps)), "gpat_particle_mover")
+        return steps.value
+
+    def debug_push_n(self, t0, dtf, nsteps) -> int:
+        steps = C.c_uint64(0)
+        self._ck(self.lib.gpat_debug_push_n(self.h, t0, dtf, nsteps, C.byref(steps)), "gpat_debug_push_n")
+        return steps.value
+
+    def split(self, split_ratio, pmin_split, nsteps_interval=100):
+        self._ck(self.lib.gpat_split(self.h, split_ratio, pmin_split, nsteps_interval), "gpat_split")
+
+    def download_particles(self) -> np.ndarray:
+        n = C.c_int64(0)
+        self._ck(self.lib.gpat_download_particles(self.h, None, 0, C.byref(n)), "gpat_download_particles")
+        out = np.zeros(max(n.value, 1), dtype=PARTICLE_DTYPE)
+        self._ck(self.lib.gpat_download_particles(self.h, ptr(out), n.value, C.byref(n)),
+                 "gpat_download_particles")
+        return out[:n.value]
+
+    def upload_particles(self, ptl: np.ndarray):
+        ptl = np.ascontiguousarray(ptl, dtype=PARTICLE_DTYPE)
+        self._ck(self.lib.gpat_upload_particles(self.h, ptr(ptl) if len(ptl) else None, len(ptl)),
+                 "gpat_upload_particles")
+
+    def download_escaped(self) -> np.ndarray:
+        n = C.c_int64(0)
+        self._ck(self.lib.gpat_download_escaped(self.h, None, 0, C.byref(n)), "gpat_download_escaped")
+        out = np.zeros(max(n.value, 1), dtype=PARTICLE_DTYPE)
+        self._ck(self.lib.gpat_download_escaped(self.h, ptr(out), n.value, C.byref(n)),
+                 "gpat_download_escaped")
+        return out[:n.value]
+
+    def reset_escaped(self):
+        self._ck(self.lib.gpat_reset_escaped(self.h), "gpat_reset_escaped")
+
+    def counters(self) -> Counters:
+        c = Counters()
+        self._ck(self.lib.gpat_get_counters(self.h, C.byref(c)), "gpat_get_counters")
+        return c
+
+    def set_counters(self, c: Counters):
+        self._ck(self.lib.gpat_set_counters(self.h, C.byref(c)), "gpat_set_counters")
+
+    def set_rng_table(self, u: np.ndarray):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        self._ck(self.lib.gpat_set_rng_table(self.h, ptr(u), u.shape[0], u.shape[1]), "gpat_set_rng_table")
+
+    # ---- diagnostics --------------------------------------------------------
+    def local_shape(self, k: int):
+        P, s = self.P, self.P.local[k]
+        nrx = (P.nx + s.rx - 1) // s.rx
+        nry = (P.ny + s.ry - 1) // s.ry
+        nrz = (P.nz + s.rz - 1) // s.rz
+        return nrz, nry, nrx, s.npbins, s.nmu  # C-order view of Fortran (nmu,np,nrx,nry,nrz)
+
+    def alloc_diagnostics(self):
+        """Host arrays with the shapes of diagnostics.f90:182-191, 235-245."""
+        P = self.P
+        fglobal = np.zeros((P.npp_global, P.nmu_global), dtype=np.float64)
+        flocal = [np.zeros(self.local_shape(k), dtype=np.float64) if P.local[k].enabled else None
+                  for k in range(4)]
+        return fglobal, flocal
+
+    def diagnostics(self, local_dist: bool = True, out=None):
+        fglobal, flocal = out if out is not None else self.alloc_diagnostics()
+        ptrs = (C.c_void_p * 4)(*[ptr(a) if a is not None else None for a in flocal])
+        quick = np.zeros(8, dtype=np.float64)
+        pmax = C.c_double(0.0)
+        self._ck(self.lib.gpat_diagnostics(self.h, int(local_dist), ptr(fglobal), ptrs, ptr(quick),
+                                           C.byref(pmax)), "gpat_diagnostics")
+        return dict(fglobal=fglobal, flocal=flocal, quick=quick, pmax=pmax.value)
+
+    def escaped_diagnostics(self) -> np.ndarray:
+        P = self.P
+        out = np.zeros((2 * P.ndim, P.npp_global, P.nmu_global), dtype=np.float64)
+        self._ck(self.lib.gpat_escaped_diagnostics(self.h, ptr(out)), "gpat_escaped_diagnostics")
+        return out
+
+    def hist_edges(self, which: int = 0):
+        P = self.P
+        np_ = P.local[which - 1].npbins if which else P.npp_global
+        nmu = P.local[which - 1].nmu if which else P.nmu_global
+        pe, me = np.zeros(np_ + 1), np.zeros(nmu + 1)
+        self._ck(self.lib.gpat_hist_edges(self.h, which, ptr(pe), ptr(me)), "gpat_hist_edges")
+        return pe, me
+
+    # ---- multi-GPU ------------------------------------------------------------
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = self.lib.gpat_comm_unique_id(buf)
+        if rc != abi.GPAT_OK:
+            msg = self.lib.gpat_last_error(None)
+            raise GpatError(f"gpat_comm_unique_id failed ({rc}): {msg.decode() if msg else ''}")
+        return buf.raw
+
+    def comm_init(self, uid: bytes, nranks: int, rank: int):
+        self._ck(self.lib.gpat_comm_init(self.h, uid, nranks, rank), "gpat_comm_init")
+
+    def comm_destroy(self):
+        self._ck(self.lib.gpat_comm_destroy(self.h), "gpat_comm_destroy")
+
+    def timings(self) -> Timings:
+        t = Timings()
+        self._ck(self.lib.gpat_get_timings(self.h, C.byref(t)), "gpat_get_timings")
+        return t
+
+
+def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, power_index=6.2,
+                  part_box=None, inject_new_ptl=True, tmax_to_inject=1 << 30, split_flag=1,
+                  split_ratio=2.0, pmin_split=2.0, nsteps_interval=100, num_fine_steps=1,
+                  local_dist=True, dump_escaped_dist=False, dt_inject=0.0, on_interval=None):
+    """solve_transport_equation (stochastic-mhd.f90:312-567) for one rank.
+
+    `sim` is a GpatSim (or the test oracle, which has the same methods); `frames` is a
+    sequence (or callable frame -> ndarray) of 8-variable MHD frames; `tstamps[i]` is the
+    time of frame i (tstamps_mhd, mhd_config.f90:263-271).  Returns the per-interval records
+    the reference writes to quick.dat / pmax_global.dat / fdists_NNNN.h5.
+    """
+    get = frames if callable(frames) else (lambda i: frames[i])
+    P = sim.P
+    if part_box is None:  # stochastic-mhd.f90:384-390
+        part_box = [P.xmin, P.ymin, P.zmin, P.xmax, P.ymax, P.zmax]
+    nframes = len(tstamps)
+    records = []
+    sim.upload_fields(0, get(0))                               # :320-321, :350
+    total_steps = 0
+    for tf in range(1, nframes):                               # :397
+        # read_field_data_parallel(..., var_flag=time_interp_flag): without time interpolation
+        # the new frame REPLACES farray1 (:404-406, :426)
+        sim.upload_fields(1 if P.time_interp else 0, get(tf))
+        t0, dtf = tstamps[tf - 1], tstamps[tf] - tstamps[tf - 1]
+        if (tf == 1 or inject_new_ptl) and tf <= tmax_to_inject:   # :462-485
+            sim.inject_uniform(nptl, dt_inject, dist_flag, particle_v0, t0, dtf, part_box, power_index)
+        if tf == 1:                                            # :488-494
+            d0 = sim.diagnostics(local_dist)
+            d0["frame"] = 0
+            records.append(d0)
+        steps = sim.particle_mover(t0, dtf, nsteps_interval, num_fine_steps, int(dump_escaped_dist))  # :502
+        total_steps += steps
+        if split_flag == 1:
+            sim.split(split_ratio, pmin_split, nsteps_interval)  # :515
+        d = sim.diagnostics(local_dist)                        # :518-521
+        d["frame"] = tf
+        d["steps"] = steps
+        if dump_escaped_dist:
+            d["fescaped"] = sim.escaped_diagnostics()
+            sim.reset_escaped()                                # :533
+        records.append(d)
+        if on_interval is not None:
+            on_interval(tf, d)
+        if P.time_interp:
+            sim.swap_fields()                                  # :538
+    return records, total_steps

@@ -1,0 +1,303 @@
+"""GPU parity tests: libgpat_cuda.so (through the C ABI) against the CPU oracle.
+
+Bars (north_star): with identical random increments trajectories agree to 1e-12 relative in
+FP64; integer/index work (histogram counts, tags, compaction order, RNG counters) bit-exact.
+`strict_math=1` selects the no-contraction build of the push kernel, whose only arithmetic
+difference from the oracle is CUDA's libdevice pow/log10 vs glibc's (<= 2 ulp); the fast build
+(FMA contraction, fused time blend) is held to the same 1e-12 per step.
+"""
+import numpy as np
+import pytest
+
+from helpers import assert_particles_close, box_of, make_case, rel_err, sort_by_key
+from oracle.oracle import Oracle
+from stochastic_parker_b200 import GpatSim, run_intervals
+from stochastic_parker_b200.abi import PARTICLE_DTYPE, rng_steps
+
+pytestmark = pytest.mark.gpu
+
+STEP_RTOL = 1e-12    # one push, FP64 (north_star)
+FRAME_RTOL = 1e-9    # a whole MHD interval: ~1e3 dependent steps, errors compound
+
+
+def pair(P, nptl_max, strict=1):
+    Pg = P.copy()
+    Pg.strict_math = strict
+    return GpatSim(Pg, nptl_max), Oracle(P, nptl_max)
+
+
+def load_fields(sims, frames, time_interp=True):
+    for s in sims:
+        s.upload_fields(0, frames[0])
+        if time_interp:
+            s.upload_fields(1, frames[1])
+
+
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("key,grid", [("c1", 48), ("c5", 20)])
+def test_gradients_bit_exact(key, grid):
+    """calc_fields_gradients (mhd_data_parallel.f90:533-566): all 24 FP32 gradients, every
+    grid point including the one-sided ghost edges, bit for bit."""
+    w, P, frames, _ = make_case(key, grid=grid, nptl=8)
+    g, o = pair(P, w.nptl_max)
+    o.upload_fields(0, frames[0])
+    ref = o.get_fields(0).reshape(-1, 32)
+    got = g.debug_gradients(frames[0]).reshape(-1, 32)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    g.close()
+
+
+@pytest.mark.parametrize("key,grid,cli", [("c1", 48, {}), ("c4", 48, {}), ("c5", 20, {}),
+                                          ("c5", 20, dict(dpp_wave=1, dpp_shear=1))])
+@pytest.mark.parametrize("strict", [1, 0])
+def test_interp_parity(key, grid, cli, strict):
+    """get_interp_paramters + interp_fields incl. the time blend, on every slot the pusher
+    reads (strict: identical operations -> identical bits)."""
+    w, P, frames, _ = make_case(key, grid=grid, nptl=8, cli=cli)
+    g, o = pair(P, w.nptl_max, strict)
+    load_fields((g, o), frames)
+    rng = np.random.default_rng(1)
+    n = 4000
+    x = rng.uniform(P.xmin - 0.5 * P.dx, P.xmax + 0.5 * P.dx, n)
+    y = rng.uniform(P.ymin - 0.5 * P.dy, P.ymax + 0.5 * P.dy, n)
+    z = rng.uniform(P.zmin - 0.5 * P.dz, P.zmax + 0.5 * P.dz, n) if P.ndim == 3 else rng.uniform(0, 1, n)
+    rt = rng.uniform(0, 1, n)
+    ref = o.interp(x, y, z, rt)
+    got = g.interp(x, y, z, rt)
+    used = np.any(got != 0.0, axis=0)
+    assert used.sum() >= 15
+    if strict:
+        assert np.array_equal(got[:, used], ref[:, used])
+    else:
+        scale = np.maximum(np.abs(ref[:, used]).max(axis=0), 1e-30)
+        assert np.max(np.abs(got[:, used] - ref[:, used]) / scale) < 1e-14
+    g.close()
+
+
+@pytest.mark.parametrize("dist_flag", [1, 0, 2])
+def test_inject_parity(dist_flag):
+    """inject_particles_spatial_uniform + inject_one_particle: same Philox stream, same
+    arithmetic -> bit-exact for the delta distribution; exp/pow ulps for the others."""
+    w, P, frames, _ = make_case("c1", grid=32, nptl=3000)
+    g, o = pair(P, 4000)
+    for s in (g, o):
+        s.inject_uniform(3000, 1e-4, dist_flag, w.particle_v0, 0.3, 0.1, box_of(P), 6.2)
+        s.inject_uniform(1500, 1e-4, dist_flag, w.particle_v0, 0.4, 0.1, box_of(P), 6.2)  # hits capacity
+    a, b = g.download_particles(), o.download_particles()
+    assert len(a) == len(b) == 4000
+    cg, co = g.counters(), o.counters()
+    assert (cg.nptl_current, cg.tag_max) == (co.nptl_current, co.tag_max) == (4000, 4500)
+    if dist_flag == 1:
+        assert a.tobytes() == b.tobytes()
+    else:
+        assert_particles_close(a, b, 1e-13, f"inject dist_flag={dist_flag}", frac_outliers=0.002)
+    g.close()
+
+
+CASES = {
+    "c1_2d": dict(key="c1", grid=64),
+    "c1_2d_no_time_interp": dict(key="c1", grid=64, cli=dict(time_interp=0)),
+    "c1_2d_check_drift": dict(key="c1", grid=64, cli=dict(check_drift_2d=1)),
+    "c1_2d_nlgc": dict(key="c1", grid=64, conf=dict(dt_min_rel=1e-3), cli=dict(nlgc=1, kperp_kpara=0.05)),
+    "c1_2d_acc_region": dict(key="c1", grid=64, conf=dict(acc_region_flag=1)),
+    "c1_2d_include_3rd": dict(key="c1", grid=64, cli=dict(include_3rd_dim=1)),
+    "c2_flare_open": dict(key="c2", grid=64),
+    "c3_shock_open": dict(key="c3", grid=64),
+    "c4_dpp_wave_shear": dict(key="c4", grid=64),
+    "c4_dpp_strong_kret0": dict(key="c4", grid=64, conf=dict(kret=0.0), cli=dict(weak_scattering=0)),
+    "c5_3d": dict(key="c5", grid=24),
+    "c5_3d_dpp_nlgc": dict(key="c5", grid=24, conf=dict(kpara0=0.02, dt_min_rel=1e-3),
+                           cli=dict(dpp_wave=1, dpp_shear=1, nlgc=1, kperp_kpara=0.05)),
+}
+
+
+def _inject(sims, w, P, n, t0=0.0, dist_flag=1):
+    for s in sims:
+        s.inject_uniform(n, 0.0, dist_flag, w.particle_v0, t0, w.dt_out, box_of(P), w.power_index)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("strict", [1, 0])
+def test_step_parity(name, strict):
+    """One and then 40 consecutive calls of push_particle_* per particle (BC test, gather,
+    kappa, drift, adaptive dt, stochastic step, momentum floor) with identical uniforms."""
+    w, P, frames, _ = make_case(**CASES[name], nptl=512)
+    g, o = pair(P, w.nptl_max, strict)
+    load_fields((g, o), frames, P.time_interp)
+    _inject((g, o), w, P, 512, dist_flag=0)
+    for nsteps in (1, 40):
+        sg = g.debug_push_n(0.0, w.dt_out, nsteps)
+        so = o.debug_push_n(0.0, w.dt_out, nsteps)
+        assert sg == so
+        a, b = g.download_particles(), o.download_particles()
+        # a single flipped branch (1-ulp pow difference at a min()/BC edge) is tolerated on
+        # at most 1 particle in 500; everything else must sit inside 1e-12
+        assert_particles_close(a, b, STEP_RTOL * max(1, nsteps // 4), f"{name} {nsteps} steps strict={strict}",
+                               frac_outliers=0.002)
+    g.close()
+
+
+@pytest.mark.parametrize("name", ["c1_2d", "c3_shock_open", "c4_dpp_wave_shear", "c5_3d"])
+def test_table_rng_parity(name):
+    """north_star wording: 'fed the same pre-generated random increments' -- both sides replay
+    one table of uniforms instead of generating them."""
+    from stochastic_parker_b200.abi import RNG_TABLE
+    w, P, frames, _ = make_case(**CASES[name], nptl=256)
+    P.rng_mode = RNG_TABLE
+    g, o = pair(P, w.nptl_max, 1)
+    u = np.random.default_rng(7).uniform(0, 1, (256, 32, 4))
+    g.set_rng_table(u)
+    o.set_rng_table(u)
+    load_fields((g, o), frames, P.time_interp)
+    _inject((g, o), w, P, 256)
+    assert g.debug_push_n(0.0, w.dt_out, 30) == o.debug_push_n(0.0, w.dt_out, 30)
+    assert_particles_close(g.download_particles(), o.download_particles(), 1e-11, name, frac_outliers=0.004)
+    g.close()
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_interval_parity_strict(name):
+    """particle_mover over two MHD intervals (adaptive steps, end-of-interval roll-back +
+    fixed-dt re-push, both remove_particles passes, split, field swap), strict build."""
+    w, P, frames, ts = make_case(**CASES[name], nptl=400)
+    g, o = pair(P, w.nptl_max, 1)
+    kw = dict(nptl=400, dist_flag=1, particle_v0=w.particle_v0, inject_new_ptl=True, split_flag=1,
+              pmin_split=1.05, split_ratio=1.05, num_fine_steps=2, dump_escaped_dist=True)
+    rg, sg = run_intervals(g, frames, ts, **kw)
+    ro, so = run_intervals(o, frames, ts, **kw)
+    a, b = g.download_particles(), o.download_particles()
+    assert abs(sg - so) <= 2e-3 * so, (sg, so)
+    assert abs(len(a) - len(b)) <= 2
+    if len(a) == len(b):
+        # same ORDER as the reference's swap-with-tail remove and append-at-tail split
+        same_order = all(np.array_equal(a[f], b[f]) for f in ("origin", "tag_injected", "tag_splitted"))
+        assert same_order
+        assert_particles_close(a, b, FRAME_RTOL, name, int_exact=False, frac_outliers=0.01)
+    cg, co = g.counters(), o.counters()
+    assert abs(cg.nptl_escaped - co.nptl_escaped) <= 1
+    assert rel_err(cg.leak, co.leak) < 1e-2 or abs(cg.leak - co.leak) <= 1.0
+    g.close()
+
+
+def test_interval_parity_fast():
+    """The production (fast-math) build over two intervals against the oracle."""
+    w, P, frames, ts = make_case("c1", grid=64, nptl=2000)
+    g, o = pair(P, w.nptl_max, 0)
+    kw = dict(nptl=2000, dist_flag=1, particle_v0=w.particle_v0, split_flag=1)
+    rg, sg = run_intervals(g, frames, ts, **kw)
+    ro, so = run_intervals(o, frames, ts, **kw)
+    assert abs(sg - so) <= 1e-3 * so
+    a, b = sort_by_key(g.download_particles()), sort_by_key(o.download_particles())
+    assert_particles_close(a, b, FRAME_RTOL, "fast c1", int_exact=False, frac_outliers=0.01)
+    # spectra: identical up to particles that sit within rounding of a bin edge
+    for x, y in zip(rg, ro):
+        assert np.abs(x["fglobal"] - y["fglobal"]).sum() <= 4.0
+    g.close()
+
+
+@pytest.mark.parametrize("name", ["c1_2d", "c3_shock_open", "c5_3d"])
+def test_histograms_bit_exact(name):
+    """calc_particle_distributions + quick_check + get_pmax_global on the SAME particle set:
+    every histogram count bit-exact (dyadic weights -> order-independent FP64 sums)."""
+    w, P, frames, ts = make_case(**CASES[name], nptl=3000)
+    g, o = pair(P, w.nptl_max, 1)
+    run_intervals(o, frames, ts, nptl=3000, particle_v0=w.particle_v0, pmin_split=1.02, split_ratio=1.02)
+    ptl = o.download_particles()
+    assert len(ptl) > 0 and len(np.unique(ptl["weight"])) > 1
+    g.upload_particles(ptl)
+    c = o.counters()
+    g.set_counters(c)
+    dg, do = g.diagnostics(True), o.diagnostics(True)
+    assert np.array_equal(dg["fglobal"], do["fglobal"])
+    assert dg["fglobal"].sum() > 0
+    for k in range(4):
+        if do["flocal"][k] is None:
+            assert dg["flocal"][k] is None
+            continue
+        assert np.array_equal(dg["flocal"][k], do["flocal"][k]), f"flocal{k + 1}"
+    assert np.array_equal(dg["quick"][[0, 1, 2, 3, 4, 6, 7]], do["quick"][[0, 1, 2, 3, 4, 6, 7]])
+    assert rel_err(dg["quick"][5], do["quick"][5]) < 1e-12  # sum(dt): not dyadic, order-dependent
+    assert dg["pmax"] == do["pmax"]
+    pe_g, me_g = g.hist_edges(0)
+    pe_o, me_o = o.hist_edges(0)
+    assert np.array_equal(pe_g, pe_o) and np.array_equal(me_g, me_o)
+    g.close()
+
+
+def test_split_and_remove_exact():
+    """split_particle (append order, tags, weights, capacity stop) and remove_particles
+    (swap-with-tail order) reproduce the serial reference bit for bit."""
+    w, P, frames, ts = make_case("c1", grid=32, nptl=64)
+    nmax = 5000
+    g, o = pair(P, nmax, 1)
+    rng = np.random.default_rng(3)
+    n = 4000
+    ptl = np.zeros(n, dtype=PARTICLE_DTYPE)
+    ptl["x"] = rng.uniform(P.xmin, P.xmax, n)
+    ptl["y"] = rng.uniform(P.ymin, P.ymax, n)
+    ptl["z"] = rng.uniform(0, 1, n)
+    ptl["p"] = P.p0 * 10 ** rng.uniform(-0.3, 1.5, n)
+    ptl["weight"] = 0.5 ** rng.integers(0, 4, n)
+    ptl["split_times"] = rng.integers(0, 4, n)
+    ptl["count_flag"] = rng.choice([1, 1, 1, 0, -1, -2, -4], n)
+    ptl["tag_injected"] = np.arange(n)
+    ptl["tag_splitted"] = 1
+    ptl["dt"] = 1e-4
+    ptl["mu"] = rng.uniform(-0.9, 0.9, n)
+    rng_steps(ptl)[:] = rng.integers(0, 1000, n).astype(np.uint64)
+    for s in (g, o):
+        s.upload_particles(ptl)
+    # two consecutive splits: the second one runs into nptl_max
+    for it in range(2):
+        g.split(2.0, 2.0)
+        o.split(2.0, 2.0)
+        a, b = g.download_particles(), o.download_particles()
+        assert len(a) == len(b)
+        assert a.tobytes() == b.tobytes(), f"split pass {it}"
+        assert g.counters().nptl_split == o.counters().nptl_split
+    assert g.counters().nptl_current == nmax
+    # remove via a mover call over an interval that is already over for every particle
+    load_fields((g, o), frames)
+    for s in (g, o):
+        q = s.download_particles()
+        q["t"] = 0.1
+        s.upload_particles(q)
+    assert g.particle_mover(0.0, 0.1, 100, 1, 1) == o.particle_mover(0.0, 0.1, 100, 1, 1) == 0
+    a, b = g.download_particles(), o.download_particles()
+    assert len(a) == len(b) and len(a) < nmax
+    assert a.tobytes() == b.tobytes()
+    cg, co = g.counters(), o.counters()
+    assert (cg.nptl_escaped, cg.leak, cg.leak_negp) == (co.nptl_escaped, co.leak, co.leak_negp)
+    ea, eb = sort_by_key(g.download_escaped()), sort_by_key(o.download_escaped())
+    assert ea.tobytes() == eb.tobytes()
+    assert np.array_equal(g.escaped_diagnostics(), o.escaped_diagnostics())
+    g.close()
+
+
+def test_edge_cases():
+    """Empty population, zero-particle injection, mover before fields, bad parameters."""
+    from stochastic_parker_b200 import GpatError
+    w, P, frames, ts = make_case("c1", grid=32, nptl=16)
+    g = GpatSim(P, 64)
+    with pytest.raises(GpatError):
+        g.particle_mover(0.0, 0.1)  # fields not uploaded: GPAT_ERR_STATE
+    load_fields((g,), frames)
+    assert g.particle_mover(0.0, 0.1) == 0
+    g.inject_uniform(0, 0.0, 1, 1.0, 0.0, 0.1, box_of(P), 6.2)
+    g.split(2.0, 2.0)
+    d = g.diagnostics(True)
+    assert d["fglobal"].sum() == 0 and d["quick"][0] == 0 and d["quick"][6] == 1.0 and d["pmax"] == 0.0
+    assert len(g.download_particles()) == 0
+    with pytest.raises((GpatError, ValueError)):
+        g.upload_fields(0, frames[0][:-1])
+    with pytest.raises(GpatError):
+        g.inject_uniform(4, 0.0, 7, 1.0, 0.0, 0.1, box_of(P), 6.2)
+    bad = P.copy()
+    bad.focused_transport = 1
+    with pytest.raises(GpatError):
+        GpatSim(bad, 64)
+    bad = P.copy()
+    bad.local[0].rx = 5  # does not divide nx: check_local_dist_configuration
+    with pytest.raises(GpatError):
+        GpatSim(bad, 64)
+    g.close()
