@@ -1012,6 +1012,7 @@ void orc_debug_push_n(orc_sim* S, double t0, double dtf, int nsteps, uint64_t* s
             if (ptl.count_flag != GPAT_COUNT_FLAG_INBOX) break;
             one_push(S, &ptl, t0, dtf, 0, &dx_, &dy_, &dz_, &dp_);
             steps++;
+            ptl.nsteps_pushed = (ptl.nsteps_pushed + 1) % (1 << 30);
         }
         S->ptls[i] = ptl;
     }

@@ -113,6 +113,8 @@ struct gpat_sim {
     size_t local_bins[4] = {0, 0, 0, 0};
     int nrx[4] = {0}, nry[4] = {0}, nrz[4] = {0};
     double* d_fesc = nullptr;
+    double* d_pthr = nullptr;             // momentum-bin thresholds: global, then local 1..4
+    size_t pthr_off[5] = {0, 0, 0, 0, 0};
     double* d_sums = nullptr;             // [2]
     unsigned long long* d_minmax = nullptr;  // [3]
     double* d_quick = nullptr;            // [9]
@@ -254,9 +256,44 @@ size_t field_floats(const gpat_sim* h)
     return (size_t)h->dp.nxg * h->dp.nyg * h->dp.nzg * nrec_of(h->layout) * (h->dp.time_interp ? 2 : 1);
 }
 
+// The smallest positive double p with floor((log10(p) - pmin_log)/dp_log) >= k, found by
+// bisection over the bit patterns with the host's libm (the libm the reference itself runs on).
+double bin_threshold(double pmin_log, double dp_log, int k)
+{
+    auto f_ge = [&](double p) { return std::floor((std::log10(p) - pmin_log) / dp_log) >= (double)k; };
+    uint64_t lo = 0x0010000000000000ull;  // smallest normal: f very negative
+    uint64_t hi = 0x7fe0000000000000ull;  // ~9e307
+    auto as_d = [](uint64_t b) { double d; memcpy(&d, &b, 8); return d; };
+    if (f_ge(as_d(lo))) return as_d(lo);
+    if (!f_ge(as_d(hi))) return HUGE_VAL;
+    while (hi - lo > 1) {
+        uint64_t mid = lo + (hi - lo) / 2;
+        if (f_ge(as_d(mid))) hi = mid; else lo = mid;
+    }
+    return as_d(hi);
+}
+
 int alloc_hists(gpat_sim* h)
 {
     const gpat_params& p = h->hp;
+    {
+        std::vector<double> thr;
+        auto add = [&](double pmin, double pmax, int nb) {
+            double pmin_log = std::log10(pmin);
+            double dp_log = (std::log10(pmax) - pmin_log) / nb;
+            for (int k = 0; k <= nb; ++k) thr.push_back(bin_threshold(pmin_log, dp_log, k));
+        };
+        h->pthr_off[0] = 0;
+        add(p.pmin, p.pmax, p.npp_global);
+        for (int k = 0; k < 4; ++k) {
+            h->pthr_off[k + 1] = thr.size();
+            if (p.local[k].enabled) add(p.local[k].pmin, p.local[k].pmax, p.local[k].npbins);
+        }
+        if (h->d_pthr) cudaFree(h->d_pthr);
+        h->d_pthr = nullptr;
+        CU(cudaMalloc(&h->d_pthr, thr.size() * sizeof(double)));
+        CU(cudaMemcpy(h->d_pthr, thr.data(), thr.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     for (int k = 0; k < 4; ++k) {
         if (h->d_flocal[k]) { cudaFree(h->d_flocal[k]); h->d_flocal[k] = nullptr; }
         h->local_bins[k] = 0;
@@ -288,8 +325,10 @@ void fill_diag_args(const gpat_sim* h, DiagArgs& a, int local_dist)
     a.dmu = (double)(2.0f / (float)p.nmu_global);
     a.xmin = p.xmin; a.ymin = p.ymin; a.zmin = p.zmin;
     a.fglobal = h->d_fglobal;
+    a.gthr = h->d_pthr + h->pthr_off[0];
     for (int k = 0; k < 4; ++k) {
         HistDev& d = a.loc[k];
+        d.pthr = h->d_pthr + h->pthr_off[k + 1];
         const gpat_hist_spec& s = p.local[k];
         d.enabled = s.enabled && h->d_flocal[k];
         d.npbins = s.npbins; d.nmu = s.nmu; d.nrx = h->nrx[k]; d.nry = h->nry[k]; d.nrz = h->nrz[k];
@@ -498,7 +537,7 @@ int gpat_finalize(gpat_handle h)
     void* ptrs[] = {h->ptl_mem, h->esc_mem, h->d_counters, h->d_nptl_split, h->d_leak, h->d_queue,
                     h->w.tile_counts, h->w.tile_offsets, h->idx_a, h->idx_b, h->fld, h->stage,
                     h->d_fglobal, h->d_flocal[0], h->d_flocal[1], h->d_flocal[2], h->d_flocal[3],
-                    h->d_fesc, h->d_sums, h->d_minmax, h->d_quick, h->d_table, h->d_aos};
+                    h->d_fesc, h->d_pthr, h->d_sums, h->d_minmax, h->d_quick, h->d_table, h->d_aos};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& ev : h->ev)

@@ -19,6 +19,18 @@ __device__ __forceinline__ bool ifloor_ok(double v, long long& out)
     return true;
 }
 
+// momentum bin index f(p) in [-1, K] from the host-libm thresholds T[0..K]; lp = device log10(p)
+// only provides the starting guess.
+__device__ __forceinline__ int pbin(const double* __restrict__ T, int K, double p, double lp,
+                                    double pmin_log, double dp_log)
+{
+    double v = (lp - pmin_log) / dp_log;
+    int c = !(v == v) ? -1 : (v < -1.0) ? -1 : (v > (double)K) ? K : (int)floor(v);
+    while (c < K && p >= T[c + 1]) ++c;
+    while (c >= 0 && p < T[c]) --c;
+    return c;
+}
+
 constexpr int kMaxSharedBins = 4096;
 
 __global__ void __launch_bounds__(256) diag_kernel(const PtlSoA P, const __grid_constant__ DiagArgs a)
@@ -57,8 +69,8 @@ __global__ void __launch_bounds__(256) diag_kernel(const PtlSoA P, const __grid_
         // global spectrum (diagnostics.f90:773-780)
         int gbin = -1;
         if (live && a.fglobal && p > a.pmin && p <= a.pmax && mu >= -1.0 && mu <= 1.0) {
-            long long ip, imu;
-            if (ifloor_ok((lp - a.pmin_log) / a.dp_log, ip) && ifloor_ok((mu + 1.0) / a.dmu, imu)) {
+            long long ip = pbin(a.gthr, a.npp_g, p, lp, a.pmin_log, a.dp_log), imu;
+            if (ifloor_ok((mu + 1.0) / a.dmu, imu)) {
                 ip += 1; imu += 1;
                 long long lin = (imu - 1) + (ip - 1) * (long long)a.nmu_g;
                 if (ip >= 1 && imu >= 1 && lin >= 0 && lin < nglob) gbin = (int)lin;
@@ -92,9 +104,9 @@ __global__ void __launch_bounds__(256) diag_kernel(const PtlSoA P, const __grid_
                 bool ok = ifloor_ok((x - a.xmin) / h.dx_diag, ix) &&
                           ifloor_ok((y - a.ymin) / h.dy_diag, iy) &&
                           ifloor_ok((z - a.zmin) / h.dz_diag, iz) &&
-                          ifloor_ok((lp - h.pmin_log) / h.dp_log, ip) &&
                           ifloor_ok((mu + 1.0) / h.dmu, imu);
                 if (!ok) continue;
+                ip = pbin(h.pthr, h.npbins, p, lp, h.pmin_log, h.dp_log);
                 ix += 1; iy += 1; iz += 1; ip += 1; imu += 1;
                 if (ix >= 1 && ix <= h.nrx && iy >= 1 && iy <= h.nry && iz >= 1 && iz <= h.nrz &&
                     ip > 0 && ip < h.npbins /* top bin never filled, diagnostics.f90:799 */ &&
@@ -175,8 +187,8 @@ __global__ void escaped_diag_kernel(const PtlSoA E, long long n, DiagArgs a, int
     int face = -(int)E.count_flag[i];
     if (face < 1 || face > nface) return;
     if (p > a.pmin && p <= a.pmax && mu >= -1.0 && mu <= 1.0) {
-        long long ip, imu;
-        if (ifloor_ok((log10(p) - a.pmin_log) / a.dp_log, ip) && ifloor_ok((mu + 1.0) / a.dmu, imu)) {
+        long long ip = pbin(a.gthr, a.npp_g, p, log10(p), a.pmin_log, a.dp_log), imu;
+        if (ifloor_ok((mu + 1.0) / a.dmu, imu)) {
             ip += 1; imu += 1;
             long long lin = (imu - 1) + (ip - 1) * (long long)a.nmu_g;
             long long nglob = (long long)a.nmu_g * a.npp_g;

@@ -129,6 +129,7 @@ struct HistDev {
     int enabled, npbins, nmu, nrx, nry, nrz;
     double pmin_log, dp_log, dmu, dx_diag, dy_diag, dz_diag;
     double* data;
+    const double* pthr;  // npbins+1 momentum thresholds (see DiagArgs::gthr)
 };
 
 struct DiagArgs {
@@ -138,6 +139,11 @@ struct DiagArgs {
     double pmin, pmax, pmin_log, dp_log, dmu;
     double xmin, ymin, zmin;
     double* fglobal;  // (nmu_g, npp_g) column-major
+    // gthr[k], k = 0..npp_g: the smallest double p for which the HOST libm evaluates
+    // floor((log10(p) - pmin_log)/dp_log) >= k.  Binning against these thresholds gives the
+    // bin the reference's own expression (diagnostics.f90:777) yields on this host, bit for
+    // bit, whatever the last-ulp behaviour of the device log10.
+    const double* gthr;
     HistDev loc[4];
     double* sums;                // [0] sum weight [1] sum dt
     unsigned long long* minmax;  // [0] min dt bits [1] max dt bits [2] max p bits

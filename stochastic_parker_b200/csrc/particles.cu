@@ -59,8 +59,8 @@ __global__ void inject_kernel(const __grid_constant__ DevParams prm, const PtlSo
     // particle_module.f90:491-492: past capacity every particle lands in slot nptl_max; the
     // serial loop leaves the LAST one there.
     long long slot = a.start + i;
-    if (slot >= a.nptl_max) {
-        if (i != a.n - 1) return;
+    if (a.start + a.n > a.nptl_max && slot >= a.nptl_max - 1) {
+        if (i != a.n - 1) return;  // slot nptl_max is owned by the last injected particle
         slot = a.nptl_max - 1;
     }
     InjStream s{(unsigned)(a.tag0 + i), prm.key0, prm.key1 + (unsigned)prm.mpi_rank, 0u, make_uint4(0, 0, 0, 0)};

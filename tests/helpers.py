@@ -66,3 +66,14 @@ def assert_particles_close(got, ref, rtol, what="", int_exact=True, frac_outlier
     nbad = int(bad.sum())
     assert nbad <= frac_outliers * len(got), f"{what}: {nbad}/{len(got)} particles beyond {rtol:g}; worst {worst}"
     return worst
+
+
+def assert_particles_identical(got, ref, what=""):
+    """Field-by-field bit equality (the 2 alignment bytes of the record are not data)."""
+    assert len(got) == len(ref), f"{what}: {len(got)} vs {len(ref)} particles"
+    for f in PARTICLE_DTYPE.names:
+        a, b = np.ascontiguousarray(got[f]), np.ascontiguousarray(ref[f])
+        if a.dtype.kind == "f":
+            a, b = a.view(np.uint64), b.view(np.uint64)
+        bad = np.nonzero(a != b)[0]
+        assert len(bad) == 0, f"{what}: field {f} differs at {len(bad)} particles, first {bad[:5]}: {got[f][bad[:3]]} vs {ref[f][bad[:3]]}"
