@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- pseudo-particle steps/s of the Parker-transport push on B200.
+
+One "step" of this benchmark = one MHD interval of the reference's time loop
+(stochastic-mhd.f90:397-551) for the whole particle population of a rank:
+    upload next MHD frame -> [inject] -> particle_mover -> split_particle -> diagnostics
+The headline metric counts push_particle_* calls ("pseudo-particle steps").
+
+  value  : steps/s of gpat_particle_mover alone (push kernel + both remove passes), device
+           time from CUDA events on the library's stream, inputs resident in HBM
+  e2e    : the same count over the wall time of the whole interval through the C ABI with
+           HOST buffers: H2D of the frame, gradient/pack kernel, mover, split, histograms,
+           NCCL all-reduce (N>1) and D2H of the reduced histograms
+  roofline: push kernel only: algorithmic bytes (480 B/step for 2-D Parker)
+           / push-kernel time, against the measured HBM copy bandwidth
+
+Launch: python bench.py [--gpus 1]            or
+        python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N
+`--impl reference` times the CPU restatement of the reference path (oracle/, the one place
+besides tests where it may run) on the host cores, same metric and config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ALGO_BYTES = {"L2B": 480, "L2E": 576, "L3B": 1344, "L3E": 1344 + 7 * 8 * 4 * 2}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c1", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--nptl", type=int, default=0, help="particles per GPU (0 = workload default)")
+    ap.add_argument("--grid", type=int, default=0, help="override the grid size (debug)")
+    ap.add_argument("--strict", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons during the timed region (pynvml, 100 ms period)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.ok:
+            self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def workload_setup(args):
+    from stochastic_parker_b200 import config, mhd
+    w = config.WORKLOADS[args.workload]
+    if args.grid:
+        w = w.scaled(grid=args.grid)
+    if args.nptl:
+        w.nptl = args.nptl
+        w.nptl_max = 2 * args.nptl
+    # single-GPU default populations sized so that a default run ends within minutes
+    defaults = {"c1": 1_000_000, "c2": 4_000_000, "c3": 1_000_000, "c4": 2_000_000, "c5": 2_000_000}
+    if not args.nptl:
+        w.nptl = defaults[args.workload]
+        w.nptl_max = 2 * w.nptl
+    cfg = mhd.mhd_config(w.nx, w.ny, w.nz, w.lx, w.ly, w.lz, w.dt_out, w.ndim)
+    return w, cfg
+
+
+def cpu_rate(w, P, cfg, seconds, threads_note=True):
+    """steps/s of the CPU restatement (oracle, -O3 -march=native, OpenMP over particles: one
+    particle stream per worker like the reference's ranks) on a bounded sample of the workload."""
+    from oracle import oracle as orc
+    from stochastic_parker_b200 import mhd
+    try:
+        orc.build(fast_native=True)
+    except Exception:
+        orc.build()
+    f0 = mhd.make_frame(w.kind, w.nx, w.ny, w.nz, 0, w.dt_out)
+    f1 = mhd.make_frame(w.kind, w.nx, w.ny, w.nz, 1, w.dt_out)
+    box = [cfg["xmin"], cfg["ymin"], cfg["zmin"], cfg["xmax"], cfg["ymax"], cfg["zmax"]]
+
+    def run(n):
+        o = orc.Oracle(P, max(2 * n, 16), fast=True)
+        o.upload_fields(0, f0)
+        o.upload_fields(1, f1)
+        o.inject_uniform(n, 0.0, w.dist_flag, w.particle_v0, 0.0, w.dt_out, box, w.power_index)
+        t = time.perf_counter()
+        s = o.particle_mover(0.0, w.dt_out, w.nsteps_interval, w.num_fine_steps, 0)
+        dt = time.perf_counter() - t
+        cores = o.num_threads()
+        o.close()
+        return s, dt, cores
+
+    s, dt, cores = run(512 * max(1, os.cpu_count() or 1) // 8)
+    rate = s / max(dt, 1e-9)
+    per_ptl = s / max(1, 512 * max(1, os.cpu_count() or 1) // 8)
+    n = int(max(1024, min(w.nptl, seconds * rate / max(per_ptl, 1.0))))
+    s, dt, cores = run(n)
+    return dict(value=s / dt, unit="particle-steps/s", cores=cores, kind="port",
+                sample=f"{n} particles of {w.name} pushed through one full MHD interval "
+                       f"({s} steps, {dt:.1f} s) by the C restatement of the reference path "
+                       f"(oracle/gpat_oracle.c, gcc -O3 -march=native, OpenMP)"), n
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (restated; the Fortran cannot be built here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from stochastic_parker_b200 import config
+    w, cfg = workload_setup(args)
+    P = config.build_params(w.conf_text(), cfg, w.ndim, nframes=200, cli=w.cli)
+    per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    base, n = cpu_rate(w, P, cfg, per_step)
+    # K timed steps of that bounded sample
+    from oracle import oracle as orc
+    from stochastic_parker_b200 import mhd
+    frames = [mhd.make_frame(w.kind, w.nx, w.ny, w.nz, f, w.dt_out) for f in range(2)]
+    box = [cfg["xmin"], cfg["ymin"], cfg["zmin"], cfg["xmax"], cfg["ymax"], cfg["zmax"]]
+    tot_s, tot_t = 0, 0.0
+    for it in range(args.warmup + args.steps):
+        o = orc.Oracle(P, 2 * n, fast=True)
+        o.upload_fields(0, frames[0])
+        o.upload_fields(1, frames[1])
+        o.inject_uniform(n, 0.0, w.dist_flag, w.particle_v0, 0.0, w.dt_out, box, w.power_index)
+        t = time.perf_counter()
+        s = o.particle_mover(0.0, w.dt_out, w.nsteps_interval, w.num_fine_steps, 0)
+        dt = time.perf_counter() - t
+        cores = o.num_threads()
+        o.close()
+        if it >= args.warmup:
+            tot_s += s
+            tot_t += dt
+    v = tot_s / tot_t
+    line = {
+        "impl": "reference", "metric": "pseudo-particle steps/s", "value": v, "unit": "particle-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w.name, "grid": [w.nx, w.ny, w.nz], "time_interp": 1,
+                   "particles_per_step_sample": n, "source": w.source},
+        "cpu_baseline": dict(base, value=v, cores=cores,
+                             sample=f"{n} particles x one MHD interval per step, {args.steps} steps"),
+        "e2e": {"value": v, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+
+    import stochastic_parker_b200 as spb
+    from stochastic_parker_b200 import config, mhd
+
+    w, cfg = workload_setup(args)
+    P = config.build_params(w.conf_text(), cfg, w.ndim, nframes=200, cli=w.cli, mpi_rank=rank)
+    P.strict_math = args.strict
+    sim = spb.GpatSim(P, w.nptl_max, device=local_rank)
+    if world > 1:
+        # NCCL communicator of the library (histogram all-reduce), id distributed by torch
+        obj = [sim.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        sim.comm_init(obj[0], world, rank)
+
+    nint = args.warmup + args.steps
+    shape = (w.ny + 4, w.nx + 4, 8) if w.ndim == 2 else (w.nz + 4, w.ny + 4, w.nx + 4, 8)
+    # host frames in pinned memory (what the Fortran driver's farray would be after
+    # cudaHostRegister); generated before the timed region
+    frames = []
+    for f in range(nint + 1):
+        t = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+        t.numpy()[...] = mhd.make_frame(w.kind, w.nx, w.ny, w.nz, f, w.dt_out)
+        frames.append(t)
+    tstamps = [f * w.dt_out for f in range(nint + 1)]
+    box = [P.xmin, P.ymin, P.zmin, P.xmax, P.ymax, P.zmax]
+    out = sim.alloc_diagnostics()
+    frame_bytes = frames[0].numel() * 4
+    hist_bytes = out[0].nbytes + sum(a.nbytes for a in out[1] if a is not None) + 9 * 8
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sim.upload_fields(0, frames[0].numpy())
+    sampler = None
+    tot = dict(steps=0, mover_ms=0.0, push_ms=0.0, compact_ms=0.0, upload_ms=0.0, grad_ms=0.0,
+               split_ms=0.0, diag_ms=0.0, inject_ms=0.0)
+    launches0 = 0
+    t_e2e0 = 0.0
+    per_interval = []
+    for it in range(1, nint + 1):
+        if it == args.warmup + 1:
+            barrier()
+            sampler = ClockSampler(local_rank)
+            sampler.start()
+            launches0 = sim.timings().total_launches
+            t_e2e0 = time.perf_counter()
+        sim.upload_fields(1, frames[it].numpy())
+        t0, dtf = tstamps[it - 1], tstamps[it] - tstamps[it - 1]
+        if it == 1 or w.inject_new_ptl:
+            sim.inject_uniform(w.nptl, 0.0, w.dist_flag, w.particle_v0, t0, dtf, box, w.power_index)
+        steps = sim.particle_mover(t0, dtf, w.nsteps_interval, w.num_fine_steps, 0)
+        if w.split_flag:
+            sim.split(w.split_ratio, w.pmin_split, w.nsteps_interval)
+        d = sim.diagnostics(w.local_dist, out=out)
+        sim.swap_fields()
+        tm = sim.timings()
+        per_interval.append((steps, tm.push_ms, tm.mover_ms))
+        if it > args.warmup:
+            tot["steps"] += steps
+            for k in ("mover_ms", "push_ms", "compact_ms", "upload_ms", "grad_ms", "split_ms", "diag_ms",
+                      "inject_ms"):
+                tot[k] += getattr(tm, k)
+    barrier()
+    e2e_s = time.perf_counter() - t_e2e0
+    clocks = sampler.stop() if sampler else {}
+    launches = sim.timings().total_launches - launches0
+    nptl_end = int(d["quick"][0])
+
+    # max over ranks of the device times, sum over ranks of the work
+    vec = torch.tensor([tot["mover_ms"], tot["push_ms"], e2e_s * 1e3], dtype=torch.float64, device=dev)
+    work = torch.tensor([float(tot["steps"])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vec, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    mover_ms, push_ms, e2e_ms = (float(v) for v in vec.tolist())
+    total_steps = float(work.item())
+
+    layout = {2: "L2E" if (P.dpp_wave or P.dpp_shear or P.include_3rd_dim) else "L2B",
+              3: "L3E" if (P.dpp_wave or P.dpp_shear) else "L3B"}[w.ndim]
+    peak, peak_src = measured_peaks()
+    # roofline of the push kernel on THIS rank (per launch: steps of one interval x bytes/step)
+    ach = tot["steps"] * ALGO_BYTES[layout] / (tot["push_ms"] * 1e-3) / 1e9 if tot["push_ms"] > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "push_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            with open(tpath) as f:
+                traffic = json.load(f).get(f"{args.workload}_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    line = {
+        "metric": "pseudo-particle steps/s",
+        "value": total_steps / (mover_ms * 1e-3),
+        "unit": "particle-steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": mover_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": w.name, "grid": [w.nx, w.ny, w.nz], "time_interp": int(P.time_interp),
+            "particles_per_gpu": w.nptl, "particles_per_gpu_end": nptl_end, "split": w.split_flag,
+            "field_layout": layout, "strict_math": int(args.strict),
+            "step": "one MHD interval (dt_out) of the whole population",
+            "parallelism": f"particles sharded over {world} GPU(s), full field per GPU, NCCL allreduce of histograms",
+            "l2": "field store (135 MB at 1024^2) + particle arrays exceed the 126 MB L2; frames change every step",
+            "source": w.source,
+        },
+        "e2e": {"value": total_steps / (e2e_ms * 1e-3), "unit": "particle-steps/s",
+                "h2d_bytes_per_step": frame_bytes, "d2h_bytes_per_step": hist_bytes,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                     "frac": ach / peak, "traffic": traffic, "kernel": "push_kernel",
+                     "algorithmic_bytes_per_step": ALGO_BYTES[layout], "peak_source": peak_src,
+                     "push_ms_per_launch": tot["push_ms"] / args.steps},
+        "breakdown_ms_per_step": {k: v / args.steps for k, v in tot.items() if k.endswith("_ms")},
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                base, _ = cpu_rate(w, P, cfg, args.cpu_seconds)
+                line["cpu_baseline"] = base
+            except Exception as e:  # the GPU numbers stand on their own
+                line["cpu_baseline"] = {"value": None, "unit": "particle-steps/s", "cores": 0,
+                                        "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    sim.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

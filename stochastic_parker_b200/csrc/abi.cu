@@ -217,6 +217,17 @@ void fill_dev_params(gpat_sim* h)
     d.qdrift = (double)(1.0f / (float)(3 * p.pcharge));  // FP32 quotient, particle_module.f90:3436
     d.drift1 = p.drift1; d.drift2 = p.drift2; d.tau0 = p.tau0;
     d.p0_pow = std::pow(p.p0, 2.0 - p.pindex);
+    d.idx = 1.0 / p.dx; d.idy = 1.0 / p.dy; d.idz = 1.0 / p.dz; d.ip0 = 1.0 / p.p0;
+    d.sqrt_kret = std::sqrt(p.kret);
+    d.sqrt_1mkret = std::sqrt(1.0 - p.kret);
+    d.d1p0 = p.drift1 * p.p0;
+    d.d2p02 = p.drift2 * p.p0 * p.p0;
+    {
+        double hx = 0.5 * p.dx, hy = 0.5 * p.dy, hz = 0.5 * p.dz;
+        d.hd2min2 = std::fmin(hx * hx, hy * hy);
+        d.hd2min3 = std::fmin(d.hd2min2, hz * hz);
+    }
+    d.pfloor = 0.25 * p.p0;
     for (int i = 0; i < 6; ++i) d.acc_region[i] = p.acc_region[i];
     d.momentum_dependency = p.momentum_dependency; d.mag_dependency = p.mag_dependency;
     d.acc_region_flag = p.acc_region_flag;
@@ -404,6 +415,7 @@ int run_push(gpat_sim* h, double t0, double dtf, int nsteps_interval, int num_fi
 {
     PushArgs a{};
     a.t0 = t0; a.dtf = dtf;
+    a.idtf = 1.0 / dtf;
     a.dt_fine = dtf / num_fine_steps;
     a.dt_min = h->hp.dt_min_rel * dtf;  // set_dt_min_max, particle_module.f90:5519-5524
     a.dt_max = h->hp.dt_max_rel * dtf;

@@ -95,6 +95,12 @@ struct DevParams {
     double qdrift;   // dble(1.0 / (3*pcharge)) evaluated in FP32 (particle_module.f90:3436)
     double drift1, drift2, tau0;
     double p0_pow;   // p0**(2 - pindex)
+    // reciprocals and products used by the production (non-strict) arithmetic
+    double idx, idy, idz, ip0;
+    double sqrt_kret, sqrt_1mkret;  // sqrt(kret), sqrt(1 - kret)
+    double d1p0, d2p02;             // drift1*p0, drift2*p0**2
+    double hd2min2, hd2min3;        // min((dx/2)^2,(dy/2)^2[,(dz/2)^2])
+    double pfloor;                  // 0.25*p0
     double acc_region[6];
     int momentum_dependency, mag_dependency, acc_region_flag;
     int dpp_wave, dpp_shear, weak_scattering, check_drift_2d, include_3rd_dim, nlgc;
@@ -106,6 +112,7 @@ struct DevParams {
 
 struct PushArgs {
     double t0, dtf, dt_fine, dt_min, dt_max;
+    double idtf;             // 1/dtf
     double dt_target_limit;  // dtf + dt_fine*0.1 (particle_module.f90:1596)
     int nsteps_interval;
     int debug_nsteps;        // >0: gpat_debug_push_n mode

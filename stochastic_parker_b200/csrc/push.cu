@@ -118,8 +118,13 @@ __device__ __forceinline__ void gather(const DevParams& prm, const float* __rest
     const int nfr = prm.time_interp ? 2 : 1;
     const long long stride = (long long)NREC * nfr;  // floats per grid point
 
+#if GPAT_STRICT
     double px = (x - prm.xmin) / prm.dx;
     double py = (y - prm.ymin) / prm.dy;
+#else
+    double px = (x - prm.xmin) * prm.idx;
+    double py = (y - prm.ymin) * prm.idy;
+#endif
     int ix = (int)floor(px) + 1;  // Fortran pos(1)
     int iy = (int)floor(py) + 1;
     double rx = px - (double)ix + 1.0;
@@ -134,7 +139,11 @@ __device__ __forceinline__ void gather(const DevParams& prm, const float* __rest
     if (NC == 4) {
         w[0] = rx1 * ry1; w[1] = rx * ry1; w[2] = rx1 * ry; w[3] = rx * ry;
     } else {
+#if GPAT_STRICT
         double pz = (z - prm.zmin) / prm.dz;
+#else
+        double pz = (z - prm.zmin) * prm.idz;
+#endif
         int iz = (int)floor(pz) + 1;
         double rz = pz - (double)iz + 1.0;
         double rz1 = 1.0 - rz;
@@ -515,6 +524,10 @@ __device__ __forceinline__ void push_once(const DevParams& prm, const PushArgs& 
     q.dpl = ddp;
 }
 
+#if !GPAT_STRICT
+#include "push_fast.cuh"
+#endif
+
 // ---- the kernel -------------------------------------------------------------------------
 enum : int { ST_IDLE = 0, ST_ADAPT = 1, ST_FIX = 2 };
 enum : int { AT_OUTER_HEAD = 0, AT_INNER_HEAD = 1, AFTER_FIXED_PUSH = 2 };
@@ -641,7 +654,11 @@ push_kernel(const __grid_constant__ DevParams prm, const PtlSoA P, const float* 
             }
         }
         if (state != ST_IDLE) {
+#if GPAT_STRICT
             push_once<L>(prm, a, fld, q, state == ST_FIX);
+#else
+            push_once_fast<L>(prm, a, fld, q, state == ST_FIX);
+#endif
             nsteps++;
             q.nsteps_pushed = (q.nsteps_pushed + 1) % a.nsteps_interval;  // particle_module.f90:1694
             if (a.debug_nsteps > 0)

@@ -1,0 +1,271 @@
+// push_fast.cuh -- production arithmetic of one push_particle_* call (GPAT_STRICT=0 build).
+//
+// Same physics as push_once() in push.cu (which keeps the reference's operation order for the
+// parity build), restructured for the FP64 pipe of sm_100a:
+//   * divisions by run constants (dx, dtf, p0, 3) are multiplications by reciprocals;
+//   * b, 1/b come from one rsqrt; sqrt(2 kperp) and sqrt(2(kpara-kperp)) are sqrt(2 kpara)
+//     times constants; the three sqrt(.)*sqrt(dt) products are one sqrt(2 kpara dt);
+//   * the two pow() of kappa (particle_module.f90:2242,2258) are one exp of a sum of logs;
+//   * the five dt candidates (particle_module.f90:3519-3523) need 3 divisions instead of 5;
+//   * the uniform -> [-sqrt3, sqrt3] map is a single FMA.
+// Each change moves a result by a few ulp; tests hold this build to 1e-12 per step against the
+// oracle (tests/test_gpu_parity.py::test_step_parity[0-*]).
+#pragma once
+
+template <int L>
+__device__ __forceinline__ void push_once_fast(const DevParams& prm, const PushArgs& a,
+                                               const float* __restrict__ fld, Lane& q, bool fixed_dt)
+{
+    constexpr bool D3 = (Rec<L>::NDIM == 3);
+    constexpr bool EXT = Rec<L>::EXT;
+    double F[Rec<L>::NREC];
+    const double rt = (q.t - a.t0) * a.idtf;
+    gather<L>(prm, fld, a.sel, q.x, q.y, q.z, rt, F);
+
+    // ---- uniforms -> ran1, ran2, ran3, ran_p in [-sqrt3, sqrt3] ----
+    double ran1, ran2, ran3, ranp;
+    {
+        const double sqrt3 = 1.7320508075688772;
+        if (prm.rng_mode == GPAT_RNG_TABLE) {
+            double u0 = 0.5, u1 = 0.5, u2 = 0.5, u3 = 0.5;
+            long long slot = q.tag_inj;
+            if (a.rng_table && slot >= 0 && slot < a.rng_slots && (long long)q.rng < a.rng_max_steps) {
+                const double* tb = a.rng_table + ((size_t)slot * a.rng_max_steps + q.rng) * 4;
+                u0 = tb[0]; u1 = tb[1]; u2 = tb[2]; u3 = tb[3];
+            }
+            ran1 = (2.0 * u0 - 1.0) * sqrt3; ran2 = (2.0 * u1 - 1.0) * sqrt3;
+            ran3 = (2.0 * u2 - 1.0) * sqrt3; ranp = (2.0 * u3 - 1.0) * sqrt3;
+        } else {
+            uint4 r = philox4x32_10(make_uint4((unsigned)q.rng, (unsigned)(q.rng >> 32),
+                                               (unsigned)q.tag_inj, (unsigned)q.tag_spl),
+                                    prm.key0, prm.key1 + (unsigned)q.origin);
+            const double c = 2.0 * sqrt3 / 4294967295.0;
+            ran1 = fma((double)r.x, c, -sqrt3); ran2 = fma((double)r.y, c, -sqrt3);
+            ran3 = fma((double)r.z, c, -sqrt3); ranp = fma((double)r.w, c, -sqrt3);
+        }
+        q.rng += 1;
+    }
+
+    // ---- unpack the interpolated record ----
+    double vx, vy, vz = 0.0, rho = 1.0;
+    double bx, by, bz;
+    double dbx_dx, dbx_dy, dbx_dz = 0.0, dby_dx, dby_dy, dby_dz = 0.0, dbz_dx, dbz_dy, dbz_dz = 0.0;
+    double db_dx, db_dy, db_dz = 0.0;
+    double dvx_dx, dvy_dy, dvz_dz = 0.0;
+    double dvx_dy = 0.0, dvx_dz = 0.0, dvy_dx = 0.0, dvy_dz = 0.0, dvz_dx = 0.0, dvz_dy = 0.0;
+    if constexpr (!D3) {
+        vx = F[s2::vx]; vy = F[s2::vy];
+        bx = F[s2::bx]; by = F[s2::by]; bz = F[s2::bz];
+        dbx_dx = F[s2::dbx_dx]; dbx_dy = F[s2::dbx_dy]; dby_dx = F[s2::dby_dx]; dby_dy = F[s2::dby_dy];
+        dbz_dx = F[s2::dbz_dx]; dbz_dy = F[s2::dbz_dy]; db_dx = F[s2::db_dx]; db_dy = F[s2::db_dy];
+        dvx_dx = F[s2::dvx_dx]; dvy_dy = F[s2::dvy_dy];
+        if constexpr (EXT) {
+            vz = F[s2::vz]; rho = F[s2::rho];
+            dvx_dy = F[s2::dvx_dy]; dvy_dx = F[s2::dvy_dx]; dvz_dx = F[s2::dvz_dx]; dvz_dy = F[s2::dvz_dy];
+        }
+    } else {
+        vx = F[s3::vx]; vy = F[s3::vy]; vz = F[s3::vz];
+        bx = F[s3::bx]; by = F[s3::by]; bz = F[s3::bz];
+        dbx_dx = F[s3::dbx_dx]; dbx_dy = F[s3::dbx_dy]; dbx_dz = F[s3::dbx_dz];
+        dby_dx = F[s3::dby_dx]; dby_dy = F[s3::dby_dy]; dby_dz = F[s3::dby_dz];
+        dbz_dx = F[s3::dbz_dx]; dbz_dy = F[s3::dbz_dy]; dbz_dz = F[s3::dbz_dz];
+        db_dx = F[s3::db_dx]; db_dy = F[s3::db_dy]; db_dz = F[s3::db_dz];
+        dvx_dx = F[s3::dvx_dx]; dvy_dy = F[s3::dvy_dy]; dvz_dz = F[s3::dvz_dz];
+        if constexpr (EXT) {
+            rho = F[s3::rho];
+            dvx_dy = F[s3::dvx_dy]; dvx_dz = F[s3::dvx_dz]; dvy_dx = F[s3::dvy_dx];
+            dvy_dz = F[s3::dvy_dz]; dvz_dx = F[s3::dvz_dx]; dvz_dy = F[s3::dvz_dy];
+        }
+    }
+    const bool third = D3 || (EXT && prm.include_3rd_dim);
+
+    // ---- |B|, 1/|B| from one rsqrt ----
+    const double b2 = bx * bx + by * by + bz * bz;
+    const bool tiny = b2 < kEps * kEps;             // b < EPSILON(b)
+    const double ibr = tiny ? 0.0 : rsqrt(b2);      // push_particle_*: ib = 0 for tiny b
+    const double b = b2 * ibr;
+    const double ibk = tiny ? 1.0 : ibr;            // kappa routine: ib1 = 1 for tiny b
+    const double ibk2 = ibk * ibk, ibk3 = ibk2 * ibk;
+    const double ib2 = ibr * ibr, ib3 = ib2 * ibr;
+
+    // ---- kappa_para, kappa_perp (particle_module.f90:2239-2269 / 2497-2533) ----
+    const double lb = prm.mag_dependency == 1 ? log(b) : 0.0;
+    const double lpr = log(q.p * prm.ip0);
+    double knp = 1.0, kpara, rk, srk, s1mrk;  // rk = kperp/kpara and its square roots
+    if (EXT || prm.nlgc) {
+        if (prm.mag_dependency == 1) knp = exp(prm.gm2 * lb);
+        const double pp = prm.momentum_dependency == 1 ? exp(prm.pindex * lpr) : 1.0;
+        kpara = prm.kpara0 * knp * pp;
+    } else {
+        const double e = (prm.mag_dependency == 1 ? prm.gm2 * lb : 0.0) +
+                         (prm.momentum_dependency == 1 ? prm.pindex * lpr : 0.0);
+        kpara = prm.kpara0 * exp(e);
+    }
+    if (!prm.nlgc) {
+        rk = prm.kret; srk = prm.sqrt_kret; s1mrk = prm.sqrt_1mkret;
+    } else {
+        const double e = (prm.mag_dependency == 1 ? prm.gm2_3 * lb : 0.0) +
+                         (prm.momentum_dependency == 1 ? prm.pidx_perp * lpr : 0.0);
+        const double kperp = prm.kpara0 * prm.kperp_kpara * exp(e) * q.mu * q.mu;
+        rk = kperp / kpara;
+        srk = sqrt(rk);
+        s1mrk = sqrt(1.0 - rk);
+    }
+    const double kperp = kpara * rk;
+    const double kpp = kpara - kperp;
+
+    // ---- gradients of the kappa tensor (particle_module.f90:2377-2387, 2425-2448) ----
+    double ax, ay, az = 0.0, ex, ey, ez = 0.0;  // kpp-like and kperp-like d(kappa)/dx_i factors
+    {
+        double gx = 0.0, gy = 0.0, gz = 0.0;
+        if (prm.mag_dependency == 1) {
+            // 3-D non-NLGC omits 1/B (particle_module.f90:2405-2409)
+            const double s = (D3 && !prm.nlgc) ? prm.gm2 : prm.gm2 * ibk;
+            gx = db_dx * s; gy = db_dy * s; gz = db_dz * s;
+        }
+        if (!prm.nlgc) {
+            ex = kperp * gx; ey = kperp * gy; ez = kperp * gz;
+            ax = kpp * gx; ay = kpp * gy; az = kpp * gz;
+        } else {
+            const double third_ = 1.0 / 3.0;
+            ex = kperp * gx * third_; ey = kperp * gy * third_; ez = kperp * gz * third_;
+            ax = kpara * gx - ex; ay = kpara * gy - ey; az = kpara * gz - ez;
+        }
+    }
+    const double bxn2 = bx * bx * ibk2, byn2 = by * by * ibk2, bxyn2 = bx * by * ibk2;
+    const double k2 = 2.0 * kpp * ibk3;
+    const double dkxx_dx = ex + ax * bxn2 + k2 * bx * (dbx_dx * b - bx * db_dx);
+    const double dkyy_dy = ey + ay * byn2 + k2 * by * (dby_dy * b - by * db_dy);
+    const double dkxy_dx = ax * bxyn2 + kpp * ((dbx_dx * by + bx * dby_dx) * ibk2 - 2.0 * bx * by * db_dx * ibk3);
+    const double dkxy_dy = ay * bxyn2 + kpp * ((dbx_dy * by + bx * dby_dy) * ibk2 - 2.0 * bx * by * db_dy * ibk3);
+
+    // ---- drift (particle_module.f90:3436-3446 / 4739-4741) ----
+    const double ip = 1.0 / q.p;
+    const double da = prm.d1p0 * ip, dbb = prm.d2p02 * ip * ip;
+    const double vdp = prm.qdrift * rsqrt(da * da + dbb * dbb);
+    double dx_dt, dy_dt, dz_dt, divv;
+    if (!third) {
+        const double vdx = vdp * (dbz_dy * ib2 - 2.0 * bz * db_dy * ib3);
+        const double vdy = vdp * (-dbz_dx * ib2 + 2.0 * bz * db_dx * ib3);
+        dz_dt = prm.check_drift_2d
+                    ? vdp * ((dby_dx - dbx_dy) * ib2 - 2.0 * (by * db_dx - bx * db_dy) * ib3)
+                    : 0.0;
+        dx_dt = vx + vdx + dkxx_dx + dkxy_dy;
+        dy_dt = vy + vdy + dkxy_dx + dkyy_dy;
+        divv = dvx_dx + dvy_dy;
+    } else {
+        const double vdx = vdp * ((dbz_dy - dby_dz) * ib2 - 2.0 * (bz * db_dy - by * db_dz) * ib3);
+        const double vdy = vdp * ((dbx_dz - dbz_dx) * ib2 - 2.0 * (bx * db_dz - bz * db_dx) * ib3);
+        const double vdz = vdp * ((dby_dx - dbx_dy) * ib2 - 2.0 * (by * db_dx - bx * db_dy) * ib3);
+        const double bzn2 = bz * bz * ibk2, bxzn2 = bx * bz * ibk2, byzn2 = by * bz * ibk2;
+        const double dkxz_dx = ax * bxzn2 + kpp * ((dbx_dx * bz + bx * dbz_dx) * ibk2 - 2.0 * bx * bz * db_dx * ibk3);
+        const double dkyz_dy = ay * byzn2 + kpp * ((dby_dy * bz + by * dbz_dy) * ibk2 - 2.0 * by * bz * db_dy * ibk3);
+        double dkzz_dz = 0.0, dkxz_dz = 0.0, dkyz_dz = 0.0;
+        if (D3) {  // the 2-D variant zeroes the d/dz terms (particle_module.f90:4094-4096)
+            dkzz_dz = ez + az * bzn2 + k2 * bz * (dbz_dz * b - bz * db_dz);
+            dkxz_dz = az * bxzn2 + kpp * ((dbx_dz * bz + bx * dbz_dz) * ibk2 - 2.0 * bx * bz * db_dz * ibk3);
+            dkyz_dz = az * byzn2 + kpp * ((dby_dz * bz + by * dbz_dz) * ibk2 - 2.0 * by * bz * db_dz * ibk3);
+        }
+        dx_dt = vx + vdx + dkxx_dx + dkxy_dy + dkxz_dz;
+        dy_dt = vy + vdy + dkxy_dx + dkyy_dy + dkyz_dz;
+        dz_dt = vz + vdz + dkxz_dx + dkyz_dy + dkzz_dz;
+        divv = dvx_dx + dvy_dy + dvz_dz;
+    }
+    double dp_dt = -q.p * divv * (1.0 / 3.0);
+    const double ikp = 1.0 / kpara;
+
+    // ---- momentum diffusion (particle_module.f90:2918-2979) ----
+    double dpp = 0.0;
+    if constexpr (EXT) {
+        if (prm.dpp_wave) {
+            const double va2 = b2 / rho;
+            const double pv = q.p * va2 * ikp;
+            dp_dt += (prm.momentum_dependency == 1 ? 8.0 / 27.0 : 4.0 / 9.0) * pv;
+            dpp += q.p * pv * (1.0 / 9.0);
+        }
+        if (prm.dpp_shear) {
+            const double d3 = divv * (1.0 / 3.0);
+            const double sxx = dvx_dx - d3, syy = dvy_dy - d3, szz = dvz_dz - d3;
+            const double sxy = 0.5 * (dvx_dy + dvy_dx);
+            const double sxz = third ? 0.5 * (dvx_dz + dvz_dx) : 0.0;
+            const double syz = third ? 0.5 * (dvy_dz + dvz_dy) : 0.0;
+            double gshear;
+            if (prm.weak_scattering) {
+                double bbs = sxx * bx * bx + syy * by * by + szz * bz * bz +
+                             2.0 * (sxy * bx * by + sxz * bx * bz + syz * by * bz);
+                bbs = bbs * ib2;
+                gshear = bbs * bbs * 0.2;
+            } else {
+                gshear = (2.0 / 15.0) * (sxx * sxx + syy * syy + szz * szz +
+                                         2.0 * (sxy * sxy + sxz * sxz + syz * syz));
+            }
+            if (gshear > 0.0) {
+                // p**pindex * p0**(2-pindex) = p0^2 (p/p0)**pindex
+                const double pw = prm.p0 * prm.p0 * exp(prm.pindex * lpr);
+                const double g = gshear * prm.tau0 * knp * pw;
+                dp_dt += (2.0 + prm.pindex) * g * ip;
+                dpp += g;
+            }
+        }
+    }
+
+    // ---- time step (particle_module.f90:3499-3543 / 4791-4843) ----
+    if (!fixed_dt) {
+        double d;
+        if (dx_dt != 0.0 && dy_dt != 0.0 && dp_dt != 0.0) {
+            const double s2 = 2.0 * ((rk > 0.0) ? kperp : kpara);
+            double m = fmax(dx_dt * dx_dt, dy_dt * dy_dt);
+            if (D3) m = fmax(m, dz_dt * dz_dt);  // (s/0)^2 = +Inf is ignored by min, as in the reference
+            d = fmin((D3 ? prm.hd2min3 : prm.hd2min2) * 0.5 * ikp, s2 / m);
+            d = fmin(d, (double)0.1f * q.p / fabs(dp_dt));
+        } else {
+            d = a.dt_min;
+        }
+        d = fmax(d, a.dt_min);
+        d = fmin(d, a.dt_max);
+        q.dt = d;
+    }
+
+    // ---- stochastic step ----
+    const double sA = sqrt(2.0 * kpara * q.dt);  // sqrt(2 kpara) sqrt(dt)
+    double ddx, ddy, ddz;
+    if (!third) {
+        const double sp = sA * srk, spp = sA * s1mrk * ran3 * ibr;
+        ddx = fma(dx_dt, q.dt, fma(ran1, sp, spp * bx));
+        ddy = fma(dy_dt, q.dt, fma(ran2, sp, spp * by));
+        ddz = dz_dt * q.dt;
+        q.dzl = 0.0;  // the mover's own deltaz stays 0 in plain 2-D (particle_module.f90:1564)
+    } else {
+        const double bxn = bx * ibr, byn = by * ibr, bzn = bz * ibr;
+        const double h2 = bxn * bxn + byn * byn;
+        const double ih = (h2 < kEps * kEps) ? 0.0 : rsqrt(h2);
+        const double hxy = h2 * ih;
+        const double sp = sA * srk;
+        const double t2 = sp * ih * ran2, t3 = sp * ih * ran3, t1 = sA * ran1;
+        ddx = fma(dx_dt, q.dt, bxn * t1 - bxn * bzn * t2 - byn * t3);
+        ddy = fma(dy_dt, q.dt, byn * t1 - byn * bzn * t2 + bxn * t3);
+        ddz = fma(dz_dt, q.dt, bzn * t1 + hxy * sp * ran2);
+        q.dzl = ddz;
+    }
+    q.x += ddx;
+    q.y += ddy;
+    q.z += ddz;
+    q.t += q.dt;
+    q.dxl = ddx;
+    q.dyl = ddy;
+
+    double ddp = dp_dt * q.dt;
+    if constexpr (EXT) ddp = fma(ranp, sqrt(2.0 * dpp * q.dt), ddp);
+    if (prm.acc_region_flag == 1) {
+        if (in_acc_region(prm, q)) q.p += ddp;
+        else ddp = 0.0;
+    } else {
+        q.p += ddp;
+    }
+    if (q.p < prm.pfloor) {  // particle_module.f90:3601-3605
+        q.p -= ddp;
+        ddp = prm.pfloor - q.p;
+        q.p = prm.pfloor;
+    }
+    q.dpl = ddp;
+}
