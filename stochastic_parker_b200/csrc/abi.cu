@@ -82,6 +82,7 @@ struct gpat_sim {
     cudaStream_t st = nullptr;
     int layout = L2B;
     int sel = 0;
+    int push_variant = 1;  // production kernel: lane-group gather (GPAT_PUSH_VARIANT=0: one lane per particle)
     bool have_field[2] = {false, false};
     long long nptl_max = 0;
     // particles
@@ -264,7 +265,7 @@ void carve_soa(void* mem, long long n, PtlSoA& P)
 
 size_t field_floats(const gpat_sim* h)
 {
-    return (size_t)h->dp.nxg * h->dp.nyg * h->dp.nzg * nrec_of(h->layout) * (h->dp.time_interp ? 2 : 1);
+    return (size_t)h->dp.nxg * h->dp.nyg * h->dp.nzg * nrec_of(h->layout) * 2;  // both halves, always
 }
 
 // The smallest positive double p with floor((log10(p) - pmin_log)/dp_log) >= k, found by
@@ -423,6 +424,7 @@ int run_push(gpat_sim* h, double t0, double dtf, int nsteps_interval, int num_fi
     a.nsteps_interval = nsteps_interval > 0 ? nsteps_interval : 1;
     a.debug_nsteps = debug_nsteps;
     a.sel = h->sel;
+    a.variant = h->push_variant;
     a.nptl = h->nptl_current;
     a.queue = h->d_queue;
     a.steps = h->d_queue + 1;
@@ -490,6 +492,7 @@ int gpat_init(gpat_handle* out, int device, int64_t nptl_max, const gpat_params*
     h->hp = *params;
     h->nptl_max = nptl_max;
     h->layout = pick_layout(h->hp);
+    if (const char* v = getenv("GPAT_PUSH_VARIANT")) h->push_variant = atoi(v);
     fill_dev_params(h);
     CUI(cudaMalloc(&h->ptl_mem, soa_bytes(nptl_max)));
     CUI(cudaMemsetAsync(h->ptl_mem, 0, soa_bytes(nptl_max), h->st));  // init_particles zero fill

@@ -48,7 +48,10 @@ __device__ __forceinline__ float grad_one(const float* __restrict__ src, int nva
     return __double2float_rn(__dmul_rn((double)diff, idh));
 }
 
-// One thread per grid point: fills its record (one frame half) in the packed store.
+// One thread per grid point: fills its record (one frame half) in the packed store.  A grid
+// point owns 2*nrec floats made of 32-byte chunks [4 slots of half 0 | the same 4 slots of
+// half 1] (gpat_internal.cuh "packed field record layouts"): both time frames of a slot quad
+// arrive with one 256-bit load.
 __global__ void pack_kernel(const float* __restrict__ src, int nvar, int with_grad, GridDims g,
                             SlotMap map, float* __restrict__ dst, long long stride, int half_off)
 {
@@ -72,7 +75,7 @@ __global__ void pack_kernel(const float* __restrict__ src, int nvar, int with_gr
                 }
                 v4[e] = val;
             }
-            *reinterpret_cast<float4*>(out + q) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+            *reinterpret_cast<float4*>(out + 2 * q) = make_float4(v4[0], v4[1], v4[2], v4[3]);
         }
     }
 }
@@ -99,8 +102,8 @@ void launch_pack(const float* src, int nvar, int with_grad, const DevParams& prm
     SlotMap map;
     map.nrec = nrec_of(layout);
     for (int k = 0; k < 32; ++k) map.slot[k] = (k < map.nrec) ? slot_of(layout, k) : 0;
-    const long long stride = (long long)map.nrec * (prm.time_interp ? 2 : 1);
-    const int half_off = (prm.time_interp ? half : 0) * map.nrec;
+    const long long stride = 2LL * map.nrec;
+    const int half_off = (prm.time_interp ? half : 0) * 4;
     pack_kernel<<<sm_count * 8, 256, 0, st>>>(src, nvar, with_grad, g, map, dst, stride, half_off);
 }
 

@@ -6,8 +6,11 @@
 //    upload/download boundary);
 //  * fields: one packed record per grid point holding ONLY the slots the configured
 //    pusher reads (15 of the reference's 32 for 2-D Parker), FP32 exactly as the
-//    reference stores them (mhd_data_parallel.f90:35), the two time frames of a grid
-//    point interleaved so that one 128-byte line holds both frames of a 2-D cell.
+//    reference stores them (mhd_data_parallel.f90:35).  A grid point owns 2*NREC floats
+//    made of 32-byte chunks: chunk c = [slots 4c..4c+3 of half 0 | the same slots of half 1],
+//    the two halves being the two MHD time frames (which half is farray1 flips at every
+//    gpat_swap_fields).  One 128-byte line therefore holds both frames of a 2-D Parker
+//    cell, and one 256-bit load brings both frames of four slots.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -117,6 +120,7 @@ struct PushArgs {
     int nsteps_interval;
     int debug_nsteps;        // >0: gpat_debug_push_n mode
     int sel;                 // which half of a record pair holds farray1
+    int variant;             // fast build: 0 = one lane gathers its own particle, 1 = lane groups
     long long nptl;
     unsigned long long* queue;   // work counter
     unsigned long long* steps;   // push_particle_* calls

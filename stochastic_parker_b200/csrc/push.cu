@@ -107,17 +107,21 @@ __device__ __forceinline__ void negp_or_bc(const DevParams& prm, Lane& q, double
 }
 
 // ---- gather: get_interp_paramters + interp_fields -------------------------------------
-template <int L>
-__device__ __forceinline__ void gather(const DevParams& prm, const float* __restrict__ fld,
-                                       int sel, double x, double y, double z, double rt,
-                                       double (&F)[Rec<L>::NREC])
+// 256-bit read-only load (LDG.E.256 on sm_100a): one 32-byte chunk = four slots of both frames
+__device__ __forceinline__ void ldg256(const float* __restrict__ p, float4& lo, float4& hi)
 {
-    constexpr int NREC = Rec<L>::NREC;
-    constexpr int NQ = (Rec<L>::NUSED + 3) / 4;
-    constexpr int NC = (Rec<L>::NDIM == 3) ? 8 : 4;
-    const int nfr = prm.time_interp ? 2 : 1;
-    const long long stride = (long long)NREC * nfr;  // floats per grid point
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z),
+                   "=f"(hi.w)
+                 : "l"(p));
+}
 
+// cell index + in-cell offsets of a position (get_interp_paramters, particle_module.f90:642-674);
+// the cell is clamped so that a runaway particle cannot fault.
+template <int NDIM>
+__device__ __forceinline__ long long locate(const DevParams& prm, double x, double y, double z,
+                                            double& rx, double& ry, double& rz)
+{
 #if GPAT_STRICT
     double px = (x - prm.xmin) / prm.dx;
     double py = (y - prm.ymin) / prm.dy;
@@ -127,28 +131,46 @@ __device__ __forceinline__ void gather(const DevParams& prm, const float* __rest
 #endif
     int ix = (int)floor(px) + 1;  // Fortran pos(1)
     int iy = (int)floor(py) + 1;
-    double rx = px - (double)ix + 1.0;
-    double ry = py - (double)iy + 1.0;
-    double rx1 = 1.0 - rx, ry1 = 1.0 - ry;
-    // Fortran index -> storage index is +1; clamp so a runaway particle cannot fault
+    rx = px - (double)ix + 1.0;
+    ry = py - (double)iy + 1.0;
+    // Fortran index -> storage index is +1 (lower bound -1, mhd_data_parallel.f90:82)
     int cx = min(max(ix + 1, 0), prm.nxg - 2);
     int cy = min(max(iy + 1, 0), prm.nyg - 2);
     long long cell = (long long)cy * prm.nxg + cx;
-    double w[NC];
-    long long off[NC];
-    if (NC == 4) {
-        w[0] = rx1 * ry1; w[1] = rx * ry1; w[2] = rx1 * ry; w[3] = rx * ry;
-    } else {
+    rz = 0.0;
+    if (NDIM == 3) {
 #if GPAT_STRICT
         double pz = (z - prm.zmin) / prm.dz;
 #else
         double pz = (z - prm.zmin) * prm.idz;
 #endif
         int iz = (int)floor(pz) + 1;
-        double rz = pz - (double)iz + 1.0;
-        double rz1 = 1.0 - rz;
+        rz = pz - (double)iz + 1.0;
         int cz = min(max(iz + 1, 0), prm.nzg - 2);
         cell += (long long)cz * prm.nxg * prm.nyg;
+    }
+    return cell;
+}
+
+template <int L>
+__device__ __forceinline__ void gather(const DevParams& prm, const float* __restrict__ fld,
+                                       int sel, double x, double y, double z, double rt,
+                                       double (&F)[Rec<L>::NREC])
+{
+    constexpr int NREC = Rec<L>::NREC;
+    constexpr int NQ = (Rec<L>::NUSED + 3) / 4;
+    constexpr int NC = (Rec<L>::NDIM == 3) ? 8 : 4;
+    constexpr long long stride = 2LL * NREC;  // floats per grid point (both halves)
+
+    double rx, ry, rz;
+    const long long cell = locate<Rec<L>::NDIM>(prm, x, y, z, rx, ry, rz);
+    const double rx1 = 1.0 - rx, ry1 = 1.0 - ry;
+    double w[NC];
+    long long off[NC];
+    if (NC == 4) {
+        w[0] = rx1 * ry1; w[1] = rx * ry1; w[2] = rx1 * ry; w[3] = rx * ry;
+    } else {
+        const double rz1 = 1.0 - rz;
         w[0] = rx1 * ry1 * rz1; w[1] = rx * ry1 * rz1; w[2] = rx1 * ry * rz1; w[3] = rx * ry * rz1;
         w[4] = rx1 * ry1 * rz;  w[5] = rx * ry1 * rz;  w[6] = rx1 * ry * rz;  w[7] = rx * ry * rz;
     }
@@ -156,22 +178,22 @@ __device__ __forceinline__ void gather(const DevParams& prm, const float* __rest
     for (int c = 0; c < NC; ++c)
         off[c] = (cell + (c & 1) + (long long)((c >> 1) & 1) * prm.nxg +
                   (long long)(c >> 2) * prm.nxg * prm.nyg) * stride;
-    const int hA = (prm.time_interp ? sel : 0) * NREC;
-    const int hB = (sel ^ 1) * NREC;
 
 #if GPAT_STRICT
     // reference order: per frame, sum over corners starting from 0, then blend
+    const int hA = (prm.time_interp ? sel : 0) * 4;
+    const int hB = (sel ^ 1) * 4;
     const double rt1 = 1.0 - rt;
 #pragma unroll
     for (int qd = 0; qd < NQ; ++qd) {
         double a[4] = {0.0, 0.0, 0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-            float4 fa = __ldg(reinterpret_cast<const float4*>(fld + off[c] + hA) + qd);
+            float4 fa = __ldg(reinterpret_cast<const float4*>(fld + off[c] + 8 * qd + hA));
             a[0] = a[0] + (double)fa.x * w[c]; a[1] = a[1] + (double)fa.y * w[c];
             a[2] = a[2] + (double)fa.z * w[c]; a[3] = a[3] + (double)fa.w * w[c];
             if (prm.time_interp) {
-                float4 fb = __ldg(reinterpret_cast<const float4*>(fld + off[c] + hB) + qd);
+                float4 fb = __ldg(reinterpret_cast<const float4*>(fld + off[c] + 8 * qd + hB));
                 b[0] = b[0] + (double)fb.x * w[c]; b[1] = b[1] + (double)fb.y * w[c];
                 b[2] = b[2] + (double)fb.z * w[c]; b[3] = b[3] + (double)fb.w * w[c];
             }
@@ -181,27 +203,27 @@ __device__ __forceinline__ void gather(const DevParams& prm, const float* __rest
             F[4 * qd + e] = prm.time_interp ? (a[e] * rt1 + b[e] * rt) : a[e];
     }
 #else
-    // fast: fold the time blend into the corner weights, one FMA per loaded value
-    double wa[NC], wb[NC];
-    const double rt1 = 1.0 - rt;
+    // fast: fold the time blend into the corner weights, one FMA per loaded value; w0/w1 are the
+    // weights of half 0 / half 1 of each chunk
+    double w0[NC], w1[NC];
+    {
+        const double rt1 = 1.0 - rt;
+        const double tA = prm.time_interp ? rt1 : 1.0, tB = prm.time_interp ? rt : 0.0;
+        const double t0 = (sel == 0) ? tA : tB, t1 = (sel == 0) ? tB : tA;
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        wa[c] = prm.time_interp ? w[c] * rt1 : w[c];
-        wb[c] = w[c] * rt;
+        for (int c = 0; c < NC; ++c) { w0[c] = w[c] * t0; w1[c] = w[c] * t1; }
     }
 #pragma unroll
     for (int qd = 0; qd < NQ; ++qd) {
         double a[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-            float4 fa = __ldg(reinterpret_cast<const float4*>(fld + off[c] + hA) + qd);
-            a[0] = fma((double)fa.x, wa[c], a[0]); a[1] = fma((double)fa.y, wa[c], a[1]);
-            a[2] = fma((double)fa.z, wa[c], a[2]); a[3] = fma((double)fa.w, wa[c], a[3]);
-            if (prm.time_interp) {
-                float4 fb = __ldg(reinterpret_cast<const float4*>(fld + off[c] + hB) + qd);
-                a[0] = fma((double)fb.x, wb[c], a[0]); a[1] = fma((double)fb.y, wb[c], a[1]);
-                a[2] = fma((double)fb.z, wb[c], a[2]); a[3] = fma((double)fb.w, wb[c], a[3]);
-            }
+            float4 f0, f1;
+            ldg256(fld + off[c] + 8 * qd, f0, f1);
+            a[0] = fma((double)f0.x, w0[c], a[0]); a[1] = fma((double)f0.y, w0[c], a[1]);
+            a[2] = fma((double)f0.z, w0[c], a[2]); a[3] = fma((double)f0.w, w0[c], a[3]);
+            a[0] = fma((double)f1.x, w1[c], a[0]); a[1] = fma((double)f1.y, w1[c], a[1]);
+            a[2] = fma((double)f1.z, w1[c], a[2]); a[3] = fma((double)f1.w, w1[c], a[3]);
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) F[4 * qd + e] = a[e];
@@ -573,6 +595,80 @@ __device__ __forceinline__ int next_state(const DevParams& prm, const PushArgs& 
     }
 }
 
+// particle record -> lane registers, and the initial state of its loop nest
+// (particle_module.f90:1561-1592)
+__device__ __forceinline__ int load_lane(const DevParams& prm, const PushArgs& a, const PtlSoA& P,
+                                         long long idx, Lane& q, int& remaining)
+{
+    q.x = P.x[idx]; q.y = P.y[idx]; q.z = P.z[idx]; q.p = P.p[idx];
+    q.t = P.t[idx]; q.dt = P.dt[idx]; q.weight = P.weight[idx]; q.mu = P.mu[idx];
+    q.rng = P.rng[idx]; q.tag_inj = P.tag_injected[idx];
+    q.tag_spl = P.tag_splitted[idx]; q.origin = P.origin[idx];
+    q.nsteps_pushed = P.nsteps_pushed[idx]; q.count_flag = P.count_flag[idx];
+    q.dxl = q.dyl = q.dzl = q.dpl = 0.0;
+    q.dt_old = q.dt;
+    if (a.debug_nsteps > 0) {
+        remaining = a.debug_nsteps;
+        q.dt_target = a.dtf;
+        return (q.count_flag == GPAT_COUNT_FLAG_INBOX) ? ST_ADAPT : ST_IDLE;
+    }
+    // target time of the first fine step, particle_module.f90:1570-1578
+    int step = (int)ceil((q.t - a.t0) / a.dt_fine);
+    q.dt_target = (step <= 0) ? a.dt_fine : step * a.dt_fine;
+    if (q.dt_target > a.dtf) q.dt_target = a.dtf;
+    // safe check, particle_module.f90:1581-1592
+    if (q.p < 0.0 && q.count_flag == GPAT_COUNT_FLAG_INBOX) {
+        q.count_flag = GPAT_COUNT_FLAG_OTHERS;
+        atomicAdd(a.leak + 1, q.weight);
+    } else {
+        boundary(prm, q, prm.ext, a.leak);
+    }
+    return (q.count_flag == GPAT_COUNT_FLAG_INBOX) ? next_state(prm, a, q, AT_OUTER_HEAD) : ST_IDLE;
+}
+
+__device__ __forceinline__ void store_lane(const PushArgs& a, const PtlSoA& P, long long idx,
+                                           const Lane& q)
+{
+    P.x[idx] = q.x; P.y[idx] = q.y; P.z[idx] = q.z; P.p[idx] = q.p;
+    P.t[idx] = q.t; P.dt[idx] = q.dt; P.rng[idx] = q.rng;
+    P.nsteps_pushed[idx] = q.nsteps_pushed;
+    P.count_flag[idx] = (signed char)q.count_flag;
+    if (a.debug_nsteps == 0) P.nsteps_tracked[idx] = 1;  // particle_module.f90:1913
+}
+
+// idle lanes take the next particles of the work counter (one warp-aggregated atomic)
+__device__ __forceinline__ void refill(const DevParams& prm, const PushArgs& a, const PtlSoA& P,
+                                       unsigned lane, Lane& q, int& state, long long& idx,
+                                       bool& exhausted, int& remaining)
+{
+    __syncwarp();
+    const bool want = (state == ST_IDLE) && !exhausted;
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (!m) return;
+    unsigned long long base = 0;
+    const int leader = __ffs(m) - 1;
+    if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (want) {
+        idx = (long long)(base + __popc(m & ((1u << lane) - 1u)));
+        if (idx >= a.nptl) {
+            exhausted = true;
+        } else {
+            state = load_lane(prm, a, P, idx, q, remaining);
+            if (state == ST_IDLE) store_lane(a, P, idx, q);
+        }
+    }
+}
+
+// after one push_particle_* call: step counter, next state (particle_module.f90:1694-1704)
+__device__ __forceinline__ int after_push(const DevParams& prm, const PushArgs& a, Lane& q, int state,
+                                          int& remaining)
+{
+    q.nsteps_pushed = (q.nsteps_pushed + 1) % a.nsteps_interval;  // particle_module.f90:1694
+    if (a.debug_nsteps > 0) return (--remaining == 0) ? ST_IDLE : ST_ADAPT;
+    return next_state(prm, a, q, state == ST_FIX ? AFTER_FIXED_PUSH : AT_INNER_HEAD);
+}
+
 template <int L>
 __global__ void __launch_bounds__(kBlock)
 push_kernel(const __grid_constant__ DevParams prm, const PtlSoA P, const float* __restrict__ fld,
@@ -586,60 +682,8 @@ push_kernel(const __grid_constant__ DevParams prm, const PtlSoA P, const float* 
     int remaining = 0;
     unsigned long long nsteps = 0;
 
-    auto store = [&]() {
-        P.x[idx] = q.x; P.y[idx] = q.y; P.z[idx] = q.z; P.p[idx] = q.p;
-        P.t[idx] = q.t; P.dt[idx] = q.dt; P.rng[idx] = q.rng;
-        P.nsteps_pushed[idx] = q.nsteps_pushed;
-        P.count_flag[idx] = (signed char)q.count_flag;
-        if (a.debug_nsteps == 0) P.nsteps_tracked[idx] = 1;  // particle_module.f90:1913
-    };
-
     for (;;) {
-        // ---- refill idle lanes from the work counter (warp-aggregated atomic) ----
-        __syncwarp();
-        const bool want = (state == ST_IDLE) && !exhausted;
-        const unsigned m = __ballot_sync(0xffffffffu, want);
-        if (m) {
-            unsigned long long base = 0;
-            const int leader = __ffs(m) - 1;
-            if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (want) {
-                idx = (long long)(base + __popc(m & ((1u << lane) - 1u)));
-                if (idx >= a.nptl) {
-                    exhausted = true;
-                } else {
-                    q.x = P.x[idx]; q.y = P.y[idx]; q.z = P.z[idx]; q.p = P.p[idx];
-                    q.t = P.t[idx]; q.dt = P.dt[idx]; q.weight = P.weight[idx]; q.mu = P.mu[idx];
-                    q.rng = P.rng[idx]; q.tag_inj = P.tag_injected[idx];
-                    q.tag_spl = P.tag_splitted[idx]; q.origin = P.origin[idx];
-                    q.nsteps_pushed = P.nsteps_pushed[idx]; q.count_flag = P.count_flag[idx];
-                    q.dxl = q.dyl = q.dzl = q.dpl = 0.0;
-                    q.dt_old = q.dt;
-                    if (a.debug_nsteps > 0) {
-                        remaining = a.debug_nsteps;
-                        q.dt_target = a.dtf;
-                        state = (q.count_flag == GPAT_COUNT_FLAG_INBOX) ? ST_ADAPT : ST_IDLE;
-                    } else {
-                        // target time of the first fine step, particle_module.f90:1570-1578
-                        int step = (int)ceil((q.t - a.t0) / a.dt_fine);
-                        q.dt_target = (step <= 0) ? a.dt_fine : step * a.dt_fine;
-                        if (q.dt_target > a.dtf) q.dt_target = a.dtf;
-                        // safe check, particle_module.f90:1581-1592
-                        if (q.p < 0.0 && q.count_flag == GPAT_COUNT_FLAG_INBOX) {
-                            q.count_flag = GPAT_COUNT_FLAG_OTHERS;
-                            atomicAdd(a.leak + 1, q.weight);
-                        } else {
-                            boundary(prm, q, prm.ext, a.leak);
-                        }
-                        state = (q.count_flag == GPAT_COUNT_FLAG_INBOX)
-                                    ? next_state(prm, a, q, AT_OUTER_HEAD)
-                                    : ST_IDLE;
-                        if (state == ST_IDLE) store();
-                    }
-                }
-            }
-        }
+        refill(prm, a, P, lane, q, state, idx, exhausted, remaining);
         if (__all_sync(0xffffffffu, state == ST_IDLE)) {
             if (__all_sync(0xffffffffu, exhausted)) break;
             continue;
@@ -649,7 +693,7 @@ push_kernel(const __grid_constant__ DevParams prm, const PtlSoA P, const float* 
         if (state == ST_ADAPT) {  // top of the inner while body, particle_module.f90:1602-1612
             negp_or_bc(prm, q, a.leak);
             if (q.count_flag != GPAT_COUNT_FLAG_INBOX) {
-                store();
+                store_lane(a, P, idx, q);
                 state = ST_IDLE;
             }
         }
@@ -660,12 +704,8 @@ push_kernel(const __grid_constant__ DevParams prm, const PtlSoA P, const float* 
             push_once_fast<L>(prm, a, fld, q, state == ST_FIX);
 #endif
             nsteps++;
-            q.nsteps_pushed = (q.nsteps_pushed + 1) % a.nsteps_interval;  // particle_module.f90:1694
-            if (a.debug_nsteps > 0)
-                state = (--remaining == 0) ? ST_IDLE : ST_ADAPT;
-            else
-                state = next_state(prm, a, q, state == ST_FIX ? AFTER_FIXED_PUSH : AT_INNER_HEAD);
-            if (state == ST_IDLE) store();
+            state = after_push(prm, a, q, state, remaining);
+            if (state == ST_IDLE) store_lane(a, P, idx, q);
         }
     }
     // warp-aggregated step count
@@ -673,6 +713,160 @@ push_kernel(const __grid_constant__ DevParams prm, const PtlSoA P, const float* 
     for (int o = 16; o > 0; o >>= 1) nsteps += __shfl_down_sync(0xffffffffu, nsteps, o);
     if (lane == 0 && nsteps) atomicAdd(a.steps, nsteps);
 }
+
+#if !GPAT_STRICT
+// ---- lane-group gather ---------------------------------------------------------------------
+// A lane that gathers its own particle touches 32 different 128-byte lines per warp load
+// instruction, and the L1 data pipe spends one wavefront per line: that pipe, not HBM or L2,
+// bounds the one-lane-per-particle kernel (profiles/r01a_push_kernel.md).  Here G lanes read
+// ONE particle's line together (G x 32 contiguous bytes per corner), so a warp-wide load touches
+// 32/G lines; the G particles of a group are served in G rounds and every lane ends a round
+// with final values of the slots of its chunks, parked in shared memory for the owner lane.
+template <int L> struct Coop {
+    static constexpr int NREC = Rec<L>::NREC;
+    static constexpr int NCH = NREC / 4;                          // 32-byte chunks per grid point
+    static constexpr int G = (NCH == 4 || NCH == 8) ? 4 : 2;      // lanes per particle
+    static constexpr int CPL = NCH / G;                           // chunks per lane
+    static constexpr int NC = (Rec<L>::NDIM == 3) ? 8 : 4;
+    static constexpr int ROW = NREC + 2;                          // doubles per result row (+16 B: bank skew)
+    static constexpr int PAR = 6;                                 // doubles per parameter row (48 B)
+};
+
+template <int L>
+__global__ void __launch_bounds__(kBlock)
+push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
+                 const float* __restrict__ fld, const __grid_constant__ PushArgs a)
+{
+    using C = Coop<L>;
+    constexpr int NW = kBlock / 32;
+    __shared__ __align__(16) double sm_par[NW][32 * C::PAR];
+    __shared__ __align__(16) double sm_res[NW][32 * C::ROW];
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned wid = threadIdx.x >> 5;
+    double* const par = sm_par[wid];
+    double* const res = sm_res[wid];
+    const int gq = (int)(lane & (C::G - 1));
+    const int gbase = (int)(lane & ~(unsigned)(C::G - 1));
+    constexpr long long stride = 2LL * C::NREC;
+
+    Lane q;
+    int state = ST_IDLE;
+    long long idx = -1;
+    bool exhausted = false;
+    int remaining = 0;
+    unsigned long long nsteps = 0;
+
+    for (;;) {
+        refill(prm, a, P, lane, q, state, idx, exhausted, remaining);
+        if (__all_sync(0xffffffffu, state == ST_IDLE)) {
+            if (__all_sync(0xffffffffu, exhausted)) break;
+            continue;
+        }
+        if (state == ST_ADAPT) {  // top of the inner while body, particle_module.f90:1602-1612
+            negp_or_bc(prm, q, a.leak);
+            if (q.count_flag != GPAT_COUNT_FLAG_INBOX) {
+                store_lane(a, P, idx, q);
+                state = ST_IDLE;
+            }
+        }
+
+        // ---- phase A: every lane publishes where its particle is ----
+        {
+            double rx = 0.0, ry = 0.0, rz = 0.0, rt = 0.0;
+            long long cell = 0;
+            if (state != ST_IDLE) {
+                cell = locate<Rec<L>::NDIM>(prm, q.x, q.y, q.z, rx, ry, rz);
+                rt = (q.t - a.t0) * a.idtf;
+            }
+            double2* row = reinterpret_cast<double2*>(par + lane * C::PAR);
+            row[0] = make_double2(rx, ry);
+            row[1] = make_double2(rz, rt);
+            row[2] = make_double2(__longlong_as_double(cell), 0.0);
+        }
+        __syncwarp();
+
+        // ---- phase B: G rounds, one particle of the group per round ----
+#pragma unroll
+        for (int r = 0; r < C::G; ++r) {
+            const int owner = gbase + r;
+            const double2* row = reinterpret_cast<const double2*>(par + owner * C::PAR);
+            const double2 pa = row[0], pb = row[1], pc = row[2];
+            const double rx = pa.x, ry = pa.y, rz = pb.x, rt = pb.y;
+            const long long cell = __double_as_longlong(pc.x);
+            // weights of half 0 / half 1 at each corner (time blend folded in)
+            double w0[C::NC], w1[C::NC];
+            {
+                const double rt1 = 1.0 - rt;
+                const double tA = prm.time_interp ? rt1 : 1.0, tB = prm.time_interp ? rt : 0.0;
+                const double t0 = (a.sel == 0) ? tA : tB, t1 = (a.sel == 0) ? tB : tA;
+                const double rx1 = 1.0 - rx, ry1 = 1.0 - ry;
+                if (C::NC == 4) {
+                    const double a0 = ry1 * t0, b0 = ry * t0, a1 = ry1 * t1, b1 = ry * t1;
+                    w0[0] = rx1 * a0; w0[1] = rx * a0; w0[2] = rx1 * b0; w0[3] = rx * b0;
+                    w1[0] = rx1 * a1; w1[1] = rx * a1; w1[2] = rx1 * b1; w1[3] = rx * b1;
+                } else {
+                    const double rz1 = 1.0 - rz;
+                    const double wxy[4] = {rx1 * ry1, rx * ry1, rx1 * ry, rx * ry};
+                    const double z00 = rz1 * t0, z10 = rz * t0, z01 = rz1 * t1, z11 = rz * t1;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        w0[c] = wxy[c] * z00; w0[c + 4] = wxy[c] * z10;
+                        w1[c] = wxy[c] * z01; w1[c + 4] = wxy[c] * z11;
+                    }
+                }
+            }
+            double acc[C::CPL][4];
+#pragma unroll
+            for (int j = 0; j < C::CPL; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
+            const float* base = fld + cell * stride + (gq * C::CPL) * 8;
+#pragma unroll
+            for (int c = 0; c < C::NC; ++c) {
+                const float* pc_ = base + ((c & 1) + (long long)((c >> 1) & 1) * prm.nxg +
+                                           (long long)(c >> 2) * prm.nxg * prm.nyg) * stride;
+#pragma unroll
+                for (int j = 0; j < C::CPL; ++j) {
+                    float4 f0, f1;
+                    ldg256(pc_ + 8 * j, f0, f1);
+                    acc[j][0] = fma((double)f0.x, w0[c], acc[j][0]);
+                    acc[j][1] = fma((double)f0.y, w0[c], acc[j][1]);
+                    acc[j][2] = fma((double)f0.z, w0[c], acc[j][2]);
+                    acc[j][3] = fma((double)f0.w, w0[c], acc[j][3]);
+                    acc[j][0] = fma((double)f1.x, w1[c], acc[j][0]);
+                    acc[j][1] = fma((double)f1.y, w1[c], acc[j][1]);
+                    acc[j][2] = fma((double)f1.z, w1[c], acc[j][2]);
+                    acc[j][3] = fma((double)f1.w, w1[c], acc[j][3]);
+                }
+            }
+            double2* out = reinterpret_cast<double2*>(res + owner * C::ROW + (gq * C::CPL) * 4);
+#pragma unroll
+            for (int j = 0; j < C::CPL; ++j) {
+                out[2 * j] = make_double2(acc[j][0], acc[j][1]);
+                out[2 * j + 1] = make_double2(acc[j][2], acc[j][3]);
+            }
+        }
+        __syncwarp();
+
+        // ---- phase C: the owner lane finishes its push ----
+        if (state != ST_IDLE) {
+            double F[C::NREC];
+            const double2* row = reinterpret_cast<const double2*>(res + lane * C::ROW);
+#pragma unroll
+            for (int k = 0; k < C::NREC / 2; ++k) {
+                const double2 v = row[k];
+                F[2 * k] = v.x;
+                F[2 * k + 1] = v.y;
+            }
+            physics_fast<L>(prm, a, F, q, state == ST_FIX);
+            nsteps++;
+            state = after_push(prm, a, q, state, remaining);
+            if (state == ST_IDLE) store_lane(a, P, idx, q);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nsteps += __shfl_down_sync(0xffffffffu, nsteps, o);
+    if (lane == 0 && nsteps) atomicAdd(a.steps, nsteps);
+}
+#endif
 
 // debug: interpolated fields in the reference's 32-slot order
 template <int L>
@@ -699,6 +893,16 @@ void launch_one(const DevParams& prm, const PtlSoA& P, const float* fld, const P
     long long want = (a.nptl + kBlock - 1) / kBlock;
     long long grid = (long long)sm_count * per_sm;  // persistent: a multiple of the SM count
     if (want < grid) grid = want > 0 ? want : 1;
+#if !GPAT_STRICT
+    if (a.variant == 1) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel_coop<L>, kBlock, 0);
+        if (per_sm < 1) per_sm = 1;
+        grid = (long long)sm_count * per_sm;
+        if (want < grid) grid = want > 0 ? want : 1;
+        push_kernel_coop<L><<<(unsigned)grid, kBlock, 0, st>>>(prm, P, fld, a);
+        return;
+    }
+#endif
     push_kernel<L><<<(unsigned)grid, kBlock, 0, st>>>(prm, P, fld, a);
 }
 

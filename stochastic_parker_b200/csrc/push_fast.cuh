@@ -12,15 +12,14 @@
 // oracle (tests/test_gpu_parity.py::test_step_parity[0-*]).
 #pragma once
 
-template <int L>
-__device__ __forceinline__ void push_once_fast(const DevParams& prm, const PushArgs& a,
-                                               const float* __restrict__ fld, Lane& q, bool fixed_dt)
+// F: the interpolated record of this particle (registers, or a shared-memory row written by
+// the lane group that gathered it)
+template <int L, typename FT>
+__device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArgs& a,
+                                             const FT& F, Lane& q, bool fixed_dt)
 {
     constexpr bool D3 = (Rec<L>::NDIM == 3);
     constexpr bool EXT = Rec<L>::EXT;
-    double F[Rec<L>::NREC];
-    const double rt = (q.t - a.t0) * a.idtf;
-    gather<L>(prm, fld, a.sel, q.x, q.y, q.z, rt, F);
 
     // ---- uniforms -> ran1, ran2, ran3, ran_p in [-sqrt3, sqrt3] ----
     double ran1, ran2, ran3, ranp;
@@ -268,4 +267,14 @@ __device__ __forceinline__ void push_once_fast(const DevParams& prm, const PushA
         q.p = prm.pfloor;
     }
     q.dpl = ddp;
+}
+
+template <int L>
+__device__ __forceinline__ void push_once_fast(const DevParams& prm, const PushArgs& a,
+                                               const float* __restrict__ fld, Lane& q, bool fixed_dt)
+{
+    double F[Rec<L>::NREC];
+    const double rt = (q.t - a.t0) * a.idtf;
+    gather<L>(prm, fld, a.sel, q.x, q.y, q.z, rt, F);
+    physics_fast<L>(prm, a, F, q, fixed_dt);
 }

@@ -1,0 +1,318 @@
+"""CPU tests of the oracle (oracle/gpat_oracle.c): the checker itself must be trustworthy.
+
+The reference ships NO golden vectors for the particle path, so the
+oracle is pinned here by what can be pinned without the Fortran binary:
+  * the published Philox4x32-10 known-answer vectors (Random123 kat_vectors),
+  * a second, independent restatement of the 2-D step in numpy (oracle/np_step.py),
+  * closed-form properties of the algorithm (exact interpolation/gradients of linear fields,
+    variance 2*kappa*t of the stochastic step, dyadic split weights, histogram identities),
+  * the reference's own Python-side files (tests/golden/, generated from /root/reference by
+    tests/golden/make_golden.py).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_particles_close, assert_particles_identical, box_of, make_case, rel_err, sort_by_key
+from oracle import np_step
+from oracle.oracle import Oracle, philox4x32_10
+from stochastic_parker_b200 import run_intervals
+from stochastic_parker_b200.abi import PARTICLE_DTYPE, RNG_TABLE, rng_steps
+
+
+# ---- RNG -----------------------------------------------------------------------------------
+# Random123 kat_vectors, "philox4x32 10" lines (counter, key -> output)
+PHILOX_KAT = [
+    ((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+    ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+    ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+     (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+]
+
+
+@pytest.mark.parametrize("ctr,key,want", PHILOX_KAT)
+def test_philox_known_answers(ctr, key, want):
+    assert tuple(philox4x32_10(ctr, key)) == want
+
+
+def test_injection_uses_documented_philox_stream():
+    """inject_one_particle draws x, y, z, mu, t in that order (particle_module.f90:401-436)
+    from counter (0xFFFFFFFF.., tag) blocks; here: positions are uniform in the box, mu in
+    [-mu_max, mu_max] with mu_max = dble(0.99f), t in the frame, and two ranks never share a
+    stream (the key carries `origin`)."""
+    w, P, frames, _ = make_case("c1", grid=32, nptl=4000)
+    o = Oracle(P, 8000)
+    o.inject_uniform(4000, 1e-5, 1, w.particle_v0, 0.3, 0.1, box_of(P), 6.2)
+    a = o.download_particles()
+    assert len(a) == 4000
+    assert a["x"].min() >= P.xmin and a["x"].max() <= P.xmax
+    assert a["y"].min() >= P.ymin and a["y"].max() <= P.ymax
+    assert np.all(np.abs(a["mu"]) <= float(np.float32(0.99)))
+    assert np.all((a["t"] >= 0.3) & (a["t"] <= 0.4))
+    assert np.all(a["p"] == P.p0) and np.all(a["weight"] == 1.0) and np.all(a["dt"] == 1e-5)
+    assert np.array_equal(a["tag_injected"], np.arange(4000)) and np.all(a["tag_splitted"] == 1)
+    assert abs(a["x"].mean() - 0.5 * (P.xmin + P.xmax)) < 5 * P.lx / np.sqrt(12 * 4000)
+    P2 = P.copy()
+    P2.mpi_rank = 1
+    o2 = Oracle(P2, 8000)
+    o2.inject_uniform(4000, 1e-5, 1, w.particle_v0, 0.3, 0.1, box_of(P), 6.2)
+    b = o2.download_particles()
+    assert np.all(b["origin"] == 1) and not np.any(a["x"] == b["x"])
+
+
+# ---- gradients and interpolation ---------------------------------------------------------------
+def _linear_frame(nx, ny, coef):
+    """8-variable frame whose variable v is a0 + ax*i + ay*j on storage indices (exact in FP32)."""
+    j, i = np.meshgrid(np.arange(ny + 4), np.arange(nx + 4), indexing="ij")
+    f = np.zeros((ny + 4, nx + 4, 8), dtype=np.float32)
+    for v, (a0, ax, ay) in enumerate(coef):
+        f[..., v] = a0 + ax * i + ay * j
+    return f
+
+
+def test_gradients_of_linear_fields_are_exact():
+    """calc_fields_gradients (mhd_data_parallel.f90:533-566): centred and one-sided 3-point
+    differences are exact for linear data, including the ghost edges."""
+    w, P, _, _ = make_case("c1", grid=16, nptl=8)
+    coef = [(1.0, 0.5, -0.25), (0.0, 2.0, 1.0), (3.0, 0.0, 0.0), (1.0, 0.125, 0.0),
+            (-2.0, 1.0, 1.0), (0.5, -1.0, 2.0), (0.25, 0.0, -0.5), (4.0, 0.75, 0.25)]
+    f = _linear_frame(P.nx, P.ny, coef)
+    o = Oracle(P, 16)
+    o.upload_fields(0, f)
+    g = o.get_fields(0)[0]  # (ny+4, nx+4, 32)
+    for v, (_, ax, ay) in enumerate(coef):
+        assert np.all(g[..., 8 + 3 * v + 0] == np.float32(ax * 0.5 / P.dx * 2.0))
+        assert np.all(g[..., 8 + 3 * v + 1] == np.float32(ay * 0.5 / P.dy * 2.0))
+        assert np.all(g[..., 8 + 3 * v + 2] == 0.0)  # unresolved z in 2-D
+
+
+def test_gradients_match_numpy_restatement():
+    w, P, frames, _ = make_case("c1", grid=24, nptl=8)
+    o = Oracle(P, 16)
+    o.upload_fields(0, frames[0])
+    got = o.get_fields(0)[0]
+    ref = np_step.gradients32(frames[0], P.dx, P.dy)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+def test_interp_is_exact_for_bilinear_data_and_blends_in_time():
+    """interp_fields (mhd_data_parallel.f90:1751-1793): bilinear weights reproduce a linear
+    field, and the time blend is fields*(1-rt) + fields2*rt."""
+    w, P, _, _ = make_case("c1", grid=16, nptl=8)
+    coef = [(1.0, 0.5, -0.25)] * 8
+    f0 = _linear_frame(P.nx, P.ny, coef)
+    f1 = (3.0 * f0).astype(np.float32)
+    o = Oracle(P, 16)
+    o.upload_fields(0, f0)
+    o.upload_fields(1, f1)
+    rng = np.random.default_rng(0)
+    n = 500
+    x = rng.uniform(P.xmin, P.xmax, n)
+    y = rng.uniform(P.ymin, P.ymax, n)
+    rt = rng.uniform(0, 1, n)
+    F = o.interp(x, y, np.zeros(n), rt)
+    # storage index of a position: i = (x - xmin)/dx + 2 (Fortran index floor(px)+1, lower bound -1)
+    exact = 1.0 + 0.5 * ((x - P.xmin) / P.dx + 2) - 0.25 * ((y - P.ymin) / P.dy + 2)
+    assert np.max(np.abs(F[:, 0] - exact * (1 + 2 * rt))) < 1e-12
+    # against the independent numpy restatement, all 32 slots
+    fa1, fa2 = np_step.gradients32(f0, P.dx, P.dy), np_step.gradients32(f1, P.dx, P.dy)
+    ref = np_step.interp32(fa1, fa2, P, x, y, rt)
+    assert np.array_equal(F, ref)
+
+
+# ---- one step: C oracle vs the independent numpy restatement ---------------------------------
+@pytest.mark.parametrize("conf", [dict(), dict(mag_dependency=0), dict(momentum_dependency=0), dict(kret=0.0)])
+def test_step_matches_numpy_restatement(conf):
+    w, P, frames, _ = make_case("c1", grid=48, nptl=400, conf=conf)
+    P.rng_mode = RNG_TABLE
+    o = Oracle(P, w.nptl_max)
+    u = np.random.default_rng(5).uniform(0, 1, (400, 2, 4))
+    o.set_rng_table(u)
+    o.upload_fields(0, frames[0])
+    o.upload_fields(1, frames[1])
+    o.inject_uniform(400, 0.0, 0, w.particle_v0, 0.0, w.dt_out, box_of(P), w.power_index)
+    before = o.download_particles()
+    assert o.debug_push_n(0.0, w.dt_out, 1) == 400
+    after = o.download_particles()
+    fa1 = np_step.gradients32(frames[0], P.dx, P.dy)
+    fa2 = np_step.gradients32(frames[1], P.dx, P.dy)
+    F = np_step.interp32(fa1, fa2, P, before["x"], before["y"], (before["t"] - 0.0) / w.dt_out)
+    qdrift = float(np.float32(1.0) / np.float32(3 * P.pcharge))
+    x, y, p, t, dt = np_step.push_2d(P, F, before["p"], P.dt_min_rel * w.dt_out, P.dt_max_rel * w.dt_out,
+                                    u[before["tag_injected"], 0], before["x"], before["y"], before["t"], qdrift)
+    for name, ref in (("x", x), ("y", y), ("p", p), ("t", t), ("dt", dt)):
+        scale = max(1.0, np.abs(ref).max()) if name in "xy" else np.abs(ref)
+        err = np.abs(after[name] - ref) / scale
+        assert err.max() < 2e-15, (name, err.max())  # identical operations; pow() may differ by an ulp
+    assert np.array_equal(rng_steps(after), rng_steps(before) + np.uint64(1))
+
+
+# ---- statistics of the stochastic step -----------------------------------------------------------
+def test_pure_diffusion_variance():
+    """Uniform B along x, no flow, constant kappa: after time T the displacement variance is
+    2*kpara*T along B and 2*kperp*T across it (docs/source/theory/parker_1d2d.rst; the noise
+    is uniform on [-sqrt3, sqrt3], particle_module.f90:3547-3550).  With dx/dt = dp/dt = 0 the
+    reference falls back to dt_min (particle_module.f90:3532-3534), so dt_min = dt_max here."""
+    w, P, _, _ = make_case("c1", grid=32, nptl=20000, conf=dict(momentum_dependency=0, mag_dependency=0,
+                                                               kpara0=0.002, kret=0.25, dt_min_rel=5e-3, dt_max_rel=5e-3))
+    f = np.zeros((P.ny + 4, P.nx + 4, 8), dtype=np.float32)
+    f[..., 3] = 1.0
+    f[..., 4] = 1.0
+    f[..., 7] = 1.0
+    o = Oracle(P, 40000)
+    o.upload_fields(0, f)
+    o.upload_fields(1, f)
+    n = 20000
+    ptl = np.zeros(n, dtype=PARTICLE_DTYPE)
+    ptl["x"] = 0.5 * (P.xmin + P.xmax)
+    ptl["y"] = 0.5 * (P.ymin + P.ymax)
+    ptl["p"] = P.p0
+    ptl["weight"] = 1.0
+    ptl["count_flag"] = 1
+    ptl["tag_injected"] = np.arange(n)
+    ptl["tag_splitted"] = 1
+    ptl["dt"] = 1e-4
+    o.upload_particles(ptl)
+    T = 0.1
+    o.particle_mover(0.0, T, 100, 1, 0)
+    a = o.download_particles()
+    assert len(a) == n and np.all(a["t"] == T)
+    vx, vy = np.var(a["x"] - ptl["x"][0]), np.var(a["y"] - ptl["y"][0])
+    # relative standard error of a variance estimate ~ sqrt(2/n) = 1 %; allow 5 sigma
+    assert abs(vx / (2 * 0.002 * T) - 1) < 0.05
+    assert abs(vy / (2 * 0.002 * 0.25 * T) - 1) < 0.05
+    assert np.all(a["p"] == P.p0)  # div v = 0, no D_pp: momentum untouched
+
+
+def test_adiabatic_compression_energises():
+    """dp/dt = -p div(v)/3 (particle_module.f90:3477): in a uniformly converging flow every
+    particle gains momentum by exp(-divv T/3)."""
+    w, P, _, _ = make_case("c1", grid=32, nptl=64, conf=dict(momentum_dependency=0, mag_dependency=0,
+                                                            kpara0=1e-6, kret=1.0, dt_min_rel=1e-3, dt_max_rel=1e-3))
+    j, i = np.meshgrid(np.arange(P.ny + 4), np.arange(P.nx + 4), indexing="ij")
+    f = np.zeros((P.ny + 4, P.nx + 4, 8), dtype=np.float32)
+    c = 0.5
+    f[..., 0] = -c * ((i - 2) * P.dx - 1.0)  # vx = -c (x - 1): div v = -c
+    f[..., 3] = 1.0
+    f[..., 6] = 1.0  # B along z: no in-plane field-aligned motion
+    f[..., 7] = 1.0
+    o = Oracle(P, 256)
+    o.upload_fields(0, f)
+    o.upload_fields(1, f)
+    o.inject_uniform(64, 1e-5, 1, 1.0, 0.0, 1e-9, [0.9, 0.9, 0, 1.1, 1.1, 1], 6.2)
+    o.particle_mover(0.0, 0.1, 100, 1, 0)
+    a = o.download_particles()
+    assert len(a) == 64
+    assert np.max(np.abs(a["p"] / P.p0 / np.exp(c * 0.1 / 3.0) - 1)) < 2e-3  # first-order Euler in t
+
+
+# ---- split / remove / histograms ------------------------------------------------------------------
+def test_split_semantics():
+    """split_particle (particle_module.f90:5430-5480): threshold pmin_split*p0*ratio**split_times,
+    both copies get weight 0.5**(1+split_times), child tag = parent + 2**(split_times-1) (after the
+    increment), append at the tail, silent stop at nptl_max."""
+    w, P, _, _ = make_case("c1", grid=16, nptl=8)
+    o = Oracle(P, 10)
+    ptl = np.zeros(6, dtype=PARTICLE_DTYPE)
+    ptl["p"] = P.p0 * np.array([1.0, 2.5, 4.5, 3.9, 9.0, 120.0])
+    ptl["split_times"] = [0, 0, 1, 1, 2, 0]
+    ptl["weight"] = 0.5 ** ptl["split_times"].astype(float)
+    ptl["count_flag"] = 1
+    ptl["tag_injected"] = np.arange(6)
+    ptl["tag_splitted"] = 1
+    o.upload_particles(ptl)
+    o.split(2.0, 2.0)
+    a = o.download_particles()
+    # 1: below threshold; 2.5 > 2: split; 4.5 > 4: split; 3.9 < 4: no; 9 > 8: split; 120*p0 = 12 > pmax = 10: no
+    assert len(a) == 9 and o.counters().nptl_split == 3
+    assert list(a["split_times"][:6]) == [0, 1, 2, 1, 3, 0]
+    assert list(a["weight"][:6]) == [1.0, 0.5, 0.25, 0.5, 0.125, 1.0]
+    assert list(a["tag_injected"][6:]) == [1, 2, 4] and list(a["split_times"][6:]) == [1, 2, 3]
+    assert list(a["weight"][6:]) == [0.5, 0.25, 0.125]
+    assert list(a["tag_splitted"][6:]) == [1 + 2 ** 0, 1 + 2 ** 1, 1 + 2 ** 2]
+    assert a["weight"].sum() == ptl["weight"].sum()  # splitting conserves the weight
+    o.split(1.0001, 0.01)  # everything (but the particle beyond pmax) qualifies; only one slot is left
+    assert o.counters().nptl_current == 10
+
+
+def test_histograms_match_numpy_binning():
+    """calc_particle_distributions (diagnostics.f90:757-879): global spectrum p in (pmin, pmax],
+    local sets drop their top momentum bin (ip < npbins, diagnostics.f90:799)."""
+    w, P, frames, ts = make_case("c1", grid=32, nptl=3000)
+    o = Oracle(P, w.nptl_max)
+    run_intervals(o, frames, ts, nptl=3000, particle_v0=w.particle_v0, dist_flag=2, pmin_split=1.2,
+                  split_ratio=1.2)
+    a = o.download_particles()
+    d = o.diagnostics(True)
+    pmin_log = np.log10(P.pmin)
+    dp_log = (np.log10(P.pmax) - pmin_log) / P.npp_global
+    sel = (a["p"] > P.pmin) & (a["p"] <= P.pmax)
+    ip = np.floor((np.log10(a["p"][sel]) - pmin_log) / dp_log).astype(int)
+    ref = np.bincount(np.minimum(ip, P.npp_global - 1), weights=a["weight"][sel], minlength=P.npp_global)
+    assert np.array_equal(d["fglobal"][:, 0], ref)
+    assert d["fglobal"].sum() == a["weight"][sel].sum()
+    s = P.local[0]
+    nrx, nry = P.nx // s.rx, P.ny // s.ry
+    dpl = (np.log10(s.pmax) - np.log10(s.pmin)) / s.npbins
+    ix = np.floor((a["x"] - P.xmin) / (P.lx / nrx)).astype(int)
+    iy = np.floor((a["y"] - P.ymin) / (P.ly / nry)).astype(int)
+    ipl = np.floor((np.log10(a["p"]) - np.log10(s.pmin)) / dpl).astype(int)  # 0-based: Fortran ip - 1
+    ok = (ix >= 0) & (ix < nrx) & (iy >= 0) & (iy < nry) & (ipl >= 0) & (ipl < s.npbins - 1)
+    ref = np.zeros((nry, nrx, s.npbins))
+    np.add.at(ref, (iy[ok], ix[ok], ipl[ok]), a["weight"][ok])
+    assert np.array_equal(d["flocal"][0][0, :, :, :, 0], ref)
+    assert d["flocal"][0][..., s.npbins - 1, :].sum() == 0.0
+    q = d["quick"]
+    assert q[0] == len(a) and q[2] == a["weight"].sum() and d["pmax"] == a["p"].max()
+    assert q[6] == a["dt"].min() and q[7] == a["dt"].max()
+    pe, me = o.hist_edges(0)
+    assert len(pe) == P.npp_global + 1 and rel_err(pe[0], P.pmin) < 1e-15 and rel_err(pe[-1], P.pmax) < 1e-14
+    assert list(me) == [-1.0, 1.0]
+
+
+def test_mover_ends_every_particle_on_the_frame_time_and_is_deterministic():
+    """particle_mover: the roll-back + fixed-dt re-push lands every surviving particle exactly
+    on t0 + dtf (particle_module.f90:1707-1826); the Philox stream makes reruns bit-identical
+    and independent of the OpenMP schedule."""
+    w, P, frames, ts = make_case("c1", grid=32, nptl=500)
+    outs = []
+    for _ in range(2):
+        o = Oracle(P, w.nptl_max)
+        rec, steps = run_intervals(o, frames, ts, nptl=500, particle_v0=w.particle_v0, num_fine_steps=2)
+        outs.append((sort_by_key(o.download_particles()), steps, rec))
+    a, b = outs[0][0], outs[1][0]
+    assert outs[0][1] == outs[1][1] > 500 * 50
+    assert_particles_identical(a, b, 'rerun')
+    assert np.max(np.abs(a["t"] - ts[-1])) < 1e-12
+    assert np.all(a["count_flag"] == 1)
+    assert np.all((a["x"] >= P.xmin) & (a["x"] <= P.xmax))  # final BC pass with the un-extended box
+
+
+def test_open_boundaries_leak_weight():
+    """particle_boundary_condition (particle_module.f90:1984-2129) with pbc = 1: escapes are
+    flagged -1..-4, removed, and their weight goes to `leak`."""
+    w, P, frames, ts = make_case("c2", grid=32, nptl=600)
+    o = Oracle(P, w.nptl_max)
+    run_intervals(o, frames, ts, nptl=600, particle_v0=w.particle_v0, split_flag=0, inject_new_ptl=False,
+                  dump_escaped_dist=False)
+    c = o.counters()
+    a = o.download_particles()
+    assert c.leak > 0 and c.leak + c.leak_negp + a["weight"].sum() == 600.0
+    assert np.all(a["count_flag"] == 1)
+
+
+def test_empty_and_capacity_edges():
+    w, P, frames, ts = make_case("c1", grid=16, nptl=8)
+    o = Oracle(P, 12)
+    o.upload_fields(0, frames[0])
+    o.upload_fields(1, frames[1])
+    assert o.particle_mover(0.0, 0.1) == 0
+    d = o.diagnostics(True)
+    assert d["fglobal"].sum() == 0 and d["quick"][0] == 0
+    o.inject_uniform(0, 0.0, 1, 1.0, 0.0, 0.1, box_of(P), 6.2)
+    assert len(o.download_particles()) == 0
+    o.inject_uniform(20, 0.0, 1, 1.0, 0.0, 0.1, box_of(P), 6.2)  # overflow: slot nptl_max is overwritten
+    c = o.counters()
+    assert c.nptl_current == 12 and c.tag_max == 20
+    assert o.download_particles()["tag_injected"][-1] == 19
