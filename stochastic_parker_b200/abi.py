@@ -14,7 +14,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libgpat_cuda.so")
+# GPAT_LIB selects an experiment build of the same library (csrc/Makefile `variant`)
+LIB_PATH = os.environ.get("GPAT_LIB") or os.path.join(_HERE, "csrc", "libgpat_cuda.so")
 
 GPAT_OK = 0
 COUNT_FLAG_INBOX = 1

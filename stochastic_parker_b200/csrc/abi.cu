@@ -223,6 +223,8 @@ void fill_dev_params(gpat_sim* h)
     d.sqrt_1mkret = std::sqrt(1.0 - p.kret);
     d.d1p0 = p.drift1 * p.p0;
     d.d2p02 = p.drift2 * p.p0 * p.p0;
+    d.d1p0sq = d.d1p0 * d.d1p0;
+    d.d2p02sq = d.d2p02 * d.d2p02;
     {
         double hx = 0.5 * p.dx, hy = 0.5 * p.dy, hz = 0.5 * p.dz;
         d.hd2min2 = std::fmin(hx * hx, hy * hy);

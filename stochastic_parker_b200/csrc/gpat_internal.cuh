@@ -102,6 +102,7 @@ struct DevParams {
     double idx, idy, idz, ip0;
     double sqrt_kret, sqrt_1mkret;  // sqrt(kret), sqrt(1 - kret)
     double d1p0, d2p02;             // drift1*p0, drift2*p0**2
+    double d1p0sq, d2p02sq;         // their squares
     double hd2min2, hd2min3;        // min((dx/2)^2,(dy/2)^2[,(dz/2)^2])
     double pfloor;                  // 0.25*p0
     double acc_region[6];

@@ -17,7 +17,10 @@
 // This translation unit is compiled twice:
 //   GPAT_STRICT=1, -fmad=false : reference operation order, no contraction (parity build)
 //   GPAT_STRICT=0              : FMA contraction, time-blend folded into the weights
+#include <cstdlib>
+
 #include "gpat_internal.cuh"
+#include "fastmath.cuh"
 
 #ifndef GPAT_STRICT
 #define GPAT_STRICT 0
@@ -664,7 +667,12 @@ __device__ __forceinline__ void refill(const DevParams& prm, const PushArgs& a, 
 __device__ __forceinline__ int after_push(const DevParams& prm, const PushArgs& a, Lane& q, int state,
                                           int& remaining)
 {
-    q.nsteps_pushed = (q.nsteps_pushed + 1) % a.nsteps_interval;  // particle_module.f90:1694
+    // mod(nsteps_pushed + 1, nsteps_interval), particle_module.f90:1694; the counter is already
+    // inside [0, interval) except right after a restart with a smaller interval
+    {
+        const int n1 = q.nsteps_pushed + 1;
+        q.nsteps_pushed = (n1 < a.nsteps_interval) ? n1 : (n1 == a.nsteps_interval ? 0 : n1 % a.nsteps_interval);
+    }
     if (a.debug_nsteps > 0) return (--remaining == 0) ? ST_IDLE : ST_ADAPT;
     return next_state(prm, a, q, state == ST_FIX ? AFTER_FIXED_PUSH : AT_INNER_HEAD);
 }
@@ -722,18 +730,35 @@ push_kernel(const __grid_constant__ DevParams prm, const PtlSoA P, const float* 
 // ONE particle's line together (G x 32 contiguous bytes per corner), so a warp-wide load touches
 // 32/G lines; the G particles of a group are served in G rounds and every lane ends a round
 // with final values of the slots of its chunks, parked in shared memory for the owner lane.
+#ifdef GPAT_EXP_NOCVT  // timing experiment only (wrong numbers): what do the F2F conversions cost?
+__device__ __forceinline__ double cvt(float f) { return __hiloint2double(__float_as_int(f), 0); }
+#else
+__device__ __forceinline__ double cvt(float f) { return (double)f; }
+#endif
+
 template <int L> struct Coop {
     static constexpr int NREC = Rec<L>::NREC;
     static constexpr int NCH = NREC / 4;                          // 32-byte chunks per grid point
+#ifdef GPAT_COOP_G
+    static constexpr int G = GPAT_COOP_G;
+#else
     static constexpr int G = (NCH == 4 || NCH == 8) ? 4 : 2;      // lanes per particle
+#endif
     static constexpr int CPL = NCH / G;                           // chunks per lane
     static constexpr int NC = (Rec<L>::NDIM == 3) ? 8 : 4;
     static constexpr int ROW = NREC + 2;                          // doubles per result row (+16 B: bank skew)
     static constexpr int PAR = 6;                                 // doubles per parameter row (48 B)
 };
 
+// resident CTAs per SM the register allocation must allow: the kernel is latency-bound, and
+// 2-D Parker sits right at the 128-register edge between 4 and 3 CTAs (16 vs 12 warps: 14 %)
+#ifdef GPAT_MINBLOCKS
+template <int L> struct MinBlocks { static constexpr int V = GPAT_MINBLOCKS; };
+#else
+template <int L> struct MinBlocks { static constexpr int V = (L == L2B) ? 4 : 3; };
+#endif
 template <int L>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, MinBlocks<L>::V)
 push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                  const float* __restrict__ fld, const __grid_constant__ PushArgs a)
 {
@@ -772,16 +797,20 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
 
         // ---- phase A: every lane publishes where its particle is ----
         {
-            double rx = 0.0, ry = 0.0, rz = 0.0, rt = 0.0;
+            // t0/t1: time-blend factors of half 0 / half 1 of every chunk
+            double rx = 0.0, ry = 0.0, rz = 0.0, t0 = 0.0, t1 = 0.0;
             long long cell = 0;
             if (state != ST_IDLE) {
                 cell = locate<Rec<L>::NDIM>(prm, q.x, q.y, q.z, rx, ry, rz);
-                rt = (q.t - a.t0) * a.idtf;
+                const double rt = (q.t - a.t0) * a.idtf;
+                const double tA = prm.time_interp ? 1.0 - rt : 1.0, tB = prm.time_interp ? rt : 0.0;
+                t0 = (a.sel == 0) ? tA : tB;
+                t1 = (a.sel == 0) ? tB : tA;
             }
             double2* row = reinterpret_cast<double2*>(par + lane * C::PAR);
             row[0] = make_double2(rx, ry);
-            row[1] = make_double2(rz, rt);
-            row[2] = make_double2(__longlong_as_double(cell), 0.0);
+            row[1] = make_double2(t0, t1);
+            row[2] = make_double2(__longlong_as_double(cell), rz);
         }
         __syncwarp();
 
@@ -791,14 +820,11 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
             const int owner = gbase + r;
             const double2* row = reinterpret_cast<const double2*>(par + owner * C::PAR);
             const double2 pa = row[0], pb = row[1], pc = row[2];
-            const double rx = pa.x, ry = pa.y, rz = pb.x, rt = pb.y;
+            const double rx = pa.x, ry = pa.y, t0 = pb.x, t1 = pb.y, rz = pc.y;
             const long long cell = __double_as_longlong(pc.x);
             // weights of half 0 / half 1 at each corner (time blend folded in)
             double w0[C::NC], w1[C::NC];
             {
-                const double rt1 = 1.0 - rt;
-                const double tA = prm.time_interp ? rt1 : 1.0, tB = prm.time_interp ? rt : 0.0;
-                const double t0 = (a.sel == 0) ? tA : tB, t1 = (a.sel == 0) ? tB : tA;
                 const double rx1 = 1.0 - rx, ry1 = 1.0 - ry;
                 if (C::NC == 4) {
                     const double a0 = ry1 * t0, b0 = ry * t0, a1 = ry1 * t1, b1 = ry * t1;
@@ -827,14 +853,14 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                 for (int j = 0; j < C::CPL; ++j) {
                     float4 f0, f1;
                     ldg256(pc_ + 8 * j, f0, f1);
-                    acc[j][0] = fma((double)f0.x, w0[c], acc[j][0]);
-                    acc[j][1] = fma((double)f0.y, w0[c], acc[j][1]);
-                    acc[j][2] = fma((double)f0.z, w0[c], acc[j][2]);
-                    acc[j][3] = fma((double)f0.w, w0[c], acc[j][3]);
-                    acc[j][0] = fma((double)f1.x, w1[c], acc[j][0]);
-                    acc[j][1] = fma((double)f1.y, w1[c], acc[j][1]);
-                    acc[j][2] = fma((double)f1.z, w1[c], acc[j][2]);
-                    acc[j][3] = fma((double)f1.w, w1[c], acc[j][3]);
+                    acc[j][0] = fma(cvt(f0.x), w0[c], acc[j][0]);
+                    acc[j][1] = fma(cvt(f0.y), w0[c], acc[j][1]);
+                    acc[j][2] = fma(cvt(f0.z), w0[c], acc[j][2]);
+                    acc[j][3] = fma(cvt(f0.w), w0[c], acc[j][3]);
+                    acc[j][0] = fma(cvt(f1.x), w1[c], acc[j][0]);
+                    acc[j][1] = fma(cvt(f1.y), w1[c], acc[j][1]);
+                    acc[j][2] = fma(cvt(f1.z), w1[c], acc[j][2]);
+                    acc[j][3] = fma(cvt(f1.w), w1[c], acc[j][3]);
                 }
             }
             double2* out = reinterpret_cast<double2*>(res + owner * C::ROW + (gq * C::CPL) * 4);
@@ -895,11 +921,17 @@ void launch_one(const DevParams& prm, const PtlSoA& P, const float* fld, const P
     if (want < grid) grid = want > 0 ? want : 1;
 #if !GPAT_STRICT
     if (a.variant == 1) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel_coop<L>, kBlock, 0);
+        // GPAT_PUSH_SMEM_PAD: occupancy experiments (unused dynamic shared memory per CTA)
+        size_t pad = 0;
+        if (const char* e = getenv("GPAT_PUSH_SMEM_PAD")) {
+            pad = (size_t)atol(e);
+            cudaFuncSetAttribute(push_kernel_coop<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+        }
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel_coop<L>, kBlock, pad);
         if (per_sm < 1) per_sm = 1;
         grid = (long long)sm_count * per_sm;
         if (want < grid) grid = want > 0 ? want : 1;
-        push_kernel_coop<L><<<(unsigned)grid, kBlock, 0, st>>>(prm, P, fld, a);
+        push_kernel_coop<L><<<(unsigned)grid, kBlock, pad, st>>>(prm, P, fld, a);
         return;
     }
 #endif

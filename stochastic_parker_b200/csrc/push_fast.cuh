@@ -6,7 +6,11 @@
 //   * b, 1/b come from one rsqrt; sqrt(2 kperp) and sqrt(2(kpara-kperp)) are sqrt(2 kpara)
 //     times constants; the three sqrt(.)*sqrt(dt) products are one sqrt(2 kpara dt);
 //   * the two pow() of kappa (particle_module.f90:2242,2258) are one exp of a sum of logs;
-//   * the five dt candidates (particle_module.f90:3519-3523) need 3 divisions instead of 5;
+//   * the five dt candidates (particle_module.f90:3519-3523) are compared as fractions by
+//     cross-multiplication and only the smallest one is divided out (1 reciprocal, not 5);
+//   * the drift speed needs no 1/p: q/sqrt((d1 p0/p)^2 + (d2 p0^2/p^2)^2) =
+//     q p^2 / sqrt((d1 p0)^2 p^2 + (d2 p0^2)^2);
+//   * log, exp, reciprocal, rsqrt and sqrt are the straight-line versions of fastmath.cuh;
 //   * the uniform -> [-sqrt3, sqrt3] map is a single FMA.
 // Each change moves a result by a few ulp; tests hold this build to 1e-12 per step against the
 // oracle (tests/test_gpu_parity.py::test_step_parity[0-*]).
@@ -39,8 +43,12 @@ __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArg
                                                (unsigned)q.tag_inj, (unsigned)q.tag_spl),
                                     prm.key0, prm.key1 + (unsigned)q.origin);
             const double c = 2.0 * sqrt3 / 4294967295.0;
-            ran1 = fma((double)r.x, c, -sqrt3); ran2 = fma((double)r.y, c, -sqrt3);
-            ran3 = fma((double)r.z, c, -sqrt3); ranp = fma((double)r.w, c, -sqrt3);
+            // u32 -> f64 through the 2^52 exponent trick (an FP64 add, not a conversion-unit op)
+            const double two52 = 4503599627370496.0;
+            ran1 = fma(__hiloint2double(0x43300000, (int)r.x) - two52, c, -sqrt3);
+            ran2 = fma(__hiloint2double(0x43300000, (int)r.y) - two52, c, -sqrt3);
+            ran3 = fma(__hiloint2double(0x43300000, (int)r.z) - two52, c, -sqrt3);
+            ranp = fma(__hiloint2double(0x43300000, (int)r.w) - two52, c, -sqrt3);
         }
         q.rng += 1;
     }
@@ -81,34 +89,35 @@ __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArg
     // ---- |B|, 1/|B| from one rsqrt ----
     const double b2 = bx * bx + by * by + bz * bz;
     const bool tiny = b2 < kEps * kEps;             // b < EPSILON(b)
-    const double ibr = tiny ? 0.0 : rsqrt(b2);      // push_particle_*: ib = 0 for tiny b
+    const double ibr = tiny ? 0.0 : fm::rsqrt(tiny ? 1.0 : b2);  // push_particle_*: ib = 0 for tiny b
     const double b = b2 * ibr;
     const double ibk = tiny ? 1.0 : ibr;            // kappa routine: ib1 = 1 for tiny b
     const double ibk2 = ibk * ibk, ibk3 = ibk2 * ibk;
     const double ib2 = ibr * ibr, ib3 = ib2 * ibr;
 
     // ---- kappa_para, kappa_perp (particle_module.f90:2239-2269 / 2497-2533) ----
-    const double lb = prm.mag_dependency == 1 ? log(b) : 0.0;
-    const double lpr = log(q.p * prm.ip0);
+    // log|B| = log(b2)/2; a vanishing field only has to stay finite here
+    const double lb = prm.mag_dependency == 1 ? 0.5 * fm::log_pos(fmax(b2, 1e-300)) : 0.0;
+    const double lpr = fm::log_pos(q.p * prm.ip0);
     double knp = 1.0, kpara, rk, srk, s1mrk;  // rk = kperp/kpara and its square roots
     if (EXT || prm.nlgc) {
-        if (prm.mag_dependency == 1) knp = exp(prm.gm2 * lb);
-        const double pp = prm.momentum_dependency == 1 ? exp(prm.pindex * lpr) : 1.0;
+        if (prm.mag_dependency == 1) knp = fm::exp_mid(prm.gm2 * lb);
+        const double pp = prm.momentum_dependency == 1 ? fm::exp_mid(prm.pindex * lpr) : 1.0;
         kpara = prm.kpara0 * knp * pp;
     } else {
         const double e = (prm.mag_dependency == 1 ? prm.gm2 * lb : 0.0) +
                          (prm.momentum_dependency == 1 ? prm.pindex * lpr : 0.0);
-        kpara = prm.kpara0 * exp(e);
+        kpara = prm.kpara0 * fm::exp_mid(e);
     }
     if (!prm.nlgc) {
         rk = prm.kret; srk = prm.sqrt_kret; s1mrk = prm.sqrt_1mkret;
     } else {
         const double e = (prm.mag_dependency == 1 ? prm.gm2_3 * lb : 0.0) +
                          (prm.momentum_dependency == 1 ? prm.pidx_perp * lpr : 0.0);
-        const double kperp = prm.kpara0 * prm.kperp_kpara * exp(e) * q.mu * q.mu;
-        rk = kperp / kpara;
-        srk = sqrt(rk);
-        s1mrk = sqrt(1.0 - rk);
+        const double kperp = prm.kpara0 * prm.kperp_kpara * fm::exp_mid(e) * q.mu * q.mu;
+        rk = kperp * fm::rcp(kpara);
+        srk = fm::sqrt_pos(rk);
+        s1mrk = fm::sqrt_pos(1.0 - rk);
     }
     const double kperp = kpara * rk;
     const double kpp = kpara - kperp;
@@ -139,9 +148,8 @@ __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArg
     const double dkxy_dy = ay * bxyn2 + kpp * ((dbx_dy * by + bx * dby_dy) * ibk2 - 2.0 * bx * by * db_dy * ibk3);
 
     // ---- drift (particle_module.f90:3436-3446 / 4739-4741) ----
-    const double ip = 1.0 / q.p;
-    const double da = prm.d1p0 * ip, dbb = prm.d2p02 * ip * ip;
-    const double vdp = prm.qdrift * rsqrt(da * da + dbb * dbb);
+    const double p2 = q.p * q.p;
+    const double vdp = prm.qdrift * p2 * fm::rsqrt(fma(prm.d1p0sq, p2, prm.d2p02sq));
     double dx_dt, dy_dt, dz_dt, divv;
     if (!third) {
         const double vdx = vdp * (dbz_dy * ib2 - 2.0 * bz * db_dy * ib3);
@@ -171,14 +179,12 @@ __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArg
         divv = dvx_dx + dvy_dy + dvz_dz;
     }
     double dp_dt = -q.p * divv * (1.0 / 3.0);
-    const double ikp = 1.0 / kpara;
 
     // ---- momentum diffusion (particle_module.f90:2918-2979) ----
     double dpp = 0.0;
     if constexpr (EXT) {
         if (prm.dpp_wave) {
-            const double va2 = b2 / rho;
-            const double pv = q.p * va2 * ikp;
+            const double pv = q.p * b2 * fm::rcp(rho * kpara);  // p va^2 / kpara
             dp_dt += (prm.momentum_dependency == 1 ? 8.0 / 27.0 : 4.0 / 9.0) * pv;
             dpp += q.p * pv * (1.0 / 9.0);
         }
@@ -200,9 +206,9 @@ __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArg
             }
             if (gshear > 0.0) {
                 // p**pindex * p0**(2-pindex) = p0^2 (p/p0)**pindex
-                const double pw = prm.p0 * prm.p0 * exp(prm.pindex * lpr);
+                const double pw = prm.p0 * prm.p0 * fm::exp_mid(prm.pindex * lpr);
                 const double g = gshear * prm.tau0 * knp * pw;
-                dp_dt += (2.0 + prm.pindex) * g * ip;
+                dp_dt += (2.0 + prm.pindex) * g * fm::rcp(q.p);
                 dpp += g;
             }
         }
@@ -212,11 +218,15 @@ __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArg
     if (!fixed_dt) {
         double d;
         if (dx_dt != 0.0 && dy_dt != 0.0 && dp_dt != 0.0) {
-            const double s2 = 2.0 * ((rk > 0.0) ? kperp : kpara);
+            // three positive fractions n/dn; pick the smallest by cross-multiplication
             double m = fmax(dx_dt * dx_dt, dy_dt * dy_dt);
             if (D3) m = fmax(m, dz_dt * dz_dt);  // (s/0)^2 = +Inf is ignored by min, as in the reference
-            d = fmin((D3 ? prm.hd2min3 : prm.hd2min2) * 0.5 * ikp, s2 / m);
-            d = fmin(d, (double)0.1f * q.p / fabs(dp_dt));
+            double n = (D3 ? prm.hd2min3 : prm.hd2min2) * 0.5, dn = kpara;
+            const double n1 = 2.0 * ((rk > 0.0) ? kperp : kpara);
+            if (n1 * dn < n * m) { n = n1; dn = m; }
+            const double n2 = (double)0.1f * q.p, d2 = fabs(dp_dt);
+            if (n2 * dn < n * d2) { n = n2; dn = d2; }
+            d = n * fm::rcp(dn);
         } else {
             d = a.dt_min;
         }
@@ -226,7 +236,7 @@ __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArg
     }
 
     // ---- stochastic step ----
-    const double sA = sqrt(2.0 * kpara * q.dt);  // sqrt(2 kpara) sqrt(dt)
+    const double sA = fm::sqrt_pos(2.0 * kpara * q.dt);  // sqrt(2 kpara) sqrt(dt)
     double ddx, ddy, ddz;
     if (!third) {
         const double sp = sA * srk, spp = sA * s1mrk * ran3 * ibr;
@@ -237,7 +247,7 @@ __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArg
     } else {
         const double bxn = bx * ibr, byn = by * ibr, bzn = bz * ibr;
         const double h2 = bxn * bxn + byn * byn;
-        const double ih = (h2 < kEps * kEps) ? 0.0 : rsqrt(h2);
+        const double ih = (h2 < kEps * kEps) ? 0.0 : fm::rsqrt(h2 < kEps * kEps ? 1.0 : h2);
         const double hxy = h2 * ih;
         const double sp = sA * srk;
         const double t2 = sp * ih * ran2, t3 = sp * ih * ran3, t1 = sA * ran1;
@@ -254,7 +264,7 @@ __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArg
     q.dyl = ddy;
 
     double ddp = dp_dt * q.dt;
-    if constexpr (EXT) ddp = fma(ranp, sqrt(2.0 * dpp * q.dt), ddp);
+    if constexpr (EXT) ddp = fma(ranp, fm::sqrt_pos(2.0 * dpp * q.dt), ddp);
     if (prm.acc_region_flag == 1) {
         if (in_acc_region(prm, q)) q.p += ddp;
         else ddp = 0.0;

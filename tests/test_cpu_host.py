@@ -1,0 +1,209 @@
+"""CPU tests of the boundary and the host-side mirror (no GPU compute calls).
+
+ * libgpat_cuda.so loads and exports every symbol include/gpat_cuda.h declares;
+ * the ctypes view of the POD structs matches the C compiler's layout of the header;
+ * without a CUDA device the library fails loudly (no CPU fallback);
+ * conf.dat grammar (read_config.f90:22-45), mhd_config.dat / mhd_data_NNNN formats
+   (reorganize_fields.py, mhd_config.f90:139-148), the named workloads;
+ * the straight-line FP64 math of the production kernel (csrc/fastmath.cuh) on the host.
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "gpat_cuda.h")
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def _declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gpat_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_reference_procedures():
+    """One entry point per procedure the driver calls on the path."""
+    syms = _declared_symbols()
+    for need in ("gpat_init", "gpat_set_params", "gpat_finalize", "gpat_upload_fields", "gpat_swap_fields",
+                 "gpat_inject_uniform", "gpat_particle_mover", "gpat_split", "gpat_diagnostics",
+                 "gpat_escaped_diagnostics", "gpat_download_particles", "gpat_upload_particles",
+                 "gpat_comm_init", "gpat_hist_edges", "gpat_get_counters"):
+        assert need in syms
+    text = open(HEADER).read()
+    # every entry point cites the reference lines it replaces
+    for cite in ("particle_module.f90:1846", "particle_module.f90:5430", "particle_module.f90:454",
+                 "diagnostics.f90:738", "mhd_data_parallel.f90:504", "mhd_data_parallel.f90:1920",
+                 "random_number_generator.f90:28"):
+        assert cite in text, cite
+
+
+def test_library_exports_every_declared_symbol():
+    from stochastic_parker_b200 import abi
+    lib = abi.load_library()
+    declared = _declared_symbols()
+    assert len(declared) >= 26
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in gpat_cuda.h but not exported"
+        assert name in abi.SIGNATURES, f"{name} has no ctypes signature in abi.py"
+    assert set(abi.SIGNATURES) == set(declared)
+    # dynamic symbol table: extern "C", no mangling
+    out = subprocess.run(["nm", "-D", "--defined-only", abi.LIB_PATH], capture_output=True, text=True,
+                         check=True).stdout
+    exported = set(re.findall(r" T (gpat_[a-z0-9_]+)", out))
+    assert set(declared) <= exported
+
+
+def test_struct_layouts_match_the_c_header(tmp_path):
+    """sizeof/offsetof from gcc on include/gpat_cuda.h == the ctypes / numpy views."""
+    from stochastic_parker_b200 import abi
+    src = tmp_path / "layout.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "gpat_cuda.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu\n", sizeof(gpat_params), sizeof(gpat_particle), sizeof(gpat_hist_spec),
+         sizeof(gpat_counters), sizeof(gpat_timings));
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", offsetof(gpat_params, dx), offsetof(gpat_params, acc_region),
+         offsetof(gpat_params, tau0), offsetof(gpat_params, kperp_kpara), offsetof(gpat_params, local),
+         offsetof(gpat_params, seed), offsetof(gpat_params, strict_math));
+  printf("%zu %zu %zu %zu %zu\n", offsetof(gpat_particle, count_flag), offsetof(gpat_particle, origin),
+         offsetof(gpat_particle, tag_splitted), offsetof(gpat_particle, x), offsetof(gpat_particle, padding));
+  return 0;
+}''')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    l1, l2, l3 = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()
+    sizes = [int(v) for v in l1.split()]
+    assert sizes == [C.sizeof(abi.Params), abi.PARTICLE_DTYPE.itemsize, C.sizeof(abi.HistSpec),
+                     C.sizeof(abi.Counters), C.sizeof(abi.Timings)]
+    assert sizes[1] == 104  # particle_type, particle_module.f90:38-50
+    P = abi.Params
+    assert [int(v) for v in l2.split()] == [getattr(P, f).offset for f in
+                                            ("dx", "acc_region", "tau0", "kperp_kpara", "local", "seed",
+                                             "strict_math")]
+    off = abi.PARTICLE_DTYPE.fields
+    assert [int(v) for v in l3.split()] == [off[f][1] for f in
+                                            ("count_flag", "origin", "tag_splitted", "x", "padding")]
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-device error path")
+def test_no_cuda_device_fails_loudly():
+    """There is no CPU fallback: gpat_init reports GPAT_ERR_CUDA and says so."""
+    from helpers import make_case
+    from stochastic_parker_b200 import GpatError, GpatSim
+    w, P, _, _ = make_case("c1", grid=16, nptl=8)
+    with pytest.raises(GpatError) as e:
+        GpatSim(P, 64)
+    assert "(2)" in str(e.value) and "no CPU fallback" in str(e.value)
+
+
+def test_missing_library_is_an_error(tmp_path):
+    from stochastic_parker_b200 import abi
+    with pytest.raises(RuntimeError) as e:
+        abi.load_library(str(tmp_path / "libgpat_cuda.so"))
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under stochastic_parker_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "stochastic_parker_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", "Makefile")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "liborc" not in text and "gpat_oracle" not in text, os.path.join(dirpath, f)
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), os.path.join(dirpath, f)
+
+
+# ---- conf.dat grammar -----------------------------------------------------------------------------
+def test_conf_reader_is_a_forward_only_scan():
+    """get_variable (read_config.f90:22-45): first line containing the key after the current
+    position, value after '=', -1.0 when the key never appears again."""
+    from stochastic_parker_b200.config import ConfReader
+    text = "b0 = 1.0\np0 = 0.1 ; comment\npmin = 1E-2\npmax = 1.0D1\np0 = 0.5\n"
+    r = ConfReader(text)
+    assert r.get("b0") == 1.0 and r.get("p0") == 0.1 and r.get("pmin") == 0.01 and r.get("pmax") == 10.0
+    assert r.get("p0") == 0.5       # the scan continues from where it stopped
+    assert r.get("b0") == -1.0      # ... and never rewinds
+    r = ConfReader(text)
+    assert r.get("pmax") == 10.0 and r.get("pmin") == -1.0  # key order in the file matters
+
+
+def test_build_params_follows_the_reference_read_order():
+    from helpers import make_case
+    w, P, _, _ = make_case("c1", grid=64, nptl=16)
+    assert (P.p0, P.pmin, P.pmax) == (0.1, 0.01, 10.0)
+    assert P.gamma_turb == 1.6666667 and abs(P.pindex - (3.0 - 1.6666667)) < 1e-15  # particle_module.f90:2797-2798
+    assert (P.kpara0, P.kret) == (0.00743592, 0.01)    # diffusion_reconnection.sh:183-185
+    assert P.nmu_global == 1 and all(P.local[k].nmu == 1 for k in range(4))  # diagnostics.f90:2107-2128
+    assert [P.local[k].enabled for k in range(4)] == [1, 1, 1, 0]
+    assert (P.drift1, P.drift2, P.pcharge) == (850964.408, 13575468.975, -1)  # diffusion_reconnection.sh:188-190
+    assert list(P.acc_region) == [0.0, 1.0, 0.0, 1.0, 0.0, 1.0]
+    assert list(P.pbc) == [0, 0, 0] and P.time_interp == 1
+
+
+def test_named_workloads_cover_baseline_configs():
+    from stochastic_parker_b200 import WORKLOADS
+    assert sorted(WORKLOADS) == ["c1", "c2", "c3", "c4", "c5"]
+    assert (WORKLOADS["c1"].nx, WORKLOADS["c1"].ny, WORKLOADS["c1"].nptl) == (1024, 1024, 1_000_000)
+    assert WORKLOADS["c2"].nptl == 100_000_000 and WORKLOADS["c4"].nx == 4096
+    assert (WORKLOADS["c5"].nx, WORKLOADS["c5"].ndim) == (512, 3)
+    assert WORKLOADS["c4"].cli["dpp_wave"] == 1 and WORKLOADS["c3"].split_flag == 1
+
+
+# ---- on-disk formats --------------------------------------------------------------------------------
+def test_mhd_files_round_trip(tmp_path):
+    from stochastic_parker_b200 import mhd
+    cfg = mhd.write_run(str(tmp_path), "reconnection_2d", 24, 16, 1, nframes=2)
+    raw = open(tmp_path / "mhd_config.dat", "rb").read()
+    assert len(raw) == 13 * 8 + 14 * 4  # reorganize_fields.py:209-259
+    back = mhd.read_mhd_config(str(tmp_path / "mhd_config.dat"))
+    for k in ("dx", "dy", "xmax", "lx", "dt_out", "nx", "ny", "nz", "nvar"):
+        assert back[k] == cfg[k]
+    f = mhd.read_frame(str(tmp_path), 1, cfg)
+    assert f.shape == (20, 28, 8) and f.dtype == np.float32
+    assert np.array_equal(f, mhd.make_frame("reconnection_2d", 24, 16, 1, 1))
+    # periodic ghost fill of reorganize_fields.py:134-137
+    n = 16
+    assert np.array_equal(f[0:2], f[n - 1:n + 1]) and np.array_equal(f[n + 2:], f[3:5])
+    # |B| slot: f64 sqrt of the components, then cast (reorganize_fields.py:62)
+    b = np.sqrt(f[..., 4].astype(np.float64) ** 2 + f[..., 5].astype(np.float64) ** 2 + f[..., 6].astype(np.float64) ** 2)
+    assert np.max(np.abs(f[..., 7] - b)) < 2e-7 * b.max()
+
+
+@pytest.mark.parametrize("kind,shape", [("flare_2d", (12, 12)), ("shock_2d", (16, 8)), ("turbulence_2d", (12, 12)),
+                                        ("fluxrope_3d", (8, 8, 8))])
+def test_synthetic_frames_are_finite_and_time_dependent(kind, shape):
+    from stochastic_parker_b200 import mhd
+    nx, ny = shape[0], shape[1]
+    nz = shape[2] if len(shape) == 3 else 1
+    f0 = mhd.make_frame(kind, nx, ny, nz, 0)
+    f1 = mhd.make_frame(kind, nx, ny, nz, 1)
+    assert np.all(np.isfinite(f0)) and not np.array_equal(f0, f1)
+    assert f0.shape[-1] == 8 and f0.shape[-2] == nx + 4
+    assert np.all(f0[..., 3] > 0) and np.all(f0[..., 7] > 0)  # rho, |B|
+
+
+# ---- production math on the host -------------------------------------------------------------------
+def test_fastmath_accuracy_on_host(tmp_path):
+    exe = tmp_path / "fmcheck"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-o", str(exe),
+                    os.path.join(ROOT, "tests", "fastmath_host_check.cpp")], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    vals = dict(zip(out[0::2], (float(v) for v in out[1::2])))
+    assert vals["rcp"] <= 2 and vals["rsqrt"] <= 2 and vals["sqrt"] <= 1 and vals["log"] <= 2 and vals["exp"] <= 2
+    assert vals["pow_rel"] < 5e-15
