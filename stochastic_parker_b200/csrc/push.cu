@@ -98,6 +98,14 @@ __device__ __forceinline__ void boundary(const DevParams& prm, Lane& q, const do
     }
 }
 
+// true when negp_or_bc() would change anything
+__device__ __forceinline__ bool outside_or_negp(const DevParams& prm, const Lane& q)
+{
+    bool o = (q.p < 0.0) | (q.x < prm.ext[0]) | (q.x > prm.ext[1]) | (q.y < prm.ext[2]) | (q.y > prm.ext[3]);
+    if (prm.ndim == 3 || prm.include_3rd_dim) o = o | (q.z < prm.ext[4]) | (q.z > prm.ext[5]);
+    return o;
+}
+
 // particle_module.f90:1602-1609
 __device__ __forceinline__ void negp_or_bc(const DevParams& prm, Lane& q, double* leak)
 {
@@ -730,6 +738,9 @@ push_kernel(const __grid_constant__ DevParams prm, const PtlSoA P, const float* 
 // ONE particle's line together (G x 32 contiguous bytes per corner), so a warp-wide load touches
 // 32/G lines; the G particles of a group are served in G rounds and every lane ends a round
 // with final values of the slots of its chunks, parked in shared memory for the owner lane.
+#ifndef GPAT_COOP_DEPTH
+#define GPAT_COOP_DEPTH 1
+#endif
 #ifdef GPAT_EXP_NOCVT  // timing experiment only (wrong numbers): what do the F2F conversions cost?
 __device__ __forceinline__ double cvt(float f) { return __hiloint2double(__float_as_int(f), 0); }
 #else
@@ -787,7 +798,9 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
             if (__all_sync(0xffffffffu, exhausted)) break;
             continue;
         }
-        if (state == ST_ADAPT) {  // top of the inner while body, particle_module.f90:1602-1612
+        // top of the inner while body, particle_module.f90:1602-1612.  One combined test keeps the
+        // common case (inside the extended box, p >= 0) to a single untaken branch.
+        if (state == ST_ADAPT && outside_or_negp(prm, q)) {
             negp_or_bc(prm, q, a.leak);
             if (q.count_flag != GPAT_COUNT_FLAG_INBOX) {
                 store_lane(a, P, idx, q);
@@ -814,60 +827,78 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
         }
         __syncwarp();
 
-        // ---- phase B: G rounds, one particle of the group per round ----
+        // ---- phase B: G rounds, one particle of the group per round; the loads of DEPTH rounds
+        // are in flight at once (the L2 round trip is the longest stall of the whole step) ----
+        {
+            constexpr int NLD = C::NC * C::CPL;  // 256-bit loads per lane per round
+            constexpr int DEPTH = (GPAT_COOP_DEPTH < C::G) ? GPAT_COOP_DEPTH : C::G;
+            float4 lo[DEPTH][NLD], hi[DEPTH][NLD];
+            auto issue = [&](int r, int slot) {
+                const long long cell = __double_as_longlong(par[(gbase + r) * C::PAR + 4]);
+                const float* base = fld + cell * stride + (gq * C::CPL) * 8;
 #pragma unroll
-        for (int r = 0; r < C::G; ++r) {
-            const int owner = gbase + r;
-            const double2* row = reinterpret_cast<const double2*>(par + owner * C::PAR);
-            const double2 pa = row[0], pb = row[1], pc = row[2];
-            const double rx = pa.x, ry = pa.y, t0 = pb.x, t1 = pb.y, rz = pc.y;
-            const long long cell = __double_as_longlong(pc.x);
-            // weights of half 0 / half 1 at each corner (time blend folded in)
-            double w0[C::NC], w1[C::NC];
-            {
-                const double rx1 = 1.0 - rx, ry1 = 1.0 - ry;
-                if (C::NC == 4) {
-                    const double a0 = ry1 * t0, b0 = ry * t0, a1 = ry1 * t1, b1 = ry * t1;
-                    w0[0] = rx1 * a0; w0[1] = rx * a0; w0[2] = rx1 * b0; w0[3] = rx * b0;
-                    w1[0] = rx1 * a1; w1[1] = rx * a1; w1[2] = rx1 * b1; w1[3] = rx * b1;
-                } else {
-                    const double rz1 = 1.0 - rz;
-                    const double wxy[4] = {rx1 * ry1, rx * ry1, rx1 * ry, rx * ry};
-                    const double z00 = rz1 * t0, z10 = rz * t0, z01 = rz1 * t1, z11 = rz * t1;
+                for (int c = 0; c < C::NC; ++c) {
+                    const float* pc_ = base + ((c & 1) + (long long)((c >> 1) & 1) * prm.nxg +
+                                               (long long)(c >> 2) * prm.nxg * prm.nyg) * stride;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        w0[c] = wxy[c] * z00; w0[c + 4] = wxy[c] * z10;
-                        w1[c] = wxy[c] * z01; w1[c + 4] = wxy[c] * z11;
+                    for (int j = 0; j < C::CPL; ++j)
+                        ldg256(pc_ + 8 * j, lo[slot][c * C::CPL + j], hi[slot][c * C::CPL + j]);
+                }
+            };
+#pragma unroll
+            for (int r = 0; r < DEPTH; ++r) issue(r, r);
+#pragma unroll
+            for (int r = 0; r < C::G; ++r) {
+                const int owner = gbase + r;
+                const int slot = r % DEPTH;
+                const double2* row = reinterpret_cast<const double2*>(par + owner * C::PAR);
+                const double2 pa = row[0], pb = row[1];
+                const double rx = pa.x, ry = pa.y, t0 = pb.x, t1 = pb.y;
+                // weights of half 0 / half 1 at each corner (time blend folded in)
+                double w0[C::NC], w1[C::NC];
+                {
+                    const double rx1 = 1.0 - rx, ry1 = 1.0 - ry;
+                    if (C::NC == 4) {
+                        const double a0 = ry1 * t0, b0 = ry * t0, a1 = ry1 * t1, b1 = ry * t1;
+                        w0[0] = rx1 * a0; w0[1] = rx * a0; w0[2] = rx1 * b0; w0[3] = rx * b0;
+                        w1[0] = rx1 * a1; w1[1] = rx * a1; w1[2] = rx1 * b1; w1[3] = rx * b1;
+                    } else {
+                        const double rz = par[owner * C::PAR + 5];
+                        const double rz1 = 1.0 - rz;
+                        const double wxy[4] = {rx1 * ry1, rx * ry1, rx1 * ry, rx * ry};
+                        const double z00 = rz1 * t0, z10 = rz * t0, z01 = rz1 * t1, z11 = rz * t1;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            w0[c] = wxy[c] * z00; w0[c + 4] = wxy[c] * z10;
+                            w1[c] = wxy[c] * z01; w1[c + 4] = wxy[c] * z11;
+                        }
                     }
                 }
-            }
-            double acc[C::CPL][4];
+                double acc[C::CPL][4];
 #pragma unroll
-            for (int j = 0; j < C::CPL; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
-            const float* base = fld + cell * stride + (gq * C::CPL) * 8;
+                for (int j = 0; j < C::CPL; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
 #pragma unroll
-            for (int c = 0; c < C::NC; ++c) {
-                const float* pc_ = base + ((c & 1) + (long long)((c >> 1) & 1) * prm.nxg +
-                                           (long long)(c >> 2) * prm.nxg * prm.nyg) * stride;
+                for (int c = 0; c < C::NC; ++c) {
+#pragma unroll
+                    for (int j = 0; j < C::CPL; ++j) {
+                        const float4 f0 = lo[slot][c * C::CPL + j], f1 = hi[slot][c * C::CPL + j];
+                        acc[j][0] = fma(cvt(f0.x), w0[c], acc[j][0]);
+                        acc[j][1] = fma(cvt(f0.y), w0[c], acc[j][1]);
+                        acc[j][2] = fma(cvt(f0.z), w0[c], acc[j][2]);
+                        acc[j][3] = fma(cvt(f0.w), w0[c], acc[j][3]);
+                        acc[j][0] = fma(cvt(f1.x), w1[c], acc[j][0]);
+                        acc[j][1] = fma(cvt(f1.y), w1[c], acc[j][1]);
+                        acc[j][2] = fma(cvt(f1.z), w1[c], acc[j][2]);
+                        acc[j][3] = fma(cvt(f1.w), w1[c], acc[j][3]);
+                    }
+                }
+                if (r + DEPTH < C::G) issue(r + DEPTH, slot);
+                double2* out = reinterpret_cast<double2*>(res + owner * C::ROW + (gq * C::CPL) * 4);
 #pragma unroll
                 for (int j = 0; j < C::CPL; ++j) {
-                    float4 f0, f1;
-                    ldg256(pc_ + 8 * j, f0, f1);
-                    acc[j][0] = fma(cvt(f0.x), w0[c], acc[j][0]);
-                    acc[j][1] = fma(cvt(f0.y), w0[c], acc[j][1]);
-                    acc[j][2] = fma(cvt(f0.z), w0[c], acc[j][2]);
-                    acc[j][3] = fma(cvt(f0.w), w0[c], acc[j][3]);
-                    acc[j][0] = fma(cvt(f1.x), w1[c], acc[j][0]);
-                    acc[j][1] = fma(cvt(f1.y), w1[c], acc[j][1]);
-                    acc[j][2] = fma(cvt(f1.z), w1[c], acc[j][2]);
-                    acc[j][3] = fma(cvt(f1.w), w1[c], acc[j][3]);
+                    out[2 * j] = make_double2(acc[j][0], acc[j][1]);
+                    out[2 * j + 1] = make_double2(acc[j][2], acc[j][3]);
                 }
-            }
-            double2* out = reinterpret_cast<double2*>(res + owner * C::ROW + (gq * C::CPL) * 4);
-#pragma unroll
-            for (int j = 0; j < C::CPL; ++j) {
-                out[2 * j] = make_double2(acc[j][0], acc[j][1]);
-                out[2 * j + 1] = make_double2(acc[j][2], acc[j][3]);
             }
         }
         __syncwarp();
