@@ -301,3 +301,113 @@ def test_edge_cases():
     with pytest.raises(GpatError):
         GpatSim(bad, 64)
     g.close()
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE.json's full sizes: size-independent properties + a sub-population against the oracle
+def test_full_size_c1_properties():
+    """C1 at its full shape (1024^2 field, 1e6 particles), production build, two intervals with
+    splitting: integer bookkeeping exact, weights conserved, everybody on the frame time, and a
+    2000-particle sub-population re-run on the oracle (same Philox streams) agrees."""
+    from stochastic_parker_b200 import WORKLOADS, config, mhd
+    w = WORKLOADS["c1"].scaled()
+    n = 1_000_000
+    cfg = mhd.mhd_config(w.nx, w.ny, w.nz, w.lx, w.ly, w.lz, w.dt_out, w.ndim)
+    P = config.build_params(w.conf_text(), cfg, w.ndim, nframes=200, cli=w.cli)
+    frames = [mhd.make_frame(w.kind, w.nx, w.ny, w.nz, f, w.dt_out) for f in range(3)]
+    g = GpatSim(P, 2 * n)
+    g.upload_fields(0, frames[0])
+    g.upload_fields(1, frames[1])
+    g.inject_uniform(n, 0.0, 1, w.particle_v0, 0.0, w.dt_out, box_of(P), w.power_index)
+    start = g.download_particles()
+    steps1 = g.particle_mover(0.0, w.dt_out, 100, 1, 0)
+    a = g.download_particles()
+    assert len(a) == n and steps1 > 100 * n
+    assert int(rng_steps(a).sum()) == steps1            # one Philox block per push, nothing else
+    assert np.all(a["count_flag"] == 1) and a["weight"].sum() == float(n)
+    assert np.max(np.abs(a["t"] - w.dt_out)) < 1e-13
+    assert a["x"].min() >= P.xmin and a["x"].max() <= P.xmax and a["y"].min() >= P.ymin and a["y"].max() <= P.ymax
+    assert np.array_equal(np.sort(a["tag_injected"]), np.arange(n))
+    # sub-population on the oracle
+    sel = np.sort(np.random.default_rng(0).choice(n, 2000, replace=False))
+    o = Oracle(P, 4096)
+    o.upload_fields(0, frames[0])
+    o.upload_fields(1, frames[1])
+    o.upload_particles(start[sel])
+    so = o.particle_mover(0.0, w.dt_out, 100, 1, 0)
+    b = sort_by_key(o.download_particles())
+    ga = sort_by_key(a[np.isin(a["tag_injected"], start["tag_injected"][sel])])
+    assert abs(int(rng_steps(ga).sum()) - so) <= 2e-3 * so
+    assert_particles_close(ga, b, FRAME_RTOL, "c1 full size", int_exact=False, frac_outliers=0.01)
+    # second interval with a low split threshold: weight is conserved by splitting, histograms add up
+    g.swap_fields()
+    g.upload_fields(1, frames[2])
+    g.particle_mover(w.dt_out, w.dt_out, 100, 1, 0)
+    g.split(1.02, 1.02)
+    c = g.counters()
+    d = g.diagnostics(True)
+    assert c.nptl_current == d["quick"][0] > n and c.nptl_split == c.nptl_current - n
+    assert d["quick"][2] == float(n)                    # sum of weights, exact (dyadic)
+    assert d["fglobal"].sum() == float(n)               # every particle is inside (pmin, pmax]
+    for k in range(3):
+        fl = d["flocal"][k]
+        assert fl[..., -1, :].sum() == 0.0 and 0 < fl.sum() <= float(n)
+    g.close()
+
+
+def test_full_size_c4_and_c5_layouts_run():
+    """The two other field-record layouts at a size where the field store no longer fits L2
+    (C4: 2-D + D_pp, 24 slots; C5: 3-D, 24 slots): counters consistent, no particle lost."""
+    from stochastic_parker_b200 import WORKLOADS, config, mhd
+    for key, grid, n in (("c4", 2048, 400_000), ("c5", 192, 400_000)):
+        w = WORKLOADS[key].scaled(grid=grid)
+        cfg = mhd.mhd_config(w.nx, w.ny, w.nz, w.lx, w.ly, w.lz, w.dt_out, w.ndim)
+        P = config.build_params(w.conf_text(), cfg, w.ndim, nframes=200, cli=w.cli)
+        g = GpatSim(P, 2 * n)
+        for s in (0, 1):
+            g.upload_fields(s, mhd.make_frame(w.kind, w.nx, w.ny, w.nz, s, w.dt_out))
+        g.inject_uniform(n, 0.0, 1, w.particle_v0, 0.0, w.dt_out, box_of(P), w.power_index)
+        steps = g.particle_mover(0.0, w.dt_out, 100, 1, 0)
+        a = g.download_particles()
+        assert len(a) == n and int(rng_steps(a).sum()) == steps > 10 * n
+        assert np.max(np.abs(a["t"] - w.dt_out)) < 1e-13 and np.all(np.isfinite(a["p"])) and a["p"].min() >= 0.25 * P.p0
+        g.close()
+
+
+def _free_port():
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def test_two_gpus_nccl_allreduce(tmp_path):
+    """N = 2: two processes, one GPU each, the library's own NCCL all-reduce inside
+    gpat_diagnostics.  Reduced histograms == histograms of the union of the shards, bit for bit."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(root, "tests", "multigpu_worker.py"), str(tmp_path), "20001"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    shards = [np.load(tmp_path / f"ptl_{k}.npy") for k in range(2)]
+    red = [np.load(tmp_path / f"reduced_{k}.npz") for k in range(2)]
+    w, P, frames, ts = make_case("c1", grid=64, nptl=20001)
+    o = Oracle(P, 8 * 20001)
+    o.upload_particles(np.concatenate(shards))
+    d = o.diagnostics(True)
+    for k in range(2):  # all-reduce: every rank holds the reduced arrays
+        assert np.array_equal(red[k]["fglobal"], d["fglobal"])
+        for j in range(3):
+            assert np.array_equal(red[k][f"flocal{j}"], d["flocal"][j])
+        assert red[k]["quick"][0] == len(shards[0]) + len(shards[1])
+        assert red[k]["quick"][2] == d["quick"][2] and float(red[k]["pmax"]) == d["pmax"]
+        assert red[k]["quick"][6] == d["quick"][6] and red[k]["quick"][7] == d["quick"][7]
