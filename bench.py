@@ -236,9 +236,7 @@ def main():
     sim = spb.GpatSim(P, w.nptl_max, device=local_rank)
     if world > 1:
         # NCCL communicator of the library (histogram all-reduce), id distributed by torch
-        obj = [sim.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(obj, src=0)
-        sim.comm_init(obj[0], world, rank)
+        spb.bootstrap_comm(sim, dist)
 
     nint = args.warmup + args.steps
     shape = (w.ny + 4, w.nx + 4, 8) if w.ndim == 2 else (w.nz + 4, w.ny + 4, w.nx + 4, 8)
@@ -295,7 +293,7 @@ def main():
     e2e_s = time.perf_counter() - t_e2e0
     clocks = sampler.stop() if sampler else {}
     launches = sim.timings().total_launches - launches0
-    nptl_end = int(d["quick"][0])
+    nptl_end = int(sim.counters().nptl_current)  # this rank (quick[0] is already summed over ranks)
 
     # max over ranks of the device times, sum over ranks of the work
     vec = torch.tensor([tot["mover_ms"], tot["push_ms"], e2e_s * 1e3], dtype=torch.float64, device=dev)
@@ -334,7 +332,8 @@ def main():
             "field_layout": layout, "strict_math": int(args.strict),
             "step": "one MHD interval (dt_out) of the whole population",
             "parallelism": f"particles sharded over {world} GPU(s), full field per GPU, NCCL allreduce of histograms",
-            "l2": "field store (135 MB at 1024^2) + particle arrays exceed the 126 MB L2; frames change every step",
+            "l2": "no flush: the two-frame field store (135 MB at 1024^2) plus the particle arrays (102 MB) exceed "
+                  "the 126 MB L2, and every step uploads a new MHD frame and repacks half of the store",
             "source": w.source,
         },
         "e2e": {"value": total_steps / (e2e_ms * 1e-3), "unit": "particle-steps/s",

@@ -741,11 +741,43 @@ push_kernel(const __grid_constant__ DevParams prm, const PtlSoA P, const float* 
 #ifndef GPAT_COOP_DEPTH
 #define GPAT_COOP_DEPTH 1
 #endif
-#ifdef GPAT_EXP_NOCVT  // timing experiment only (wrong numbers): what do the F2F conversions cost?
-__device__ __forceinline__ double cvt(float f) { return __hiloint2double(__float_as_int(f), 0); }
-#else
-__device__ __forceinline__ double cvt(float f) { return (double)f; }
+// FP32 -> FP64 on the integer pipe.  F2F.F64.F32 runs on the XU at 16 lanes/clk/SM (2 cycles per
+// warp instruction, scripts/micro/pipes.cu) and the 128 conversions of a 2-D step were the busiest
+// pipe of the kernel.  Placing the float's sign | 8-bit exponent | 23-bit mantissa into the
+// sign | 11-bit exponent | 52-bit mantissa fields of a double WITHOUT re-biasing the exponent gives
+// exactly f * 2^-896 (zero, denormals and signs included), and the missing 2^896 is folded into the
+// interpolation weight, so the FMA sees the same exact product f*w as with a real conversion.
+// GPAT_CVT_ALU_MASK picks which (row cy, frame half h) quarter of the corner values goes this
+// way: bit 2*cy + h.
+#ifndef GPAT_CVT_ALU_MASK
+#define GPAT_CVT_ALU_MASK 0
 #endif
+constexpr double kTwo896 = 5.2829453113566525e+269;  // 2^896
+__device__ __forceinline__ double cvt(float f) { return (double)f; }
+__device__ __forceinline__ double cvt_scaled(float f)  // f * 2^-896
+{
+    const int b = __float_as_int(f);
+    return __hiloint2double((b >> 3) & 0x8fffffff, b << 29);
+}
+template <int CY, int H> __device__ __forceinline__ double cvt_sel(float f)
+{
+    if constexpr ((GPAT_CVT_ALU_MASK >> (2 * CY + H)) & 1) return cvt_scaled(f);
+    else return cvt(f);
+}
+__host__ __device__ constexpr double cvt_weight_scale(int cy, int h) { return ((GPAT_CVT_ALU_MASK >> (2 * cy + h)) & 1) ? kTwo896 : 1.0; }
+
+// acc[0..3] += four slots of one frame half at corner c (row cy = bit 1 of c) times its weight
+template <int CYDUMMY, int H>
+__device__ __forceinline__ void fma_chunk(int c, const float4& f, double w, double (&acc)[4])
+{
+    if ((c >> 1) & 1) {
+        acc[0] = fma(cvt_sel<1, H>(f.x), w, acc[0]); acc[1] = fma(cvt_sel<1, H>(f.y), w, acc[1]);
+        acc[2] = fma(cvt_sel<1, H>(f.z), w, acc[2]); acc[3] = fma(cvt_sel<1, H>(f.w), w, acc[3]);
+    } else {
+        acc[0] = fma(cvt_sel<0, H>(f.x), w, acc[0]); acc[1] = fma(cvt_sel<0, H>(f.y), w, acc[1]);
+        acc[2] = fma(cvt_sel<0, H>(f.z), w, acc[2]); acc[3] = fma(cvt_sel<0, H>(f.w), w, acc[3]);
+    }
+}
 
 template <int L> struct Coop {
     static constexpr int NREC = Rec<L>::NREC;
@@ -859,7 +891,8 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                 {
                     const double rx1 = 1.0 - rx, ry1 = 1.0 - ry;
                     if (C::NC == 4) {
-                        const double a0 = ry1 * t0, b0 = ry * t0, a1 = ry1 * t1, b1 = ry * t1;
+                        const double a0 = ry1 * t0 * cvt_weight_scale(0, 0), b0 = ry * t0 * cvt_weight_scale(1, 0);
+                        const double a1 = ry1 * t1 * cvt_weight_scale(0, 1), b1 = ry * t1 * cvt_weight_scale(1, 1);
                         w0[0] = rx1 * a0; w0[1] = rx * a0; w0[2] = rx1 * b0; w0[3] = rx * b0;
                         w1[0] = rx1 * a1; w1[1] = rx * a1; w1[2] = rx1 * b1; w1[3] = rx * b1;
                     } else {
@@ -869,8 +902,9 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                         const double z00 = rz1 * t0, z10 = rz * t0, z01 = rz1 * t1, z11 = rz * t1;
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
-                            w0[c] = wxy[c] * z00; w0[c + 4] = wxy[c] * z10;
-                            w1[c] = wxy[c] * z01; w1[c + 4] = wxy[c] * z11;
+                            const double s0 = cvt_weight_scale(c >> 1, 0), s1 = cvt_weight_scale(c >> 1, 1);
+                            w0[c] = wxy[c] * z00 * s0; w0[c + 4] = wxy[c] * z10 * s0;
+                            w1[c] = wxy[c] * z01 * s1; w1[c + 4] = wxy[c] * z11 * s1;
                         }
                     }
                 }
@@ -882,14 +916,8 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
 #pragma unroll
                     for (int j = 0; j < C::CPL; ++j) {
                         const float4 f0 = lo[slot][c * C::CPL + j], f1 = hi[slot][c * C::CPL + j];
-                        acc[j][0] = fma(cvt(f0.x), w0[c], acc[j][0]);
-                        acc[j][1] = fma(cvt(f0.y), w0[c], acc[j][1]);
-                        acc[j][2] = fma(cvt(f0.z), w0[c], acc[j][2]);
-                        acc[j][3] = fma(cvt(f0.w), w0[c], acc[j][3]);
-                        acc[j][0] = fma(cvt(f1.x), w1[c], acc[j][0]);
-                        acc[j][1] = fma(cvt(f1.y), w1[c], acc[j][1]);
-                        acc[j][2] = fma(cvt(f1.z), w1[c], acc[j][2]);
-                        acc[j][3] = fma(cvt(f1.w), w1[c], acc[j][3]);
+                        fma_chunk<0, 0>(c, f0, w0[c], acc[j]);
+                        fma_chunk<0, 1>(c, f1, w1[c], acc[j]);
                     }
                 }
                 if (r + DEPTH < C::G) issue(r + DEPTH, slot);

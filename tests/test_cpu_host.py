@@ -207,3 +207,33 @@ def test_fastmath_accuracy_on_host(tmp_path):
     vals = dict(zip(out[0::2], (float(v) for v in out[1::2])))
     assert vals["rcp"] <= 2 and vals["rsqrt"] <= 2 and vals["sqrt"] <= 1 and vals["log"] <= 2 and vals["exp"] <= 2
     assert vals["pow_rel"] < 5e-15
+
+
+# ---- C++ host driver (host/gpat_driver.cpp) ---------------------------------------------------------
+def _build_driver():
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "host")], check=True)
+    return os.path.join(ROOT, "host", "gpat_driver")
+
+
+def test_cpp_driver_accepts_the_reference_command_line(tmp_path):
+    """The switches of examples/reconnection_2d/diffusion_reconnection.sh:137-164 parse; an unknown
+    switch is an error; with no GPU the run stops at gpat_init with the library's message."""
+    from stochastic_parker_b200 import WORKLOADS, mhd
+    exe = _build_driver()
+    w = WORKLOADS["c1"].scaled(grid=16, nptl=64)
+    mhd.write_run(str(tmp_path / "mhd"), w.kind, w.nx, w.ny, w.nz, nframes=3)
+    conf = tmp_path / "conf.dat"
+    conf.write_text(w.conf_text())
+    args = [exe, "-qh", "5.0", "-rf", ".false.", "-ft", ".false.", "-nl", ".false.", "-kk", "0.01", "-pv", "17.2",
+            "-sm", "1", "-dm", str(tmp_path / "mhd") + "/", "-mc", "mhd_config.dat", "-np", "64", "-ti", "1",
+            "-ts", "0", "-te", "2", "-st", "0", "-df", "1", "-pi", "6.2", "-sf", "1", "-sr", "2.0", "-ps", "2.0",
+            "-ni", "100", "-dd", str(tmp_path) + "/", "-cf", str(conf), "-ld", ".true.", "-nm", "1000",
+            "-in", ".false.", "-dw", "0", "-ds", "0", "-t0", "7.53877e-5", "-nd", "2", "-dp1", "850964.408",
+            "-dp2", "13575468.975", "-ch", "-1", "-ug", "1", "-cd", "0"]
+    r = subprocess.run(args + ["--no_such_switch", "1"], capture_output=True, text=True)
+    assert r.returncode == 2 and "unknown switch" in r.stderr
+    r = subprocess.run(args[:-2] + ["-is", ".true."], capture_output=True, text=True)
+    assert r.returncode == 2 and "outside the GPU particle path" in r.stderr
+    if not _has_gpu():
+        r = subprocess.run(args, capture_output=True, text=True)
+        assert r.returncode == 1 and "gpat_init failed (2)" in r.stderr and "no CPU fallback" in r.stderr

@@ -411,3 +411,49 @@ def test_two_gpus_nccl_allreduce(tmp_path):
         assert red[k]["quick"][0] == len(shards[0]) + len(shards[1])
         assert red[k]["quick"][2] == d["quick"][2] and float(red[k]["pmax"]) == d["pmax"]
         assert red[k]["quick"][6] == d["quick"][6] and red[k]["quick"][7] == d["quick"][7]
+
+
+def test_cpp_driver_matches_python_driver(tmp_path):
+    """host/gpat_driver (C++ above the C ABI, the reference's switches and files) writes the same
+    quick.dat numbers and bit-identical spectra as run_intervals through ctypes."""
+    import os
+    import subprocess
+    from stochastic_parker_b200 import WORKLOADS, config, mhd
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-s", "-C", os.path.join(root, "host")], check=True)
+    w = WORKLOADS["c1"].scaled(grid=64, nptl=5000)
+    nfr = 4
+    cfg = mhd.write_run(str(tmp_path / "mhd"), w.kind, w.nx, w.ny, w.nz, nframes=nfr, lx=w.lx, ly=w.ly, lz=w.lz,
+                        dt_out=w.dt_out)
+    conf = tmp_path / "conf.dat"
+    conf.write_text(w.conf_text())
+    out = tmp_path / "out"
+    out.mkdir()
+    args = [os.path.join(root, "host", "gpat_driver"), "-nl", ".false.", "-pv", repr(w.particle_v0),
+            "-dm", str(tmp_path / "mhd") + "/", "-np", "5000", "-ti", "1", "-ts", "0", "-te", str(nfr - 1),
+            "-df", "1", "-pi", "6.2", "-sf", "1", "-sr", "1.05", "-ps", "1.05", "-ni", "100", "-dt", "0.0",
+            "-dd", str(out) + "/", "-cf", str(conf), "-ld", ".true.", "-nm", "40000", "-in", ".true.",
+            "-t0", "7.53877e-5", "-nd", "2", "-dp1", "850964.408", "-dp2", "13575468.975", "-ch", "-1"]
+    r = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    P = config.build_params(w.conf_text(), mhd.read_mhd_config(str(tmp_path / "mhd" / "mhd_config.dat")), 2,
+                            nframes=nfr - 1, cli=w.cli)
+    g = GpatSim(P, 40000)
+    frames = [mhd.read_frame(str(tmp_path / "mhd"), f, dict(cfg, ndim=2)) for f in range(nfr)]
+    rec, steps = run_intervals(g, frames, [f * w.dt_out for f in range(nfr)], nptl=5000, dist_flag=1,
+                               particle_v0=w.particle_v0, power_index=6.2, split_ratio=1.05, pmin_split=1.05)
+    assert f"Total particle steps: {steps} " in r.stdout
+    for d in rec:
+        raw = open(out / f"fdists_{d['frame']:04d}.bin", "rb").read()
+        nmu, npp = np.frombuffer(raw[:8], dtype=np.int32)
+        fg = np.frombuffer(raw[8:8 + 8 * nmu * npp], dtype=np.float64).reshape(npp, nmu)
+        assert np.array_equal(fg, d["fglobal"])
+        loc = open(out / f"fdists_local2_{d['frame']:04d}.bin", "rb").read()
+        shp = np.frombuffer(loc[:20], dtype=np.int32)
+        assert np.array_equal(np.frombuffer(loc[20:], dtype=np.float64).reshape(tuple(shp[::-1])), d["flocal"][1])
+    rows = [l.split() for l in open(out / "quick.dat").read().splitlines()]
+    assert rows[0][:3] == ["iframe", "nptl_current", "nptl_split"] and len(rows) == 1 + nfr
+    last = open(out / "quick.dat").read().splitlines()[-1]
+    assert last[:6] == f"{nfr - 1:06d}" and float(last[6:19]) == float(f"{rec[-1]['quick'][0]:.6E}")
+    assert len(open(out / "pmax_global.dat").read().split()) == nfr
+    g.close()
