@@ -750,7 +750,7 @@ push_kernel(const __grid_constant__ DevParams prm, const PtlSoA P, const float* 
 // GPAT_CVT_ALU_MASK picks which (row cy, frame half h) quarter of the corner values goes this
 // way: bit 2*cy + h.
 #ifndef GPAT_CVT_ALU_MASK
-#define GPAT_CVT_ALU_MASK 0
+#define GPAT_CVT_ALU_MASK 10  // the second frame half on the integer pipe: XU 60 % -> 33 %, +1.8 % steps/s on C1
 #endif
 constexpr double kTwo896 = 5.2829453113566525e+269;  // 2^896
 __device__ __forceinline__ double cvt(float f) { return (double)f; }

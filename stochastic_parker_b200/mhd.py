@@ -85,19 +85,23 @@ def _fields_flare_2d(X, Y, t):
 
 
 def _fields_shock_2d(X, Y, t):
-    """Planar shock moving along +x with compression ratio 4 (upstream on the left)."""
+    """Planar shock moving along +x with compression ratio 4 (upstream on the left).  A weak
+    smooth ripple covers the whole box: exactly uniform regions would make dx/dt, dy/dt or dp/dt
+    exactly zero, and the reference then falls back to dt = dt_min (particle_module.f90:3532-3534),
+    which no real MHD frame ever triggers."""
     w = 2.0 / X.shape[-1]
     xs = 0.45 + 0.05 * t
     u_u, u_d = 1.0, 0.25
     prof = 0.5 * (1.0 - np.tanh((X - xs) / w))  # 1 upstream, 0 downstream
     ripple = 0.02 * np.sin(2 * np.pi * Y)
-    vx = u_d + (u_u - u_d) * prof + ripple * (1 - prof)
-    vy = 0.02 * np.cos(2 * np.pi * Y) * (1 - prof)
+    thx, thy = 2 * np.pi * X, 2 * np.pi * Y
+    vx = u_d + (u_u - u_d) * prof + ripple * (1 - prof) + 0.004 * np.sin(thx + 0.3) * np.cos(thy)
+    vy = 0.02 * np.cos(2 * np.pi * Y) * (1 - prof) + 0.003 * np.cos(thx) * np.sin(thy + 0.2)
     vz = 0.0 * X
     rho = 4.0 - 3.0 * prof
-    bx = 0.5 + 0.0 * X
-    by = 0.3 * rho
-    bz = 0.05 * rho
+    bx = 0.5 + 0.01 * np.cos(thy) * np.sin(thx)
+    by = 0.3 * rho + 0.01 * np.sin(thx + 0.7)
+    bz = 0.05 * rho + 0.005 * np.cos(thx) * np.cos(thy)
     return vx, vy, vz, rho, bx, by, bz
 
 

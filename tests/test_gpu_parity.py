@@ -457,3 +457,40 @@ def test_cpp_driver_matches_python_driver(tmp_path):
     assert last[:6] == f"{nfr - 1:06d}" and float(last[6:19]) == float(f"{rec[-1]['quick'][0]:.6E}")
     assert len(open(out / "pmax_global.dat").read().split()) == nfr
     g.close()
+
+
+def test_restart_round_trip_is_bit_exact():
+    """dump_particles / read_particles + save/read_particle_module_state (diagnostics.f90:1811-1888,
+    particle_module.f90:5532-5664, 5744-5816): a run that is stopped after one interval, downloaded
+    to the AoS records of the restart file (Philox counters ride in `padding`), and resumed in a
+    NEW handle continues bit-identically to the uninterrupted run."""
+    w, P, frames, ts = make_case("c1", grid=64, nptl=3000, nframes=4)
+    kw = dict(nptl=3000, dist_flag=2, particle_v0=w.particle_v0, pmin_split=1.05, split_ratio=1.05,
+              inject_new_ptl=True)
+    for strict in (1, 0):
+        Pg = P.copy()
+        Pg.strict_math = strict
+        a = GpatSim(Pg, w.nptl_max * 4)
+        run_intervals(a, frames, ts, **kw)
+        ref = a.download_particles()
+        ca = a.counters()
+        a.close()
+        b = GpatSim(Pg, w.nptl_max * 4)
+        run_intervals(b, frames[:2], ts[:2], **kw)          # first interval only
+        dump, cb = b.download_particles(), b.counters()
+        b.close()
+        c = GpatSim(Pg, w.nptl_max * 4)                     # "restart"
+        c.upload_particles(dump)
+        c.set_counters(cb)
+        c.upload_fields(0, frames[1])
+        for tf in (2, 3):                                    # the loop of run_intervals from frame 2 on
+            c.upload_fields(1, frames[tf])
+            c.inject_uniform(3000, 0.0, 2, w.particle_v0, ts[tf - 1], ts[tf] - ts[tf - 1], box_of(P), 6.2)
+            c.particle_mover(ts[tf - 1], ts[tf] - ts[tf - 1], 100, 1, 0)
+            c.split(1.05, 1.05)
+            c.swap_fields()
+        got, cc = c.download_particles(), c.counters()
+        assert_particles_identical(got, ref, f"restart strict={strict}")
+        assert (cc.nptl_current, cc.nptl_split, cc.tag_max, cc.leak, cc.leak_negp) == \
+               (ca.nptl_current, ca.nptl_split, ca.tag_max, ca.leak, ca.leak_negp)
+        c.close()
