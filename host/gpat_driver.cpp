@@ -134,7 +134,7 @@ void define_switches(Cli& c)
     c.def("--duu_init", "-du", "1.0");               c.def("--dump_escaped_dist", "-ded", ".false.");
     c.def("--dump_escaped", "-de", ".false.");
     // this driver only
-    c.def("--device", "-gpu", "0");                  c.def("--seed", "-seed", "97394724");  // 0x5DE2024
+    c.def("--device", "-gpu", "0");                  c.def("--seed", "-seed", "98443300");  // 0x5DE2024
     c.def("--strict_math", "-strict", "0");
 }
 
