@@ -284,7 +284,11 @@ static void get_interp_parameters(const orc_sim* S, double px, double py, double
                                   double w[8])
 {
     double rx, ry, rz;
-    if (S->P.ndim == 2) {
+    if (S->P.ndim == 1) { /* PM:649-652 */
+        pos[0] = (int)floor(px) + 1; pos[1] = 1; pos[2] = 1;
+        ry = 0.0;
+        rz = 0.0;
+    } else if (S->P.ndim == 2) {
         pos[0] = (int)floor(px) + 1; pos[1] = (int)floor(py) + 1; pos[2] = 1;
         ry = py - pos[1] + 1;
         rz = 0.0;
@@ -394,6 +398,14 @@ static void calc_kappa(const orc_sim* S, const gpat_particle* ptl, const double*
     kp->skperp = sqrt(2.0 * kp->kperp);
     kp->skpara_perp = sqrt(2.0 * (kp->kpara - kp->kperp));
 
+    if (P->ndim == 1) {
+        /* PM:2271-2292.  With mag_dependency = 1 the reference multiplies by a db_dx that this
+         * branch never assigns (PM:2274): undefined there, rejected by
+         * orc_create_checked / gpat_init here, so dkdx is 0 whenever this line is reached. */
+        double dkdx = 0.0;
+        kp->dkxx_dx = kp->kpara * dkdx; /* not focused transport */
+        return;
+    }
     int three = (P->ndim == 3) || (P->ndim == 2 && P->include_3rd_dim);
     double dbx_dx = FG(13), dbx_dy = FG(14), dby_dx = FG(16), dby_dy = FG(17);
     double db_dx = FG(22), db_dy = FG(23);
@@ -471,6 +483,11 @@ static void calc_kappa_nlgc(const orc_sim* S, const gpat_particle* ptl, const do
     kp->skperp = sqrt(2.0 * kp->kperp);
     kp->skpara_perp = sqrt(2.0 * (kp->kpara - kp->kperp));
 
+    if (P->ndim == 1) { /* PM:2535-2562, same uninitialised db_dx with mag_dependency = 1 */
+        double dkpara_dx = 0.0;
+        kp->dkxx_dx = kp->kpara * dkpara_dx;
+        return;
+    }
     int three = (P->ndim == 3) || (P->ndim == 2 && P->include_3rd_dim);
     double dbx_dx = FG(13), dbx_dy = FG(14), dby_dx = FG(16), dby_dy = FG(17);
     double db_dx = FG(22), db_dy = FG(23);
@@ -603,6 +620,52 @@ static double drift_vdp(const orc_sim* S, const gpat_particle* ptl)
     /* `1.0 / (3 * pcharge)` is a default-real division, PM:3436 */
     float q = 1.0f / (float)(3 * P->pcharge);
     return (double)q / sqrt(sq(P->drift1 * P->p0 / ptl->p) + sq(P->drift2 * sq(P->p0) / sq(ptl->p)));
+}
+
+/* ------------------------------------------------------------------------ */
+/* push_particle_1d, PM:2993-3111 (Cartesian, uniform grid): two uniforms per */
+/* step, ran1 for x then one for p (PM:3085-3088)                             */
+/* ------------------------------------------------------------------------ */
+static void push_particle_1d(orc_sim* S, gpat_particle* ptl, const double* fields,
+                             const kappa_type* kp, int fixed_dt, const double u[4], double* deltax,
+                             double* deltap)
+{
+    const gpat_params* P = &S->P;
+    double vx = F(1), bx = F(5), by = F(6), bz = F(7);
+    double b = sqrt(sq(bx) + sq(by) + sq(bz));
+    double dvx_dx = FG(1);
+    double dxm = P->dx;
+    double dx_dt = vx + kp->dkxx_dx; /* PM:3036 */
+    double divv = dvx_dx;
+    double dp_dt = -ptl->p * divv / 3.0;
+    double dpp = 0.0;
+    if (P->dpp_wave) calc_dpp_wave_scattering(S, F(4), b, kp->kpara, ptl, &dp_dt, &dpp);
+    if (P->dpp_shear) { /* PM:3050-3056: `divv / 3` is an integer literal promoted to f64 */
+        double sxx = dvx_dx - divv / 3.0, syy = -divv / 3.0, szz = -divv / 3.0;
+        calc_dpp_flow_shear(S, b, bx, by, bz, kp->knorm_para, sxx, syy, szz, 0.0, 0.0, 0.0, ptl,
+                            &dp_dt, &dpp);
+    }
+    if (!fixed_dt) {
+        if (dx_dt != 0.0 && dp_dt != 0.0) { /* PM:3060-3072 */
+            double s = (kp->skperp > 0.0) ? kp->skperp : kp->skpara;
+            double d = sq(0.5 * dxm / kp->skpara);
+            d = min2(d, sq(s / dx_dt));
+            d = min2(d, (double)0.1f * ptl->p / fabs(dp_dt));
+            ptl->dt = d;
+        } else {
+            ptl->dt = S->dt_min;
+        }
+        if (ptl->dt < S->dt_min) ptl->dt = S->dt_min;
+        if (ptl->dt > S->dt_max) ptl->dt = S->dt_max;
+    }
+    double sdt = sqrt(ptl->dt);
+    double sqrt3 = sqrt(3.0);
+    double ran1 = (2.0 * u[0] - 1.0) * sqrt3;
+    *deltax = dx_dt * ptl->dt + ran1 * kp->skpara * sdt;
+    ptl->x = ptl->x + *deltax;
+    ptl->t = ptl->t + ptl->dt;
+    double ranp = (2.0 * u[1] - 1.0) * sqrt3;
+    update_momentum(S, ptl, dp_dt, dpp, sdt, ranp, deltap);
 }
 
 /* ------------------------------------------------------------------------ */
@@ -856,7 +919,9 @@ static void one_push(orc_sim* S, gpat_particle* ptl, double t0, double dtf, int 
     else
         calc_kappa(S, ptl, fields, &kp);
     step_uniforms(S, ptl, u);
-    if (P->ndim == 2 && !P->include_3rd_dim)
+    if (P->ndim == 1)
+        push_particle_1d(S, ptl, fields, &kp, fixed_dt, u, deltax, deltap);
+    else if (P->ndim == 2 && !P->include_3rd_dim)
         push_particle_2d(S, ptl, fields, &kp, fixed_dt, u, deltax, deltay, deltap);
     else
         push_particle_3d_like(S, ptl, fields, &kp, fixed_dt, u, deltax, deltay, deltaz, deltap);

@@ -218,7 +218,7 @@ class Workload:
 
     @property
     def ndim(self) -> int:
-        return 3 if self.kind.endswith("3d") else 2
+        return 3 if self.kind.endswith("3d") else (1 if self.kind.endswith("1d") else 2)
 
     def conf_text(self) -> str:
         d = dict(p0=0.1, pmin=1.0e-2, pmax=1.0e1, momentum_dependency=1, gamma_turb=1.6666667,
@@ -232,7 +232,9 @@ class Workload:
         """Same physics on a smaller grid / population (parity-test sizes)."""
         w = dataclasses.replace(self)
         if grid is not None:
-            w.nx = w.ny = grid
+            w.nx = grid
+            if w.ndim >= 2:
+                w.ny = grid
             if w.ndim == 3:
                 w.nz = grid
         if nptl is not None:
@@ -244,6 +246,12 @@ class Workload:
 _DRIFT = dict(drift_param1=850964.408, drift_param2=13575468.975, charge=-1)
 
 WORKLOADS = {
+    # 1-D shock (push_particle_1d, particle_module.f90:2993-3111); mag_dependency must be 0 there
+    # because the reference's 1-D kappa branch reads an unassigned db_dx otherwise (:2274)
+    "s1": Workload("s1_shock_1d", "shock_1d", 2048, 1, 1, lx=8.0, ly=1.0,
+                   conf=dict(momentum_dependency=1, gamma_turb=3.0, mag_dependency=0,
+                             kpara0=8.0 / 2048 * 10 * 1.0, kret=0.03, pbcx=1, r1=4, r2=8, r3=16),
+                   cli=dict(_DRIFT), source="config/shock.sh:52 in 1-D"),
     # C1: examples/reconnection_2d/conf_reconnection.dat + diffusion_reconnection.sh:181-194
     "c1": Workload("c1_reconnection_2d", "reconnection_2d", 1024, 1024, 1,
                    conf=dict(kpara0=0.00743592, kret=0.01), cli=dict(_DRIFT, tau0=7.53877e-5),

@@ -160,9 +160,15 @@ int fail(gpat_sim* h, int code, const std::string& msg)
 
 int validate(const gpat_params* p, std::string& why)
 {
-    if (p->ndim != 2 && p->ndim != 3) { why = "ndim must be 2 or 3 (1-D push is not on the GPU path)"; return 1; }
+    if (p->ndim < 1 || p->ndim > 3) { why = "ndim must be 1, 2 or 3"; return 1; }
     if (p->nx < 1 || p->ny < 1 || p->nz < 1) { why = "bad grid"; return 1; }
     if (p->ndim == 2 && p->nz != 1) { why = "2-D runs need nz = 1"; return 1; }
+    if (p->ndim == 1 && (p->ny != 1 || p->nz != 1)) { why = "1-D runs need ny = nz = 1"; return 1; }
+    if (p->ndim == 1 && p->mag_dependency) {
+        // particle_module.f90:2274 / 2539 multiply by a db_dx the 1-D branch never assigns
+        why = "1-D with mag_dependency = 1 reads an uninitialised db_dx in the reference (undefined there)";
+        return 1;
+    }
     if (p->focused_transport) { why = "focused transport pushers are outside the GPU path"; return 1; }
     if (p->spherical_coord) { why = "spherical coordinates are outside the GPU path"; return 1; }
     if (p->nonuniform_grid) { why = "non-uniform grids are outside the GPU path"; return 1; }
@@ -177,7 +183,7 @@ int validate(const gpat_params* p, std::string& why)
         if (s.rx < 1 || s.ry < 1 || s.rz < 1 || s.npbins < 1 || s.nmu < 1) { why = "bad local histogram spec"; return 1; }
         int nrx = (p->nx + s.rx - 1) / s.rx, nry = (p->ny + s.ry - 1) / s.ry, nrz = (p->nz + s.rz - 1) / s.rz;
         // check_local_dist_configuration (diagnostics.f90:1976-2016)
-        if (nrx * s.rx != p->nx || nry * s.ry != p->ny || (p->ndim == 3 && nrz * s.rz != p->nz)) {
+        if (nrx * s.rx != p->nx || (p->ndim >= 2 && nry * s.ry != p->ny) || (p->ndim == 3 && nrz * s.rz != p->nz)) {
             why = "Wrong factor 'rx/ry/rz' for particle distribution";
             return 1;
         }
@@ -188,7 +194,8 @@ int validate(const gpat_params* p, std::string& why)
 int pick_layout(const gpat_params& p)
 {
     bool ext = p.dpp_wave || p.dpp_shear || (p.ndim == 2 && p.include_3rd_dim);
-    if (p.ndim == 2) return ext ? L2E : L2B;
+    // 1-D runs live in the 2-D record layouts (one physical row + one zero row, fill_dev_params)
+    if (p.ndim <= 2) return ext ? L2E : L2B;
     return ext ? L3E : L3B;
 }
 
@@ -198,7 +205,10 @@ void fill_dev_params(gpat_sim* h)
     DevParams& d = h->dp;
     d.ndim = p.ndim; d.nx = p.nx; d.ny = p.ny; d.nz = p.nz;
     d.nxg = p.nx + 4;
-    d.nyg = p.ny + 4;
+    // 1-D (farray(:, -1:nx+2, 1, 1), mhd_data_parallel.f90:78): the store gets a second, all-zero
+    // row so that the bilinear gather with ry = 0 reads defined memory and adds exact zeros
+    d.nyg = (p.ndim == 1) ? 2 : p.ny + 4;
+    d.nyg_src = (p.ndim == 1) ? 1 : p.ny + 4;
     d.nzg = (p.ndim == 3) ? p.nz + 4 : 1;
     d.time_interp = p.time_interp ? 1 : 0;
     for (int i = 0; i < 3; ++i) d.pbc[i] = p.pbc[i];
@@ -437,7 +447,8 @@ int run_push(gpat_sim* h, double t0, double dtf, int nsteps_interval, int num_fi
     CU(cudaMemsetAsync(h->d_queue, 0, 2 * sizeof(unsigned long long), h->st));
     CU(cudaEventRecord(h->ev[0], h->st));
     if (a.nptl > 0) {
-        if (h->hp.strict_math) launch_push_strict(h->layout, h->dp, h->P, h->fld, a, h->sm_count, h->st);
+        // 1-D (push_particle_1d) exists in the reference-order build only: it is not a throughput path
+        if (h->hp.strict_math || h->hp.ndim == 1) launch_push_strict(h->layout, h->dp, h->P, h->fld, a, h->sm_count, h->st);
         else launch_push_fast(h->layout, h->dp, h->P, h->fld, a, h->sm_count, h->st);
         h->tm.total_launches++;
     }
@@ -573,7 +584,7 @@ int gpat_upload_fields(gpat_handle h, int slot, const float* f, int nvar, int wi
     if (slot == 1 && !h->dp.time_interp)
         return fail(h, GPAT_ERR_INVALID, "gpat_upload_fields: slot 1 (farray2) exists only with time_interp = 1");
     CU(cudaSetDevice(h->device));
-    size_t bytes = (size_t)h->dp.nxg * h->dp.nyg * h->dp.nzg * nvar * sizeof(float);
+    size_t bytes = (size_t)h->dp.nxg * h->dp.nyg_src * h->dp.nzg * nvar * sizeof(float);
     if (bytes > h->stage_bytes) {
         if (h->stage) cudaFree(h->stage);
         h->stage = nullptr;
@@ -940,7 +951,7 @@ int gpat_debug_gradients(gpat_handle h, const float* f8, float* out32)
 {
     if (!h || !f8 || !out32) return GPAT_ERR_INVALID;
     CU(cudaSetDevice(h->device));
-    size_t ncell = (size_t)h->dp.nxg * h->dp.nyg * h->dp.nzg;
+    size_t ncell = (size_t)h->dp.nxg * h->dp.nyg_src * h->dp.nzg;
     float *d_in = nullptr, *d_out = nullptr;
     CU(cudaMalloc(&d_in, ncell * 8 * sizeof(float)));
     cudaError_t e = cudaMalloc(&d_out, ncell * 32 * sizeof(float));

@@ -98,7 +98,8 @@ __global__ void grad32_kernel(const float* __restrict__ src, GridDims g, float* 
 void launch_pack(const float* src, int nvar, int with_grad, const DevParams& prm, int layout,
                  float* dst, int half, int sm_count, cudaStream_t st)
 {
-    GridDims g{prm.nxg, prm.nyg, prm.nzg, 0.5 / prm.dx, 0.5 / prm.dy, 0.5 / prm.dz};
+    // source and destination share the cell index: a 1-D frame fills row 0 of the two-row store
+    GridDims g{prm.nxg, prm.nyg_src, prm.nzg, 0.5 / prm.dx, 0.5 / prm.dy, 0.5 / prm.dz};
     SlotMap map;
     map.nrec = nrec_of(layout);
     for (int k = 0; k < 32; ++k) map.slot[k] = (k < map.nrec) ? slot_of(layout, k) : 0;
@@ -110,7 +111,7 @@ void launch_pack(const float* src, int nvar, int with_grad, const DevParams& prm
 void launch_grad32(const float* src8, const DevParams& prm, float* out32, int sm_count,
                    cudaStream_t st)
 {
-    GridDims g{prm.nxg, prm.nyg, prm.nzg, 0.5 / prm.dx, 0.5 / prm.dy, 0.5 / prm.dz};
+    GridDims g{prm.nxg, prm.nyg_src, prm.nzg, 0.5 / prm.dx, 0.5 / prm.dy, 0.5 / prm.dz};
     grad32_kernel<<<sm_count * 8, 256, 0, st>>>(src8, g, out32);
 }
 

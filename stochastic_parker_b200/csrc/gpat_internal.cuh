@@ -86,6 +86,7 @@ struct PtlSoA {
 struct DevParams {
     // grid
     int ndim, nx, ny, nz, nxg, nyg, nzg;
+    int nyg_src;  // rows of a host frame (1 in 1-D, where the device store has a second zero row)
     int time_interp;
     int pbc[3];
     double dx, dy, dz, xmin, ymin, zmin, xmax, ymax, zmax, lx, ly, lz;

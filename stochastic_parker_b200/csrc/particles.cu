@@ -323,7 +323,9 @@ __global__ void final_bc_kernel(const __grid_constant__ DevParams prm, PtlSoA P,
             if (prm.pbc[0]) { atomicAdd(leak, w); flag = GPAT_COUNT_FLAG_ESCAPE_HX; }
             else x = x - prm.xmax + prm.xmin;
         }
-        if (y < prm.ymin && flag == GPAT_COUNT_FLAG_INBOX) {
+        if (prm.ndim == 1) {
+            // particle_module.f90:2036: y is not tested in 1-D
+        } else if (y < prm.ymin && flag == GPAT_COUNT_FLAG_INBOX) {
             if (prm.pbc[1]) { atomicAdd(leak, w); flag = GPAT_COUNT_FLAG_ESCAPE_LY; }
             else y = y - prm.ymin + prm.ymax;
         } else if (y > prm.ymax && flag == GPAT_COUNT_FLAG_INBOX) {

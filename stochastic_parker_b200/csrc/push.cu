@@ -80,6 +80,9 @@ __device__ __forceinline__ void boundary(const DevParams& prm, Lane& q, const do
         if (prm.pbc[0]) { atomicAdd(leak, q.weight); q.count_flag = GPAT_COUNT_FLAG_ESCAPE_HX; }
         else q.x = q.x - e[1] + e[0];
     }
+#if GPAT_STRICT
+    if (prm.ndim > 1)  // particle_module.f90:2036 (1-D runs use the reference-order build only)
+#endif
     if (q.y < e[2] && q.count_flag == GPAT_COUNT_FLAG_INBOX) {
         if (prm.pbc[1]) { atomicAdd(leak, q.weight); q.count_flag = GPAT_COUNT_FLAG_ESCAPE_LY; }
         else q.y = q.y - e[2] + e[3];
@@ -102,6 +105,9 @@ __device__ __forceinline__ void boundary(const DevParams& prm, Lane& q, const do
 __device__ __forceinline__ bool outside_or_negp(const DevParams& prm, const Lane& q)
 {
     bool o = (q.p < 0.0) | (q.x < prm.ext[0]) | (q.x > prm.ext[1]) | (q.y < prm.ext[2]) | (q.y > prm.ext[3]);
+#if GPAT_STRICT
+    if (prm.ndim == 1) o = (q.p < 0.0) | (q.x < prm.ext[0]) | (q.x > prm.ext[1]);
+#endif
     if (prm.ndim == 3 || prm.include_3rd_dim) o = o | (q.z < prm.ext[4]) | (q.z > prm.ext[5]);
     return o;
 }
@@ -147,6 +153,9 @@ __device__ __forceinline__ long long locate(const DevParams& prm, double x, doub
     // Fortran index -> storage index is +1 (lower bound -1, mhd_data_parallel.f90:82)
     int cx = min(max(ix + 1, 0), prm.nxg - 2);
     int cy = min(max(iy + 1, 0), prm.nyg - 2);
+#if GPAT_STRICT
+    if (prm.ndim == 1) { cy = 0; ry = 0.0; }  // pos(2) = 1, ry = 0 (particle_module.f90:649-652)
+#endif
     long long cell = (long long)cy * prm.nxg + cx;
     rz = 0.0;
     if (NDIM == 3) {
@@ -220,9 +229,9 @@ __device__ __forceinline__ void gather(const DevParams& prm, const float* __rest
     {
         const double rt1 = 1.0 - rt;
         const double tA = prm.time_interp ? rt1 : 1.0, tB = prm.time_interp ? rt : 0.0;
-        const double t0 = (sel == 0) ? tA : tB, t1 = (sel == 0) ? tB : tA;
+        // w0 / w1: weights of farray1 / farray2 (the loads below put them in f0 / f1)
 #pragma unroll
-        for (int c = 0; c < NC; ++c) { w0[c] = w[c] * t0; w1[c] = w[c] * t1; }
+        for (int c = 0; c < NC; ++c) { w0[c] = w[c] * tA; w1[c] = w[c] * tB; }
     }
 #pragma unroll
     for (int qd = 0; qd < NQ; ++qd) {
@@ -230,7 +239,8 @@ __device__ __forceinline__ void gather(const DevParams& prm, const float* __rest
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             float4 f0, f1;
-            ldg256(fld + off[c] + 8 * qd, f0, f1);
+            if (sel == 0) ldg256(fld + off[c] + 8 * qd, f0, f1);  // f0 = farray1, f1 = farray2:
+            else ldg256(fld + off[c] + 8 * qd, f1, f0);           // same summation order for both sel
             a[0] = fma((double)f0.x, w0[c], a[0]); a[1] = fma((double)f0.y, w0[c], a[1]);
             a[2] = fma((double)f0.z, w0[c], a[2]); a[3] = fma((double)f0.w, w0[c], a[3]);
             a[0] = fma((double)f1.x, w1[c], a[0]); a[1] = fma((double)f1.y, w1[c], a[1]);
@@ -374,14 +384,85 @@ __device__ __forceinline__ bool in_acc_region(const DevParams& prm, const Lane& 
 {
     double xn = (q.x - prm.xmin) / prm.lx;
     bool in = (xn >= prm.acc_region[0]) && (xn <= prm.acc_region[1]);
-    double yn = (q.y - prm.ymin) / prm.ly;
-    in = in && (yn >= prm.acc_region[2]) && (yn <= prm.acc_region[3]);
+    if (prm.ndim > 1) {  // particle_module.f90:2897
+        double yn = (q.y - prm.ymin) / prm.ly;
+        in = in && (yn >= prm.acc_region[2]) && (yn <= prm.acc_region[3]);
+    }
     if (prm.ndim == 3) {
         double zn = (q.z - prm.zmin) / prm.lz;
         in = in && (zn >= prm.acc_region[4]) && (zn <= prm.acc_region[5]);
     }
     return in;
 }
+
+#if GPAT_STRICT
+// push_particle_1d (particle_module.f90:2993-3111) on a 2-D record whose second row is zero.
+// Two uniforms per step: ran1 for x, then one for p (particle_module.f90:3085-3088).
+template <int L>
+__device__ __forceinline__ void push_1d(const DevParams& prm, const PushArgs& a,
+                                        const double (&F)[Rec<L>::NREC], double u0, double u1,
+                                        Lane& q, bool fixed_dt)
+{
+    BField B;
+    VGrad V;
+    B.bx = F[s2::bx]; B.by = F[s2::by]; B.bz = F[s2::bz];
+    B.b = sqrt(sq(B.bx) + sq(B.by) + sq(B.bz));
+    B.dbx_dx = B.dbx_dy = B.dbx_dz = B.dby_dx = B.dby_dy = B.dby_dz = 0.0;
+    B.dbz_dx = B.dbz_dy = B.dbz_dz = B.db_dx = B.db_dy = B.db_dz = 0.0;
+    V.dvx_dx = F[s2::dvx_dx];
+    V.dvy_dy = V.dvz_dz = V.dvx_dy = V.dvx_dz = V.dvy_dx = V.dvy_dz = V.dvz_dx = V.dvz_dy = 0.0;
+    double rho = 1.0;
+    if constexpr (Rec<L>::EXT) rho = F[s2::rho];
+    Kappa k;
+    calc_kappa<false, false>(prm, B, q.p, q.mu, k);
+    // particle_module.f90:2271-2292: dkdx = 0 (mag_dependency = 1 is rejected by gpat_init because
+    // the reference would multiply by an unassigned db_dx there)
+    k.dkxx_dx = k.kpara * 0.0;
+    const double dx_dt = F[s2::vx] + k.dkxx_dx;
+    const double divv = V.dvx_dx;
+    double dp_dt = -q.p * divv / 3.0;
+    double dpp = 0.0;
+    if (Rec<L>::EXT) momentum_diffusion(prm, B, V, rho, divv, k, q.p, dp_dt, dpp);
+    if (!fixed_dt) {
+        double d;
+        if (dx_dt != 0.0 && dp_dt != 0.0) {  // particle_module.f90:3060-3072
+            const double s = (k.skperp > 0.0) ? k.skperp : k.skpara;
+            d = sq(0.5 * prm.dx / k.skpara);
+            d = min2(d, sq(s / dx_dt));
+            d = min2(d, (double)0.1f * q.p / fabs(dp_dt));
+        } else {
+            d = a.dt_min;
+        }
+        if (d < a.dt_min) d = a.dt_min;
+        if (d > a.dt_max) d = a.dt_max;
+        q.dt = d;
+    }
+    const double sdt = sqrt(q.dt);
+    const double sqrt3 = 1.7320508075688772;
+    const double ran1 = (2.0 * u0 - 1.0) * sqrt3;
+    const double ddx = dx_dt * q.dt + ran1 * k.skpara * sdt;
+    q.x = q.x + ddx;
+    q.t = q.t + q.dt;
+    q.dxl = ddx;
+    q.dyl = 0.0;
+    q.dzl = 0.0;
+    const double ranp = (2.0 * u1 - 1.0) * sqrt3;
+    double ddp = dp_dt * q.dt + ranp * sqrt(2.0 * dpp) * sdt;
+    if (prm.acc_region_flag == 1) {
+        if (in_acc_region(prm, q)) q.p = q.p + ddp;
+        else ddp = 0.0;
+    } else {
+        q.p = q.p + ddp;
+    }
+    const double pfloor = 0.25 * prm.p0;
+    if (q.p < pfloor) {
+        q.p = q.p - ddp;
+        ddp = pfloor - q.p;
+        q.p = pfloor;
+    }
+    q.dpl = ddp;
+}
+#endif
 
 // One call of push_particle_*: everything between the BC test and the step counter.
 template <int L>
@@ -411,6 +492,15 @@ __device__ __forceinline__ void push_once(const DevParams& prm, const PushArgs& 
         u0 = u01(r.x); u1 = u01(r.y); u2 = u01(r.z); u3 = u01(r.w);
     }
     q.rng += 1;
+
+#if GPAT_STRICT
+    if constexpr (!D3) {
+        if (prm.ndim == 1) {
+            push_1d<L>(prm, a, F, u0, u1, q, fixed_dt);
+            return;
+        }
+    }
+#endif
 
     BField B;
     VGrad V;
@@ -800,7 +890,11 @@ template <int L> struct MinBlocks { static constexpr int V = GPAT_MINBLOCKS; };
 #else
 template <int L> struct MinBlocks { static constexpr int V = (L == L2B) ? 4 : 3; };
 #endif
-template <int L>
+// SEL = which half of the store is farray1 (PushArgs::sel).  It is a template parameter because
+// the two frames must enter every sum in the order (farray1, farray2) whatever half they live in:
+// a run restarted from a dump starts with sel = 0 again and has to continue bit-identically
+// (tests/test_gpu_parity.py::test_restart_round_trip_is_bit_exact).
+template <int L, int SEL>
 __global__ void __launch_bounds__(kBlock, MinBlocks<L>::V)
 push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                  const float* __restrict__ fld, const __grid_constant__ PushArgs a)
@@ -849,8 +943,8 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                 cell = locate<Rec<L>::NDIM>(prm, q.x, q.y, q.z, rx, ry, rz);
                 const double rt = (q.t - a.t0) * a.idtf;
                 const double tA = prm.time_interp ? 1.0 - rt : 1.0, tB = prm.time_interp ? rt : 0.0;
-                t0 = (a.sel == 0) ? tA : tB;
-                t1 = (a.sel == 0) ? tB : tA;
+                t0 = (SEL == 0) ? tA : tB;
+                t1 = (SEL == 0) ? tB : tA;
             }
             double2* row = reinterpret_cast<double2*>(par + lane * C::PAR);
             row[0] = make_double2(rx, ry);
@@ -916,8 +1010,13 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
 #pragma unroll
                     for (int j = 0; j < C::CPL; ++j) {
                         const float4 f0 = lo[slot][c * C::CPL + j], f1 = hi[slot][c * C::CPL + j];
-                        fma_chunk<0, 0>(c, f0, w0[c], acc[j]);
-                        fma_chunk<0, 1>(c, f1, w1[c], acc[j]);
+                        if constexpr (SEL == 0) {
+                            fma_chunk<0, 0>(c, f0, w0[c], acc[j]);
+                            fma_chunk<0, 1>(c, f1, w1[c], acc[j]);
+                        } else {
+                            fma_chunk<0, 1>(c, f1, w1[c], acc[j]);
+                            fma_chunk<0, 0>(c, f0, w0[c], acc[j]);
+                        }
                     }
                 }
                 if (r + DEPTH < C::G) issue(r + DEPTH, slot);
@@ -984,13 +1083,15 @@ void launch_one(const DevParams& prm, const PtlSoA& P, const float* fld, const P
         size_t pad = 0;
         if (const char* e = getenv("GPAT_PUSH_SMEM_PAD")) {
             pad = (size_t)atol(e);
-            cudaFuncSetAttribute(push_kernel_coop<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+            cudaFuncSetAttribute(push_kernel_coop<L, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
+            cudaFuncSetAttribute(push_kernel_coop<L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
         }
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel_coop<L>, kBlock, pad);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel_coop<L, 0>, kBlock, pad);
         if (per_sm < 1) per_sm = 1;
         grid = (long long)sm_count * per_sm;
         if (want < grid) grid = want > 0 ? want : 1;
-        push_kernel_coop<L><<<(unsigned)grid, kBlock, pad, st>>>(prm, P, fld, a);
+        if (a.sel == 0) push_kernel_coop<L, 0><<<(unsigned)grid, kBlock, pad, st>>>(prm, P, fld, a);
+        else push_kernel_coop<L, 1><<<(unsigned)grid, kBlock, pad, st>>>(prm, P, fld, a);
         return;
     }
 #endif

@@ -61,7 +61,8 @@ class GpatSim:
     def grid_shape(self):
         P = self.P
         nzg = P.nz + 4 if P.ndim > 2 else 1
-        return nzg, P.ny + 4, P.nx + 4
+        nyg = P.ny + 4 if P.ndim > 1 else 1
+        return nzg, nyg, P.nx + 4
 
     def set_params(self, params: Params):
         self._ck(self.lib.gpat_set_params(self.h, C.byref(params)), "gpat_set_params")

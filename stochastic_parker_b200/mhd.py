@@ -21,6 +21,7 @@ x = xmin to Fortran index 1, particle_module.f90:1616 + 654).
 from __future__ import annotations
 
 import os
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -105,6 +106,21 @@ def _fields_shock_2d(X, Y, t):
     return vx, vy, vz, rho, bx, by, bz
 
 
+def _fields_shock_1d(X, t):
+    """1-D planar shock along x (the 1-D runs of push_particle_1d, particle_module.f90:2993):
+    compression ratio 4, smooth ripple so that dx/dt and dp/dt are never exactly zero."""
+    w = 2.0 / X.shape[-1]
+    xs = 0.45 + 0.05 * t
+    prof = 0.5 * (1.0 - np.tanh((X - xs) / w))
+    thx = 2 * np.pi * X
+    vx = 0.25 + 0.75 * prof + 0.004 * np.sin(thx + 0.3)
+    rho = 4.0 - 3.0 * prof
+    bx = 0.5 + 0.0 * X
+    by = 0.3 * rho + 0.01 * np.sin(thx + 0.7)
+    bz = 0.05 * rho + 0.005 * np.cos(thx)
+    return vx, 0.0 * X, 0.0 * X, rho, bx, by, bz
+
+
 def _fields_turbulence_2d(X, Y, t, nmodes=6, seed=7):
     """Multi-mode 'PIC-like' fluctuating field on a mean field."""
     rng = np.random.default_rng(seed)
@@ -149,6 +165,7 @@ def _fields_fluxrope_3d(X, Y, Z, t):
 
 
 KINDS = {
+    "shock_1d": (_fields_shock_1d, 1, "reflect"),
     "reconnection_2d": (_fields_reconnection_2d, 2, "periodic"),
     "flare_2d": (_fields_flare_2d, 2, "reflect"),
     "shock_2d": (_fields_shock_2d, 2, "reflect"),
@@ -171,24 +188,44 @@ def _pack(out, comps):
 
 def make_frame(kind: str, nx: int, ny: int, nz: int, frame: int, dt_out: float = 0.1,
                boundary: str | None = None) -> np.ndarray:
-    """One frame with ghost cells, float32, shape (ny+4, nx+4, 8) or (nz+4, ny+4, nx+4, 8)."""
+    """One frame with ghost cells, float32, shape (nx+4, 8), (ny+4, nx+4, 8) or
+    (nz+4, ny+4, nx+4, 8)."""
     fn, ndim, default_bc = KINDS[kind]
     mode = boundary or default_bc
     t = frame * dt_out
     xs = np.arange(nx, dtype=np.float64) / max(nx - 1, 1)
     ys = np.arange(ny, dtype=np.float64) / max(ny - 1, 1)
+    if ndim == 1:  # farray(:, -1:nx+2, 1, 1), mhd_data_parallel.f90:78
+        out = np.zeros((nx + 4, NVAR), dtype=np.float32)
+        _pack(out[2:nx + 2], fn(xs, t))
+        _ghost_fill(out, 0, mode)
+        return out
+    # elementwise closed forms: row blocks (2-D) / planes (3-D) are evaluated by a thread pool
+    # (numpy ufuncs release the GIL); the values do not depend on the blocking
+    nthr = max(1, min(32, os.cpu_count() or 1))
     if ndim == 2:
         out = np.zeros((ny + 4, nx + 4, NVAR), dtype=np.float32)
-        X, Y = np.meshgrid(xs, ys)  # (ny, nx)
-        _pack(out[2:ny + 2, 2:nx + 2], fn(X, Y, t))
+        rows = max(16, -(-ny // (4 * nthr)))
+
+        def block(j0):
+            j1 = min(ny, j0 + rows)
+            X, Y = np.meshgrid(xs, ys[j0:j1])  # (rows, nx)
+            _pack(out[2 + j0:2 + j1, 2:nx + 2], fn(X, Y, t))
+
+        with ThreadPoolExecutor(nthr) as ex:
+            list(ex.map(block, range(0, ny, rows)))
         _ghost_fill(out, 0, mode)
         _ghost_fill(out, 1, mode)
         return out
     zs = np.arange(nz, dtype=np.float64) / max(nz - 1, 1)
     out = np.zeros((nz + 4, ny + 4, nx + 4, NVAR), dtype=np.float32)
     X, Y = np.meshgrid(xs, ys)
-    for k in range(nz):  # plane by plane to bound memory at 512^3
+
+    def plane(k):  # plane by plane to bound memory at 512^3
         _pack(out[k + 2, 2:ny + 2, 2:nx + 2], fn(X, Y, zs[k] + 0.0 * X, t))
+
+    with ThreadPoolExecutor(nthr) as ex:
+        list(ex.map(plane, range(nz)))
     _ghost_fill(out, 0, mode)
     _ghost_fill(out, 1, mode)
     _ghost_fill(out, 2, mode)
@@ -244,6 +281,9 @@ def write_run(directory: str, kind: str, nx: int, ny: int, nz: int, nframes: int
 def read_frame(directory: str, frame: int, cfg: dict) -> np.ndarray:
     nx, ny, nz = cfg["nx"], cfg["ny"], cfg["nz"]
     a = np.fromfile(os.path.join(directory, f"mhd_data_{frame:04d}"), dtype=np.float32)
-    if cfg.get("ndim", 3 if nz > 1 else 2) == 2:
+    ndim = cfg.get("ndim", 3 if nz > 1 else (2 if ny > 1 else 1))
+    if ndim == 1:
+        return a.reshape(nx + 4, NVAR)
+    if ndim == 2:
         return a.reshape(ny + 4, nx + 4, NVAR)
     return a.reshape(nz + 4, ny + 4, nx + 4, NVAR)

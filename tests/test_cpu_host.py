@@ -158,7 +158,8 @@ def test_build_params_follows_the_reference_read_order():
 
 def test_named_workloads_cover_baseline_configs():
     from stochastic_parker_b200 import WORKLOADS
-    assert sorted(WORKLOADS) == ["c1", "c2", "c3", "c4", "c5"]
+    assert sorted(WORKLOADS) == ["c1", "c2", "c3", "c4", "c5", "s1"]  # s1: the 1-D pusher
+    assert WORKLOADS["s1"].ndim == 1
     assert (WORKLOADS["c1"].nx, WORKLOADS["c1"].ny, WORKLOADS["c1"].nptl) == (1024, 1024, 1_000_000)
     assert WORKLOADS["c2"].nptl == 100_000_000 and WORKLOADS["c4"].nx == 4096
     assert (WORKLOADS["c5"].nx, WORKLOADS["c5"].ndim) == (512, 3)

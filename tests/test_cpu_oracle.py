@@ -316,3 +316,78 @@ def test_empty_and_capacity_edges():
     c = o.counters()
     assert c.nptl_current == 12 and c.tag_max == 20
     assert o.download_particles()["tag_injected"][-1] == 19
+
+
+# ---- 1-D (push_particle_1d, particle_module.f90:2993-3111) ---------------------------------------
+def _np_step_1d(P, frames, before, u, t0, dtf):
+    """Independent numpy restatement of one 1-D step written from the Fortran: 2-corner
+    interpolation (particle_module.f90:649-652, mhd_data_parallel.f90:1776-1792), the 1-D kappa
+    branch with mag_dependency = 0 (:2255-2292) and push_particle_1d."""
+    def grads(f):  # d/dx of the 8 primaries, FP32 difference x FP64 0.5/dx -> FP32
+        g = np.zeros_like(f)
+        g[1:-1] = f[2:] - f[:-2]
+        g[0] = (np.float32(-3) * f[0] + np.float32(4) * f[1]) - f[2]
+        g[-1] = (np.float32(3) * f[-1] - np.float32(4) * f[-2]) + f[-3]
+        return (g.astype(np.float64) * (0.5 / P.dx)).astype(np.float32)
+    x, p, t = before["x"], before["p"], before["t"]
+    px = (x - P.xmin) / P.dx
+    ix = np.floor(px).astype(np.int64) + 1
+    rx = px - ix + 1
+    rt = (t - t0) / dtf
+    F = []
+    for f in frames:
+        g = grads(f)
+        c = ix + 1  # Fortran index -> storage index
+        val = lambda a, v: a[c, v].astype(np.float64) * (1.0 - rx) + a[c + 1, v].astype(np.float64) * rx
+        F.append(dict(vx=val(f, 0), rho=val(f, 3), bx=val(f, 4), by=val(f, 5), bz=val(f, 6), dvx=val(g, 0)))
+    Fi = {k: F[0][k] * (1.0 - rt) + F[1][k] * rt for k in F[0]}
+    knorm = (p / P.p0) ** P.pindex if P.momentum_dependency == 1 else np.ones_like(p)
+    kpara = P.kpara0 * knorm
+    kperp = kpara * P.kret
+    skpara, skperp = np.sqrt(2.0 * kpara), np.sqrt(2.0 * kperp)
+    dx_dt = Fi["vx"] + kpara * 0.0
+    dp_dt = -p * Fi["dvx"] / 3.0
+    s = np.where(skperp > 0, skperp, skpara)
+    dt = np.minimum(np.minimum((0.5 * P.dx / skpara) ** 2, (s / dx_dt) ** 2),
+                    float(np.float32(0.1)) * p / np.abs(dp_dt))
+    dt = np.where((dx_dt != 0) & (dp_dt != 0), dt, P.dt_min_rel * dtf)
+    dt = np.clip(dt, P.dt_min_rel * dtf, P.dt_max_rel * dtf)
+    sdt = np.sqrt(dt)
+    ran1 = (2.0 * u[:, 0] - 1.0) * np.sqrt(3.0)
+    xn = x + (dx_dt * dt + ran1 * skpara * sdt)
+    pn = p + dp_dt * dt  # dpp = 0: the momentum noise term is exactly zero
+    pn = np.maximum(pn, 0.25 * P.p0)  # particle_module.f90:3105-3109
+    return xn, pn, t + dt, dt
+
+
+def test_1d_step_matches_numpy_restatement():
+    w, P, frames, _ = make_case("s1", grid=256, nptl=300)
+    assert P.ndim == 1 and frames[0].shape == (260, 8)
+    P.rng_mode = RNG_TABLE
+    o = Oracle(P, w.nptl_max)
+    u = np.random.default_rng(11).uniform(0, 1, (300, 2, 4))
+    o.set_rng_table(u)
+    o.upload_fields(0, frames[0])
+    o.upload_fields(1, frames[1])
+    o.inject_uniform(300, 0.0, 0, w.particle_v0, 0.0, w.dt_out, box_of(P), w.power_index)
+    before = o.download_particles()
+    assert o.debug_push_n(0.0, w.dt_out, 1) == 300
+    after = o.download_particles()
+    x, p, t, dt = _np_step_1d(P, frames[:2], before, u[before["tag_injected"], 0], 0.0, w.dt_out)
+    for name, ref in (("x", x), ("p", p), ("t", t), ("dt", dt)):
+        err = np.abs(after[name] - ref) / np.maximum(np.abs(ref), 1.0 if name == "x" else 1e-300)
+        assert err.max() < 2e-15, (name, err.max())
+    assert np.array_equal(after["y"], before["y"]) and np.array_equal(after["z"], before["z"])
+
+
+def test_1d_intervals_end_on_frame_time_and_leak_through_open_x():
+    w, P, frames, ts = make_case("s1", grid=128, nptl=400, nframes=3)
+    o = Oracle(P, w.nptl_max)
+    res, steps = run_intervals(o, frames, ts, nptl=400, dist_flag=1, particle_v0=w.particle_v0)
+    ptl = o.download_particles()
+    c = o.counters()
+    assert steps > 400 and len(ptl) == c.nptl_current
+    assert np.all(ptl["t"] == ts[-1])
+    # weight is conserved between the box and the open-x leak; y never moves in 1-D so no y escapes
+    assert abs(ptl["weight"].sum() + c.leak + c.leak_negp - 800.0) < 1e-9  # 400 injected per interval
+    assert res[-1]["quick"][0] == c.nptl_current

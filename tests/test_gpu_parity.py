@@ -94,6 +94,29 @@ def test_inject_parity(dist_flag):
     g.close()
 
 
+def test_1d_gradients_and_interp_bit_exact():
+    """1-D fields (farray(:, -1:nx+2, 1, 1), mhd_data_parallel.f90:78): d/dx gradients incl. the
+    one-sided ends, y/z gradients left at the zero fill, and the 2-corner interpolation of
+    get_interp_paramters' 1-D branch (particle_module.f90:649-652), bit for bit."""
+    w, P, frames, _ = make_case("s1", grid=192, nptl=8, cli=dict(dpp_wave=1))
+    g, o = pair(P, w.nptl_max)
+    o.upload_fields(0, frames[0])
+    ref = o.get_fields(0).reshape(-1, 32)
+    got = g.debug_gradients(frames[0]).reshape(-1, 32)
+    assert got.shape == (196, 32)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    load_fields((g, o), frames)
+    rng = np.random.default_rng(2)
+    n = 3000
+    x = rng.uniform(P.xmin - 0.5 * P.dx, P.xmax + 0.5 * P.dx, n)
+    y, z, rt = rng.uniform(0, 1, n), rng.uniform(0, 1, n), rng.uniform(0, 1, n)
+    refi, goti = o.interp(x, y, z, rt), g.interp(x, y, z, rt)
+    used = np.any(goti != 0.0, axis=0)
+    assert used[[0, 3, 4, 5, 6, 8]].all()  # vx rho bx by bz dvx_dx
+    assert np.array_equal(goti[:, used], refi[:, used])
+    g.close()
+
+
 CASES = {
     "c1_2d": dict(key="c1", grid=64),
     "c1_2d_no_time_interp": dict(key="c1", grid=64, cli=dict(time_interp=0)),
@@ -105,6 +128,9 @@ CASES = {
     "c3_shock_open": dict(key="c3", grid=64),
     "c4_dpp_wave_shear": dict(key="c4", grid=64),
     "c4_dpp_strong_kret0": dict(key="c4", grid=64, conf=dict(kret=0.0), cli=dict(weak_scattering=0)),
+    "s1_shock_1d": dict(key="s1", grid=256),
+    "s1_shock_1d_dpp_nlgc": dict(key="s1", grid=256, conf=dict(dt_min_rel=1e-3),
+                                 cli=dict(dpp_wave=1, dpp_shear=1, nlgc=1, kperp_kpara=0.05)),
     "c5_3d": dict(key="c5", grid=32),
     "c5_3d_dpp_nlgc": dict(key="c5", grid=32, conf=dict(kpara0=0.02, dt_min_rel=1e-3),
                            cli=dict(dpp_wave=1, dpp_shear=1, nlgc=1, kperp_kpara=0.05)),
@@ -195,7 +221,7 @@ def test_interval_parity_fast():
     g.close()
 
 
-@pytest.mark.parametrize("name", ["c1_2d", "c3_shock_open", "c5_3d"])
+@pytest.mark.parametrize("name", ["c1_2d", "c3_shock_open", "c5_3d", "s1_shock_1d"])
 def test_histograms_bit_exact(name):
     """calc_particle_distributions + quick_check + get_pmax_global on the SAME particle set:
     every histogram count bit-exact (dyadic weights -> order-independent FP64 sums)."""
