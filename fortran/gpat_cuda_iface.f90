@@ -13,7 +13,7 @@ module gpat_cuda
     public :: gpat_params, gpat_hist_spec, gpat_particle, gpat_counters, gpat_timings
     public :: gpat_init, gpat_set_params, gpat_finalize, gpat_last_error
     public :: gpat_upload_fields, gpat_swap_fields
-    public :: gpat_inject_uniform, gpat_particle_mover, gpat_split
+    public :: gpat_inject_uniform, gpat_inject_targeted, gpat_particle_mover, gpat_split
     public :: gpat_download_particles, gpat_upload_particles
     public :: gpat_download_escaped, gpat_reset_escaped
     public :: gpat_get_counters, gpat_set_counters
@@ -38,7 +38,7 @@ module gpat_cuda
         real(c_double) :: dt_min_rel, dt_max_rel
         integer(c_int32_t) :: momentum_dependency, mag_dependency, acc_region_flag, pad0
         real(c_double) :: acc_region(6)
-        integer(c_int32_t) :: dpp_wave, dpp_shear, weak_scattering, pad1
+        integer(c_int32_t) :: dpp_wave, dpp_shear, weak_scattering, keep_rho
         real(c_double) :: tau0, drift1, drift2
         integer(c_int32_t) :: pcharge, check_drift_2d, include_3rd_dim, nlgc
         real(c_double) :: kperp_kpara
@@ -121,6 +121,20 @@ module gpat_cuda
             integer(c_int), value :: dist_flag
             real(c_double), intent(in) :: part_box(6)
         end function gpat_inject_uniform
+
+        !< inject_particles_at_large_jz / _absj / _divv / _rho (particle_module.f90:785-1468) with
+        !< get_ncells_large_* (mhd_data_parallel.f90:2211-2498); mode = 1 jz, 2 absj, 4 divv, 5 rho
+        integer(c_int) function gpat_inject_targeted(h, mode, nptl, dt, dist_flag, particle_v0, &
+                t_frame, dt_mhd, part_box, power_index, inject_same_nptl, vmin, ncells_norm, &
+                nptl_injected, ncells) bind(C, name="gpat_inject_targeted")
+            import :: c_ptr, c_int, c_int64_t, c_double
+            type(c_ptr), value :: h
+            integer(c_int), value :: mode, dist_flag, inject_same_nptl
+            integer(c_int64_t), value :: nptl, ncells_norm
+            real(c_double), value :: dt, particle_v0, t_frame, dt_mhd, power_index, vmin
+            real(c_double), intent(in) :: part_box(6)
+            integer(c_int64_t), intent(out) :: nptl_injected, ncells
+        end function gpat_inject_targeted
 
         !< particle_mover (particle_module.f90:1846), both remove_particles passes included
         integer(c_int) function gpat_particle_mover(h, t0, dtf, nsteps_interval, num_fine_steps, &

@@ -89,7 +89,7 @@ typedef struct gpat_hist_spec {
  * (simulation_setup.f90:171-253), particle BCs (simulation_setup.f90:107-123). */
 typedef struct gpat_params {
     /* grid */
-    int32_t ndim;        /* ndim_field: 2 or 3 (1-D is not on the GPU path) */
+    int32_t ndim;        /* ndim_field: 1, 2 or 3 (1-D: ny = nz = 1, reference-order build only) */
     int32_t nx, ny, nz;  /* mhd_config%nx.. without ghost cells (nz=1 in 2-D) */
     int32_t time_interp; /* time_interp_flag */
     int32_t pbc[3];      /* pbcx,pbcy,pbcz: 0 periodic, 1 open */
@@ -108,7 +108,7 @@ typedef struct gpat_params {
     double acc_region[6]; /* xmin,xmax,ymin,ymax,zmin,zmax in [0,1] */
     /* momentum diffusion */
     int32_t dpp_wave, dpp_shear, weak_scattering;
-    int32_t pad1_;
+    int32_t keep_rho; /* keep the density slot in the device record (inject_large_rho) */
     double tau0;
     /* drift */
     double drift1, drift2;
@@ -178,6 +178,32 @@ int gpat_swap_fields(gpat_handle h);
 int gpat_inject_uniform(gpat_handle h, int64_t nptl, double dt, int dist_flag,
                         double particle_v0, double t_frame, double dt_mhd,
                         const double part_box[6], double power_index);
+
+/* Targeted injection on the device.  Replaces inject_particles_at_large_jz
+ * (particle_module.f90:785-905), _at_large_absj (:919-1061), _at_large_divv (:1250-1341) and
+ * _at_large_rho (:1356-1468) together with the cell counters get_ncells_large_jz / _absj /
+ * _divv / _rho (mhd_data_parallel.f90:2211-2261, 2269-2335, 2385-2455, 2463-2498), for the
+ * whole-field-per-rank decomposition (mpi_sub_size = 1):
+ *   ncells      = cells of part_box whose farray1 value exceeds vmin (jz_min / absj_min /
+ *                 divv_min / rho_min);
+ *   nptl_inject = int(nptl * ncells / (inject_same_nptl ? ncells : ncells_norm));
+ *   every new particle draws positions uniformly in the WHOLE domain from its own Philox
+ *   injection stream until the field interpolated at rt = 0 passes the threshold inside
+ *   part_box, then continues like gpat_inject_uniform (mu, momentum, time).
+ * nptl_injected / ncells (may be NULL) receive nptl_inject and the cell count.
+ * GPAT_INJECT_LARGE_DB2 (inject_particles_at_large_db2, :1075-1236) needs the deltab maps
+ * and returns GPAT_ERR_INVALID; GPAT_INJECT_LARGE_RHO needs gpat_params.keep_rho = 1 unless
+ * momentum diffusion already keeps the density slot. */
+#define GPAT_INJECT_LARGE_JZ 1
+#define GPAT_INJECT_LARGE_ABSJ 2
+#define GPAT_INJECT_LARGE_DB2 3
+#define GPAT_INJECT_LARGE_DIVV 4
+#define GPAT_INJECT_LARGE_RHO 5
+int gpat_inject_targeted(gpat_handle h, int mode, int64_t nptl, double dt, int dist_flag,
+                         double particle_v0, double t_frame, double dt_mhd,
+                         const double part_box[6], double power_index, int inject_same_nptl,
+                         double vmin, int64_t ncells_norm, int64_t* nptl_injected,
+                         int64_t* ncells);
 
 /* Replaces particle_mover (particle_module.f90:1846-1974) including both
  * remove_particles passes (particle_module.f90:5365-5403).  t0 = tstamps_mhd(frame),

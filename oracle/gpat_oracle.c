@@ -1088,6 +1088,50 @@ void orc_debug_push_n(orc_sim* S, double t0, double dtf, int nsteps, uint64_t* s
 /* ------------------------------------------------------------------------ */
 /* injection: PM:454-530 (whole-field branch) + PM:385-441                     */
 /* ------------------------------------------------------------------------ */
+/* inject_one_particle, PM:385-441; `st` continues the particle's injection stream */
+static void inject_one_particle(orc_sim* S, inj_stream* st, double xpos, double ypos, double zpos,
+                                int dist_flag, double particle_v0, double mu, double t_frame,
+                                double dt_mhd, double dt, double power_index)
+{
+    const gpat_params* P = &S->P;
+    gpat_particle* q = &S->ptls[S->nptl_current - 1];
+    memset(q, 0, sizeof(*q));
+    q->x = xpos; q->y = ypos; q->z = zpos;
+    if (dist_flag == 0) { /* PM:399-407 */
+        double ftest = 1.0, fxp = 0.5, ptmp = 0.0;
+        while (ftest > fxp) {
+            ptmp = (inj_next(st) * (P->pmax - P->pmin) + P->pmin) / P->p0;
+            fxp = sq(ptmp) * exp(-sq(ptmp));
+            ftest = inj_next(st) * (double)0.37f;
+        }
+        q->p = ptmp * P->p0;
+    } else if (dist_flag == 1) {
+        q->p = P->p0;
+    } else if (dist_flag == 2) { /* PM:410-418 */
+        double r01 = inj_next(st);
+        if ((int)power_index == 1) {
+            q->p = pow(P->pmax / P->p0, r01) * P->p0;
+        } else {
+            double norm = pow(P->pmax, -power_index + 1) - pow(P->p0, -power_index + 1);
+            q->p = pow(r01 * norm + pow(P->p0, -power_index + 1), 1.0 / (-power_index + 1));
+        }
+    }
+    q->v = particle_v0 * q->p / P->p0;
+    q->mu = mu;
+    q->weight = 1.0;
+    q->t = t_frame + inj_next(st) * dt_mhd;
+    q->dt = dt;
+    q->split_times = 0;
+    q->count_flag = GPAT_COUNT_FLAG_INBOX;
+    q->origin = P->mpi_rank;
+    q->nsteps_tracked = 0;
+    q->nsteps_pushed = 0;
+    q->tag_injected = (int32_t)S->tag_max;
+    S->tag_max++;
+    q->tag_splitted = 1;
+    set_rng_step(q, 0);
+}
+
 void orc_inject_uniform(orc_sim* S, int64_t nptl, double dt, int dist_flag, double particle_v0,
                         double t_frame, double dt_mhd, const double part_box[6],
                         double power_index)
@@ -1100,48 +1144,138 @@ void orc_inject_uniform(orc_sim* S, int64_t nptl, double dt, int dist_flag, doub
     for (int64_t i = 0; i < nptl; ++i) {
         S->nptl_current++;
         if (S->nptl_current > S->nptl_max) S->nptl_current = S->nptl_max; /* PM:491-492 */
-        gpat_particle* q = &S->ptls[S->nptl_current - 1];
         inj_stream st = {S, (uint32_t)S->tag_max, (uint32_t)P->mpi_rank, 0, {0, 0, 0, 0}};
         double xtmp = inj_next(&st) * (xmax_box - xmin_box) + xmin_box;
         double ytmp = inj_next(&st) * (ymax_box - ymin_box) + ymin_box;
         double ztmp = inj_next(&st) * (zmax_box - zmin_box) + zmin_box;
         double mu_tmp = mu_max * (2.0 * inj_next(&st) - 1.0);
-        memset(q, 0, sizeof(*q));
-        q->x = xtmp; q->y = ytmp; q->z = ztmp;
-        if (dist_flag == 0) { /* PM:399-407 */
-            double ftest = 1.0, fxp = 0.5, ptmp = 0.0;
-            while (ftest > fxp) {
-                ptmp = (inj_next(&st) * (P->pmax - P->pmin) + P->pmin) / P->p0;
-                fxp = sq(ptmp) * exp(-sq(ptmp));
-                ftest = inj_next(&st) * (double)0.37f;
+        inject_one_particle(S, &st, xtmp, ytmp, ztmp, dist_flag, particle_v0, mu_tmp, t_frame,
+                            dt_mhd, dt, power_index);
+    }
+}
+
+/* ------------------------------------------------------------------------ */
+/* targeted injection: inject_particles_at_large_jz / _absj / _divv / _rho    */
+/* (PM:785-905, 919-1061, 1250-1341, 1356-1468) with the cell counters        */
+/* get_ncells_large_* (MD:2211-2261, 2269-2335, 2385-2455, 2463-2498),        */
+/* Cartesian uniform grid, one rank per field copy (mpi_sub_size = 1).        */
+/* mode: 1 jz, 2 absj, 4 divv, 5 rho (3 = db2 needs the deltab maps).         */
+/* ------------------------------------------------------------------------ */
+static int cell_in_box(const orc_sim* S, int ix, int iy, int iz, const double* b)
+{
+    /* xpos_local(ix) = dx*(ix-1) + xmin for the physical cells (MD:2129-2171) */
+    const gpat_params* P = &S->P;
+    int inx = (P->dx * (ix - 1) + P->xmin) > b[0] && (P->dx * (ix - 1) + P->xmin) < b[3];
+    int iny = 1, inz = 1;
+    if (P->ndim > 1) iny = (P->dy * (iy - 1) + P->ymin) > b[1] && (P->dy * (iy - 1) + P->ymin) < b[4];
+    if (P->ndim > 2) inz = (P->dz * (iz - 1) + P->zmin) > b[2] && (P->dz * (iz - 1) + P->zmin) < b[5];
+    return inx && iny && inz;
+}
+
+/* farray1(slot, ix, iy, iz) with Fortran indices (lower bound -1 on resolved axes) */
+static float fa1(const orc_sim* S, int slot, int ix, int iy, int iz)
+{
+    int cj = (S->P.ndim > 1) ? iy + 1 : 0, ck = (S->P.ndim > 2) ? iz + 1 : 0;
+    return S->farray1[FIDX(S, slot - 1, ix + 1, cj, ck)];
+}
+
+int64_t orc_ncells_large(const orc_sim* S, int mode, double vmin, const double part_box[6])
+{
+    const gpat_params* P = &S->P;
+    int64_t n = 0;
+    for (int iz = 1; iz <= P->nz; ++iz)
+        for (int iy = 1; iy <= P->ny; ++iy)
+            for (int ix = 1; ix <= P->nx; ++ix) {
+                if (!cell_in_box(S, ix, iy, iz, part_box)) continue;
+                double v;
+                if (mode == 1) { /* MD:2235-2236: FP32 difference and abs, then promoted */
+                    float d = fa1(S, NFIELDS + 16, ix, iy, iz) - fa1(S, NFIELDS + 14, ix, iy, iz);
+                    v = (double)fabsf(d);
+                } else if (mode == 2) { /* MD:2306-2311: all in FP32 */
+                    float a = fa1(S, NFIELDS + 18, ix, iy, iz) - fa1(S, NFIELDS + 20, ix, iy, iz);
+                    float b = fa1(S, NFIELDS + 19, ix, iy, iz) - fa1(S, NFIELDS + 15, ix, iy, iz);
+                    float c = fa1(S, NFIELDS + 14, ix, iy, iz) - fa1(S, NFIELDS + 16, ix, iy, iz);
+                    float s2 = a * a + b * b;
+                    s2 = s2 + c * c;
+                    v = (double)sqrtf(s2);
+                } else if (mode == 4) {
+                    /* MD:2417-2424: `divv = farray1(nfields+1, :, :, :)` assigns the WHOLE array
+                     * (ghosts included) to an allocatable declared (nx,ny,nz); with Fortran 2003
+                     * reallocation-on-assignment (gfortran's default) divv gets lower bounds 1,
+                     * so divv(ix,iy,iz) is farray1(.., ix-2, iy-2, iz-2): the counter looks two
+                     * cells to the lower-left of the cell whose position it tests.  Kept. */
+                    int sx = ix - 2, sy = (P->ndim > 1) ? iy - 2 : iy, sz = (P->ndim > 2) ? iz - 2 : iz;
+                    v = (double)fa1(S, NFIELDS + 1, sx, sy, sz);
+                    if (P->ndim > 1) {
+                        v = v + (double)fa1(S, NFIELDS + 5, sx, sy, sz);
+                        if (P->ndim > 2) v = v + (double)fa1(S, NFIELDS + 9, sx, sy, sz);
+                    }
+                    v = -v;
+                } else { /* MD:2490 */
+                    v = (double)fa1(S, 4, ix, iy, iz);
+                }
+                if (v > vmin) n++;
             }
-            q->p = ptmp * P->p0;
-        } else if (dist_flag == 1) {
-            q->p = P->p0;
-        } else if (dist_flag == 2) { /* PM:410-418 */
-            double r01 = inj_next(&st);
-            if ((int)power_index == 1) {
-                q->p = pow(P->pmax / P->p0, r01) * P->p0;
+    return n;
+}
+
+int64_t orc_inject_targeted(orc_sim* S, int mode, int64_t nptl, double dt, int dist_flag,
+                            double particle_v0, double t_frame, double dt_mhd,
+                            const double part_box[6], double power_index, int inject_same_nptl,
+                            double vmin, int64_t ncells_norm)
+{
+    const gpat_params* P = &S->P;
+    const double mu_max = (double)0.99f;
+    const double xmin = P->xmin, ymin = P->ymin, zmin = P->zmin;
+    const double xmax = P->xmax, ymax = P->ymax, zmax = P->zmax;
+    int64_t ncells = orc_ncells_large(S, mode, vmin, part_box);
+    /* one rank per field copy: mpi_sub_size = 1 and the "global" count is the local one */
+    int64_t denom = inject_same_nptl ? ncells : ncells_norm;
+    int64_t nptl_inject = (int64_t)((double)(nptl * 1) * ((double)ncells / (double)denom));
+    if (denom == 0) nptl_inject = 0; /* 0/0 -> int(NaN) is undefined in the reference */
+    S->nptl_inject = nptl_inject;
+    for (int64_t i = 0; i < nptl_inject; ++i) {
+        S->nptl_current++;
+        if (S->nptl_current > S->nptl_max) S->nptl_current = S->nptl_max;
+        inj_stream st = {S, (uint32_t)S->tag_max, (uint32_t)P->mpi_rank, 0, {0, 0, 0, 0}};
+        double xtmp = part_box[0], ytmp = part_box[1], ztmp = part_box[2];
+        double crit = (mode == 4) ? 2.0 : (mode == 5 ? 0.0 : -2.0);
+        for (;;) {
+            int again = (mode == 4) ? (-crit < vmin) : (crit < vmin);
+            if (!again) break;
+            xtmp = inj_next(&st) * (xmax - xmin) + xmin;
+            ytmp = inj_next(&st) * (ymax - ymin) + ymin;
+            ztmp = inj_next(&st) * (zmax - zmin) + zmin;
+            if (xtmp >= part_box[0] && xtmp <= part_box[3] && ytmp >= part_box[1] &&
+                ytmp <= part_box[4] && ztmp >= part_box[2] && ztmp <= part_box[5]) {
+                double px = (xtmp - xmin) / P->dx, py = (ytmp - ymin) / P->dy;
+                double pz = (ztmp - zmin) / P->dz;
+                int pos[3];
+                double w[8], fields[NVAR];
+                get_interp_parameters(S, px, py, pz, pos, w);
+                interp_fields(S, pos, w, 0.0, fields);
+                if (mode == 1) {
+                    crit = fabs(FG(16) - FG(14));
+                } else if (mode == 2) {
+                    crit = sqrt(sq(FG(18) - FG(20)) + sq(FG(19) - FG(15)) + sq(FG(14) - FG(16)));
+                } else if (mode == 4) {
+                    crit = FG(1);
+                    if (P->ndim > 1) {
+                        crit = crit + FG(5);
+                        if (P->ndim > 2) crit = crit + FG(9);
+                    }
+                } else {
+                    crit = F(4);
+                }
             } else {
-                double norm = pow(P->pmax, -power_index + 1) - pow(P->p0, -power_index + 1);
-                q->p = pow(r01 * norm + pow(P->p0, -power_index + 1), 1.0 / (-power_index + 1));
+                crit = (mode == 4) ? 3.0 : (mode == 5 ? 0.0 : -3.0);
             }
         }
-        q->v = particle_v0 * q->p / P->p0;
-        q->mu = mu_tmp;
-        q->weight = 1.0;
-        q->t = t_frame + inj_next(&st) * dt_mhd;
-        q->dt = dt;
-        q->split_times = 0;
-        q->count_flag = GPAT_COUNT_FLAG_INBOX;
-        q->origin = P->mpi_rank;
-        q->nsteps_tracked = 0;
-        q->nsteps_pushed = 0;
-        q->tag_injected = (int32_t)S->tag_max;
-        S->tag_max++;
-        q->tag_splitted = 1;
-        set_rng_step(q, 0);
+        double mu_tmp = mu_max * (2.0 * inj_next(&st) - 1.0);
+        inject_one_particle(S, &st, xtmp, ytmp, ztmp, dist_flag, particle_v0, mu_tmp, t_frame,
+                            dt_mhd, dt, power_index);
     }
+    return nptl_inject;
 }
 
 /* ------------------------------------------------------------------------ */

@@ -106,6 +106,19 @@ class Oracle:
                                     C.c_double(particle_v0), C.c_double(t_frame),
                                     C.c_double(dt_mhd), box, C.c_double(power_index))
 
+    def inject_targeted(self, mode, nptl, dt, dist_flag, particle_v0, t_frame, dt_mhd, part_box,
+                        power_index, inject_same_nptl=True, vmin=0.0, ncells_norm=1):
+        box = (C.c_double * 6)(*part_box)
+        self.lib.orc_ncells_large.restype = C.c_int64
+        self.lib.orc_inject_targeted.restype = C.c_int64
+        ncells = self.lib.orc_ncells_large(self.h, C.c_int(mode), C.c_double(vmin), box)
+        ninj = self.lib.orc_inject_targeted(self.h, C.c_int(mode), C.c_int64(nptl), C.c_double(dt),
+                                            C.c_int(dist_flag), C.c_double(particle_v0),
+                                            C.c_double(t_frame), C.c_double(dt_mhd), box,
+                                            C.c_double(power_index), C.c_int(int(bool(inject_same_nptl))),
+                                            C.c_double(vmin), C.c_int64(ncells_norm))
+        return int(ninj), int(ncells)
+
     def particle_mover(self, t0, dtf, nsteps_interval=100, num_fine_steps=1,
                        dump_escaped_dist=0) -> int:
         steps = C.c_uint64(0)

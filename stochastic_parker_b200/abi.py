@@ -31,6 +31,10 @@ class HistSpec(C.Structure):
     ]
 
 
+# gpat_inject_targeted modes (include/gpat_cuda.h)
+INJECT_LARGE_JZ, INJECT_LARGE_ABSJ, INJECT_LARGE_DB2, INJECT_LARGE_DIVV, INJECT_LARGE_RHO = 1, 2, 3, 4, 5
+
+
 class Params(C.Structure):
     """struct gpat_params (include/gpat_cuda.h)."""
     _fields_ = [
@@ -48,7 +52,7 @@ class Params(C.Structure):
         ("acc_region_flag", C.c_int32), ("pad0_", C.c_int32),
         ("acc_region", C.c_double * 6),
         ("dpp_wave", C.c_int32), ("dpp_shear", C.c_int32), ("weak_scattering", C.c_int32),
-        ("pad1_", C.c_int32),
+        ("keep_rho", C.c_int32),
         ("tau0", C.c_double),
         ("drift1", C.c_double), ("drift2", C.c_double),
         ("pcharge", C.c_int32), ("check_drift_2d", C.c_int32),
@@ -121,6 +125,9 @@ SIGNATURES = {
     "gpat_swap_fields": (C.c_int, [C.c_void_p]),
     "gpat_inject_uniform": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_double,
                                       C.c_double, C.c_double, _DP, C.c_double]),
+    "gpat_inject_targeted": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_int, C.c_double,
+                                       C.c_double, C.c_double, _DP, C.c_double, C.c_int, C.c_double,
+                                       C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "gpat_particle_mover": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int,
                                       C.c_int, C.POINTER(C.c_uint64)]),
     "gpat_split": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int]),

@@ -191,9 +191,11 @@ int validate(const gpat_params* p, std::string& why)
     return 0;
 }
 
+bool Rec_has_rho(int layout) { return layout == L2E || layout == L3E; }
+
 int pick_layout(const gpat_params& p)
 {
-    bool ext = p.dpp_wave || p.dpp_shear || (p.ndim == 2 && p.include_3rd_dim);
+    bool ext = p.dpp_wave || p.dpp_shear || (p.ndim == 2 && p.include_3rd_dim) || p.keep_rho;
     // 1-D runs live in the 2-D record layouts (one physical row + one zero row, fill_dev_params)
     if (p.ndim <= 2) return ext ? L2E : L2B;
     return ext ? L3E : L3B;
@@ -634,6 +636,58 @@ int gpat_inject_uniform(gpat_handle h, int64_t nptl, double dt, int dist_flag, d
     h->nptl_current += nptl;
     if (h->nptl_current > h->nptl_max) h->nptl_current = h->nptl_max;  // particle_module.f90:491-492
     h->tag_max += nptl;
+    return GPAT_OK;
+}
+
+int gpat_inject_targeted(gpat_handle h, int mode, int64_t nptl, double dt, int dist_flag, double particle_v0,
+                         double t_frame, double dt_mhd, const double part_box[6], double power_index,
+                         int inject_same_nptl, double vmin, int64_t ncells_norm, int64_t* nptl_injected,
+                         int64_t* ncells_out)
+{
+    if (!h || !part_box || nptl < 0) return fail(h, GPAT_ERR_INVALID, "gpat_inject_targeted: bad arguments");
+    if (dist_flag < 0 || dist_flag > 2) return fail(h, GPAT_ERR_INVALID, "gpat_inject_targeted: dist_flag must be 0, 1 or 2");
+    if (mode == GPAT_INJECT_LARGE_DB2)
+        return fail(h, GPAT_ERR_INVALID, "gpat_inject_targeted: inject_large_db2 needs the deltab maps (outside the GPU path)");
+    if (mode != GPAT_INJECT_LARGE_JZ && mode != GPAT_INJECT_LARGE_ABSJ && mode != GPAT_INJECT_LARGE_DIVV &&
+        mode != GPAT_INJECT_LARGE_RHO)
+        return fail(h, GPAT_ERR_INVALID, "gpat_inject_targeted: unknown mode");
+    if (mode == GPAT_INJECT_LARGE_RHO && !Rec_has_rho(h->layout))
+        return fail(h, GPAT_ERR_INVALID, "gpat_inject_targeted: inject_large_rho needs gpat_params.keep_rho = 1");
+    if (!h->have_field[0]) return fail(h, GPAT_ERR_STATE, "gpat_inject_targeted: farray1 has not been uploaded");
+    if (!inject_same_nptl && ncells_norm <= 0)
+        return fail(h, GPAT_ERR_INVALID, "gpat_inject_targeted: ncells_norm must be positive");
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventRecord(h->ev[2], h->st));
+    // d_queue doubles as the cell counter and the non-convergence flag (it is idle between pushes)
+    launch_ncells(h->dp, h->layout, h->fld, h->sel, mode, vmin, part_box, h->d_queue, h->sm_count, h->st);
+    h->tm.total_launches++;
+    unsigned long long ncells = 0;
+    CU(cudaMemcpyAsync(&ncells, h->d_queue, sizeof(ncells), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    const double denom = inject_same_nptl ? (double)ncells : (double)ncells_norm;
+    // int(nptl * mpi_sub_size * (dble(ncells) / dble(denominator))), particle_module.f90:843-853
+    long long ninj = (denom > 0.0) ? (long long)((double)nptl * ((double)ncells / denom)) : 0;
+    if (ncells_out) *ncells_out = (int64_t)ncells;
+    if (nptl_injected) *nptl_injected = ninj;
+    if (ninj > 0) {
+        int* d_fail = reinterpret_cast<int*>(h->d_queue);
+        CU(cudaMemsetAsync(d_fail, 0, sizeof(int), h->st));
+        launch_inject(h->dp, h->P, ninj, h->nptl_current, h->nptl_max, h->tag_max, dt, dist_flag, particle_v0,
+                      t_frame, dt_mhd, part_box, power_index, h->st, mode, vmin, h->layout, h->fld, h->sel, d_fail);
+        h->tm.total_launches++;
+        int failed = 0;
+        CU(cudaEventRecord(h->ev[3], h->st));
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(&failed, d_fail, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        CU(cudaStreamSynchronize(h->st));
+        h->tm.inject_ms = elapsed(h->ev[2], h->ev[3]);
+        h->nptl_current += ninj;
+        if (h->nptl_current > h->nptl_max) h->nptl_current = h->nptl_max;
+        h->tag_max += ninj;
+        if (failed)
+            return fail(h, GPAT_ERR_STATE, "gpat_inject_targeted: a rejection loop did not find an admissible "
+                                           "position in 2^22 draws (the reference would spin forever)");
+    }
     return GPAT_OK;
 }
 

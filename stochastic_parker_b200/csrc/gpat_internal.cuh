@@ -173,7 +173,10 @@ void launch_grad32(const float* src8, const DevParams& prm, float* out32, int sm
 void launch_inject(const DevParams& prm, const PtlSoA& P, long long n, long long start,
                    long long nptl_max, long long tag0, double dt, int dist_flag, double particle_v0,
                    double t_frame, double dt_mhd, const double box[6], double power_index,
-                   cudaStream_t st);
+                   cudaStream_t st, int mode = 0, double vmin = 0.0, int layout = 0,
+                   const float* fld = nullptr, int sel = 0, int* fail = nullptr);
+void launch_ncells(const DevParams& prm, int layout, const float* fld, int sel, int mode, double vmin,
+                   const double box[6], unsigned long long* d_count, int sm_count, cudaStream_t st);
 void launch_remove(const PtlSoA& P, const PtlSoA& E, long long ecap, long long n, long long* counters,
                    const ScanWork& w, long long* idx_a, long long* idx_b, int dump_escaped,
                    cudaStream_t st);

@@ -49,7 +49,84 @@ struct InjectArgs {
     double dt, particle_v0, t_frame, dt_mhd, power_index;
     double box[6];
     int dist_flag;
+    // targeted injection (inject_particles_at_large_jz/_absj/_divv/_rho, particle_module.f90:785-1468)
+    int mode;            // 0 uniform in part_box; GPAT_INJECT_LARGE_*
+    double vmin;         // jz_min / absj_min / divv_min / rho_min
+    const float* fld;    // packed field store
+    int nrec, half;      // floats per record half-pair / which half is farray1
+    int pos[10];         // packed position of dbx_dy dbx_dz dby_dx dby_dz dbz_dx dbz_dy dvx_dx dvy_dy dvz_dz rho (-1: absent = 0)
+    int* fail;           // set when a rejection loop hits kMaxTrials
 };
+
+constexpr int kMaxTrials = 1 << 22;  // the reference's loop is unbounded; a kernel must end
+
+// one reference slot of farray1 at storage cell `cell` (gpat_internal.cuh record layout)
+__device__ __forceinline__ float rec_get(const float* __restrict__ fld, long long cell, int nrec, int half, int pos)
+{
+    return fld[cell * (2LL * nrec) + (pos >> 2) * 8 + half * 4 + (pos & 3)];
+}
+
+// get_interp_paramters + interp_fields at rt = 0 for ONE slot, reference summation order, no
+// contraction (particle_module.f90:642-674, mhd_data_parallel.f90:1776-1792)
+struct InjInterp {
+    long long cell[8];
+    double w[8];
+    int nc;
+    __device__ void locate(const DevParams& prm, double x, double y, double z)
+    {
+        const double px = __ddiv_rn(__dsub_rn(x, prm.xmin), prm.dx);
+        const double py = __ddiv_rn(__dsub_rn(y, prm.ymin), prm.dy);
+        const double pz = __ddiv_rn(__dsub_rn(z, prm.zmin), prm.dz);
+        const int ix = (int)floor(px) + 1;
+        const int iy = (prm.ndim > 1) ? (int)floor(py) + 1 : 1;
+        const int iz = (prm.ndim > 2) ? (int)floor(pz) + 1 : 1;
+        const double rx = __dadd_rn(__dsub_rn(px, (double)ix), 1.0);
+        const double ry = (prm.ndim > 1) ? __dadd_rn(__dsub_rn(py, (double)iy), 1.0) : 0.0;
+        const double rz = (prm.ndim > 2) ? __dadd_rn(__dsub_rn(pz, (double)iz), 1.0) : 0.0;
+        const double rx1 = __dsub_rn(1.0, rx), ry1 = __dsub_rn(1.0, ry), rz1 = __dsub_rn(1.0, rz);
+        const int cx = min(max(ix + 1, 0), prm.nxg - 2);
+        const int cy = (prm.ndim > 1) ? min(max(iy + 1, 0), prm.nyg - 2) : 0;
+        const int cz = (prm.ndim > 2) ? min(max(iz + 1, 0), prm.nzg - 2) : 0;
+        nc = (prm.ndim > 2) ? 8 : (prm.ndim > 1 ? 4 : 2);
+        for (int c = 0; c < nc; ++c) {
+            const int i = c & 1, j = (c >> 1) & 1, k = c >> 2;
+            cell[c] = ((long long)(cz + k) * prm.nyg + (cy + j)) * prm.nxg + (cx + i);
+            const double wx = i ? rx : rx1, wy = j ? ry : ry1, wz = k ? rz : rz1;
+            w[c] = __dmul_rn(__dmul_rn(wx, wy), wz);
+        }
+    }
+    __device__ double slot(const InjectArgs& a, int pos) const
+    {
+        if (pos < 0) return 0.0;  // a gradient the layout does not store is identically zero (d/dz in 2-D)
+        double f = 0.0;
+        for (int c = 0; c < nc; ++c)
+            f = __dadd_rn(f, __dmul_rn((double)rec_get(a.fld, cell[c], a.nrec, a.half, pos), w[c]));
+        return f;
+    }
+};
+
+__device__ double inject_criterion(const DevParams& prm, const InjectArgs& a, double x, double y, double z)
+{
+    InjInterp I;
+    I.locate(prm, x, y, z);
+    if (a.mode == GPAT_INJECT_LARGE_JZ)
+        return fabs(__dsub_rn(I.slot(a, a.pos[2]), I.slot(a, a.pos[0])));
+    if (a.mode == GPAT_INJECT_LARGE_ABSJ) {
+        const double dbx_dy = I.slot(a, a.pos[0]), dbx_dz = I.slot(a, a.pos[1]), dby_dx = I.slot(a, a.pos[2]);
+        const double dby_dz = I.slot(a, a.pos[3]), dbz_dx = I.slot(a, a.pos[4]), dbz_dy = I.slot(a, a.pos[5]);
+        const double j1 = __dsub_rn(dby_dz, dbz_dy), j2 = __dsub_rn(dbz_dx, dbx_dz), j3 = __dsub_rn(dbx_dy, dby_dx);
+        return sqrt(__dadd_rn(__dadd_rn(__dmul_rn(j1, j1), __dmul_rn(j2, j2)), __dmul_rn(j3, j3)));
+    }
+    if (a.mode == GPAT_INJECT_LARGE_DIVV) {
+        double d = I.slot(a, a.pos[6]);
+        if (prm.ndim > 1) {
+            d = __dadd_rn(d, I.slot(a, a.pos[7]));
+            if (prm.ndim > 2) d = __dadd_rn(d, I.slot(a, a.pos[8]));
+        }
+        return d;
+    }
+    return I.slot(a, a.pos[9]);  // rho
+}
 
 __global__ void inject_kernel(const __grid_constant__ DevParams prm, const PtlSoA P,
                               const __grid_constant__ InjectArgs a)
@@ -66,9 +143,30 @@ __global__ void inject_kernel(const __grid_constant__ DevParams prm, const PtlSo
     InjStream s{(unsigned)(a.tag0 + i), prm.key0, prm.key1 + (unsigned)prm.mpi_rank, 0u, make_uint4(0, 0, 0, 0)};
     const double mu_max = (double)0.99f;  // particle_module.f90:121
     // no contraction here: these are parity-checked bit for bit against the oracle
-    double x = __dadd_rn(__dmul_rn(s.next(), a.box[3] - a.box[0]), a.box[0]);
-    double y = __dadd_rn(__dmul_rn(s.next(), a.box[4] - a.box[1]), a.box[1]);
-    double z = __dadd_rn(__dmul_rn(s.next(), a.box[5] - a.box[2]), a.box[2]);
+    double x, y, z;
+    if (a.mode == 0) {
+        x = __dadd_rn(__dmul_rn(s.next(), a.box[3] - a.box[0]), a.box[0]);
+        y = __dadd_rn(__dmul_rn(s.next(), a.box[4] - a.box[1]), a.box[1]);
+        z = __dadd_rn(__dmul_rn(s.next(), a.box[5] - a.box[2]), a.box[2]);
+    } else {
+        // rejection loop of inject_particles_at_large_* (e.g. particle_module.f90:860-899): positions
+        // uniform in the whole domain, criterion = interpolated field at rt = 0, a position outside
+        // part_box counts as a miss.  Initial / miss values as in the reference.
+        const bool divv = (a.mode == GPAT_INJECT_LARGE_DIVV), rho = (a.mode == GPAT_INJECT_LARGE_RHO);
+        double crit = divv ? 2.0 : (rho ? 0.0 : -2.0);
+        x = a.box[0]; y = a.box[1]; z = a.box[2];
+        int trials = 0;
+        while (divv ? (-crit < a.vmin) : (crit < a.vmin)) {
+            if (++trials > kMaxTrials) { *a.fail = 1; break; }
+            x = __dadd_rn(__dmul_rn(s.next(), prm.xmax - prm.xmin), prm.xmin);
+            y = __dadd_rn(__dmul_rn(s.next(), prm.ymax - prm.ymin), prm.ymin);
+            z = __dadd_rn(__dmul_rn(s.next(), prm.zmax - prm.zmin), prm.zmin);
+            if (x >= a.box[0] && x <= a.box[3] && y >= a.box[1] && y <= a.box[4] && z >= a.box[2] && z <= a.box[5])
+                crit = inject_criterion(prm, a, x, y, z);
+            else
+                crit = divv ? 3.0 : (rho ? 0.0 : -3.0);
+        }
+    }
     double mu = __dmul_rn(mu_max, __dsub_rn(__dmul_rn(2.0, s.next()), 1.0));
     double p;
     if (a.dist_flag == 0) {  // particle_module.f90:399-407
@@ -108,13 +206,98 @@ __global__ void inject_kernel(const __grid_constant__ DevParams prm, const PtlSo
     P.tag_splitted[slot] = 1;
 }
 
+// ---- get_ncells_large_jz/_absj/_divv/_rho (mhd_data_parallel.f90:2211-2498) ---------------------
+// One thread per physical cell; the cell positions are xpos_local(ix) = dx*(ix-1) + xmin.
+__global__ void ncells_kernel(const __grid_constant__ DevParams prm, const __grid_constant__ InjectArgs a,
+                              unsigned long long* count)
+{
+    const long long ncell = (long long)prm.nx * prm.ny * prm.nz;
+    unsigned long long mine = 0;
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < ncell;
+         c += (long long)gridDim.x * blockDim.x) {
+        const int ix = (int)(c % prm.nx) + 1, iy = (int)((c / prm.nx) % prm.ny) + 1;
+        const int iz = (int)(c / ((long long)prm.nx * prm.ny)) + 1;
+        const double xp = __dadd_rn(__dmul_rn(prm.dx, (double)(ix - 1)), prm.xmin);
+        bool in = xp > a.box[0] && xp < a.box[3];
+        if (prm.ndim > 1) {
+            const double yp = __dadd_rn(__dmul_rn(prm.dy, (double)(iy - 1)), prm.ymin);
+            in = in && yp > a.box[1] && yp < a.box[4];
+        }
+        if (prm.ndim > 2) {
+            const double zp = __dadd_rn(__dmul_rn(prm.dz, (double)(iz - 1)), prm.zmin);
+            in = in && zp > a.box[2] && zp < a.box[5];
+        }
+        if (!in) continue;
+        // Fortran index -> storage index: +1 on resolved axes
+        auto cell_of = [&](int fx, int fy, int fz) {
+            const int cy = (prm.ndim > 1) ? fy + 1 : 0, cz = (prm.ndim > 2) ? fz + 1 : 0;
+            return ((long long)cz * prm.nyg + cy) * prm.nxg + (fx + 1);
+        };
+        auto get = [&](long long cell, int pos) { return pos < 0 ? 0.0f : rec_get(a.fld, cell, a.nrec, a.half, pos); };
+        double v;
+        if (a.mode == GPAT_INJECT_LARGE_JZ) {  // FP32 difference and abs, mhd_data_parallel.f90:2235
+            const long long cc = cell_of(ix, iy, iz);
+            v = (double)fabsf(__fsub_rn(get(cc, a.pos[2]), get(cc, a.pos[0])));
+        } else if (a.mode == GPAT_INJECT_LARGE_ABSJ) {  // all FP32, mhd_data_parallel.f90:2306-2311
+            const long long cc = cell_of(ix, iy, iz);
+            const float j1 = __fsub_rn(get(cc, a.pos[3]), get(cc, a.pos[5]));
+            const float j2 = __fsub_rn(get(cc, a.pos[4]), get(cc, a.pos[1]));
+            const float j3 = __fsub_rn(get(cc, a.pos[0]), get(cc, a.pos[2]));
+            const float s2 = __fadd_rn(__fadd_rn(__fmul_rn(j1, j1), __fmul_rn(j2, j2)), __fmul_rn(j3, j3));
+            v = (double)__fsqrt_rn(s2);
+        } else if (a.mode == GPAT_INJECT_LARGE_DIVV) {
+            // mhd_data_parallel.f90:2417-2424 assigns the whole ghosted array to an allocatable of
+            // shape (nx,ny,nz); after reallocation-on-assignment divv(ix,iy,iz) is the value two
+            // cells to the lower-left on every resolved axis.  Reproduced, not repaired.
+            const long long cc = cell_of(ix - 2, (prm.ndim > 1) ? iy - 2 : iy, (prm.ndim > 2) ? iz - 2 : iz);
+            double d = (double)get(cc, a.pos[6]);
+            if (prm.ndim > 1) {
+                d = __dadd_rn(d, (double)get(cc, a.pos[7]));
+                if (prm.ndim > 2) d = __dadd_rn(d, (double)get(cc, a.pos[8]));
+            }
+            v = -d;
+        } else {
+            v = (double)get(cell_of(ix, iy, iz), a.pos[9]);
+        }
+        if (v > a.vmin) mine++;
+    }
+    // warp-aggregated count
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(count, mine);
+}
+
+static void fill_target(InjectArgs& a, const DevParams& prm, int layout, const float* fld, int sel,
+                        int mode, double vmin, const double box[6], int* fail)
+{
+    a.mode = mode; a.vmin = vmin; a.fld = fld; a.nrec = nrec_of(layout);
+    a.half = prm.time_interp ? sel : 0;
+    a.fail = fail;
+    for (int i = 0; i < 6; ++i) a.box[i] = box[i];
+    const int want[10] = {8 + 14, 8 + 15, 8 + 16, 8 + 18, 8 + 19, 8 + 20, 8 + 1, 8 + 5, 8 + 9, 4};
+    for (int i = 0; i < 10; ++i) {
+        a.pos[i] = -1;
+        for (int k = 0; k < a.nrec; ++k)
+            if (slot_of(layout, k) == want[i]) a.pos[i] = k;
+    }
+}
+
+void launch_ncells(const DevParams& prm, int layout, const float* fld, int sel, int mode, double vmin,
+                   const double box[6], unsigned long long* d_count, int sm_count, cudaStream_t st)
+{
+    InjectArgs a{};
+    fill_target(a, prm, layout, fld, sel, mode, vmin, box, nullptr);
+    cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st);
+    ncells_kernel<<<sm_count * 4, 256, 0, st>>>(prm, a, d_count);
+}
+
 void launch_inject(const DevParams& prm, const PtlSoA& P, long long n, long long start,
                    long long nptl_max, long long tag0, double dt, int dist_flag, double particle_v0,
                    double t_frame, double dt_mhd, const double box[6], double power_index,
-                   cudaStream_t st)
+                   cudaStream_t st, int mode, double vmin, int layout, const float* fld, int sel, int* fail)
 {
     if (n <= 0) return;
-    InjectArgs a;
+    InjectArgs a{};
+    if (mode != 0) fill_target(a, prm, layout, fld, sel, mode, vmin, box, fail);
     a.n = n; a.start = start; a.nptl_max = nptl_max; a.tag0 = tag0; a.dt = dt;
     a.particle_v0 = particle_v0; a.t_frame = t_frame; a.dt_mhd = dt_mhd;
     a.power_index = power_index; a.dist_flag = dist_flag;

@@ -888,7 +888,8 @@ template <int L> struct Coop {
 #ifdef GPAT_MINBLOCKS
 template <int L> struct MinBlocks { static constexpr int V = GPAT_MINBLOCKS; };
 #else
-template <int L> struct MinBlocks { static constexpr int V = (L == L2B) ? 4 : 3; };
+// 3-D Parker at 4 CTAs spills 32 bytes and is still 6 % faster than 3 CTAs on C5 (profiles/README.md)
+template <int L> struct MinBlocks { static constexpr int V = (L == L2B || L == L3B) ? 4 : 3; };
 #endif
 // SEL = which half of the store is farray1 (PushArgs::sel).  It is a template parameter because
 // the two frames must enter every sum in the order (farray1, farray2) whatever half they live in:

@@ -98,6 +98,18 @@ class GpatSim:
         self._ck(self.lib.gpat_inject_uniform(self.h, nptl, dt, dist_flag, particle_v0, t_frame, dt_mhd,
                                               box, power_index), "gpat_inject_uniform")
 
+    def inject_targeted(self, mode, nptl, dt, dist_flag, particle_v0, t_frame, dt_mhd, part_box, power_index,
+                        inject_same_nptl=True, vmin=0.0, ncells_norm=1):
+        """inject_particles_at_large_jz/_absj/_divv/_rho (particle_module.f90:785-1468); returns
+        (nptl_inject, ncells)."""
+        box = (C.c_double * 6)(*part_box)
+        ninj, ncells = C.c_int64(0), C.c_int64(0)
+        self._ck(self.lib.gpat_inject_targeted(self.h, mode, nptl, dt, dist_flag, particle_v0, t_frame, dt_mhd,
+                                               box, power_index, int(bool(inject_same_nptl)), vmin,
+                                               ncells_norm, C.byref(ninj), C.byref(ncells)),
+                 "gpat_inject_targeted")
+        return ninj.value, ncells.value
+
     def particle_mover(self, t0, dtf, nsteps_interval=100, num_fine_steps=1, dump_escaped_dist=0) -> int:
         steps = C.c_uint64(0)
         self._ck(self.lib.gpat_particle_mover(self.h, t0, dtf, nsteps_interval, num_fine_steps,
@@ -211,7 +223,8 @@ class GpatSim:
 def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, power_index=6.2,
                   part_box=None, inject_new_ptl=True, tmax_to_inject=1 << 30, split_flag=1,
                   split_ratio=2.0, pmin_split=2.0, nsteps_interval=100, num_fine_steps=1,
-                  local_dist=True, dump_escaped_dist=False, dt_inject=0.0, on_interval=None):
+                  local_dist=True, dump_escaped_dist=False, dt_inject=0.0, on_interval=None,
+                  inject_mode=0, inject_same_nptl=True, inject_min=0.0, ncells_norm=1):
     """solve_transport_equation (stochastic-mhd.f90:312-567) for one rank.
 
     `sim` is a GpatSim (or the test oracle, which has the same methods); `frames` is a
@@ -233,7 +246,11 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
         sim.upload_fields(1 if P.time_interp else 0, get(tf))
         t0, dtf = tstamps[tf - 1], tstamps[tf] - tstamps[tf - 1]
         if (tf == 1 or inject_new_ptl) and tf <= tmax_to_inject:   # :462-485
-            sim.inject_uniform(nptl, dt_inject, dist_flag, particle_v0, t0, dtf, part_box, power_index)
+            if inject_mode:                                    # :464-480 (inject_large_jz ... _rho)
+                sim.inject_targeted(inject_mode, nptl, dt_inject, dist_flag, particle_v0, t0, dtf, part_box,
+                                    power_index, inject_same_nptl, inject_min, ncells_norm)
+            else:
+                sim.inject_uniform(nptl, dt_inject, dist_flag, particle_v0, t0, dtf, part_box, power_index)
         if tf == 1:                                            # :488-494
             d0 = sim.diagnostics(local_dist)
             d0["frame"] = 0

@@ -391,3 +391,41 @@ def test_1d_intervals_end_on_frame_time_and_leak_through_open_x():
     # weight is conserved between the box and the open-x leak; y never moves in 1-D so no y escapes
     assert abs(ptl["weight"].sum() + c.leak + c.leak_negp - 800.0) < 1e-9  # 400 injected per interval
     assert res[-1]["quick"][0] == c.nptl_current
+
+
+# ---- targeted injection (particle_module.f90:785-1468, mhd_data_parallel.f90:2211-2498) ----------
+@pytest.mark.parametrize("mode", [1, 2, 4, 5])
+def test_targeted_injection_counts_and_accepts_like_the_reference(mode):
+    w, P, frames, _ = make_case("c3", grid=48, nptl=8)
+    o = Oracle(P, 4000)
+    o.upload_fields(0, frames[0])
+    o.upload_fields(1, frames[1])
+    fa = o.get_fields(0).reshape(P.ny + 4, P.nx + 4, 32)
+    jz = np.abs(fa[..., 8 + 15] - fa[..., 8 + 13])                      # FP32, as get_ncells_large_jz
+    absj = np.sqrt((fa[..., 8 + 17] - fa[..., 8 + 19]) ** 2 + (fa[..., 8 + 18] - fa[..., 8 + 14]) ** 2
+                   + (fa[..., 8 + 13] - fa[..., 8 + 15]) ** 2)
+    ndivv = -(fa[..., 8].astype(np.float64) + fa[..., 8 + 4].astype(np.float64))
+    rho = fa[..., 3]
+    box = box_of(P)
+    box[0] += 0.2 * P.lx
+    box[3] -= 0.1 * P.lx
+    xs = P.xmin + P.dx * np.arange(P.nx)
+    ys = P.ymin + P.dy * np.arange(P.ny)
+    inbox = ((ys > box[1]) & (ys < box[4]))[:, None] & ((xs > box[0]) & (xs < box[3]))[None, :]
+    phys = {1: jz[2:-2, 2:-2], 2: absj[2:-2, 2:-2], 5: rho[2:-2, 2:-2],
+            4: ndivv[0:P.ny, 0:P.nx]}[mode]   # the divv counter reads two cells to the lower-left
+    vmin = float(np.quantile(phys[inbox], 0.6))
+    want_cells = int(np.count_nonzero(inbox & (phys > vmin)))
+    ninj, ncells = o.inject_targeted(mode, 900, 0.0, 1, w.particle_v0, 0.0, 0.1, box, 6.2, False, vmin, 2 * want_cells)
+    assert ncells == want_cells and ninj == 450           # int(900 * ncells / (2 ncells))
+    ptl = o.download_particles()
+    assert len(ptl) == 450 and np.array_equal(ptl["tag_injected"], np.arange(450))
+    assert np.all((ptl["x"] >= box[0]) & (ptl["x"] <= box[3]))
+    F = o.interp(ptl["x"], ptl["y"], ptl["z"], np.zeros(len(ptl)))
+    got = {1: np.abs(F[:, 8 + 15] - F[:, 8 + 13]),
+           2: np.sqrt((F[:, 8 + 17] - F[:, 8 + 19]) ** 2 + (F[:, 8 + 18] - F[:, 8 + 14]) ** 2
+                      + (F[:, 8 + 13] - F[:, 8 + 15]) ** 2),
+           4: -(F[:, 8] + F[:, 8 + 4]), 5: F[:, 3]}[mode]
+    assert np.all(got >= vmin)                            # the loop runs while crit < vmin
+    # the accepted positions favour the cells above the threshold: not uniform in the box
+    assert (ptl["t"] >= 0.0).all() and (ptl["t"] <= 0.1).all() and np.all(ptl["weight"] == 1.0)

@@ -520,3 +520,60 @@ def test_restart_round_trip_is_bit_exact():
         assert (cc.nptl_current, cc.nptl_split, cc.tag_max, cc.leak, cc.leak_negp) == \
                (ca.nptl_current, ca.nptl_split, ca.tag_max, ca.leak, ca.leak_negp)
         c.close()
+
+
+@pytest.mark.parametrize("key,grid,mode,vmin,same", [
+    ("c1", 64, 1, None, True),      # inject_large_jz, every rank injects nptl
+    ("c1", 64, 2, None, False),     # inject_large_absj, scaled by ncells / ncells_norm
+    ("c3", 64, 4, None, True),      # inject_large_divv (compression at the shock)
+    ("c4", 64, 5, None, True),      # inject_large_rho (density slot kept by the D_pp layout)
+    ("c5", 24, 1, None, True),      # 3-D
+])
+def test_targeted_injection_parity(key, grid, mode, vmin, same):
+    """inject_particles_at_large_jz/_absj/_divv/_rho + get_ncells_large_* (particle_module.f90:
+    785-1468, mhd_data_parallel.f90:2211-2498): same cell count, same number of particles, and
+    the same accepted positions from the same per-particle Philox streams, bit for bit."""
+    w, P, frames, _ = make_case(key, grid=grid, nptl=8)
+    g, o = pair(P, 6000)
+    load_fields((g, o), frames, P.time_interp)
+    box = box_of(P)
+    box[0] += 0.1 * (P.xmax - P.xmin)       # a part_box smaller than the domain: misses are redrawn
+    box[4] -= 0.15 * (P.ymax - P.ymin)
+    # threshold = a value the interpolated criterion exceeds on roughly a third of the box
+    fa = o.get_fields(0).reshape(-1, 32)
+    crit = {1: np.abs(fa[:, 8 + 15] - fa[:, 8 + 13]),
+            2: np.sqrt((fa[:, 8 + 17] - fa[:, 8 + 19]) ** 2 + (fa[:, 8 + 18] - fa[:, 8 + 14]) ** 2
+                       + (fa[:, 8 + 13] - fa[:, 8 + 15]) ** 2),
+            4: -(fa[:, 8] + fa[:, 8 + 4] + (fa[:, 8 + 8] if P.ndim == 3 else 0.0)),
+            5: fa[:, 3]}[mode]
+    vmin = float(np.quantile(crit, 0.7))
+    norm = 3 * grid
+    rg = g.inject_targeted(mode, 1500, 1e-4, 1, w.particle_v0, 0.0, 0.1, box, 6.2, same, vmin, norm)
+    ro = o.inject_targeted(mode, 1500, 1e-4, 1, w.particle_v0, 0.0, 0.1, box, 6.2, same, vmin, norm)
+    assert rg == ro and ro[0] > 0 and ro[1] > 0
+    if same:
+        assert ro[0] == 1500
+    a, b = g.download_particles(), o.download_particles()
+    assert_particles_identical(a, b, f"targeted injection mode {mode}")
+    assert np.all((a["x"] >= box[0]) & (a["x"] <= box[3]) & (a["y"] >= box[1]) & (a["y"] <= box[4]))
+    cg, co = g.counters(), o.counters()
+    assert (cg.nptl_current, cg.tag_max) == (co.nptl_current, co.tag_max)
+    g.close()
+
+
+def test_targeted_injection_rejects_what_it_cannot_do():
+    from stochastic_parker_b200 import GpatError
+    w, P, frames, _ = make_case("c1", grid=32, nptl=8)
+    g = GpatSim(P, 100)
+    g.upload_fields(0, frames[0])
+    with pytest.raises(GpatError):   # the base 2-D record has no density slot
+        g.inject_targeted(5, 10, 0.0, 1, 1.0, 0.0, 0.1, box_of(P), 6.2, True, 0.5, 1)
+    with pytest.raises(GpatError):   # deltab maps are outside the GPU path
+        g.inject_targeted(3, 10, 0.0, 1, 1.0, 0.0, 0.1, box_of(P), 6.2, True, 0.5, 1)
+    g.close()
+    P.keep_rho = 1
+    g = GpatSim(P, 100)
+    g.upload_fields(0, frames[0])
+    n, nc = g.inject_targeted(5, 10, 0.0, 1, 1.0, 0.0, 0.1, box_of(P), 6.2, True, 0.5, 1)
+    assert n == 10 and nc > 0
+    g.close()
