@@ -12,7 +12,7 @@ module gpat_cuda
     private
     public :: gpat_params, gpat_hist_spec, gpat_particle, gpat_counters, gpat_timings
     public :: gpat_init, gpat_set_params, gpat_finalize, gpat_last_error
-    public :: gpat_upload_fields, gpat_swap_fields
+    public :: gpat_upload_fields, gpat_prefetch_fields, gpat_swap_fields
     public :: gpat_inject_uniform, gpat_inject_targeted, gpat_particle_mover, gpat_split
     public :: gpat_download_particles, gpat_upload_particles
     public :: gpat_download_escaped, gpat_reset_escaped
@@ -104,6 +104,15 @@ module gpat_cuda
             type(c_ptr), value :: h, f
             integer(c_int), value :: slot, nvar, with_grad
         end function gpat_upload_fields
+
+        !< frame pipeline: start the H2D copy of a frame already read into farray-shaped host
+        !< memory (e.g. frame tf+1 during the push of frame tf); a later gpat_upload_fields with
+        !< the same pointer only runs the gradient/pack kernel (stochastic-mhd.f90:401-447)
+        integer(c_int) function gpat_prefetch_fields(h, f, nvar) bind(C, name="gpat_prefetch_fields")
+            import :: c_ptr, c_int
+            type(c_ptr), value :: h, f
+            integer(c_int), value :: nvar
+        end function gpat_prefetch_fields
 
         !< copy_fields (mhd_data_parallel.f90:1920)
         integer(c_int) function gpat_swap_fields(h) bind(C, name="gpat_swap_fields")

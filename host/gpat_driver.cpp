@@ -210,7 +210,7 @@ int main(int argc, char** argv)
         return 2;
     }
     // features outside the GPU path must stay off; the library re-checks the ones it is told about
-    for (const char* k : {"-is", "-ij", "-ib", "-iv", "-ir", "-iaj", "-tf", "-rf", "-vdt"})
+    for (const char* k : {"-is", "-ib", "-tf", "-rf", "-vdt"})
         if (cli.b(k)) {
             std::fprintf(stderr, "gpat_driver: switch %s is outside the GPU particle path\n", k);
             return 2;
@@ -277,12 +277,14 @@ int main(int argc, char** argv)
     P.deltab_flag = (int)cli.i("-db"); P.correlation_flag = (int)cli.i("-co"); P.acc_by_surface = (int)cli.i("-as");
     P.seed = (uint64_t)cli.i("-seed"); P.rng_mode = GPAT_RNG_PHILOX; P.mpi_rank = 0;
     P.strict_math = (int)cli.i("-strict");
+    P.keep_rho = cli.b("-ir") ? 1 : 0;  // inject_large_rho interpolates the density (particle_module.f90:1448)
 
     gpat_handle h = nullptr;
     const long long nptl_max = cli.i("-nm"), nptl = cli.i("-np");
     CK(gpat_init(&h, (int)cli.i("-gpu"), nptl_max, &P), "gpat_init");
 
-    const size_t ncell = (size_t)(mc.nx + 4) * (mc.ny + 4) * (P.ndim == 3 ? mc.nz + 4 : 1);
+    // farray(:, -1:nx+2, [-1:ny+2, [-1:nz+2]]) (mhd_data_parallel.f90:77-83)
+    const size_t ncell = (size_t)(mc.nx + 4) * (P.ndim >= 2 ? mc.ny + 4 : 1) * (P.ndim == 3 ? mc.nz + 4 : 1);
     std::vector<float> frame;
     // calc_tstamps_mhd (mhd_config.f90:263-271): uniform output interval
     auto tstamp = [&](int i) { return i * mc.dt_out; };
@@ -371,9 +373,24 @@ int main(int argc, char** argv)
             CK(gpat_upload_fields(h, P.time_interp ? 1 : 0, frame.data(), 8, 0), "gpat_upload_fields");
         }
         const double t0 = tstamp(tf - 1), dtf = tstamp(tf) - tstamp(tf - 1);  // tstamps_mhd(tf - t_start), particle_module.f90:1868
-        if ((tf == t_start + 1 || inject_new) && tf <= tmax_to_inject)  // :462-485
-            CK(gpat_inject_uniform(h, nptl, cli.d("-dt"), dist_flag, cli.d("-pv"), t0, dtf, part_box, cli.d("-pi")),
-               "gpat_inject_uniform");
+        if ((tf == t_start + 1 || inject_new) && tf <= tmax_to_inject) {  // :462-485, same precedence
+            int mode = 0;
+            double vmin = 0.0;
+            long long norm = 1;
+            if (cli.b("-ij")) { mode = GPAT_INJECT_LARGE_JZ; vmin = cli.d("-jz"); norm = cli.i("-nn"); }
+            else if (cli.b("-iaj")) { mode = GPAT_INJECT_LARGE_ABSJ; vmin = cli.d("-ajm"); norm = cli.i("-naj"); }
+            else if (cli.b("-iv")) { mode = GPAT_INJECT_LARGE_DIVV; vmin = cli.d("-dv"); norm = cli.i("-nv"); }
+            else if (cli.b("-ir")) { mode = GPAT_INJECT_LARGE_RHO; vmin = cli.d("-rm"); norm = cli.i("-nr"); }
+            if (mode) {
+                int64_t ninj = 0, ncells = 0;
+                CK(gpat_inject_targeted(h, mode, nptl, cli.d("-dt"), dist_flag, cli.d("-pv"), t0, dtf, part_box,
+                                        cli.d("-pi"), cli.b("-sn") ? 1 : 0, vmin, norm, &ninj, &ncells),
+                   "gpat_inject_targeted");
+            } else {
+                CK(gpat_inject_uniform(h, nptl, cli.d("-dt"), dist_flag, cli.d("-pv"), t0, dtf, part_box, cli.d("-pi")),
+                   "gpat_inject_uniform");
+            }
+        }
         if (tf == t_start + 1) CK(diagnostics(t_start, true), "initial diagnostics");  // :488-494
         uint64_t steps = 0;
         CK(gpat_particle_mover(h, t0, dtf, nsteps_interval, num_fine_steps, dump_escaped_dist ? 1 : 0, &steps),

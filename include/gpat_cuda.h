@@ -166,6 +166,16 @@ const char* gpat_last_error(gpat_handle h);
  * slot = 0 -> farray1 (frame at t0), 1 -> farray2 (frame at t0 + dtf). */
 int gpat_upload_fields(gpat_handle h, int slot, const float* f, int nvar, int with_grad);
 
+/* Frame pipeline (stochastic-mhd.f90:401-447 reads frame tf at the top of every iteration,
+ * serially).  gpat_prefetch_fields starts the host->device copy of a frame the caller has
+ * ALREADY read (e.g. frame tf+1, read while frame tf is being pushed) on a separate copy
+ * stream and returns at once, so the copy overlaps the next gpat_particle_mover.  A later
+ * gpat_upload_fields with the same host pointer and nvar finds the bytes on the device and
+ * only runs the gradient/pack kernel.  The host buffer must stay unchanged (and should be
+ * page-locked) until that gpat_upload_fields call returns.  Optional: without it
+ * gpat_upload_fields copies synchronously as before. */
+int gpat_prefetch_fields(gpat_handle h, const float* f, int nvar);
+
 /* Replaces copy_fields (mhd_data_parallel.f90:1920): farray1 = farray2. O(1). */
 int gpat_swap_fields(gpat_handle h);
 

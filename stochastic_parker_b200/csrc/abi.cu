@@ -106,6 +106,14 @@ struct gpat_sim {
     float* fld = nullptr;
     float* stage = nullptr;
     size_t stage_bytes = 0;
+    // frame pipeline (gpat_prefetch_fields): the next frame's H2D copy runs on its own stream into a
+    // second staging buffer while the push kernel owns the compute stream
+    cudaStream_t st_copy = nullptr;
+    cudaEvent_t ev_copy = nullptr;
+    float* stage2 = nullptr;
+    size_t stage2_bytes = 0;
+    const float* pf_ptr = nullptr;  // host pointer of the frame in flight / landed in stage2
+    int pf_nvar = 0;
     const void* registered_host[2] = {nullptr, nullptr};
     size_t registered_bytes[2] = {0, 0};
     // histograms
@@ -129,7 +137,7 @@ struct gpat_sim {
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
     // instrumentation
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     gpat_timings tm{};
     std::string err;
 };
@@ -565,13 +573,15 @@ int gpat_finalize(gpat_handle h)
     for (int i = 0; i < 2; ++i)
         if (h->registered_host[i]) cudaHostUnregister(const_cast<void*>(h->registered_host[i]));
     void* ptrs[] = {h->ptl_mem, h->esc_mem, h->d_counters, h->d_nptl_split, h->d_leak, h->d_queue,
-                    h->w.tile_counts, h->w.tile_offsets, h->idx_a, h->idx_b, h->fld, h->stage,
+                    h->w.tile_counts, h->w.tile_offsets, h->idx_a, h->idx_b, h->fld, h->stage, h->stage2,
                     h->d_fglobal, h->d_flocal[0], h->d_flocal[1], h->d_flocal[2], h->d_flocal[3],
                     h->d_fesc, h->d_pthr, h->d_sums, h->d_minmax, h->d_quick, h->d_table, h->d_aos};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& ev : h->ev)
         if (ev) cudaEventDestroy(ev);
+    if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+    if (h->st_copy) { cudaStreamSynchronize(h->st_copy); cudaStreamDestroy(h->st_copy); }
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
     return GPAT_OK;
@@ -587,18 +597,27 @@ int gpat_upload_fields(gpat_handle h, int slot, const float* f, int nvar, int wi
         return fail(h, GPAT_ERR_INVALID, "gpat_upload_fields: slot 1 (farray2) exists only with time_interp = 1");
     CU(cudaSetDevice(h->device));
     size_t bytes = (size_t)h->dp.nxg * h->dp.nyg_src * h->dp.nzg * nvar * sizeof(float);
-    if (bytes > h->stage_bytes) {
-        if (h->stage) cudaFree(h->stage);
-        h->stage = nullptr;
-        h->stage_bytes = 0;
-        CU(cudaMalloc(&h->stage, bytes));
-        h->stage_bytes = bytes;
-    }
+    const float* src;
     CU(cudaEventRecord(h->ev[2], h->st));
-    CU(cudaMemcpyAsync(h->stage, f, bytes, cudaMemcpyHostToDevice, h->st));
+    if (h->pf_ptr == f && h->pf_nvar == nvar) {
+        // the frame was (or is being) copied by gpat_prefetch_fields: only the pack kernel is left
+        CU(cudaStreamWaitEvent(h->st, h->ev_copy, 0));
+        src = h->stage2;
+        h->pf_ptr = nullptr;
+    } else {
+        if (bytes > h->stage_bytes) {
+            if (h->stage) cudaFree(h->stage);
+            h->stage = nullptr;
+            h->stage_bytes = 0;
+            CU(cudaMalloc(&h->stage, bytes));
+            h->stage_bytes = bytes;
+        }
+        CU(cudaMemcpyAsync(h->stage, f, bytes, cudaMemcpyHostToDevice, h->st));
+        src = h->stage;
+    }
     CU(cudaEventRecord(h->ev[3], h->st));
     int half = (slot == 0) ? h->sel : (h->sel ^ 1);
-    launch_pack(h->stage, nvar, with_grad, h->dp, h->layout, h->fld, half, h->sm_count, h->st);
+    launch_pack(src, nvar, with_grad, h->dp, h->layout, h->fld, half, h->sm_count, h->st);
     h->tm.total_launches++;
     CU(cudaEventRecord(h->ev[4], h->st));
     CU(cudaGetLastError());
@@ -607,6 +626,34 @@ int gpat_upload_fields(gpat_handle h, int slot, const float* f, int nvar, int wi
     h->tm.grad_ms = elapsed(h->ev[3], h->ev[4]);
     h->have_field[slot] = true;
     return GPAT_OK;
+}
+
+int gpat_prefetch_fields(gpat_handle h, const float* f, int nvar)
+{
+    if (!h || !f) return fail(h, GPAT_ERR_INVALID, "gpat_prefetch_fields: bad arguments");
+    if (nvar != 8 && nvar != 32) return fail(h, GPAT_ERR_INVALID, "gpat_prefetch_fields: nvar must be 8 or 32");
+    CU(cudaSetDevice(h->device));
+    if (!h->st_copy) {
+        CU(cudaStreamCreateWithFlags(&h->st_copy, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+    }
+    size_t bytes = (size_t)h->dp.nxg * h->dp.nyg_src * h->dp.nzg * nvar * sizeof(float);
+    if (bytes > h->stage2_bytes) {
+        CU(cudaStreamSynchronize(h->st_copy));
+        if (h->stage2) cudaFree(h->stage2);
+        h->stage2 = nullptr;
+        h->stage2_bytes = 0;
+        CU(cudaMalloc(&h->stage2, bytes));
+        h->stage2_bytes = bytes;
+    }
+    // stage2 may still feed the pack kernel of the previous frame on the compute stream
+    CU(cudaEventRecord(h->ev[6], h->st));
+    CU(cudaStreamWaitEvent(h->st_copy, h->ev[6], 0));
+    CU(cudaMemcpyAsync(h->stage2, f, bytes, cudaMemcpyHostToDevice, h->st_copy));
+    CU(cudaEventRecord(h->ev_copy, h->st_copy));
+    h->pf_ptr = f;
+    h->pf_nvar = nvar;
+    return GPAT_OK;  // no synchronisation: the copy overlaps whatever the caller launches next
 }
 
 int gpat_swap_fields(gpat_handle h)

@@ -69,6 +69,16 @@ class GpatSim:
         self.P = params.copy()
 
     # ---- fields -------------------------------------------------------------
+    def prefetch_fields(self, f: np.ndarray):
+        """Start the H2D copy of a frame that a later upload_fields(slot, f) will pack; `f` must be
+        C-contiguous float32 (ideally page-locked) and must not change until then."""
+        if f.dtype != np.float32 or not f.flags["C_CONTIGUOUS"]:
+            raise ValueError("prefetch_fields needs a C-contiguous float32 array (no temporary copies)")
+        nvar = f.shape[-1]
+        if f.size != int(np.prod(self.grid_shape)) * nvar:
+            raise ValueError(f"field array has {f.size} floats, grid {self.grid_shape} x {nvar} expected")
+        self._ck(self.lib.gpat_prefetch_fields(self.h, f.ctypes.data_as(C.c_void_p), nvar), "gpat_prefetch_fields")
+
     def upload_fields(self, slot: int, f: np.ndarray, with_grad: int = 0):
         f = np.ascontiguousarray(f, dtype=np.float32)
         nvar = f.shape[-1]

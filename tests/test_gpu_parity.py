@@ -577,3 +577,29 @@ def test_targeted_injection_rejects_what_it_cannot_do():
     n, nc = g.inject_targeted(5, 10, 0.0, 1, 1.0, 0.0, 0.1, box_of(P), 6.2, True, 0.5, 1)
     assert n == 10 and nc > 0
     g.close()
+
+
+def test_prefetched_frames_give_identical_runs():
+    """gpat_prefetch_fields (frame pipeline): copying frame tf+1 on the copy stream while frame
+    tf is pushed changes nothing in the results, bit for bit, in either build."""
+    w, P, frames, ts = make_case("c1", grid=64, nptl=1500, nframes=4)
+    frames = [np.ascontiguousarray(f, dtype=np.float32) for f in frames]
+    for strict in (1, 0):
+        Pg = P.copy()
+        Pg.strict_math = strict
+        outs = []
+        for pipelined in (False, True):
+            g = GpatSim(Pg, w.nptl_max)
+            g.upload_fields(0, frames[0])
+            for tf in (1, 2, 3):
+                g.upload_fields(1, frames[tf])
+                if pipelined and tf < 3:
+                    g.prefetch_fields(frames[tf + 1])
+                if tf == 1:
+                    g.inject_uniform(1500, 0.0, 1, w.particle_v0, ts[0], ts[1] - ts[0], box_of(P), 6.2)
+                g.particle_mover(ts[tf - 1], ts[tf] - ts[tf - 1], 100, 1, 0)
+                g.split(2.0, 2.0)
+                g.swap_fields()
+            outs.append(g.download_particles())
+            g.close()
+        assert_particles_identical(outs[1], outs[0], f"prefetch strict={strict}")
