@@ -14,6 +14,7 @@ module gpat_cuda
     public :: gpat_init, gpat_set_params, gpat_finalize, gpat_last_error
     public :: gpat_upload_fields, gpat_prefetch_fields, gpat_swap_fields
     public :: gpat_inject_uniform, gpat_inject_targeted, gpat_particle_mover, gpat_split
+    public :: gpat_init_tracking, gpat_tracked_shape, gpat_download_tracked, gpat_reset_tracked
     public :: gpat_download_particles, gpat_upload_particles
     public :: gpat_download_escaped, gpat_reset_escaped
     public :: gpat_get_counters, gpat_set_counters
@@ -144,6 +145,36 @@ module gpat_cuda
             real(c_double), intent(in) :: part_box(6)
             integer(c_int64_t), intent(out) :: nptl_injected, ncells
         end function gpat_inject_targeted
+
+        !< init_particle_tracking (particle_module.f90:5825) without the HDF5 read:
+        !< tags = c_loc(tags_tracking), ncols = split_times_max + 2
+        integer(c_int) function gpat_init_tracking(h, tags, ncols, nptl_tracking, nsteps_interval) &
+                bind(C, name="gpat_init_tracking")
+            import :: c_ptr, c_int, c_int64_t
+            type(c_ptr), value :: h, tags
+            integer(c_int), value :: ncols, nsteps_interval
+            integer(c_int64_t), value :: nptl_tracking
+        end function gpat_init_tracking
+
+        integer(c_int) function gpat_tracked_shape(h, nsteps_tracking_max, nptl_tracking) &
+                bind(C, name="gpat_tracked_shape")
+            import :: c_ptr, c_int, c_int64_t
+            type(c_ptr), value :: h
+            integer(c_int64_t), intent(out) :: nsteps_tracking_max, nptl_tracking
+        end function gpat_tracked_shape
+
+        !< particles_tracked(nsteps_tracking_max, nptl_tracking) for dump_tracked_particles
+        !< (particle_module.f90:6236); out = c_loc(particles_tracked)
+        integer(c_int) function gpat_download_tracked(h, out) bind(C, name="gpat_download_tracked")
+            import :: c_ptr, c_int
+            type(c_ptr), value :: h, out
+        end function gpat_download_tracked
+
+        !< reset_tracked_particles (particle_module.f90:5884)
+        integer(c_int) function gpat_reset_tracked(h) bind(C, name="gpat_reset_tracked")
+            import :: c_ptr, c_int
+            type(c_ptr), value :: h
+        end function gpat_reset_tracked
 
         !< particle_mover (particle_module.f90:1846), both remove_particles passes included
         integer(c_int) function gpat_particle_mover(h, t0, dtf, nsteps_interval, num_fine_steps, &

@@ -215,6 +215,28 @@ int gpat_inject_targeted(gpat_handle h, int mode, int64_t nptl, double dt, int d
                          double vmin, int64_t ncells_norm, int64_t* nptl_injected,
                          int64_t* ncells);
 
+/* ---- particle tracking ---------------------------------------------------
+ * The second run of the reference's two-run workflow (docs/source/development/
+ * particle_module.rst:42-131): particles whose (origin, tag_injected, tag_splitted chain) appears
+ * in the tag table are marked by NEGATED tags at injection (particle_module.f90:434-440), sampled
+ * every nsteps_interval pushes into particles_tracked (particle_module.f90:1697-1724, 1806-1812)
+ * and followed through splits (particle_module.f90:5452-5473).  The per-particle Philox streams
+ * are keyed by |tag|, so the tracking run replays the trajectories of the run the tags came from.
+ *
+ * gpat_init_tracking replaces init_particle_tracking (particle_module.f90:5825-5879) minus the
+ * HDF5 read: tags = tags_tracking(ncols = split_times_max + 2, nptl_tracking), column-major, sorted
+ * by origin, tag_injected and the tag_splitted chain.  particles_tracked has
+ * nsteps_tracking_max = ceiling((1/dt_min_rel)/nsteps_interval) + 1 rows per tracked particle.
+ * gpat_download_tracked copies particles_tracked(nsteps_tracking_max, nptl_tracking) (column-major
+ * records, what dump_tracked_particles writes, particle_module.f90:6236-6299);
+ * gpat_reset_tracked is reset_tracked_particles (particle_module.f90:5884-5902).
+ * Tracking runs call gpat_particle_mover with num_fine_steps = 1 (stochastic-mhd.f90:497-499). */
+int gpat_init_tracking(gpat_handle h, const int32_t* tags, int ncols, int64_t nptl_tracking,
+                       int nsteps_interval);
+int gpat_tracked_shape(gpat_handle h, int64_t* nsteps_tracking_max, int64_t* nptl_tracking);
+int gpat_download_tracked(gpat_handle h, gpat_particle* out);
+int gpat_reset_tracked(gpat_handle h);
+
 /* Replaces particle_mover (particle_module.f90:1846-1974) including both
  * remove_particles passes (particle_module.f90:5365-5403).  t0 = tstamps_mhd(frame),
  * dtf = tstamps_mhd(frame+1) - t0.  Blocking.  steps_done (may be NULL) receives

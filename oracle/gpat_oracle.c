@@ -53,9 +53,16 @@ typedef struct orc_sim {
     const double* rng_table;  /* optional uniform table */
     int64_t rng_slots, rng_max_steps;
     uint64_t steps;           /* push_particle_* calls */
+    /* particle tracking, PM:144-150 */
+    int track_particle_flag;
+    int split_times_max;
+    int64_t nptl_tracking, nsteps_tracking_max;
+    int32_t* tags_tracking;          /* (split_times_max+2, nptl_tracking), column-major */
+    gpat_particle* particles_tracked; /* (nsteps_tracking_max, nptl_tracking), column-major */
 } orc_sim;
 
 static inline double sq(double x) { return x * x; }
+static void track_after_push(orc_sim* S, gpat_particle* ptl); /* particle tracking, below */
 
 /* ------------------------------------------------------------------------ */
 /* Philox4x32-10 (Salmon et al., SC'11), written from the published algorithm. */
@@ -99,8 +106,8 @@ static void step_uniforms(const orc_sim* S, const gpat_particle* ptl, double u[4
 {
     uint64_t step = get_rng_step(ptl);
     if (S->P.rng_mode == GPAT_RNG_TABLE && S->rng_table) {
-        int64_t slot = ptl->tag_injected;
-        if (slot < 0 || slot >= S->rng_slots || (int64_t)step >= S->rng_max_steps) {
+        int64_t slot = abs(ptl->tag_injected);
+        if (slot >= S->rng_slots || (int64_t)step >= S->rng_max_steps) {
             u[0] = u[1] = u[2] = u[3] = 0.5;
             return;
         }
@@ -108,8 +115,10 @@ static void step_uniforms(const orc_sim* S, const gpat_particle* ptl, double u[4
         u[0] = t[0]; u[1] = t[1]; u[2] = t[2]; u[3] = t[3];
         return;
     }
-    uint32_t ctr[4] = {(uint32_t)step, (uint32_t)(step >> 32), (uint32_t)ptl->tag_injected,
-                       (uint32_t)ptl->tag_splitted};
+    /* tracked particles carry NEGATED tags (PM:436-437, 5453-5472); the stream is keyed by the
+     * magnitudes so that a tracking run replays the trajectories of the run it was selected from */
+    uint32_t ctr[4] = {(uint32_t)step, (uint32_t)(step >> 32), (uint32_t)abs(ptl->tag_injected),
+                       (uint32_t)abs(ptl->tag_splitted)};
     uint32_t key[2] = {(uint32_t)S->P.seed, (uint32_t)(S->P.seed >> 32) + (uint32_t)ptl->origin};
     uint32_t o[4];
     philox4x32_10(ctr, key, o);
@@ -178,6 +187,7 @@ void orc_destroy(orc_sim* S)
 {
     if (!S) return;
     free(S->farray1); free(S->farray2); free(S->ptls); free(S->escaped);
+    free(S->tags_tracking); free(S->particles_tracked);
     free(S);
 }
 
@@ -971,6 +981,7 @@ static void particle_mover_one_cycle(orc_sim* S, double t0, double dtf, int nste
                 one_push(S, &ptl, t0, dtf, 0, &deltax, &deltay, &deltaz, &deltap);
                 steps++;
                 ptl.nsteps_pushed = (ptl.nsteps_pushed + 1) % nsteps_interval; /* PM:1694 */
+                track_after_push(S, &ptl);                                     /* PM:1697-1703 */
             }
             /* make sure ptl%t reaches the target exactly, PM:1707-1826 */
             if ((ptl.t - t0) > dt_target && ptl.count_flag == GPAT_COUNT_FLAG_INBOX) {
@@ -982,11 +993,17 @@ static void particle_mover_one_cycle(orc_sim* S, double t0, double dtf, int nste
                 double dt_old = ptl.dt;
                 ptl.dt = t0 + dt_target - ptl.t;
                 if (ptl.dt > 0) {
-                    ptl.nsteps_pushed = ptl.nsteps_pushed - 1; /* PM:1723 (untracked) */
+                    if (ptl.tag_splitted < 0 && ptl.nsteps_pushed == 0) { /* PM:1717-1721 */
+                        ptl.nsteps_tracked = ptl.nsteps_tracked - 1; /* back one step */
+                        ptl.nsteps_pushed = nsteps_interval - 2;
+                    } else {
+                        ptl.nsteps_pushed = ptl.nsteps_pushed - 1; /* PM:1723 */
+                    }
                     one_push(S, &ptl, t0, dtf, 1, &deltax, &deltay, &deltaz, &deltap);
                     steps++;
                     /* Fortran mod keeps the sign of the dividend, like C's % */
                     ptl.nsteps_pushed = (ptl.nsteps_pushed + 1) % nsteps_interval;
+                    track_after_push(S, &ptl);                      /* PM:1806-1812 */
                 }
                 ptl.dt = dt_old;
                 negp_or_bc(S, &ptl, e);
@@ -1088,6 +1105,96 @@ void orc_debug_push_n(orc_sim* S, double t0, double dtf, int nsteps, uint64_t* s
 /* ------------------------------------------------------------------------ */
 /* injection: PM:454-530 (whole-field branch) + PM:385-441                     */
 /* ------------------------------------------------------------------------ */
+/* ------------------------------------------------------------------------ */
+/* particle tracking: init_particle_tracking (PM:5825-5879), reset (PM:5884),  */
+/* is_particle_selected (PM:5920-5959), locate_particle (PM:5967-5990)         */
+/* ------------------------------------------------------------------------ */
+void orc_init_tracking(orc_sim* S, const int32_t* tags, int ncols, int64_t nptl_tracking,
+                       int nsteps_interval)
+{
+    free(S->tags_tracking); free(S->particles_tracked);
+    S->track_particle_flag = 1;
+    S->split_times_max = ncols - 2;
+    S->nptl_tracking = nptl_tracking;
+    S->tags_tracking = (int32_t*)malloc(sizeof(int32_t) * (size_t)ncols * nptl_tracking);
+    memcpy(S->tags_tracking, tags, sizeof(int32_t) * (size_t)ncols * nptl_tracking);
+    /* `1.0 / dt_min_rel` promotes the default-real literal; ceiling of the f64 quotient */
+    S->nsteps_tracking_max = (int64_t)ceil((1.0 / S->P.dt_min_rel) / nsteps_interval) + 1;
+    S->particles_tracked = (gpat_particle*)calloc((size_t)S->nsteps_tracking_max * nptl_tracking,
+                                                  sizeof(gpat_particle));
+}
+
+void orc_reset_tracked(orc_sim* S)
+{
+    if (S->particles_tracked)
+        memset(S->particles_tracked, 0, sizeof(gpat_particle) * (size_t)S->nsteps_tracking_max * S->nptl_tracking);
+}
+
+int64_t orc_get_tracked(const orc_sim* S, gpat_particle* out, int64_t* nsteps_max)
+{
+    if (nsteps_max) *nsteps_max = S->nsteps_tracking_max;
+    if (out && S->particles_tracked)
+        memcpy(out, S->particles_tracked, sizeof(gpat_particle) * (size_t)S->nsteps_tracking_max * S->nptl_tracking);
+    return S->nptl_tracking;
+}
+
+#define TAG(r, c) S->tags_tracking[((r) - 1) + (size_t)(S->split_times_max + 2) * ((c) - 1)]
+/* findloc(tags(row, lo:hi), v, dim=1 [, back]) relative to lo (1-based), 0 if absent */
+static int64_t findloc_row(const orc_sim* S, int row, int64_t lo, int64_t hi, int32_t v, int back)
+{
+    if (!back) { for (int64_t c = lo; c <= hi; ++c) if (TAG(row, c) == v) return c - lo + 1; }
+    else { for (int64_t c = hi; c >= lo; --c) if (TAG(row, c) == v) return c - lo + 1; }
+    return 0;
+}
+
+static int is_particle_selected(const orc_sim* S, const gpat_particle* ptl, int64_t* iptl_lo,
+                                int64_t* iptl_hi)
+{
+    *iptl_lo = -1; *iptl_hi = -1;
+    int nsplit = ptl->split_times;
+    if (nsplit > S->split_times_max) return 0;
+    int64_t n = S->nptl_tracking;
+    int64_t i1 = findloc_row(S, 1, 1, n, ptl->origin, 0);
+    if (i1 <= 0) return 0;
+    int64_t i2 = findloc_row(S, 1, 1, n, ptl->origin, 1);
+    int64_t i3 = findloc_row(S, 2, i1, i2, abs(ptl->tag_injected), 0);
+    if (i3 <= 0) return 0;
+    int64_t i4 = findloc_row(S, 2, i1, i2, abs(ptl->tag_injected), 1);
+    i3 = i3 + i1 - 1;
+    i4 = i4 + i1 - 1;
+    if (nsplit > 0) {
+        int64_t i5 = findloc_row(S, nsplit + 2, i3, i4, abs(ptl->tag_splitted), 0);
+        if (i5 <= 0) return 0;
+        int64_t i6 = findloc_row(S, nsplit + 2, i3, i4, abs(ptl->tag_splitted), 1);
+        *iptl_lo = i5 + i3 - 1;
+        *iptl_hi = i6 + i3 - 1;
+    } else {
+        *iptl_lo = i3;
+        *iptl_hi = i4;
+    }
+    return 1;
+}
+
+/* particles_tracked(n, lo:hi) = ptl */
+static void record_tracked(orc_sim* S, const gpat_particle* ptl, int64_t lo, int64_t hi)
+{
+    int64_t n = ptl->nsteps_tracked;
+    if (n < 1 || n > S->nsteps_tracking_max) return; /* out of bounds in the reference */
+    for (int64_t c = lo; c <= hi; ++c)
+        S->particles_tracked[(n - 1) + (size_t)S->nsteps_tracking_max * (c - 1)] = *ptl;
+}
+
+/* the tracking block after every push, PM:1697-1703 / 1806-1812 */
+static void track_after_push(orc_sim* S, gpat_particle* ptl)
+{
+    if (S->track_particle_flag && ptl->tag_splitted < 0 && ptl->nsteps_pushed == 0) {
+        int64_t lo, hi;
+        is_particle_selected(S, ptl, &lo, &hi); /* locate_particle: same search, no checks */
+        ptl->nsteps_tracked = ptl->nsteps_tracked + 1;
+        if (lo > 0) record_tracked(S, ptl, lo, hi);
+    }
+}
+
 /* inject_one_particle, PM:385-441; `st` continues the particle's injection stream */
 static void inject_one_particle(orc_sim* S, inj_stream* st, double xpos, double ypos, double zpos,
                                 int dist_flag, double particle_v0, double mu, double t_frame,
@@ -1130,6 +1237,15 @@ static void inject_one_particle(orc_sim* S, inj_stream* st, double xpos, double 
     S->tag_max++;
     q->tag_splitted = 1;
     set_rng_step(q, 0);
+    if (S->track_particle_flag) { /* PM:434-440 */
+        int64_t lo, hi;
+        if (is_particle_selected(S, q, &lo, &hi)) {
+            q->nsteps_tracked = 1;
+            q->tag_injected = -q->tag_injected;
+            q->tag_splitted = -1;
+            record_tracked(S, q, lo, hi);
+        }
+    }
 }
 
 void orc_inject_uniform(orc_sim* S, int64_t nptl, double dt, int dist_flag, double particle_v0,
@@ -1309,9 +1425,30 @@ void orc_split(orc_sim* S, double split_ratio, double pmin_split, int nsteps_int
             S->nptl_split++;
             ptl.weight = (double)powf(0.5f, 1.0f + (float)ptl.split_times); /* PM:5449 */
             ptl.split_times = (int8_t)(ptl.split_times + 1);
-            S->ptls[S->nptl_current - 1] = ptl;
-            S->ptls[S->nptl_current - 1].tag_splitted =
-                ptl.tag_splitted + (1 << (ptl.split_times - 1)); /* PM:5475 */
+            gpat_particle* child = &S->ptls[S->nptl_current - 1];
+            *child = ptl;
+            if (ptl.tag_splitted < 0) { /* tracked particle, PM:5452-5473 */
+                int64_t lo, hi;
+                child->tag_splitted = ptl.tag_splitted - (1 << (ptl.split_times - 1));
+                if (is_particle_selected(S, child, &lo, &hi)) {
+                    if (ptl.nsteps_pushed == 0) {
+                        child->nsteps_tracked = child->nsteps_tracked + 1;
+                        record_tracked(S, child, lo, hi);
+                    }
+                } else {
+                    child->tag_splitted = -child->tag_splitted;
+                }
+                if (is_particle_selected(S, &ptl, &lo, &hi)) {
+                    if (ptl.nsteps_pushed == 0) {
+                        ptl.nsteps_tracked = ptl.nsteps_tracked + 1;
+                        record_tracked(S, &ptl, lo, hi);
+                    }
+                } else {
+                    ptl.tag_splitted = -ptl.tag_splitted; /* stop tracking */
+                }
+            } else {
+                child->tag_splitted = ptl.tag_splitted + (1 << (ptl.split_times - 1)); /* PM:5475 */
+            }
             S->ptls[i] = ptl;
         }
     }

@@ -154,6 +154,25 @@ class Oracle:
     def reset_escaped(self):
         self.lib.orc_reset_escaped(self.h)
 
+    # ---- particle tracking (PM:5825-5990) ----
+    def init_tracking(self, tags: np.ndarray, nsteps_interval: int):
+        tags = np.ascontiguousarray(tags, dtype=np.int32)  # (ntrack, ncols) C == (ncols, ntrack) Fortran
+        self._ntrack = tags.shape[0]
+        self.lib.orc_init_tracking(self.h, ptr(tags), C.c_int(tags.shape[1]), C.c_int64(tags.shape[0]),
+                                   C.c_int(nsteps_interval))
+
+    def download_tracked(self) -> np.ndarray:
+        """particles_tracked as (nptl_tracking, nsteps_tracking_max) records."""
+        nmax = C.c_int64(0)
+        self.lib.orc_get_tracked.restype = C.c_int64
+        n = self.lib.orc_get_tracked(self.h, None, C.byref(nmax))
+        out = np.zeros((n, nmax.value), dtype=PARTICLE_DTYPE)
+        self.lib.orc_get_tracked(self.h, ptr(out), C.byref(nmax))
+        return out
+
+    def reset_tracked(self):
+        self.lib.orc_reset_tracked(self.h)
+
     def counters(self) -> Counters:
         c = Counters()
         self.lib.orc_get_counters(self.h, C.byref(c))

@@ -114,6 +114,10 @@ struct gpat_sim {
     size_t stage2_bytes = 0;
     const float* pf_ptr = nullptr;  // host pointer of the frame in flight / landed in stage2
     int pf_nvar = 0;
+    // particle tracking (gpat_init_tracking)
+    TrackDev trk{};
+    int* d_tags = nullptr;
+    gpat_particle* d_tracked = nullptr;
     const void* registered_host[2] = {nullptr, nullptr};
     size_t registered_bytes[2] = {0, 0};
     // histograms
@@ -454,6 +458,7 @@ int run_push(gpat_sim* h, double t0, double dtf, int nsteps_interval, int num_fi
     a.rng_table = h->d_table;
     a.rng_slots = h->table_slots;
     a.rng_max_steps = h->table_steps;
+    a.trk = h->trk;
     CU(cudaMemsetAsync(h->d_queue, 0, 2 * sizeof(unsigned long long), h->st));
     CU(cudaEventRecord(h->ev[0], h->st));
     if (a.nptl > 0) {
@@ -574,6 +579,7 @@ int gpat_finalize(gpat_handle h)
         if (h->registered_host[i]) cudaHostUnregister(const_cast<void*>(h->registered_host[i]));
     void* ptrs[] = {h->ptl_mem, h->esc_mem, h->d_counters, h->d_nptl_split, h->d_leak, h->d_queue,
                     h->w.tile_counts, h->w.tile_offsets, h->idx_a, h->idx_b, h->fld, h->stage, h->stage2,
+                    h->d_tags, h->d_tracked,
                     h->d_fglobal, h->d_flocal[0], h->d_flocal[1], h->d_flocal[2], h->d_flocal[3],
                     h->d_fesc, h->d_pthr, h->d_sums, h->d_minmax, h->d_quick, h->d_table, h->d_aos};
     for (void* p : ptrs)
@@ -674,7 +680,8 @@ int gpat_inject_uniform(gpat_handle h, int64_t nptl, double dt, int dist_flag, d
     CU(cudaSetDevice(h->device));
     CU(cudaEventRecord(h->ev[2], h->st));
     launch_inject(h->dp, h->P, nptl, h->nptl_current, h->nptl_max, h->tag_max, dt, dist_flag,
-                  particle_v0, t_frame, dt_mhd, part_box, power_index, h->st);
+                  particle_v0, t_frame, dt_mhd, part_box, power_index, h->st, 0, 0.0, h->layout, h->fld, h->sel,
+                  nullptr, &h->trk);
     if (nptl > 0) h->tm.total_launches++;
     CU(cudaEventRecord(h->ev[3], h->st));
     CU(cudaGetLastError());
@@ -720,7 +727,8 @@ int gpat_inject_targeted(gpat_handle h, int mode, int64_t nptl, double dt, int d
         int* d_fail = reinterpret_cast<int*>(h->d_queue);
         CU(cudaMemsetAsync(d_fail, 0, sizeof(int), h->st));
         launch_inject(h->dp, h->P, ninj, h->nptl_current, h->nptl_max, h->tag_max, dt, dist_flag, particle_v0,
-                      t_frame, dt_mhd, part_box, power_index, h->st, mode, vmin, h->layout, h->fld, h->sel, d_fail);
+                      t_frame, dt_mhd, part_box, power_index, h->st, mode, vmin, h->layout, h->fld, h->sel, d_fail,
+                      &h->trk);
         h->tm.total_launches++;
         int failed = 0;
         CU(cudaEventRecord(h->ev[3], h->st));
@@ -735,6 +743,60 @@ int gpat_inject_targeted(gpat_handle h, int mode, int64_t nptl, double dt, int d
             return fail(h, GPAT_ERR_STATE, "gpat_inject_targeted: a rejection loop did not find an admissible "
                                            "position in 2^22 draws (the reference would spin forever)");
     }
+    return GPAT_OK;
+}
+
+int gpat_init_tracking(gpat_handle h, const int32_t* tags, int ncols, int64_t nptl_tracking, int nsteps_interval)
+{
+    if (!h || !tags || ncols < 2 || nptl_tracking < 1 || nsteps_interval < 1)
+        return fail(h, GPAT_ERR_INVALID, "gpat_init_tracking: bad arguments");
+    CU(cudaSetDevice(h->device));
+    if (h->d_tags) { cudaFree(h->d_tags); h->d_tags = nullptr; }
+    if (h->d_tracked) { cudaFree(h->d_tracked); h->d_tracked = nullptr; }
+    h->trk = TrackDev{};
+    // nsteps_tracking_max = ceiling((1.0 / dt_min_rel) / nsteps_interval) + 1, particle_module.f90:5876
+    const long long nmax = (long long)std::ceil((1.0 / h->hp.dt_min_rel) / nsteps_interval) + 1;
+    const size_t rec_bytes = (size_t)nmax * (size_t)nptl_tracking * sizeof(gpat_particle);
+    CU(cudaMalloc(&h->d_tags, (size_t)ncols * nptl_tracking * sizeof(int)));
+    cudaError_t e = cudaMalloc(&h->d_tracked, rec_bytes);
+    if (e != cudaSuccess)
+        return fail(h, GPAT_ERR_CUDA, "gpat_init_tracking: particles_tracked(" + std::to_string(nmax) + ", " +
+                                          std::to_string((long long)nptl_tracking) + ") does not fit: " +
+                                          cudaGetErrorString(e));
+    CU(cudaMemcpyAsync(h->d_tags, tags, (size_t)ncols * nptl_tracking * sizeof(int), cudaMemcpyHostToDevice, h->st));
+    CU(cudaMemsetAsync(h->d_tracked, 0, rec_bytes, h->st));  // reset_tracked_particles
+    CU(cudaStreamSynchronize(h->st));
+    h->trk.enabled = 1; h->trk.ncols = ncols; h->trk.ntrack = nptl_tracking; h->trk.nsteps_max = nmax;
+    h->trk.tags = h->d_tags; h->trk.rec = h->d_tracked;
+    return GPAT_OK;
+}
+
+int gpat_tracked_shape(gpat_handle h, int64_t* nsteps_tracking_max, int64_t* nptl_tracking)
+{
+    if (!h) return GPAT_ERR_INVALID;
+    if (nsteps_tracking_max) *nsteps_tracking_max = h->trk.enabled ? h->trk.nsteps_max : 0;
+    if (nptl_tracking) *nptl_tracking = h->trk.enabled ? h->trk.ntrack : 0;
+    return GPAT_OK;
+}
+
+int gpat_download_tracked(gpat_handle h, gpat_particle* out)
+{
+    if (!h || !out) return fail(h, GPAT_ERR_INVALID, "gpat_download_tracked: bad arguments");
+    if (!h->trk.enabled) return fail(h, GPAT_ERR_STATE, "gpat_download_tracked: gpat_init_tracking was not called");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(out, h->d_tracked, (size_t)h->trk.nsteps_max * h->trk.ntrack * sizeof(gpat_particle),
+                       cudaMemcpyDeviceToHost, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    return GPAT_OK;
+}
+
+int gpat_reset_tracked(gpat_handle h)
+{
+    if (!h) return GPAT_ERR_INVALID;
+    if (!h->trk.enabled) return GPAT_OK;
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemsetAsync(h->d_tracked, 0, (size_t)h->trk.nsteps_max * h->trk.ntrack * sizeof(gpat_particle), h->st));
+    CU(cudaStreamSynchronize(h->st));
     return GPAT_OK;
 }
 
@@ -803,7 +865,7 @@ int gpat_split(gpat_handle h, double split_ratio, double pmin_split, int nsteps_
     if (h->nptl_current > 0) {
         CU(cudaEventRecord(h->ev[2], h->st));
         launch_split(h->dp, h->P, h->nptl_current, h->nptl_max, split_ratio, pmin_split, h->d_counters,
-                     h->d_nptl_split, h->w, h->idx_a, h->st);
+                     h->d_nptl_split, h->w, h->idx_a, h->st, &h->trk);
         h->tm.total_launches += 5;
         CU(cudaEventRecord(h->ev[3], h->st));
         CU(cudaGetLastError());

@@ -115,6 +115,62 @@ struct DevParams {
     int mpi_rank;
 };
 
+// ---- particle tracking (particle_module.f90:144-150, 5825-5990) -----------------------------
+struct TrackDev {
+    int enabled;
+    int ncols;                 // split_times_max + 2
+    long long ntrack;          // nptl_tracking
+    long long nsteps_max;      // nsteps_tracking_max
+    const int* tags;           // tags_tracking(ncols, ntrack), column-major
+    gpat_particle* rec;        // particles_tracked(nsteps_max, ntrack), column-major
+};
+
+#ifdef __CUDACC__
+// findloc(tags(row, lo:hi), v, dim=1[, back]) relative to lo (1-based), 0 if absent
+__device__ __forceinline__ long long trk_findloc(const TrackDev& t, int row, long long lo, long long hi,
+                                                 int v, bool back)
+{
+    if (!back) { for (long long c = lo; c <= hi; ++c) if (t.tags[(row - 1) + (long long)t.ncols * (c - 1)] == v) return c - lo + 1; }
+    else { for (long long c = hi; c >= lo; --c) if (t.tags[(row - 1) + (long long)t.ncols * (c - 1)] == v) return c - lo + 1; }
+    return 0;
+}
+
+// is_particle_selected / locate_particle (particle_module.f90:5920-5990)
+__device__ __forceinline__ bool trk_selected(const TrackDev& t, int origin, int tag_inj, int tag_spl,
+                                             int nsplit, long long& lo, long long& hi)
+{
+    lo = hi = -1;
+    if (nsplit > t.ncols - 2) return false;
+    const long long i1 = trk_findloc(t, 1, 1, t.ntrack, origin, false);
+    if (i1 <= 0) return false;
+    const long long i2 = trk_findloc(t, 1, 1, t.ntrack, origin, true);
+    long long i3 = trk_findloc(t, 2, i1, i2, abs(tag_inj), false);
+    if (i3 <= 0) return false;
+    long long i4 = trk_findloc(t, 2, i1, i2, abs(tag_inj), true);
+    i3 += i1 - 1;
+    i4 += i1 - 1;
+    if (nsplit > 0) {
+        const long long i5 = trk_findloc(t, nsplit + 2, i3, i4, abs(tag_spl), false);
+        if (i5 <= 0) return false;
+        const long long i6 = trk_findloc(t, nsplit + 2, i3, i4, abs(tag_spl), true);
+        lo = i5 + i3 - 1;
+        hi = i6 + i3 - 1;
+    } else {
+        lo = i3;
+        hi = i4;
+    }
+    return true;
+}
+
+// particles_tracked(n, lo:hi) = ptl
+__device__ __forceinline__ void trk_record(const TrackDev& t, const gpat_particle& q, long long lo, long long hi)
+{
+    const long long n = q.nsteps_tracked;
+    if (n < 1 || n > t.nsteps_max || lo < 1) return;
+    for (long long c = lo; c <= hi; ++c) t.rec[(n - 1) + t.nsteps_max * (c - 1)] = q;
+}
+#endif
+
 struct PushArgs {
     double t0, dtf, dt_fine, dt_min, dt_max;
     double idtf;             // 1/dtf
@@ -129,6 +185,7 @@ struct PushArgs {
     double* leak;                // [0] leak, [1] leak_negp
     const double* rng_table;
     long long rng_slots, rng_max_steps;
+    TrackDev trk;                // particle tracking (enabled = 0: the production kernels)
 };
 
 // ---- stream-compaction scratch (particles.cu) ---------------------------------------------
@@ -174,7 +231,8 @@ void launch_inject(const DevParams& prm, const PtlSoA& P, long long n, long long
                    long long nptl_max, long long tag0, double dt, int dist_flag, double particle_v0,
                    double t_frame, double dt_mhd, const double box[6], double power_index,
                    cudaStream_t st, int mode = 0, double vmin = 0.0, int layout = 0,
-                   const float* fld = nullptr, int sel = 0, int* fail = nullptr);
+                   const float* fld = nullptr, int sel = 0, int* fail = nullptr,
+                   const TrackDev* trk = nullptr);
 void launch_ncells(const DevParams& prm, int layout, const float* fld, int sel, int mode, double vmin,
                    const double box[6], unsigned long long* d_count, int sm_count, cudaStream_t st);
 void launch_remove(const PtlSoA& P, const PtlSoA& E, long long ecap, long long n, long long* counters,
@@ -184,7 +242,7 @@ void launch_final_bc(const DevParams& prm, const PtlSoA& P, long long nmax, cons
                      double* leak, cudaStream_t st);
 void launch_split(const DevParams& prm, const PtlSoA& P, long long n, long long nptl_max,
                   double split_ratio, double pmin_split, long long* counters, long long* nptl_split,
-                  const ScanWork& w, long long* idx_a, cudaStream_t st);
+                  const ScanWork& w, long long* idx_a, cudaStream_t st, const TrackDev* trk = nullptr);
 void launch_to_aos(const PtlSoA& P, gpat_particle* out, long long n, cudaStream_t st);
 void launch_from_aos(const PtlSoA& P, const gpat_particle* in, long long n, cudaStream_t st);
 void launch_diag(const PtlSoA& P, const DiagArgs& a, int sm_count, cudaStream_t st);

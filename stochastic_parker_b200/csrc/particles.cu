@@ -31,6 +31,20 @@ __device__ __forceinline__ uint4 philox_inj(uint4 c, unsigned k0, unsigned k1)
     return c;
 }
 
+// SoA slot -> the reference's particle_type record (for particles_tracked)
+__device__ __forceinline__ gpat_particle soa_record(const PtlSoA& P, long long i)
+{
+    gpat_particle q;
+    q.split_times = P.split_times[i]; q.count_flag = P.count_flag[i]; q.pad_[0] = q.pad_[1] = 0;
+    q.origin = P.origin[i]; q.nsteps_tracked = P.nsteps_tracked[i];
+    q.nsteps_pushed = P.nsteps_pushed[i]; q.tag_injected = P.tag_injected[i];
+    q.tag_splitted = P.tag_splitted[i];
+    q.x = P.x[i]; q.y = P.y[i]; q.z = P.z[i]; q.p = P.p[i]; q.v = P.v[i]; q.mu = P.mu[i];
+    q.weight = P.weight[i]; q.t = P.t[i]; q.dt = P.dt[i];
+    q.padding = __longlong_as_double((long long)P.rng[i]);
+    return q;
+}
+
 struct InjStream {  // word k of ctr = (k/4, 0, tag_injected, 0)
     unsigned tag, k0, k1, k;
     uint4 buf;
@@ -56,6 +70,7 @@ struct InjectArgs {
     int nrec, half;      // floats per record half-pair / which half is farray1
     int pos[10];         // packed position of dbx_dy dbx_dz dby_dx dby_dz dbz_dx dbz_dy dvx_dx dvy_dy dvz_dz rho (-1: absent = 0)
     int* fail;           // set when a rejection loop hits kMaxTrials
+    TrackDev trk;        // particle tracking (particle_module.f90:434-440)
 };
 
 constexpr int kMaxTrials = 1 << 22;  // the reference's loop is unbounded; a kernel must end
@@ -204,6 +219,15 @@ __global__ void inject_kernel(const __grid_constant__ DevParams prm, const PtlSo
     P.nsteps_pushed[slot] = 0;
     P.tag_injected[slot] = (int)(a.tag0 + i);
     P.tag_splitted[slot] = 1;
+    if (a.trk.enabled) {  // particle_module.f90:434-440
+        long long lo, hi;
+        if (trk_selected(a.trk, prm.mpi_rank, (int)(a.tag0 + i), 1, 0, lo, hi)) {
+            P.nsteps_tracked[slot] = 1;
+            P.tag_injected[slot] = -(int)(a.tag0 + i);
+            P.tag_splitted[slot] = -1;
+            trk_record(a.trk, soa_record(P, slot), lo, hi);
+        }
+    }
 }
 
 // ---- get_ncells_large_jz/_absj/_divv/_rho (mhd_data_parallel.f90:2211-2498) ---------------------
@@ -293,10 +317,12 @@ void launch_ncells(const DevParams& prm, int layout, const float* fld, int sel, 
 void launch_inject(const DevParams& prm, const PtlSoA& P, long long n, long long start,
                    long long nptl_max, long long tag0, double dt, int dist_flag, double particle_v0,
                    double t_frame, double dt_mhd, const double box[6], double power_index,
-                   cudaStream_t st, int mode, double vmin, int layout, const float* fld, int sel, int* fail)
+                   cudaStream_t st, int mode, double vmin, int layout, const float* fld, int sel, int* fail,
+                   const TrackDev* trk)
 {
     if (n <= 0) return;
     InjectArgs a{};
+    if (trk) a.trk = *trk;
     if (mode != 0) fill_target(a, prm, layout, fld, sel, mode, vmin, box, fail);
     a.n = n; a.start = start; a.nptl_max = nptl_max; a.tag0 = tag0; a.dt = dt;
     a.particle_v0 = particle_v0; a.t_frame = t_frame; a.dt_mhd = dt_mhd;
@@ -538,7 +564,7 @@ void launch_final_bc(const DevParams& prm, const PtlSoA& P, long long nmax, cons
 
 // ---- split_particle ----------------------------------------------------------------------
 __global__ void split_apply_kernel(PtlSoA P, const long long* idx, long long* counters, long long n,
-                                   long long nptl_max)
+                                   long long nptl_max, TrackDev trk)
 {
     long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     long long total = counters[6];
@@ -553,7 +579,35 @@ __global__ void split_apply_kernel(PtlSoA P, const long long* idx, long long* co
     P.weight[i] = wgt;
     P.split_times[i] = (signed char)(st + 1);
     copy_particle(P, child, P, i);
-    P.tag_splitted[child] = P.tag_splitted[i] + (1 << st);  // 2**(split_times_new - 1)
+    const int tag = P.tag_splitted[i];
+    if (tag >= 0) {
+        P.tag_splitted[child] = tag + (1 << st);  // 2**(split_times_new - 1)
+        return;
+    }
+    // a tracked particle splits (particle_module.f90:5452-5473): whichever branch is still an
+    // ancestor of a selected particle keeps its negative tag (and is sampled if it sits on a
+    // sampling step); the other one stops being tracked.
+    const int origin = P.origin[i], tinj = P.tag_injected[i], ns = st + 1;
+    const bool sample = (P.nsteps_pushed[i] == 0);
+    long long lo, hi;
+    const int ctag = tag - (1 << st);
+    P.tag_splitted[child] = ctag;
+    if (trk.enabled && trk_selected(trk, origin, tinj, ctag, ns, lo, hi)) {
+        if (sample) {
+            P.nsteps_tracked[child] = P.nsteps_tracked[child] + 1;
+            trk_record(trk, soa_record(P, child), lo, hi);
+        }
+    } else {
+        P.tag_splitted[child] = -ctag;
+    }
+    if (trk.enabled && trk_selected(trk, origin, tinj, tag, ns, lo, hi)) {
+        if (sample) {
+            P.nsteps_tracked[i] = P.nsteps_tracked[i] + 1;
+            trk_record(trk, soa_record(P, i), lo, hi);
+        }
+    } else {
+        P.tag_splitted[i] = -tag;  // stop tracking
+    }
 }
 
 __global__ void after_split_kernel(long long* c, long long n, long long nptl_max, long long* nptl_split)
@@ -568,12 +622,13 @@ __global__ void after_split_kernel(long long* c, long long n, long long nptl_max
 
 void launch_split(const DevParams& prm, const PtlSoA& P, long long n, long long nptl_max,
                   double split_ratio, double pmin_split, long long* counters, long long* nptl_split,
-                  const ScanWork& w, long long* idx_a, cudaStream_t st)
+                  const ScanWork& w, long long* idx_a, cudaStream_t st, const TrackDev* trk)
 {
     if (n <= 0) return;
     PredArgs a{P.count_flag, P.split_times, P.p, counters + 2, pmin_split * prm.p0, split_ratio, prm.pmax};
     select_indices<PRED_SPLIT>(a, n, w, idx_a, counters + 6, st);
-    split_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, idx_a, counters, n, nptl_max);
+    split_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, idx_a, counters, n, nptl_max,
+                                                                      trk ? *trk : TrackDev{});
     after_split_kernel<<<1, 1, 0, st>>>(counters, n, nptl_max, nptl_split);
 }
 

@@ -67,6 +67,7 @@ struct Lane {
     int tag_inj, tag_spl, origin;
     int nsteps_pushed;
     int count_flag;
+    int nsteps_tracked;  // used by the tracking instantiations only
 };
 
 // particle_boundary_condition for a single rank (neighbours are self or -1)
@@ -465,10 +466,13 @@ __device__ __forceinline__ void push_1d(const DevParams& prm, const PushArgs& a,
 #endif
 
 // One call of push_particle_*: everything between the BC test and the step counter.
-template <int L>
+template <int L, bool TRACK = false>
 __device__ __forceinline__ void push_once(const DevParams& prm, const PushArgs& a,
                                           const float* __restrict__ fld, Lane& q, bool fixed_dt)
 {
+    // tracked particles carry negated tags; the streams are keyed by the magnitudes so that a
+    // tracking run replays the run its particles were selected from
+    const int tag_inj = TRACK ? abs(q.tag_inj) : q.tag_inj, tag_spl = TRACK ? abs(q.tag_spl) : q.tag_spl;
     constexpr bool D3 = (Rec<L>::NDIM == 3);
     constexpr bool EXT = Rec<L>::EXT;
     double F[Rec<L>::NREC];
@@ -478,7 +482,7 @@ __device__ __forceinline__ void push_once(const DevParams& prm, const PushArgs& 
     // uniforms of this step: ran1, ran2, ran3, ran_p
     double u0, u1, u2, u3;
     if (prm.rng_mode == GPAT_RNG_TABLE) {
-        long long slot = q.tag_inj;
+        long long slot = tag_inj;
         if (a.rng_table && slot >= 0 && slot < a.rng_slots && (long long)q.rng < a.rng_max_steps) {
             const double* tb = a.rng_table + ((size_t)slot * a.rng_max_steps + q.rng) * 4;
             u0 = tb[0]; u1 = tb[1]; u2 = tb[2]; u3 = tb[3];
@@ -487,7 +491,7 @@ __device__ __forceinline__ void push_once(const DevParams& prm, const PushArgs& 
         }
     } else {
         uint4 r = philox4x32_10(make_uint4((unsigned)q.rng, (unsigned)(q.rng >> 32),
-                                           (unsigned)q.tag_inj, (unsigned)q.tag_spl),
+                                           (unsigned)tag_inj, (unsigned)tag_spl),
                                 prm.key0, prm.key1 + (unsigned)q.origin);
         u0 = u01(r.x); u1 = u01(r.y); u2 = u01(r.z); u3 = u01(r.w);
     }
@@ -664,6 +668,7 @@ enum : int { AT_OUTER_HEAD = 0, AT_INNER_HEAD = 1, AFTER_FIXED_PUSH = 2 };
 //        then dt = dt_old; BC                             <- AFTER_FIXED_PUSH
 //     dt_target += dt_fine
 // Returns ST_IDLE when the particle is done for this interval.
+template <bool TRACK = false>
 __device__ __forceinline__ int next_state(const DevParams& prm, const PushArgs& a, Lane& q,
                                           int entry)
 {
@@ -678,7 +683,12 @@ __device__ __forceinline__ int next_state(const DevParams& prm, const PushArgs& 
                 q.dt_old = q.dt;
                 q.dt = a.t0 + q.dt_target - q.t;
                 if (q.dt > 0) {
-                    q.nsteps_pushed = q.nsteps_pushed - 1;  // particle_module.f90:1723
+                    if (TRACK && q.tag_spl < 0 && q.nsteps_pushed == 0) {  // particle_module.f90:1717-1721
+                        q.nsteps_tracked = q.nsteps_tracked - 1;             // back one sample
+                        q.nsteps_pushed = a.nsteps_interval - 2;
+                    } else {
+                        q.nsteps_pushed = q.nsteps_pushed - 1;  // particle_module.f90:1723
+                    }
                     return ST_FIX;
                 }
                 q.dt = q.dt_old;  // particle_module.f90:1816-1825
@@ -698,9 +708,11 @@ __device__ __forceinline__ int next_state(const DevParams& prm, const PushArgs& 
 
 // particle record -> lane registers, and the initial state of its loop nest
 // (particle_module.f90:1561-1592)
+template <bool TRACK = false>
 __device__ __forceinline__ int load_lane(const DevParams& prm, const PushArgs& a, const PtlSoA& P,
                                          long long idx, Lane& q, int& remaining)
 {
+    q.nsteps_tracked = 1;  // reset at the start of the MHD interval, particle_module.f90:1910-1913
     q.x = P.x[idx]; q.y = P.y[idx]; q.z = P.z[idx]; q.p = P.p[idx];
     q.t = P.t[idx]; q.dt = P.dt[idx]; q.weight = P.weight[idx]; q.mu = P.mu[idx];
     q.rng = P.rng[idx]; q.tag_inj = P.tag_injected[idx];
@@ -724,7 +736,7 @@ __device__ __forceinline__ int load_lane(const DevParams& prm, const PushArgs& a
     } else {
         boundary(prm, q, prm.ext, a.leak);
     }
-    return (q.count_flag == GPAT_COUNT_FLAG_INBOX) ? next_state(prm, a, q, AT_OUTER_HEAD) : ST_IDLE;
+    return (q.count_flag == GPAT_COUNT_FLAG_INBOX) ? next_state<TRACK>(prm, a, q, AT_OUTER_HEAD) : ST_IDLE;
 }
 
 __device__ __forceinline__ void store_lane(const PushArgs& a, const PtlSoA& P, long long idx,
@@ -734,10 +746,12 @@ __device__ __forceinline__ void store_lane(const PushArgs& a, const PtlSoA& P, l
     P.t[idx] = q.t; P.dt[idx] = q.dt; P.rng[idx] = q.rng;
     P.nsteps_pushed[idx] = q.nsteps_pushed;
     P.count_flag[idx] = (signed char)q.count_flag;
-    if (a.debug_nsteps == 0) P.nsteps_tracked[idx] = 1;  // particle_module.f90:1913
+    // particle_module.f90:1913 sets 1 at the start of the interval; tracked particles count up from it
+    if (a.debug_nsteps == 0) P.nsteps_tracked[idx] = q.nsteps_tracked;
 }
 
 // idle lanes take the next particles of the work counter (one warp-aggregated atomic)
+template <bool TRACK = false>
 __device__ __forceinline__ void refill(const DevParams& prm, const PushArgs& a, const PtlSoA& P,
                                        unsigned lane, Lane& q, int& state, long long& idx,
                                        bool& exhausted, int& remaining)
@@ -755,15 +769,35 @@ __device__ __forceinline__ void refill(const DevParams& prm, const PushArgs& a, 
         if (idx >= a.nptl) {
             exhausted = true;
         } else {
-            state = load_lane(prm, a, P, idx, q, remaining);
+            state = load_lane<TRACK>(prm, a, P, idx, q, remaining);
             if (state == ST_IDLE) store_lane(a, P, idx, q);
         }
     }
 }
 
 // after one push_particle_* call: step counter, next state (particle_module.f90:1694-1704)
+// the tracking block after every push (particle_module.f90:1697-1703, 1806-1812): a tracked
+// particle (negative tag_splitted) is sampled every nsteps_interval pushes into the rows of all
+// the selected particles it is an ancestor of
+__device__ __noinline__ void track_sample(const PushArgs& a, const PtlSoA& P, long long idx, Lane& q)
+{
+    long long lo, hi;
+    const int nsplit = P.split_times[idx];
+    trk_selected(a.trk, q.origin, q.tag_inj, q.tag_spl, nsplit, lo, hi);  // locate_particle
+    q.nsteps_tracked = q.nsteps_tracked + 1;
+    gpat_particle r;
+    r.split_times = (int8_t)nsplit; r.count_flag = (int8_t)q.count_flag; r.pad_[0] = r.pad_[1] = 0;
+    r.origin = q.origin; r.nsteps_tracked = q.nsteps_tracked; r.nsteps_pushed = q.nsteps_pushed;
+    r.tag_injected = q.tag_inj; r.tag_splitted = q.tag_spl;
+    r.x = q.x; r.y = q.y; r.z = q.z; r.p = q.p; r.v = P.v[idx]; r.mu = q.mu;
+    r.weight = q.weight; r.t = q.t; r.dt = q.dt;
+    r.padding = __longlong_as_double((long long)q.rng);
+    trk_record(a.trk, r, lo, hi);
+}
+
+template <bool TRACK = false>
 __device__ __forceinline__ int after_push(const DevParams& prm, const PushArgs& a, Lane& q, int state,
-                                          int& remaining)
+                                          int& remaining, const PtlSoA& P, long long idx)
 {
     // mod(nsteps_pushed + 1, nsteps_interval), particle_module.f90:1694; the counter is already
     // inside [0, interval) except right after a restart with a smaller interval
@@ -771,11 +805,12 @@ __device__ __forceinline__ int after_push(const DevParams& prm, const PushArgs& 
         const int n1 = q.nsteps_pushed + 1;
         q.nsteps_pushed = (n1 < a.nsteps_interval) ? n1 : (n1 == a.nsteps_interval ? 0 : n1 % a.nsteps_interval);
     }
+    if (TRACK && q.tag_spl < 0 && q.nsteps_pushed == 0) track_sample(a, P, idx, q);
     if (a.debug_nsteps > 0) return (--remaining == 0) ? ST_IDLE : ST_ADAPT;
-    return next_state(prm, a, q, state == ST_FIX ? AFTER_FIXED_PUSH : AT_INNER_HEAD);
+    return next_state<TRACK>(prm, a, q, state == ST_FIX ? AFTER_FIXED_PUSH : AT_INNER_HEAD);
 }
 
-template <int L>
+template <int L, bool TRACK = false>
 __global__ void __launch_bounds__(kBlock)
 push_kernel(const __grid_constant__ DevParams prm, const PtlSoA P, const float* __restrict__ fld,
             const __grid_constant__ PushArgs a)
@@ -789,7 +824,7 @@ push_kernel(const __grid_constant__ DevParams prm, const PtlSoA P, const float* 
     unsigned long long nsteps = 0;
 
     for (;;) {
-        refill(prm, a, P, lane, q, state, idx, exhausted, remaining);
+        refill<TRACK>(prm, a, P, lane, q, state, idx, exhausted, remaining);
         if (__all_sync(0xffffffffu, state == ST_IDLE)) {
             if (__all_sync(0xffffffffu, exhausted)) break;
             continue;
@@ -805,12 +840,12 @@ push_kernel(const __grid_constant__ DevParams prm, const PtlSoA P, const float* 
         }
         if (state != ST_IDLE) {
 #if GPAT_STRICT
-            push_once<L>(prm, a, fld, q, state == ST_FIX);
+            push_once<L, TRACK>(prm, a, fld, q, state == ST_FIX);
 #else
-            push_once_fast<L>(prm, a, fld, q, state == ST_FIX);
+            push_once_fast<L, TRACK>(prm, a, fld, q, state == ST_FIX);
 #endif
             nsteps++;
-            state = after_push(prm, a, q, state, remaining);
+            state = after_push<TRACK>(prm, a, q, state, remaining, P, idx);
             if (state == ST_IDLE) store_lane(a, P, idx, q);
         }
     }
@@ -895,7 +930,7 @@ template <int L> struct MinBlocks { static constexpr int V = (L == L2B || L == L
 // the two frames must enter every sum in the order (farray1, farray2) whatever half they live in:
 // a run restarted from a dump starts with sel = 0 again and has to continue bit-identically
 // (tests/test_gpu_parity.py::test_restart_round_trip_is_bit_exact).
-template <int L, int SEL>
+template <int L, int SEL, bool TRACK = false>
 __global__ void __launch_bounds__(kBlock, MinBlocks<L>::V)
 push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                  const float* __restrict__ fld, const __grid_constant__ PushArgs a)
@@ -920,7 +955,7 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
     unsigned long long nsteps = 0;
 
     for (;;) {
-        refill(prm, a, P, lane, q, state, idx, exhausted, remaining);
+        refill<TRACK>(prm, a, P, lane, q, state, idx, exhausted, remaining);
         if (__all_sync(0xffffffffu, state == ST_IDLE)) {
             if (__all_sync(0xffffffffu, exhausted)) break;
             continue;
@@ -1041,9 +1076,9 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                 F[2 * k] = v.x;
                 F[2 * k + 1] = v.y;
             }
-            physics_fast<L>(prm, a, F, q, state == ST_FIX);
+            physics_fast<L, double[C::NREC], TRACK>(prm, a, F, q, state == ST_FIX);
             nsteps++;
-            state = after_push(prm, a, q, state, remaining);
+            state = after_push<TRACK>(prm, a, q, state, remaining, P, idx);
             if (state == ST_IDLE) store_lane(a, P, idx, q);
         }
     }
@@ -1091,12 +1126,19 @@ void launch_one(const DevParams& prm, const PtlSoA& P, const float* fld, const P
         if (per_sm < 1) per_sm = 1;
         grid = (long long)sm_count * per_sm;
         if (want < grid) grid = want > 0 ? want : 1;
-        if (a.sel == 0) push_kernel_coop<L, 0><<<(unsigned)grid, kBlock, pad, st>>>(prm, P, fld, a);
-        else push_kernel_coop<L, 1><<<(unsigned)grid, kBlock, pad, st>>>(prm, P, fld, a);
+        // tracking runs use their own instantiations: the production kernels carry no tracking code
+        if (a.trk.enabled) {
+            if (a.sel == 0) push_kernel_coop<L, 0, true><<<(unsigned)grid, kBlock, pad, st>>>(prm, P, fld, a);
+            else push_kernel_coop<L, 1, true><<<(unsigned)grid, kBlock, pad, st>>>(prm, P, fld, a);
+        } else {
+            if (a.sel == 0) push_kernel_coop<L, 0><<<(unsigned)grid, kBlock, pad, st>>>(prm, P, fld, a);
+            else push_kernel_coop<L, 1><<<(unsigned)grid, kBlock, pad, st>>>(prm, P, fld, a);
+        }
         return;
     }
 #endif
-    push_kernel<L><<<(unsigned)grid, kBlock, 0, st>>>(prm, P, fld, a);
+    if (a.trk.enabled) push_kernel<L, true><<<(unsigned)grid, kBlock, 0, st>>>(prm, P, fld, a);
+    else push_kernel<L><<<(unsigned)grid, kBlock, 0, st>>>(prm, P, fld, a);
 }
 
 }  // namespace

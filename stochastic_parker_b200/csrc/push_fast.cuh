@@ -18,10 +18,12 @@
 
 // F: the interpolated record of this particle (registers, or a shared-memory row written by
 // the lane group that gathered it)
-template <int L, typename FT>
+template <int L, typename FT, bool TRACK = false>
 __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArgs& a,
                                              const FT& F, Lane& q, bool fixed_dt)
 {
+    // tracked particles carry negated tags; the random streams are keyed by the magnitudes
+    const int tag_inj = TRACK ? abs(q.tag_inj) : q.tag_inj, tag_spl = TRACK ? abs(q.tag_spl) : q.tag_spl;
     constexpr bool D3 = (Rec<L>::NDIM == 3);
     constexpr bool EXT = Rec<L>::EXT;
 
@@ -31,7 +33,7 @@ __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArg
         const double sqrt3 = 1.7320508075688772;
         if (prm.rng_mode == GPAT_RNG_TABLE) {
             double u0 = 0.5, u1 = 0.5, u2 = 0.5, u3 = 0.5;
-            long long slot = q.tag_inj;
+            long long slot = tag_inj;
             if (a.rng_table && slot >= 0 && slot < a.rng_slots && (long long)q.rng < a.rng_max_steps) {
                 const double* tb = a.rng_table + ((size_t)slot * a.rng_max_steps + q.rng) * 4;
                 u0 = tb[0]; u1 = tb[1]; u2 = tb[2]; u3 = tb[3];
@@ -40,7 +42,7 @@ __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArg
             ran3 = (2.0 * u2 - 1.0) * sqrt3; ranp = (2.0 * u3 - 1.0) * sqrt3;
         } else {
             uint4 r = philox4x32_10(make_uint4((unsigned)q.rng, (unsigned)(q.rng >> 32),
-                                               (unsigned)q.tag_inj, (unsigned)q.tag_spl),
+                                               (unsigned)tag_inj, (unsigned)tag_spl),
                                     prm.key0, prm.key1 + (unsigned)q.origin);
             const double c = 2.0 * sqrt3 / 4294967295.0;
             // u32 -> f64 through the 2^52 exponent trick (an FP64 add, not a conversion-unit op)
@@ -279,12 +281,12 @@ __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArg
     q.dpl = ddp;
 }
 
-template <int L>
+template <int L, bool TRACK = false>
 __device__ __forceinline__ void push_once_fast(const DevParams& prm, const PushArgs& a,
                                                const float* __restrict__ fld, Lane& q, bool fixed_dt)
 {
     double F[Rec<L>::NREC];
     const double rt = (q.t - a.t0) * a.idtf;
     gather<L>(prm, fld, a.sel, q.x, q.y, q.z, rt, F);
-    physics_fast<L>(prm, a, F, q, fixed_dt);
+    physics_fast<L, double[Rec<L>::NREC], TRACK>(prm, a, F, q, fixed_dt);
 }

@@ -120,6 +120,25 @@ class GpatSim:
                  "gpat_inject_targeted")
         return ninj.value, ncells.value
 
+    # ---- particle tracking ----------------------------------------------------
+    def init_tracking(self, tags: np.ndarray, nsteps_interval: int):
+        """init_particle_tracking (particle_module.f90:5825-5879); tags: (nptl_tracking, split_times_max+2)
+        int32 rows as written by tracking.select_tags (== the Fortran (ncols, nptl) array)."""
+        tags = np.ascontiguousarray(tags, dtype=np.int32)
+        self._ck(self.lib.gpat_init_tracking(self.h, ptr(tags), tags.shape[1], tags.shape[0], nsteps_interval),
+                 "gpat_init_tracking")
+
+    def download_tracked(self) -> np.ndarray:
+        """particles_tracked as (nptl_tracking, nsteps_tracking_max) records."""
+        nmax, ntrk = C.c_int64(0), C.c_int64(0)
+        self._ck(self.lib.gpat_tracked_shape(self.h, C.byref(nmax), C.byref(ntrk)), "gpat_tracked_shape")
+        out = np.zeros((ntrk.value, nmax.value), dtype=PARTICLE_DTYPE)
+        self._ck(self.lib.gpat_download_tracked(self.h, ptr(out)), "gpat_download_tracked")
+        return out
+
+    def reset_tracked(self):
+        self._ck(self.lib.gpat_reset_tracked(self.h), "gpat_reset_tracked")
+
     def particle_mover(self, t0, dtf, nsteps_interval=100, num_fine_steps=1, dump_escaped_dist=0) -> int:
         steps = C.c_uint64(0)
         self._ck(self.lib.gpat_particle_mover(self.h, t0, dtf, nsteps_interval, num_fine_steps,
@@ -234,7 +253,8 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
                   part_box=None, inject_new_ptl=True, tmax_to_inject=1 << 30, split_flag=1,
                   split_ratio=2.0, pmin_split=2.0, nsteps_interval=100, num_fine_steps=1,
                   local_dist=True, dump_escaped_dist=False, dt_inject=0.0, on_interval=None,
-                  inject_mode=0, inject_same_nptl=True, inject_min=0.0, ncells_norm=1):
+                  inject_mode=0, inject_same_nptl=True, inject_min=0.0, ncells_norm=1,
+                  track_tags=None, on_tracked=None):
     """solve_transport_equation (stochastic-mhd.f90:312-567) for one rank.
 
     `sim` is a GpatSim (or the test oracle, which has the same methods); `frames` is a
@@ -244,6 +264,9 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
     """
     get = frames if callable(frames) else (lambda i: frames[i])
     P = sim.P
+    track = track_tags is not None
+    if track:                                                  # :226-229 init_particle_tracking
+        sim.init_tracking(track_tags, nsteps_interval)
     if part_box is None:  # stochastic-mhd.f90:384-390
         part_box = [P.xmin, P.ymin, P.zmin, P.xmax, P.ymax, P.zmax]
     nframes = len(tstamps)
@@ -261,14 +284,26 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
                                     power_index, inject_same_nptl, inject_min, ncells_norm)
             else:
                 sim.inject_uniform(nptl, dt_inject, dist_flag, particle_v0, t0, dtf, part_box, power_index)
-        if tf == 1:                                            # :488-494
+        if tf == 1 and not track:                              # :488-494
             d0 = sim.diagnostics(local_dist)
             d0["frame"] = 0
             records.append(d0)
-        steps = sim.particle_mover(t0, dtf, nsteps_interval, num_fine_steps, int(dump_escaped_dist))  # :502
+        # a tracking run moves the particles with num_fine_steps = 1 (:497-503)
+        steps = sim.particle_mover(t0, dtf, nsteps_interval, 1 if track else num_fine_steps,
+                                   int(dump_escaped_dist))
         total_steps += steps
+        if track:                                              # :509-511 dump_tracked_particles
+            if on_tracked is not None:
+                on_tracked(tf, sim.download_tracked())
+            sim.reset_tracked()
         if split_flag == 1:
             sim.split(split_ratio, pmin_split, nsteps_interval)  # :515
+        if track:                                              # no distributions in a tracking run (:516)
+            d = dict(frame=tf, steps=steps)
+            records.append(d)
+            if P.time_interp:
+                sim.swap_fields()
+            continue
         d = sim.diagnostics(local_dist)                        # :518-521
         d["frame"] = tf
         d["steps"] = steps

@@ -429,3 +429,55 @@ def test_targeted_injection_counts_and_accepts_like_the_reference(mode):
     assert np.all(got >= vmin)                            # the loop runs while crit < vmin
     # the accepted positions favour the cells above the threshold: not uniform in the box
     assert (ptl["t"] >= 0.0).all() and (ptl["t"] <= 0.1).all() and np.all(ptl["weight"] == 1.0)
+
+
+# ---- particle tracking (particle_module.f90:5825-5990, hooks at :434-440, 1697-1724, 5452-5473) ---
+def _tracking_pair(sim_cls, nptl=600, nsel=25, strict=None):
+    """First run -> tag table of the highest-energy particles -> tracking run (same seed)."""
+    from stochastic_parker_b200.tracking import select_tags
+    # dt_min_rel sizes particles_tracked: nsteps_tracking_max = ceiling(1/dt_min_rel/nsteps_interval) + 1
+    w, P, frames, ts = make_case("c1", grid=48, nptl=nptl, nframes=4, conf=dict(dt_min_rel=1e-4))
+    if strict is not None:
+        P.strict_math = strict
+    kw = dict(nptl=nptl, dist_flag=2, particle_v0=w.particle_v0, inject_new_ptl=False, split_flag=1,
+              pmin_split=1.02, split_ratio=1.02, nsteps_interval=50)
+    a = sim_cls(P, 8 * nptl)
+    run_intervals(a, frames, ts, **kw)
+    first = a.download_particles()
+    assert first["split_times"].max() >= 2
+    sel = np.argsort(first["p"])[-nsel:]
+    tags = select_tags(first, sel)
+    frames_rec = []
+    b = sim_cls(P, 8 * nptl)
+    run_intervals(b, frames, ts, track_tags=tags, on_tracked=lambda tf, rec: frames_rec.append(rec.copy()), **kw)
+    return first, sel, tags, b.download_particles(), frames_rec
+
+
+def test_tracking_replays_and_records_the_selected_particles():
+    first, sel, tags, second, recs = _tracking_pair(Oracle)
+    assert tags.shape[0] == 25 and tags.shape[1] == first["split_times"][sel].max() + 2
+    # the tracking run moves with num_fine_steps = 1 like the first one and keys Philox by |tag|:
+    # every particle of the first run exists again, same trajectory, with negated tags if tracked
+    key = lambda q: (q["origin"], np.abs(q["tag_injected"]), np.abs(q["tag_splitted"]))
+    oa, ob = np.lexsort(key(first)[::-1]), np.lexsort(key(second)[::-1])
+    fa, fb = first[oa], second[ob]
+    assert len(fa) == len(fb)
+    for f in ("x", "y", "p", "t", "weight"):
+        assert np.array_equal(fa[f], fb[f]), f
+    tracked_now = fb["tag_splitted"] < 0
+    want = np.zeros(len(fa), dtype=bool)
+    want[np.isin(np.arange(len(first)), sel)[oa]] = True
+    assert np.array_equal(tracked_now, want)          # exactly the selected leaves are still tagged
+    # records: one array per MHD interval, (nptl_tracking, nsteps_tracking_max)
+    assert len(recs) == 3 and recs[0].shape[0] == 25
+    for rec in recs:
+        for row in rec:
+            used = row["tag_splitted"] < 0
+            t = row["t"][used]
+            assert np.all(np.diff(t) > 0)             # a trajectory: time increases along the row
+            assert np.all(row["nsteps_pushed"][used] == 0)   # sampled every nsteps_interval pushes
+    # the last sample of every tracked row belongs to the selected particle's ancestry
+    last = recs[-1]
+    assert np.count_nonzero((last["tag_splitted"] < 0).any(axis=1)) == 25
+    assert np.all(np.abs(last["tag_injected"][last["tag_splitted"] < 0]) ==
+                  np.repeat(tags[:, 1], (last["tag_splitted"] < 0).sum(axis=1)))
