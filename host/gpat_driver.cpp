@@ -210,7 +210,7 @@ int main(int argc, char** argv)
         return 2;
     }
     // features outside the GPU path must stay off; the library re-checks the ones it is told about
-    for (const char* k : {"-is", "-ib", "-tf", "-rf", "-vdt"})
+    for (const char* k : {"-is", "-ib", "-rf", "-vdt"})
         if (cli.b(k)) {
             std::fprintf(stderr, "gpat_driver: switch %s is outside the GPU particle path\n", k);
             return 2;
@@ -360,6 +360,39 @@ int main(int argc, char** argv)
         return 0;
     };
 
+    // ---- particle tracking (stochastic-mhd.f90:226-229): the tag table is the reference's HDF5
+    // dataset "tags" (nptl_tracking x (split_times_max+2) int32, C order) as a raw file
+    // [int32 nptl_tracking, int32 ncols, data...] -- no HDF5 in this image
+    const bool track = cli.b("-tf");
+    if (track) {
+        FILE* f = std::fopen(cli.s("-ptf").c_str(), "rb");
+        int32_t hdr[2] = {0, 0};
+        if (!f || std::fread(hdr, sizeof(int32_t), 2, f) != 2 || hdr[0] < 1 || hdr[1] < 2)
+            return die(h, "read particle_tags_file header", -1);
+        std::vector<int32_t> tags((size_t)hdr[0] * hdr[1]);
+        if (std::fread(tags.data(), sizeof(int32_t), tags.size(), f) != tags.size())
+            return die(h, "read particle_tags_file", -1);
+        std::fclose(f);
+        CK(gpat_init_tracking(h, tags.data(), hdr[1], hdr[0], nsteps_interval), "gpat_init_tracking");
+    }
+    auto dump_tracked = [&](int iframe) -> int {  // dump_tracked_particles, particle_module.f90:6236-6299
+        int64_t nmax = 0, ntrk = 0;
+        int rc = gpat_tracked_shape(h, &nmax, &ntrk);
+        if (rc) return rc;
+        std::vector<gpat_particle> rec((size_t)nmax * ntrk);
+        rc = gpat_download_tracked(h, rec.data());
+        if (rc) return rc;
+        char name[96];
+        std::snprintf(name, sizeof(name), "particle_tracking_particles_tracked_%04d.bin", iframe);
+        FILE* f = std::fopen((diag_dir + name).c_str(), "wb");
+        if (!f) return -1;
+        const int64_t hdr[2] = {ntrk, nmax};
+        std::fwrite(hdr, sizeof(int64_t), 2, f);
+        std::fwrite(rec.data(), sizeof(gpat_particle), rec.size(), f);
+        std::fclose(f);
+        return gpat_reset_tracked(h);
+    };
+
     // ---- solve_transport_equation (stochastic-mhd.f90:312-567) ----
     if (!read_frame(dir_mhd, t_start, ncell * 8, frame)) return die(h, "read first mhd_data frame", -1);
     CK(gpat_upload_fields(h, 0, frame.data(), 8, 0), "gpat_upload_fields");
@@ -391,16 +424,20 @@ int main(int argc, char** argv)
                    "gpat_inject_uniform");
             }
         }
-        if (tf == t_start + 1) CK(diagnostics(t_start, true), "initial diagnostics");  // :488-494
+        if (tf == t_start + 1 && !track) CK(diagnostics(t_start, true), "initial diagnostics");  // :488-494
         uint64_t steps = 0;
-        CK(gpat_particle_mover(h, t0, dtf, nsteps_interval, num_fine_steps, dump_escaped_dist ? 1 : 0, &steps),
-           "gpat_particle_mover");  // :502
+        CK(gpat_particle_mover(h, t0, dtf, nsteps_interval, track ? 1 : num_fine_steps, dump_escaped_dist ? 1 : 0,
+                               &steps),
+           "gpat_particle_mover");  // :497-503: a tracking run moves with num_fine_steps = 1
         total_steps += steps;
         std::printf(" Finishing moving particles \n");
+        if (track) CK(dump_tracked(tf), "dump_tracked_particles");  // :509-511
         if (split_flag == 1) CK(gpat_split(h, cli.d("-sr"), cli.d("-ps"), nsteps_interval), "gpat_split");  // :515
-        CK(diagnostics(tf, false), "diagnostics");  // :518-521
-        std::printf(" Finishing distribution diagnostics \n");
-        if (dump_escaped_dist) CK(gpat_reset_escaped(h), "gpat_reset_escaped");  // :533
+        if (!track) {  // :516-535
+            CK(diagnostics(tf, false), "diagnostics");  // :518-521
+            std::printf(" Finishing distribution diagnostics \n");
+            if (dump_escaped_dist) CK(gpat_reset_escaped(h), "gpat_reset_escaped");  // :533
+        }
         if (P.time_interp == 1) {
             CK(gpat_swap_fields(h), "gpat_swap_fields");  // :538
             std::printf(" Finishing copying fields \n");
