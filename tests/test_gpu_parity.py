@@ -640,3 +640,41 @@ def test_tracking_run_replays_and_matches_the_oracle(strict):
             used = row["tag_splitted"] < 0
             assert np.all(np.diff(row["t"][used]) > 0)
             assert np.all(row["nsteps_pushed"][used] == 0)
+
+
+def test_spectra_agree_within_poisson_error_for_independent_streams():
+    """north_star's second bar: with on-device Philox, spectra and spatial distributions agree with
+    the reference path within Poisson statistical error.  The production build runs with one seed,
+    the oracle with another (independent streams, nothing shared but the physics); unit weights
+    (no splitting) make every bin count a Poisson variate, so chi^2/dof of the difference ~ 1."""
+    w, P, frames, ts = make_case("c1", grid=64, nptl=30000, nframes=3)
+    kw = dict(nptl=30000, dist_flag=0, particle_v0=w.particle_v0, inject_new_ptl=False, split_flag=0)
+    Pg = P.copy()
+    Pg.strict_math = 0
+    Pg.seed = 0x1234ABCD
+    g = GpatSim(Pg, w.nptl_max)
+    rg, _ = run_intervals(g, frames, ts, **kw)
+    g.close()
+    Po = P.copy()
+    Po.seed = 0x0BADC0DE
+    o = Oracle(Po, w.nptl_max)
+    ro, _ = run_intervals(o, frames, ts, **kw)
+
+    def chi2(a, b, min_count=25):
+        a, b = np.asarray(a, dtype=np.float64).ravel(), np.asarray(b, dtype=np.float64).ravel()
+        m = (a + b) >= 2 * min_count
+        return float(np.sum((a[m] - b[m]) ** 2 / (a[m] + b[m]))), int(m.sum())
+
+    # momentum spectrum after two intervals
+    c, dof = chi2(rg[-1]["fglobal"], ro[-1]["fglobal"])
+    assert dof >= 10
+    assert c / dof < 1.0 + 4.0 * np.sqrt(2.0 / dof), (c, dof)      # 4 sigma of a chi^2 with dof bins
+    # spatial distribution: local set 1 summed over momentum, rebinned to 8 x 8
+    # flocal1 arrives as (nrz, nry, nrx, npbins, nmu): sum the last two axes -> the spatial map
+    sa = np.asarray(rg[-1]["flocal"][0]).sum(axis=(-1, -2))
+    sb = np.asarray(ro[-1]["flocal"][0]).sum(axis=(-1, -2))
+    c, dof = chi2(sa, sb)
+    assert dof >= 20
+    assert c / dof < 1.0 + 4.0 * np.sqrt(2.0 / dof), (c, dof)
+    # and the totals: weight is conserved on both sides
+    assert abs(rg[-1]["quick"][2] - ro[-1]["quick"][2]) <= 5.0 * np.sqrt(rg[-1]["quick"][2] + 1)
