@@ -82,6 +82,7 @@ struct gpat_sim {
     cudaStream_t st = nullptr;
     int layout = L2B;
     int sel = 0;
+    int push_generic = 0;  // GPAT_PUSH_GENERIC=1: A/B switch for the specialised kernel
     int push_variant = 1;  // production kernel: lane-group gather (GPAT_PUSH_VARIANT=0: one lane per particle)
     bool have_field[2] = {false, false};
     long long nptl_max = 0;
@@ -451,6 +452,7 @@ int run_push(gpat_sim* h, double t0, double dtf, int nsteps_interval, int num_fi
     a.debug_nsteps = debug_nsteps;
     a.sel = h->sel;
     a.variant = h->push_variant;
+    a.generic = h->push_generic;
     a.nptl = h->nptl_current;
     a.queue = h->d_queue;
     a.steps = h->d_queue + 1;
@@ -521,6 +523,7 @@ int gpat_init(gpat_handle* out, int device, int64_t nptl_max, const gpat_params*
     h->nptl_max = nptl_max;
     h->layout = pick_layout(h->hp);
     if (const char* v = getenv("GPAT_PUSH_VARIANT")) h->push_variant = atoi(v);
+    if (const char* v = getenv("GPAT_PUSH_GENERIC")) h->push_generic = atoi(v);
     fill_dev_params(h);
     CUI(cudaMalloc(&h->ptl_mem, soa_bytes(nptl_max)));
     CUI(cudaMemsetAsync(h->ptl_mem, 0, soa_bytes(nptl_max), h->st));  // init_particles zero fill

@@ -179,6 +179,7 @@ struct PushArgs {
     int debug_nsteps;        // >0: gpat_debug_push_n mode
     int sel;                 // which half of a record pair holds farray1
     int variant;             // fast build: 0 = one lane gathers its own particle, 1 = lane groups
+    int generic;             // 1: never pick the switch-specialised instantiation (GPAT_PUSH_GENERIC=1)
     long long nptl;
     unsigned long long* queue;   // work counter
     unsigned long long* steps;   // push_particle_* calls

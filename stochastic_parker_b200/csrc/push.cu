@@ -103,13 +103,16 @@ __device__ __forceinline__ void boundary(const DevParams& prm, Lane& q, const do
 }
 
 // true when negp_or_bc() would change anything
+// MAYZ = false: the layout rules out a resolved z axis (base 2-D record: ndim = 2 and no
+// include_3rd_dim, which needs the extended record), so the z test is not even compiled
+template <bool MAYZ = true>
 __device__ __forceinline__ bool outside_or_negp(const DevParams& prm, const Lane& q)
 {
     bool o = (q.p < 0.0) | (q.x < prm.ext[0]) | (q.x > prm.ext[1]) | (q.y < prm.ext[2]) | (q.y > prm.ext[3]);
 #if GPAT_STRICT
     if (prm.ndim == 1) o = (q.p < 0.0) | (q.x < prm.ext[0]) | (q.x > prm.ext[1]);
 #endif
-    if (prm.ndim == 3 || prm.include_3rd_dim) o = o | (q.z < prm.ext[4]) | (q.z > prm.ext[5]);
+    if (MAYZ && (prm.ndim == 3 || prm.include_3rd_dim)) o = o | (q.z < prm.ext[4]) | (q.z > prm.ext[5]);
     return o;
 }
 
@@ -795,7 +798,7 @@ __device__ __noinline__ void track_sample(const PushArgs& a, const PtlSoA& P, lo
     trk_record(a.trk, r, lo, hi);
 }
 
-template <bool TRACK = false>
+template <bool TRACK = false, bool SPEC = false>
 __device__ __forceinline__ int after_push(const DevParams& prm, const PushArgs& a, Lane& q, int state,
                                           int& remaining, const PtlSoA& P, long long idx)
 {
@@ -806,7 +809,7 @@ __device__ __forceinline__ int after_push(const DevParams& prm, const PushArgs& 
         q.nsteps_pushed = (n1 < a.nsteps_interval) ? n1 : (n1 == a.nsteps_interval ? 0 : n1 % a.nsteps_interval);
     }
     if (TRACK && q.tag_spl < 0 && q.nsteps_pushed == 0) track_sample(a, P, idx, q);
-    if (a.debug_nsteps > 0) return (--remaining == 0) ? ST_IDLE : ST_ADAPT;
+    if (!SPEC && a.debug_nsteps > 0) return (--remaining == 0) ? ST_IDLE : ST_ADAPT;  // SPEC: never the debug mode
     return next_state<TRACK>(prm, a, q, state == ST_FIX ? AFTER_FIXED_PUSH : AT_INNER_HEAD);
 }
 
@@ -914,8 +917,18 @@ template <int L> struct Coop {
 #endif
     static constexpr int CPL = NCH / G;                           // chunks per lane
     static constexpr int NC = (Rec<L>::NDIM == 3) ? 8 : 4;
-    static constexpr int ROW = NREC + 2;                          // doubles per result row (+16 B: bank skew)
-    static constexpr int PAR = 6;                                 // doubles per parameter row (48 B)
+    // result rows (G = 4): NREC doubles + 32 B.  Rows of ODD lane groups start 16 B later (row_off), so that
+    // the two groups of a quarter-warp store phase hit disjoint banks, and 8 consecutive owner
+    // rows (160 B apart in 2-D) still tile the 32 banks on the read side
+    // (profiles/r01e_push_coop_ncu.txt: 3.2e9 shared-memory bank conflicts before this).
+    static constexpr bool SKEW = (G == 4);                        // G = 2 rows (NREC = 24) are conflict-free at +16 B
+    static constexpr int ROW = SKEW ? NREC + 4 : NREC + 2;
+    // parameter rows.  2-D: the owner publishes its eight finished corner weights (time blend and
+    // conversion scale folded in) + the cell, 80 B; the other lanes of the group load them instead
+    // of recomputing 16 products per round.  3-D: rx ry t0 t1 cell rz, 48 B, weights per round.
+    static constexpr bool PUBW = (NC == 4);
+    static constexpr int PAR = PUBW ? 10 : 6;
+    __device__ static __forceinline__ int row_off(int owner) { return owner * ROW + (SKEW ? ((owner / G) & 1) * 2 : 0); }
 };
 
 // resident CTAs per SM the register allocation must allow: the kernel is latency-bound, and
@@ -930,7 +943,7 @@ template <int L> struct MinBlocks { static constexpr int V = (L == L2B || L == L
 // the two frames must enter every sum in the order (farray1, farray2) whatever half they live in:
 // a run restarted from a dump starts with sel = 0 again and has to continue bit-identically
 // (tests/test_gpu_parity.py::test_restart_round_trip_is_bit_exact).
-template <int L, int SEL, bool TRACK = false>
+template <int L, int SEL, bool TRACK = false, bool SPEC = false>
 __global__ void __launch_bounds__(kBlock, MinBlocks<L>::V)
 push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                  const float* __restrict__ fld, const __grid_constant__ PushArgs a)
@@ -962,7 +975,7 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
         }
         // top of the inner while body, particle_module.f90:1602-1612.  One combined test keeps the
         // common case (inside the extended box, p >= 0) to a single untaken branch.
-        if (state == ST_ADAPT && outside_or_negp(prm, q)) {
+        if (state == ST_ADAPT && outside_or_negp<(Rec<L>::NDIM == 3) || Rec<L>::EXT>(prm, q)) {
             negp_or_bc(prm, q, a.leak);
             if (q.count_flag != GPAT_COUNT_FLAG_INBOX) {
                 store_lane(a, P, idx, q);
@@ -978,14 +991,26 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
             if (state != ST_IDLE) {
                 cell = locate<Rec<L>::NDIM>(prm, q.x, q.y, q.z, rx, ry, rz);
                 const double rt = (q.t - a.t0) * a.idtf;
-                const double tA = prm.time_interp ? 1.0 - rt : 1.0, tB = prm.time_interp ? rt : 0.0;
+                const bool ti = SPEC || prm.time_interp;  // SPEC: time interpolation on
+                const double tA = ti ? 1.0 - rt : 1.0, tB = ti ? rt : 0.0;
                 t0 = (SEL == 0) ? tA : tB;
                 t1 = (SEL == 0) ? tB : tA;
             }
             double2* row = reinterpret_cast<double2*>(par + lane * C::PAR);
-            row[0] = make_double2(rx, ry);
-            row[1] = make_double2(t0, t1);
-            row[2] = make_double2(__longlong_as_double(cell), rz);
+            if constexpr (C::PUBW) {
+                const double rx1 = 1.0 - rx, ry1 = 1.0 - ry;
+                const double a0 = ry1 * t0 * cvt_weight_scale(0, 0), b0 = ry * t0 * cvt_weight_scale(1, 0);
+                const double a1 = ry1 * t1 * cvt_weight_scale(0, 1), b1 = ry * t1 * cvt_weight_scale(1, 1);
+                row[0] = make_double2(rx1 * a0, rx * a0);  // w0[0..3]: half 0 at the four corners
+                row[1] = make_double2(rx1 * b0, rx * b0);
+                row[2] = make_double2(rx1 * a1, rx * a1);  // w1[0..3]: half 1
+                row[3] = make_double2(rx1 * b1, rx * b1);
+                row[4] = make_double2(__longlong_as_double(cell), 0.0);
+            } else {
+                row[0] = make_double2(rx, ry);
+                row[1] = make_double2(t0, t1);
+                row[2] = make_double2(__longlong_as_double(cell), rz);
+            }
         }
         __syncwarp();
 
@@ -996,7 +1021,7 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
             constexpr int DEPTH = (GPAT_COOP_DEPTH < C::G) ? GPAT_COOP_DEPTH : C::G;
             float4 lo[DEPTH][NLD], hi[DEPTH][NLD];
             auto issue = [&](int r, int slot) {
-                const long long cell = __double_as_longlong(par[(gbase + r) * C::PAR + 4]);
+                const long long cell = __double_as_longlong(par[(gbase + r) * C::PAR + (C::PUBW ? 8 : 4)]);
                 const float* base = fld + cell * stride + (gq * C::CPL) * 8;
 #pragma unroll
                 for (int c = 0; c < C::NC; ++c) {
@@ -1014,18 +1039,17 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                 const int owner = gbase + r;
                 const int slot = r % DEPTH;
                 const double2* row = reinterpret_cast<const double2*>(par + owner * C::PAR);
-                const double2 pa = row[0], pb = row[1];
-                const double rx = pa.x, ry = pa.y, t0 = pb.x, t1 = pb.y;
                 // weights of half 0 / half 1 at each corner (time blend folded in)
                 double w0[C::NC], w1[C::NC];
-                {
+                if constexpr (C::PUBW) {
+                    const double2 q0 = row[0], q1 = row[1], q2 = row[2], q3 = row[3];
+                    w0[0] = q0.x; w0[1] = q0.y; w0[2] = q1.x; w0[3] = q1.y;
+                    w1[0] = q2.x; w1[1] = q2.y; w1[2] = q3.x; w1[3] = q3.y;
+                } else {
+                    const double2 pa = row[0], pb = row[1];
+                    const double rx = pa.x, ry = pa.y, t0 = pb.x, t1 = pb.y;
                     const double rx1 = 1.0 - rx, ry1 = 1.0 - ry;
-                    if (C::NC == 4) {
-                        const double a0 = ry1 * t0 * cvt_weight_scale(0, 0), b0 = ry * t0 * cvt_weight_scale(1, 0);
-                        const double a1 = ry1 * t1 * cvt_weight_scale(0, 1), b1 = ry * t1 * cvt_weight_scale(1, 1);
-                        w0[0] = rx1 * a0; w0[1] = rx * a0; w0[2] = rx1 * b0; w0[3] = rx * b0;
-                        w1[0] = rx1 * a1; w1[1] = rx * a1; w1[2] = rx1 * b1; w1[3] = rx * b1;
-                    } else {
+                    {
                         const double rz = par[owner * C::PAR + 5];
                         const double rz1 = 1.0 - rz;
                         const double wxy[4] = {rx1 * ry1, rx * ry1, rx1 * ry, rx * ry};
@@ -1056,7 +1080,7 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                     }
                 }
                 if (r + DEPTH < C::G) issue(r + DEPTH, slot);
-                double2* out = reinterpret_cast<double2*>(res + owner * C::ROW + (gq * C::CPL) * 4);
+                double2* out = reinterpret_cast<double2*>(res + C::row_off(owner) + (gq * C::CPL) * 4);
 #pragma unroll
                 for (int j = 0; j < C::CPL; ++j) {
                     out[2 * j] = make_double2(acc[j][0], acc[j][1]);
@@ -1069,16 +1093,16 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
         // ---- phase C: the owner lane finishes its push ----
         if (state != ST_IDLE) {
             double F[C::NREC];
-            const double2* row = reinterpret_cast<const double2*>(res + lane * C::ROW);
+            const double2* row = reinterpret_cast<const double2*>(res + C::row_off((int)lane));
 #pragma unroll
             for (int k = 0; k < C::NREC / 2; ++k) {
                 const double2 v = row[k];
                 F[2 * k] = v.x;
                 F[2 * k + 1] = v.y;
             }
-            physics_fast<L, double[C::NREC], TRACK>(prm, a, F, q, state == ST_FIX);
+            physics_fast<L, double[C::NREC], TRACK, SPEC>(prm, a, F, q, state == ST_FIX);
             nsteps++;
-            state = after_push<TRACK>(prm, a, q, state, remaining, P, idx);
+            state = after_push<TRACK, SPEC>(prm, a, q, state, remaining, P, idx);
             if (state == ST_IDLE) store_lane(a, P, idx, q);
         }
     }
@@ -1127,6 +1151,22 @@ void launch_one(const DevParams& prm, const PtlSoA& P, const float* fld, const P
         grid = (long long)sm_count * per_sm;
         if (want < grid) grid = want > 0 ? want : 1;
         // tracking runs use their own instantiations: the production kernels carry no tracking code
+        // the common switch set of the named 2-D configs gets its own instantiation (physics_fast)
+        const bool common = (L == L2B) && a.debug_nsteps == 0 && prm.mag_dependency == 1 &&
+                            prm.momentum_dependency == 1 && !prm.nlgc && prm.rng_mode != GPAT_RNG_TABLE &&
+                            !prm.check_drift_2d && prm.acc_region_flag != 1 && prm.time_interp && !a.generic;
+        if constexpr (L == L2B) {
+            if (common && !a.trk.enabled) {
+                if (a.sel == 0) push_kernel_coop<L, 0, false, true><<<(unsigned)grid, kBlock, pad, st>>>(prm, P, fld, a);
+                else push_kernel_coop<L, 1, false, true><<<(unsigned)grid, kBlock, pad, st>>>(prm, P, fld, a);
+                return;
+            }
+            if (common) {  // a tracking run must replay the run it was selected from: same arithmetic
+                if (a.sel == 0) push_kernel_coop<L, 0, true, true><<<(unsigned)grid, kBlock, pad, st>>>(prm, P, fld, a);
+                else push_kernel_coop<L, 1, true, true><<<(unsigned)grid, kBlock, pad, st>>>(prm, P, fld, a);
+                return;
+            }
+        }
         if (a.trk.enabled) {
             if (a.sel == 0) push_kernel_coop<L, 0, true><<<(unsigned)grid, kBlock, pad, st>>>(prm, P, fld, a);
             else push_kernel_coop<L, 1, true><<<(unsigned)grid, kBlock, pad, st>>>(prm, P, fld, a);

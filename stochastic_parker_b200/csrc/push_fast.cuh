@@ -18,10 +18,20 @@
 
 // F: the interpolated record of this particle (registers, or a shared-memory row written by
 // the lane group that gathered it)
-template <int L, typename FT, bool TRACK = false>
+// SPEC = true: the run's switches are the common case of the named configs -- mag_dependency = 1,
+// momentum_dependency = 1, no NLGC, on-device Philox, no out-of-plane drift check, no acceleration
+// region (launch_one checks this) -- and are compile-time constants here: ~15 uniform branches and
+// their flag loads disappear and the log/exp/rsqrt chains share one basic block.
+template <int L, typename FT, bool TRACK = false, bool SPEC = false>
 __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArgs& a,
                                              const FT& F, Lane& q, bool fixed_dt)
 {
+    const bool f_mag = SPEC || prm.mag_dependency == 1;
+    const bool f_mom = SPEC || prm.momentum_dependency == 1;
+    const bool f_nlgc = !SPEC && prm.nlgc;
+    const bool f_table = !SPEC && prm.rng_mode == GPAT_RNG_TABLE;
+    const bool f_drift2d = !SPEC && prm.check_drift_2d;
+    const bool f_acc = !SPEC && prm.acc_region_flag == 1;
     // tracked particles carry negated tags; the random streams are keyed by the magnitudes
     const int tag_inj = TRACK ? abs(q.tag_inj) : q.tag_inj, tag_spl = TRACK ? abs(q.tag_spl) : q.tag_spl;
     constexpr bool D3 = (Rec<L>::NDIM == 3);
@@ -31,7 +41,7 @@ __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArg
     double ran1, ran2, ran3, ranp;
     {
         const double sqrt3 = 1.7320508075688772;
-        if (prm.rng_mode == GPAT_RNG_TABLE) {
+        if (f_table) {
             double u0 = 0.5, u1 = 0.5, u2 = 0.5, u3 = 0.5;
             long long slot = tag_inj;
             if (a.rng_table && slot >= 0 && slot < a.rng_slots && (long long)q.rng < a.rng_max_steps) {
@@ -99,23 +109,23 @@ __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArg
 
     // ---- kappa_para, kappa_perp (particle_module.f90:2239-2269 / 2497-2533) ----
     // log|B| = log(b2)/2; a vanishing field only has to stay finite here
-    const double lb = prm.mag_dependency == 1 ? 0.5 * fm::log_pos(fmax(b2, 1e-300)) : 0.0;
+    const double lb = f_mag ? 0.5 * fm::log_pos(fmax(b2, 1e-300)) : 0.0;
     const double lpr = fm::log_pos(q.p * prm.ip0);
     double knp = 1.0, kpara, rk, srk, s1mrk;  // rk = kperp/kpara and its square roots
-    if (EXT || prm.nlgc) {
-        if (prm.mag_dependency == 1) knp = fm::exp_mid(prm.gm2 * lb);
-        const double pp = prm.momentum_dependency == 1 ? fm::exp_mid(prm.pindex * lpr) : 1.0;
+    if (EXT || f_nlgc) {
+        if (f_mag) knp = fm::exp_mid(prm.gm2 * lb);
+        const double pp = f_mom ? fm::exp_mid(prm.pindex * lpr) : 1.0;
         kpara = prm.kpara0 * knp * pp;
     } else {
-        const double e = (prm.mag_dependency == 1 ? prm.gm2 * lb : 0.0) +
-                         (prm.momentum_dependency == 1 ? prm.pindex * lpr : 0.0);
+        const double e = (f_mag ? prm.gm2 * lb : 0.0) +
+                         (f_mom ? prm.pindex * lpr : 0.0);
         kpara = prm.kpara0 * fm::exp_mid(e);
     }
-    if (!prm.nlgc) {
+    if (!f_nlgc) {
         rk = prm.kret; srk = prm.sqrt_kret; s1mrk = prm.sqrt_1mkret;
     } else {
-        const double e = (prm.mag_dependency == 1 ? prm.gm2_3 * lb : 0.0) +
-                         (prm.momentum_dependency == 1 ? prm.pidx_perp * lpr : 0.0);
+        const double e = (f_mag ? prm.gm2_3 * lb : 0.0) +
+                         (f_mom ? prm.pidx_perp * lpr : 0.0);
         const double kperp = prm.kpara0 * prm.kperp_kpara * fm::exp_mid(e) * q.mu * q.mu;
         rk = kperp * fm::rcp(kpara);
         srk = fm::sqrt_pos(rk);
@@ -128,12 +138,12 @@ __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArg
     double ax, ay, az = 0.0, ex, ey, ez = 0.0;  // kpp-like and kperp-like d(kappa)/dx_i factors
     {
         double gx = 0.0, gy = 0.0, gz = 0.0;
-        if (prm.mag_dependency == 1) {
+        if (f_mag) {
             // 3-D non-NLGC omits 1/B (particle_module.f90:2405-2409)
-            const double s = (D3 && !prm.nlgc) ? prm.gm2 : prm.gm2 * ibk;
+            const double s = (D3 && !f_nlgc) ? prm.gm2 : prm.gm2 * ibk;
             gx = db_dx * s; gy = db_dy * s; gz = db_dz * s;
         }
-        if (!prm.nlgc) {
+        if (!f_nlgc) {
             ex = kperp * gx; ey = kperp * gy; ez = kperp * gz;
             ax = kpp * gx; ay = kpp * gy; az = kpp * gz;
         } else {
@@ -156,7 +166,7 @@ __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArg
     if (!third) {
         const double vdx = vdp * (dbz_dy * ib2 - 2.0 * bz * db_dy * ib3);
         const double vdy = vdp * (-dbz_dx * ib2 + 2.0 * bz * db_dx * ib3);
-        dz_dt = prm.check_drift_2d
+        dz_dt = f_drift2d
                     ? vdp * ((dby_dx - dbx_dy) * ib2 - 2.0 * (by * db_dx - bx * db_dy) * ib3)
                     : 0.0;
         dx_dt = vx + vdx + dkxx_dx + dkxy_dy;
@@ -187,7 +197,7 @@ __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArg
     if constexpr (EXT) {
         if (prm.dpp_wave) {
             const double pv = q.p * b2 * fm::rcp(rho * kpara);  // p va^2 / kpara
-            dp_dt += (prm.momentum_dependency == 1 ? 8.0 / 27.0 : 4.0 / 9.0) * pv;
+            dp_dt += (f_mom ? 8.0 / 27.0 : 4.0 / 9.0) * pv;
             dpp += q.p * pv * (1.0 / 9.0);
         }
         if (prm.dpp_shear) {
@@ -267,7 +277,7 @@ __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArg
 
     double ddp = dp_dt * q.dt;
     if constexpr (EXT) ddp = fma(ranp, fm::sqrt_pos(2.0 * dpp * q.dt), ddp);
-    if (prm.acc_region_flag == 1) {
+    if (f_acc) {
         if (in_acc_region(prm, q)) q.p += ddp;
         else ddp = 0.0;
     } else {
