@@ -18,6 +18,7 @@
 //   GPAT_STRICT=1, -fmad=false : reference operation order, no contraction (parity build)
 //   GPAT_STRICT=0              : FMA contraction, time-blend folded into the weights
 #include <cstdlib>
+#include <type_traits>
 
 #include "gpat_internal.cuh"
 #include "fastmath.cuh"
@@ -798,7 +799,7 @@ __device__ __noinline__ void track_sample(const PushArgs& a, const PtlSoA& P, lo
     trk_record(a.trk, r, lo, hi);
 }
 
-template <bool TRACK = false, bool SPEC = false>
+template <bool TRACK = false, int SPEC = 0>
 __device__ __forceinline__ int after_push(const DevParams& prm, const PushArgs& a, Lane& q, int state,
                                           int& remaining, const PtlSoA& P, long long idx)
 {
@@ -943,7 +944,7 @@ template <int L> struct MinBlocks { static constexpr int V = (L == L2B || L == L
 // the two frames must enter every sum in the order (farray1, farray2) whatever half they live in:
 // a run restarted from a dump starts with sel = 0 again and has to continue bit-identically
 // (tests/test_gpu_parity.py::test_restart_round_trip_is_bit_exact).
-template <int L, int SEL, bool TRACK = false, bool SPEC = false>
+template <int L, int SEL, bool TRACK = false, int SPEC = 0>
 __global__ void __launch_bounds__(kBlock, MinBlocks<L>::V)
 push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                  const float* __restrict__ fld, const __grid_constant__ PushArgs a)
@@ -1151,29 +1152,37 @@ void launch_one(const DevParams& prm, const PtlSoA& P, const float* fld, const P
         grid = (long long)sm_count * per_sm;
         if (want < grid) grid = want > 0 ? want : 1;
         // tracking runs use their own instantiations: the production kernels carry no tracking code
-        // the common switch set of the named 2-D configs gets its own instantiation (physics_fast)
-        const bool common = (L == L2B) && a.debug_nsteps == 0 && prm.mag_dependency == 1 &&
-                            prm.momentum_dependency == 1 && !prm.nlgc && prm.rng_mode != GPAT_RNG_TABLE &&
-                            !prm.check_drift_2d && prm.acc_region_flag != 1 && prm.time_interp && !a.generic;
-        if constexpr (L == L2B) {
-            if (common && !a.trk.enabled) {
-                if (a.sel == 0) push_kernel_coop<L, 0, false, true><<<(unsigned)grid, kBlock, pad, st>>>(prm, P, fld, a);
-                else push_kernel_coop<L, 1, false, true><<<(unsigned)grid, kBlock, pad, st>>>(prm, P, fld, a);
-                return;
-            }
-            if (common) {  // a tracking run must replay the run it was selected from: same arithmetic
-                if (a.sel == 0) push_kernel_coop<L, 0, true, true><<<(unsigned)grid, kBlock, pad, st>>>(prm, P, fld, a);
-                else push_kernel_coop<L, 1, true, true><<<(unsigned)grid, kBlock, pad, st>>>(prm, P, fld, a);
-                return;
-            }
+        // switch-specialised instantiations (physics_fast): every layout for mag = mom = 1, plus the
+        // two other combinations the named configs use (C3: mag 0 on the base 2-D record, C5: mom 0
+        // on the base 3-D record).  Tracking runs pick the same SPEC so that they replay the run
+        // their particles were selected from with identical arithmetic.
+        int spec = 0;
+        if (a.debug_nsteps == 0 && !prm.nlgc && prm.rng_mode != GPAT_RNG_TABLE && !prm.check_drift_2d &&
+            prm.acc_region_flag != 1 && prm.time_interp && !a.generic) {
+            const int want = 1 | (prm.mag_dependency == 1 ? 2 : 0) | (prm.momentum_dependency == 1 ? 4 : 0);
+            if (want == kSpec11 || (L == L2B && want == kSpec01) || (L == L3B && want == kSpec10)) spec = want;
         }
-        if (a.trk.enabled) {
-            if (a.sel == 0) push_kernel_coop<L, 0, true><<<(unsigned)grid, kBlock, pad, st>>>(prm, P, fld, a);
-            else push_kernel_coop<L, 1, true><<<(unsigned)grid, kBlock, pad, st>>>(prm, P, fld, a);
-        } else {
-            if (a.sel == 0) push_kernel_coop<L, 0><<<(unsigned)grid, kBlock, pad, st>>>(prm, P, fld, a);
-            else push_kernel_coop<L, 1><<<(unsigned)grid, kBlock, pad, st>>>(prm, P, fld, a);
-        }
+        auto go = [&](auto sel_c, auto trk_c, auto spec_c) {
+            push_kernel_coop<L, decltype(sel_c)::value, decltype(trk_c)::value, decltype(spec_c)::value>
+                <<<(unsigned)grid, kBlock, pad, st>>>(prm, P, fld, a);
+        };
+        auto by_spec = [&](auto sel_c, auto trk_c) {
+            using I = std::integral_constant<int, 0>;
+            if (spec == kSpec11) go(sel_c, trk_c, std::integral_constant<int, kSpec11>{});
+            else if constexpr (L == L2B) {
+                if (spec == kSpec01) go(sel_c, trk_c, std::integral_constant<int, kSpec01>{});
+                else go(sel_c, trk_c, I{});
+            } else if constexpr (L == L3B) {
+                if (spec == kSpec10) go(sel_c, trk_c, std::integral_constant<int, kSpec10>{});
+                else go(sel_c, trk_c, I{});
+            } else go(sel_c, trk_c, I{});
+        };
+        auto by_trk = [&](auto sel_c) {
+            if (a.trk.enabled) by_spec(sel_c, std::true_type{});
+            else by_spec(sel_c, std::false_type{});
+        };
+        if (a.sel == 0) by_trk(std::integral_constant<int, 0>{});
+        else by_trk(std::integral_constant<int, 1>{});
         return;
     }
 #endif

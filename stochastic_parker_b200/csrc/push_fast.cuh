@@ -18,16 +18,20 @@
 
 // F: the interpolated record of this particle (registers, or a shared-memory row written by
 // the lane group that gathered it)
-// SPEC = true: the run's switches are the common case of the named configs -- mag_dependency = 1,
-// momentum_dependency = 1, no NLGC, on-device Philox, no out-of-plane drift check, no acceleration
-// region (launch_one checks this) -- and are compile-time constants here: ~15 uniform branches and
-// their flag loads disappear and the log/exp/rsqrt chains share one basic block.
-template <int L, typename FT, bool TRACK = false, bool SPEC = false>
+// SPEC != 0: the run's switches are compile-time constants: no NLGC, on-device Philox, no
+// out-of-plane drift check, no acceleration region, time interpolation on (launch_one checks
+// this), mag_dependency = bit 1 and momentum_dependency = bit 2 of SPEC.  ~15 uniform branches and
+// their flag loads disappear and the log/exp/rsqrt chains share one basic block (-10 % executed
+// instructions on C1, profiles/r01f_push_coop_spec_ncu.txt).  SPEC = 0 reads every switch at run time.
+constexpr int kSpec11 = 1 | 2 | 4;  // mag_dependency = 1, momentum_dependency = 1 (C1, C2, C4)
+constexpr int kSpec01 = 1 | 4;      // mag_dependency = 0, momentum_dependency = 1 (C3)
+constexpr int kSpec10 = 1 | 2;      // mag_dependency = 1, momentum_dependency = 0 (C5)
+template <int L, typename FT, bool TRACK = false, int SPEC = 0>
 __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArgs& a,
                                              const FT& F, Lane& q, bool fixed_dt)
 {
-    const bool f_mag = SPEC || prm.mag_dependency == 1;
-    const bool f_mom = SPEC || prm.momentum_dependency == 1;
+    const bool f_mag = SPEC ? bool(SPEC & 2) : prm.mag_dependency == 1;
+    const bool f_mom = SPEC ? bool(SPEC & 4) : prm.momentum_dependency == 1;
     const bool f_nlgc = !SPEC && prm.nlgc;
     const bool f_table = !SPEC && prm.rng_mode == GPAT_RNG_TABLE;
     const bool f_drift2d = !SPEC && prm.check_drift_2d;
