@@ -339,6 +339,9 @@ def main():
             "l2": "no flush: the two-frame field store (135 MB at 1024^2) plus the particle arrays (102 MB) exceed "
                   "the 126 MB L2, and every step uploads a new MHD frame and repacks half of the store",
             "source": w.source,
+            "why_this_workload": "north_star states its target on the 2D reconnection config (configs[0]); configs[1] "
+                                 "(C2, 1e8 particles x 2.4e4 steps per MHD interval = 2 min per step at this rate) runs "
+                                 "with --workload c2 and reaches the same steps/s (profiles/README.md)",
         },
         "e2e": {"value": total_steps / (e2e_ms * 1e-3), "unit": "particle-steps/s",
                 "h2d_bytes_per_step": frame_bytes, "d2h_bytes_per_step": hist_bytes,
@@ -348,7 +351,11 @@ def main():
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                      "frac": ach / peak, "traffic": traffic, "kernel": "push_kernel",
                      "algorithmic_bytes_per_step": ALGO_BYTES[layout], "peak_source": peak_src,
-                     "push_ms_per_launch": tot["push_ms"] / args.steps},
+                     "push_ms_per_launch": tot["push_ms"] / args.steps,
+                     "note": "frac > 1 means the gathers never reach HBM: a lane keeps one particle for the whole "
+                             "interval, so the live working set (resident lanes x 4 records = 39 MB in 2-D) sits in "
+                             "the 126 MB L2 (97 % hit rate, 8.7 DRAM bytes per step in `traffic`); the kernel is bound "
+                             "by instruction issue / FP64 latency (profiles/r01f_push_coop_spec_ncu.txt), not bandwidth"},
         "breakdown_ms_per_step": {k: v / args.steps for k, v in tot.items() if k.endswith("_ms")},
     }
     if rank == 0:

@@ -42,7 +42,7 @@ module gpat_cuda
         integer(c_int32_t) :: dpp_wave, dpp_shear, weak_scattering, keep_rho
         real(c_double) :: tau0, drift1, drift2
         integer(c_int32_t) :: pcharge, check_drift_2d, include_3rd_dim, nlgc
-        real(c_double) :: kperp_kpara
+        real(c_double) :: kperp_kpara, duu0
         integer(c_int32_t) :: focused_transport, spherical_coord, nonuniform_grid
         integer(c_int32_t) :: deltab_flag, correlation_flag, acc_by_surface
         integer(c_int32_t) :: npp_global, nmu_global

@@ -250,16 +250,17 @@ int main(int argc, char** argv)
     // read_diagnostics_params: a fresh open (diagnostics.f90:2060-2104)
     r.pos = 0;
     P.npp_global = (int)r.get("npp_global");
-    r.get("nmu_global");
-    P.nmu_global = 1;  // Parker transport, diagnostics.f90:2107-2111
+    const bool ft = cli.b("-ft");
+    const int nmu_global_conf = (int)r.get("nmu_global");
+    P.nmu_global = ft ? nmu_global_conf : 1;  // 1 for Parker transport, diagnostics.f90:2107-2111
     for (int k = 0; k < 4; ++k) {
         const std::string n = std::to_string(k + 1);
         gpat_hist_spec& s = P.local[k];
         const int dump_interval = (int)r.get("dump_interval" + n);
         s.pmin = r.get("pmin" + n); s.pmax = r.get("pmax" + n);
         s.npbins = (int)r.get("npbins" + n);
-        r.get("nmu" + n);
-        s.nmu = 1;  // diagnostics.f90:2124-2128
+        const int nmu_conf = (int)r.get("nmu" + n);
+        s.nmu = ft ? nmu_conf : 1;  // diagnostics.f90:2124-2128
         s.rx = (int)r.get("rx" + n); s.ry = (int)r.get("ry" + n); s.rz = (int)r.get("rz" + n);
         s.enabled = dump_interval < nframes_run ? 1 : 0;  // nframes = t_end - t_start, diagnostics.f90:2129, stochastic-mhd.f90:205
     }
@@ -272,7 +273,8 @@ int main(int argc, char** argv)
     P.drift1 = cli.d("-dp1"); P.drift2 = cli.d("-dp2"); P.pcharge = (int)cli.i("-ch");
     P.check_drift_2d = (int)cli.i("-cd"); P.include_3rd_dim = (int)cli.i("-i3");
     P.nlgc = cli.b("-nl") ? 1 : 0; P.kperp_kpara = cli.d("-kk");
-    P.focused_transport = cli.b("-ft") ? 1 : 0;
+    P.focused_transport = ft ? 1 : 0;
+    P.duu0 = cli.d("-du");  // set_duu_params, stochastic-mhd.f90:207
     P.spherical_coord = (int)cli.i("-sc"); P.nonuniform_grid = 1 - (int)cli.i("-ug");
     P.deltab_flag = (int)cli.i("-db"); P.correlation_flag = (int)cli.i("-co"); P.acc_by_surface = (int)cli.i("-as");
     P.seed = (uint64_t)cli.i("-seed"); P.rng_mode = GPAT_RNG_PHILOX; P.mpi_rank = 0;

@@ -118,7 +118,9 @@ typedef struct gpat_params {
     int32_t include_3rd_dim; /* include_3rd_dim_in2d_flag */
     int32_t nlgc;
     double kperp_kpara;
-    /* switches that must be 0/false on the GPU path (error otherwise) */
+    double duu0; /* duu_init (set_duu_params, particle_module.f90:279-283): focused transport only */
+    /* focused_transport = 1: 2-D Cartesian push_particle_2d_ft only (reference-order build);
+     * the other switches must be 0/false on the GPU path (error otherwise) */
     int32_t focused_transport, spherical_coord, nonuniform_grid;
     int32_t deltab_flag, correlation_flag, acc_by_surface;
     /* diagnostics */

@@ -433,7 +433,8 @@ static void calc_kappa(const orc_sim* S, const gpat_particle* ptl, const double*
             dkdy = db_dy * ib1 * (P->gamma_turb - 2.0);
         }
     }
-    double kpp = kp->kpara - kp->kperp; /* not focused transport */
+    /* PM:2372-2376: the focused-transport equation carries the parallel streaming itself */
+    double kpp = P->focused_transport ? -kp->kperp : kp->kpara - kp->kperp;
     kp->dkxx_dx = kp->kperp * dkdx + kpp * dkdx * sq(bx) * ib2 +
                   2.0 * kpp * bx * (dbx_dx * b - bx * db_dx) * ib3;
     kp->dkyy_dy = kp->kperp * dkdy + kpp * dkdy * sq(by) * ib2 +
@@ -516,7 +517,7 @@ static void calc_kappa_nlgc(const orc_sim* S, const gpat_particle* ptl, const do
             dkperp_dz = db_dz * ib1 * (P->gamma_turb - 2.0) / 3.0;
         }
     }
-    double kpp = kp->kpara - kp->kperp;
+    double kpp = P->focused_transport ? -kp->kperp : kp->kpara - kp->kperp; /* PM:2605-2609 */
     double kpa = kp->kpara, kpe = kp->kperp;
     kp->dkxx_dx = kpe * dkperp_dx + (kpa * dkpara_dx - kpe * dkperp_dx) * sq(bx) * ib2 +
                   2.0 * kpp * bx * (dbx_dx * b - bx * db_dx) * ib3;
@@ -750,6 +751,156 @@ static void push_particle_2d(orc_sim* S, gpat_particle* ptl, const double* field
 }
 
 /* ------------------------------------------------------------------------ */
+/* focused transport, 2-D Cartesian: calc_duu (PM:3116-3155) and              */
+/* push_particle_2d_ft (PM:3626-3977).  Four uniforms per step: two for the   */
+/* perpendicular displacement, one for p, one for mu (PM:3881-3882, 3918-3921)*/
+/* ------------------------------------------------------------------------ */
+static void calc_duu(const orc_sim* S, const gpat_particle* ptl, double b, double div_bnorm,
+                     double divv, double bb_gradv, double bv_gradv, double mu2, double* dmu_dt,
+                     double* duu, double* duu_du)
+{
+    const gpat_params* P = &S->P;
+    *dmu_dt = ptl->v * div_bnorm + ptl->mu * divv - 3 * ptl->mu * bb_gradv - 2 * bv_gradv / ptl->v;
+    *dmu_dt = *dmu_dt * (1 - mu2) * 0.5;
+    double h0 = (double)0.2f; /* `h0 = 0.2`: a default-real literal assigned to real(dp) */
+    double dtmp = pow(fabs(ptl->mu), P->gamma_turb - 1) + h0;
+    *duu = P->duu0 * (1 - mu2) * dtmp;
+    if (ptl->mu > 0.0)
+        *duu_du = P->duu0 * (-2 * ptl->mu * dtmp + (1 - mu2) * pow(fabs(ptl->mu), P->gamma_turb - 2));
+    else if (ptl->mu < 0.0)
+        *duu_du = P->duu0 * (-2 * ptl->mu * dtmp - (1 - mu2) * pow(fabs(ptl->mu), P->gamma_turb - 2));
+    else
+        *duu_du = 0.0;
+    double duu_norm = 1.0;
+    if (P->mag_dependency == 1) duu_norm = duu_norm * pow(b, 2.0 - P->gamma_turb);
+    if (P->momentum_dependency == 1) duu_norm = duu_norm * pow(ptl->p / P->p0, P->gamma_turb - 1);
+    *duu_du = *duu_du * duu_norm;
+    *duu = *duu * duu_norm;
+    *dmu_dt = *dmu_dt + *duu_du;
+}
+
+static void push_particle_2d_ft(orc_sim* S, gpat_particle* ptl, const double* fields,
+                                const kappa_type* kp, int fixed_dt, const double u[4], double* deltax,
+                                double* deltay, double* deltap, double* deltav, double* deltamu)
+{
+    const gpat_params* P = &S->P;
+    const double mu_max = (double)0.99f;
+    double vx = F(1), vy = F(2), vz = F(3), bx = F(5), by = F(6), bz = F(7);
+    double b = sqrt(sq(bx) + sq(by) + sq(bz));
+    double dxm = P->dx, dym = P->dy;
+    double ib = (b < 2.220446049250313e-16) ? 0.0 : 1.0 / b;
+    double dbx_dx = FG(13), dbx_dy = FG(14), dby_dx = FG(16), dby_dy = FG(17);
+    double dbz_dx = FG(19), dbz_dy = FG(20), db_dx = FG(22), db_dy = FG(23);
+    double ib2 = ib * ib, ib3 = ib * ib2;
+    /* `1.0 / pcharge` is a default-real quotient, PM:3716 */
+    double vdp = (double)(1.0f / (float)P->pcharge) /
+                 sqrt(sq(P->drift1 * P->p0 / ptl->p) + sq(P->drift2 * sq(P->p0) / sq(ptl->p)));
+    double mu2 = sq(ptl->mu);
+    double muf1 = 0.5 * (1.0 - mu2), muf2 = 0.5 * (3.0 * mu2 - 1.0);
+    double kx = bx * dbx_dx + by * dbx_dy;
+    double ky = bx * dby_dx + by * dby_dy;
+    double kz = bx * dbz_dx + by * dbz_dy;
+    double bdot_curvb = bx * dbz_dy - by * dbz_dx + bz * (dby_dx - dbx_dy);
+    double vdx = vdp * (muf1 * (-bz * db_dy) * ib2 + mu2 * (by * kz - bz * ky) * ib3 +
+                        muf1 * bx * bdot_curvb * ib3);
+    double vdy = vdp * (muf1 * (bz * db_dx) * ib2 + mu2 * (bz * kx - bx * kz) * ib3 +
+                        muf1 * by * bdot_curvb * ib3);
+    double vdz = 0.0;
+    if (P->check_drift_2d)
+        vdz = vdp * (muf1 * (bx * db_dy - by * db_dx) * ib2 + mu2 * (bx * ky - by * kx) * ib3 +
+                     muf1 * bz * bdot_curvb * ib3);
+    double vbx = ptl->v * ptl->mu * ib;
+    double vby = vbx * by; /* particle velocity along the magnetic field */
+    vbx = vbx * bx;
+    double dvx_dx = FG(1), dvx_dy = FG(2), dvy_dx = FG(4), dvy_dy = FG(5), dvz_dx = FG(7), dvz_dy = FG(8);
+    double dx_dt = vx + vdx + vbx + kp->dkxx_dx + kp->dkxy_dy;
+    double dy_dt = vy + vdy + vby + kp->dkxy_dx + kp->dkyy_dy;
+    double dz_dt = vdz;
+    double divv = dvx_dx + dvy_dy;
+    double bb_gradv = (bx * (bx * dvx_dx + by * dvx_dy) + by * (bx * dvy_dx + by * dvy_dy) +
+                       bz * (bx * dvz_dx + by * dvz_dy)) * ib2;
+    double bv_gradv = (bx * (vx * dvx_dx + vy * dvx_dy) + by * (vx * dvy_dx + vy * dvy_dy) +
+                       bz * (vx * dvz_dx + vy * dvz_dy)) * ib;
+    double acc_rate = -(muf1 * divv + muf2 * bb_gradv + ptl->mu * bv_gradv / ptl->v);
+    double dp_dt = ptl->p * acc_rate;
+    double dpp = 0.0;
+    if (P->dpp_wave) calc_dpp_wave_scattering(S, F(4), b, kp->kpara, ptl, &dp_dt, &dpp);
+    if (P->dpp_shear) {
+        double sxx = dvx_dx - divv / 3, syy = dvy_dy - divv / 3, szz = -divv / 3;
+        double sxy = (dvx_dy + dvy_dx) / 2;
+        calc_dpp_flow_shear(S, b, bx, by, bz, kp->knorm_para, sxx, syy, szz, sxy, 0.0, 0.0, ptl,
+                            &dp_dt, &dpp);
+    }
+    double div_bnorm = -(bx * db_dx + by * db_dy) * ib2;
+    double dmu_dt, duu, duu_du;
+    calc_duu(S, ptl, b, div_bnorm, divv, bb_gradv, bv_gradv, mu2, &dmu_dt, &duu, &duu_du);
+    if (!fixed_dt) {
+        if (dx_dt != 0.0 && dy_dt != 0.0 && dp_dt != 0.0 && dmu_dt != 0.0) {
+            double s = (kp->skperp > 0.0) ? kp->skperp : kp->skpara; /* PM:3847-3864 */
+            double d = sq(0.5 * dxm / s);
+            d = min2(d, sq(0.5 * dym / s));
+            d = min2(d, sq(s / dx_dt));
+            d = min2(d, sq(s / dy_dt));
+            d = min2(d, (double)0.1f * ptl->p / fabs(dp_dt));
+            d = min2(d, (double)0.1f / fabs(dmu_dt));
+            d = min2(d, 2.0 * duu / sq(dmu_dt));
+            ptl->dt = d;
+        } else {
+            ptl->dt = S->dt_min;
+        }
+        if (ptl->dt < S->dt_min) ptl->dt = S->dt_min;
+        if (ptl->dt > S->dt_max) ptl->dt = S->dt_max;
+    }
+    double sdt = sqrt(ptl->dt);
+    double sqrt3 = sqrt(3.0);
+    double ran1 = (2.0 * u[0] - 1.0) * sqrt3;
+    double ran2 = (2.0 * u[1] - 1.0) * sqrt3;
+    double bxn = bx * ib, byn = by * ib, bzn = bz * ib;
+    double ibxyn = 1.0 / sqrt(sq(bxn) + sq(byn));
+    /* the second term uses the UN-normalised by / bx, PM:3912-3913 -- kept */
+    *deltax = dx_dt * ptl->dt + kp->skperp * ibxyn * sdt * (-bxn * bzn * ran1 - by * ran2);
+    *deltay = dy_dt * ptl->dt + kp->skperp * ibxyn * sdt * (-byn * bzn * ran1 + bx * ran2);
+    double deltaz = dz_dt * ptl->dt;
+    ran1 = (2.0 * u[2] - 1.0) * sqrt3;
+    *deltap = dp_dt * ptl->dt + ran1 * sqrt(2 * dpp) * sdt;
+    *deltav = ptl->v * *deltap / ptl->p;
+    ran1 = (2.0 * u[3] - 1.0) * sqrt3;
+    *deltamu = dmu_dt * ptl->dt + ran1 * sqrt(2 * duu) * sdt;
+    ptl->x = ptl->x + *deltax;
+    ptl->y = ptl->y + *deltay;
+    ptl->z = ptl->z + deltaz;
+    ptl->mu = ptl->mu + *deltamu;
+    ptl->t = ptl->t + ptl->dt;
+    if (ptl->mu > mu_max) {
+        *deltamu = mu_max - (ptl->mu - *deltamu);
+        ptl->mu = mu_max;
+    } else if (ptl->mu < -mu_max) {
+        *deltamu = -mu_max - (ptl->mu - *deltamu);
+        ptl->mu = -mu_max;
+    }
+    if (P->acc_region_flag == 1) {
+        if (particle_in_acceleration_region(S, ptl)) {
+            ptl->p = ptl->p + *deltap;
+            ptl->v = ptl->v + *deltav;
+        } else {
+            *deltap = 0.0;
+            *deltav = 0.0;
+        }
+    } else {
+        ptl->p = ptl->p + *deltap;
+        ptl->v = ptl->v + *deltav;
+    }
+    if (ptl->p < 0.25 * P->p0) { /* PM:3967-3974 */
+        ptl->v = ptl->v - *deltav;
+        *deltav = ptl->v * 0.25 * P->p0 / ptl->p - ptl->v;
+        ptl->v = ptl->v + *deltav;
+        ptl->p = ptl->p - *deltap;
+        *deltap = 0.25 * P->p0 - ptl->p;
+        ptl->p = 0.25 * P->p0;
+    }
+}
+
+/* ------------------------------------------------------------------------ */
 /* push_particle_2d_include_3rd (PM:3979-4245) and push_particle_3d           */
 /* (PM:4625-4907): identical structure; 2-D sets every d/dz to zero.          */
 /* ------------------------------------------------------------------------ */
@@ -912,7 +1063,8 @@ static void negp_or_bc(orc_sim* S, gpat_particle* ptl, const double e[6])
 
 /* one call of interp + kappa + push_particle_* (PM:1614-1691 / 1726-1802) */
 static void one_push(orc_sim* S, gpat_particle* ptl, double t0, double dtf, int fixed_dt,
-                     double* deltax, double* deltay, double* deltaz, double* deltap)
+                     double* deltax, double* deltay, double* deltaz, double* deltap, double* deltav,
+                     double* deltamu)
 {
     const gpat_params* P = &S->P;
     double px = (ptl->x - P->xmin) / P->dx;
@@ -929,7 +1081,9 @@ static void one_push(orc_sim* S, gpat_particle* ptl, double t0, double dtf, int 
     else
         calc_kappa(S, ptl, fields, &kp);
     step_uniforms(S, ptl, u);
-    if (P->ndim == 1)
+    if (P->focused_transport) /* PM:1647-1668: only the 2-D Cartesian FT pusher is restated */
+        push_particle_2d_ft(S, ptl, fields, &kp, fixed_dt, u, deltax, deltay, deltap, deltav, deltamu);
+    else if (P->ndim == 1)
         push_particle_1d(S, ptl, fields, &kp, fixed_dt, u, deltax, deltap);
     else if (P->ndim == 2 && !P->include_3rd_dim)
         push_particle_2d(S, ptl, fields, &kp, fixed_dt, u, deltax, deltay, deltap);
@@ -952,7 +1106,7 @@ static void particle_mover_one_cycle(orc_sim* S, double t0, double dtf, int nste
 #pragma omp parallel for schedule(dynamic, 64) reduction(+ : steps)
     for (int64_t i = S->nptl_old; i < S->nptl_current; ++i) {
         gpat_particle ptl = S->ptls[i];
-        double deltax = 0.0, deltay = 0.0, deltaz = 0.0, deltap = 0.0;
+        double deltax = 0.0, deltay = 0.0, deltaz = 0.0, deltap = 0.0, deltav = 0.0, deltamu = 0.0;
         double dt_target;
         int step = (int)ceil((ptl.t - t0) / dt_fine); /* PM:1570 */
         if (step <= 0)
@@ -978,7 +1132,7 @@ static void particle_mover_one_cycle(orc_sim* S, double t0, double dtf, int nste
             while ((ptl.t - t0) < dt_target && ptl.count_flag == GPAT_COUNT_FLAG_INBOX) {
                 negp_or_bc(S, &ptl, e);
                 if (ptl.count_flag != GPAT_COUNT_FLAG_INBOX) break;
-                one_push(S, &ptl, t0, dtf, 0, &deltax, &deltay, &deltaz, &deltap);
+                one_push(S, &ptl, t0, dtf, 0, &deltax, &deltay, &deltaz, &deltap, &deltav, &deltamu);
                 steps++;
                 ptl.nsteps_pushed = (ptl.nsteps_pushed + 1) % nsteps_interval; /* PM:1694 */
                 track_after_push(S, &ptl);                                     /* PM:1697-1703 */
@@ -989,6 +1143,8 @@ static void particle_mover_one_cycle(orc_sim* S, double t0, double dtf, int nste
                 ptl.y = ptl.y - deltay;
                 ptl.z = ptl.z - deltaz;
                 ptl.p = ptl.p - deltap;
+                ptl.v = ptl.v - deltav;   /* PM:1712-1713: zero for Parker transport */
+                ptl.mu = ptl.mu - deltamu;
                 ptl.t = ptl.t - ptl.dt;
                 double dt_old = ptl.dt;
                 ptl.dt = t0 + dt_target - ptl.t;
@@ -999,7 +1155,7 @@ static void particle_mover_one_cycle(orc_sim* S, double t0, double dtf, int nste
                     } else {
                         ptl.nsteps_pushed = ptl.nsteps_pushed - 1; /* PM:1723 */
                     }
-                    one_push(S, &ptl, t0, dtf, 1, &deltax, &deltay, &deltaz, &deltap);
+                    one_push(S, &ptl, t0, dtf, 1, &deltax, &deltay, &deltaz, &deltap, &deltav, &deltamu);
                     steps++;
                     /* Fortran mod keeps the sign of the dividend, like C's % */
                     ptl.nsteps_pushed = (ptl.nsteps_pushed + 1) % nsteps_interval;
@@ -1088,11 +1244,11 @@ void orc_debug_push_n(orc_sim* S, double t0, double dtf, int nsteps, uint64_t* s
 #pragma omp parallel for schedule(dynamic, 64) reduction(+ : steps)
     for (int64_t i = 0; i < S->nptl_current; ++i) {
         gpat_particle ptl = S->ptls[i];
-        double dx_, dy_, dz_ = 0.0, dp_;
+        double dx_, dy_, dz_ = 0.0, dp_, dv_ = 0.0, dmu_ = 0.0;
         for (int n = 0; n < nsteps && ptl.count_flag == GPAT_COUNT_FLAG_INBOX; ++n) {
             negp_or_bc(S, &ptl, e);
             if (ptl.count_flag != GPAT_COUNT_FLAG_INBOX) break;
-            one_push(S, &ptl, t0, dtf, 0, &dx_, &dy_, &dz_, &dp_);
+            one_push(S, &ptl, t0, dtf, 0, &dx_, &dy_, &dz_, &dp_, &dv_, &dmu_);
             steps++;
             ptl.nsteps_pushed = (ptl.nsteps_pushed + 1) % (1 << 30);
         }

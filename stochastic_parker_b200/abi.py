@@ -57,7 +57,7 @@ class Params(C.Structure):
         ("drift1", C.c_double), ("drift2", C.c_double),
         ("pcharge", C.c_int32), ("check_drift_2d", C.c_int32),
         ("include_3rd_dim", C.c_int32), ("nlgc", C.c_int32),
-        ("kperp_kpara", C.c_double),
+        ("kperp_kpara", C.c_double), ("duu0", C.c_double),
         ("focused_transport", C.c_int32), ("spherical_coord", C.c_int32),
         ("nonuniform_grid", C.c_int32),
         ("deltab_flag", C.c_int32), ("correlation_flag", C.c_int32), ("acc_by_surface", C.c_int32),

@@ -46,7 +46,7 @@ class ConfReader:
 # command-line defaults of the driver (stochastic-mhd.f90:871-881 for drift, 635-637 nlgc)
 CLI_DEFAULTS = dict(drift_param1=4.0e7, drift_param2=2.0e8, charge=-1, nlgc=0, kperp_kpara=0.01,
                     dpp_wave=0, dpp_shear=0, weak_scattering=1, tau0=1.0, check_drift_2d=0,
-                    include_3rd_dim=0, time_interp=1)
+                    include_3rd_dim=0, time_interp=1, focused_transport=0, duu_init=1.0)
 
 
 def build_params(conf_text: str, mhd_cfg: dict, ndim: int, nframes: int = 1 << 30,
@@ -86,16 +86,17 @@ def build_params(conf_text: str, mhd_cfg: dict, ndim: int, nframes: int = 1 << 3
     # read_diagnostics_params: a fresh open (diagnostics.f90:2060-2104)
     r = ConfReader(conf_text)
     P.npp_global = int(r.get("npp_global"))
-    r.get("nmu_global")
-    P.nmu_global = 1  # Parker transport, diagnostics.f90:2107-2111
+    ft = int(c["focused_transport"])
+    nmu_global = int(r.get("nmu_global"))
+    P.nmu_global = nmu_global if ft else 1  # 1 for Parker transport, diagnostics.f90:2107-2111
     for k in range(4):
         s = P.local[k]
         dump_interval = int(r.get(f"dump_interval{k + 1}"))
         s.pmin = r.get(f"pmin{k + 1}")
         s.pmax = r.get(f"pmax{k + 1}")
         s.npbins = int(r.get(f"npbins{k + 1}"))
-        r.get(f"nmu{k + 1}")
-        s.nmu = 1  # diagnostics.f90:2124-2128
+        nmu_k = int(r.get(f"nmu{k + 1}"))
+        s.nmu = nmu_k if ft else 1  # diagnostics.f90:2124-2128
         s.rx = int(r.get(f"rx{k + 1}"))
         s.ry = int(r.get(f"ry{k + 1}"))
         s.rz = int(r.get(f"rz{k + 1}"))
@@ -117,6 +118,8 @@ def build_params(conf_text: str, mhd_cfg: dict, ndim: int, nframes: int = 1 << 3
     P.check_drift_2d = int(c["check_drift_2d"])
     P.include_3rd_dim = int(c["include_3rd_dim"])
     P.nlgc = int(c["nlgc"])
+    P.focused_transport = ft
+    P.duu0 = float(c["duu_init"])  # set_duu_params, particle_module.f90:279-283
     P.kperp_kpara = float(c["kperp_kpara"])
     P.seed = seed
     P.rng_mode = 0

@@ -182,7 +182,10 @@ int validate(const gpat_params* p, std::string& why)
         why = "1-D with mag_dependency = 1 reads an uninitialised db_dx in the reference (undefined there)";
         return 1;
     }
-    if (p->focused_transport) { why = "focused transport pushers are outside the GPU path"; return 1; }
+    if (p->focused_transport && (p->ndim != 2 || p->include_3rd_dim)) {
+        why = "focused transport: only the 2-D Cartesian pusher (push_particle_2d_ft) is on the GPU path";
+        return 1;
+    }
     if (p->spherical_coord) { why = "spherical coordinates are outside the GPU path"; return 1; }
     if (p->nonuniform_grid) { why = "non-uniform grids are outside the GPU path"; return 1; }
     if (p->deltab_flag || p->correlation_flag) { why = "deltab/correlation maps are outside the GPU path"; return 1; }
@@ -208,7 +211,8 @@ bool Rec_has_rho(int layout) { return layout == L2E || layout == L3E; }
 
 int pick_layout(const gpat_params& p)
 {
-    bool ext = p.dpp_wave || p.dpp_shear || (p.ndim == 2 && p.include_3rd_dim) || p.keep_rho;
+    // focused transport reads vz and all six in-plane velocity gradients (particle_module.f90:3764-3789)
+    bool ext = p.dpp_wave || p.dpp_shear || (p.ndim == 2 && p.include_3rd_dim) || p.keep_rho || p.focused_transport;
     // 1-D runs live in the 2-D record layouts (one physical row + one zero row, fill_dev_params)
     if (p.ndim <= 2) return ext ? L2E : L2B;
     return ext ? L3E : L3B;
@@ -261,6 +265,7 @@ void fill_dev_params(gpat_sim* h)
     d.acc_region_flag = p.acc_region_flag;
     d.dpp_wave = p.dpp_wave; d.dpp_shear = p.dpp_shear; d.weak_scattering = p.weak_scattering;
     d.check_drift_2d = p.check_drift_2d; d.include_3rd_dim = p.include_3rd_dim; d.nlgc = p.nlgc;
+    d.focused_transport = p.focused_transport; d.duu0 = p.duu0; d.pcharge = p.pcharge;
     d.key0 = (unsigned)p.seed;
     d.key1 = (unsigned)(p.seed >> 32);
     d.rng_mode = p.rng_mode;
@@ -464,8 +469,9 @@ int run_push(gpat_sim* h, double t0, double dtf, int nsteps_interval, int num_fi
     CU(cudaMemsetAsync(h->d_queue, 0, 2 * sizeof(unsigned long long), h->st));
     CU(cudaEventRecord(h->ev[0], h->st));
     if (a.nptl > 0) {
-        // 1-D (push_particle_1d) exists in the reference-order build only: it is not a throughput path
-        if (h->hp.strict_math || h->hp.ndim == 1) launch_push_strict(h->layout, h->dp, h->P, h->fld, a, h->sm_count, h->st);
+        // 1-D (push_particle_1d) and focused transport (push_particle_2d_ft) exist in the
+        // reference-order build only: they are not throughput paths yet
+        if (h->hp.strict_math || h->hp.ndim == 1 || h->hp.focused_transport) launch_push_strict(h->layout, h->dp, h->P, h->fld, a, h->sm_count, h->st);
         else launch_push_fast(h->layout, h->dp, h->P, h->fld, a, h->sm_count, h->st);
         h->tm.total_launches++;
     }

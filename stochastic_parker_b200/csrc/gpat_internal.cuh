@@ -109,6 +109,9 @@ struct DevParams {
     double acc_region[6];
     int momentum_dependency, mag_dependency, acc_region_flag;
     int dpp_wave, dpp_shear, weak_scattering, check_drift_2d, include_3rd_dim, nlgc;
+    int focused_transport;  // 2-D Cartesian push_particle_2d_ft, reference-order build only
+    int pcharge;
+    double duu0;
     // rng
     unsigned int key0, key1;  // Philox key = (seed_lo, seed_hi + origin)
     int rng_mode;

@@ -69,6 +69,9 @@ struct Lane {
     int nsteps_pushed;
     int count_flag;
     int nsteps_tracked;  // used by the tracking instantiations only
+#if GPAT_STRICT
+    double v, dvl, dmul;  // focused transport: particle speed, last step's delta v / delta mu
+#endif
 };
 
 // particle_boundary_condition for a single rank (neighbours are self or -1)
@@ -301,7 +304,12 @@ __device__ __forceinline__ void calc_kappa(const DevParams& prm, const BField& B
     k.skpara = sqrt(2.0 * k.kpara);
     k.skperp = sqrt(2.0 * k.kperp);
     k.skpara_perp = sqrt(2.0 * (k.kpara - k.kperp));
+#if GPAT_STRICT
+    // particle_module.f90:2372-2376: focused transport carries the parallel streaming itself
+    const double kpp = prm.focused_transport ? -k.kperp : k.kpara - k.kperp;
+#else
     const double kpp = k.kpara - k.kperp;
+#endif
     double px_, py_, pz_ = 0.0;  // the "kperp*dkdx" leading terms
     if (!prm.nlgc) {
         double dkdx = 0.0, dkdy = 0.0, dkdz = 0.0;
@@ -469,6 +477,148 @@ __device__ __forceinline__ void push_1d(const DevParams& prm, const PushArgs& a,
 }
 #endif
 
+#if GPAT_STRICT
+// calc_duu (particle_module.f90:3116-3155) + push_particle_2d_ft (particle_module.f90:3626-3977),
+// Cartesian uniform grid.  Uniforms: u0, u1 perpendicular displacement, u2 momentum, u3 pitch angle.
+template <int L>
+__device__ __forceinline__ void push_2d_ft(const DevParams& prm, const PushArgs& a,
+                                           const double (&F)[Rec<L>::NREC], double u0, double u1, double u2,
+                                           double u3, Lane& q, bool fixed_dt)
+{
+    if constexpr (Rec<L>::EXT && Rec<L>::NDIM == 2) {
+        const double mu_max = (double)0.99f;
+        BField B;
+        VGrad V;
+        const double vx = F[s2::vx], vy = F[s2::vy], vz = F[s2::vz];
+        B.bx = F[s2::bx]; B.by = F[s2::by]; B.bz = F[s2::bz];
+        B.dbx_dx = F[s2::dbx_dx]; B.dbx_dy = F[s2::dbx_dy]; B.dby_dx = F[s2::dby_dx];
+        B.dby_dy = F[s2::dby_dy]; B.dbz_dx = F[s2::dbz_dx]; B.dbz_dy = F[s2::dbz_dy];
+        B.db_dx = F[s2::db_dx]; B.db_dy = F[s2::db_dy];
+        B.dbx_dz = B.dby_dz = B.dbz_dz = B.db_dz = 0.0;
+        V.dvx_dx = F[s2::dvx_dx]; V.dvy_dy = F[s2::dvy_dy]; V.dvz_dz = 0.0;
+        V.dvx_dy = F[s2::dvx_dy]; V.dvy_dx = F[s2::dvy_dx]; V.dvz_dx = 0.0; V.dvz_dy = 0.0;
+        V.dvx_dz = V.dvy_dz = 0.0;
+        const double dvz_dx = F[s2::dvz_dx], dvz_dy = F[s2::dvz_dy];
+        const double rho = F[s2::rho];
+        const double bx = B.bx, by = B.by, bz = B.bz;
+        B.b = sqrt(sq(bx) + sq(by) + sq(bz));
+        const double b = B.b;
+        Kappa k;
+        calc_kappa<false, false>(prm, B, q.p, q.mu, k);
+        const double ib = (b < kEps) ? 0.0 : 1.0 / b;
+        const double ib2 = ib * ib, ib3 = ib * ib2;
+        // `1.0 / pcharge` is a default-real quotient (particle_module.f90:3716); qdrift holds 1/(3 q)
+        const double vdp = (double)(1.0f / (float)prm.pcharge) /
+                           sqrt(sq(prm.drift1 * prm.p0 / q.p) + sq(prm.drift2 * sq(prm.p0) / sq(q.p)));
+        const double mu2 = sq(q.mu);
+        const double muf1 = 0.5 * (1.0 - mu2), muf2 = 0.5 * (3.0 * mu2 - 1.0);
+        const double kx = bx * B.dbx_dx + by * B.dbx_dy;
+        const double ky = bx * B.dby_dx + by * B.dby_dy;
+        const double kz = bx * B.dbz_dx + by * B.dbz_dy;
+        const double bdot_curvb = bx * B.dbz_dy - by * B.dbz_dx + bz * (B.dby_dx - B.dbx_dy);
+        const double vdx = vdp * (muf1 * (-bz * B.db_dy) * ib2 + mu2 * (by * kz - bz * ky) * ib3 +
+                                  muf1 * bx * bdot_curvb * ib3);
+        const double vdy = vdp * (muf1 * (bz * B.db_dx) * ib2 + mu2 * (bz * kx - bx * kz) * ib3 +
+                                  muf1 * by * bdot_curvb * ib3);
+        double vdz = 0.0;
+        if (prm.check_drift_2d)
+            vdz = vdp * (muf1 * (bx * B.db_dy - by * B.db_dx) * ib2 + mu2 * (bx * ky - by * kx) * ib3 +
+                         muf1 * bz * bdot_curvb * ib3);
+        double vbx = q.v * q.mu * ib;
+        const double vby = vbx * by;
+        vbx = vbx * bx;
+        const double dx_dt = vx + vdx + vbx + k.dkxx_dx + k.dkxy_dy;
+        const double dy_dt = vy + vdy + vby + k.dkxy_dx + k.dkyy_dy;
+        const double dz_dt = vdz;
+        const double divv = V.dvx_dx + V.dvy_dy;
+        const double bb_gradv = (bx * (bx * V.dvx_dx + by * V.dvx_dy) + by * (bx * V.dvy_dx + by * V.dvy_dy) +
+                                 bz * (bx * dvz_dx + by * dvz_dy)) * ib2;
+        const double bv_gradv = (bx * (vx * V.dvx_dx + vy * V.dvx_dy) + by * (vx * V.dvy_dx + vy * V.dvy_dy) +
+                                 bz * (vx * dvz_dx + vy * dvz_dy)) * ib;
+        const double acc_rate = -(muf1 * divv + muf2 * bb_gradv + q.mu * bv_gradv / q.v);
+        double dp_dt = q.p * acc_rate;
+        double dpp = 0.0;
+        momentum_diffusion(prm, B, V, rho, divv, k, q.p, dp_dt, dpp);  // sigma_xz = sigma_yz = 0 (V.dvz_* = 0)
+        // calc_duu
+        const double div_bnorm = -(bx * B.db_dx + by * B.db_dy) * ib2;
+        double dmu_dt = q.v * div_bnorm + q.mu * divv - 3 * q.mu * bb_gradv - 2 * bv_gradv / q.v;
+        dmu_dt = dmu_dt * (1 - mu2) * 0.5;
+        const double h0 = (double)0.2f;
+        const double dtmp = pow(fabs(q.mu), prm.gamma_turb - 1) + h0;
+        double duu = prm.duu0 * (1 - mu2) * dtmp;
+        double duu_du;
+        if (q.mu > 0.0) duu_du = prm.duu0 * (-2 * q.mu * dtmp + (1 - mu2) * pow(fabs(q.mu), prm.gamma_turb - 2));
+        else if (q.mu < 0.0) duu_du = prm.duu0 * (-2 * q.mu * dtmp - (1 - mu2) * pow(fabs(q.mu), prm.gamma_turb - 2));
+        else duu_du = 0.0;
+        double duu_norm = 1.0;
+        if (prm.mag_dependency == 1) duu_norm = duu_norm * pow(b, 2.0 - prm.gamma_turb);
+        if (prm.momentum_dependency == 1) duu_norm = duu_norm * pow(q.p / prm.p0, prm.gamma_turb - 1);
+        duu_du = duu_du * duu_norm;
+        duu = duu * duu_norm;
+        dmu_dt = dmu_dt + duu_du;
+
+        if (!fixed_dt) {
+            double d;
+            if (dx_dt != 0.0 && dy_dt != 0.0 && dp_dt != 0.0 && dmu_dt != 0.0) {
+                const double s = (k.skperp > 0.0) ? k.skperp : k.skpara;  // particle_module.f90:3847-3864
+                d = sq(0.5 * prm.dx / s);
+                d = min2(d, sq(0.5 * prm.dy / s));
+                d = min2(d, sq(s / dx_dt));
+                d = min2(d, sq(s / dy_dt));
+                d = min2(d, (double)0.1f * q.p / fabs(dp_dt));
+                d = min2(d, (double)0.1f / fabs(dmu_dt));
+                d = min2(d, 2.0 * duu / sq(dmu_dt));
+            } else {
+                d = a.dt_min;
+            }
+            if (d < a.dt_min) d = a.dt_min;
+            if (d > a.dt_max) d = a.dt_max;
+            q.dt = d;
+        }
+        const double sdt = sqrt(q.dt);
+        const double sqrt3 = 1.7320508075688772;
+        double ran1 = (2.0 * u0 - 1.0) * sqrt3;
+        const double ran2 = (2.0 * u1 - 1.0) * sqrt3;
+        const double bxn = bx * ib, byn = by * ib, bzn = bz * ib;
+        const double ibxyn = 1.0 / sqrt(sq(bxn) + sq(byn));
+        // the second term uses the UN-normalised by / bx (particle_module.f90:3912-3913): kept
+        const double ddx = dx_dt * q.dt + k.skperp * ibxyn * sdt * (-bxn * bzn * ran1 - by * ran2);
+        const double ddy = dy_dt * q.dt + k.skperp * ibxyn * sdt * (-byn * bzn * ran1 + bx * ran2);
+        const double ddz = dz_dt * q.dt;
+        ran1 = (2.0 * u2 - 1.0) * sqrt3;
+        double ddp = dp_dt * q.dt + ran1 * sqrt(2 * dpp) * sdt;
+        double ddv = q.v * ddp / q.p;
+        ran1 = (2.0 * u3 - 1.0) * sqrt3;
+        double ddmu = dmu_dt * q.dt + ran1 * sqrt(2 * duu) * sdt;
+        q.x = q.x + ddx;
+        q.y = q.y + ddy;
+        q.z = q.z + ddz;
+        q.mu = q.mu + ddmu;
+        q.t = q.t + q.dt;
+        if (q.mu > mu_max) { ddmu = mu_max - (q.mu - ddmu); q.mu = mu_max; }
+        else if (q.mu < -mu_max) { ddmu = -mu_max - (q.mu - ddmu); q.mu = -mu_max; }
+        if (prm.acc_region_flag == 1) {
+            if (in_acc_region(prm, q)) { q.p = q.p + ddp; q.v = q.v + ddv; }
+            else { ddp = 0.0; ddv = 0.0; }
+        } else {
+            q.p = q.p + ddp;
+            q.v = q.v + ddv;
+        }
+        const double pfloor = 0.25 * prm.p0;
+        if (q.p < pfloor) {  // particle_module.f90:3967-3974
+            q.v = q.v - ddv;
+            ddv = q.v * 0.25 * prm.p0 / q.p - q.v;
+            q.v = q.v + ddv;
+            q.p = q.p - ddp;
+            ddp = pfloor - q.p;
+            q.p = pfloor;
+        }
+        q.dxl = ddx; q.dyl = ddy; q.dzl = 0.0;  // the mover's own deltaz stays 0 (particle_module.f90:1564)
+        q.dpl = ddp; q.dvl = ddv; q.dmul = ddmu;
+    }
+}
+#endif
+
 // One call of push_particle_*: everything between the BC test and the step counter.
 template <int L, bool TRACK = false>
 __device__ __forceinline__ void push_once(const DevParams& prm, const PushArgs& a,
@@ -505,6 +655,10 @@ __device__ __forceinline__ void push_once(const DevParams& prm, const PushArgs& 
     if constexpr (!D3) {
         if (prm.ndim == 1) {
             push_1d<L>(prm, a, F, u0, u1, q, fixed_dt);
+            return;
+        }
+        if (prm.focused_transport) {
+            push_2d_ft<L>(prm, a, F, u0, u1, u2, u3, q, fixed_dt);
             return;
         }
     }
@@ -683,6 +837,9 @@ __device__ __forceinline__ int next_state(const DevParams& prm, const PushArgs& 
             if ((q.t - a.t0) > q.dt_target && inbox) {  // particle_module.f90:1707-1716
                 q.x = q.x - q.dxl; q.y = q.y - q.dyl; q.z = q.z - q.dzl;
                 q.p = q.p - q.dpl;
+#if GPAT_STRICT
+                if (prm.focused_transport) { q.v = q.v - q.dvl; q.mu = q.mu - q.dmul; }  // particle_module.f90:1712-1713
+#endif
                 q.t = q.t - q.dt;
                 q.dt_old = q.dt;
                 q.dt = a.t0 + q.dt_target - q.t;
@@ -723,6 +880,9 @@ __device__ __forceinline__ int load_lane(const DevParams& prm, const PushArgs& a
     q.tag_spl = P.tag_splitted[idx]; q.origin = P.origin[idx];
     q.nsteps_pushed = P.nsteps_pushed[idx]; q.count_flag = P.count_flag[idx];
     q.dxl = q.dyl = q.dzl = q.dpl = 0.0;
+#if GPAT_STRICT
+    q.v = P.v[idx]; q.dvl = 0.0; q.dmul = 0.0;
+#endif
     q.dt_old = q.dt;
     if (a.debug_nsteps > 0) {
         remaining = a.debug_nsteps;
@@ -748,6 +908,9 @@ __device__ __forceinline__ void store_lane(const PushArgs& a, const PtlSoA& P, l
 {
     P.x[idx] = q.x; P.y[idx] = q.y; P.z[idx] = q.z; P.p[idx] = q.p;
     P.t[idx] = q.t; P.dt[idx] = q.dt; P.rng[idx] = q.rng;
+#if GPAT_STRICT
+    P.v[idx] = q.v; P.mu[idx] = q.mu;  // changed by focused transport only
+#endif
     P.nsteps_pushed[idx] = q.nsteps_pushed;
     P.count_flag[idx] = (signed char)q.count_flag;
     // particle_module.f90:1913 sets 1 at the start of the interval; tracked particles count up from it
@@ -1152,15 +1315,16 @@ void launch_one(const DevParams& prm, const PtlSoA& P, const float* fld, const P
         grid = (long long)sm_count * per_sm;
         if (want < grid) grid = want > 0 ? want : 1;
         // tracking runs use their own instantiations: the production kernels carry no tracking code
-        // switch-specialised instantiations (physics_fast): every layout for mag = mom = 1, plus the
-        // two other combinations the named configs use (C3: mag 0 on the base 2-D record, C5: mom 0
-        // on the base 3-D record).  Tracking runs pick the same SPEC so that they replay the run
-        // their particles were selected from with identical arithmetic.
+        // switch-specialised instantiations (physics_fast) of the 2-D layouts: mag = mom = 1 (C1, C2,
+        // C4) and, on the base record, mag = 0 (C3).  The 3-D kernels stay generic: at their 128-
+        // register cap the specialised code spills more and measured 7 % SLOWER on C5
+        // (profiles/README.md).  Tracking runs pick the same SPEC so that they replay the run their
+        // particles were selected from with identical arithmetic.
         int spec = 0;
         if (a.debug_nsteps == 0 && !prm.nlgc && prm.rng_mode != GPAT_RNG_TABLE && !prm.check_drift_2d &&
             prm.acc_region_flag != 1 && prm.time_interp && !a.generic) {
             const int want = 1 | (prm.mag_dependency == 1 ? 2 : 0) | (prm.momentum_dependency == 1 ? 4 : 0);
-            if (want == kSpec11 || (L == L2B && want == kSpec01) || (L == L3B && want == kSpec10)) spec = want;
+            if (Rec<L>::NDIM == 2 && (want == kSpec11 || (L == L2B && want == kSpec01))) spec = want;
         }
         auto go = [&](auto sel_c, auto trk_c, auto spec_c) {
             push_kernel_coop<L, decltype(sel_c)::value, decltype(trk_c)::value, decltype(spec_c)::value>
@@ -1168,14 +1332,13 @@ void launch_one(const DevParams& prm, const PtlSoA& P, const float* fld, const P
         };
         auto by_spec = [&](auto sel_c, auto trk_c) {
             using I = std::integral_constant<int, 0>;
-            if (spec == kSpec11) go(sel_c, trk_c, std::integral_constant<int, kSpec11>{});
-            else if constexpr (L == L2B) {
-                if (spec == kSpec01) go(sel_c, trk_c, std::integral_constant<int, kSpec01>{});
-                else go(sel_c, trk_c, I{});
-            } else if constexpr (L == L3B) {
-                if (spec == kSpec10) go(sel_c, trk_c, std::integral_constant<int, kSpec10>{});
-                else go(sel_c, trk_c, I{});
-            } else go(sel_c, trk_c, I{});
+            if constexpr (Rec<L>::NDIM == 2) {
+                if (spec == kSpec11) { go(sel_c, trk_c, std::integral_constant<int, kSpec11>{}); return; }
+                if constexpr (L == L2B) {
+                    if (spec == kSpec01) { go(sel_c, trk_c, std::integral_constant<int, kSpec01>{}); return; }
+                }
+            }
+            go(sel_c, trk_c, I{});
         };
         auto by_trk = [&](auto sel_c) {
             if (a.trk.enabled) by_spec(sel_c, std::true_type{});

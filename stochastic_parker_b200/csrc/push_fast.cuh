@@ -25,7 +25,6 @@
 // instructions on C1, profiles/r01f_push_coop_spec_ncu.txt).  SPEC = 0 reads every switch at run time.
 constexpr int kSpec11 = 1 | 2 | 4;  // mag_dependency = 1, momentum_dependency = 1 (C1, C2, C4)
 constexpr int kSpec01 = 1 | 4;      // mag_dependency = 0, momentum_dependency = 1 (C3)
-constexpr int kSpec10 = 1 | 2;      // mag_dependency = 1, momentum_dependency = 0 (C5)
 template <int L, typename FT, bool TRACK = false, int SPEC = 0>
 __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArgs& a,
                                              const FT& F, Lane& q, bool fixed_dt)

@@ -481,3 +481,110 @@ def test_tracking_replays_and_records_the_selected_particles():
     assert np.count_nonzero((last["tag_splitted"] < 0).any(axis=1)) == 25
     assert np.all(np.abs(last["tag_injected"][last["tag_splitted"] < 0]) ==
                   np.repeat(tags[:, 1], (last["tag_splitted"] < 0).sum(axis=1)))
+
+
+# ---- focused transport, 2-D (calc_duu + push_particle_2d_ft, particle_module.f90:3116-3155, 3626-3977)
+def _np_step_2d_ft(P, F, ptl, u, dt_min, dt_max):
+    """Independent numpy restatement of one 2-D focused-transport step written from the Fortran."""
+    f = lambda k: F[:, k - 1]
+    g = lambda k: F[:, 8 + k - 1]
+    p, v, mu = ptl["p"], ptl["v"], ptl["mu"]
+    vx, vy, vz, rho, bx, by, bz = f(1), f(2), f(3), f(4), f(5), f(6), f(7)
+    b = np.sqrt(bx**2 + by**2 + bz**2)
+    ib = 1.0 / b
+    ib2, ib3 = ib * ib, ib * ib * ib
+    dbx_dx, dbx_dy, dby_dx, dby_dy = g(13), g(14), g(16), g(17)
+    dbz_dx, dbz_dy, db_dx, db_dy = g(19), g(20), g(22), g(23)
+    # kappa with kpp = -kperp (particle_module.f90:2372-2376)
+    knp = b ** (P.gamma_turb - 2.0) if P.mag_dependency == 1 else np.ones_like(b)
+    knorm = knp * (p / P.p0) ** P.pindex if P.momentum_dependency == 1 else knp
+    kpara = P.kpara0 * knorm
+    kperp = kpara * P.kret
+    skpara, skperp = np.sqrt(2 * kpara), np.sqrt(2 * kperp)
+    dkdx = db_dx * ib * (P.gamma_turb - 2.0) if P.mag_dependency == 1 else 0.0 * b
+    dkdy = db_dy * ib * (P.gamma_turb - 2.0) if P.mag_dependency == 1 else 0.0 * b
+    kpp = -kperp
+    dkxx_dx = kperp * dkdx + kpp * dkdx * bx**2 * ib2 + 2.0 * kpp * bx * (dbx_dx * b - bx * db_dx) * ib3
+    dkyy_dy = kperp * dkdy + kpp * dkdy * by**2 * ib2 + 2.0 * kpp * by * (dby_dy * b - by * db_dy) * ib3
+    dkxy_dx = kpp * dkdx * bx * by * ib2 + kpp * ((dbx_dx * by + bx * dby_dx) * ib2 - 2.0 * bx * by * db_dx * ib3)
+    dkxy_dy = kpp * dkdy * bx * by * ib2 + kpp * ((dbx_dy * by + bx * dby_dy) * ib2 - 2.0 * bx * by * db_dy * ib3)
+    vdp = float(np.float32(1.0) / np.float32(P.pcharge)) / np.sqrt((P.drift1 * P.p0 / p) ** 2 + (P.drift2 * P.p0**2 / p**2) ** 2)
+    mu2 = mu**2
+    muf1, muf2 = 0.5 * (1.0 - mu2), 0.5 * (3.0 * mu2 - 1.0)
+    kx, ky, kz = bx * dbx_dx + by * dbx_dy, bx * dby_dx + by * dby_dy, bx * dbz_dx + by * dbz_dy
+    bdc = bx * dbz_dy - by * dbz_dx + bz * (dby_dx - dbx_dy)
+    vdx = vdp * (muf1 * (-bz * db_dy) * ib2 + mu2 * (by * kz - bz * ky) * ib3 + muf1 * bx * bdc * ib3)
+    vdy = vdp * (muf1 * (bz * db_dx) * ib2 + mu2 * (bz * kx - bx * kz) * ib3 + muf1 * by * bdc * ib3)
+    vb = v * mu * ib
+    dvx_dx, dvx_dy, dvy_dx, dvy_dy, dvz_dx, dvz_dy = g(1), g(2), g(4), g(5), g(7), g(8)
+    dx_dt = vx + vdx + vb * bx + dkxx_dx + dkxy_dy
+    dy_dt = vy + vdy + vb * by + dkxy_dx + dkyy_dy
+    divv = dvx_dx + dvy_dy
+    bbg = (bx * (bx * dvx_dx + by * dvx_dy) + by * (bx * dvy_dx + by * dvy_dy) + bz * (bx * dvz_dx + by * dvz_dy)) * ib2
+    bvg = (bx * (vx * dvx_dx + vy * dvx_dy) + by * (vx * dvy_dx + vy * dvy_dy) + bz * (vx * dvz_dx + vy * dvz_dy)) * ib
+    dp_dt = p * -(muf1 * divv + muf2 * bbg + mu * bvg / v)
+    div_bn = -(bx * db_dx + by * db_dy) * ib2
+    dmu_dt = (v * div_bn + mu * divv - 3 * mu * bbg - 2 * bvg / v) * (1 - mu2) * 0.5
+    dtmp = np.abs(mu) ** (P.gamma_turb - 1) + float(np.float32(0.2))
+    norm = np.ones_like(b)
+    if P.mag_dependency == 1:
+        norm = norm * b ** (2.0 - P.gamma_turb)
+    if P.momentum_dependency == 1:
+        norm = norm * (p / P.p0) ** (P.gamma_turb - 1)
+    duu = P.duu0 * (1 - mu2) * dtmp * norm
+    duu_du = P.duu0 * (-2 * mu * dtmp + np.sign(mu) * (1 - mu2) * np.abs(mu) ** (P.gamma_turb - 2)) * norm
+    dmu_dt = dmu_dt + duu_du
+    s = np.where(skperp > 0, skperp, skpara)
+    cands = [(0.5 * P.dx / s) ** 2, (0.5 * P.dy / s) ** 2, (s / dx_dt) ** 2, (s / dy_dt) ** 2,
+             float(np.float32(0.1)) * p / np.abs(dp_dt), float(np.float32(0.1)) / np.abs(dmu_dt), 2.0 * duu / dmu_dt**2]
+    dt = np.clip(np.minimum.reduce(cands), dt_min, dt_max)
+    sdt, s3 = np.sqrt(dt), np.sqrt(3.0)
+    r1, r2, rp, rm = [(2.0 * u[:, k] - 1.0) * s3 for k in range(4)]
+    bxn, byn, bzn = bx * ib, by * ib, bz * ib
+    ibxyn = 1.0 / np.sqrt(bxn**2 + byn**2)
+    x = ptl["x"] + dx_dt * dt + skperp * ibxyn * sdt * (-bxn * bzn * r1 - by * r2)
+    y = ptl["y"] + dy_dt * dt + skperp * ibxyn * sdt * (-byn * bzn * r1 + bx * r2)
+    dp = dp_dt * dt
+    mun = np.clip(mu + dmu_dt * dt + rm * np.sqrt(2 * duu) * sdt, -float(np.float32(0.99)), float(np.float32(0.99)))
+    pn = p + dp
+    vn = v + v * dp / p
+    low = pn < 0.25 * P.p0
+    vn = np.where(low, v * 0.25 * P.p0 / pn, vn)  # particle_module.f90:3969 divides by the NEW (too small) p
+    pn = np.where(low, 0.25 * P.p0, pn)
+    return x, y, pn, vn, mun, ptl["t"] + dt, dt
+
+
+def test_focused_transport_2d_step_matches_numpy_restatement():
+    w, P, frames, _ = make_case("c1", grid=48, nptl=400, cli=dict(focused_transport=1, duu_init=5.0))
+    assert P.focused_transport == 1 and P.duu0 == 5.0 and P.nmu_global > 1
+    P.rng_mode = RNG_TABLE
+    o = Oracle(P, w.nptl_max)
+    u = np.random.default_rng(9).uniform(0, 1, (400, 2, 4))
+    o.set_rng_table(u)
+    o.upload_fields(0, frames[0])
+    o.upload_fields(1, frames[1])
+    o.inject_uniform(400, 0.0, 0, w.particle_v0, 0.0, w.dt_out, box_of(P), w.power_index)
+    before = o.download_particles()
+    assert o.debug_push_n(0.0, w.dt_out, 1) == 400
+    after = o.download_particles()
+    F = o.interp(before["x"], before["y"], before["z"], (before["t"] - 0.0) / w.dt_out)
+    x, y, p, v, mu, t, dt = _np_step_2d_ft(P, F, before, u[before["tag_injected"], 0],
+                                           P.dt_min_rel * w.dt_out, P.dt_max_rel * w.dt_out)
+    for name, ref in (("x", x), ("y", y), ("p", p), ("v", v), ("mu", mu), ("t", t), ("dt", dt)):
+        scale = np.maximum(np.abs(ref), 1.0 if name in "xy" else 1e-300)
+        err = np.abs(after[name] - ref) / scale
+        assert err.max() < 1e-13, (name, err.max())
+    assert np.any(after["mu"] != before["mu"]) and np.any(after["v"] != before["v"])
+
+
+def test_focused_transport_2d_intervals_fill_the_pitch_angle_bins():
+    w, P, frames, ts = make_case("c1", grid=48, nptl=1500, nframes=3, cli=dict(focused_transport=1, duu_init=20.0),
+                                 conf=dict(dt_min_rel=1e-4))
+    o = Oracle(P, w.nptl_max)
+    res, steps = run_intervals(o, frames, ts, nptl=1500, dist_flag=1, particle_v0=w.particle_v0, inject_new_ptl=False)
+    ptl = o.download_particles()
+    assert steps > 1500 and np.all(np.abs(ptl["mu"]) <= np.float64(np.float32(0.99)))
+    assert np.all(ptl["t"] == ts[-1])
+    fg = res[-1]["fglobal"]                       # (npp, nmu)
+    assert fg.shape[1] == P.nmu_global and np.count_nonzero(fg.sum(axis=0)) > P.nmu_global // 2
+    assert abs(fg.sum() - ptl["weight"][(ptl["p"] > P.pmin) & (ptl["p"] <= P.pmax)].sum()) < 1e-9

@@ -128,6 +128,10 @@ CASES = {
     "c3_shock_open": dict(key="c3", grid=64),
     "c4_dpp_wave_shear": dict(key="c4", grid=64),
     "c4_dpp_strong_kret0": dict(key="c4", grid=64, conf=dict(kret=0.0), cli=dict(weak_scattering=0)),
+    "c1_2d_focused_transport": dict(key="c1", grid=64, conf=dict(dt_min_rel=1e-4),
+                                    cli=dict(focused_transport=1, duu_init=5.0)),
+    "c4_2d_focused_transport_dpp": dict(key="c4", grid=64, conf=dict(dt_min_rel=1e-4),
+                                        cli=dict(focused_transport=1, duu_init=5.0, nlgc=1, kperp_kpara=0.05)),
     "s1_shock_1d": dict(key="s1", grid=256),
     "s1_shock_1d_dpp_nlgc": dict(key="s1", grid=256, conf=dict(dt_min_rel=1e-3),
                                  cli=dict(dpp_wave=1, dpp_shear=1, nlgc=1, kperp_kpara=0.05)),
@@ -221,7 +225,7 @@ def test_interval_parity_fast():
     g.close()
 
 
-@pytest.mark.parametrize("name", ["c1_2d", "c3_shock_open", "c5_3d", "s1_shock_1d"])
+@pytest.mark.parametrize("name", ["c1_2d", "c3_shock_open", "c5_3d", "s1_shock_1d", "c1_2d_focused_transport"])
 def test_histograms_bit_exact(name):
     """calc_particle_distributions + quick_check + get_pmax_global on the SAME particle set:
     every histogram count bit-exact (dyadic weights -> order-independent FP64 sums)."""
