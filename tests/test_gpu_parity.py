@@ -130,7 +130,7 @@ CASES = {
     "c4_dpp_strong_kret0": dict(key="c4", grid=64, conf=dict(kret=0.0), cli=dict(weak_scattering=0)),
     "c1_2d_focused_transport": dict(key="c1", grid=64, conf=dict(dt_min_rel=1e-4),
                                     cli=dict(focused_transport=1, duu_init=5.0)),
-    "c4_2d_focused_transport_dpp": dict(key="c4", grid=64, conf=dict(dt_min_rel=1e-4),
+    "c4_2d_focused_transport_dpp": dict(key="c4", grid=64, conf=dict(dt_min_rel=1e-3),
                                         cli=dict(focused_transport=1, duu_init=5.0, nlgc=1, kperp_kpara=0.05)),
     "s1_shock_1d": dict(key="s1", grid=256),
     "s1_shock_1d_dpp_nlgc": dict(key="s1", grid=256, conf=dict(dt_min_rel=1e-3),
@@ -323,7 +323,12 @@ def test_edge_cases():
     with pytest.raises(GpatError):
         g.inject_uniform(4, 0.0, 7, 1.0, 0.0, 0.1, box_of(P), 6.2)
     bad = P.copy()
-    bad.focused_transport = 1
+    bad.focused_transport = 1       # only the 2-D Cartesian FT pusher is on the GPU path ...
+    bad.include_3rd_dim = 1         # ... not push_particle_2d_include_3rd_ft
+    with pytest.raises(GpatError):
+        GpatSim(bad, 64)
+    bad = P.copy()
+    bad.spherical_coord = 1
     with pytest.raises(GpatError):
         GpatSim(bad, 64)
     bad = P.copy()
