@@ -13,7 +13,7 @@ module gpat_cuda
     public :: gpat_params, gpat_hist_spec, gpat_particle, gpat_counters, gpat_timings
     public :: gpat_init, gpat_set_params, gpat_finalize, gpat_last_error
     public :: gpat_upload_fields, gpat_prefetch_fields, gpat_swap_fields
-    public :: gpat_inject_uniform, gpat_inject_targeted, gpat_particle_mover, gpat_split
+    public :: gpat_inject_uniform, gpat_inject_targeted, gpat_inject_at_shock, gpat_particle_mover, gpat_split
     public :: gpat_init_tracking, gpat_tracked_shape, gpat_download_tracked, gpat_reset_tracked
     public :: gpat_download_particles, gpat_upload_particles
     public :: gpat_download_escaped, gpat_reset_escaped
@@ -145,6 +145,16 @@ module gpat_cuda
             real(c_double), intent(in) :: part_box(6)
             integer(c_int64_t), intent(out) :: nptl_injected, ncells
         end function gpat_inject_targeted
+
+        !< locate_shock_xpos (mhd_data_parallel.f90:1988) + inject_particles_at_shock (particle_module.f90:542)
+        integer(c_int) function gpat_inject_at_shock(h, nptl, dt, dist_flag, particle_v0, t_frame, &
+                power_index) bind(C, name="gpat_inject_at_shock")
+            import :: c_ptr, c_int, c_int64_t, c_double
+            type(c_ptr), value :: h
+            integer(c_int64_t), value :: nptl
+            integer(c_int), value :: dist_flag
+            real(c_double), value :: dt, particle_v0, t_frame, power_index
+        end function gpat_inject_at_shock
 
         !< init_particle_tracking (particle_module.f90:5825) without the HDF5 read:
         !< tags = c_loc(tags_tracking), ncols = split_times_max + 2

@@ -210,7 +210,7 @@ int main(int argc, char** argv)
         return 2;
     }
     // features outside the GPU path must stay off; the library re-checks the ones it is told about
-    for (const char* k : {"-is", "-ib", "-rf", "-vdt"})
+    for (const char* k : {"-ib", "-rf", "-vdt"})
         if (cli.b(k)) {
             std::fprintf(stderr, "gpat_driver: switch %s is outside the GPU particle path\n", k);
             return 2;
@@ -408,7 +408,10 @@ int main(int argc, char** argv)
             CK(gpat_upload_fields(h, P.time_interp ? 1 : 0, frame.data(), 8, 0), "gpat_upload_fields");
         }
         const double t0 = tstamp(tf - 1), dtf = tstamp(tf) - tstamp(tf - 1);  // tstamps_mhd(tf - t_start), particle_module.f90:1868
-        if ((tf == t_start + 1 || inject_new) && tf <= tmax_to_inject) {  // :462-485, same precedence
+        if (cli.b("-is")) {  // :451-454: locate_shock_xpos + inject_particles_at_shock, every frame
+            CK(gpat_inject_at_shock(h, nptl, cli.d("-dt"), dist_flag, cli.d("-pv"), t0, cli.d("-pi")),
+               "gpat_inject_at_shock");
+        } else if ((tf == t_start + 1 || inject_new) && tf <= tmax_to_inject) {  // :462-485, same precedence
             int mode = 0;
             double vmin = 0.0;
             long long norm = 1;

@@ -211,11 +211,21 @@ int gpat_inject_uniform(gpat_handle h, int64_t nptl, double dt, int dist_flag,
 #define GPAT_INJECT_LARGE_DB2 3
 #define GPAT_INJECT_LARGE_DIVV 4
 #define GPAT_INJECT_LARGE_RHO 5
+#define GPAT_INJECT_AT_SHOCK 6 /* internal mode of gpat_inject_at_shock */
 int gpat_inject_targeted(gpat_handle h, int mode, int64_t nptl, double dt, int dist_flag,
                          double particle_v0, double t_frame, double dt_mhd,
                          const double part_box[6], double power_index, int inject_same_nptl,
                          double vmin, int64_t ncells_norm, int64_t* nptl_injected,
                          int64_t* ncells);
+
+/* Replaces locate_shock_xpos (mhd_data_parallel.f90:1988-2006) + inject_particles_at_shock
+ * (particle_module.f90:542-633; `-is 1`, config/shock.sh).  Needs time_interp = 1 and both
+ * frames uploaded: at rt = 0 the reference's swapped time weights select the LATER frame's
+ * shock positions.  The reference accumulates into uninitialised sx1/sx2 in 2-D/3-D
+ * (mhd_data_parallel.f90:2037-2049); here they start at zero.  Everything else is kept as
+ * written (rz from dpy, weights that do not sum to one, t = frame time, the 0.75 envelope). */
+int gpat_inject_at_shock(gpat_handle h, int64_t nptl, double dt, int dist_flag, double particle_v0,
+                         double t_frame, double power_index);
 
 /* ---- particle tracking ---------------------------------------------------
  * The second run of the reference's two-run workflow (docs/source/development/

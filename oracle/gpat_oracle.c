@@ -1427,6 +1427,127 @@ void orc_inject_uniform(orc_sim* S, int64_t nptl, double dt, int dist_flag, doub
 }
 
 /* ------------------------------------------------------------------------ */
+/* shock injection: locate_shock_xpos (MD:1988-2006), interp_shock_location   */
+/* (MD:2022-2045), inject_particles_at_shock (PM:542-633).                    */
+/* The reference never zeroes sx1/sx2 in 2-D/3-D (MD:2037-2049: `sx1 = sx1 +`  */
+/* on uninitialised locals) -- undefined there; HERE THEY START AT ZERO, the   */
+/* value a fresh stack frame usually holds.  Everything else is kept as        */
+/* written: the time weights are swapped (`sx2*(1-rt) + sx1*rt`, so rt = 0     */
+/* picks the LATER frame), rz is computed from dpy (PM:581), the weights of    */
+/* the two rows therefore do not sum to one, and t is the frame time itself.   */
+/* ------------------------------------------------------------------------ */
+static void locate_shock_xpos(const orc_sim* S, const float* fa, int32_t* out)
+{
+    for (int k = 0; k < S->nzg; ++k)
+        for (int j = 0; j < S->nyg; ++j) {
+            float best = -1.0f;
+            int at = 1; /* maxloc returns the FIRST maximum, 1-based along the ghosted x extent */
+            for (int i = 0; i < S->nxg; ++i) {
+                float v = fabsf(fa[FIDX(S, NFIELDS + 0, i, j, k)]);
+                if (v > best) { best = v; at = i + 1; }
+            }
+            out[j + (size_t)S->nyg * k] = at;
+        }
+}
+
+int64_t orc_inject_at_shock(orc_sim* S, int64_t nptl, double dt, int dist_flag, double particle_v0,
+                            double t_frame, double power_index)
+{
+    const gpat_params* P = &S->P;
+    const double mu_max = (double)0.99f;
+    const double xmin = P->xmin, xmax = P->xmax, ymin = P->ymin, ymax = P->ymax;
+    const double zmin = P->zmin, zmax = P->zmax;
+    const int nxg_f = P->nx + 4; /* fconfig%nxg, SS:176 */
+    int32_t* sx2map = (int32_t*)malloc(sizeof(int32_t) * (size_t)S->nyg * S->nzg);
+    locate_shock_xpos(S, S->farray2, sx2map); /* only shock_xpos2 survives rt = 0 */
+    S->nptl_inject = nptl;
+    for (int64_t i = 0; i < nptl; ++i) {
+        S->nptl_current++;
+        if (S->nptl_current > S->nptl_max) S->nptl_current = S->nptl_max;
+        gpat_particle* q = &S->ptls[S->nptl_current - 1];
+        inj_stream st = {S, (uint32_t)S->tag_max, (uint32_t)P->mpi_rank, 0, {0, 0, 0, 0}};
+        memset(q, 0, sizeof(*q));
+        q->y = inj_next(&st) * (ymax - ymin) + ymin;
+        double dpy = q->y / P->dy;
+        int iy = (int)floor(dpy);
+        q->z = inj_next(&st) * (zmax - zmin) + zmin;
+        double dpz = q->z / P->dz;
+        int iz = (int)floor(dpz);
+        double ry = dpy - iy;
+        double rz = dpy - iy; /* PM:581, sic */
+        double w[4] = {(1 - ry) * (1 - rz), ry * (1 - rz), (1 - ry) * rz, ry * rz};
+        double sx1 = 0.0, sx2 = 0.0; /* see the header of this section */
+        if (P->ndim == 1) {
+            sx2 = sx2map[0];
+        } else if (P->ndim == 2) {
+            for (int j = 0; j <= 1; ++j) {
+                int fj = iy + j - 1 + 1; /* Fortran index iy+j-1, lower bound -1 */
+                if (fj < 0) fj = 0;
+                if (fj > S->nyg - 1) fj = S->nyg - 1;
+                sx2 = sx2 + sx2map[fj] * w[j];
+            }
+        } else {
+            for (int k = 0; k <= 1; ++k)
+                for (int j = 0; j <= 1; ++j) {
+                    int fj = iy + j, fk = iz + k;
+                    if (fj < 0) fj = 0;
+                    if (fj > S->nyg - 1) fj = S->nyg - 1;
+                    if (fk < 0) fk = 0;
+                    if (fk > S->nzg - 1) fk = S->nzg - 1;
+                    sx2 = sx2 + sx2map[fj + (size_t)S->nyg * fk] * w[k * 2 + j];
+                }
+        }
+        (void)dpz; (void)iz;
+        double shock_xpos = (sx2 * (1.0 - 0.0) + sx1 * 0.0) + 2; /* two ghost cells */
+        q->x = shock_xpos * (xmax - xmin) / nxg_f;
+        if (dist_flag == 0) { /* PM:588-596: a different Maxwellian envelope than inject_one_particle */
+            double ftest = 1.0, fxp = 0.5, ptmp = 0.0;
+            while (ftest > fxp) {
+                ptmp = (inj_next(&st) * (P->pmax - P->pmin) + P->pmin) / P->p0;
+                fxp = sq(ptmp) * exp(-0.5 * sq(ptmp));
+                ftest = inj_next(&st) * (double)0.75f;
+            }
+            q->p = ptmp * P->p0;
+        } else if (dist_flag == 1) {
+            q->p = P->p0;
+        } else if (dist_flag == 2) {
+            double r01 = inj_next(&st);
+            if ((int)power_index == 1) {
+                q->p = pow(P->pmax / P->p0, r01) * P->p0;
+            } else {
+                double norm = pow(P->pmax, -power_index + 1) - pow(P->p0, -power_index + 1);
+                q->p = pow(r01 * norm + pow(P->p0, -power_index + 1), 1.0 / (-power_index + 1));
+            }
+        }
+        q->v = particle_v0 * q->p / P->p0;
+        q->mu = mu_max * (2.0 * inj_next(&st) - 1.0);
+        q->weight = 1.0;
+        q->t = t_frame;
+        q->dt = dt;
+        q->split_times = 0;
+        q->count_flag = GPAT_COUNT_FLAG_INBOX;
+        q->origin = P->mpi_rank;
+        q->nsteps_tracked = 0;
+        q->nsteps_pushed = 0;
+        q->tag_injected = (int32_t)S->tag_max;
+        S->tag_max++;
+        q->tag_splitted = 1;
+        set_rng_step(q, 0);
+        if (S->track_particle_flag) {
+            int64_t lo, hi;
+            if (is_particle_selected(S, q, &lo, &hi)) {
+                q->nsteps_tracked = 1;
+                q->tag_injected = -q->tag_injected;
+                q->tag_splitted = -1;
+                record_tracked(S, q, lo, hi);
+            }
+        }
+    }
+    free(sx2map);
+    return nptl;
+}
+
+/* ------------------------------------------------------------------------ */
 /* targeted injection: inject_particles_at_large_jz / _absj / _divv / _rho    */
 /* (PM:785-905, 919-1061, 1250-1341, 1356-1468) with the cell counters        */
 /* get_ncells_large_* (MD:2211-2261, 2269-2335, 2385-2455, 2463-2498),        */

@@ -119,6 +119,11 @@ class Oracle:
                                             C.c_double(vmin), C.c_int64(ncells_norm))
         return int(ninj), int(ncells)
 
+    def inject_at_shock(self, nptl, dt, dist_flag, particle_v0, t_frame, power_index):
+        self.lib.orc_inject_at_shock.restype = C.c_int64
+        self.lib.orc_inject_at_shock(self.h, C.c_int64(nptl), C.c_double(dt), C.c_int(dist_flag),
+                                     C.c_double(particle_v0), C.c_double(t_frame), C.c_double(power_index))
+
     def particle_mover(self, t0, dtf, nsteps_interval=100, num_fine_steps=1,
                        dump_escaped_dist=0) -> int:
         steps = C.c_uint64(0)

@@ -129,6 +129,8 @@ SIGNATURES = {
     "gpat_inject_targeted": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_int, C.c_double,
                                        C.c_double, C.c_double, _DP, C.c_double, C.c_int, C.c_double,
                                        C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "gpat_inject_at_shock": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_double, C.c_double,
+                                       C.c_double]),
     "gpat_init_tracking": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int]),
     "gpat_tracked_shape": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "gpat_download_tracked": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -117,6 +117,7 @@ struct gpat_sim {
     int pf_nvar = 0;
     // particle tracking (gpat_init_tracking)
     TrackDev trk{};
+    int* d_shock = nullptr;  // shock_xpos2 (gpat_inject_at_shock)
     int* d_tags = nullptr;
     gpat_particle* d_tracked = nullptr;
     const void* registered_host[2] = {nullptr, nullptr};
@@ -588,7 +589,7 @@ int gpat_finalize(gpat_handle h)
         if (h->registered_host[i]) cudaHostUnregister(const_cast<void*>(h->registered_host[i]));
     void* ptrs[] = {h->ptl_mem, h->esc_mem, h->d_counters, h->d_nptl_split, h->d_leak, h->d_queue,
                     h->w.tile_counts, h->w.tile_offsets, h->idx_a, h->idx_b, h->fld, h->stage, h->stage2,
-                    h->d_tags, h->d_tracked,
+                    h->d_tags, h->d_tracked, h->d_shock,
                     h->d_fglobal, h->d_flocal[0], h->d_flocal[1], h->d_flocal[2], h->d_flocal[3],
                     h->d_fesc, h->d_pthr, h->d_sums, h->d_minmax, h->d_quick, h->d_table, h->d_aos};
     for (void* p : ptrs)
@@ -752,6 +753,34 @@ int gpat_inject_targeted(gpat_handle h, int mode, int64_t nptl, double dt, int d
             return fail(h, GPAT_ERR_STATE, "gpat_inject_targeted: a rejection loop did not find an admissible "
                                            "position in 2^22 draws (the reference would spin forever)");
     }
+    return GPAT_OK;
+}
+
+int gpat_inject_at_shock(gpat_handle h, int64_t nptl, double dt, int dist_flag, double particle_v0, double t_frame,
+                         double power_index)
+{
+    if (!h || nptl < 0) return fail(h, GPAT_ERR_INVALID, "gpat_inject_at_shock: bad arguments");
+    if (dist_flag < 0 || dist_flag > 2) return fail(h, GPAT_ERR_INVALID, "gpat_inject_at_shock: dist_flag must be 0, 1 or 2");
+    if (!h->dp.time_interp || !h->have_field[1])
+        return fail(h, GPAT_ERR_STATE, "gpat_inject_at_shock: needs time_interp = 1 and farray2 (shock_xpos2 is what "
+                                       "interp_shock_location reads at rt = 0)");
+    CU(cudaSetDevice(h->device));
+    const int nyr = (h->dp.ndim > 1) ? h->dp.ny + 4 : 1, nzr = (h->dp.ndim > 2) ? h->dp.nz + 4 : 1;
+    if (!h->d_shock) CU(cudaMalloc(&h->d_shock, (size_t)nyr * nzr * sizeof(int)));
+    CU(cudaEventRecord(h->ev[2], h->st));
+    launch_shock_xpos(h->dp, h->layout, h->fld, h->sel ^ 1, h->d_shock, h->st);  // farray2
+    const double box[6] = {0, 0, 0, 0, 0, 0};
+    launch_inject(h->dp, h->P, nptl, h->nptl_current, h->nptl_max, h->tag_max, dt, dist_flag, particle_v0, t_frame,
+                  0.0, box, power_index, h->st, GPAT_INJECT_AT_SHOCK, 0.0, h->layout, h->fld, h->sel, nullptr, &h->trk,
+                  h->d_shock);
+    h->tm.total_launches += 2;
+    CU(cudaEventRecord(h->ev[3], h->st));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->st));
+    h->tm.inject_ms = elapsed(h->ev[2], h->ev[3]);
+    h->nptl_current += nptl;
+    if (h->nptl_current > h->nptl_max) h->nptl_current = h->nptl_max;
+    h->tag_max += nptl;
     return GPAT_OK;
 }
 

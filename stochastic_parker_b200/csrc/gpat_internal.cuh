@@ -236,7 +236,8 @@ void launch_inject(const DevParams& prm, const PtlSoA& P, long long n, long long
                    double t_frame, double dt_mhd, const double box[6], double power_index,
                    cudaStream_t st, int mode = 0, double vmin = 0.0, int layout = 0,
                    const float* fld = nullptr, int sel = 0, int* fail = nullptr,
-                   const TrackDev* trk = nullptr);
+                   const TrackDev* trk = nullptr, const int* shock_x = nullptr);
+void launch_shock_xpos(const DevParams& prm, int layout, const float* fld, int half, int* d_out, cudaStream_t st);
 void launch_ncells(const DevParams& prm, int layout, const float* fld, int sel, int mode, double vmin,
                    const double box[6], unsigned long long* d_count, int sm_count, cudaStream_t st);
 void launch_remove(const PtlSoA& P, const PtlSoA& E, long long ecap, long long n, long long* counters,

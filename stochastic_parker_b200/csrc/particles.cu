@@ -71,6 +71,7 @@ struct InjectArgs {
     int pos[10];         // packed position of dbx_dy dbx_dz dby_dx dby_dz dbz_dx dbz_dy dvx_dx dvy_dy dvz_dz rho (-1: absent = 0)
     int* fail;           // set when a rejection loop hits kMaxTrials
     TrackDev trk;        // particle tracking (particle_module.f90:434-440)
+    const int* shock_x;  // mode GPAT_INJECT_AT_SHOCK: shock_xpos2(nyg, nzg), locate_shock_xpos
 };
 
 constexpr int kMaxTrials = 1 << 22;  // the reference's loop is unbounded; a kernel must end
@@ -159,7 +160,37 @@ __global__ void inject_kernel(const __grid_constant__ DevParams prm, const PtlSo
     const double mu_max = (double)0.99f;  // particle_module.f90:121
     // no contraction here: these are parity-checked bit for bit against the oracle
     double x, y, z;
-    if (a.mode == 0) {
+    if (a.mode == GPAT_INJECT_AT_SHOCK) {
+        // inject_particles_at_shock (particle_module.f90:570-587), kept as written: rz from dpy, time
+        // weights swapped (rt = 0 picks shock_xpos2), two ghost cells added to the index, scaled by
+        // (xmax - xmin)/nxg.  sx2 starts at zero here (uninitialised in the reference, see the header).
+        y = __dadd_rn(__dmul_rn(s.next(), prm.ymax - prm.ymin), prm.ymin);
+        const double dpy = __ddiv_rn(y, prm.dy);
+        const int iy = (int)floor(dpy);
+        z = __dadd_rn(__dmul_rn(s.next(), prm.zmax - prm.zmin), prm.zmin);
+        const int iz = (int)floor(__ddiv_rn(z, prm.dz));
+        const double ry = __dsub_rn(dpy, (double)iy), rz = ry;
+        const double w[4] = {__dmul_rn(__dsub_rn(1.0, ry), __dsub_rn(1.0, rz)), __dmul_rn(ry, __dsub_rn(1.0, rz)),
+                             __dmul_rn(__dsub_rn(1.0, ry), rz), __dmul_rn(ry, rz)};
+        double sx2 = 0.0;
+        const int nyr = (prm.ndim > 1) ? prm.ny + 4 : 1, nzr = (prm.ndim > 2) ? prm.nz + 4 : 1;
+        if (prm.ndim == 1) {
+            sx2 = (double)a.shock_x[0];
+        } else if (prm.ndim == 2) {
+            for (int j = 0; j <= 1; ++j) {
+                const int fj = min(max(iy + j, 0), nyr - 1);
+                sx2 = __dadd_rn(sx2, __dmul_rn((double)a.shock_x[fj], w[j]));
+            }
+        } else {
+            for (int k = 0; k <= 1; ++k)
+                for (int j = 0; j <= 1; ++j) {
+                    const int fj = min(max(iy + j, 0), nyr - 1), fk = min(max(iz + k, 0), nzr - 1);
+                    sx2 = __dadd_rn(sx2, __dmul_rn((double)a.shock_x[fj + (long long)nyr * fk], w[k * 2 + j]));
+                }
+        }
+        const double shock_xpos = __dadd_rn(sx2, 2.0);
+        x = __ddiv_rn(__dmul_rn(shock_xpos, prm.xmax - prm.xmin), (double)(prm.nx + 4));
+    } else if (a.mode == 0) {
         x = __dadd_rn(__dmul_rn(s.next(), a.box[3] - a.box[0]), a.box[0]);
         y = __dadd_rn(__dmul_rn(s.next(), a.box[4] - a.box[1]), a.box[1]);
         z = __dadd_rn(__dmul_rn(s.next(), a.box[5] - a.box[2]), a.box[2]);
@@ -182,15 +213,18 @@ __global__ void inject_kernel(const __grid_constant__ DevParams prm, const PtlSo
                 crit = divv ? 3.0 : (rho ? 0.0 : -3.0);
         }
     }
-    double mu = __dmul_rn(mu_max, __dsub_rn(__dmul_rn(2.0, s.next()), 1.0));
+    const bool shock = (a.mode == GPAT_INJECT_AT_SHOCK);
+    // the shock injector draws mu AFTER the momentum (particle_module.f90:611), the others before
+    double mu = 0.0;
+    if (!shock) mu = __dmul_rn(mu_max, __dsub_rn(__dmul_rn(2.0, s.next()), 1.0));
     double p;
-    if (a.dist_flag == 0) {  // particle_module.f90:399-407
+    if (a.dist_flag == 0) {  // particle_module.f90:399-407 / 588-596 (shock: another envelope)
         double ftest = 1.0, fxp = 0.5, ptmp = 0.0;
         while (ftest > fxp) {
             ptmp = __ddiv_rn(__dadd_rn(__dmul_rn(s.next(), prm.pmax - prm.pmin), prm.pmin), prm.p0);
             double p2 = __dmul_rn(ptmp, ptmp);
-            fxp = __dmul_rn(p2, exp(-p2));
-            ftest = __dmul_rn(s.next(), (double)0.37f);
+            fxp = shock ? __dmul_rn(p2, exp(__dmul_rn(-0.5, p2))) : __dmul_rn(p2, exp(-p2));
+            ftest = __dmul_rn(s.next(), shock ? (double)0.75f : (double)0.37f);
         }
         p = __dmul_rn(ptmp, prm.p0);
     } else if (a.dist_flag == 2) {  // particle_module.f90:410-418
@@ -207,9 +241,10 @@ __global__ void inject_kernel(const __grid_constant__ DevParams prm, const PtlSo
     }
     P.x[slot] = x; P.y[slot] = y; P.z[slot] = z; P.p[slot] = p;
     P.v[slot] = __ddiv_rn(__dmul_rn(a.particle_v0, p), prm.p0);
-    P.mu[slot] = mu;
     P.weight[slot] = 1.0;
-    P.t[slot] = __dadd_rn(a.t_frame, __dmul_rn(s.next(), a.dt_mhd));
+    if (shock) mu = __dmul_rn(mu_max, __dsub_rn(__dmul_rn(2.0, s.next()), 1.0));
+    P.mu[slot] = mu;
+    P.t[slot] = shock ? a.t_frame : __dadd_rn(a.t_frame, __dmul_rn(s.next(), a.dt_mhd));  // particle_module.f90:613
     P.dt[slot] = a.dt;
     P.rng[slot] = 0ull;
     P.split_times[slot] = 0;
@@ -290,6 +325,41 @@ __global__ void ncells_kernel(const __grid_constant__ DevParams prm, const __gri
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(count, mine);
 }
 
+// locate_shock_xpos (mhd_data_parallel.f90:1988-2006): maxloc(abs(farray(nfields+1, :, j, k)), dim=1)
+// for every row of the ghosted extent; one warp per row, first maximum wins.
+__global__ void shock_xpos_kernel(const __grid_constant__ DevParams prm, const float* __restrict__ fld, int nrec,
+                                  int half, int pos, int nyr, int nzr, int* __restrict__ out)
+{
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= nyr * nzr) return;
+    const int j = row % nyr, k = row / nyr;
+    float best = -1.0f;
+    int at = 1;
+    for (int i = lane; i < prm.nxg; i += 32) {
+        const long long cell = ((long long)k * prm.nyg + j) * prm.nxg + i;
+        const float v = fabsf(rec_get(fld, cell, nrec, half, pos));
+        if (v > best) { best = v; at = i + 1; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_down_sync(0xffffffffu, best, o);
+        const int oa = __shfl_down_sync(0xffffffffu, at, o);
+        if (ob > best || (ob == best && oa < at)) { best = ob; at = oa; }
+    }
+    if (lane == 0) out[row] = at;
+}
+
+void launch_shock_xpos(const DevParams& prm, int layout, const float* fld, int half, int* d_out, cudaStream_t st)
+{
+    const int nrec = nrec_of(layout);
+    int pos = -1;
+    for (int k = 0; k < nrec; ++k)
+        if (slot_of(layout, k) == 8 + 1) pos = k;  // dvx_dx
+    const int nyr = (prm.ndim > 1) ? prm.ny + 4 : 1, nzr = (prm.ndim > 2) ? prm.nz + 4 : 1;
+    const int rows = nyr * nzr;
+    shock_xpos_kernel<<<(rows + 3) / 4, 128, 0, st>>>(prm, fld, nrec, half, pos, nyr, nzr, d_out);
+}
+
 static void fill_target(InjectArgs& a, const DevParams& prm, int layout, const float* fld, int sel,
                         int mode, double vmin, const double box[6], int* fail)
 {
@@ -318,12 +388,14 @@ void launch_inject(const DevParams& prm, const PtlSoA& P, long long n, long long
                    long long nptl_max, long long tag0, double dt, int dist_flag, double particle_v0,
                    double t_frame, double dt_mhd, const double box[6], double power_index,
                    cudaStream_t st, int mode, double vmin, int layout, const float* fld, int sel, int* fail,
-                   const TrackDev* trk)
+                   const TrackDev* trk, const int* shock_x)
 {
     if (n <= 0) return;
     InjectArgs a{};
     if (trk) a.trk = *trk;
-    if (mode != 0) fill_target(a, prm, layout, fld, sel, mode, vmin, box, fail);
+    a.shock_x = shock_x;
+    if (mode == GPAT_INJECT_AT_SHOCK) a.mode = mode;
+    if (mode != 0 && mode != GPAT_INJECT_AT_SHOCK) fill_target(a, prm, layout, fld, sel, mode, vmin, box, fail);
     a.n = n; a.start = start; a.nptl_max = nptl_max; a.tag0 = tag0; a.dt = dt;
     a.particle_v0 = particle_v0; a.t_frame = t_frame; a.dt_mhd = dt_mhd;
     a.power_index = power_index; a.dist_flag = dist_flag;

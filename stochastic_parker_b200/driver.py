@@ -120,6 +120,11 @@ class GpatSim:
                  "gpat_inject_targeted")
         return ninj.value, ncells.value
 
+    def inject_at_shock(self, nptl, dt, dist_flag, particle_v0, t_frame, power_index):
+        """locate_shock_xpos + inject_particles_at_shock (mhd_data_parallel.f90:1988, particle_module.f90:542)."""
+        self._ck(self.lib.gpat_inject_at_shock(self.h, nptl, dt, dist_flag, particle_v0, t_frame, power_index),
+                 "gpat_inject_at_shock")
+
     # ---- particle tracking ----------------------------------------------------
     def init_tracking(self, tags: np.ndarray, nsteps_interval: int):
         """init_particle_tracking (particle_module.f90:5825-5879); tags: (nptl_tracking, split_times_max+2)
@@ -279,7 +284,9 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
         sim.upload_fields(1 if P.time_interp else 0, get(tf))
         t0, dtf = tstamps[tf - 1], tstamps[tf] - tstamps[tf - 1]
         if (tf == 1 or inject_new_ptl) and tf <= tmax_to_inject:   # :462-485
-            if inject_mode:                                    # :464-480 (inject_large_jz ... _rho)
+            if inject_mode == 6:                               # :451-454 inject_at_shock
+                sim.inject_at_shock(nptl, dt_inject, dist_flag, particle_v0, t0, power_index)
+            elif inject_mode:                                  # :464-480 (inject_large_jz ... _rho)
                 sim.inject_targeted(inject_mode, nptl, dt_inject, dist_flag, particle_v0, t0, dtf, part_box,
                                     power_index, inject_same_nptl, inject_min, ncells_norm)
             else:

@@ -588,3 +588,25 @@ def test_focused_transport_2d_intervals_fill_the_pitch_angle_bins():
     fg = res[-1]["fglobal"]                       # (npp, nmu)
     assert fg.shape[1] == P.nmu_global and np.count_nonzero(fg.sum(axis=0)) > P.nmu_global // 2
     assert abs(fg.sum() - ptl["weight"][(ptl["p"] > P.pmin) & (ptl["p"] <= P.pmax)].sum()) < 1e-9
+
+
+# ---- shock injection (mhd_data_parallel.f90:1988-2045, particle_module.f90:542-633) --------------
+def test_shock_injection_lands_on_the_later_frames_compression_peak():
+    w, P, frames, ts = make_case("c3", grid=64, nptl=8)
+    o = Oracle(P, 4000)
+    o.upload_fields(0, frames[0])
+    o.upload_fields(1, frames[1])
+    o.inject_at_shock(1500, 1e-5, 0, w.particle_v0, ts[0], 6.2)
+    ptl = o.download_particles()
+    assert len(ptl) == 1500 and np.all(ptl["t"] == ts[0]) and np.all(ptl["dt"] == 1e-5)
+    # locate_shock_xpos: 1-based index of max |dvx/dx| along the ghosted x extent, per row of farray2
+    fa2 = o.get_fields(1).reshape(P.ny + 4, P.nx + 4, 32)
+    sx = np.argmax(np.abs(fa2[..., 8]), axis=1) + 1
+    iy = np.floor(ptl["y"] / P.dy).astype(int)
+    ry = ptl["y"] / P.dy - iy
+    want = ((sx[iy] * (1 - ry) * (1 - ry) + sx[iy + 1] * ry * (1 - ry)) + 2) * (P.xmax - P.xmin) / (P.nx + 4)
+    assert np.max(np.abs(ptl["x"] - want)) < 1e-12 * P.xmax     # rz = ry: the weights are (1-ry)^2, ry(1-ry)
+    # Maxwellian envelope of the shock injector: f ~ p^2 exp(-p^2/2) in units of p0 peaks at sqrt(2) p0
+    h, edges = np.histogram(ptl["p"] / P.p0, bins=20, range=(0.1, 5.0))
+    assert 1.0 < 0.5 * (edges[np.argmax(h)] + edges[np.argmax(h) + 1]) < 2.0
+    assert np.all(np.abs(ptl["mu"]) <= np.float64(np.float32(0.99)))

@@ -687,3 +687,24 @@ def test_spectra_agree_within_poisson_error_for_independent_streams():
     assert c / dof < 1.0 + 4.0 * np.sqrt(2.0 / dof), (c, dof)
     # and the totals: weight is conserved on both sides
     assert abs(rg[-1]["quick"][2] - ro[-1]["quick"][2]) <= 5.0 * np.sqrt(rg[-1]["quick"][2] + 1)
+
+
+@pytest.mark.parametrize("key,grid,dist_flag", [("c3", 64, 0), ("c1", 48, 1), ("c5", 32, 2)])
+def test_shock_injection_parity(key, grid, dist_flag):
+    """locate_shock_xpos + inject_particles_at_shock (mhd_data_parallel.f90:1988-2045,
+    particle_module.f90:542-633; `-is 1` of config/shock.sh): shock positions, interpolation with
+    the reference's weights, momentum envelope and random stream, bit for bit."""
+    w, P, frames, ts = make_case(key, grid=grid, nptl=8)
+    g, o = pair(P, 5000)
+    load_fields((g, o), frames, True)
+    for s in (g, o):
+        s.inject_at_shock(2000, 1e-5, dist_flag, w.particle_v0, ts[0], 6.2)
+        s.inject_at_shock(1500, 1e-5, dist_flag, w.particle_v0, ts[1], 6.2)
+    a, b = g.download_particles(), o.download_particles()
+    assert len(a) == len(b) == 3500
+    if dist_flag == 1:
+        assert_particles_identical(a, b, "shock injection")
+    else:
+        assert np.array_equal(a["x"], b["x"]) and np.array_equal(a["y"], b["y"]) and np.array_equal(a["tag_injected"], b["tag_injected"])
+        assert_particles_close(a, b, 1e-13, f"shock injection dist_flag={dist_flag}", frac_outliers=0.002)
+    g.close()
