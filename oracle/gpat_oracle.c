@@ -53,6 +53,9 @@ typedef struct orc_sim {
     const double* rng_table;  /* optional uniform table */
     int64_t rng_slots, rng_max_steps;
     uint64_t steps;           /* push_particle_* calls */
+    /* ORC_RNG_MT19937: one sequential MT19937 like the reference's thread-0 stream (RNG:28-101) */
+    uint32_t mt[624];
+    int mti;
     /* particle tracking, PM:144-150 */
     int track_particle_flag;
     int split_times_max;
@@ -101,10 +104,76 @@ static inline uint64_t get_rng_step(const gpat_particle* p)
 }
 static inline void set_rng_step(gpat_particle* p, uint64_t s) { memcpy(&p->padding, &s, 8); }
 
+/* ------------------------------------------------------------------------ */
+/* MT19937 (Matsumoto & Nishimura 1998, init_by_array + genrand_int32),       */
+/* written from the published algorithm.  ORC_RNG_MT19937 is an ORACLE-ONLY   */
+/* mode: a single sequential stream seeded like random_number_generator.f90   */
+/* seeds mt_stream (iseeda = Z'123',Z'234',Z'345',Z'456', RNG:16,38) and       */
+/* mapped to [0,1] with 32-bit resolution (genrand_real1).  It is NOT claimed */
+/* to equal mt_stream's jump-ahead sub-streams; it exists so that the GPU's   */
+/* Philox statistics can be compared with a run driven by the reference's     */
+/* generator family (tests: Poisson agreement).  Serial: one thread.          */
+/* ------------------------------------------------------------------------ */
+#define ORC_RNG_MT19937 2
+static void mt_init_genrand(orc_sim* S, uint32_t s)
+{
+    S->mt[0] = s;
+    for (S->mti = 1; S->mti < 624; S->mti++)
+        S->mt[S->mti] = 1812433253u * (S->mt[S->mti - 1] ^ (S->mt[S->mti - 1] >> 30)) + (uint32_t)S->mti;
+}
+static void mt_init_by_array(orc_sim* S, const uint32_t* key, int klen)
+{
+    mt_init_genrand(S, 19650218u);
+    int i = 1, j = 0;
+    for (int k = (624 > klen ? 624 : klen); k; k--) {
+        S->mt[i] = (S->mt[i] ^ ((S->mt[i - 1] ^ (S->mt[i - 1] >> 30)) * 1664525u)) + key[j] + (uint32_t)j;
+        i++; j++;
+        if (i >= 624) { S->mt[0] = S->mt[623]; i = 1; }
+        if (j >= klen) j = 0;
+    }
+    for (int k = 623; k; k--) {
+        S->mt[i] = (S->mt[i] ^ ((S->mt[i - 1] ^ (S->mt[i - 1] >> 30)) * 1566083941u)) - (uint32_t)i;
+        i++;
+        if (i >= 624) { S->mt[0] = S->mt[623]; i = 1; }
+    }
+    S->mt[0] = 0x80000000u;
+}
+static uint32_t mt_genrand_int32(orc_sim* S)
+{
+    static const uint32_t mag01[2] = {0x0u, 0x9908b0dfu};
+    uint32_t y;
+    if (S->mti >= 624) {
+        int kk;
+        for (kk = 0; kk < 624 - 397; kk++) {
+            y = (S->mt[kk] & 0x80000000u) | (S->mt[kk + 1] & 0x7fffffffu);
+            S->mt[kk] = S->mt[kk + 397] ^ (y >> 1) ^ mag01[y & 1u];
+        }
+        for (; kk < 623; kk++) {
+            y = (S->mt[kk] & 0x80000000u) | (S->mt[kk + 1] & 0x7fffffffu);
+            S->mt[kk] = S->mt[kk + (397 - 624)] ^ (y >> 1) ^ mag01[y & 1u];
+        }
+        y = (S->mt[623] & 0x80000000u) | (S->mt[0] & 0x7fffffffu);
+        S->mt[623] = S->mt[396] ^ (y >> 1) ^ mag01[y & 1u];
+        S->mti = 0;
+    }
+    y = S->mt[S->mti++];
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= (y >> 18);
+    return y;
+}
+uint32_t orc_mt19937_next(orc_sim* S) { return mt_genrand_int32(S); }
+
 /* Four uniforms of one push step: ran1, ran2, ran3, ran_p (PM:3548-3550,3589). */
 static void step_uniforms(const orc_sim* S, const gpat_particle* ptl, double u[4])
 {
     uint64_t step = get_rng_step(ptl);
+    if (S->P.rng_mode == ORC_RNG_MT19937) {
+        orc_sim* W = (orc_sim*)S; /* the generator state advances */
+        for (int j = 0; j < 4; ++j) u[j] = u01(mt_genrand_int32(W));
+        return;
+    }
     if (S->P.rng_mode == GPAT_RNG_TABLE && S->rng_table) {
         int64_t slot = abs(ptl->tag_injected);
         if (slot >= S->rng_slots || (int64_t)step >= S->rng_max_steps) {
@@ -136,6 +205,7 @@ typedef struct inj_stream {
 
 static double inj_next(inj_stream* s)
 {
+    if (s->S->P.rng_mode == ORC_RNG_MT19937) return u01(mt_genrand_int32((orc_sim*)s->S));
     if ((s->k & 3u) == 0) {
         uint32_t ctr[4] = {s->k >> 2, 0u, s->tag, 0u};
         uint32_t key[2] = {(uint32_t)s->S->P.seed, (uint32_t)(s->S->P.seed >> 32) + s->origin};
@@ -174,6 +244,10 @@ orc_sim* orc_create(const gpat_params* p, int64_t nptl_max)
     S->nptl_escaped_max = nptl_max;
     S->escaped = (gpat_particle*)calloc((size_t)nptl_max + 1, sizeof(gpat_particle));
     set_neighbors(S);
+    {
+        const uint32_t iseeda[4] = {0x123u, 0x234u, 0x345u, 0x456u}; /* RNG:16 */
+        mt_init_by_array(S, iseeda, 4);
+    }
     return S;
 }
 
@@ -1103,7 +1177,7 @@ static void particle_mover_one_cycle(orc_sim* S, double t0, double dtf, int nste
     const double e[6] = {P->xmin - P->dx * 0.5, P->xmax + P->dx * 0.5, P->ymin - P->dy * 0.5,
                          P->ymax + P->dy * 0.5, P->zmin - P->dz * 0.5, P->zmax + P->dz * 0.5};
     uint64_t steps = 0;
-#pragma omp parallel for schedule(dynamic, 64) reduction(+ : steps)
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : steps) if (S->P.rng_mode != ORC_RNG_MT19937)
     for (int64_t i = S->nptl_old; i < S->nptl_current; ++i) {
         gpat_particle ptl = S->ptls[i];
         double deltax = 0.0, deltay = 0.0, deltaz = 0.0, deltap = 0.0, deltav = 0.0, deltamu = 0.0;
@@ -1241,7 +1315,7 @@ void orc_debug_push_n(orc_sim* S, double t0, double dtf, int nsteps, uint64_t* s
                          P->ymax + P->dy * 0.5, P->zmin - P->dz * 0.5, P->zmax + P->dz * 0.5};
     set_dt_min_max(S, dtf);
     uint64_t steps = 0;
-#pragma omp parallel for schedule(dynamic, 64) reduction(+ : steps)
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : steps) if (S->P.rng_mode != ORC_RNG_MT19937)
     for (int64_t i = 0; i < S->nptl_current; ++i) {
         gpat_particle ptl = S->ptls[i];
         double dx_, dy_, dz_ = 0.0, dp_, dv_ = 0.0, dmu_ = 0.0;

@@ -610,3 +610,16 @@ def test_shock_injection_lands_on_the_later_frames_compression_peak():
     h, edges = np.histogram(ptl["p"] / P.p0, bins=20, range=(0.1, 5.0))
     assert 1.0 < 0.5 * (edges[np.argmax(h)] + edges[np.argmax(h) + 1]) < 2.0
     assert np.all(np.abs(ptl["mu"]) <= np.float64(np.float32(0.99)))
+
+
+# ---- MT19937 stand-in stream (oracle only) ---------------------------------------------------------
+def test_mt19937_known_answers():
+    """mt19937ar.c's published test output for init_by_array({0x123, 0x234, 0x345, 0x456}) -- the very
+    seed array random_number_generator.f90:16 hands to mt_stream -- starts 1067595299 955945823
+    477289528 4107218783 4228976476."""
+    import ctypes as C
+    w, P, _, _ = make_case("c1", grid=16, nptl=8)
+    o = Oracle(P, 16)
+    o.lib.orc_mt19937_next.restype = C.c_uint32
+    got = [o.lib.orc_mt19937_next(o.h) for _ in range(5)]
+    assert got == [1067595299, 955945823, 477289528, 4107218783, 4228976476]

@@ -653,8 +653,9 @@ def test_tracking_run_replays_and_matches_the_oracle(strict):
 
 def test_spectra_agree_within_poisson_error_for_independent_streams():
     """north_star's second bar: with on-device Philox, spectra and spatial distributions agree with
-    the reference path within Poisson statistical error.  The production build runs with one seed,
-    the oracle with another (independent streams, nothing shared but the physics); unit weights
+    the reference path within Poisson statistical error.  The production build draws from per-particle
+    Philox streams, the oracle from one sequential MT19937 seeded with the reference's own seed array
+    (the generator family behind mt_stream; nothing shared but the physics); unit weights
     (no splitting) make every bin count a Poisson variate, so chi^2/dof of the difference ~ 1."""
     w, P, frames, ts = make_case("c1", grid=64, nptl=30000, nframes=3)
     kw = dict(nptl=30000, dist_flag=0, particle_v0=w.particle_v0, inject_new_ptl=False, split_flag=0)
@@ -665,7 +666,7 @@ def test_spectra_agree_within_poisson_error_for_independent_streams():
     rg, _ = run_intervals(g, frames, ts, **kw)
     g.close()
     Po = P.copy()
-    Po.seed = 0x0BADC0DE
+    Po.rng_mode = 2   # oracle-only: one sequential MT19937 seeded like random_number_generator.f90:16,38
     o = Oracle(Po, w.nptl_max)
     ro, _ = run_intervals(o, frames, ts, **kw)
 
