@@ -12,7 +12,7 @@ module gpat_cuda
     private
     public :: gpat_params, gpat_hist_spec, gpat_particle, gpat_counters, gpat_timings
     public :: gpat_init, gpat_set_params, gpat_finalize, gpat_last_error
-    public :: gpat_upload_fields, gpat_prefetch_fields, gpat_swap_fields
+    public :: gpat_upload_fields, gpat_upload_turbulence, gpat_prefetch_fields, gpat_swap_fields
     public :: gpat_inject_uniform, gpat_inject_targeted, gpat_inject_at_shock, gpat_particle_mover, gpat_split
     public :: gpat_init_tracking, gpat_tracked_shape, gpat_download_tracked, gpat_reset_tracked
     public :: gpat_download_particles, gpat_upload_particles
@@ -105,6 +105,14 @@ module gpat_cuda
             type(c_ptr), value :: h, f
             integer(c_int), value :: slot, nvar, with_grad
         end function gpat_upload_fields
+
+        !< read_magnetic_fluctuation / read_correlation_length + their gradient passes
+        !< (mhd_data_parallel.f90:306-497, 771-1604); data = slab array then 2-D array
+        integer(c_int) function gpat_upload_turbulence(h, which, slot, data) bind(C, name="gpat_upload_turbulence")
+            import :: c_ptr, c_int
+            type(c_ptr), value :: h, data
+            integer(c_int), value :: which, slot
+        end function gpat_upload_turbulence
 
         !< frame pipeline: start the H2D copy of a frame already read into farray-shaped host
         !< memory (e.g. frame tf+1 during the push of frame tf); a later gpat_upload_fields with

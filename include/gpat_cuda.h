@@ -120,8 +120,9 @@ typedef struct gpat_params {
     double kperp_kpara;
     double duu0; /* duu_init (set_duu_params, particle_module.f90:279-283): focused transport only */
     /* focused_transport = 1: 2-D Cartesian push_particle_2d_ft only (reference-order build);
-     * the other switches must be 0/false on the GPU path (error otherwise) */
+     * spherical_coord, nonuniform_grid, acc_by_surface must be 0 on the GPU path (error otherwise) */
     int32_t focused_transport, spherical_coord, nonuniform_grid;
+    /* deltab_flag / correlation_flag: turbulence maps via gpat_upload_turbulence */
     int32_t deltab_flag, correlation_flag, acc_by_surface;
     /* diagnostics */
     int32_t npp_global, nmu_global;
@@ -168,6 +169,17 @@ const char* gpat_last_error(gpat_handle h);
  * slot = 0 -> farray1 (frame at t0), 1 -> farray2 (frame at t0 + dtf). */
 int gpat_upload_fields(gpat_handle h, int slot, const float* f, int nvar, int with_grad);
 
+/* Turbulence maps (`-db 1`, `-co 1`).  Replaces read_magnetic_fluctuation + calc_grad_sigma2_slab
+ * + calc_grad_sigma2_2d (which = 0; mhd_data_parallel.f90:306-397, 771-1116) and
+ * read_correlation_length + calc_grad_lc_slab + calc_grad_lc_2d (which = 1; :406-497, 1259-1604):
+ * data holds the slab array followed by the 2-D array, one float per ghosted grid point each --
+ * the content of the reference's deltab_NNNN / lc_NNNN file.  slot as in gpat_upload_fields;
+ * gpat_swap_fields also stands for copy_magnetic_fluctuation / copy_correlation_length
+ * (:1928-1941).  The maps enter kappa (particle_module.f90:2246-2254, 2314-2321, 2505-2517,
+ * 2589-2604), D_mumu (:3143-3148) and inject_large_db2; runs that use them take the
+ * reference-order build of the push kernel. */
+int gpat_upload_turbulence(gpat_handle h, int which, int slot, const float* data);
+
 /* Frame pipeline (stochastic-mhd.f90:401-447 reads frame tf at the top of every iteration,
  * serially).  gpat_prefetch_fields starts the host->device copy of a frame the caller has
  * ALREADY read (e.g. frame tf+1, read while frame tf is being pushed) on a separate copy
@@ -203,8 +215,9 @@ int gpat_inject_uniform(gpat_handle h, int64_t nptl, double dt, int dist_flag,
  *   injection stream until the field interpolated at rt = 0 passes the threshold inside
  *   part_box, then continues like gpat_inject_uniform (mu, momentum, time).
  * nptl_injected / ncells (may be NULL) receive nptl_inject and the cell count.
- * GPAT_INJECT_LARGE_DB2 (inject_particles_at_large_db2, :1075-1236) needs the deltab maps
- * and returns GPAT_ERR_INVALID; GPAT_INJECT_LARGE_RHO needs gpat_params.keep_rho = 1 unless
+ * GPAT_INJECT_LARGE_DB2 (inject_particles_at_large_db2, :1075-1236, get_ncells_large_db2
+ * mhd_data_parallel.f90:2343-2377) needs the deltab maps (gpat_upload_turbulence);
+ * GPAT_INJECT_LARGE_RHO needs gpat_params.keep_rho = 1 unless
  * momentum diffusion already keeps the density slot. */
 #define GPAT_INJECT_LARGE_JZ 1
 #define GPAT_INJECT_LARGE_ABSJ 2

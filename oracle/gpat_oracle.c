@@ -42,6 +42,10 @@ typedef struct orc_sim {
     int nxg, nyg, nzg;        /* array extents with ghosts: nx+4, ny+4, nz+4 | 1 */
     float* farray1;           /* (32, nxg, nyg, nzg), MD:35,82-102 */
     float* farray2;
+    /* sigma2_slab, sigma2_2d, lc_slab, lc_2d (MD:36-41, 107-182): (4 arrays x 4 comps, cells),
+     * comp 0 the value, 1..3 its gradients; allocated lazily, 1.0 everywhere like the reference */
+    float* aux1;
+    float* aux2;
     gpat_particle* ptls;      /* PM:65 */
     gpat_particle* escaped;   /* PM:134 */
     int64_t nptl_current, nptl_old, nptl_max, nptl_split, nptl_inject;
@@ -261,6 +265,7 @@ void orc_destroy(orc_sim* S)
 {
     if (!S) return;
     free(S->farray1); free(S->farray2); free(S->ptls); free(S->escaped);
+    free(S->aux1); free(S->aux2);
     free(S->tags_tracking); free(S->particles_tracked);
     free(S);
 }
@@ -350,15 +355,106 @@ void orc_calc_gradients(orc_sim* S, int slot)
                 }
 }
 
+/* ------------------------------------------------------------------------ */
+/* turbulence maps: read_magnetic_fluctuation / read_correlation_length        */
+/* (MD:306-497: the file holds the slab array then the 2-D array),             */
+/* calc_grad_sigma2_slab/_2d, calc_grad_lc_slab/_2d (MD:771-1604: the same     */
+/* FP32-difference x FP64 0.5/dx arithmetic as the fields)                     */
+/* ------------------------------------------------------------------------ */
+#define NAUX 16
+#define AIDX(S, a, c, i, j, k) ((size_t)((a) * 4 + (c)) + (size_t)NAUX * ((size_t)(i) + (size_t)(S)->nxg * ((size_t)(j) + (size_t)(S)->nyg * (size_t)(k))))
+static float* aux_of(orc_sim* S, int slot)
+{
+    float** pa = slot ? &S->aux2 : &S->aux1;
+    if (!*pa) {
+        size_t n = (size_t)NAUX * S->nxg * S->nyg * S->nzg;
+        *pa = (float*)malloc(n * sizeof(float));
+        for (size_t i = 0; i < n; ++i) (*pa)[i] = 1.0f; /* MD:125-126, 165-166 */
+    }
+    return *pa;
+}
+
+void orc_set_turbulence(orc_sim* S, int which, int slot, const float* data)
+{
+    float* ax = aux_of(S, slot);
+    const int nxg = S->nxg, nyg = S->nyg, nzg = S->nzg;
+    const size_t ncell = (size_t)nxg * nyg * nzg;
+    const double idh[3] = {0.5 / S->P.dx, 0.5 / S->P.dy, 0.5 / S->P.dz};
+    for (int t = 0; t < 2; ++t) { /* slab, then 2-D */
+        const int a = which * 2 + t;
+        const float* src = data + (size_t)t * ncell;
+        for (int k = 0; k < nzg; ++k)
+            for (int j = 0; j < nyg; ++j)
+                for (int i = 0; i < nxg; ++i)
+                    ax[AIDX(S, a, 0, i, j, k)] = src[(size_t)i + (size_t)nxg * ((size_t)j + (size_t)nyg * k)];
+        for (int k = 0; k < nzg; ++k)
+            for (int j = 0; j < nyg; ++j)
+                for (int i = 0; i < nxg; ++i)
+                    for (int d = 0; d < 3; ++d) {
+                        const int n = d == 0 ? nxg : (d == 1 ? nyg : nzg);
+                        const int pos = d == 0 ? i : (d == 1 ? j : k);
+                        if (n <= 1) continue; /* `if (uny > lny)`: the 1.0 fill stays */
+                        int c[3] = {i, j, k};
+#define AV(o) (c[d] = pos + (o), ax[AIDX(S, a, 0, c[0], c[1], c[2])])
+                        float g;
+                        if (pos == 0) {
+                            float p0 = -3.0f * AV(0), p1 = 4.0f * AV(1);
+                            g = (p0 + p1) - AV(2);
+                        } else if (pos == n - 1) {
+                            float p0 = 3.0f * AV(0), p1 = 4.0f * AV(-1);
+                            g = (p0 - p1) + AV(-2);
+                        } else {
+                            float hi = AV(1), lo = AV(-1);
+                            g = hi - lo;
+                        }
+#undef AV
+                        ax[AIDX(S, a, 1 + d, i, j, k)] = (float)((double)g * idh[d]);
+                    }
+    }
+}
+
 void orc_get_fields(const orc_sim* S, int slot, float* out32)
 {
     const float* fa = slot ? S->farray2 : S->farray1;
     memcpy(out32, fa, sizeof(float) * (size_t)NVAR * S->nxg * S->nyg * S->nzg);
 }
 
-void orc_copy_fields(orc_sim* S) /* MD:1920-1923 */
+void orc_copy_fields(orc_sim* S) /* MD:1920-1923; copy_magnetic_fluctuation / _correlation_length MD:1928-1941 */
 {
     memcpy(S->farray1, S->farray2, sizeof(float) * (size_t)NVAR * S->nxg * S->nyg * S->nzg);
+    if (S->aux2) memcpy(aux_of(S, 0), S->aux2, sizeof(float) * (size_t)NAUX * S->nxg * S->nyg * S->nzg);
+}
+
+/* interp_magnetic_fluctuation + interp_correlation_length (MD:1806-1915): 16 values =
+ * db2_slab(1:4), db2_2d(1:4), lc_slab(1:4), lc_2d(1:4) */
+static void interp_aux(const orc_sim* S, const int pos[3], const double w[8], double rt, double out[NAUX])
+{
+    double o2[NAUX];
+    const int ze = (S->P.ndim > 2) ? 1 : 0, ye = (S->P.ndim > 1) ? 1 : 0;
+    for (int v = 0; v < NAUX; ++v) { out[v] = 0.0; o2[v] = 0.0; }
+    for (int k = 0; k <= ze; ++k)
+        for (int j = 0; j <= ye; ++j)
+            for (int i = 0; i <= 1; ++i) {
+                int idx = k * 4 + j * 2 + i;
+                int c0 = pos[0] + 1, c1 = pos[1] + 1, c2 = pos[2] + 1;
+                if (c0 < 0) c0 = 0;
+                if (c0 > S->nxg - 2) c0 = S->nxg - 2;
+                if (c1 < 0) c1 = 0;
+                if (c1 > S->nyg - 2) c1 = S->nyg - 2;
+                if (c2 < 0) c2 = 0;
+                if (c2 > S->nzg - 2) c2 = S->nzg - 2;
+                int ci = c0 + i, cj = (S->P.ndim > 1) ? c1 + j : 0, ck = (S->P.ndim > 2) ? c2 + k : 0;
+                const float* a1 = S->aux1 + AIDX(S, 0, 0, ci, cj, ck);
+                for (int v = 0; v < NAUX; ++v) out[v] = out[v] + (double)a1[v] * w[idx];
+                if (S->P.time_interp) {
+                    const float* a2 = S->aux2 + AIDX(S, 0, 0, ci, cj, ck);
+                    for (int v = 0; v < NAUX; ++v) o2[v] = o2[v] + (double)a2[v] * w[idx];
+                }
+            }
+    if (S->P.time_interp) {
+        double rt1 = 1.0 - rt;
+        for (int v = 0; v < NAUX; ++v) out[v] = out[v] * rt1 + o2[v] * rt;
+    }
 }
 
 /* ------------------------------------------------------------------------ */
@@ -456,8 +552,13 @@ typedef struct kappa_type {
 #define F(n) fields[(n) - 1]           /* fields(n), 1-based */
 #define FG(n) fields[NFIELDS + (n) - 1] /* fields(nfields+n) */
 
+/* aux: db2_slab(1:4) db2_2d(1:4) lc_slab(1:4) lc_2d(1:4) at the particle (interp_aux) */
+#define DB2S(n) aux[(n) - 1]
+#define DB22(n) aux[4 + (n) - 1]
+#define LCS(n) aux[8 + (n) - 1]
+#define LC2(n) aux[12 + (n) - 1]
 static void calc_kappa(const orc_sim* S, const gpat_particle* ptl, const double* fields,
-                       kappa_type* kp)
+                       const double* aux, kappa_type* kp)
 {
     const gpat_params* P = &S->P;
     double bx = F(5), by = F(6), bz = F(7);
@@ -470,6 +571,8 @@ static void calc_kappa(const orc_sim* S, const gpat_particle* ptl, const double*
     kp->knorm_para = 1.0;
     kp->knorm_perp = 1.0;
     if (P->mag_dependency == 1) kp->knorm_para = kp->knorm_para * pow(b, P->gamma_turb - 2.0);
+    if (P->deltab_flag) kp->knorm_para = kp->knorm_para / DB2S(1);                       /* PM:2246-2248 */
+    if (P->correlation_flag) kp->knorm_para = kp->knorm_para * pow(LCS(1), P->gamma_turb - 1.0); /* PM:2252-2254 */
     double knorm;
     if (P->momentum_dependency == 1)
         knorm = kp->knorm_para * pow(ptl->p / P->p0, P->pindex);
@@ -487,6 +590,8 @@ static void calc_kappa(const orc_sim* S, const gpat_particle* ptl, const double*
          * branch never assigns (PM:2274): undefined there, rejected by
          * orc_create_checked / gpat_init here, so dkdx is 0 whenever this line is reached. */
         double dkdx = 0.0;
+        if (P->deltab_flag) dkdx = dkdx - DB2S(2) / DB2S(1);
+        if (P->correlation_flag) dkdx = dkdx + (P->gamma_turb - 1.0) * LCS(2) / LCS(1);
         kp->dkxx_dx = kp->kpara * dkdx; /* not focused transport */
         return;
     }
@@ -506,6 +611,16 @@ static void calc_kappa(const orc_sim* S, const gpat_particle* ptl, const double*
             dkdx = db_dx * ib1 * (P->gamma_turb - 2.0);
             dkdy = db_dy * ib1 * (P->gamma_turb - 2.0);
         }
+    }
+    if (P->deltab_flag) { /* PM:2314-2317, 2364-2367, 2410-2414 */
+        dkdx = dkdx - DB2S(2) / DB2S(1);
+        dkdy = dkdy - DB2S(3) / DB2S(1);
+        if (P->ndim == 3) dkdz = dkdz - DB2S(4) / DB2S(1);
+    }
+    if (P->correlation_flag) { /* PM:2318-2321, 2368-2371, 2415-2419 */
+        dkdx = dkdx + (P->gamma_turb - 1.0) * LCS(2) / LCS(1);
+        dkdy = dkdy + (P->gamma_turb - 1.0) * LCS(3) / LCS(1);
+        if (P->ndim == 3) dkdz = dkdz + (P->gamma_turb - 1.0) * LCS(4) / LCS(1);
     }
     /* PM:2372-2376: the focused-transport equation carries the parallel streaming itself */
     double kpp = P->focused_transport ? -kp->kperp : kp->kpara - kp->kperp;
@@ -539,7 +654,7 @@ static void calc_kappa(const orc_sim* S, const gpat_particle* ptl, const double*
 
 /* NLGC variant, PM:2464-2771 (deltab/correlation flags off) */
 static void calc_kappa_nlgc(const orc_sim* S, const gpat_particle* ptl, const double* fields,
-                            kappa_type* kp)
+                            const double* aux, kappa_type* kp)
 {
     const gpat_params* P = &S->P;
     double bx = F(5), by = F(6), bz = F(7);
@@ -553,6 +668,14 @@ static void calc_kappa_nlgc(const orc_sim* S, const gpat_particle* ptl, const do
     if (P->mag_dependency == 1) {
         kp->knorm_para = kp->knorm_para * pow(b, P->gamma_turb - 2.0);
         kp->knorm_perp = kp->knorm_perp * pow(b, (P->gamma_turb - 2.0) / 3.0);
+    }
+    if (P->deltab_flag) { /* PM:2505-2509 */
+        kp->knorm_para = kp->knorm_para / DB2S(1);
+        kp->knorm_perp = kp->knorm_perp * pow(DB2S(1), -1.0 / 3.0) * pow(DB22(1), 2.0 / 3.0);
+    }
+    if (P->correlation_flag) { /* PM:2513-2517 */
+        kp->knorm_para = kp->knorm_para * pow(LCS(1), P->gamma_turb - 1.0);
+        kp->knorm_perp = kp->knorm_perp * pow(LCS(1), (P->gamma_turb - 1.0) / 3.0) * pow(LC2(1), 2.0 / 3.0);
     }
     double knorm_para, knorm_perp;
     if (P->momentum_dependency == 1) {
@@ -570,6 +693,8 @@ static void calc_kappa_nlgc(const orc_sim* S, const gpat_particle* ptl, const do
 
     if (P->ndim == 1) { /* PM:2535-2562, same uninitialised db_dx with mag_dependency = 1 */
         double dkpara_dx = 0.0;
+        if (P->deltab_flag) dkpara_dx = dkpara_dx - DB2S(2) / DB2S(1);
+        if (P->correlation_flag) dkpara_dx = dkpara_dx + (P->gamma_turb - 1.0) * LCS(2) / LCS(1);
         kp->dkxx_dx = kp->kpara * dkpara_dx;
         return;
     }
@@ -589,6 +714,26 @@ static void calc_kappa_nlgc(const orc_sim* S, const gpat_particle* ptl, const do
         if (P->ndim == 3) {
             dkpara_dz = db_dz * ib1 * (P->gamma_turb - 2.0);
             dkperp_dz = db_dz * ib1 * (P->gamma_turb - 2.0) / 3.0;
+        }
+    }
+    if (P->deltab_flag) { /* PM:2589-2596 and the 2-D+3rd / 3-D twins */
+        dkpara_dx = dkpara_dx - DB2S(2) / DB2S(1);
+        dkpara_dy = dkpara_dy - DB2S(3) / DB2S(1);
+        dkperp_dx = dkperp_dx - DB2S(2) / DB2S(1) / 3.0 + 2.0 * DB22(2) / DB22(1) / 3.0;
+        dkperp_dy = dkperp_dy - DB2S(3) / DB2S(1) / 3.0 + 2.0 * DB22(3) / DB22(1) / 3.0;
+        if (P->ndim == 3) {
+            dkpara_dz = dkpara_dz - DB2S(4) / DB2S(1);
+            dkperp_dz = dkperp_dz - DB2S(4) / DB2S(1) / 3.0 + 2.0 * DB22(4) / DB22(1) / 3.0;
+        }
+    }
+    if (P->correlation_flag) { /* PM:2597-2604 */
+        dkpara_dx = dkpara_dx + (P->gamma_turb - 1.0) * LCS(2) / LCS(1);
+        dkpara_dy = dkpara_dy + (P->gamma_turb - 1.0) * LCS(3) / LCS(1);
+        dkperp_dx = dkperp_dx + (P->gamma_turb - 1.0) * LCS(2) / LCS(1) / 3.0 + 2.0 * LC2(2) / LC2(1) / 3.0;
+        dkperp_dy = dkperp_dy + (P->gamma_turb - 1.0) * LCS(3) / LCS(1) / 3.0 + 2.0 * LC2(3) / LC2(1) / 3.0;
+        if (P->ndim == 3) {
+            dkpara_dz = dkpara_dz + (P->gamma_turb - 1.0) * LCS(4) / LCS(1);
+            dkperp_dz = dkperp_dz + (P->gamma_turb - 1.0) * LCS(4) / LCS(1) / 3.0 + 2.0 * LC2(4) / LC2(1) / 3.0;
         }
     }
     double kpp = P->focused_transport ? -kp->kperp : kp->kpara - kp->kperp; /* PM:2605-2609 */
@@ -829,7 +974,7 @@ static void push_particle_2d(orc_sim* S, gpat_particle* ptl, const double* field
 /* push_particle_2d_ft (PM:3626-3977).  Four uniforms per step: two for the   */
 /* perpendicular displacement, one for p, one for mu (PM:3881-3882, 3918-3921)*/
 /* ------------------------------------------------------------------------ */
-static void calc_duu(const orc_sim* S, const gpat_particle* ptl, double b, double div_bnorm,
+static void calc_duu(const orc_sim* S, const gpat_particle* ptl, double b, const double* aux, double div_bnorm,
                      double divv, double bb_gradv, double bv_gradv, double mu2, double* dmu_dt,
                      double* duu, double* duu_du)
 {
@@ -847,13 +992,15 @@ static void calc_duu(const orc_sim* S, const gpat_particle* ptl, double b, doubl
         *duu_du = 0.0;
     double duu_norm = 1.0;
     if (P->mag_dependency == 1) duu_norm = duu_norm * pow(b, 2.0 - P->gamma_turb);
+    if (P->deltab_flag) duu_norm = duu_norm * DB2S(1);                                        /* PM:3143-3145 */
+    if (P->correlation_flag) duu_norm = duu_norm * pow(LCS(1), (double)1.0f - P->gamma_turb); /* PM:3146-3148 */
     if (P->momentum_dependency == 1) duu_norm = duu_norm * pow(ptl->p / P->p0, P->gamma_turb - 1);
     *duu_du = *duu_du * duu_norm;
     *duu = *duu * duu_norm;
     *dmu_dt = *dmu_dt + *duu_du;
 }
 
-static void push_particle_2d_ft(orc_sim* S, gpat_particle* ptl, const double* fields,
+static void push_particle_2d_ft(orc_sim* S, gpat_particle* ptl, const double* fields, const double* aux,
                                 const kappa_type* kp, int fixed_dt, const double u[4], double* deltax,
                                 double* deltay, double* deltap, double* deltav, double* deltamu)
 {
@@ -907,7 +1054,7 @@ static void push_particle_2d_ft(orc_sim* S, gpat_particle* ptl, const double* fi
     }
     double div_bnorm = -(bx * db_dx + by * db_dy) * ib2;
     double dmu_dt, duu, duu_du;
-    calc_duu(S, ptl, b, div_bnorm, divv, bb_gradv, bv_gradv, mu2, &dmu_dt, &duu, &duu_du);
+    calc_duu(S, ptl, b, aux, div_bnorm, divv, bb_gradv, bv_gradv, mu2, &dmu_dt, &duu, &duu_du);
     if (!fixed_dt) {
         if (dx_dt != 0.0 && dy_dt != 0.0 && dp_dt != 0.0 && dmu_dt != 0.0) {
             double s = (kp->skperp > 0.0) ? kp->skperp : kp->skpara; /* PM:3847-3864 */
@@ -1150,13 +1297,16 @@ static void one_push(orc_sim* S, gpat_particle* ptl, double t0, double dtf, int 
     kappa_type kp;
     get_interp_parameters(S, px, py, pz, pos, w);
     interp_fields(S, pos, w, rt, fields);
+    double aux[NAUX];
+    for (int v = 0; v < NAUX; ++v) aux[v] = 1.0;
+    if (P->deltab_flag || P->correlation_flag) interp_aux(S, pos, w, rt, aux); /* PM:1634-1639 */
     if (P->nlgc)
-        calc_kappa_nlgc(S, ptl, fields, &kp);
+        calc_kappa_nlgc(S, ptl, fields, aux, &kp);
     else
-        calc_kappa(S, ptl, fields, &kp);
+        calc_kappa(S, ptl, fields, aux, &kp);
     step_uniforms(S, ptl, u);
     if (P->focused_transport) /* PM:1647-1668: only the 2-D Cartesian FT pusher is restated */
-        push_particle_2d_ft(S, ptl, fields, &kp, fixed_dt, u, deltax, deltay, deltap, deltav, deltamu);
+        push_particle_2d_ft(S, ptl, fields, aux, &kp, fixed_dt, u, deltax, deltay, deltap, deltav, deltamu);
     else if (P->ndim == 1)
         push_particle_1d(S, ptl, fields, &kp, fixed_dt, u, deltax, deltap);
     else if (P->ndim == 2 && !P->include_3rd_dim)
@@ -1678,6 +1828,9 @@ int64_t orc_ncells_large(const orc_sim* S, int mode, double vmin, const double p
                         if (P->ndim > 2) v = v + (double)fa1(S, NFIELDS + 9, sx, sy, sz);
                     }
                     v = -v;
+                } else if (mode == 3) { /* get_ncells_large_db2, MD:2371: sigma2_slab_1(1, ix, iy, iz) */
+                    int cj = (P->ndim > 1) ? iy + 1 : 0, ck = (P->ndim > 2) ? iz + 1 : 0;
+                    v = (double)S->aux1[AIDX(S, 0, 0, ix + 1, cj, ck)];
                 } else { /* MD:2490 */
                     v = (double)fa1(S, 4, ix, iy, iz);
                 }
@@ -1721,7 +1874,11 @@ int64_t orc_inject_targeted(orc_sim* S, int mode, int64_t nptl, double dt, int d
                 double w[8], fields[NVAR];
                 get_interp_parameters(S, px, py, pz, pos, w);
                 interp_fields(S, pos, w, 0.0, fields);
-                if (mode == 1) {
+                if (mode == 3) { /* PM:1173-1174 */
+                    double ax[NAUX];
+                    interp_aux(S, pos, w, 0.0, ax);
+                    crit = ax[0];
+                } else if (mode == 1) {
                     crit = fabs(FG(16) - FG(14));
                 } else if (mode == 2) {
                     crit = sqrt(sq(FG(18) - FG(20)) + sq(FG(19) - FG(15)) + sq(FG(14) - FG(16)));

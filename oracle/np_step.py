@@ -78,9 +78,11 @@ def interp32(fa1, fa2, P, x, y, t_rel_over_dtf):
     return f1
 
 
-def push_2d(P, F, p, dt_min, dt_max, u, x, y, t, qdrift):
+def push_2d(P, F, p, dt_min, dt_max, u, x, y, t, qdrift, aux=None):
     """One adaptive push_particle_2d.  F: (n, 32) interpolated fields (1-based slot s at F[:, s-1]).
-    u: (n, 4) uniforms.  Returns x, y, p, t, dt after the step."""
+    u: (n, 4) uniforms.  aux: (n, 16) interpolated db2_slab(1:4) db2_2d(1:4) lc_slab(1:4) lc_2d(1:4)
+    when deltab_flag / correlation_flag are set (particle_module.f90:2246-2254, 2364-2371).
+    Returns x, y, p, t, dt after the step."""
     nf = NFIELDS
     bx, by, bz = F[:, 4], F[:, 5], F[:, 6]
     b = np.sqrt(bx ** 2 + by ** 2 + bz ** 2)
@@ -93,6 +95,10 @@ def push_2d(P, F, p, dt_min, dt_max, u, x, y, t, qdrift):
     knp = np.ones_like(b)
     if P.mag_dependency == 1:
         knp = knp * b ** (P.gamma_turb - 2.0)
+    if P.deltab_flag:
+        knp = knp / aux[:, 0]
+    if P.correlation_flag:
+        knp = knp * aux[:, 8] ** (P.gamma_turb - 1.0)
     knorm = knp * (p / P.p0) ** P.pindex if P.momentum_dependency == 1 else knp
     kpara = P.kpara0 * knorm
     kperp = kpara * P.kret
@@ -108,6 +114,12 @@ def push_2d(P, F, p, dt_min, dt_max, u, x, y, t, qdrift):
     if P.mag_dependency == 1:
         dkdx = db_dx * ib1 * (P.gamma_turb - 2.0)
         dkdy = db_dy * ib1 * (P.gamma_turb - 2.0)
+    if P.deltab_flag:
+        dkdx = dkdx - aux[:, 1] / aux[:, 0]
+        dkdy = dkdy - aux[:, 2] / aux[:, 0]
+    if P.correlation_flag:
+        dkdx = dkdx + (P.gamma_turb - 1.0) * aux[:, 9] / aux[:, 8]
+        dkdy = dkdy + (P.gamma_turb - 1.0) * aux[:, 10] / aux[:, 8]
     kpp = kpara - kperp
     dkxx_dx = kperp * dkdx + kpp * dkdx * bx ** 2 * ib2k + 2.0 * kpp * bx * (dbx_dx * b - bx * db_dx) * ib3k
     dkyy_dy = kperp * dkdy + kpp * dkdy * by ** 2 * ib2k + 2.0 * kpp * by * (dby_dy * b - by * db_dy) * ib3k
@@ -145,3 +157,42 @@ def push_2d(P, F, p, dt_min, dt_max, u, x, y, t, qdrift):
     low = pn < 0.25 * P.p0
     pn = np.where(low, 0.25 * P.p0, pn)
     return x + ddx, y + ddy, pn, t + dt, dt
+
+
+def turbulence_grad(a, dx, dy):
+    """value + d/dx, d/dy (+ zero d/dz) of one 2-D turbulence map (ny+4, nx+4) float32, with the
+    arithmetic of calc_grad_sigma2_slab (mhd_data_parallel.f90:771-872): FP32 differences, one-sided
+    at the array ends, times 0.5/dx in FP64, stored FP32.  Returns (ny+4, nx+4, 4) float32."""
+    out = np.zeros(a.shape + (4,), dtype=np.float32)
+    out[..., 0] = a
+    for axis, h in ((1, dx), (0, dy)):
+        g = np.zeros_like(a)
+        sl = lambda s: tuple(s if k == axis else slice(None) for k in range(2))
+        g[sl(slice(1, -1))] = a[sl(slice(2, None))] - a[sl(slice(None, -2))]
+        g[sl(0)] = (np.float32(-3) * a[sl(0)] + np.float32(4) * a[sl(1)]) - a[sl(2)]
+        g[sl(-1)] = (np.float32(3) * a[sl(-1)] - np.float32(4) * a[sl(-2)]) + a[sl(-3)]
+        out[..., 1 if axis == 1 else 2] = (g.astype(np.float64) * (0.5 / h)).astype(np.float32)
+    return out
+
+
+def interp_aux(maps1, maps2, P, x, y, rt):
+    """interp_magnetic_fluctuation / interp_correlation_length (mhd_data_parallel.f90:1806-1915) for
+    four maps given as lists of (ny+4, nx+4, 4) arrays: returns (n, 16)."""
+    px = (x - P.xmin) / P.dx
+    py = (y - P.ymin) / P.dy
+    ix = np.floor(px).astype(np.int64) + 1
+    iy = np.floor(py).astype(np.int64) + 1
+    rx, ry = px - ix + 1, py - iy + 1
+    w = [(1.0 - rx) * (1.0 - ry) * 1.0, rx * (1.0 - ry) * 1.0, (1.0 - rx) * ry * 1.0, rx * ry * 1.0]
+    out = []
+    for m1, m2 in zip(maps1, maps2):
+        f1 = np.zeros((len(x), 4))
+        f2 = np.zeros((len(x), 4))
+        c = 0
+        for j in (0, 1):
+            for i in (0, 1):
+                f1 = f1 + m1[iy + j + 1, ix + i + 1, :].astype(np.float64) * w[c][:, None]
+                f2 = f2 + m2[iy + j + 1, ix + i + 1, :].astype(np.float64) * w[c][:, None]
+                c += 1
+        out.append(f1 * (1.0 - rt[:, None]) + f2 * rt[:, None])
+    return np.concatenate(out, axis=1)

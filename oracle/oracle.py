@@ -84,6 +84,14 @@ class Oracle:
         if not with_grad:
             self.lib.orc_calc_gradients(self.h, C.c_int(slot))
 
+    def upload_turbulence(self, which: int, slot: int, slab: np.ndarray, two_d: np.ndarray):
+        """read_magnetic_fluctuation (which = 0) / read_correlation_length (1) + their gradient passes;
+        slab and two_d are float32 arrays over the ghosted grid (the two halves of the reference's file)."""
+        data = np.ascontiguousarray(np.stack([slab, two_d]), dtype=np.float32)
+        if data.size != 2 * int(np.prod(self.grid_shape)):
+            raise ValueError("turbulence map has the wrong size")
+        self.lib.orc_set_turbulence(self.h, C.c_int(which), C.c_int(slot), ptr(data))
+
     def get_fields(self, slot: int) -> np.ndarray:
         out = np.empty(self.grid_shape + (NVAR,), dtype=np.float32)
         self.lib.orc_get_fields(self.h, C.c_int(slot), ptr(out))

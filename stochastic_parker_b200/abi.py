@@ -123,6 +123,7 @@ SIGNATURES = {
     "gpat_last_error": (C.c_char_p, [C.c_void_p]),
     "gpat_upload_fields": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]),
     "gpat_swap_fields": (C.c_int, [C.c_void_p]),
+    "gpat_upload_turbulence": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "gpat_prefetch_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "gpat_inject_uniform": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_double,
                                       C.c_double, C.c_double, _DP, C.c_double]),

@@ -118,6 +118,8 @@ struct gpat_sim {
     // particle tracking (gpat_init_tracking)
     TrackDev trk{};
     int* d_shock = nullptr;  // shock_xpos2 (gpat_inject_at_shock)
+    float* aux = nullptr;    // turbulence maps (gpat_upload_turbulence), 32 floats per grid point
+    bool have_aux[2] = {false, false};
     int* d_tags = nullptr;
     gpat_particle* d_tracked = nullptr;
     const void* registered_host[2] = {nullptr, nullptr};
@@ -189,7 +191,6 @@ int validate(const gpat_params* p, std::string& why)
     }
     if (p->spherical_coord) { why = "spherical coordinates are outside the GPU path"; return 1; }
     if (p->nonuniform_grid) { why = "non-uniform grids are outside the GPU path"; return 1; }
-    if (p->deltab_flag || p->correlation_flag) { why = "deltab/correlation maps are outside the GPU path"; return 1; }
     if (p->acc_by_surface) { why = "acc_by_surface is outside the GPU path"; return 1; }
     if (p->include_3rd_dim && p->ndim != 2) { why = "include_3rd_dim needs ndim = 2"; return 1; }
     if (p->npp_global < 1 || p->nmu_global < 1) { why = "npp_global/nmu_global must be >= 1"; return 1; }
@@ -267,6 +268,7 @@ void fill_dev_params(gpat_sim* h)
     d.dpp_wave = p.dpp_wave; d.dpp_shear = p.dpp_shear; d.weak_scattering = p.weak_scattering;
     d.check_drift_2d = p.check_drift_2d; d.include_3rd_dim = p.include_3rd_dim; d.nlgc = p.nlgc;
     d.focused_transport = p.focused_transport; d.duu0 = p.duu0; d.pcharge = p.pcharge;
+    d.deltab_flag = p.deltab_flag; d.correlation_flag = p.correlation_flag;
     d.key0 = (unsigned)p.seed;
     d.key1 = (unsigned)(p.seed >> 32);
     d.rng_mode = p.rng_mode;
@@ -467,12 +469,16 @@ int run_push(gpat_sim* h, double t0, double dtf, int nsteps_interval, int num_fi
     a.rng_slots = h->table_slots;
     a.rng_max_steps = h->table_steps;
     a.trk = h->trk;
+    a.aux = h->aux;
+    if ((h->hp.deltab_flag && !h->have_aux[0]) || (h->hp.correlation_flag && !h->have_aux[1]))
+        return fail(h, GPAT_ERR_STATE, "the deltab / correlation maps have not been uploaded (gpat_upload_turbulence)");
     CU(cudaMemsetAsync(h->d_queue, 0, 2 * sizeof(unsigned long long), h->st));
     CU(cudaEventRecord(h->ev[0], h->st));
     if (a.nptl > 0) {
-        // 1-D (push_particle_1d) and focused transport (push_particle_2d_ft) exist in the
-        // reference-order build only: they are not throughput paths yet
-        if (h->hp.strict_math || h->hp.ndim == 1 || h->hp.focused_transport) launch_push_strict(h->layout, h->dp, h->P, h->fld, a, h->sm_count, h->st);
+        // 1-D (push_particle_1d), focused transport (push_particle_2d_ft) and the turbulence maps
+        // (deltab / correlation) exist in the reference-order build only: not throughput paths yet
+        if (h->hp.strict_math || h->hp.ndim == 1 || h->hp.focused_transport || h->hp.deltab_flag ||
+            h->hp.correlation_flag) launch_push_strict(h->layout, h->dp, h->P, h->fld, a, h->sm_count, h->st);
         else launch_push_fast(h->layout, h->dp, h->P, h->fld, a, h->sm_count, h->st);
         h->tm.total_launches++;
     }
@@ -589,7 +595,7 @@ int gpat_finalize(gpat_handle h)
         if (h->registered_host[i]) cudaHostUnregister(const_cast<void*>(h->registered_host[i]));
     void* ptrs[] = {h->ptl_mem, h->esc_mem, h->d_counters, h->d_nptl_split, h->d_leak, h->d_queue,
                     h->w.tile_counts, h->w.tile_offsets, h->idx_a, h->idx_b, h->fld, h->stage, h->stage2,
-                    h->d_tags, h->d_tracked, h->d_shock,
+                    h->d_tags, h->d_tracked, h->d_shock, h->aux,
                     h->d_fglobal, h->d_flocal[0], h->d_flocal[1], h->d_flocal[2], h->d_flocal[3],
                     h->d_fesc, h->d_pthr, h->d_sums, h->d_minmax, h->d_quick, h->d_table, h->d_aos};
     for (void* p : ptrs)
@@ -641,6 +647,36 @@ int gpat_upload_fields(gpat_handle h, int slot, const float* f, int nvar, int wi
     h->tm.upload_ms = elapsed(h->ev[2], h->ev[4]);
     h->tm.grad_ms = elapsed(h->ev[3], h->ev[4]);
     h->have_field[slot] = true;
+    return GPAT_OK;
+}
+
+int gpat_upload_turbulence(gpat_handle h, int which, int slot, const float* data)
+{
+    if (!h || !data || (which != 0 && which != 1) || (slot != 0 && slot != 1))
+        return fail(h, GPAT_ERR_INVALID, "gpat_upload_turbulence: bad arguments");
+    if (slot == 1 && !h->dp.time_interp)
+        return fail(h, GPAT_ERR_INVALID, "gpat_upload_turbulence: slot 1 exists only with time_interp = 1");
+    CU(cudaSetDevice(h->device));
+    const size_t ncell_dev = (size_t)h->dp.nxg * h->dp.nyg * h->dp.nzg;
+    if (!h->aux) {
+        CU(cudaMalloc(&h->aux, ncell_dev * 32 * sizeof(float)));
+        launch_fill(h->aux, (long long)(ncell_dev * 32), 1.0f, h->sm_count, h->st);  // sigma2 = lc = 1.0, :125, :165
+    }
+    const size_t bytes = (size_t)h->dp.nxg * h->dp.nyg_src * h->dp.nzg * 2 * sizeof(float);
+    if (bytes > h->stage_bytes) {
+        if (h->stage) cudaFree(h->stage);
+        h->stage = nullptr;
+        h->stage_bytes = 0;
+        CU(cudaMalloc(&h->stage, bytes));
+        h->stage_bytes = bytes;
+    }
+    CU(cudaMemcpyAsync(h->stage, data, bytes, cudaMemcpyHostToDevice, h->st));
+    const int half = (slot == 0) ? h->sel : (h->sel ^ 1);
+    launch_pack_aux(h->stage, h->dp, which, h->aux, half, h->sm_count, h->st);
+    h->tm.total_launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->st));
+    h->have_aux[which] = true;
     return GPAT_OK;
 }
 
@@ -710,10 +746,10 @@ int gpat_inject_targeted(gpat_handle h, int mode, int64_t nptl, double dt, int d
 {
     if (!h || !part_box || nptl < 0) return fail(h, GPAT_ERR_INVALID, "gpat_inject_targeted: bad arguments");
     if (dist_flag < 0 || dist_flag > 2) return fail(h, GPAT_ERR_INVALID, "gpat_inject_targeted: dist_flag must be 0, 1 or 2");
-    if (mode == GPAT_INJECT_LARGE_DB2)
-        return fail(h, GPAT_ERR_INVALID, "gpat_inject_targeted: inject_large_db2 needs the deltab maps (outside the GPU path)");
+    if (mode == GPAT_INJECT_LARGE_DB2 && (!h->aux || !h->have_aux[0]))
+        return fail(h, GPAT_ERR_STATE, "gpat_inject_targeted: inject_large_db2 needs the deltab maps (gpat_upload_turbulence)");
     if (mode != GPAT_INJECT_LARGE_JZ && mode != GPAT_INJECT_LARGE_ABSJ && mode != GPAT_INJECT_LARGE_DIVV &&
-        mode != GPAT_INJECT_LARGE_RHO)
+        mode != GPAT_INJECT_LARGE_RHO && mode != GPAT_INJECT_LARGE_DB2)
         return fail(h, GPAT_ERR_INVALID, "gpat_inject_targeted: unknown mode");
     if (mode == GPAT_INJECT_LARGE_RHO && !Rec_has_rho(h->layout))
         return fail(h, GPAT_ERR_INVALID, "gpat_inject_targeted: inject_large_rho needs gpat_params.keep_rho = 1");
@@ -723,7 +759,7 @@ int gpat_inject_targeted(gpat_handle h, int mode, int64_t nptl, double dt, int d
     CU(cudaSetDevice(h->device));
     CU(cudaEventRecord(h->ev[2], h->st));
     // d_queue doubles as the cell counter and the non-convergence flag (it is idle between pushes)
-    launch_ncells(h->dp, h->layout, h->fld, h->sel, mode, vmin, part_box, h->d_queue, h->sm_count, h->st);
+    launch_ncells(h->dp, h->layout, h->fld, h->sel, mode, vmin, part_box, h->d_queue, h->sm_count, h->st, h->aux);
     h->tm.total_launches++;
     unsigned long long ncells = 0;
     CU(cudaMemcpyAsync(&ncells, h->d_queue, sizeof(ncells), cudaMemcpyDeviceToHost, h->st));
@@ -738,7 +774,7 @@ int gpat_inject_targeted(gpat_handle h, int mode, int64_t nptl, double dt, int d
         CU(cudaMemsetAsync(d_fail, 0, sizeof(int), h->st));
         launch_inject(h->dp, h->P, ninj, h->nptl_current, h->nptl_max, h->tag_max, dt, dist_flag, particle_v0,
                       t_frame, dt_mhd, part_box, power_index, h->st, mode, vmin, h->layout, h->fld, h->sel, d_fail,
-                      &h->trk);
+                      &h->trk, nullptr, h->aux);
         h->tm.total_launches++;
         int failed = 0;
         CU(cudaEventRecord(h->ev[3], h->st));

@@ -108,6 +108,49 @@ void launch_pack(const float* src, int nvar, int with_grad, const DevParams& prm
     pack_kernel<<<sm_count * 8, 256, 0, st>>>(src, nvar, with_grad, g, map, dst, stride, half_off);
 }
 
+// Turbulence maps: consumer side of read_magnetic_fluctuation / read_correlation_length
+// (mhd_data_parallel.f90:306-497) + calc_grad_sigma2_slab/_2d, calc_grad_lc_slab/_2d (:771-1604).
+// src holds the slab array then the 2-D array (each one float per ghosted grid point); chunk
+// 2*which + t of every grid point receives [value, d/dx, d/dy, d/dz] of array t for this frame half.
+__global__ void pack_aux_kernel(const float* __restrict__ src, GridDims g, int which, float* __restrict__ aux,
+                                int half_off)
+{
+    const long long ncell = (long long)g.nxg * g.nyg * g.nzg;
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < 2 * ncell;
+         c += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(c / ncell);
+        const long long cc = c % ncell;
+        const int i = (int)(cc % g.nxg);
+        const int j = (int)((cc / g.nxg) % g.nyg);
+        const int k = (int)(cc / ((long long)g.nxg * g.nyg));
+        const float* a = src + t * ncell;
+        float4 v;
+        v.x = a[cc];
+        // an unresolved axis keeps the 1.0 the reference initialises these arrays with (:125-126)
+        v.y = (g.nxg > 1) ? grad_one(a, 1, g, 0, 0, i, j, k) : 1.0f;
+        v.z = (g.nyg > 1) ? grad_one(a, 1, g, 0, 1, i, j, k) : 1.0f;
+        v.w = (g.nzg > 1) ? grad_one(a, 1, g, 0, 2, i, j, k) : 1.0f;
+        *reinterpret_cast<float4*>(aux + cc * 32 + (2 * which + t) * 8 + half_off) = v;
+    }
+}
+
+__global__ void fill_kernel(float* __restrict__ p, long long n, float v)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+void launch_fill(float* p, long long n, float v, int sm_count, cudaStream_t st)
+{
+    fill_kernel<<<sm_count * 8, 256, 0, st>>>(p, n, v);
+}
+
+void launch_pack_aux(const float* src2, const DevParams& prm, int which, float* aux, int half, int sm_count,
+                     cudaStream_t st)
+{
+    GridDims g{prm.nxg, prm.nyg_src, prm.nzg, 0.5 / prm.dx, 0.5 / prm.dy, 0.5 / prm.dz};
+    pack_aux_kernel<<<sm_count * 8, 256, 0, st>>>(src2, g, which, aux, (prm.time_interp ? half : 0) * 4);
+}
+
 void launch_grad32(const float* src8, const DevParams& prm, float* out32, int sm_count,
                    cudaStream_t st)
 {

@@ -110,6 +110,7 @@ struct DevParams {
     int momentum_dependency, mag_dependency, acc_region_flag;
     int dpp_wave, dpp_shear, weak_scattering, check_drift_2d, include_3rd_dim, nlgc;
     int focused_transport;  // 2-D Cartesian push_particle_2d_ft, reference-order build only
+    int deltab_flag, correlation_flag;  // turbulence maps (reference-order build only)
     int pcharge;
     double duu0;
     // rng
@@ -190,6 +191,9 @@ struct PushArgs {
     const double* rng_table;
     long long rng_slots, rng_max_steps;
     TrackDev trk;                // particle tracking (enabled = 0: the production kernels)
+    // turbulence maps sigma2_slab, sigma2_2d, lc_slab, lc_2d (mhd_data_parallel.f90:36-41): per grid
+    // point four 32-byte chunks [value d/dx d/dy d/dz of half 0 | the same of half 1]
+    const float* aux;
 };
 
 // ---- stream-compaction scratch (particles.cu) ---------------------------------------------
@@ -229,6 +233,9 @@ constexpr int kNumCounters = 8;
 
 void launch_pack(const float* src, int nvar, int with_grad, const DevParams& prm, int layout,
                  float* dst, int half, int sm_count, cudaStream_t st);
+void launch_fill(float* p, long long n, float v, int sm_count, cudaStream_t st);
+void launch_pack_aux(const float* src2, const DevParams& prm, int which, float* aux, int half, int sm_count,
+                     cudaStream_t st);
 void launch_grad32(const float* src8, const DevParams& prm, float* out32, int sm_count,
                    cudaStream_t st);
 void launch_inject(const DevParams& prm, const PtlSoA& P, long long n, long long start,
@@ -236,10 +243,11 @@ void launch_inject(const DevParams& prm, const PtlSoA& P, long long n, long long
                    double t_frame, double dt_mhd, const double box[6], double power_index,
                    cudaStream_t st, int mode = 0, double vmin = 0.0, int layout = 0,
                    const float* fld = nullptr, int sel = 0, int* fail = nullptr,
-                   const TrackDev* trk = nullptr, const int* shock_x = nullptr);
+                   const TrackDev* trk = nullptr, const int* shock_x = nullptr, const float* aux = nullptr);
 void launch_shock_xpos(const DevParams& prm, int layout, const float* fld, int half, int* d_out, cudaStream_t st);
 void launch_ncells(const DevParams& prm, int layout, const float* fld, int sel, int mode, double vmin,
-                   const double box[6], unsigned long long* d_count, int sm_count, cudaStream_t st);
+                   const double box[6], unsigned long long* d_count, int sm_count, cudaStream_t st,
+                   const float* aux = nullptr);
 void launch_remove(const PtlSoA& P, const PtlSoA& E, long long ecap, long long n, long long* counters,
                    const ScanWork& w, long long* idx_a, long long* idx_b, int dump_escaped,
                    cudaStream_t st);

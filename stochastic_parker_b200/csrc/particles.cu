@@ -72,6 +72,7 @@ struct InjectArgs {
     int* fail;           // set when a rejection loop hits kMaxTrials
     TrackDev trk;        // particle tracking (particle_module.f90:434-440)
     const int* shock_x;  // mode GPAT_INJECT_AT_SHOCK: shock_xpos2(nyg, nzg), locate_shock_xpos
+    const float* aux;    // mode GPAT_INJECT_LARGE_DB2: turbulence maps (sigma2_slab is chunk 0)
 };
 
 constexpr int kMaxTrials = 1 << 22;  // the reference's loop is unbounded; a kernel must end
@@ -125,6 +126,12 @@ __device__ double inject_criterion(const DevParams& prm, const InjectArgs& a, do
 {
     InjInterp I;
     I.locate(prm, x, y, z);
+    if (a.mode == GPAT_INJECT_LARGE_DB2) {  // db2_slab(1) at rt = 0, particle_module.f90:1173-1174
+        double f = 0.0;
+        for (int c = 0; c < I.nc; ++c)
+            f = __dadd_rn(f, __dmul_rn((double)a.aux[I.cell[c] * 32 + a.half * 4], I.w[c]));
+        return f;
+    }
     if (a.mode == GPAT_INJECT_LARGE_JZ)
         return fabs(__dsub_rn(I.slot(a, a.pos[2]), I.slot(a, a.pos[0])));
     if (a.mode == GPAT_INJECT_LARGE_ABSJ) {
@@ -294,7 +301,9 @@ __global__ void ncells_kernel(const __grid_constant__ DevParams prm, const __gri
         };
         auto get = [&](long long cell, int pos) { return pos < 0 ? 0.0f : rec_get(a.fld, cell, a.nrec, a.half, pos); };
         double v;
-        if (a.mode == GPAT_INJECT_LARGE_JZ) {  // FP32 difference and abs, mhd_data_parallel.f90:2235
+        if (a.mode == GPAT_INJECT_LARGE_DB2) {  // sigma2_slab_1(1, ix, iy, iz), mhd_data_parallel.f90:2371
+            v = (double)a.aux[cell_of(ix, iy, iz) * 32 + a.half * 4];
+        } else if (a.mode == GPAT_INJECT_LARGE_JZ) {  // FP32 difference and abs, mhd_data_parallel.f90:2235
             const long long cc = cell_of(ix, iy, iz);
             v = (double)fabsf(__fsub_rn(get(cc, a.pos[2]), get(cc, a.pos[0])));
         } else if (a.mode == GPAT_INJECT_LARGE_ABSJ) {  // all FP32, mhd_data_parallel.f90:2306-2311
@@ -376,10 +385,11 @@ static void fill_target(InjectArgs& a, const DevParams& prm, int layout, const f
 }
 
 void launch_ncells(const DevParams& prm, int layout, const float* fld, int sel, int mode, double vmin,
-                   const double box[6], unsigned long long* d_count, int sm_count, cudaStream_t st)
+                   const double box[6], unsigned long long* d_count, int sm_count, cudaStream_t st, const float* aux)
 {
     InjectArgs a{};
     fill_target(a, prm, layout, fld, sel, mode, vmin, box, nullptr);
+    a.aux = aux;
     cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st);
     ncells_kernel<<<sm_count * 4, 256, 0, st>>>(prm, a, d_count);
 }
@@ -388,7 +398,7 @@ void launch_inject(const DevParams& prm, const PtlSoA& P, long long n, long long
                    long long nptl_max, long long tag0, double dt, int dist_flag, double particle_v0,
                    double t_frame, double dt_mhd, const double box[6], double power_index,
                    cudaStream_t st, int mode, double vmin, int layout, const float* fld, int sel, int* fail,
-                   const TrackDev* trk, const int* shock_x)
+                   const TrackDev* trk, const int* shock_x, const float* aux)
 {
     if (n <= 0) return;
     InjectArgs a{};
@@ -396,6 +406,7 @@ void launch_inject(const DevParams& prm, const PtlSoA& P, long long n, long long
     a.shock_x = shock_x;
     if (mode == GPAT_INJECT_AT_SHOCK) a.mode = mode;
     if (mode != 0 && mode != GPAT_INJECT_AT_SHOCK) fill_target(a, prm, layout, fld, sel, mode, vmin, box, fail);
+    a.aux = aux;
     a.n = n; a.start = start; a.nptl_max = nptl_max; a.tag0 = tag0; a.dt = dt;
     a.particle_v0 = particle_v0; a.t_frame = t_frame; a.dt_mhd = dt_mhd;
     a.power_index = power_index; a.dist_flag = dist_flag;

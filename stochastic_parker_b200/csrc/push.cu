@@ -260,6 +260,48 @@ __device__ __forceinline__ void gather(const DevParams& prm, const float* __rest
 #endif
 }
 
+#if GPAT_STRICT
+// interp_magnetic_fluctuation + interp_correlation_length (mhd_data_parallel.f90:1806-1915): the
+// sixteen values db2_slab(1:4) db2_2d(1:4) lc_slab(1:4) lc_2d(1:4), reference summation order
+template <int NDIM>
+__device__ __forceinline__ void gather_aux(const DevParams& prm, const float* __restrict__ aux, int sel,
+                                           double x, double y, double z, double rt, double (&A)[16])
+{
+    constexpr int NC = (NDIM == 3) ? 8 : 4;
+    double rx, ry, rz;
+    const long long cell = locate<NDIM>(prm, x, y, z, rx, ry, rz);
+    const double rx1 = 1.0 - rx, ry1 = 1.0 - ry, rz1 = 1.0 - rz;
+    double w[NC];
+    if (NC == 4) {
+        w[0] = rx1 * ry1; w[1] = rx * ry1; w[2] = rx1 * ry; w[3] = rx * ry;
+    } else {
+        w[0] = rx1 * ry1 * rz1; w[1] = rx * ry1 * rz1; w[2] = rx1 * ry * rz1; w[3] = rx * ry * rz1;
+        w[4] = rx1 * ry1 * rz;  w[5] = rx * ry1 * rz;  w[6] = rx1 * ry * rz;  w[7] = rx * ry * rz;
+    }
+    const int hA = (prm.time_interp ? sel : 0) * 4, hB = (sel ^ 1) * 4;
+    const double rt1 = 1.0 - rt;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        double a[4] = {0.0, 0.0, 0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const long long off = (cell + (c & 1) + (long long)((c >> 1) & 1) * prm.nxg +
+                                   (long long)(c >> 2) * prm.nxg * prm.nyg) * 32 + 8 * q;
+            const float4 fa = __ldg(reinterpret_cast<const float4*>(aux + off + hA));
+            a[0] = a[0] + (double)fa.x * w[c]; a[1] = a[1] + (double)fa.y * w[c];
+            a[2] = a[2] + (double)fa.z * w[c]; a[3] = a[3] + (double)fa.w * w[c];
+            if (prm.time_interp) {
+                const float4 fb = __ldg(reinterpret_cast<const float4*>(aux + off + hB));
+                b[0] = b[0] + (double)fb.x * w[c]; b[1] = b[1] + (double)fb.y * w[c];
+                b[2] = b[2] + (double)fb.z * w[c]; b[3] = b[3] + (double)fb.w * w[c];
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) A[4 * q + e] = prm.time_interp ? (a[e] * rt1 + b[e] * rt) : a[e];
+    }
+}
+#endif
+
 // ---- kappa (particle_module.f90:93-104) --------------------------------------------
 struct Kappa {
     double knorm_para, kpara, kperp, skpara, skperp, skpara_perp;
@@ -273,9 +315,10 @@ struct BField {  // B and its gradients at the particle
 };
 
 // THREE: z-components needed (3-D or 2-D with include_3rd_dim); FULL3D: ndim == 3
+// aux (reference-order build): the 16 interpolated turbulence values, or nullptr
 template <bool THREE, bool FULL3D>
 __device__ __forceinline__ void calc_kappa(const DevParams& prm, const BField& B, double p,
-                                           double mu, Kappa& k)
+                                           double mu, Kappa& k, const double* aux = nullptr)
 {
     const double bx = B.bx, by = B.by, bz = B.bz, b = B.b;
     const double ib1 = (b < kEps) ? 1.0 : 1.0 / b;  // particle_module.f90:2230-2234
@@ -286,6 +329,17 @@ __device__ __forceinline__ void calc_kappa(const DevParams& prm, const BField& B
         knp = knp * pow(b, prm.gm2);
         if (prm.nlgc) knperp = knperp * pow(b, prm.gm2_3);
     }
+#if GPAT_STRICT
+    const bool dbf = aux && prm.deltab_flag, cof = aux && prm.correlation_flag;
+    if (dbf) {  // particle_module.f90:2246-2248 / 2505-2509
+        knp = knp / aux[0];
+        if (prm.nlgc) knperp = knperp * pow(aux[0], -1.0 / 3.0) * pow(aux[4], 2.0 / 3.0);
+    }
+    if (cof) {  // particle_module.f90:2252-2254 / 2513-2517
+        knp = knp * pow(aux[8], prm.gamma_turb - 1.0);
+        if (prm.nlgc) knperp = knperp * pow(aux[8], (prm.gamma_turb - 1.0) / 3.0) * pow(aux[12], 2.0 / 3.0);
+    }
+#endif
     k.knorm_para = knp;
     double ax = 0.0, ay = 0.0, az = 0.0;  // coefficients multiplying the b_i b_j terms
     if (!prm.nlgc) {
@@ -320,6 +374,17 @@ __device__ __forceinline__ void calc_kappa(const DevParams& prm, const BField& B
                 dkdx = B.db_dx * ib1 * prm.gm2; dkdy = B.db_dy * ib1 * prm.gm2;
             }
         }
+#if GPAT_STRICT
+        if (dbf) {  // particle_module.f90:2314-2317, 2364-2367, 2410-2414
+            dkdx = dkdx - aux[1] / aux[0]; dkdy = dkdy - aux[2] / aux[0];
+            if (FULL3D) dkdz = dkdz - aux[3] / aux[0];
+        }
+        if (cof) {  // particle_module.f90:2318-2321, 2368-2371, 2415-2419
+            const double g1 = prm.gamma_turb - 1.0;
+            dkdx = dkdx + g1 * aux[9] / aux[8]; dkdy = dkdy + g1 * aux[10] / aux[8];
+            if (FULL3D) dkdz = dkdz + g1 * aux[11] / aux[8];
+        }
+#endif
         px_ = k.kperp * dkdx; py_ = k.kperp * dkdy; pz_ = k.kperp * dkdz;
         ax = kpp * dkdx; ay = kpp * dkdy; az = kpp * dkdz;
     } else {
@@ -329,6 +394,27 @@ __device__ __forceinline__ void calc_kappa(const DevParams& prm, const BField& B
             dpe_x = B.db_dx * ib1 * prm.gm2 / 3.0; dpe_y = B.db_dy * ib1 * prm.gm2 / 3.0;
             if (FULL3D) { dpa_z = B.db_dz * ib1 * prm.gm2; dpe_z = B.db_dz * ib1 * prm.gm2 / 3.0; }
         }
+#if GPAT_STRICT
+        if (dbf) {  // particle_module.f90:2589-2596 and the 2-D+3rd / 3-D twins
+            dpa_x = dpa_x - aux[1] / aux[0]; dpa_y = dpa_y - aux[2] / aux[0];
+            dpe_x = dpe_x - aux[1] / aux[0] / 3.0 + 2.0 * aux[5] / aux[4] / 3.0;
+            dpe_y = dpe_y - aux[2] / aux[0] / 3.0 + 2.0 * aux[6] / aux[4] / 3.0;
+            if (FULL3D) {
+                dpa_z = dpa_z - aux[3] / aux[0];
+                dpe_z = dpe_z - aux[3] / aux[0] / 3.0 + 2.0 * aux[7] / aux[4] / 3.0;
+            }
+        }
+        if (cof) {  // particle_module.f90:2597-2604
+            const double g1 = prm.gamma_turb - 1.0;
+            dpa_x = dpa_x + g1 * aux[9] / aux[8]; dpa_y = dpa_y + g1 * aux[10] / aux[8];
+            dpe_x = dpe_x + g1 * aux[9] / aux[8] / 3.0 + 2.0 * aux[13] / aux[12] / 3.0;
+            dpe_y = dpe_y + g1 * aux[10] / aux[8] / 3.0 + 2.0 * aux[14] / aux[12] / 3.0;
+            if (FULL3D) {
+                dpa_z = dpa_z + g1 * aux[11] / aux[8];
+                dpe_z = dpe_z + g1 * aux[11] / aux[8] / 3.0 + 2.0 * aux[15] / aux[12] / 3.0;
+            }
+        }
+#endif
         px_ = k.kperp * dpe_x; py_ = k.kperp * dpe_y; pz_ = k.kperp * dpe_z;
         ax = k.kpara * dpa_x - k.kperp * dpe_x;
         ay = k.kpara * dpa_y - k.kperp * dpe_y;
@@ -414,7 +500,7 @@ __device__ __forceinline__ bool in_acc_region(const DevParams& prm, const Lane& 
 template <int L>
 __device__ __forceinline__ void push_1d(const DevParams& prm, const PushArgs& a,
                                         const double (&F)[Rec<L>::NREC], double u0, double u1,
-                                        Lane& q, bool fixed_dt)
+                                        Lane& q, bool fixed_dt, const double* aux)
 {
     BField B;
     VGrad V;
@@ -427,10 +513,13 @@ __device__ __forceinline__ void push_1d(const DevParams& prm, const PushArgs& a,
     double rho = 1.0;
     if constexpr (Rec<L>::EXT) rho = F[s2::rho];
     Kappa k;
-    calc_kappa<false, false>(prm, B, q.p, q.mu, k);
-    // particle_module.f90:2271-2292: dkdx = 0 (mag_dependency = 1 is rejected by gpat_init because
-    // the reference would multiply by an unassigned db_dx there)
-    k.dkxx_dx = k.kpara * 0.0;
+    calc_kappa<false, false>(prm, B, q.p, q.mu, k, aux);
+    // particle_module.f90:2271-2292: dkdx has no magnetic term here (mag_dependency = 1 is rejected by
+    // gpat_init because the reference would multiply by an unassigned db_dx)
+    double dkdx = 0.0;
+    if (aux && prm.deltab_flag) dkdx = dkdx - aux[1] / aux[0];
+    if (aux && prm.correlation_flag) dkdx = dkdx + (prm.gamma_turb - 1.0) * aux[9] / aux[8];
+    k.dkxx_dx = k.kpara * dkdx;
     const double dx_dt = F[s2::vx] + k.dkxx_dx;
     const double divv = V.dvx_dx;
     double dp_dt = -q.p * divv / 3.0;
@@ -483,7 +572,7 @@ __device__ __forceinline__ void push_1d(const DevParams& prm, const PushArgs& a,
 template <int L>
 __device__ __forceinline__ void push_2d_ft(const DevParams& prm, const PushArgs& a,
                                            const double (&F)[Rec<L>::NREC], double u0, double u1, double u2,
-                                           double u3, Lane& q, bool fixed_dt)
+                                           double u3, Lane& q, bool fixed_dt, const double* aux)
 {
     if constexpr (Rec<L>::EXT && Rec<L>::NDIM == 2) {
         const double mu_max = (double)0.99f;
@@ -504,7 +593,7 @@ __device__ __forceinline__ void push_2d_ft(const DevParams& prm, const PushArgs&
         B.b = sqrt(sq(bx) + sq(by) + sq(bz));
         const double b = B.b;
         Kappa k;
-        calc_kappa<false, false>(prm, B, q.p, q.mu, k);
+        calc_kappa<false, false>(prm, B, q.p, q.mu, k, aux);
         const double ib = (b < kEps) ? 0.0 : 1.0 / b;
         const double ib2 = ib * ib, ib3 = ib * ib2;
         // `1.0 / pcharge` is a default-real quotient (particle_module.f90:3716); qdrift holds 1/(3 q)
@@ -552,6 +641,8 @@ __device__ __forceinline__ void push_2d_ft(const DevParams& prm, const PushArgs&
         else duu_du = 0.0;
         double duu_norm = 1.0;
         if (prm.mag_dependency == 1) duu_norm = duu_norm * pow(b, 2.0 - prm.gamma_turb);
+        if (aux && prm.deltab_flag) duu_norm = duu_norm * aux[0];                                    // :3143-3145
+        if (aux && prm.correlation_flag) duu_norm = duu_norm * pow(aux[8], 1.0 - prm.gamma_turb);   // :3146-3148
         if (prm.momentum_dependency == 1) duu_norm = duu_norm * pow(q.p / prm.p0, prm.gamma_turb - 1);
         duu_du = duu_du * duu_norm;
         duu = duu * duu_norm;
@@ -651,14 +742,20 @@ __device__ __forceinline__ void push_once(const DevParams& prm, const PushArgs& 
     }
     q.rng += 1;
 
+    const double* auxp = nullptr;
 #if GPAT_STRICT
+    double A[16];
+    if (a.aux && (prm.deltab_flag || prm.correlation_flag)) {  // particle_module.f90:1634-1639
+        gather_aux<Rec<L>::NDIM>(prm, a.aux, a.sel, q.x, q.y, q.z, rt, A);
+        auxp = A;
+    }
     if constexpr (!D3) {
         if (prm.ndim == 1) {
-            push_1d<L>(prm, a, F, u0, u1, q, fixed_dt);
+            push_1d<L>(prm, a, F, u0, u1, q, fixed_dt, auxp);
             return;
         }
         if (prm.focused_transport) {
-            push_2d_ft<L>(prm, a, F, u0, u1, u2, u3, q, fixed_dt);
+            push_2d_ft<L>(prm, a, F, u0, u1, u2, u3, q, fixed_dt, auxp);
             return;
         }
     }
@@ -703,9 +800,9 @@ __device__ __forceinline__ void push_once(const DevParams& prm, const PushArgs& 
     const bool third = D3 || (EXT && prm.include_3rd_dim);  // push_particle_3d-like path
 
     Kappa k;
-    if (D3) calc_kappa<true, true>(prm, B, q.p, q.mu, k);
-    else if (EXT && prm.include_3rd_dim) calc_kappa<true, false>(prm, B, q.p, q.mu, k);
-    else calc_kappa<false, false>(prm, B, q.p, q.mu, k);
+    if (D3) calc_kappa<true, true>(prm, B, q.p, q.mu, k, auxp);
+    else if (EXT && prm.include_3rd_dim) calc_kappa<true, false>(prm, B, q.p, q.mu, k, auxp);
+    else calc_kappa<false, false>(prm, B, q.p, q.mu, k, auxp);
 
     const double ib = (B.b < kEps) ? 0.0 : 1.0 / B.b;  // particle_module.f90:3414-3418
     const double ib2 = ib * ib;

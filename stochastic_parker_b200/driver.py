@@ -69,6 +69,14 @@ class GpatSim:
         self.P = params.copy()
 
     # ---- fields -------------------------------------------------------------
+    def upload_turbulence(self, which: int, slot: int, slab: np.ndarray, two_d: np.ndarray):
+        """read_magnetic_fluctuation (which = 0) / read_correlation_length (which = 1) and their gradient
+        passes (mhd_data_parallel.f90:306-497, 771-1604); slab, two_d: float32 over the ghosted grid."""
+        data = np.ascontiguousarray(np.stack([slab, two_d]), dtype=np.float32)
+        if data.size != 2 * int(np.prod(self.grid_shape)):
+            raise ValueError("turbulence map has the wrong size")
+        self._ck(self.lib.gpat_upload_turbulence(self.h, which, slot, ptr(data)), "gpat_upload_turbulence")
+
     def prefetch_fields(self, f: np.ndarray):
         """Start the H2D copy of a frame that a later upload_fields(slot, f) will pack; `f` must be
         C-contiguous float32 (ideally page-locked) and must not change until then."""

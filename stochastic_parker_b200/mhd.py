@@ -287,3 +287,25 @@ def read_frame(directory: str, frame: int, cfg: dict) -> np.ndarray:
     if ndim == 2:
         return a.reshape(ny + 4, nx + 4, NVAR)
     return a.reshape(nz + 4, ny + 4, nx + 4, NVAR)
+
+
+def make_turbulence_maps(nx: int, ny: int, nz: int, frame: int, ndim: int = 2, dt_out: float = 0.1):
+    """Synthetic deltab_NNNN / lc_NNNN content (read_magnetic_fluctuation, read_correlation_length,
+    mhd_data_parallel.f90:306-497: each file holds the slab array then the 2-D array over the ghosted
+    grid, float32).  Smooth, strictly positive, time-dependent: returns
+    (sigma2_slab, sigma2_2d, lc_slab, lc_2d), each (ny+4, nx+4) or (nz+4, ny+4, nx+4)."""
+    t = frame * dt_out
+    xs = (np.arange(nx + 4, dtype=np.float64) - 2.0) / max(nx - 1, 1)
+    ys = (np.arange(ny + 4, dtype=np.float64) - 2.0) / max(ny - 1, 1)
+    if ndim == 2:
+        X, Y = np.meshgrid(xs, ys)
+        Z = 0.0 * X
+    else:
+        zs = (np.arange(nz + 4, dtype=np.float64) - 2.0) / max(nz - 1, 1)
+        Z, Y, X = np.meshgrid(zs, ys, xs, indexing="ij")
+    tx, ty, tz = 2 * np.pi * X, 2 * np.pi * Y, 2 * np.pi * Z
+    s2s = 0.05 * (1.0 + 0.5 * np.sin(tx + 0.3 + t) * np.cos(ty) + 0.2 * np.cos(tz))
+    s22 = 0.08 * (1.0 + 0.4 * np.cos(tx) * np.sin(ty + 0.5 - t) + 0.1 * np.sin(tz))
+    lcs = 0.6 * (1.0 + 0.3 * np.sin(tx - 0.2) * np.sin(ty + t) + 0.1 * np.cos(tz + 0.4))
+    lc2 = 0.4 * (1.0 + 0.25 * np.cos(tx + t) * np.cos(ty - 0.7) + 0.15 * np.sin(tz))
+    return tuple(a.astype(np.float32) for a in (s2s, s22, lcs, lc2))

@@ -623,3 +623,41 @@ def test_mt19937_known_answers():
     o.lib.orc_mt19937_next.restype = C.c_uint32
     got = [o.lib.orc_mt19937_next(o.h) for _ in range(5)]
     assert got == [1067595299, 955945823, 477289528, 4107218783, 4228976476]
+
+
+# ---- turbulence maps: deltab_flag / correlation_flag (particle_module.f90:2246-2254, 2364-2371) ----
+def test_deltab_and_correlation_step_matches_numpy_restatement():
+    from stochastic_parker_b200 import mhd
+    w, P, frames, _ = make_case("c1", grid=48, nptl=400)
+    P.deltab_flag = 1
+    P.correlation_flag = 1
+    P.rng_mode = RNG_TABLE
+    o = Oracle(P, w.nptl_max)
+    u = np.random.default_rng(21).uniform(0, 1, (400, 2, 4))
+    o.set_rng_table(u)
+    maps = [mhd.make_turbulence_maps(P.nx, P.ny, 1, f) for f in (0, 1)]
+    for slot in (0, 1):
+        o.upload_fields(slot, frames[slot])
+        o.upload_turbulence(0, slot, maps[slot][0], maps[slot][1])
+        o.upload_turbulence(1, slot, maps[slot][2], maps[slot][3])
+    o.inject_uniform(400, 0.0, 0, w.particle_v0, 0.0, w.dt_out, box_of(P), w.power_index)
+    before = o.download_particles()
+    assert o.debug_push_n(0.0, w.dt_out, 1) == 400
+    after = o.download_particles()
+    rt = (before["t"] - 0.0) / w.dt_out
+    fa1 = np_step.gradients32(frames[0], P.dx, P.dy)
+    fa2 = np_step.gradients32(frames[1], P.dx, P.dy)
+    F = np_step.interp32(fa1, fa2, P, before["x"], before["y"], rt)
+    g = [[np_step.turbulence_grad(m, P.dx, P.dy) for m in maps[s]] for s in (0, 1)]
+    aux = np_step.interp_aux(g[0], g[1], P, before["x"], before["y"], rt)
+    qdrift = float(np.float32(1.0) / np.float32(3 * P.pcharge))
+    x, y, p, t, dt = np_step.push_2d(P, F, before["p"], P.dt_min_rel * w.dt_out, P.dt_max_rel * w.dt_out,
+                                    u[before["tag_injected"], 0], before["x"], before["y"], before["t"], qdrift, aux=aux)
+    for name, ref in (("x", x), ("y", y), ("p", p), ("t", t), ("dt", dt)):
+        scale = max(1.0, np.abs(ref).max()) if name in "xy" else np.abs(ref)
+        assert (np.abs(after[name] - ref) / scale).max() < 5e-15, name
+    # the maps matter: the same step without them lands elsewhere
+    x0 = np_step.push_2d(P.copy(), F, before["p"], P.dt_min_rel * w.dt_out, P.dt_max_rel * w.dt_out,
+                         u[before["tag_injected"], 0], before["x"], before["y"], before["t"], qdrift,
+                         aux=np.ones_like(aux) * np.array([1, 0, 0, 0] * 4))[0]
+    assert np.max(np.abs(x0 - x)) > 1e-6

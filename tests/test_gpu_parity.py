@@ -709,3 +709,74 @@ def test_shock_injection_parity(key, grid, dist_flag):
         assert np.array_equal(a["x"], b["x"]) and np.array_equal(a["y"], b["y"]) and np.array_equal(a["tag_injected"], b["tag_injected"])
         assert_particles_close(a, b, 1e-13, f"shock injection dist_flag={dist_flag}", frac_outliers=0.002)
     g.close()
+
+
+def _with_maps(sims, P, frames_idx=(0, 1)):
+    from stochastic_parker_b200 import mhd
+    for slot, f in enumerate(frames_idx):
+        m = mhd.make_turbulence_maps(P.nx, P.ny, P.nz, f, ndim=P.ndim)
+        for s in sims:
+            s.upload_turbulence(0, slot, m[0], m[1])
+            s.upload_turbulence(1, slot, m[2], m[3])
+
+
+@pytest.mark.parametrize("key,grid,cli", [
+    ("c1", 64, {}),                                              # 2-D Parker
+    ("c1", 64, dict(nlgc=1, kperp_kpara=0.05)),                  # NLGC: sigma2_2d and lc_2d enter kappa_perp
+    ("c5", 32, {}),                                              # 3-D: d/dz of the maps
+    ("c1", 64, dict(focused_transport=1, duu_init=5.0)),         # D_mumu normalisation
+])
+def test_turbulence_maps_step_parity(key, grid, cli):
+    """deltab_flag + correlation_flag (particle_module.f90:2246-2254, 2314-2321, 2505-2517, 2589-2604,
+    3143-3148; maps and gradients mhd_data_parallel.f90:306-497, 771-1604, 1806-1915)."""
+    w, P, frames, _ = make_case(key, grid=grid, nptl=512, cli=cli, conf=dict(dt_min_rel=1e-4))
+    P.deltab_flag = 1
+    P.correlation_flag = 1
+    g, o = pair(P, w.nptl_max, 0)   # the library routes map runs to the reference-order build itself
+    load_fields((g, o), frames, True)
+    with pytest.raises(Exception):   # maps not uploaded yet
+        g.debug_push_n(0.0, w.dt_out, 1)
+    _with_maps((g, o), P)
+    _inject((g, o), w, P, 512, dist_flag=0)
+    for nsteps in (1, 40):
+        assert g.debug_push_n(0.0, w.dt_out, nsteps) == o.debug_push_n(0.0, w.dt_out, nsteps)
+        assert_particles_close(g.download_particles(), o.download_particles(), STEP_RTOL * max(1, nsteps // 4),
+                               f"maps {key} {cli} {nsteps} steps", frac_outliers=0.004)
+    # and they matter: the same particles without the maps land elsewhere
+    P0 = P.copy()
+    P0.deltab_flag = P0.correlation_flag = 0
+    o0 = Oracle(P0, w.nptl_max)
+    load_fields((o0,), frames, True)
+    _inject((o0,), w, P0, 512, dist_flag=0)
+    o0.debug_push_n(0.0, w.dt_out, 1)
+    o1 = Oracle(P, w.nptl_max)
+    load_fields((o1,), frames, True)
+    _with_maps((o1,), P)
+    _inject((o1,), w, P, 512, dist_flag=0)
+    o1.debug_push_n(0.0, w.dt_out, 1)
+    assert np.max(np.abs(o0.download_particles()["x"] - o1.download_particles()["x"])) > 1e-9
+    g.close()
+
+
+def test_turbulence_maps_swap_and_db2_injection():
+    """copy_magnetic_fluctuation via gpat_swap_fields + inject_particles_at_large_db2
+    (particle_module.f90:1075-1236, mhd_data_parallel.f90:2343-2377), bit for bit."""
+    from stochastic_parker_b200 import mhd
+    w, P, frames, ts = make_case("c1", grid=64, nptl=8, nframes=3)
+    P.deltab_flag = 1
+    g, o = pair(P, 5000, 1)
+    load_fields((g, o), frames, True)
+    _with_maps((g, o), P)
+    for s in (g, o):
+        s.swap_fields()
+        s.upload_fields(1, frames[2])
+    m = mhd.make_turbulence_maps(P.nx, P.ny, 1, 2)
+    for s in (g, o):
+        s.upload_turbulence(0, 1, m[0], m[1])
+    m1 = mhd.make_turbulence_maps(P.nx, P.ny, 1, 1)[0]     # farray1 is now frame 1
+    vmin = float(np.quantile(m1, 0.7))
+    rg = g.inject_targeted(3, 1200, 0.0, 1, w.particle_v0, ts[1], 0.1, box_of(P), 6.2, True, vmin, 1)
+    ro = o.inject_targeted(3, 1200, 0.0, 1, w.particle_v0, ts[1], 0.1, box_of(P), 6.2, True, vmin, 1)
+    assert rg == ro and ro[0] == 1200 and ro[1] > 0
+    assert_particles_identical(g.download_particles(), o.download_particles(), "inject_large_db2")
+    g.close()
