@@ -153,10 +153,11 @@ bool read_mhd_config(const std::string& path, MhdConfig& m)
     return ok;
 }
 
-bool read_frame(const std::string& dir, int frame, size_t nfloats, std::vector<float>& buf)
+bool read_frame(const std::string& dir, int frame, size_t nfloats, std::vector<float>& buf,
+                const char* stem = "mhd_data")
 {
-    char name[32];
-    std::snprintf(name, sizeof(name), "mhd_data_%04d", frame);
+    char name[48];
+    std::snprintf(name, sizeof(name), "%s_%04d", stem, frame);
     FILE* f = std::fopen((dir + name).c_str(), "rb");
     if (!f) return false;
     buf.resize(nfloats);
@@ -210,7 +211,7 @@ int main(int argc, char** argv)
         return 2;
     }
     // features outside the GPU path must stay off; the library re-checks the ones it is told about
-    for (const char* k : {"-ib", "-rf", "-vdt"})
+    for (const char* k : {"-rf", "-vdt"})
         if (cli.b(k)) {
             std::fprintf(stderr, "gpat_driver: switch %s is outside the GPU particle path\n", k);
             return 2;
@@ -395,9 +396,27 @@ int main(int argc, char** argv)
         return gpat_reset_tracked(h);
     };
 
+    // deltab_NNNN / lc_NNNN: slab array then 2-D array (read_magnetic_fluctuation,
+    // read_correlation_length, mhd_data_parallel.f90:306-497; stochastic-mhd.f90:330-346, 413-420)
+    std::vector<float> maps;
+    auto upload_maps = [&](int tframe, int slot) -> int {
+        if (P.deltab_flag) {
+            if (!read_frame(dir_mhd, tframe, ncell * 2, maps, "deltab")) return die(h, "read deltab frame", -1);
+            int rc = gpat_upload_turbulence(h, 0, slot, maps.data());
+            if (rc) return rc;
+        }
+        if (P.correlation_flag) {
+            if (!read_frame(dir_mhd, tframe, ncell * 2, maps, "lc")) return die(h, "read lc frame", -1);
+            int rc = gpat_upload_turbulence(h, 1, slot, maps.data());
+            if (rc) return rc;
+        }
+        return 0;
+    };
+
     // ---- solve_transport_equation (stochastic-mhd.f90:312-567) ----
     if (!read_frame(dir_mhd, t_start, ncell * 8, frame)) return die(h, "read first mhd_data frame", -1);
     CK(gpat_upload_fields(h, 0, frame.data(), 8, 0), "gpat_upload_fields");
+    CK(upload_maps(t_start, 0), "gpat_upload_turbulence");
     uint64_t total_steps = 0;
     auto wall0 = std::chrono::steady_clock::now();
     auto step1 = wall0;
@@ -406,6 +425,7 @@ int main(int argc, char** argv)
         if (single_frame == 0 && tf <= tmax_mhd) {  // :400-447
             if (!read_frame(dir_mhd, tf, ncell * 8, frame)) return die(h, "read mhd_data frame", -1);
             CK(gpat_upload_fields(h, P.time_interp ? 1 : 0, frame.data(), 8, 0), "gpat_upload_fields");
+            CK(upload_maps(tf, P.time_interp ? 1 : 0), "gpat_upload_turbulence");
         }
         const double t0 = tstamp(tf - 1), dtf = tstamp(tf) - tstamp(tf - 1);  // tstamps_mhd(tf - t_start), particle_module.f90:1868
         if (cli.b("-is")) {  // :451-454: locate_shock_xpos + inject_particles_at_shock, every frame
@@ -417,6 +437,7 @@ int main(int argc, char** argv)
             long long norm = 1;
             if (cli.b("-ij")) { mode = GPAT_INJECT_LARGE_JZ; vmin = cli.d("-jz"); norm = cli.i("-nn"); }
             else if (cli.b("-iaj")) { mode = GPAT_INJECT_LARGE_ABSJ; vmin = cli.d("-ajm"); norm = cli.i("-naj"); }
+            else if (cli.b("-ib")) { mode = GPAT_INJECT_LARGE_DB2; vmin = cli.d("-db2"); norm = cli.i("-nb"); }
             else if (cli.b("-iv")) { mode = GPAT_INJECT_LARGE_DIVV; vmin = cli.d("-dv"); norm = cli.i("-nv"); }
             else if (cli.b("-ir")) { mode = GPAT_INJECT_LARGE_RHO; vmin = cli.d("-rm"); norm = cli.i("-nr"); }
             if (mode) {
