@@ -17,7 +17,9 @@
  * MT19937, random_number_generator.f90:9,35-44,100).  north_star defines parity
  * as "fed the same pre-generated random increments", so uniforms are an INPUT
  * here: either a table, or Philox4x32-10 keyed per particle (the stream the GPU
- * library defines; specification in DESIGN.md "RNG").
+ * library defines; specification in DESIGN.md "RNG"), or -- oracle only, for the
+ * statistical comparison -- one sequential MT19937 seeded with the reference's
+ * seed array (pinned by mt19937ar's published output).
  *
  * All file:line citations are relative to /root/reference/src/modules/ with
  * PM = particle_module.f90, MD = mhd_data_parallel.f90, DG = diagnostics.f90.
