@@ -16,6 +16,11 @@
 // oracle (tests/test_gpu_parity.py::test_step_parity[0-*]).
 #pragma once
 
+// FP64 max/min as one compare + select (fmax/fmin add NaN handling: 4-5 instructions each); a NaN
+// first argument yields the second, like fmax/fmin
+__device__ __forceinline__ double max2(double a, double b) { return (a > b) ? a : b; }
+__device__ __forceinline__ double min2f(double a, double b) { return (a < b) ? a : b; }
+
 // F: the interpolated record of this particle (registers, or a shared-memory row written by
 // the lane group that gathered it)
 // SPEC != 0: the run's switches are compile-time constants: no NLGC, on-device Philox, no
@@ -112,7 +117,7 @@ __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArg
 
     // ---- kappa_para, kappa_perp (particle_module.f90:2239-2269 / 2497-2533) ----
     // log|B| = log(b2)/2; a vanishing field only has to stay finite here
-    const double lb = f_mag ? 0.5 * fm::log_pos(fmax(b2, 1e-300)) : 0.0;
+    const double lb = f_mag ? 0.5 * fm::log_pos(max2(b2, 1e-300)) : 0.0;
     const double lpr = fm::log_pos(q.p * prm.ip0);
     double knp = 1.0, kpara, rk, srk, s1mrk;  // rk = kperp/kpara and its square roots
     if (EXT || f_nlgc) {
@@ -234,8 +239,8 @@ __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArg
         double d;
         if (dx_dt != 0.0 && dy_dt != 0.0 && dp_dt != 0.0) {
             // three positive fractions n/dn; pick the smallest by cross-multiplication
-            double m = fmax(dx_dt * dx_dt, dy_dt * dy_dt);
-            if (D3) m = fmax(m, dz_dt * dz_dt);  // (s/0)^2 = +Inf is ignored by min, as in the reference
+            double m = max2(dx_dt * dx_dt, dy_dt * dy_dt);
+            if (D3) m = max2(m, dz_dt * dz_dt);  // (s/0)^2 = +Inf is ignored by min, as in the reference
             double n = (D3 ? prm.hd2min3 : prm.hd2min2) * 0.5, dn = kpara;
             const double n1 = 2.0 * ((rk > 0.0) ? kperp : kpara);
             if (n1 * dn < n * m) { n = n1; dn = m; }
@@ -245,8 +250,8 @@ __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArg
         } else {
             d = a.dt_min;
         }
-        d = fmax(d, a.dt_min);
-        d = fmin(d, a.dt_max);
+        d = max2(d, a.dt_min);
+        d = min2f(d, a.dt_max);
         q.dt = d;
     }
 
