@@ -1388,6 +1388,8 @@ __global__ void interp_kernel(const __grid_constant__ DevParams prm, const float
     for (int k = 0; k < Rec<L>::NUSED; ++k) out32[i * 32 + slot_of(L, k) - 1] = F[k];
 }
 
+template <int L> constexpr int C_NC() { return (Rec<L>::NDIM == 3) ? 8 : 4; }
+
 template <int L>
 void launch_one(const DevParams& prm, const PtlSoA& P, const float* fld, const PushArgs& a,
                 int sm_count, cudaStream_t st)
@@ -1409,6 +1411,26 @@ void launch_one(const DevParams& prm, const PtlSoA& P, const float* fld, const P
         }
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel_coop<L, 0>, kBlock, pad);
         if (per_sm < 1) per_sm = 1;
+        {
+            // Size residency to the L2, not to the register file.  A lane re-reads the same NC records
+            // step after step, so the live working set is resident lanes x NC x record bytes; it is
+            // served by L2 only while it fits about half of it (the 126 MB L2 of a B200 is two
+            // partitions).  2-D records: 39-58 MB at full occupancy, no cap.  3-D Parker: 29 MB per
+            // resident CTA per SM -> 2 CTAs; measured on C5: 1/2/3/4 CTAs per SM = 2.61/3.45/3.17/2.84e9
+            // steps/s (profiles/README.md).  GPAT_PUSH_MAXCTAS overrides.
+            static int l2_bytes = 0;
+            if (!l2_bytes) {
+                int dev = 0;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, dev);
+                if (l2_bytes <= 0) l2_bytes = 64 << 20;
+            }
+            const double per_cta = (double)sm_count * kBlock * C_NC<L>() * (2.0 * Rec<L>::NREC * 4.0);
+            int cap = (int)(0.5 * (double)l2_bytes / per_cta + 0.5);
+            if (cap < 1) cap = 1;
+            if (const char* e = getenv("GPAT_PUSH_MAXCTAS")) cap = atoi(e) > 0 ? atoi(e) : cap;
+            if (per_sm > cap) per_sm = cap;
+        }
         grid = (long long)sm_count * per_sm;
         if (want < grid) grid = want > 0 ? want : 1;
         // tracking runs use their own instantiations: the production kernels carry no tracking code
