@@ -209,16 +209,28 @@ def test_interval_parity_strict(name):
     g.close()
 
 
-def test_interval_parity_fast():
-    """The production (fast-math) build over two intervals against the oracle."""
-    w, P, frames, ts = make_case("c1", grid=64, nptl=2000)
+@pytest.mark.parametrize("key,grid", [("c1", 64),    # L2B, switch-specialised (mag 1, mom 1)
+                                      ("c3", 64),    # L2B, specialised (mag 0, mom 1), open x
+                                      ("c4", 64),    # L2E (D_pp), specialised
+                                      ("c5", 32)])   # L3B, generic kernel, L2-sized residency
+def test_interval_parity_fast(key, grid):
+    """The production (fast-math) build over two intervals against the oracle: these are the
+    kernels bench.py times (particle_mover picks the specialised instantiations; the per-step
+    tests above run the generic ones through gpat_debug_push_n)."""
+    w, P, frames, ts = make_case(key, grid=grid, nptl=2000)
     g, o = pair(P, w.nptl_max, 0)
     kw = dict(nptl=2000, dist_flag=1, particle_v0=w.particle_v0, split_flag=1)
     rg, sg = run_intervals(g, frames, ts, **kw)
     ro, so = run_intervals(o, frames, ts, **kw)
     assert abs(sg - so) <= 1e-3 * so
     a, b = sort_by_key(g.download_particles()), sort_by_key(o.download_particles())
-    assert_particles_close(a, b, FRAME_RTOL, "fast c1", int_exact=False, frac_outliers=0.01)
+    if len(a) != len(b):   # an escape decided by the last bits of a position (open boundaries)
+        assert abs(len(a) - len(b)) <= 2
+        keys = lambda q: set(zip(q["origin"].tolist(), q["tag_injected"].tolist(), q["tag_splitted"].tolist()))
+        both = keys(a) & keys(b)
+        pick = lambda q: q[[k in both for k in zip(q["origin"].tolist(), q["tag_injected"].tolist(), q["tag_splitted"].tolist())]]
+        a, b = pick(a), pick(b)
+    assert_particles_close(a, b, FRAME_RTOL, f"fast {key}", int_exact=False, frac_outliers=0.01)
     # spectra: identical up to particles that sit within rounding of a bin edge
     for x, y in zip(rg, ro):
         assert np.abs(x["fglobal"] - y["fglobal"]).sum() <= 4.0
