@@ -262,6 +262,13 @@ int gpat_tracked_shape(gpat_handle h, int64_t* nsteps_tracking_max, int64_t* npt
 int gpat_download_tracked(gpat_handle h, gpat_particle* out);
 int gpat_reset_tracked(gpat_handle h);
 
+/* Particle ORDER.  The reference-order build (strict_math = 1) keeps the reference's order
+ * (injection order, swap-with-tail removal, children appended).  The production build sorts the
+ * particle arrays by grid cell at the start of every gpat_particle_mover (better locality of the
+ * field gathers); particles are identified by (origin, tag_injected, tag_splitted), never by
+ * position in the array, and no result of this interface depends on the order except which
+ * particle is dropped when nptl_max overflows (particle_module.f90:491-492, 5444-5447). */
+
 /* Replaces particle_mover (particle_module.f90:1846-1974) including both
  * remove_particles passes (particle_module.f90:5365-5403).  t0 = tstamps_mhd(frame),
  * dtf = tstamps_mhd(frame+1) - t0.  Blocking.  steps_done (may be NULL) receives

@@ -184,6 +184,7 @@ struct PushArgs {
     int sel;                 // which half of a record pair holds farray1
     int variant;             // fast build: 0 = one lane gathers its own particle, 1 = lane groups
     int generic;             // 1: never pick the switch-specialised instantiation (GPAT_PUSH_GENERIC=1)
+    int sorted;              // 1: the particle arrays were cell-sorted for this push (sort.cu)
     long long nptl;
     unsigned long long* queue;   // work counter
     unsigned long long* steps;   // push_particle_* calls
@@ -256,6 +257,9 @@ void launch_final_bc(const DevParams& prm, const PtlSoA& P, long long nmax, cons
 void launch_split(const DevParams& prm, const PtlSoA& P, long long n, long long nptl_max,
                   double split_ratio, double pmin_split, long long* counters, long long* nptl_split,
                   const ScanWork& w, long long* idx_a, cudaStream_t st, const TrackDev* trk = nullptr);
+size_t sort_scratch_bytes(long long n);
+cudaError_t launch_cell_sort(const DevParams& prm, const PtlSoA& S, const PtlSoA& D, long long n, unsigned* keys,
+                             unsigned* idx, void* tmp, size_t tmp_bytes, cudaStream_t st);
 void launch_to_aos(const PtlSoA& P, gpat_particle* out, long long n, cudaStream_t st);
 void launch_from_aos(const PtlSoA& P, const gpat_particle* in, long long n, cudaStream_t st);
 void launch_diag(const PtlSoA& P, const DiagArgs& a, int sm_count, cudaStream_t st);

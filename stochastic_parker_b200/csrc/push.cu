@@ -1428,6 +1428,9 @@ void launch_one(const DevParams& prm, const PtlSoA& P, const float* fld, const P
             const double per_cta = (double)sm_count * kBlock * C_NC<L>() * (2.0 * Rec<L>::NREC * 4.0);
             int cap = (int)(0.5 * (double)l2_bytes / per_cta + 0.5);
             if (cap < 1) cap = 1;
+            // Cell-sorted particles (sort.cu) share their records across the lanes of a warp: the working
+            // set per lane shrinks and full occupancy wins again (C5 sorted: 2/3/4 CTAs = 4.8/5.6/5.7e9).
+            if (a.sorted) cap = per_sm;
             if (const char* e = getenv("GPAT_PUSH_MAXCTAS")) cap = atoi(e) > 0 ? atoi(e) : cap;
             if (per_sm > cap) per_sm = cap;
         }
