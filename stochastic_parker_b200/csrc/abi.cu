@@ -120,7 +120,8 @@ struct gpat_sim {
     int* d_shock = nullptr;  // shock_xpos2 (gpat_inject_at_shock)
     // spatial ordering before a push (sort.cu): second particle buffer + sort scratch, lazily allocated
     int sorted_now = 0;      // the current particle order is the cell order of this interval's start
-    int sort_mode = -1;      // 0: off (GPAT_PUSH_SORT=0); anything else: sort in the production build
+    int sort_mode = -1;      // GPAT_PUSH_SORT: 0 off, 1 on, unset: on when the field store exceeds the L2
+    int l2_bytes = 0;
     void* ptl_mem2 = nullptr;
     PtlSoA P2{};
     unsigned* sort_keys = nullptr;  // 2n keys + 2n indices
@@ -461,7 +462,15 @@ int sort_before_push(gpat_sim* h)
 {
     const bool strict = h->hp.strict_math || h->hp.ndim == 1 || h->hp.focused_transport || h->hp.deltab_flag ||
                         h->hp.correlation_flag;
-    const bool want = (h->sort_mode != 0);  // default on: +4 % on C1/C2, +10 % on C4, 2x on C5 (profiles/README.md)
+    // Default: sort when the packed field store is larger than the L2 (+4 % on C1/C2, +10 % on C4, 2x
+    // on C5).  A store that is L2-resident as a whole has no locality left to gain, and clustering
+    // particles with similar step counts into the same warps costs load balance (C3: -4.5 %).
+    if (h->l2_bytes <= 0) {
+        cudaDeviceGetAttribute(&h->l2_bytes, cudaDevAttrL2CacheSize, h->device);
+        if (h->l2_bytes <= 0) h->l2_bytes = 64 << 20;
+    }
+    const bool want = (h->sort_mode == 1) ||
+                      (h->sort_mode < 0 && field_floats(h) * sizeof(float) > (size_t)h->l2_bytes);
     const long long n = h->nptl_current;
     h->sorted_now = 0;
     if (strict || !want || n < 2 || n > 0x7fffffffLL) return GPAT_OK;

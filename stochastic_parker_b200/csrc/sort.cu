@@ -6,7 +6,9 @@
 // Particles are sorted by the cell they sit in (x fastest) at the start of gpat_particle_mover: the
 // lanes of a warp, which take consecutive particles from the work queue, then gather from
 // neighbouring grid points and share their 128-byte lines.  Measured (profiles/README.md r01j):
-// C5 (3-D, store does not fit the L2) 2.8e9 -> 5.7e9 steps/s, C1 / C2 +4 %, C4 +10 %, sort included.
+// C5 (3-D, store does not fit the L2) 2.8e9 -> 5.7e9 steps/s, C1 / C2 +4 %, C4 +10 %, sort included;
+// C3, whose 68 MB store is L2-resident as a whole, loses 4.5 % (particles with similar step counts end
+// up in the same warps), so the default sorts only when the store is larger than the L2.
 // Keys: one kernel; order: cub::DeviceRadixSort (CCCL, shipped with the CUDA toolkit -- library
 // plumbing, not the hot path); permutation: one gather kernel over the 17 SoA arrays into the
 // second particle buffer, after which the two buffers swap roles.
