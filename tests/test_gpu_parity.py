@@ -792,3 +792,32 @@ def test_turbulence_maps_swap_and_db2_injection():
     assert rg == ro and ro[0] == 1200 and ro[1] > 0
     assert_particles_identical(g.download_particles(), o.download_particles(), "inject_large_db2")
     g.close()
+
+
+@pytest.mark.parametrize("key,grid", [("c1", 64), ("c5", 32)])
+def test_cell_sorted_particles_change_nothing_but_the_order(key, grid, monkeypatch):
+    """csrc/sort.cu: the production build may sort the particle arrays by grid cell before a push.
+    Every particle owns its random stream, so the sorted run must reproduce the unsorted one bit
+    for bit, particle by particle (identified by origin / tag_injected / tag_splitted), with the
+    same counters and histograms."""
+    w, P, frames, ts = make_case(key, grid=grid, nptl=3000, nframes=4)
+    Pg = P.copy()
+    Pg.strict_math = 0
+    kw = dict(nptl=3000, dist_flag=2, particle_v0=w.particle_v0, inject_new_ptl=True, split_flag=1,
+              pmin_split=1.05, split_ratio=1.05)
+    runs = []
+    for sort in ("0", "1"):
+        monkeypatch.setenv("GPAT_PUSH_SORT", sort)
+        g = GpatSim(Pg, 8 * w.nptl_max)
+        res, steps = run_intervals(g, frames, ts, **kw)
+        runs.append((g.download_particles(), res, steps, g.counters()))
+        g.close()
+    (a, ra, sa, ca), (b, rb, sb, cb) = runs
+    assert sa == sb and len(a) == len(b)
+    assert not np.array_equal(a["tag_injected"], b["tag_injected"])      # the order did change
+    assert_particles_identical(sort_by_key(a), sort_by_key(b), f"sorted vs unsorted {key}")
+    assert (ca.nptl_current, ca.nptl_split, ca.tag_max, ca.leak) == (cb.nptl_current, cb.nptl_split, cb.tag_max, cb.leak)
+    for x, y in zip(ra, rb):
+        assert np.array_equal(x["fglobal"], y["fglobal"])
+        for fx, fy in zip(x["flocal"], y["flocal"]):
+            assert (fx is None and fy is None) or np.array_equal(fx, fy)
