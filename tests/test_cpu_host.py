@@ -238,3 +238,18 @@ def test_cpp_driver_accepts_the_reference_command_line(tmp_path):
     if not _has_gpu():
         r = subprocess.run(args, capture_output=True, text=True)
         assert r.returncode == 1 and "gpat_init failed (2)" in r.stderr and "no CPU fallback" in r.stderr
+
+
+def test_fortran_interface_binds_every_entry_point():
+    """fortran/gpat_cuda_iface.f90 (the ISO_C_BINDING module of INTEGRATION.md) has one
+    `bind(C, name=...)` interface per entry point of include/gpat_cuda.h; only the test hooks
+    (gpat_debug_*, gpat_set_rng_table) are left to C callers."""
+    text = open(os.path.join(ROOT, "fortran", "gpat_cuda_iface.f90")).read()
+    bound = set(re.findall(r'bind\(C,\s*name="(gpat_[a-z0-9_]+)"\)', text))
+    declared = set(_declared_symbols())
+    test_hooks = {"gpat_debug_gradients", "gpat_debug_interp", "gpat_debug_push_n", "gpat_set_rng_table"}
+    assert declared - bound == test_hooks, sorted(declared - bound - test_hooks)
+    assert bound <= declared, sorted(bound - declared)
+    # the derived types carry the fields added to gpat_params in this round
+    for field in ("keep_rho", "duu0", "focused_transport", "deltab_flag"):
+        assert field in text, field
