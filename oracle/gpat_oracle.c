@@ -200,6 +200,22 @@ static void step_uniforms(const orc_sim* S, const gpat_particle* ptl, double u[4
     for (int j = 0; j < 4; ++j) u[j] = u01(o[j]);
 }
 
+/* The fifth uniform of a step (push_particle_2d_include_3rd_ft / _3d_ft draw ran1..ran3, then one
+ * for p and one for mu: PM:4521-4523, 4573-4576): first word of a SECOND Philox block of the same
+ * step, counter word 1 with its top bit flipped.  MT19937 mode: the next draw.  Table mode: the
+ * tables hold four uniforms per step, so these pushers are rejected there (gpat_init). */
+static double step_uniform5(const orc_sim* S, const gpat_particle* ptl)
+{
+    if (S->P.rng_mode == ORC_RNG_MT19937) return u01(mt_genrand_int32((orc_sim*)S));
+    uint64_t step = get_rng_step(ptl);
+    uint32_t ctr[4] = {(uint32_t)step, (uint32_t)(step >> 32) ^ 0x80000000u, (uint32_t)abs(ptl->tag_injected),
+                       (uint32_t)abs(ptl->tag_splitted)};
+    uint32_t key[2] = {(uint32_t)S->P.seed, (uint32_t)(S->P.seed >> 32) + (uint32_t)ptl->origin};
+    uint32_t o[4];
+    philox4x32_10(ctr, key, o);
+    return u01(o[0]);
+}
+
 /* Sequential uniform reader for injection: word k of the stream
  * ctr = (k/4, 0, tag_injected, 0), same key as above. */
 typedef struct inj_stream {
@@ -1124,6 +1140,169 @@ static void push_particle_2d_ft(orc_sim* S, gpat_particle* ptl, const double* fi
 }
 
 /* ------------------------------------------------------------------------ */
+/* push_particle_2d_include_3rd_ft (PM:4267-4623) and push_particle_3d_ft     */
+/* (PM:4930-5320), Cartesian, no acc_by_surface: one body, the 2-D variant    */
+/* has every d/dz equal to zero (x - 0, x + 0 and 0 * x are exact, so the     */
+/* shared expressions give the bits of the two-dimensional formulas).         */
+/* Five uniforms: ran1..ran3 (ran3 is drawn and unused in Cartesian runs),    */
+/* then one for p and one for mu.                                             */
+/* ------------------------------------------------------------------------ */
+static void push_particle_ft_3d_like(orc_sim* S, gpat_particle* ptl, const double* fields, const double* aux,
+                                     const kappa_type* kp, int fixed_dt, const double u[4], double u5,
+                                     double* deltax, double* deltay, double* deltaz, double* deltap,
+                                     double* deltav, double* deltamu)
+{
+    const gpat_params* P = &S->P;
+    const int full3d = (P->ndim == 3);
+    const double mu_max = (double)0.99f;
+    double vx = F(1), vy = F(2), vz = F(3), bx = F(5), by = F(6), bz = F(7);
+    double b = sqrt(sq(bx) + sq(by) + sq(bz));
+    double ib = (b < 2.220446049250313e-16) ? 0.0 : 1.0 / b;
+    double bxn = bx * ib, byn = by * ib, bzn = bz * ib;
+    double bxyn = sqrt(sq(bxn) + sq(byn));
+    double ibxyn = (bxyn < 2.220446049250313e-16) ? 0.0 : 1.0 / bxyn;
+    double dxm = P->dx, dym = P->dy, dzm = P->dz;
+    double dbx_dx = FG(13), dbx_dy = FG(14), dby_dx = FG(16), dby_dy = FG(17);
+    double dbz_dx = FG(19), dbz_dy = FG(20), db_dx = FG(22), db_dy = FG(23);
+    double dbx_dz = full3d ? FG(15) : 0.0, dby_dz = full3d ? FG(18) : 0.0;
+    double dbz_dz = full3d ? FG(21) : 0.0, db_dz = full3d ? FG(24) : 0.0;
+    double ib2 = ib * ib, ib3 = ib * ib2;
+    double vdp = (double)(1.0f / (float)P->pcharge) /
+                 sqrt(sq(P->drift1 * P->p0 / ptl->p) + sq(P->drift2 * sq(P->p0) / sq(ptl->p)));
+    double mu2 = sq(ptl->mu);
+    double muf1 = 0.5 * (1.0 - mu2), muf2 = 0.5 * (3.0 * mu2 - 1.0);
+    double kx, ky, kz, bdot_curvb, vdx, vdy, vdz;
+    if (full3d) { /* PM:5049-5063 */
+        kx = bx * dbx_dx + by * dbx_dy + bz * dbx_dz;
+        ky = bx * dby_dx + by * dby_dy + bz * dby_dz;
+        kz = bx * dbz_dx + by * dbz_dy + bz * dbz_dz;
+        bdot_curvb = bx * (dbz_dy - dby_dz) + by * (dbx_dz - dbz_dx) + bz * (dby_dx - dbx_dy);
+        vdx = vdp * (muf1 * (by * db_dz - bz * db_dy) * ib2 + mu2 * (by * kz - bz * ky) * ib3 +
+                     muf1 * bx * bdot_curvb * ib3);
+        vdy = vdp * (muf1 * (bz * db_dx - bx * db_dz) * ib2 + mu2 * (bz * kx - bx * kz) * ib3 +
+                     muf1 * by * bdot_curvb * ib3);
+    } else { /* PM:4388-4400 */
+        kx = bx * dbx_dx + by * dbx_dy;
+        ky = bx * dby_dx + by * dby_dy;
+        kz = bx * dbz_dx + by * dbz_dy;
+        bdot_curvb = bx * (dbz_dy) + by * (-dbz_dx) + bz * (dby_dx - dbx_dy);
+        vdx = vdp * (muf1 * (-bz * db_dy) * ib2 + mu2 * (by * kz - bz * ky) * ib3 +
+                     muf1 * bx * bdot_curvb * ib3);
+        vdy = vdp * (muf1 * (bz * db_dx) * ib2 + mu2 * (bz * kx - bx * kz) * ib3 +
+                     muf1 * by * bdot_curvb * ib3);
+    }
+    vdz = vdp * (muf1 * (bx * db_dy - by * db_dx) * ib2 + mu2 * (bx * ky - by * kx) * ib3 +
+                 muf1 * bz * bdot_curvb * ib3);
+    double vbx = ptl->v * ptl->mu * ib;
+    double vby = vbx * by;
+    double vbz = vbx * bz;
+    vbx = vbx * bx;
+    double dvx_dx = FG(1), dvx_dy = FG(2), dvy_dx = FG(4), dvy_dy = FG(5), dvz_dx = FG(7), dvz_dy = FG(8);
+    double dvx_dz = full3d ? FG(3) : 0.0, dvy_dz = full3d ? FG(6) : 0.0, dvz_dz = full3d ? FG(9) : 0.0;
+    double dx_dt, dy_dt, dz_dt, divv, bb_gradv, bv_gradv;
+    if (full3d) { /* PM:5104-5115 */
+        dx_dt = vx + vbx + vdx + kp->dkxx_dx + kp->dkxy_dy + kp->dkxz_dz;
+        dy_dt = vy + vby + vdy + kp->dkxy_dx + kp->dkyy_dy + kp->dkyz_dz;
+        dz_dt = vz + vbz + vdz + kp->dkxz_dx + kp->dkyz_dy + kp->dkzz_dz;
+        divv = dvx_dx + dvy_dy + dvz_dz;
+        bb_gradv = (bx * (bx * dvx_dx + by * dvx_dy + bz * dvx_dz) + by * (bx * dvy_dx + by * dvy_dy + bz * dvy_dz) +
+                    bz * (bx * dvz_dx + by * dvz_dy + bz * dvz_dz)) * ib2;
+        bv_gradv = (bx * (vx * dvx_dx + vy * dvx_dy + vz * dvx_dz) + by * (vx * dvy_dx + vy * dvy_dy + vz * dvy_dz) +
+                    bz * (vx * dvz_dx + vy * dvz_dy + vz * dvz_dz)) * ib;
+    } else { /* PM:4432-4442 */
+        dx_dt = vx + vbx + vdx + kp->dkxx_dx + kp->dkxy_dy;
+        dy_dt = vy + vby + vdy + kp->dkxy_dx + kp->dkyy_dy;
+        dz_dt = vz + vbz + vdz + kp->dkxz_dx + kp->dkyz_dy;
+        divv = dvx_dx + dvy_dy;
+        bb_gradv = (bx * (bx * dvx_dx + by * dvx_dy) + by * (bx * dvy_dx + by * dvy_dy) +
+                    bz * (bx * dvz_dx + by * dvz_dy)) * ib2;
+        bv_gradv = (bx * (vx * dvx_dx + vy * dvx_dy) + by * (vx * dvy_dx + vy * dvy_dy) +
+                    bz * (vx * dvz_dx + vy * dvz_dy)) * ib;
+    }
+    double acc_rate = -(muf1 * divv + muf2 * bb_gradv + ptl->mu * bv_gradv / ptl->v);
+    double dp_dt = ptl->p * acc_rate;
+    double dpp = 0.0;
+    if (P->dpp_wave) calc_dpp_wave_scattering(S, F(4), b, kp->kpara, ptl, &dp_dt, &dpp);
+    if (P->dpp_shear) {
+        double sxx = dvx_dx - divv / 3, syy = dvy_dy - divv / 3;
+        double szz = full3d ? dvz_dz - divv / 3 : -divv / 3;
+        double sxy = (dvx_dy + dvy_dx) / 2;
+        double sxz = full3d ? (dvx_dz + dvz_dx) / 2 : dvz_dx / 2;
+        double syz = full3d ? (dvy_dz + dvz_dy) / 2 : dvz_dy / 2;
+        calc_dpp_flow_shear(S, b, bx, by, bz, kp->knorm_para, sxx, syy, szz, sxy, sxz, syz, ptl, &dp_dt, &dpp);
+    }
+    double div_bnorm = full3d ? -(bx * db_dx + by * db_dy + bz * db_dz) * ib2 : -(bx * db_dx + by * db_dy) * ib2;
+    double dmu_dt, duu, duu_du;
+    calc_duu(S, ptl, b, aux, div_bnorm, divv, bb_gradv, bv_gradv, mu2, &dmu_dt, &duu, &duu_du);
+    if (!fixed_dt) {
+        int ok = dx_dt != 0.0 && dy_dt != 0.0 && dp_dt != 0.0 && dmu_dt != 0.0;
+        if (full3d) ok = ok && dz_dt != 0.0; /* PM:5156-5160; the 2-D variant does not test dz_dt, PM:4482-4485 */
+        if (ok) {
+            double s = (kp->skperp > 0.0) ? kp->skperp : kp->skpara;
+            double d = sq(0.5 * dxm / s);
+            d = min2(d, sq(0.5 * dym / s));
+            if (full3d) d = min2(d, sq(0.5 * dzm / s));
+            d = min2(d, sq(s / dx_dt));
+            d = min2(d, sq(s / dy_dt));
+            if (full3d) d = min2(d, sq(s / dz_dt));
+            d = min2(d, (double)0.1f * ptl->p / fabs(dp_dt));
+            d = min2(d, (double)0.1f / fabs(dmu_dt));
+            d = min2(d, 2.0 * duu / sq(dmu_dt));
+            ptl->dt = d;
+        } else {
+            ptl->dt = S->dt_min;
+        }
+        if (ptl->dt < S->dt_min) ptl->dt = S->dt_min;
+        if (ptl->dt > S->dt_max) ptl->dt = S->dt_max;
+    }
+    double sdt = sqrt(ptl->dt);
+    double sqrt3 = sqrt(3.0);
+    double ran1 = (2.0 * u[0] - 1.0) * sqrt3;
+    double ran2 = (2.0 * u[1] - 1.0) * sqrt3;
+    /* ran3 = u[2] is drawn and not used by the Cartesian branch, PM:4523, 5233 */
+    *deltax = dx_dt * ptl->dt + (-bxn * bzn * kp->skperp * ibxyn * ran1 - byn * kp->skperp * ibxyn * ran2) * sdt;
+    *deltay = dy_dt * ptl->dt + (-byn * bzn * kp->skperp * ibxyn * ran1 + bxn * kp->skperp * ibxyn * ran2) * sdt;
+    *deltaz = dz_dt * ptl->dt + bxyn * kp->skperp * ran1 * sdt;
+    ran1 = (2.0 * u[3] - 1.0) * sqrt3;
+    *deltap = dp_dt * ptl->dt + ran1 * sqrt(2 * dpp) * sdt;
+    *deltav = ptl->v * *deltap / ptl->p;
+    ran1 = (2.0 * u5 - 1.0) * sqrt3;
+    *deltamu = dmu_dt * ptl->dt + ran1 * sqrt(2 * duu) * sdt;
+    ptl->x = ptl->x + *deltax;
+    ptl->y = ptl->y + *deltay;
+    ptl->z = ptl->z + *deltaz;
+    ptl->mu = ptl->mu + *deltamu;
+    ptl->t = ptl->t + ptl->dt;
+    if (ptl->mu > mu_max) {
+        *deltamu = mu_max - (ptl->mu - *deltamu);
+        ptl->mu = mu_max;
+    } else if (ptl->mu < -mu_max) {
+        *deltamu = -mu_max - (ptl->mu - *deltamu);
+        ptl->mu = -mu_max;
+    }
+    if (P->acc_region_flag == 1) {
+        if (particle_in_acceleration_region(S, ptl)) {
+            ptl->p = ptl->p + *deltap;
+            ptl->v = ptl->v + *deltav;
+        } else {
+            *deltap = 0.0;
+            *deltav = 0.0;
+        }
+    } else {
+        ptl->p = ptl->p + *deltap;
+        ptl->v = ptl->v + *deltav;
+    }
+    if (ptl->p < 0.25 * P->p0) {
+        ptl->v = ptl->v - *deltav;
+        *deltav = ptl->v * 0.25 * P->p0 / ptl->p - ptl->v;
+        ptl->v = ptl->v + *deltav;
+        ptl->p = ptl->p - *deltap;
+        *deltap = 0.25 * P->p0 - ptl->p;
+        ptl->p = 0.25 * P->p0;
+    }
+}
+
+/* ------------------------------------------------------------------------ */
 /* push_particle_2d_include_3rd (PM:3979-4245) and push_particle_3d           */
 /* (PM:4625-4907): identical structure; 2-D sets every d/dz to zero.          */
 /* ------------------------------------------------------------------------ */
@@ -1307,7 +1486,10 @@ static void one_push(orc_sim* S, gpat_particle* ptl, double t0, double dtf, int 
     else
         calc_kappa(S, ptl, fields, aux, &kp);
     step_uniforms(S, ptl, u);
-    if (P->focused_transport) /* PM:1647-1668: only the 2-D Cartesian FT pusher is restated */
+    if (P->focused_transport && (P->ndim == 3 || (P->ndim == 2 && P->include_3rd_dim))) /* PM:1653-1668 */
+        push_particle_ft_3d_like(S, ptl, fields, aux, &kp, fixed_dt, u, step_uniform5(S, ptl), deltax, deltay,
+                                 deltaz, deltap, deltav, deltamu);
+    else if (P->focused_transport) /* PM:1659-1662; the 1-D FT pusher reads an unassigned dx_dt */
         push_particle_2d_ft(S, ptl, fields, aux, &kp, fixed_dt, u, deltax, deltay, deltap, deltav, deltamu);
     else if (P->ndim == 1)
         push_particle_1d(S, ptl, fields, &kp, fixed_dt, u, deltax, deltap);

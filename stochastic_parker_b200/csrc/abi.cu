@@ -195,8 +195,13 @@ int validate(const gpat_params* p, std::string& why)
         why = "1-D with mag_dependency = 1 reads an uninitialised db_dx in the reference (undefined there)";
         return 1;
     }
-    if (p->focused_transport && (p->ndim != 2 || p->include_3rd_dim)) {
-        why = "focused transport: only the 2-D Cartesian pusher (push_particle_2d_ft) is on the GPU path";
+    if (p->focused_transport && p->ndim == 1) {
+        // particle_module.f90:3225 assigns dv_dt, :3270 and :3304 read dx_dt
+        why = "focused transport in 1-D: push_particle_1d_ft advances x with a dx_dt it never assigns (undefined in the reference)";
+        return 1;
+    }
+    if (p->focused_transport && (p->ndim == 3 || p->include_3rd_dim) && p->rng_mode == GPAT_RNG_TABLE) {
+        why = "push_particle_2d_include_3rd_ft / _3d_ft draw five uniforms per step; the uniform table holds four";
         return 1;
     }
     if (p->spherical_coord) { why = "spherical coordinates are outside the GPU path"; return 1; }

@@ -710,6 +710,192 @@ __device__ __forceinline__ void push_2d_ft(const DevParams& prm, const PushArgs&
 }
 #endif
 
+#if GPAT_STRICT
+// push_particle_2d_include_3rd_ft (particle_module.f90:4267-4623) and push_particle_3d_ft (:4930-5320),
+// Cartesian, no acc_by_surface: one body, the 2-D variant with every d/dz equal to zero (x - 0, x + 0
+// and 0 * x are exact).  Uniforms: u0 u1 (u2 = ran3 is drawn and unused in Cartesian runs), u3 for p,
+// u4 for mu -- the first word of a second Philox block of the same step.
+template <int L>
+__device__ __forceinline__ void push_ft_3d_like(const DevParams& prm, const PushArgs& a,
+                                                const double (&F)[Rec<L>::NREC], double u0, double u1, double u3,
+                                                double u4, Lane& q, bool fixed_dt, const double* aux)
+{
+    if constexpr (Rec<L>::EXT) {
+        constexpr bool D3 = (Rec<L>::NDIM == 3);
+        const double mu_max = (double)0.99f;
+        BField B;
+        VGrad V;
+        double vx, vy, vz, rho;
+        if constexpr (!D3) {
+            vx = F[s2::vx]; vy = F[s2::vy]; vz = F[s2::vz]; rho = F[s2::rho];
+            B.bx = F[s2::bx]; B.by = F[s2::by]; B.bz = F[s2::bz];
+            B.dbx_dx = F[s2::dbx_dx]; B.dbx_dy = F[s2::dbx_dy]; B.dby_dx = F[s2::dby_dx];
+            B.dby_dy = F[s2::dby_dy]; B.dbz_dx = F[s2::dbz_dx]; B.dbz_dy = F[s2::dbz_dy];
+            B.db_dx = F[s2::db_dx]; B.db_dy = F[s2::db_dy];
+            B.dbx_dz = B.dby_dz = B.dbz_dz = B.db_dz = 0.0;
+            V.dvx_dx = F[s2::dvx_dx]; V.dvy_dy = F[s2::dvy_dy]; V.dvz_dz = 0.0;
+            V.dvx_dy = F[s2::dvx_dy]; V.dvy_dx = F[s2::dvy_dx]; V.dvz_dx = F[s2::dvz_dx]; V.dvz_dy = F[s2::dvz_dy];
+            V.dvx_dz = V.dvy_dz = 0.0;
+        } else {
+            vx = F[s3::vx]; vy = F[s3::vy]; vz = F[s3::vz]; rho = F[s3::rho];
+            B.bx = F[s3::bx]; B.by = F[s3::by]; B.bz = F[s3::bz];
+            B.dbx_dx = F[s3::dbx_dx]; B.dbx_dy = F[s3::dbx_dy]; B.dbx_dz = F[s3::dbx_dz];
+            B.dby_dx = F[s3::dby_dx]; B.dby_dy = F[s3::dby_dy]; B.dby_dz = F[s3::dby_dz];
+            B.dbz_dx = F[s3::dbz_dx]; B.dbz_dy = F[s3::dbz_dy]; B.dbz_dz = F[s3::dbz_dz];
+            B.db_dx = F[s3::db_dx]; B.db_dy = F[s3::db_dy]; B.db_dz = F[s3::db_dz];
+            V.dvx_dx = F[s3::dvx_dx]; V.dvy_dy = F[s3::dvy_dy]; V.dvz_dz = F[s3::dvz_dz];
+            V.dvx_dy = F[s3::dvx_dy]; V.dvx_dz = F[s3::dvx_dz]; V.dvy_dx = F[s3::dvy_dx];
+            V.dvy_dz = F[s3::dvy_dz]; V.dvz_dx = F[s3::dvz_dx]; V.dvz_dy = F[s3::dvz_dy];
+        }
+        const double bx = B.bx, by = B.by, bz = B.bz;
+        B.b = sqrt(sq(bx) + sq(by) + sq(bz));
+        const double b = B.b;
+        Kappa k;
+        if (D3) calc_kappa<true, true>(prm, B, q.p, q.mu, k, aux);
+        else calc_kappa<true, false>(prm, B, q.p, q.mu, k, aux);
+        const double ib = (b < kEps) ? 0.0 : 1.0 / b;
+        const double bxn = bx * ib, byn = by * ib, bzn = bz * ib;
+        const double bxyn = sqrt(sq(bxn) + sq(byn));
+        const double ibxyn = (bxyn < kEps) ? 0.0 : 1.0 / bxyn;
+        const double ib2 = ib * ib, ib3 = ib * ib2;
+        const double vdp = (double)(1.0f / (float)prm.pcharge) /
+                           sqrt(sq(prm.drift1 * prm.p0 / q.p) + sq(prm.drift2 * sq(prm.p0) / sq(q.p)));
+        const double mu2 = sq(q.mu);
+        const double muf1 = 0.5 * (1.0 - mu2), muf2 = 0.5 * (3.0 * mu2 - 1.0);
+        double kx, ky, kz, bdot_curvb, vdx, vdy;
+        if (D3) {  // particle_module.f90:5049-5063
+            kx = bx * B.dbx_dx + by * B.dbx_dy + bz * B.dbx_dz;
+            ky = bx * B.dby_dx + by * B.dby_dy + bz * B.dby_dz;
+            kz = bx * B.dbz_dx + by * B.dbz_dy + bz * B.dbz_dz;
+            bdot_curvb = bx * (B.dbz_dy - B.dby_dz) + by * (B.dbx_dz - B.dbz_dx) + bz * (B.dby_dx - B.dbx_dy);
+            vdx = vdp * (muf1 * (by * B.db_dz - bz * B.db_dy) * ib2 + mu2 * (by * kz - bz * ky) * ib3 +
+                         muf1 * bx * bdot_curvb * ib3);
+            vdy = vdp * (muf1 * (bz * B.db_dx - bx * B.db_dz) * ib2 + mu2 * (bz * kx - bx * kz) * ib3 +
+                         muf1 * by * bdot_curvb * ib3);
+        } else {  // particle_module.f90:4388-4400
+            kx = bx * B.dbx_dx + by * B.dbx_dy;
+            ky = bx * B.dby_dx + by * B.dby_dy;
+            kz = bx * B.dbz_dx + by * B.dbz_dy;
+            bdot_curvb = bx * (B.dbz_dy) + by * (-B.dbz_dx) + bz * (B.dby_dx - B.dbx_dy);
+            vdx = vdp * (muf1 * (-bz * B.db_dy) * ib2 + mu2 * (by * kz - bz * ky) * ib3 +
+                         muf1 * bx * bdot_curvb * ib3);
+            vdy = vdp * (muf1 * (bz * B.db_dx) * ib2 + mu2 * (bz * kx - bx * kz) * ib3 +
+                         muf1 * by * bdot_curvb * ib3);
+        }
+        const double vdz = vdp * (muf1 * (bx * B.db_dy - by * B.db_dx) * ib2 + mu2 * (bx * ky - by * kx) * ib3 +
+                                  muf1 * bz * bdot_curvb * ib3);
+        double vbx = q.v * q.mu * ib;
+        const double vby = vbx * by;
+        const double vbz = vbx * bz;
+        vbx = vbx * bx;
+        double dx_dt, dy_dt, dz_dt, divv, bb_gradv, bv_gradv;
+        if (D3) {  // particle_module.f90:5104-5115
+            dx_dt = vx + vbx + vdx + k.dkxx_dx + k.dkxy_dy + k.dkxz_dz;
+            dy_dt = vy + vby + vdy + k.dkxy_dx + k.dkyy_dy + k.dkyz_dz;
+            dz_dt = vz + vbz + vdz + k.dkxz_dx + k.dkyz_dy + k.dkzz_dz;
+            divv = V.dvx_dx + V.dvy_dy + V.dvz_dz;
+            bb_gradv = (bx * (bx * V.dvx_dx + by * V.dvx_dy + bz * V.dvx_dz) +
+                        by * (bx * V.dvy_dx + by * V.dvy_dy + bz * V.dvy_dz) +
+                        bz * (bx * V.dvz_dx + by * V.dvz_dy + bz * V.dvz_dz)) * ib2;
+            bv_gradv = (bx * (vx * V.dvx_dx + vy * V.dvx_dy + vz * V.dvx_dz) +
+                        by * (vx * V.dvy_dx + vy * V.dvy_dy + vz * V.dvy_dz) +
+                        bz * (vx * V.dvz_dx + vy * V.dvz_dy + vz * V.dvz_dz)) * ib;
+        } else {  // particle_module.f90:4432-4442
+            dx_dt = vx + vbx + vdx + k.dkxx_dx + k.dkxy_dy;
+            dy_dt = vy + vby + vdy + k.dkxy_dx + k.dkyy_dy;
+            dz_dt = vz + vbz + vdz + k.dkxz_dx + k.dkyz_dy;
+            divv = V.dvx_dx + V.dvy_dy;
+            bb_gradv = (bx * (bx * V.dvx_dx + by * V.dvx_dy) + by * (bx * V.dvy_dx + by * V.dvy_dy) +
+                        bz * (bx * V.dvz_dx + by * V.dvz_dy)) * ib2;
+            bv_gradv = (bx * (vx * V.dvx_dx + vy * V.dvx_dy) + by * (vx * V.dvy_dx + vy * V.dvy_dy) +
+                        bz * (vx * V.dvz_dx + vy * V.dvz_dy)) * ib;
+        }
+        const double acc_rate = -(muf1 * divv + muf2 * bb_gradv + q.mu * bv_gradv / q.v);
+        double dp_dt = q.p * acc_rate;
+        double dpp = 0.0;
+        momentum_diffusion(prm, B, V, rho, divv, k, q.p, dp_dt, dpp);
+        const double div_bnorm = D3 ? -(bx * B.db_dx + by * B.db_dy + bz * B.db_dz) * ib2
+                                    : -(bx * B.db_dx + by * B.db_dy) * ib2;
+        double dmu_dt = q.v * div_bnorm + q.mu * divv - 3 * q.mu * bb_gradv - 2 * bv_gradv / q.v;
+        dmu_dt = dmu_dt * (1 - mu2) * 0.5;
+        const double h0 = (double)0.2f;
+        const double dtmp = pow(fabs(q.mu), prm.gamma_turb - 1) + h0;
+        double duu = prm.duu0 * (1 - mu2) * dtmp;
+        double duu_du;
+        if (q.mu > 0.0) duu_du = prm.duu0 * (-2 * q.mu * dtmp + (1 - mu2) * pow(fabs(q.mu), prm.gamma_turb - 2));
+        else if (q.mu < 0.0) duu_du = prm.duu0 * (-2 * q.mu * dtmp - (1 - mu2) * pow(fabs(q.mu), prm.gamma_turb - 2));
+        else duu_du = 0.0;
+        double duu_norm = 1.0;
+        if (prm.mag_dependency == 1) duu_norm = duu_norm * pow(b, 2.0 - prm.gamma_turb);
+        if (aux && prm.deltab_flag) duu_norm = duu_norm * aux[0];
+        if (aux && prm.correlation_flag) duu_norm = duu_norm * pow(aux[8], 1.0 - prm.gamma_turb);
+        if (prm.momentum_dependency == 1) duu_norm = duu_norm * pow(q.p / prm.p0, prm.gamma_turb - 1);
+        duu_du = duu_du * duu_norm;
+        duu = duu * duu_norm;
+        dmu_dt = dmu_dt + duu_du;
+        if (!fixed_dt) {
+            double d;
+            bool ok = dx_dt != 0.0 && dy_dt != 0.0 && dp_dt != 0.0 && dmu_dt != 0.0;
+            if (D3) ok = ok && dz_dt != 0.0;  // particle_module.f90:5156-5160; the 2-D variant does not test dz_dt
+            if (ok) {
+                const double s = (k.skperp > 0.0) ? k.skperp : k.skpara;
+                d = sq(0.5 * prm.dx / s);
+                d = min2(d, sq(0.5 * prm.dy / s));
+                if (D3) d = min2(d, sq(0.5 * prm.dz / s));
+                d = min2(d, sq(s / dx_dt));
+                d = min2(d, sq(s / dy_dt));
+                if (D3) d = min2(d, sq(s / dz_dt));
+                d = min2(d, (double)0.1f * q.p / fabs(dp_dt));
+                d = min2(d, (double)0.1f / fabs(dmu_dt));
+                d = min2(d, 2.0 * duu / sq(dmu_dt));
+            } else {
+                d = a.dt_min;
+            }
+            if (d < a.dt_min) d = a.dt_min;
+            if (d > a.dt_max) d = a.dt_max;
+            q.dt = d;
+        }
+        const double sdt = sqrt(q.dt);
+        const double sqrt3 = 1.7320508075688772;
+        double ran1 = (2.0 * u0 - 1.0) * sqrt3;
+        const double ran2 = (2.0 * u1 - 1.0) * sqrt3;
+        const double ddx = dx_dt * q.dt + (-bxn * bzn * k.skperp * ibxyn * ran1 - byn * k.skperp * ibxyn * ran2) * sdt;
+        const double ddy = dy_dt * q.dt + (-byn * bzn * k.skperp * ibxyn * ran1 + bxn * k.skperp * ibxyn * ran2) * sdt;
+        const double ddz = dz_dt * q.dt + bxyn * k.skperp * ran1 * sdt;
+        ran1 = (2.0 * u3 - 1.0) * sqrt3;
+        double ddp = dp_dt * q.dt + ran1 * sqrt(2 * dpp) * sdt;
+        double ddv = q.v * ddp / q.p;
+        ran1 = (2.0 * u4 - 1.0) * sqrt3;
+        double ddmu = dmu_dt * q.dt + ran1 * sqrt(2 * duu) * sdt;
+        q.x = q.x + ddx;
+        q.y = q.y + ddy;
+        q.z = q.z + ddz;
+        q.mu = q.mu + ddmu;
+        q.t = q.t + q.dt;
+        if (q.mu > mu_max) { ddmu = mu_max - (q.mu - ddmu); q.mu = mu_max; }
+        else if (q.mu < -mu_max) { ddmu = -mu_max - (q.mu - ddmu); q.mu = -mu_max; }
+        if (prm.acc_region_flag == 1) {
+            if (in_acc_region(prm, q)) { q.p = q.p + ddp; q.v = q.v + ddv; }
+            else { ddp = 0.0; ddv = 0.0; }
+        } else {
+            q.p = q.p + ddp;
+            q.v = q.v + ddv;
+        }
+        const double pfloor = 0.25 * prm.p0;
+        if (q.p < pfloor) {
+            q.v = q.v - ddv;
+            ddv = q.v * 0.25 * prm.p0 / q.p - q.v;
+            q.v = q.v + ddv;
+            q.p = q.p - ddp;
+            ddp = pfloor - q.p;
+            q.p = pfloor;
+        }
+        q.dxl = ddx; q.dyl = ddy; q.dzl = ddz;
+        q.dpl = ddp; q.dvl = ddv; q.dmul = ddmu;
+    }
+}
+#endif
+
 // One call of push_particle_*: everything between the BC test and the step counter.
 template <int L, bool TRACK = false>
 __device__ __forceinline__ void push_once(const DevParams& prm, const PushArgs& a,
@@ -754,10 +940,19 @@ __device__ __forceinline__ void push_once(const DevParams& prm, const PushArgs& 
             push_1d<L>(prm, a, F, u0, u1, q, fixed_dt, auxp);
             return;
         }
-        if (prm.focused_transport) {
+    }
+    if (prm.focused_transport) {
+        if (D3 || (EXT && prm.include_3rd_dim)) {
+            // fifth uniform: first word of a second Philox block of this step (counter word 1, top bit flipped)
+            const unsigned long long step = q.rng - 1;
+            const uint4 r5 = philox4x32_10(make_uint4((unsigned)step, (unsigned)(step >> 32) ^ 0x80000000u,
+                                                       (unsigned)tag_inj, (unsigned)tag_spl),
+                                           prm.key0, prm.key1 + (unsigned)q.origin);
+            push_ft_3d_like<L>(prm, a, F, u0, u1, u3, u01(r5.x), q, fixed_dt, auxp);
+        } else if constexpr (!D3) {
             push_2d_ft<L>(prm, a, F, u0, u1, u2, u3, q, fixed_dt, auxp);
-            return;
         }
+        return;
     }
 #endif
 

@@ -661,3 +661,120 @@ def test_deltab_and_correlation_step_matches_numpy_restatement():
                          u[before["tag_injected"], 0], before["x"], before["y"], before["t"], qdrift,
                          aux=np.ones_like(aux) * np.array([1, 0, 0, 0] * 4))[0]
     assert np.max(np.abs(x0 - x)) > 1e-6
+
+
+# ---- focused transport, 2-D + 3rd dimension and 3-D (PM:4267-4623, 4930-5320) ----------------------
+def _np_step_ft_3d_like(P, F, ptl, u, u5, dt_min, dt_max):
+    """Independent numpy restatement of one push_particle_2d_include_3rd_ft / push_particle_3d_ft
+    step (Cartesian), with the kappa branch it is called with (PM:2294-2351 / 2392-2450, kpp = -kperp)."""
+    full3d = P.ndim == 3
+    f = lambda k: F[:, k - 1]
+    g = lambda k: F[:, 8 + k - 1]
+    Z = np.zeros(len(F))
+    p, v, mu = ptl["p"], ptl["v"], ptl["mu"]
+    vx, vy, vz, rho, bx, by, bz = f(1), f(2), f(3), f(4), f(5), f(6), f(7)
+    b = np.sqrt(bx**2 + by**2 + bz**2)
+    ib = 1.0 / b
+    ib2, ib3 = ib * ib, ib * ib * ib
+    dbx_dx, dbx_dy, dby_dx, dby_dy, dbz_dx, dbz_dy, db_dx, db_dy = g(13), g(14), g(16), g(17), g(19), g(20), g(22), g(23)
+    dbx_dz, dby_dz, dbz_dz, db_dz = (g(15), g(18), g(21), g(24)) if full3d else (Z, Z, Z, Z)
+    knp = b ** (P.gamma_turb - 2.0) if P.mag_dependency == 1 else np.ones_like(b)
+    knorm = knp * (p / P.p0) ** P.pindex if P.momentum_dependency == 1 else knp
+    kpara = P.kpara0 * knorm
+    kperp = kpara * P.kret
+    skpara, skperp = np.sqrt(2 * kpara), np.sqrt(2 * kperp)
+    gm2 = P.gamma_turb - 2.0
+    if P.mag_dependency == 1:
+        # 3-D: no 1/B (PM:2405-2409); 2-D + 3rd: with 1/B and no z term (PM:2310-2313)
+        dkdx, dkdy, dkdz = (db_dx * gm2, db_dy * gm2, db_dz * gm2) if full3d else (db_dx * ib * gm2, db_dy * ib * gm2, Z)
+    else:
+        dkdx = dkdy = dkdz = Z
+    kpp = -kperp
+    dk = lambda lead, d, bi, bj, dbi, dbj, dbm: lead + kpp * d * bi * bj * ib2 + kpp * ((dbi * bj + bi * dbj) * ib2 - 2.0 * bi * bj * dbm * ib3)
+    dkxx_dx = kperp * dkdx + kpp * dkdx * bx**2 * ib2 + 2.0 * kpp * bx * (dbx_dx * b - bx * db_dx) * ib3
+    dkyy_dy = kperp * dkdy + kpp * dkdy * by**2 * ib2 + 2.0 * kpp * by * (dby_dy * b - by * db_dy) * ib3
+    dkzz_dz = kperp * dkdz + kpp * dkdz * bz**2 * ib2 + 2.0 * kpp * bz * (dbz_dz * b - bz * db_dz) * ib3
+    dkxy_dx = dk(0.0, dkdx, bx, by, dbx_dx, dby_dx, db_dx)
+    dkxy_dy = dk(0.0, dkdy, bx, by, dbx_dy, dby_dy, db_dy)
+    dkxz_dx = dk(0.0, dkdx, bx, bz, dbx_dx, dbz_dx, db_dx)
+    dkxz_dz = dk(0.0, dkdz, bx, bz, dbx_dz, dbz_dz, db_dz)
+    dkyz_dy = dk(0.0, dkdy, by, bz, dby_dy, dbz_dy, db_dy)
+    dkyz_dz = dk(0.0, dkdz, by, bz, dby_dz, dbz_dz, db_dz)
+    vdp = float(np.float32(1.0) / np.float32(P.pcharge)) / np.sqrt((P.drift1 * P.p0 / p) ** 2 + (P.drift2 * P.p0**2 / p**2) ** 2)
+    mu2 = mu**2
+    muf1, muf2 = 0.5 * (1.0 - mu2), 0.5 * (3.0 * mu2 - 1.0)
+    kx = bx * dbx_dx + by * dbx_dy + bz * dbx_dz
+    ky = bx * dby_dx + by * dby_dy + bz * dby_dz
+    kz = bx * dbz_dx + by * dbz_dy + bz * dbz_dz
+    bdc = bx * (dbz_dy - dby_dz) + by * (dbx_dz - dbz_dx) + bz * (dby_dx - dbx_dy)
+    vdx = vdp * (muf1 * (by * db_dz - bz * db_dy) * ib2 + mu2 * (by * kz - bz * ky) * ib3 + muf1 * bx * bdc * ib3)
+    vdy = vdp * (muf1 * (bz * db_dx - bx * db_dz) * ib2 + mu2 * (bz * kx - bx * kz) * ib3 + muf1 * by * bdc * ib3)
+    vdz = vdp * (muf1 * (bx * db_dy - by * db_dx) * ib2 + mu2 * (bx * ky - by * kx) * ib3 + muf1 * bz * bdc * ib3)
+    vb = v * mu * ib
+    dvx_dx, dvx_dy, dvy_dx, dvy_dy, dvz_dx, dvz_dy = g(1), g(2), g(4), g(5), g(7), g(8)
+    dvx_dz, dvy_dz, dvz_dz = (g(3), g(6), g(9)) if full3d else (Z, Z, Z)
+    dx_dt = vx + vb * bx + vdx + dkxx_dx + dkxy_dy + dkxz_dz
+    dy_dt = vy + vb * by + vdy + dkxy_dx + dkyy_dy + dkyz_dz
+    dz_dt = vz + vb * bz + vdz + dkxz_dx + dkyz_dy + dkzz_dz
+    divv = dvx_dx + dvy_dy + dvz_dz
+    bbg = (bx * (bx * dvx_dx + by * dvx_dy + bz * dvx_dz) + by * (bx * dvy_dx + by * dvy_dy + bz * dvy_dz)
+           + bz * (bx * dvz_dx + by * dvz_dy + bz * dvz_dz)) * ib2
+    bvg = (bx * (vx * dvx_dx + vy * dvx_dy + vz * dvx_dz) + by * (vx * dvy_dx + vy * dvy_dy + vz * dvy_dz)
+           + bz * (vx * dvz_dx + vy * dvz_dy + vz * dvz_dz)) * ib
+    dp_dt = p * -(muf1 * divv + muf2 * bbg + mu * bvg / v)
+    div_bn = -(bx * db_dx + by * db_dy + bz * db_dz) * ib2
+    dmu_dt = (v * div_bn + mu * divv - 3 * mu * bbg - 2 * bvg / v) * (1 - mu2) * 0.5
+    dtmp = np.abs(mu) ** (P.gamma_turb - 1) + float(np.float32(0.2))
+    norm = np.ones_like(b)
+    if P.mag_dependency == 1:
+        norm = norm * b ** (2.0 - P.gamma_turb)
+    if P.momentum_dependency == 1:
+        norm = norm * (p / P.p0) ** (P.gamma_turb - 1)
+    duu = P.duu0 * (1 - mu2) * dtmp * norm
+    dmu_dt = dmu_dt + P.duu0 * (-2 * mu * dtmp + np.sign(mu) * (1 - mu2) * np.abs(mu) ** (P.gamma_turb - 2)) * norm
+    s = np.where(skperp > 0, skperp, skpara)
+    cands = [(0.5 * P.dx / s) ** 2, (0.5 * P.dy / s) ** 2, (s / dx_dt) ** 2, (s / dy_dt) ** 2,
+             float(np.float32(0.1)) * p / np.abs(dp_dt), float(np.float32(0.1)) / np.abs(dmu_dt), 2.0 * duu / dmu_dt**2]
+    if full3d:
+        cands += [(0.5 * P.dz / s) ** 2, (s / dz_dt) ** 2]
+    dt = np.clip(np.minimum.reduce(cands), dt_min, dt_max)
+    sdt, s3 = np.sqrt(dt), np.sqrt(3.0)
+    r1, r2, rp = [(2.0 * u[:, k] - 1.0) * s3 for k in (0, 1, 3)]
+    rm = (2.0 * u5 - 1.0) * s3
+    bxn, byn, bzn = bx * ib, by * ib, bz * ib
+    bxyn = np.sqrt(bxn**2 + byn**2)
+    x = ptl["x"] + dx_dt * dt + (-bxn * bzn * skperp / bxyn * r1 - byn * skperp / bxyn * r2) * sdt
+    y = ptl["y"] + dy_dt * dt + (-byn * bzn * skperp / bxyn * r1 + bxn * skperp / bxyn * r2) * sdt
+    z = ptl["z"] + dz_dt * dt + bxyn * skperp * r1 * sdt
+    mun = np.clip(mu + dmu_dt * dt + rm * np.sqrt(2 * duu) * sdt, -float(np.float32(0.99)), float(np.float32(0.99)))
+    dp = dp_dt * dt
+    pn = p + dp
+    vn = v + v * dp / p
+    low = pn < 0.25 * P.p0
+    vn = np.where(low, v * 0.25 * P.p0 / pn, vn)
+    pn = np.where(low, 0.25 * P.p0, pn)
+    return x, y, z, pn, vn, mun, ptl["t"] + dt, dt
+
+
+@pytest.mark.parametrize("key,grid,cli", [("c1", 48, dict(include_3rd_dim=1)), ("c5", 24, {})])
+def test_focused_transport_3d_like_step_matches_numpy_restatement(key, grid, cli):
+    w, P, frames, _ = make_case(key, grid=grid, nptl=300, cli=dict(cli, focused_transport=1, duu_init=5.0),
+                                conf=dict(r1=4, r2=8, r3=12) if key == "c5" else None)
+    o = Oracle(P, w.nptl_max)
+    o.upload_fields(0, frames[0])
+    o.upload_fields(1, frames[1])
+    o.inject_uniform(300, 0.0, 0, w.particle_v0, 0.0, w.dt_out, box_of(P), w.power_index)
+    before = o.download_particles()
+    assert o.debug_push_n(0.0, w.dt_out, 1) == 300
+    after = o.download_particles()
+    F = o.interp(before["x"], before["y"], before["z"], (before["t"] - 0.0) / w.dt_out)
+    # the uniforms of step 0: block A = Philox((0, 0, tag, 1)), fifth = word 0 of Philox((0, 0x80000000, tag, 1))
+    key0, key1 = P.seed & 0xFFFFFFFF, (P.seed >> 32) & 0xFFFFFFFF
+    uA = np.array([[w_ / 4294967295.0 for w_ in philox4x32_10((0, 0, int(t), 1), (key0, key1))] for t in before["tag_injected"]])
+    u5 = np.array([philox4x32_10((0, 0x80000000, int(t), 1), (key0, key1))[0] / 4294967295.0 for t in before["tag_injected"]])
+    x, y, z, p, v, mu, t, dt = _np_step_ft_3d_like(P, F, before, uA, u5, P.dt_min_rel * w.dt_out, P.dt_max_rel * w.dt_out)
+    for name, ref in (("x", x), ("y", y), ("z", z), ("p", p), ("v", v), ("mu", mu), ("t", t), ("dt", dt)):
+        scale = np.maximum(np.abs(ref), 1.0 if name in "xyz" else 1e-300)
+        err = np.abs(after[name] - ref) / scale
+        assert err.max() < 1e-12, (name, err.max())
+    assert np.any(after["z"] != before["z"])

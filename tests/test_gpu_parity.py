@@ -132,6 +132,9 @@ CASES = {
                                     cli=dict(focused_transport=1, duu_init=5.0)),
     "c4_2d_focused_transport_dpp": dict(key="c4", grid=64, conf=dict(dt_min_rel=1e-3),
                                         cli=dict(focused_transport=1, duu_init=5.0, nlgc=1, kperp_kpara=0.05)),
+    "c1_2d_ft_include_3rd": dict(key="c1", grid=64, conf=dict(dt_min_rel=1e-3),
+                                 cli=dict(focused_transport=1, duu_init=5.0, include_3rd_dim=1)),
+    "c5_3d_ft": dict(key="c5", grid=32, conf=dict(dt_min_rel=1e-3), cli=dict(focused_transport=1, duu_init=5.0)),
     "s1_shock_1d": dict(key="s1", grid=256),
     "s1_shock_1d_dpp_nlgc": dict(key="s1", grid=256, conf=dict(dt_min_rel=1e-3),
                                  cli=dict(dpp_wave=1, dpp_shear=1, nlgc=1, kperp_kpara=0.05)),
@@ -335,8 +338,9 @@ def test_edge_cases():
     with pytest.raises(GpatError):
         g.inject_uniform(4, 0.0, 7, 1.0, 0.0, 0.1, box_of(P), 6.2)
     bad = P.copy()
-    bad.focused_transport = 1       # only the 2-D Cartesian FT pusher is on the GPU path ...
-    bad.include_3rd_dim = 1         # ... not push_particle_2d_include_3rd_ft
+    bad.focused_transport = 1       # the five-uniform FT pushers cannot replay a four-column table
+    bad.include_3rd_dim = 1
+    bad.rng_mode = 1
     with pytest.raises(GpatError):
         GpatSim(bad, 64)
     bad = P.copy()
