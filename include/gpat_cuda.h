@@ -119,7 +119,8 @@ typedef struct gpat_params {
     int32_t nlgc;
     double kperp_kpara;
     double duu0; /* duu_init (set_duu_params, particle_module.f90:279-283): focused transport only */
-    /* focused_transport = 1: 2-D Cartesian push_particle_2d_ft only (reference-order build);
+    /* focused_transport = 1: Cartesian push_particle_2d_ft / _2d_include_3rd_ft / _3d_ft (reference-
+     * order build); 1-D is rejected (push_particle_1d_ft reads an unassigned dx_dt);
      * spherical_coord, nonuniform_grid, acc_by_surface must be 0 on the GPU path (error otherwise) */
     int32_t focused_transport, spherical_coord, nonuniform_grid;
     /* deltab_flag / correlation_flag: turbulence maps via gpat_upload_turbulence */
