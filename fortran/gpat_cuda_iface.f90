@@ -12,7 +12,7 @@ module gpat_cuda
     private
     public :: gpat_params, gpat_hist_spec, gpat_particle, gpat_counters, gpat_timings
     public :: gpat_init, gpat_set_params, gpat_finalize, gpat_last_error
-    public :: gpat_upload_fields, gpat_upload_turbulence, gpat_prefetch_fields, gpat_swap_fields
+    public :: gpat_upload_fields, gpat_upload_turbulence, gpat_upload_acc_surface, gpat_prefetch_fields, gpat_swap_fields
     public :: gpat_inject_uniform, gpat_inject_targeted, gpat_inject_at_shock, gpat_particle_mover, gpat_split
     public :: gpat_init_tracking, gpat_tracked_shape, gpat_download_tracked, gpat_reset_tracked
     public :: gpat_download_particles, gpat_upload_particles
@@ -48,7 +48,8 @@ module gpat_cuda
         integer(c_int32_t) :: npp_global, nmu_global
         type(gpat_hist_spec) :: local(4)
         integer(c_int64_t) :: seed
-        integer(c_int32_t) :: rng_mode, mpi_rank, strict_math, pad2
+        integer(c_int32_t) :: rng_mode, mpi_rank, strict_math
+        integer(c_int32_t) :: surface_norm1, surface_norm2, surface2_existed, is_intersection, pad2
     end type gpat_params
 
     !< struct gpat_particle == particle_type (particle_module.f90:38-50), 104 bytes
@@ -113,6 +114,14 @@ module gpat_cuda
             type(c_ptr), value :: h, data
             integer(c_int), value :: which, slot
         end function gpat_upload_turbulence
+
+        !< read_acc_surface (acc_region_surface.f90:121); heights = c_loc(acc_surfaceK1 or K2)
+        integer(c_int) function gpat_upload_acc_surface(h, which, slot, heights) &
+                bind(C, name="gpat_upload_acc_surface")
+            import :: c_ptr, c_int
+            type(c_ptr), value :: h, heights
+            integer(c_int), value :: which, slot
+        end function gpat_upload_acc_surface
 
         !< frame pipeline: start the H2D copy of a frame already read into farray-shaped host
         !< memory (e.g. frame tf+1 during the push of frame tf); a later gpat_upload_fields with

@@ -278,6 +278,15 @@ int main(int argc, char** argv)
     P.duu0 = cli.d("-du");  // set_duu_params, stochastic-mhd.f90:207
     P.spherical_coord = (int)cli.i("-sc"); P.nonuniform_grid = 1 - (int)cli.i("-ug");
     P.deltab_flag = (int)cli.i("-db"); P.correlation_flag = (int)cli.i("-co"); P.acc_by_surface = (int)cli.i("-as");
+    // surface_norm1/2 ('+x' ... '-z', stochastic-mhd.f90:911-938): anything but x / y in the second character
+    // is z and anything but '+' in the first is the negative direction (acc_region_surface.f90:44-50, 350-366)
+    auto norm_code = [](const std::string& v) {
+        const char sign = v.size() > 0 ? v[0] : ' ', ax = v.size() > 1 ? v[1] : ' ';
+        const int axis = ax == 'x' ? 1 : (ax == 'y' ? 2 : 3);
+        return sign == '+' ? axis : -axis;
+    };
+    P.surface_norm1 = norm_code(cli.s("-sn1")); P.surface_norm2 = norm_code(cli.s("-sn2"));
+    P.surface2_existed = cli.b("-s2e") ? 1 : 0; P.is_intersection = cli.b("-ii") ? 1 : 0;
     P.seed = (uint64_t)cli.i("-seed"); P.rng_mode = GPAT_RNG_PHILOX; P.mpi_rank = 0;
     P.strict_math = (int)cli.i("-strict");
     P.keep_rho = cli.b("-ir") ? 1 : 0;  // inject_large_rho interpolates the density (particle_module.f90:1448)
@@ -413,9 +422,32 @@ int main(int argc, char** argv)
         return 0;
     };
 
+    // <surface_filenameK>_NNNN.dat: float64 heights over the ghosted plane (read_acc_surface,
+    // acc_region_surface.f90:118-206; stochastic-mhd.f90:323-334, 405-416)
+    std::vector<double> surf;
+    auto upload_surfaces = [&](int tframe, int slot) -> int {
+        if (!P.acc_by_surface) return 0;
+        for (int k = 0; k < (P.surface2_existed ? 2 : 1); ++k) {
+            const int axis = std::abs(k ? P.surface_norm2 : P.surface_norm1) - 1;
+            const size_t n = (size_t)(axis == 0 ? mc.ny + 4 : mc.nx + 4) * (axis == 2 ? mc.ny + 4 : mc.nz + 4);
+            char name[512];
+            std::snprintf(name, sizeof(name), "%s%s_%04d.dat", dir_mhd.c_str(), cli.s(k ? "-sf2" : "-sf1").c_str(), tframe);
+            surf.resize(n);
+            FILE* f = std::fopen(name, "rb");
+            if (!f) return die(h, "open acceleration surface file", -1);
+            const size_t got = std::fread(surf.data(), sizeof(double), n, f);
+            std::fclose(f);
+            if (got != n) return die(h, "read acceleration surface file", -1);
+            int rc = gpat_upload_acc_surface(h, k, slot, surf.data());
+            if (rc) return rc;
+        }
+        return 0;
+    };
+
     // ---- solve_transport_equation (stochastic-mhd.f90:312-567) ----
     if (!read_frame(dir_mhd, t_start, ncell * 8, frame)) return die(h, "read first mhd_data frame", -1);
     CK(gpat_upload_fields(h, 0, frame.data(), 8, 0), "gpat_upload_fields");
+    CK(upload_surfaces(t_start, 0), "gpat_upload_acc_surface");
     CK(upload_maps(t_start, 0), "gpat_upload_turbulence");
     uint64_t total_steps = 0;
     auto wall0 = std::chrono::steady_clock::now();
@@ -425,6 +457,7 @@ int main(int argc, char** argv)
         if (single_frame == 0 && tf <= tmax_mhd) {  // :400-447
             if (!read_frame(dir_mhd, tf, ncell * 8, frame)) return die(h, "read mhd_data frame", -1);
             CK(gpat_upload_fields(h, P.time_interp ? 1 : 0, frame.data(), 8, 0), "gpat_upload_fields");
+            CK(upload_surfaces(tf, P.time_interp ? 1 : 0), "gpat_upload_acc_surface");
             CK(upload_maps(tf, P.time_interp ? 1 : 0), "gpat_upload_turbulence");
         }
         const double t0 = tstamp(tf - 1), dtf = tstamp(tf) - tstamp(tf - 1);  // tstamps_mhd(tf - t_start), particle_module.f90:1868

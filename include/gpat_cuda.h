@@ -121,9 +121,10 @@ typedef struct gpat_params {
     double duu0; /* duu_init (set_duu_params, particle_module.f90:279-283): focused transport only */
     /* focused_transport = 1: Cartesian push_particle_2d_ft / _2d_include_3rd_ft / _3d_ft (reference-
      * order build); 1-D is rejected (push_particle_1d_ft reads an unassigned dx_dt);
-     * spherical_coord, nonuniform_grid, acc_by_surface must be 0 on the GPU path (error otherwise) */
+     * spherical_coord and nonuniform_grid must be 0 on the GPU path (error otherwise) */
     int32_t focused_transport, spherical_coord, nonuniform_grid;
-    /* deltab_flag / correlation_flag: turbulence maps via gpat_upload_turbulence */
+    /* deltab_flag / correlation_flag: turbulence maps via gpat_upload_turbulence;
+     * acc_by_surface: 3-D only, heights via gpat_upload_acc_surface */
     int32_t deltab_flag, correlation_flag, acc_by_surface;
     /* diagnostics */
     int32_t npp_global, nmu_global;
@@ -136,6 +137,11 @@ typedef struct gpat_params {
     /* arithmetic: 0 = fast (FMA contraction, fused time-blend), 1 = strict
      * (no contraction, reference operation order; used by the parity tests) */
     int32_t strict_math;
+    /* acceleration surfaces (acc_by_surface = 1, 3-D only; acc_region_surface.f90:29-94):
+     * surface_normK = sign * (axis + 1) for the reference's "+x" .. "-z" strings, i.e. +1/-1 x,
+     * +2/-2 y, +3/-3 z; surface2_existed, is_intersection as in stochastic-mhd.f90:116-117 */
+    int32_t surface_norm1, surface_norm2;
+    int32_t surface2_existed, is_intersection;
     int32_t pad2_;
 } gpat_params;
 
@@ -180,6 +186,14 @@ int gpat_upload_fields(gpat_handle h, int slot, const float* f, int nvar, int wi
  * 2589-2604), D_mumu (:3143-3148) and inject_large_db2; runs that use them take the
  * reference-order build of the push kernel. */
 int gpat_upload_turbulence(gpat_handle h, int which, int slot, const float* data);
+
+/* Acceleration surfaces (`-as 1`, 3-D).  Replaces read_acc_surface (acc_region_surface.f90:121-243):
+ * heights = acc_surfaceK1/K2, real(dp), shaped (-1:n1+2, -1:n2+2) column-major with (n1, n2) the
+ * grid sizes of the two axes other than the surface normal, in x < y < z order; which = 0/1 for
+ * surface 1/2, slot as in gpat_upload_fields (gpat_swap_fields also stands for copy_acc_surface,
+ * :390-396).  interp_acc_surface (:255-334) and check_above_acc_surface (:342-388) run inside the
+ * 3-D pushers (particle_module.f90:4887-4892, 5297-5303), reference-order build. */
+int gpat_upload_acc_surface(gpat_handle h, int which, int slot, const double* heights);
 
 /* Frame pipeline (stochastic-mhd.f90:401-447 reads frame tf at the top of every iteration,
  * serially).  gpat_prefetch_fields starts the host->device copy of a frame the caller has

@@ -39,6 +39,7 @@
 #define NGRADS 24
 #define NVAR (NFIELDS + NGRADS)
 
+struct orc_sim;
 typedef struct orc_sim {
     gpat_params P;
     int nxg, nyg, nzg;        /* array extents with ghosts: nx+4, ny+4, nz+4 | 1 */
@@ -48,6 +49,8 @@ typedef struct orc_sim {
      * comp 0 the value, 1..3 its gradients; allocated lazily, 1.0 everywhere like the reference */
     float* aux1;
     float* aux2;
+    /* acc_surface11/12, 21/22 (acc_region_surface.f90:12-13): [which][slot], real(dp), (-1:n1+2, -1:n2+2) */
+    double* surf[2][2];
     gpat_particle* ptls;      /* PM:65 */
     gpat_particle* escaped;   /* PM:134 */
     int64_t nptl_current, nptl_old, nptl_max, nptl_split, nptl_inject;
@@ -71,6 +74,7 @@ typedef struct orc_sim {
 } orc_sim;
 
 static inline double sq(double x) { return x * x; }
+static int check_above_acc_surface(const struct orc_sim* S, double x, double y, double z, double h1, double h2);
 static void track_after_push(orc_sim* S, gpat_particle* ptl); /* particle tracking, below */
 
 /* ------------------------------------------------------------------------ */
@@ -284,6 +288,7 @@ void orc_destroy(orc_sim* S)
     if (!S) return;
     free(S->farray1); free(S->farray2); free(S->ptls); free(S->escaped);
     free(S->aux1); free(S->aux2);
+    for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) free(S->surf[a][b]);
     free(S->tags_tracking); free(S->particles_tracked);
     free(S);
 }
@@ -374,6 +379,90 @@ void orc_calc_gradients(orc_sim* S, int slot)
 }
 
 /* ------------------------------------------------------------------------ */
+/* acceleration surfaces: acc_region_surface.f90 (3-D only)                   */
+/* ------------------------------------------------------------------------ */
+static void surf_dims(const orc_sim* S, int norm, int* n1, int* n2)
+{
+    int axis = abs(norm) - 1; /* 0 x, 1 y, 2 z */
+    if (axis == 0) { *n1 = S->P.ny + 4; *n2 = S->P.nz + 4; }      /* ARS:34-35 */
+    else if (axis == 1) { *n1 = S->P.nx + 4; *n2 = S->P.nz + 4; }
+    else { *n1 = S->P.nx + 4; *n2 = S->P.ny + 4; }
+}
+
+void orc_set_acc_surface(orc_sim* S, int which, int slot, const double* heights)
+{
+    int n1, n2;
+    surf_dims(S, which ? S->P.surface_norm2 : S->P.surface_norm1, &n1, &n2);
+    free(S->surf[which][slot]);
+    S->surf[which][slot] = (double*)malloc(sizeof(double) * (size_t)n1 * n2);
+    memcpy(S->surf[which][slot], heights, sizeof(double) * (size_t)n1 * n2);
+}
+
+/* interp_acc_surface, ARS:255-334 */
+static void interp_acc_surface(const orc_sim* S, const int pos[3], const double w[8], double rt, double* h1,
+                               double* h2)
+{
+    const gpat_params* P = &S->P;
+    int i1 = 0, j1 = 0;
+    double w2[4]; /* weights_2d(1,1) (2,1) (1,2) (2,2) */
+    int cur_axis = -1;
+    double out[2] = {0.0, 0.0};
+    for (int k = 0; k < 2; ++k) {
+        if (k == 1 && !P->surface2_existed) { out[1] = 0.0; break; }
+        int norm = k ? P->surface_norm2 : P->surface_norm1;
+        int axis = abs(norm) - 1;
+        if (axis != cur_axis) { /* the second surface reuses i1, j1, weights_2d when the axes agree */
+            if (axis == 0) {
+                i1 = pos[1]; j1 = pos[2];
+                w2[0] = w[0] + w[1]; w2[1] = w[2] + w[3]; w2[2] = w[4] + w[5]; w2[3] = w[6] + w[7];
+            } else if (axis == 1) {
+                i1 = pos[0]; j1 = pos[2];
+                w2[0] = w[0] + w[2]; w2[1] = w[1] + w[3]; w2[2] = w[4] + w[6]; w2[3] = w[5] + w[7];
+            } else {
+                i1 = pos[0]; j1 = pos[1];
+                w2[0] = w[0] + w[4]; w2[1] = w[1] + w[5]; w2[2] = w[2] + w[6]; w2[3] = w[3] + w[7];
+            }
+            cur_axis = axis;
+        }
+        int n1, n2;
+        surf_dims(S, norm, &n1, &n2);
+        int a = i1 + 1, b = j1 + 1; /* Fortran lower bound -1 */
+        if (a < 0) a = 0;
+        if (a > n1 - 2) a = n1 - 2;
+        if (b < 0) b = 0;
+        if (b > n2 - 2) b = n2 - 2;
+        double hh[2] = {0.0, 0.0};
+        for (int slot = 0; slot < (P->time_interp ? 2 : 1); ++slot) {
+            const double* sf = S->surf[k][slot];
+            double acc = 0.0; /* sum() over the 2x2 section in array-element order */
+            acc = acc + sf[a + (size_t)n1 * b] * w2[0];
+            acc = acc + sf[(a + 1) + (size_t)n1 * b] * w2[1];
+            acc = acc + sf[a + (size_t)n1 * (b + 1)] * w2[2];
+            acc = acc + sf[(a + 1) + (size_t)n1 * (b + 1)] * w2[3];
+            hh[slot] = acc;
+        }
+        out[k] = P->time_interp ? hh[0] * (1.0 - rt) + hh[1] * rt : hh[0];
+    }
+    *h1 = out[0];
+    *h2 = out[1];
+}
+
+/* check_above_acc_surface, ARS:342-388 */
+static int check_above_acc_surface(const orc_sim* S, double x, double y, double z, double h1, double h2)
+{
+    const gpat_params* P = &S->P;
+    const double c[3] = {x, y, z};
+    double ph = c[abs(P->surface_norm1) - 1];
+    int in = (P->surface_norm1 > 0) ? (ph > h1) : (ph < h1);
+    if (P->surface2_existed) {
+        ph = c[abs(P->surface_norm2) - 1];
+        int in2 = (P->surface_norm2 > 0) ? (ph > h2) : (ph < h2);
+        in = P->is_intersection ? (in && in2) : (in || in2);
+    }
+    return in;
+}
+
+/* ------------------------------------------------------------------------ */
 /* turbulence maps: read_magnetic_fluctuation / read_correlation_length        */
 /* (MD:306-497: the file holds the slab array then the 2-D array),             */
 /* calc_grad_sigma2_slab/_2d, calc_grad_lc_slab/_2d (MD:771-1604: the same     */
@@ -441,6 +530,13 @@ void orc_copy_fields(orc_sim* S) /* MD:1920-1923; copy_magnetic_fluctuation / _c
 {
     memcpy(S->farray1, S->farray2, sizeof(float) * (size_t)NVAR * S->nxg * S->nyg * S->nzg);
     if (S->aux2) memcpy(aux_of(S, 0), S->aux2, sizeof(float) * (size_t)NAUX * S->nxg * S->nyg * S->nzg);
+    for (int k = 0; k < 2; ++k) /* copy_acc_surface, ARS:390-396 */
+        if (S->surf[k][1]) {
+            int n1, n2;
+            surf_dims(S, k ? S->P.surface_norm2 : S->P.surface_norm1, &n1, &n2);
+            if (!S->surf[k][0]) S->surf[k][0] = (double*)malloc(sizeof(double) * (size_t)n1 * n2);
+            memcpy(S->surf[k][0], S->surf[k][1], sizeof(double) * (size_t)n1 * n2);
+        }
 }
 
 /* interp_magnetic_fluctuation + interp_correlation_length (MD:1806-1915): 16 values =
@@ -842,13 +938,21 @@ static void calc_dpp_flow_shear(const orc_sim* S, double b, double bx, double by
 static inline double min2(double a, double b) { return (b < a) ? b : a; }
 
 /* common tail of every pusher: momentum update, PM:3589-3605 */
+/* sh: the two interpolated surface heights of acc_by_surface runs (3-D pushers only), or NULL */
+static int in_acceleration_region(const orc_sim* S, const gpat_particle* ptl, const double* sh)
+{
+    int in = particle_in_acceleration_region(S, ptl);
+    if (sh) in = in && check_above_acc_surface(S, ptl->x, ptl->y, ptl->z, sh[0], sh[1]); /* PM:4889-4892 */
+    return in;
+}
+
 static void update_momentum(const orc_sim* S, gpat_particle* ptl, double dp_dt, double dpp,
-                            double sdt, double ranp, double* deltap)
+                            double sdt, double ranp, double* deltap, const double* sh)
 {
     const gpat_params* P = &S->P;
     *deltap = dp_dt * ptl->dt + ranp * sqrt(2.0 * dpp) * sdt;
     if (P->acc_region_flag == 1) {
-        if (particle_in_acceleration_region(S, ptl))
+        if (in_acceleration_region(S, ptl, sh))
             ptl->p = ptl->p + *deltap;
         else
             *deltap = 0.0;
@@ -913,7 +1017,7 @@ static void push_particle_1d(orc_sim* S, gpat_particle* ptl, const double* field
     ptl->x = ptl->x + *deltax;
     ptl->t = ptl->t + ptl->dt;
     double ranp = (2.0 * u[1] - 1.0) * sqrt3;
-    update_momentum(S, ptl, dp_dt, dpp, sdt, ranp, deltap);
+    update_momentum(S, ptl, dp_dt, dpp, sdt, ranp, deltap, NULL);
 }
 
 /* ------------------------------------------------------------------------ */
@@ -984,7 +1088,7 @@ static void push_particle_2d(orc_sim* S, gpat_particle* ptl, const double* field
     ptl->z = ptl->z + deltaz;
     ptl->t = ptl->t + ptl->dt;
     double ranp = (2.0 * u[3] - 1.0) * sqrt3;
-    update_momentum(S, ptl, dp_dt, dpp, sdt, ranp, deltap);
+    update_momentum(S, ptl, dp_dt, dpp, sdt, ranp, deltap, NULL);
 }
 
 /* ------------------------------------------------------------------------ */
@@ -1150,7 +1254,7 @@ static void push_particle_2d_ft(orc_sim* S, gpat_particle* ptl, const double* fi
 static void push_particle_ft_3d_like(orc_sim* S, gpat_particle* ptl, const double* fields, const double* aux,
                                      const kappa_type* kp, int fixed_dt, const double u[4], double u5,
                                      double* deltax, double* deltay, double* deltaz, double* deltap,
-                                     double* deltav, double* deltamu)
+                                     double* deltav, double* deltamu, const double* sh)
 {
     const gpat_params* P = &S->P;
     const int full3d = (P->ndim == 3);
@@ -1281,7 +1385,7 @@ static void push_particle_ft_3d_like(orc_sim* S, gpat_particle* ptl, const doubl
         ptl->mu = -mu_max;
     }
     if (P->acc_region_flag == 1) {
-        if (particle_in_acceleration_region(S, ptl)) {
+        if (in_acceleration_region(S, ptl, full3d ? sh : NULL)) { /* PM:5297-5303 */
             ptl->p = ptl->p + *deltap;
             ptl->v = ptl->v + *deltav;
         } else {
@@ -1308,7 +1412,7 @@ static void push_particle_ft_3d_like(orc_sim* S, gpat_particle* ptl, const doubl
 /* ------------------------------------------------------------------------ */
 static void push_particle_3d_like(orc_sim* S, gpat_particle* ptl, const double* fields,
                                   kappa_type* kp, int fixed_dt, const double u[4], double* deltax,
-                                  double* deltay, double* deltaz, double* deltap)
+                                  double* deltay, double* deltaz, double* deltap, const double* sh)
 {
     const gpat_params* P = &S->P;
     const int full3d = (P->ndim == 3);
@@ -1385,7 +1489,7 @@ static void push_particle_3d_like(orc_sim* S, gpat_particle* ptl, const double* 
     ptl->z = ptl->z + *deltaz;
     ptl->t = ptl->t + ptl->dt;
     double ranp = (2.0 * u[3] - 1.0) * sqrt3;
-    update_momentum(S, ptl, dp_dt, dpp, sdt, ranp, deltap);
+    update_momentum(S, ptl, dp_dt, dpp, sdt, ranp, deltap, full3d ? sh : NULL);
 }
 
 /* ------------------------------------------------------------------------ */
@@ -1486,9 +1590,15 @@ static void one_push(orc_sim* S, gpat_particle* ptl, double t0, double dtf, int 
     else
         calc_kappa(S, ptl, fields, aux, &kp);
     step_uniforms(S, ptl, u);
+    double shv[2] = {0.0, 0.0};
+    const double* sh = NULL;
+    if (P->acc_by_surface && P->ndim == 3) { /* PM:1662-1665, 1683-1686 */
+        interp_acc_surface(S, pos, w, rt, &shv[0], &shv[1]);
+        sh = shv;
+    }
     if (P->focused_transport && (P->ndim == 3 || (P->ndim == 2 && P->include_3rd_dim))) /* PM:1653-1668 */
         push_particle_ft_3d_like(S, ptl, fields, aux, &kp, fixed_dt, u, step_uniform5(S, ptl), deltax, deltay,
-                                 deltaz, deltap, deltav, deltamu);
+                                 deltaz, deltap, deltav, deltamu, sh);
     else if (P->focused_transport) /* PM:1659-1662; the 1-D FT pusher reads an unassigned dx_dt */
         push_particle_2d_ft(S, ptl, fields, aux, &kp, fixed_dt, u, deltax, deltay, deltap, deltav, deltamu);
     else if (P->ndim == 1)
@@ -1496,7 +1606,7 @@ static void one_push(orc_sim* S, gpat_particle* ptl, double t0, double dtf, int 
     else if (P->ndim == 2 && !P->include_3rd_dim)
         push_particle_2d(S, ptl, fields, &kp, fixed_dt, u, deltax, deltay, deltap);
     else
-        push_particle_3d_like(S, ptl, fields, &kp, fixed_dt, u, deltax, deltay, deltaz, deltap);
+        push_particle_3d_like(S, ptl, fields, &kp, fixed_dt, u, deltax, deltay, deltaz, deltap, sh);
     set_rng_step(ptl, get_rng_step(ptl) + 1);
 }
 

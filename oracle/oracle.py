@@ -92,6 +92,11 @@ class Oracle:
             raise ValueError("turbulence map has the wrong size")
         self.lib.orc_set_turbulence(self.h, C.c_int(which), C.c_int(slot), ptr(data))
 
+    def upload_acc_surface(self, which: int, slot: int, heights: np.ndarray):
+        """acc_surfaceK1 (slot 0) / acc_surfaceK2 (slot 1) of surface `which`, float64 (n2, n1) C-order."""
+        heights = np.ascontiguousarray(heights, dtype=np.float64)
+        self.lib.orc_set_acc_surface(self.h, C.c_int(which), C.c_int(slot), ptr(heights))
+
     def get_fields(self, slot: int) -> np.ndarray:
         out = np.empty(self.grid_shape + (NVAR,), dtype=np.float32)
         self.lib.orc_get_fields(self.h, C.c_int(slot), ptr(out))

@@ -66,7 +66,9 @@ class Params(C.Structure):
         ("seed", C.c_uint64),
         ("rng_mode", C.c_int32),
         ("mpi_rank", C.c_int32),
-        ("strict_math", C.c_int32), ("pad2_", C.c_int32),
+        ("strict_math", C.c_int32),
+        ("surface_norm1", C.c_int32), ("surface_norm2", C.c_int32),
+        ("surface2_existed", C.c_int32), ("is_intersection", C.c_int32), ("pad2_", C.c_int32),
     ]
 
     def copy(self) -> "Params":
@@ -124,6 +126,7 @@ SIGNATURES = {
     "gpat_upload_fields": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]),
     "gpat_swap_fields": (C.c_int, [C.c_void_p]),
     "gpat_upload_turbulence": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "gpat_upload_acc_surface": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "gpat_prefetch_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "gpat_inject_uniform": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_double,
                                       C.c_double, C.c_double, _DP, C.c_double]),

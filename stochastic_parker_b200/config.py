@@ -46,7 +46,19 @@ class ConfReader:
 # command-line defaults of the driver (stochastic-mhd.f90:871-881 for drift, 635-637 nlgc)
 CLI_DEFAULTS = dict(drift_param1=4.0e7, drift_param2=2.0e8, charge=-1, nlgc=0, kperp_kpara=0.01,
                     dpp_wave=0, dpp_shear=0, weak_scattering=1, tau0=1.0, check_drift_2d=0,
-                    include_3rd_dim=0, time_interp=1, focused_transport=0, duu_init=1.0)
+                    include_3rd_dim=0, time_interp=1, focused_transport=0, duu_init=1.0,
+                    # acceleration surfaces (stochastic-mhd.f90:899-938)
+                    acc_by_surface=0, surface_norm1="+y", surface_norm2="-y", surface2_existed=0,
+                    is_intersection=0)
+
+
+def surface_norm_code(s: str) -> int:
+    """'+x' / '-z' ... -> sign * (axis + 1), the C ABI's encoding of surface_norm1/2.  As in
+    acc_region_surface.f90 (44-50, 350-366) anything but 'x' / 'y' in the second character is z and
+    anything but '+' in the first is the negative direction."""
+    s = (str(s) + "  ")[:2]
+    axis = {"x": 1, "y": 2}.get(s[1], 3)
+    return axis if s[0] == "+" else -axis
 
 
 def build_params(conf_text: str, mhd_cfg: dict, ndim: int, nframes: int = 1 << 30,
@@ -121,6 +133,11 @@ def build_params(conf_text: str, mhd_cfg: dict, ndim: int, nframes: int = 1 << 3
     P.focused_transport = ft
     P.duu0 = float(c["duu_init"])  # set_duu_params, particle_module.f90:279-283
     P.kperp_kpara = float(c["kperp_kpara"])
+    P.acc_by_surface = int(c["acc_by_surface"])
+    P.surface_norm1 = surface_norm_code(c["surface_norm1"])
+    P.surface_norm2 = surface_norm_code(c["surface_norm2"])
+    P.surface2_existed = int(bool(c["surface2_existed"]))
+    P.is_intersection = int(bool(c["is_intersection"]))
     P.seed = seed
     P.rng_mode = 0
     P.mpi_rank = mpi_rank

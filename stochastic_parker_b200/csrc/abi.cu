@@ -128,6 +128,9 @@ struct gpat_sim {
     void* sort_tmp = nullptr;
     size_t sort_tmp_bytes = 0;
     long long sort_cap = 0;
+    double* d_surf[2] = {nullptr, nullptr};  // acceleration surfaces: two halves each
+    int surf_n1[2] = {0, 0}, surf_n2[2] = {0, 0};
+    bool have_surf[2][2] = {{false, false}, {false, false}};
     float* aux = nullptr;    // turbulence maps (gpat_upload_turbulence), 32 floats per grid point
     bool have_aux[2] = {false, false};
     int* d_tags = nullptr;
@@ -206,7 +209,14 @@ int validate(const gpat_params* p, std::string& why)
     }
     if (p->spherical_coord) { why = "spherical coordinates are outside the GPU path"; return 1; }
     if (p->nonuniform_grid) { why = "non-uniform grids are outside the GPU path"; return 1; }
-    if (p->acc_by_surface) { why = "acc_by_surface is outside the GPU path"; return 1; }
+    if (p->acc_by_surface) {
+        auto bad = [](int n) { return n == 0 || n < -3 || n > 3; };
+        if (p->ndim != 3) { why = "acc_by_surface needs ndim = 3 (only the 3-D pushers use the surfaces)"; return 1; }
+        if (bad(p->surface_norm1) || (p->surface2_existed && bad(p->surface_norm2))) {
+            why = "surface_norm must be +-1 (x), +-2 (y) or +-3 (z)";
+            return 1;
+        }
+    }
     if (p->include_3rd_dim && p->ndim != 2) { why = "include_3rd_dim needs ndim = 2"; return 1; }
     if (p->npp_global < 1 || p->nmu_global < 1) { why = "npp_global/nmu_global must be >= 1"; return 1; }
     if (p->pcharge == 0) { why = "pcharge must be non-zero"; return 1; }
@@ -284,6 +294,8 @@ void fill_dev_params(gpat_sim* h)
     d.check_drift_2d = p.check_drift_2d; d.include_3rd_dim = p.include_3rd_dim; d.nlgc = p.nlgc;
     d.focused_transport = p.focused_transport; d.duu0 = p.duu0; d.pcharge = p.pcharge;
     d.deltab_flag = p.deltab_flag; d.correlation_flag = p.correlation_flag;
+    d.acc_by_surface = p.acc_by_surface; d.surface_norm1 = p.surface_norm1; d.surface_norm2 = p.surface_norm2;
+    d.surface2_existed = p.surface2_existed; d.is_intersection = p.is_intersection;
     d.key0 = (unsigned)p.seed;
     d.key1 = (unsigned)(p.seed >> 32);
     d.rng_mode = p.rng_mode;
@@ -466,7 +478,7 @@ int push_counters(gpat_sim* h)
 int sort_before_push(gpat_sim* h)
 {
     const bool strict = h->hp.strict_math || h->hp.ndim == 1 || h->hp.focused_transport || h->hp.deltab_flag ||
-                        h->hp.correlation_flag;
+                        h->hp.correlation_flag || h->hp.acc_by_surface;
     // Default: sort when the packed field store is larger than the L2 (+4 % on C1/C2, +10 % on C4, 2x
     // on C5).  A store that is L2-resident as a whole has no locality left to gain, and clustering
     // particles with similar step counts into the same warps costs load balance (C3: -4.5 %).
@@ -529,6 +541,18 @@ int run_push(gpat_sim* h, double t0, double dtf, int nsteps_interval, int num_fi
     a.rng_max_steps = h->table_steps;
     a.trk = h->trk;
     a.aux = h->aux;
+    for (int k = 0; k < 2; ++k) {
+        a.surf[k] = h->d_surf[k];
+        a.surf_n1[k] = h->surf_n1[k];
+        a.surf_n2[k] = h->surf_n2[k];
+    }
+    if (h->hp.acc_by_surface) {
+        const int nslot = h->dp.time_interp ? 2 : 1;
+        for (int k = 0; k < (h->hp.surface2_existed ? 2 : 1); ++k)
+            for (int sl = 0; sl < nslot; ++sl)
+                if (!h->have_surf[k][sl])
+                    return fail(h, GPAT_ERR_STATE, "the acceleration surfaces have not been uploaded (gpat_upload_acc_surface)");
+    }
     if ((h->hp.deltab_flag && !h->have_aux[0]) || (h->hp.correlation_flag && !h->have_aux[1]))
         return fail(h, GPAT_ERR_STATE, "the deltab / correlation maps have not been uploaded (gpat_upload_turbulence)");
     CU(cudaMemsetAsync(h->d_queue, 0, 2 * sizeof(unsigned long long), h->st));
@@ -537,7 +561,7 @@ int run_push(gpat_sim* h, double t0, double dtf, int nsteps_interval, int num_fi
         // 1-D (push_particle_1d), focused transport (push_particle_2d_ft) and the turbulence maps
         // (deltab / correlation) exist in the reference-order build only: not throughput paths yet
         if (h->hp.strict_math || h->hp.ndim == 1 || h->hp.focused_transport || h->hp.deltab_flag ||
-            h->hp.correlation_flag) launch_push_strict(h->layout, h->dp, h->P, h->fld, a, h->sm_count, h->st);
+            h->hp.correlation_flag || h->hp.acc_by_surface) launch_push_strict(h->layout, h->dp, h->P, h->fld, a, h->sm_count, h->st);
         else launch_push_fast(h->layout, h->dp, h->P, h->fld, a, h->sm_count, h->st);
         h->tm.total_launches++;
     }
@@ -656,6 +680,7 @@ int gpat_finalize(gpat_handle h)
     void* ptrs[] = {h->ptl_mem, h->esc_mem, h->d_counters, h->d_nptl_split, h->d_leak, h->d_queue,
                     h->w.tile_counts, h->w.tile_offsets, h->idx_a, h->idx_b, h->fld, h->stage, h->stage2,
                     h->d_tags, h->d_tracked, h->d_shock, h->aux, h->ptl_mem2, h->sort_keys, h->sort_tmp,
+                    h->d_surf[0], h->d_surf[1],
                     h->d_fglobal, h->d_flocal[0], h->d_flocal[1], h->d_flocal[2], h->d_flocal[3],
                     h->d_fesc, h->d_pthr, h->d_sums, h->d_minmax, h->d_quick, h->d_table, h->d_aos};
     for (void* p : ptrs)
@@ -737,6 +762,33 @@ int gpat_upload_turbulence(gpat_handle h, int which, int slot, const float* data
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->st));
     h->have_aux[which] = true;
+    return GPAT_OK;
+}
+
+int gpat_upload_acc_surface(gpat_handle h, int which, int slot, const double* heights)
+{
+    if (!h || !heights || (which != 0 && which != 1) || (slot != 0 && slot != 1))
+        return fail(h, GPAT_ERR_INVALID, "gpat_upload_acc_surface: bad arguments");
+    if (!h->hp.acc_by_surface) return fail(h, GPAT_ERR_STATE, "gpat_upload_acc_surface: acc_by_surface is 0");
+    if (which == 1 && !h->hp.surface2_existed)
+        return fail(h, GPAT_ERR_INVALID, "gpat_upload_acc_surface: surface2_existed is false");
+    if (slot == 1 && !h->dp.time_interp)
+        return fail(h, GPAT_ERR_INVALID, "gpat_upload_acc_surface: slot 1 exists only with time_interp = 1");
+    CU(cudaSetDevice(h->device));
+    const int axis = std::abs(which ? h->hp.surface_norm2 : h->hp.surface_norm1) - 1;
+    const int n1 = (axis == 0) ? h->hp.ny + 4 : h->hp.nx + 4;       // acc_region_surface.f90:33-39
+    const int n2 = (axis == 2) ? h->hp.ny + 4 : h->hp.nz + 4;
+    const size_t n = (size_t)n1 * n2;
+    if (!h->d_surf[which]) {
+        CU(cudaMalloc(&h->d_surf[which], 2 * n * sizeof(double)));
+        CU(cudaMemsetAsync(h->d_surf[which], 0, 2 * n * sizeof(double), h->st));  // acc_surface = 0.0
+        h->surf_n1[which] = n1;
+        h->surf_n2[which] = n2;
+    }
+    const int half = h->dp.time_interp ? ((slot == 0) ? h->sel : (h->sel ^ 1)) : 0;
+    CU(cudaMemcpyAsync(h->d_surf[which] + (size_t)half * n, heights, n * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    CU(cudaStreamSynchronize(h->st));
+    h->have_surf[which][slot] = true;
     return GPAT_OK;
 }
 

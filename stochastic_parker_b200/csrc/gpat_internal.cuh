@@ -111,6 +111,8 @@ struct DevParams {
     int dpp_wave, dpp_shear, weak_scattering, check_drift_2d, include_3rd_dim, nlgc;
     int focused_transport;  // 2-D Cartesian push_particle_2d_ft, reference-order build only
     int deltab_flag, correlation_flag;  // turbulence maps (reference-order build only)
+    // acceleration surfaces (3-D, reference-order build only): normal = sign * (axis + 1)
+    int acc_by_surface, surface_norm1, surface_norm2, surface2_existed, is_intersection;
     int pcharge;
     double duu0;
     // rng
@@ -195,6 +197,9 @@ struct PushArgs {
     // turbulence maps sigma2_slab, sigma2_2d, lc_slab, lc_2d (mhd_data_parallel.f90:36-41): per grid
     // point four 32-byte chunks [value d/dx d/dy d/dz of half 0 | the same of half 1]
     const float* aux;
+    // acc_surfaceK1/K2 (acc_region_surface.f90:12-13): surf[k] -> two halves of n1 x n2 doubles each
+    const double* surf[2];
+    int surf_n1[2], surf_n2[2];
 };
 
 // ---- stream-compaction scratch (particles.cu) ---------------------------------------------

@@ -71,6 +71,7 @@ struct Lane {
     int nsteps_tracked;  // used by the tracking instantiations only
 #if GPAT_STRICT
     double v, dvl, dmul;  // focused transport: particle speed, last step's delta v / delta mu
+    double sh1, sh2;      // acc_by_surface: surface heights at this step's starting position
 #endif
 };
 
@@ -495,6 +496,73 @@ __device__ __forceinline__ bool in_acc_region(const DevParams& prm, const Lane& 
 }
 
 #if GPAT_STRICT
+// interp_acc_surface (acc_region_surface.f90:255-334): the two surface heights at the particle's
+// pre-step position, from the eight trilinear weights collapsed along each surface's normal
+__device__ __forceinline__ void surface_heights(const DevParams& prm, const PushArgs& a, double x, double y,
+                                                double z, double rt, double& h1, double& h2)
+{
+    double rx, ry, rz;
+    const double px = (x - prm.xmin) / prm.dx, py = (y - prm.ymin) / prm.dy, pz = (z - prm.zmin) / prm.dz;
+    const int pos[3] = {(int)floor(px) + 1, (int)floor(py) + 1, (int)floor(pz) + 1};
+    rx = px - (double)pos[0] + 1.0; ry = py - (double)pos[1] + 1.0; rz = pz - (double)pos[2] + 1.0;
+    const double rx1 = 1.0 - rx, ry1 = 1.0 - ry, rz1 = 1.0 - rz;
+    const double w[8] = {rx1 * ry1 * rz1, rx * ry1 * rz1, rx1 * ry * rz1, rx * ry * rz1,
+                         rx1 * ry1 * rz,  rx * ry1 * rz,  rx1 * ry * rz,  rx * ry * rz};
+    double out[2] = {0.0, 0.0};
+    int i1 = 0, j1 = 0, cur_axis = -1;
+    double w2[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = 0; k < 2; ++k) {
+        if (k == 1 && !prm.surface2_existed) break;
+        const int norm = k ? prm.surface_norm2 : prm.surface_norm1;
+        const int axis = abs(norm) - 1;
+        if (axis != cur_axis) {  // the second surface reuses i1, j1, weights_2d when the axes agree
+            if (axis == 0) {
+                i1 = pos[1]; j1 = pos[2];
+                w2[0] = w[0] + w[1]; w2[1] = w[2] + w[3]; w2[2] = w[4] + w[5]; w2[3] = w[6] + w[7];
+            } else if (axis == 1) {
+                i1 = pos[0]; j1 = pos[2];
+                w2[0] = w[0] + w[2]; w2[1] = w[1] + w[3]; w2[2] = w[4] + w[6]; w2[3] = w[5] + w[7];
+            } else {
+                i1 = pos[0]; j1 = pos[1];
+                w2[0] = w[0] + w[4]; w2[1] = w[1] + w[5]; w2[2] = w[2] + w[6]; w2[3] = w[3] + w[7];
+            }
+            cur_axis = axis;
+        }
+        const int n1 = a.surf_n1[k], n2 = a.surf_n2[k];
+        const int ia = min(max(i1 + 1, 0), n1 - 2), ib = min(max(j1 + 1, 0), n2 - 2);
+        const size_t n = (size_t)n1 * n2;
+        double hh[2] = {0.0, 0.0};
+        const int nslot = prm.time_interp ? 2 : 1;
+        for (int sl = 0; sl < nslot; ++sl) {
+            const int half = prm.time_interp ? (sl == 0 ? a.sel : (a.sel ^ 1)) : 0;
+            const double* sf = a.surf[k] + (size_t)half * n;
+            double acc = 0.0;  // sum() over the 2 x 2 section in array-element order
+            acc = acc + sf[ia + (size_t)n1 * ib] * w2[0];
+            acc = acc + sf[(ia + 1) + (size_t)n1 * ib] * w2[1];
+            acc = acc + sf[ia + (size_t)n1 * (ib + 1)] * w2[2];
+            acc = acc + sf[(ia + 1) + (size_t)n1 * (ib + 1)] * w2[3];
+            hh[sl] = acc;
+        }
+        out[k] = prm.time_interp ? hh[0] * (1.0 - rt) + hh[1] * rt : hh[0];
+    }
+    h1 = out[0];
+    h2 = out[1];
+}
+
+// check_above_acc_surface (acc_region_surface.f90:342-388) at the particle's NEW position
+__device__ __forceinline__ bool above_surface(const DevParams& prm, const Lane& q, double h1, double h2)
+{
+    const double c[3] = {q.x, q.y, q.z};
+    double ph = c[abs(prm.surface_norm1) - 1];
+    bool in = (prm.surface_norm1 > 0) ? (ph > h1) : (ph < h1);
+    if (prm.surface2_existed) {
+        ph = c[abs(prm.surface_norm2) - 1];
+        const bool in2 = (prm.surface_norm2 > 0) ? (ph > h2) : (ph < h2);
+        in = prm.is_intersection ? (in && in2) : (in || in2);
+    }
+    return in;
+}
+
 // push_particle_1d (particle_module.f90:2993-3111) on a 2-D record whose second row is zero.
 // Two uniforms per step: ran1 for x, then one for p (particle_module.f90:3085-3088).
 template <int L>
@@ -875,7 +943,9 @@ __device__ __forceinline__ void push_ft_3d_like(const DevParams& prm, const Push
         if (q.mu > mu_max) { ddmu = mu_max - (q.mu - ddmu); q.mu = mu_max; }
         else if (q.mu < -mu_max) { ddmu = -mu_max - (q.mu - ddmu); q.mu = -mu_max; }
         if (prm.acc_region_flag == 1) {
-            if (in_acc_region(prm, q)) { q.p = q.p + ddp; q.v = q.v + ddv; }
+            bool in = in_acc_region(prm, q);
+            if (prm.acc_by_surface) in = in && above_surface(prm, q, q.sh1, q.sh2);  // particle_module.f90:5297-5303
+            if (in) { q.p = q.p + ddp; q.v = q.v + ddv; }
             else { ddp = 0.0; ddv = 0.0; }
         } else {
             q.p = q.p + ddp;
@@ -934,6 +1004,9 @@ __device__ __forceinline__ void push_once(const DevParams& prm, const PushArgs& 
     if (a.aux && (prm.deltab_flag || prm.correlation_flag)) {  // particle_module.f90:1634-1639
         gather_aux<Rec<L>::NDIM>(prm, a.aux, a.sel, q.x, q.y, q.z, rt, A);
         auxp = A;
+    }
+    if constexpr (D3) {  // particle_module.f90:1662-1665, 1683-1686
+        if (prm.acc_by_surface) surface_heights(prm, a, q.x, q.y, q.z, rt, q.sh1, q.sh2);
     }
     if constexpr (!D3) {
         if (prm.ndim == 1) {
@@ -1087,7 +1160,11 @@ __device__ __forceinline__ void push_once(const DevParams& prm, const PushArgs& 
     const double ranp = (2.0 * u3 - 1.0) * sqrt3;
     double ddp = dp_dt * q.dt + ranp * sqrt(2.0 * dpp) * sdt;
     if (prm.acc_region_flag == 1) {
-        if (in_acc_region(prm, q)) q.p = q.p + ddp;
+        bool in = in_acc_region(prm, q);
+#if GPAT_STRICT
+        if (prm.acc_by_surface) in = in && above_surface(prm, q, q.sh1, q.sh2);  // particle_module.f90:4887-4892
+#endif
+        if (in) q.p = q.p + ddp;
         else ddp = 0.0;
     } else {
         q.p = q.p + ddp;
@@ -1174,6 +1251,7 @@ __device__ __forceinline__ int load_lane(const DevParams& prm, const PushArgs& a
     q.dxl = q.dyl = q.dzl = q.dpl = 0.0;
 #if GPAT_STRICT
     q.v = P.v[idx]; q.dvl = 0.0; q.dmul = 0.0;
+    q.sh1 = 0.0; q.sh2 = 0.0;
 #endif
     q.dt_old = q.dt;
     if (a.debug_nsteps > 0) {

@@ -77,6 +77,23 @@ class GpatSim:
             raise ValueError("turbulence map has the wrong size")
         self._ck(self.lib.gpat_upload_turbulence(self.h, which, slot, ptr(data)), "gpat_upload_turbulence")
 
+    def surface_shape(self, which: int):
+        """(n2, n1) C-order shape of acc_surfaceK1/K2 (acc_region_surface.f90:33-39): the two grid axes
+        other than the surface's normal, ghosted."""
+        P = self.P
+        axis = abs(P.surface_norm2 if which else P.surface_norm1) - 1
+        n1 = P.ny + 4 if axis == 0 else P.nx + 4
+        n2 = P.ny + 4 if axis == 2 else P.nz + 4
+        return n2, n1
+
+    def upload_acc_surface(self, which: int, slot: int, heights: np.ndarray):
+        """read_acc_surface (acc_region_surface.f90:91-206), in memory: heights of surface `which` (0, 1)
+        for frame slot 0 (acc_surfaceK1) or 1 (acc_surfaceK2), float64 over the ghosted plane."""
+        heights = np.ascontiguousarray(heights, dtype=np.float64)
+        if heights.shape != self.surface_shape(which):
+            raise ValueError(f"surface {which} has shape {heights.shape}, {self.surface_shape(which)} expected")
+        self._ck(self.lib.gpat_upload_acc_surface(self.h, which, slot, ptr(heights)), "gpat_upload_acc_surface")
+
     def prefetch_fields(self, f: np.ndarray):
         """Start the H2D copy of a frame that a later upload_fields(slot, f) will pack; `f` must be
         C-contiguous float32 (ideally page-locked) and must not change until then."""
@@ -267,13 +284,15 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
                   split_ratio=2.0, pmin_split=2.0, nsteps_interval=100, num_fine_steps=1,
                   local_dist=True, dump_escaped_dist=False, dt_inject=0.0, on_interval=None,
                   inject_mode=0, inject_same_nptl=True, inject_min=0.0, ncells_norm=1,
-                  track_tags=None, on_tracked=None):
+                  track_tags=None, on_tracked=None, surfaces=None):
     """solve_transport_equation (stochastic-mhd.f90:312-567) for one rank.
 
     `sim` is a GpatSim (or the test oracle, which has the same methods); `frames` is a
     sequence (or callable frame -> ndarray) of 8-variable MHD frames; `tstamps[i]` is the
     time of frame i (tstamps_mhd, mhd_config.f90:263-271).  Returns the per-interval records
-    the reference writes to quick.dat / pmax_global.dat / fdists_NNNN.h5.
+    the reference writes to quick.dat / pmax_global.dat / fdists_NNNN.h5.  With acc_by_surface,
+    `surfaces(which, frame)` returns the float64 heights of acceleration surface `which` at that frame
+    (the content of <surface_filenameK>_NNNN.dat).
     """
     get = frames if callable(frames) else (lambda i: frames[i])
     P = sim.P
@@ -285,11 +304,18 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
     nframes = len(tstamps)
     records = []
     sim.upload_fields(0, get(0))                               # :320-321, :350
+    nsurf = (2 if P.surface2_existed else 1) if P.acc_by_surface else 0
+    if nsurf and surfaces is None:
+        raise ValueError("acc_by_surface needs the `surfaces` callable")
+    for k in range(nsurf):                                     # :323-334 read_acc_surface(0, ...)
+        sim.upload_acc_surface(k, 0, surfaces(k, 0))
     total_steps = 0
     for tf in range(1, nframes):                               # :397
         # read_field_data_parallel(..., var_flag=time_interp_flag): without time interpolation
         # the new frame REPLACES farray1 (:404-406, :426)
         sim.upload_fields(1 if P.time_interp else 0, get(tf))
+        for k in range(nsurf):                                 # :405-416 read_acc_surface(time_interp_flag, ...)
+            sim.upload_acc_surface(k, 1 if P.time_interp else 0, surfaces(k, tf))
         t0, dtf = tstamps[tf - 1], tstamps[tf] - tstamps[tf - 1]
         if (tf == 1 or inject_new_ptl) and tf <= tmax_to_inject:   # :462-485
             if inject_mode == 6:                               # :451-454 inject_at_shock

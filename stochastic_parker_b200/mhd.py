@@ -309,3 +309,22 @@ def make_turbulence_maps(nx: int, ny: int, nz: int, frame: int, ndim: int = 2, d
     lcs = 0.6 * (1.0 + 0.3 * np.sin(tx - 0.2) * np.sin(ty + t) + 0.1 * np.cos(tz + 0.4))
     lc2 = 0.4 * (1.0 + 0.25 * np.cos(tx + t) * np.cos(ty - 0.7) + 0.15 * np.sin(tz))
     return tuple(a.astype(np.float32) for a in (s2s, s22, lcs, lc2))
+
+
+def make_acc_surface(P, which: int, frame: int) -> np.ndarray:
+    """Synthetic <surface_filenameK>_NNNN.dat content (read_acc_surface, acc_region_surface.f90:118-206:
+    one float64 per point of the ghosted plane spanned by the two axes other than the surface's normal,
+    first axis fastest).  A rippled sheet near the mid-plane of the box that drifts with the frame number;
+    the second surface sits a quarter of the box further along its normal.  Returns (n2, n1) C-order."""
+    norm = P.surface_norm2 if which else P.surface_norm1
+    axis = abs(norm) - 1
+    n = (P.nx, P.ny, P.nz)
+    lo = (P.xmin, P.ymin, P.zmin)
+    ext = (P.lx, P.ly, P.lz)
+    a1, a2 = [k for k in range(3) if k != axis]
+    u = (np.arange(n[a1] + 4, dtype=np.float64) - 2.0) / max(n[a1], 1)
+    v = (np.arange(n[a2] + 4, dtype=np.float64) - 2.0) / max(n[a2], 1)
+    V, U = np.meshgrid(v, u, indexing="ij")
+    mid = 0.5 + (0.2 if which else 0.0) * (1 if norm < 0 else -1)
+    h = mid + 0.12 * np.sin(2 * np.pi * (U + 0.07 * frame)) * np.cos(2 * np.pi * V + 0.3 * which) + 0.01 * frame
+    return np.ascontiguousarray(lo[axis] + ext[axis] * h, dtype=np.float64)

@@ -778,3 +778,89 @@ def test_focused_transport_3d_like_step_matches_numpy_restatement(key, grid, cli
         err = np.abs(after[name] - ref) / scale
         assert err.max() < 1e-12, (name, err.max())
     assert np.any(after["z"] != before["z"])
+
+
+# ---- acceleration surfaces (acc_region_surface.f90) -------------------------------------------
+def _np_surface_height(P, sf0, sf1, norm, x, y, z, rt):
+    """Bilinear interpolation of a surface in its own plane, written from the definition (not from the
+    eight collapsed trilinear weights the oracle uses), then the linear blend in time."""
+    axis = abs(norm) - 1
+    c = [(x - P.xmin) / P.dx, (y - P.ymin) / P.dy, (z - P.zmin) / P.dz]
+    pu, pv = [c[k] for k in range(3) if k != axis]
+    iu, iv = np.floor(pu).astype(int), np.floor(pv).astype(int)
+    ru, rv = pu - iu, pv - iv
+    a, b = iu + 2, iv + 2  # Fortran index floor + 1, array lower bound -1
+
+    def at(sf):
+        return (sf[b, a] * (1 - ru) * (1 - rv) + sf[b, a + 1] * ru * (1 - rv)
+                + sf[b + 1, a] * (1 - ru) * rv + sf[b + 1, a + 1] * ru * rv)
+    return at(sf0) * (1 - rt) + at(sf1) * rt
+
+
+@pytest.mark.parametrize("norm1,norm2,two,inter", [("+z", "-y", 0, 0), ("-y", "+y", 1, 1), ("+x", "-z", 1, 0),
+                                                   ("-z", "+z", 1, 1)])
+@pytest.mark.parametrize("ft", [0, 1])
+def test_acceleration_surfaces_gate_the_momentum_update(norm1, norm2, two, inter, ft):
+    """push_particle_3d / _3d_ft (particle_module.f90:4887-4892, 5297-5303): a particle gains or loses
+    momentum only if its NEW position is on the right side of the surface heights interpolated at its OLD
+    position.  Checked against an ungated run of the same particles (same uniforms, same displacement)."""
+    from stochastic_parker_b200 import mhd
+    cli = dict(acc_by_surface=1, surface_norm1=norm1, surface_norm2=norm2, surface2_existed=two,
+               is_intersection=inter)
+    if ft:
+        cli.update(focused_transport=1, duu_init=5.0)
+    conf = dict(acc_region_flag=1, r1=4, r2=8, r3=12)
+    w, P, frames, _ = make_case("c5", grid=24, nptl=600, cli=cli, conf=conf)
+    _, P0, _, _ = make_case("c5", grid=24, nptl=600, cli=dict(cli, acc_by_surface=0), conf=conf)
+    gated, free = Oracle(P, w.nptl_max), Oracle(P0, w.nptl_max)
+    surf = [[mhd.make_acc_surface(P, k, f) for f in (0, 1)] for k in range(2 if two else 1)]
+    for o in (gated, free):
+        o.upload_fields(0, frames[0])
+        o.upload_fields(1, frames[1])
+        o.inject_uniform(600, 0.0, 0, w.particle_v0, 0.03, w.dt_out, box_of(P), w.power_index)
+    for k, s in enumerate(surf):
+        gated.upload_acc_surface(k, 0, s[0])
+        gated.upload_acc_surface(k, 1, s[1])
+    before = gated.download_particles()
+    assert gated.debug_push_n(0.0, w.dt_out, 1) == 600 and free.debug_push_n(0.0, w.dt_out, 1) == 600
+    a, b = gated.download_particles(), free.download_particles()
+    for f in ("x", "y", "z", "t", "dt", "mu"):
+        assert np.array_equal(a[f], b[f]), f
+    rt = (before["t"] - 0.0) / w.dt_out
+    new = dict(x=a["x"], y=a["y"], z=a["z"])
+    inside, margin = None, np.full(len(a), np.inf)
+    for k, s in enumerate(surf):
+        norm = P.surface_norm2 if k else P.surface_norm1
+        h = _np_surface_height(P, s[0], s[1], norm, before["x"], before["y"], before["z"], rt)
+        ph = new["xyz"[abs(norm) - 1]]
+        side = (ph > h) if norm > 0 else (ph < h)
+        margin = np.minimum(margin, np.abs(ph - h))
+        inside = side if inside is None else ((inside & side) if inter else (inside | side))
+    sure = margin > 1e-9
+    assert 50 < inside[sure].sum() < sure.sum() - 50, "the surfaces must split the population"
+    want = np.maximum(np.where(inside, b["p"], before["p"]), 0.25 * P.p0)  # + the momentum floor, :3601-3605
+    assert np.array_equal(a["p"][sure], want[sure]), np.flatnonzero(a["p"] != want)
+    if ft:
+        off_floor = sure & (want > 0.25 * P.p0)  # the floor rescales v too, :5312-5320
+        assert np.array_equal(a["v"][off_floor], np.where(inside, b["v"], before["v"])[off_floor])
+    assert np.any(b["p"] != before["p"])
+
+
+def test_acceleration_surfaces_follow_the_frames():
+    """copy_acc_surface (acc_region_surface.f90:390-396) + the per-interval read: a run_intervals run with
+    surfaces differs from one without, and the surface used in interval 2 is frame 1's blended to frame 2's."""
+    from stochastic_parker_b200 import mhd
+    cli = dict(acc_by_surface=1, surface_norm1="+z")
+    conf = dict(acc_region_flag=1, r1=4, r2=8, r3=12)
+    w, P, frames, ts = make_case("c5", grid=24, nptl=300, cli=cli, conf=conf, nframes=3)
+    runs = []
+    for shift in (0, 1):
+        o = Oracle(P, w.nptl_max)
+        run_intervals(o, frames, ts, nptl=300, dist_flag=0, split_flag=0, local_dist=False,
+                      surfaces=lambda k, f: mhd.make_acc_surface(P, k, f + shift * (f == 2)))
+        runs.append(sort_by_key(o.download_particles()))
+    # the two runs share frames 0 and 1, so they agree in interval 1 and can only differ through frame 2's surface
+    assert len(runs[0]) == len(runs[1]) == 600
+    assert np.any(runs[0]["p"] != runs[1]["p"])
+    with pytest.raises(ValueError):
+        run_intervals(Oracle(P, w.nptl_max), frames, ts, nptl=10)

@@ -26,11 +26,22 @@ def pair(P, nptl_max, strict=1):
     return GpatSim(Pg, nptl_max), Oracle(P, nptl_max)
 
 
+def surfaces_of(P):
+    """The synthetic acceleration surfaces of a case, as run_intervals' `surfaces` callable."""
+    from stochastic_parker_b200 import mhd
+    return lambda which, frame: mhd.make_acc_surface(P, which, frame)
+
+
 def load_fields(sims, frames, time_interp=True):
     for s in sims:
         s.upload_fields(0, frames[0])
         if time_interp:
             s.upload_fields(1, frames[1])
+        if s.P.acc_by_surface:
+            for k in range(2 if s.P.surface2_existed else 1):
+                s.upload_acc_surface(k, 0, surfaces_of(s.P)(k, 0))
+                if time_interp:
+                    s.upload_acc_surface(k, 1, surfaces_of(s.P)(k, 1))
 
 
 # ------------------------------------------------------------------------------------------
@@ -139,6 +150,15 @@ CASES = {
     "s1_shock_1d_dpp_nlgc": dict(key="s1", grid=256, conf=dict(dt_min_rel=1e-3),
                                  cli=dict(dpp_wave=1, dpp_shear=1, nlgc=1, kperp_kpara=0.05)),
     "c5_3d": dict(key="c5", grid=32),
+    "c5_3d_acc_surfaces_union": dict(key="c5", grid=32, conf=dict(acc_region_flag=1),
+                                     cli=dict(acc_by_surface=1, surface_norm1="+z", surface2_existed=1,
+                                              surface_norm2="-y")),
+    "c5_3d_acc_surface_no_time_interp": dict(key="c5", grid=32, conf=dict(acc_region_flag=1),
+                                             cli=dict(acc_by_surface=1, surface_norm1="-x", time_interp=0)),
+    "c5_3d_ft_acc_surfaces_intersection": dict(key="c5", grid=32, conf=dict(acc_region_flag=1, dt_min_rel=1e-3),
+                                               cli=dict(focused_transport=1, duu_init=5.0, acc_by_surface=1,
+                                                        surface_norm1="+y", surface2_existed=1,
+                                                        surface_norm2="-z", is_intersection=1)),
     "c5_3d_dpp_nlgc": dict(key="c5", grid=32, conf=dict(kpara0=0.02, dt_min_rel=1e-3),
                            cli=dict(dpp_wave=1, dpp_shear=1, nlgc=1, kperp_kpara=0.05)),
 }
@@ -195,7 +215,7 @@ def test_interval_parity_strict(name):
     w, P, frames, ts = make_case(**CASES[name], nptl=400)
     g, o = pair(P, w.nptl_max, 1)
     kw = dict(nptl=400, dist_flag=1, particle_v0=w.particle_v0, inject_new_ptl=True, split_flag=1,
-              pmin_split=1.05, split_ratio=1.05, num_fine_steps=2, dump_escaped_dist=True)
+              pmin_split=1.05, split_ratio=1.05, num_fine_steps=2, dump_escaped_dist=True, surfaces=surfaces_of(P))
     rg, sg = run_intervals(g, frames, ts, **kw)
     ro, so = run_intervals(o, frames, ts, **kw)
     a, b = g.download_particles(), o.download_particles()
@@ -347,6 +367,22 @@ def test_edge_cases():
     bad.spherical_coord = 1
     with pytest.raises(GpatError):
         GpatSim(bad, 64)
+    bad = P.copy()
+    bad.acc_by_surface = 1          # only the 3-D pushers look at the surfaces
+    bad.surface_norm1 = 2
+    with pytest.raises(GpatError):
+        GpatSim(bad, 64)
+    w3, P3, frames3, _ = make_case("c5", grid=16, nptl=16, conf=dict(acc_region_flag=1, r1=4, r2=8, r3=8),
+                                   cli=dict(acc_by_surface=1, surface_norm1="+z"))
+    g3 = GpatSim(P3, 64)
+    g3.upload_fields(0, frames3[0])
+    g3.upload_fields(1, frames3[1])
+    g3.inject_uniform(8, 0.0, 1, 1.0, 0.0, 0.1, box_of(P3), 6.2)
+    with pytest.raises(GpatError):
+        g3.particle_mover(0.0, 0.1)  # surfaces not uploaded: GPAT_ERR_STATE
+    with pytest.raises(GpatError):
+        g3.upload_acc_surface(1, 0, np.zeros(g3.surface_shape(0)))  # surface2_existed is false
+    g3.close()
     bad = P.copy()
     bad.local[0].rx = 5  # does not divide nx: check_local_dist_configuration
     with pytest.raises(GpatError):
