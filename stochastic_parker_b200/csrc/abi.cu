@@ -478,7 +478,7 @@ int push_counters(gpat_sim* h)
 int sort_before_push(gpat_sim* h)
 {
     const bool strict = h->hp.strict_math || h->hp.ndim == 1 || h->hp.focused_transport || h->hp.deltab_flag ||
-                        h->hp.correlation_flag || h->hp.acc_by_surface;
+                        h->hp.correlation_flag;
     // Default: sort when the packed field store is larger than the L2 (+4 % on C1/C2, +10 % on C4, 2x
     // on C5).  A store that is L2-resident as a whole has no locality left to gain, and clustering
     // particles with similar step counts into the same warps costs load balance (C3: -4.5 %).
@@ -561,7 +561,7 @@ int run_push(gpat_sim* h, double t0, double dtf, int nsteps_interval, int num_fi
         // 1-D (push_particle_1d), focused transport (push_particle_2d_ft) and the turbulence maps
         // (deltab / correlation) exist in the reference-order build only: not throughput paths yet
         if (h->hp.strict_math || h->hp.ndim == 1 || h->hp.focused_transport || h->hp.deltab_flag ||
-            h->hp.correlation_flag || h->hp.acc_by_surface) launch_push_strict(h->layout, h->dp, h->P, h->fld, a, h->sm_count, h->st);
+            h->hp.correlation_flag) launch_push_strict(h->layout, h->dp, h->P, h->fld, a, h->sm_count, h->st);
         else launch_push_fast(h->layout, h->dp, h->P, h->fld, a, h->sm_count, h->st);
         h->tm.total_launches++;
     }

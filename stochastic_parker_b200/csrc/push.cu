@@ -495,7 +495,6 @@ __device__ __forceinline__ bool in_acc_region(const DevParams& prm, const Lane& 
     return in;
 }
 
-#if GPAT_STRICT
 // interp_acc_surface (acc_region_surface.f90:255-334): the two surface heights at the particle's
 // pre-step position, from the eight trilinear weights collapsed along each surface's normal
 __device__ __forceinline__ void surface_heights(const DevParams& prm, const PushArgs& a, double x, double y,
@@ -563,6 +562,7 @@ __device__ __forceinline__ bool above_surface(const DevParams& prm, const Lane& 
     return in;
 }
 
+#if GPAT_STRICT
 // push_particle_1d (particle_module.f90:2993-3111) on a 2-D record whose second row is zero.
 // Two uniforms per step: ran1 for x, then one for p (particle_module.f90:3085-3088).
 template <int L>
@@ -1343,7 +1343,7 @@ __device__ __forceinline__ int after_push(const DevParams& prm, const PushArgs& 
         q.nsteps_pushed = (n1 < a.nsteps_interval) ? n1 : (n1 == a.nsteps_interval ? 0 : n1 % a.nsteps_interval);
     }
     if (TRACK && q.tag_spl < 0 && q.nsteps_pushed == 0) track_sample(a, P, idx, q);
-    if (!SPEC && a.debug_nsteps > 0) return (--remaining == 0) ? ST_IDLE : ST_ADAPT;  // SPEC: never the debug mode
+    if (!(SPEC & 1) && a.debug_nsteps > 0) return (--remaining == 0) ? ST_IDLE : ST_ADAPT;  // SPEC: never the debug mode
     return next_state<TRACK>(prm, a, q, state == ST_FIX ? AFTER_FIXED_PUSH : AT_INNER_HEAD);
 }
 
@@ -1525,7 +1525,7 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
             if (state != ST_IDLE) {
                 cell = locate<Rec<L>::NDIM>(prm, q.x, q.y, q.z, rx, ry, rz);
                 const double rt = (q.t - a.t0) * a.idtf;
-                const bool ti = SPEC || prm.time_interp;  // SPEC: time interpolation on
+                const bool ti = (SPEC & 1) || prm.time_interp;  // SPEC: time interpolation on
                 const double tA = ti ? 1.0 - rt : 1.0, tB = ti ? rt : 0.0;
                 t0 = (SEL == 0) ? tA : tB;
                 t1 = (SEL == 0) ? tB : tA;
@@ -1732,6 +1732,9 @@ void launch_one(const DevParams& prm, const PtlSoA& P, const float* fld, const P
                 if constexpr (L == L2B) {
                     if (spec == kSpec01) { go(sel_c, trk_c, std::integral_constant<int, kSpec01>{}); return; }
                 }
+            }
+            if constexpr (Rec<L>::NDIM == 3) {  // run-time switches + the acceleration-surface gate
+                if (prm.acc_by_surface) { go(sel_c, trk_c, std::integral_constant<int, kSpecSurf>{}); return; }
             }
             go(sel_c, trk_c, I{});
         };

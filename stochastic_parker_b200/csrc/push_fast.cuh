@@ -30,16 +30,19 @@ __device__ __forceinline__ double min2f(double a, double b) { return (a < b) ? a
 // instructions on C1, profiles/r01f_push_coop_spec_ncu.txt).  SPEC = 0 reads every switch at run time.
 constexpr int kSpec11 = 1 | 2 | 4;  // mag_dependency = 1, momentum_dependency = 1 (C1, C2, C4)
 constexpr int kSpec01 = 1 | 4;      // mag_dependency = 0, momentum_dependency = 1 (C3)
+// bit 0 clear: every switch is read at run time.  kSpecSurf adds the acc_by_surface gate of the 3-D
+// pusher (particle_module.f90:4887-4892) to that generic code, so runs without surfaces never carry it.
+constexpr int kSpecSurf = 8;
 template <int L, typename FT, bool TRACK = false, int SPEC = 0>
 __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArgs& a,
                                              const FT& F, Lane& q, bool fixed_dt)
 {
-    const bool f_mag = SPEC ? bool(SPEC & 2) : prm.mag_dependency == 1;
-    const bool f_mom = SPEC ? bool(SPEC & 4) : prm.momentum_dependency == 1;
-    const bool f_nlgc = !SPEC && prm.nlgc;
-    const bool f_table = !SPEC && prm.rng_mode == GPAT_RNG_TABLE;
-    const bool f_drift2d = !SPEC && prm.check_drift_2d;
-    const bool f_acc = !SPEC && prm.acc_region_flag == 1;
+    const bool f_mag = (SPEC & 1) ? bool(SPEC & 2) : prm.mag_dependency == 1;
+    const bool f_mom = (SPEC & 1) ? bool(SPEC & 4) : prm.momentum_dependency == 1;
+    const bool f_nlgc = !(SPEC & 1) && prm.nlgc;
+    const bool f_table = !(SPEC & 1) && prm.rng_mode == GPAT_RNG_TABLE;
+    const bool f_drift2d = !(SPEC & 1) && prm.check_drift_2d;
+    const bool f_acc = !(SPEC & 1) && prm.acc_region_flag == 1;
     // tracked particles carry negated tags; the random streams are keyed by the magnitudes
     const int tag_inj = TRACK ? abs(q.tag_inj) : q.tag_inj, tag_spl = TRACK ? abs(q.tag_spl) : q.tag_spl;
     constexpr bool D3 = (Rec<L>::NDIM == 3);
@@ -276,6 +279,10 @@ __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArg
         ddz = fma(dz_dt, q.dt, bzn * t1 + hxy * sp * ran2);
         q.dzl = ddz;
     }
+    double sh1 = 0.0, sh2 = 0.0;
+    if constexpr (D3 && bool(SPEC & kSpecSurf)) {  // interp_acc_surface at the OLD position, particle_module.f90:1683-1686
+        if (f_acc) surface_heights(prm, a, q.x, q.y, q.z, (q.t - a.t0) * a.idtf, sh1, sh2);
+    }
     q.x += ddx;
     q.y += ddy;
     q.z += ddz;
@@ -286,7 +293,9 @@ __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArg
     double ddp = dp_dt * q.dt;
     if constexpr (EXT) ddp = fma(ranp, fm::sqrt_pos(2.0 * dpp * q.dt), ddp);
     if (f_acc) {
-        if (in_acc_region(prm, q)) q.p += ddp;
+        bool in = in_acc_region(prm, q);
+        if constexpr (D3 && bool(SPEC & kSpecSurf)) in = in && above_surface(prm, q, sh1, sh2);
+        if (in) q.p += ddp;
         else ddp = 0.0;
     } else {
         q.p += ddp;
@@ -306,5 +315,11 @@ __device__ __forceinline__ void push_once_fast(const DevParams& prm, const PushA
     double F[Rec<L>::NREC];
     const double rt = (q.t - a.t0) * a.idtf;
     gather<L>(prm, fld, a.sel, q.x, q.y, q.z, rt, F);
+    if constexpr (Rec<L>::NDIM == 3) {
+        if (prm.acc_by_surface) {
+            physics_fast<L, double[Rec<L>::NREC], TRACK, kSpecSurf>(prm, a, F, q, fixed_dt);
+            return;
+        }
+    }
     physics_fast<L, double[Rec<L>::NREC], TRACK>(prm, a, F, q, fixed_dt);
 }

@@ -232,17 +232,22 @@ def test_interval_parity_strict(name):
     g.close()
 
 
-@pytest.mark.parametrize("key,grid", [("c1", 64),    # L2B, switch-specialised (mag 1, mom 1)
-                                      ("c3", 64),    # L2B, specialised (mag 0, mom 1), open x
-                                      ("c4", 64),    # L2E (D_pp), specialised
-                                      ("c5", 32)])   # L3B, generic kernel, L2-sized residency
-def test_interval_parity_fast(key, grid):
+SURF_CASE = dict(conf=dict(acc_region_flag=1), cli=dict(acc_by_surface=1, surface_norm1="+z", surface2_existed=1,
+                                                        surface_norm2="-y", is_intersection=1))
+
+
+@pytest.mark.parametrize("key,grid,extra", [("c1", 64, {}),    # L2B, switch-specialised (mag 1, mom 1)
+                                            ("c3", 64, {}),    # L2B, specialised (mag 0, mom 1), open x
+                                            ("c4", 64, {}),    # L2E (D_pp), specialised
+                                            ("c5", 32, {}),    # L3B, generic kernel, L2-sized residency
+                                            ("c5", 32, SURF_CASE)])  # L3B + the acceleration-surface gate
+def test_interval_parity_fast(key, grid, extra):
     """The production (fast-math) build over two intervals against the oracle: these are the
     kernels bench.py times (particle_mover picks the specialised instantiations; the per-step
     tests above run the generic ones through gpat_debug_push_n)."""
-    w, P, frames, ts = make_case(key, grid=grid, nptl=2000)
+    w, P, frames, ts = make_case(key, grid=grid, nptl=2000, **extra)
     g, o = pair(P, w.nptl_max, 0)
-    kw = dict(nptl=2000, dist_flag=1, particle_v0=w.particle_v0, split_flag=1)
+    kw = dict(nptl=2000, dist_flag=1, particle_v0=w.particle_v0, split_flag=1, surfaces=surfaces_of(P))
     rg, sg = run_intervals(g, frames, ts, **kw)
     ro, so = run_intervals(o, frames, ts, **kw)
     assert abs(sg - so) <= 1e-3 * so
