@@ -1,5 +1,6 @@
 """Second, independent restatement (numpy, vectorised over particles) of ONE adaptive step of
-the 2-D Cartesian Parker path, used to cross-check oracle/gpat_oracle.c.
+the Cartesian Parker pushers (2-D, 2-D + third dimension, 3-D; standard and NLGC kappa; D_pp),
+used to cross-check oracle/gpat_oracle.c.
 
 TEST INFRASTRUCTURE ONLY (tests/ imports it; the product never does).  PARITY UNPINNED in the
 same sense as gpat_oracle.c: the reference ships no golden vectors and cannot be built here.
@@ -196,3 +197,305 @@ def interp_aux(maps1, maps2, P, x, y, rt):
                 c += 1
         out.append(f1 * (1.0 - rt[:, None]) + f2 * rt[:, None])
     return np.concatenate(out, axis=1)
+
+
+# ------------------------------------------------------------------------------------------------
+# 3-D gather, the general kappa tensor (standard and NLGC), D_pp, and the 3-D-like Parker pushers.
+# Written from the Fortran; nothing below calls the C oracle or the 2-D functions above.
+#   calc_fields_gradients (d/dz part)                 mhd_data_parallel.f90:556-566
+#   interp_fields (8 corners)                         mhd_data_parallel.f90:1751-1793
+#   calc_spatial_diffusion_coefficients               particle_module.f90:2208-2450
+#   calc_spatial_diffusion_coefficients_nlgc          particle_module.f90:2464-2771
+#   calc_dpp_wave_scattering / calc_dpp_flow_shear    particle_module.f90:2918-2979
+#   push_particle_2d (D_pp part)                      particle_module.f90:3476-3496
+#   push_particle_2d_include_3rd                      particle_module.f90:3979-4245
+#   push_particle_3d                                  particle_module.f90:4625-4907
+# ------------------------------------------------------------------------------------------------
+def gradients32_3d(f8: np.ndarray, dx: float, dy: float, dz: float) -> np.ndarray:
+    """(nz+4, ny+4, nx+4, 8) float32 -> (..., 32) float32."""
+    f8 = np.asarray(f8, dtype=np.float32)
+    out = np.zeros(f8.shape[:3] + (32,), dtype=np.float32)
+    out[..., :8] = f8
+    three, four = np.float32(3.0), np.float32(4.0)
+    for d, (axis, h) in enumerate(((2, dx), (1, dy), (0, dz))):
+        ih = np.float64(0.5) / np.float64(h)
+        a = np.moveaxis(f8, axis, 0)
+        g = np.empty_like(a)
+        g[1:-1] = ((a[2:] - a[:-2]).astype(np.float64) * ih).astype(np.float32)
+        g[0] = (((-three * a[0] + four * a[1]) - a[2]).astype(np.float64) * ih).astype(np.float32)
+        g[-1] = (((three * a[-1] - four * a[-2]) + a[-3]).astype(np.float64) * ih).astype(np.float32)
+        g = np.moveaxis(g, 0, axis)
+        for k in range(NFIELDS):
+            out[..., NFIELDS + 3 * k + d] = g[..., k]
+    return out
+
+
+def interp32_3d(fa1, fa2, P, x, y, z, rt):
+    """fields(1:32) from the 8 surrounding grid points, corner order i fastest, then j, then k."""
+    pc = [(x - P.xmin) / P.dx, (y - P.ymin) / P.dy, (z - P.zmin) / P.dz]
+    idx = [np.floor(c).astype(np.int64) + 1 for c in pc]   # Fortran pos
+    r = [c - i + 1 for c, i in zip(pc, idx)]
+    r1 = [1.0 - v for v in r]
+    f1 = np.zeros((len(x), 32))
+    f2 = np.zeros((len(x), 32))
+    for k in (0, 1):
+        for j in (0, 1):
+            for i in (0, 1):
+                w = (r[0] if i else r1[0]) * (r[1] if j else r1[1]) * (r[2] if k else r1[2])
+                sl = (idx[2] + k + 1, idx[1] + j + 1, idx[0] + i + 1)   # lower bound -1
+                f1 = f1 + fa1[sl].astype(np.float64) * w[:, None]
+                if fa2 is not None:
+                    f2 = f2 + fa2[sl].astype(np.float64) * w[:, None]
+    if fa2 is not None:
+        f1 = f1 * (1.0 - rt[:, None]) + f2 * rt[:, None]
+    return f1
+
+
+def kappa_tensor(P, F, p, mu, geometry, aux=None):
+    """kappa_type for geometry '2d' (ndim_field = 2), '2d3' (2-D + include_3rd_dim) or '3d'.
+    Returns a dict of arrays named as the Fortran components."""
+    nf = NFIELDS
+    g2, g1 = P.gamma_turb - 2.0, P.gamma_turb - 1.0
+    bx, by, bz = F[:, 4], F[:, 5], F[:, 6]
+    b = np.sqrt(bx ** 2 + by ** 2 + bz ** 2)
+    with np.errstate(divide="ignore"):
+        ib1 = np.where(b < EPS, 1.0, 1.0 / b)
+    ib2 = ib1 * ib1
+    ib3 = ib1 * ib2
+    one = np.ones_like(b)
+    k = {}
+    kn_para, kn_perp = one.copy(), one.copy()
+    if P.mag_dependency == 1:
+        kn_para = kn_para * b ** g2
+        kn_perp = kn_perp * b ** (g2 / 3.0)
+    if P.deltab_flag:
+        kn_para = kn_para / aux[:, 0]
+        kn_perp = kn_perp * aux[:, 0] ** (-1.0 / 3.0) * aux[:, 4] ** (2.0 / 3.0)
+    if P.correlation_flag:
+        kn_para = kn_para * aux[:, 8] ** g1
+        kn_perp = kn_perp * aux[:, 8] ** (g1 / 3.0) * aux[:, 12] ** (2.0 / 3.0)
+    k["knorm_para"] = kn_para
+    if P.nlgc:
+        if P.momentum_dependency == 1:
+            np_para = kn_para * (p / P.p0) ** P.pindex
+            np_perp = kn_perp * (p / P.p0) ** ((5.0 - P.gamma_turb) / 3.0)
+        else:
+            np_para, np_perp = kn_para, kn_perp
+        kpara = P.kpara0 * np_para
+        kperp = P.kpara0 * P.kperp_kpara * np_perp * mu ** 2
+    else:
+        knorm = kn_para * (p / P.p0) ** P.pindex if P.momentum_dependency == 1 else kn_para
+        kpara = P.kpara0 * knorm
+        kperp = kpara * P.kret
+    k["kpara"], k["kperp"] = kpara, kperp
+    k["skpara"] = np.sqrt(2.0 * kpara)
+    k["skperp"] = np.sqrt(2.0 * kperp)
+    k["skpara_perp"] = np.sqrt(2.0 * (kpara - kperp))
+
+    zero = np.zeros_like(b)
+    three = geometry != "2d"
+    full = geometry == "3d"
+    dB = {("x", "x"): F[:, nf + 12], ("x", "y"): F[:, nf + 13], ("x", "z"): F[:, nf + 14] if full else zero,
+          ("y", "x"): F[:, nf + 15], ("y", "y"): F[:, nf + 16], ("y", "z"): F[:, nf + 17] if full else zero,
+          ("z", "x"): F[:, nf + 18], ("z", "y"): F[:, nf + 19], ("z", "z"): F[:, nf + 20] if full else zero}
+    db = {"x": F[:, nf + 21], "y": F[:, nf + 22], "z": F[:, nf + 23] if full else zero}
+    comp = {"x": bx, "y": by, "z": bz}
+    axes = ("x", "y", "z") if three else ("x", "y")
+    # d ln(k_para) and d ln(k_perp) along each axis
+    dpa, dpe = {}, {}
+    for n, d in enumerate(axes):
+        live = full or d != "z"
+        a = zero
+        e = zero
+        if P.mag_dependency == 1 and live:
+            # particle_module.f90:2406-2408: the standard 3-D branch has no 1/B here; NLGC and 2-D do
+            a = db[d] * g2 if (full and not P.nlgc) else db[d] * ib1 * g2
+            e = db[d] * ib1 * g2 / 3.0
+        if P.deltab_flag and live:
+            a = a - aux[:, 1 + n] / aux[:, 0]
+            e = e - aux[:, 1 + n] / aux[:, 0] / 3.0 + 2.0 * aux[:, 5 + n] / aux[:, 4] / 3.0
+        if P.correlation_flag and live:
+            a = a + g1 * aux[:, 9 + n] / aux[:, 8]
+            e = e + g1 * aux[:, 9 + n] / aux[:, 8] / 3.0 + 2.0 * aux[:, 13 + n] / aux[:, 12] / 3.0
+        dpa[d], dpe[d] = a, e
+    kpp = kpara - kperp  # Parker transport (focused transport is restated in the tests that cover it)
+    for d in axes:       # dk_dd_dd
+        if P.nlgc:
+            iso, ani = kperp * dpe[d], kpara * dpa[d] - kperp * dpe[d]
+        else:
+            iso, ani = kperp * dpa[d], kpp * dpa[d]
+        c = comp[d]
+        k[f"dk{d}{d}_d{d}"] = iso + ani * c ** 2 * ib2 + 2.0 * kpp * c * (dB[(d, d)] * b - c * db[d]) * ib3
+    pairs = [("x", "y", "x"), ("x", "y", "y")]
+    if three:
+        pairs += [("x", "z", "x"), ("x", "z", "z"), ("y", "z", "y"), ("y", "z", "z")]
+    for i, j, d in pairs:
+        ani = (kpara * dpa[d] - kperp * dpe[d]) if P.nlgc else kpp * dpa[d]
+        ci, cj = comp[i], comp[j]
+        k[f"dk{i}{j}_d{d}"] = ani * ci * cj * ib2 + kpp * ((dB[(i, d)] * cj + ci * dB[(j, d)]) * ib2
+                                                          - 2.0 * ci * cj * db[d] * ib3)
+    return k
+
+
+def dpp_terms(P, F, p, k, dvx_dx, dvy_dy, dvz_dz, divv, dp_dt, geometry):
+    """dp_dt and dpp after calc_dpp_wave_scattering and calc_dpp_flow_shear."""
+    nf = NFIELDS
+    bx, by, bz = F[:, 4], F[:, 5], F[:, 6]
+    b = np.sqrt(bx ** 2 + by ** 2 + bz ** 2)
+    dpp = np.zeros_like(b)
+    if P.dpp_wave:
+        va = b / np.sqrt(F[:, 3])
+        if P.momentum_dependency == 1:
+            dp_dt = dp_dt + (8 * p / (27 * k["kpara"])) * va ** 2
+        else:
+            dp_dt = dp_dt + (4 * p / (9 * k["kpara"])) * va ** 2
+        dpp = dpp + (p * va) ** 2 / (9 * k["kpara"])
+    if P.dpp_shear:
+        zero = np.zeros_like(b)
+        dvx_dy, dvy_dx = F[:, nf + 1], F[:, nf + 3]
+        if geometry == "2d":
+            sxz = syz = zero
+            szz = -divv / 3
+        else:
+            full = geometry == "3d"
+            dvx_dz = F[:, nf + 2] if full else zero
+            dvy_dz = F[:, nf + 5] if full else zero
+            dvz_dx, dvz_dy = F[:, nf + 6], F[:, nf + 7]
+            szz = dvz_dz - divv / 3
+            sxz = (dvx_dz + dvz_dx) / 2
+            syz = (dvy_dz + dvz_dy) / 2
+        sxx = dvx_dx - divv / 3
+        syy = dvy_dy - divv / 3
+        sxy = (dvx_dy + dvy_dx) / 2
+        if P.weak_scattering:
+            with np.errstate(divide="ignore"):
+                ib = np.where(b < EPS, 0.0, 1.0 / b)
+            bbs = sxx * bx ** 2 + syy * by ** 2 + szz * bz ** 2 + 2.0 * (sxy * bx * by + sxz * bx * bz + syz * by * bz)
+            bbs = bbs * ib * ib
+            gshear = bbs ** 2 / 5
+        else:
+            gshear = 2 * (sxx ** 2 + syy ** 2 + szz ** 2 + 2 * (sxy ** 2 + sxz ** 2 + syz ** 2)) / 15
+        on = gshear > 0.0
+        add_dp = (2 + P.pindex) * gshear * P.tau0 * k["knorm_para"] * p ** (P.pindex - 1) * P.p0 ** (2.0 - P.pindex)
+        add_pp = gshear * P.tau0 * k["knorm_para"] * p ** P.pindex * P.p0 ** (2.0 - P.pindex)
+        dp_dt = np.where(on, dp_dt + add_dp, dp_dt)
+        dpp = np.where(on, dpp + add_pp, dpp)
+    return dp_dt, dpp
+
+
+def _finish_momentum(P, p, dp_dt, dpp, dt, sdt, ranp, inside=None):
+    ddp = dp_dt * dt + ranp * np.sqrt(2 * dpp) * sdt
+    if inside is not None:  # acc_region_flag == 1
+        ddp = np.where(inside, ddp, 0.0)
+    pn = p + ddp
+    return np.where(pn < 0.25 * P.p0, 0.25 * P.p0, pn)
+
+
+def _acc_region(P, x, y, z, ndim):
+    inside = ((x - P.xmin) / P.lx >= P.acc_region[0]) & ((x - P.xmin) / P.lx <= P.acc_region[1])
+    inside &= ((y - P.ymin) / P.ly >= P.acc_region[2]) & ((y - P.ymin) / P.ly <= P.acc_region[3])
+    if ndim == 3:
+        inside &= ((z - P.zmin) / P.lz >= P.acc_region[4]) & ((z - P.zmin) / P.lz <= P.acc_region[5])
+    return inside
+
+
+def push_2d_general(P, F, p, mu, dt_min, dt_max, u, x, y, t, qdrift, aux=None):
+    """push_particle_2d with every Parker-transport switch: NLGC kappa, D_pp (wave + shear), acc region."""
+    nf = NFIELDS
+    k = kappa_tensor(P, F, p, mu, "2d", aux)
+    bx, by, bz = F[:, 4], F[:, 5], F[:, 6]
+    b = np.sqrt(bx ** 2 + by ** 2 + bz ** 2)
+    with np.errstate(divide="ignore"):
+        ib = np.where(b < EPS, 0.0, 1.0 / b)
+    ib2 = ib * ib
+    ib3 = ib * ib2
+    vx, vy = F[:, 0], F[:, 1]
+    dvx_dx, dvy_dy = F[:, nf + 0], F[:, nf + 4]
+    dbz_dx, dbz_dy, db_dx, db_dy = F[:, nf + 18], F[:, nf + 19], F[:, nf + 21], F[:, nf + 22]
+    vdp = qdrift / np.sqrt((P.drift1 * P.p0 / p) ** 2 + (P.drift2 * P.p0 ** 2 / p ** 2) ** 2)
+    vdx = vdp * (dbz_dy * ib2 - 2.0 * bz * db_dy * ib3)
+    vdy = vdp * (-dbz_dx * ib2 + 2.0 * bz * db_dx * ib3)
+    dx_dt = vx + vdx + k["dkxx_dx"] + k["dkxy_dy"]
+    dy_dt = vy + vdy + k["dkxy_dx"] + k["dkyy_dy"]
+    divv = dvx_dx + dvy_dy
+    dp_dt = -p * divv / 3.0
+    dp_dt, dpp = dpp_terms(P, F, p, k, dvx_dx, dvy_dy, None, divv, dp_dt, "2d")
+    s = np.where(k["skperp"] > 0.0, k["skperp"], k["skpara"])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        cand = np.minimum.reduce([(0.5 * P.dx / k["skpara"]) ** 2, (0.5 * P.dy / k["skpara"]) ** 2,
+                                  (s / dx_dt) ** 2, (s / dy_dt) ** 2,
+                                  np.float64(np.float32(0.1)) * p / np.abs(dp_dt)])
+    ok = (dx_dt != 0.0) & (dy_dt != 0.0) & (dp_dt != 0.0)
+    dt = np.where(ok, cand, dt_min)
+    dt = np.where(dt < dt_min, dt_min, dt)
+    dt = np.where(dt > dt_max, dt_max, dt)
+    sdt = np.sqrt(dt)
+    sqrt3 = np.sqrt(3.0)
+    ran1, ran2, ran3, ranp = [(2.0 * u[:, c] - 1.0) * sqrt3 for c in range(4)]
+    xn = x + (dx_dt * dt + ran1 * k["skperp"] * sdt + ran3 * k["skpara_perp"] * sdt * bx * ib)
+    yn = y + (dy_dt * dt + ran2 * k["skperp"] * sdt + ran3 * k["skpara_perp"] * sdt * by * ib)
+    inside = _acc_region(P, xn, yn, None, 2) if P.acc_region_flag == 1 else None
+    return xn, yn, _finish_momentum(P, p, dp_dt, dpp, dt, sdt, ranp, inside), t + dt, dt
+
+
+def push_3d_like(P, F, p, mu, dt_min, dt_max, u, x, y, z, t, qdrift, full3d, aux=None):
+    """push_particle_3d (full3d) or push_particle_2d_include_3rd, Cartesian uniform grid.
+    Returns x, y, z, p, t, dt after the step."""
+    nf = NFIELDS
+    geometry = "3d" if full3d else "2d3"
+    k = kappa_tensor(P, F, p, mu, geometry, aux)
+    zero = np.zeros(len(p))
+    vx, vy, vz = F[:, 0], F[:, 1], F[:, 2]
+    bx, by, bz = F[:, 4], F[:, 5], F[:, 6]
+    b = np.sqrt(bx ** 2 + by ** 2 + bz ** 2)
+    with np.errstate(divide="ignore"):
+        ib = np.where(b < EPS, 0.0, 1.0 / b)
+    bxn, byn, bzn = bx * ib, by * ib, bz * ib
+    bxyn = np.sqrt(bxn ** 2 + byn ** 2)
+    with np.errstate(divide="ignore"):
+        ibxyn = np.where(bxyn < EPS, 0.0, 1.0 / bxyn)
+    dvx_dx, dvy_dy = F[:, nf + 0], F[:, nf + 4]
+    dvz_dz = F[:, nf + 8] if full3d else zero
+    dbx_dy, dby_dx = F[:, nf + 13], F[:, nf + 15]
+    dbx_dz = F[:, nf + 14] if full3d else zero
+    dby_dz = F[:, nf + 17] if full3d else zero
+    dbz_dx, dbz_dy = F[:, nf + 18], F[:, nf + 19]
+    db_dx, db_dy = F[:, nf + 21], F[:, nf + 22]
+    db_dz = F[:, nf + 23] if full3d else zero
+    ib2 = ib * ib
+    ib3 = ib * ib2
+    vdp = qdrift / np.sqrt((P.drift1 * P.p0 / p) ** 2 + (P.drift2 * P.p0 ** 2 / p ** 2) ** 2)
+    vdx = vdp * ((dbz_dy - dby_dz) * ib2 - 2 * (bz * db_dy - by * db_dz) * ib3)
+    vdy = vdp * ((dbx_dz - dbz_dx) * ib2 - 2 * (bx * db_dz - bz * db_dx) * ib3)
+    vdz = vdp * ((dby_dx - dbx_dy) * ib2 - 2 * (by * db_dx - bx * db_dy) * ib3)
+    if not full3d:  # push_particle_2d_include_3rd zeroes the d/dz components, particle_module.f90:4096-4098
+        k["dkxz_dz"], k["dkyz_dz"], k["dkzz_dz"] = zero, zero, zero
+    dx_dt = vx + vdx + k["dkxx_dx"] + k["dkxy_dy"] + k["dkxz_dz"]
+    dy_dt = vy + vdy + k["dkxy_dx"] + k["dkyy_dy"] + k["dkyz_dz"]
+    dz_dt = vz + vdz + k["dkxz_dx"] + k["dkyz_dy"] + k["dkzz_dz"]
+    divv = dvx_dx + dvy_dy + dvz_dz
+    dp_dt = -p * divv / 3.0
+    dp_dt, dpp = dpp_terms(P, F, p, k, dvx_dx, dvy_dy, dvz_dz, divv, dp_dt, geometry)
+    s = np.where(k["skperp"] > 0.0, k["skperp"], k["skpara"])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        cands = [(0.5 * P.dx / k["skpara"]) ** 2, (0.5 * P.dy / k["skpara"]) ** 2]
+        if full3d:
+            cands.append((0.5 * P.dz / k["skpara"]) ** 2)
+        cands += [(s / dx_dt) ** 2, (s / dy_dt) ** 2]
+        if full3d:
+            cands.append((s / dz_dt) ** 2)   # dz_dt is not tested against 0 (particle_module.f90:4792-4794)
+        cands.append(np.float64(np.float32(0.1)) * p / np.abs(dp_dt))
+        cand = np.minimum.reduce(cands)
+    ok = (dx_dt != 0.0) & (dy_dt != 0.0) & (dp_dt != 0.0)
+    dt = np.where(ok, cand, dt_min)
+    dt = np.where(dt < dt_min, dt_min, dt)
+    dt = np.where(dt > dt_max, dt_max, dt)
+    sdt = np.sqrt(dt)
+    sqrt3 = np.sqrt(3.0)
+    ran1, ran2, ran3, ranp = [(2.0 * u[:, c] - 1.0) * sqrt3 for c in range(4)]
+    skpa, skpe = k["skpara"], k["skperp"]
+    xn = x + (dx_dt * dt + (bxn * skpa * ran1 - bxn * bzn * skpe * ibxyn * ran2 - byn * skpe * ibxyn * ran3) * sdt)
+    yn = y + (dy_dt * dt + (byn * skpa * ran1 - byn * bzn * skpe * ibxyn * ran2 + bxn * skpe * ibxyn * ran3) * sdt)
+    zn = z + (dz_dt * dt + (bzn * skpa * ran1 + bxyn * skpe * ran2) * sdt)
+    inside = _acc_region(P, xn, yn, zn, 3 if full3d else 2) if P.acc_region_flag == 1 else None
+    return xn, yn, zn, _finish_momentum(P, p, dp_dt, dpp, dt, sdt, ranp, inside), t + dt, dt

@@ -864,3 +864,110 @@ def test_acceleration_surfaces_follow_the_frames():
     assert np.any(runs[0]["p"] != runs[1]["p"])
     with pytest.raises(ValueError):
         run_intervals(Oracle(P, w.nptl_max), frames, ts, nptl=10)
+
+
+# ---- the other Parker pushers against numpy restatements written from the Fortran ---------------
+def _table_step(key, grid, conf=None, cli=None, n=400, tweak=None, seed=11):
+    """One push of n particles with tabulated uniforms; returns (P, w, frames, before, after, u)."""
+    w, P, frames, _ = make_case(key, grid=grid, nptl=n, conf=conf, cli=cli)
+    if tweak:
+        tweak(P)
+    P.rng_mode = RNG_TABLE
+    o = Oracle(P, w.nptl_max)
+    u = np.random.default_rng(seed).uniform(0, 1, (n, 2, 4))
+    o.set_rng_table(u)
+    o.upload_fields(0, frames[0])
+    o.upload_fields(1, frames[1])
+    o.inject_uniform(n, 0.0, 0, w.particle_v0, 0.0, w.dt_out, box_of(P), w.power_index)
+    before = o.download_particles()
+    assert o.debug_push_n(0.0, w.dt_out, 1) == n
+    return P, w, frames, before, o.download_particles(), u[before["tag_injected"], 0], o
+
+
+def _check(after, want, names, tol=4e-15):
+    for name, ref in zip(names, want):
+        scale = np.maximum(np.abs(ref), 1.0) if name in "xyz" else np.abs(ref)
+        err = np.abs(after[name] - ref) / scale
+        assert err.max() < tol, (name, err.max(), int(err.argmax()))
+
+
+def test_3d_gradients_and_gather_match_numpy_restatement():
+    w, P, frames, _ = make_case("c5", grid=24, nptl=300, conf=dict(r1=4, r2=8, r3=12))
+    o = Oracle(P, w.nptl_max)
+    o.upload_fields(0, frames[0])
+    o.upload_fields(1, frames[1])
+    fa1 = np_step.gradients32_3d(frames[0], P.dx, P.dy, P.dz)
+    fa2 = np_step.gradients32_3d(frames[1], P.dx, P.dy, P.dz)
+    assert np.array_equal(o.get_fields(0), fa1) and np.array_equal(o.get_fields(1), fa2)
+    rng = np.random.default_rng(2)
+    x, y, z = (rng.uniform(lo, hi, 500) for lo, hi in ((P.xmin, P.xmax), (P.ymin, P.ymax), (P.zmin, P.zmax)))
+    rt = rng.uniform(0, 1, 500)
+    assert np.array_equal(o.interp(x, y, z, rt), np_step.interp32_3d(fa1, fa2, P, x, y, z, rt))
+
+
+def _narrow_region(P):
+    for i, v in enumerate((0.2, 0.8, 0.1, 0.7, 0.3, 0.9)):
+        P.acc_region[i] = v
+
+
+@pytest.mark.parametrize("conf,cli,tweak", [
+    (dict(), dict(), None),                                                     # C5 as configured
+    (dict(mag_dependency=1, momentum_dependency=1), dict(), None),              # quirk 8: no 1/B in dk
+    (dict(mag_dependency=1, momentum_dependency=1, kret=0.0), dict(dpp_wave=1, dpp_shear=1), None),
+    (dict(momentum_dependency=0), dict(dpp_wave=1, dpp_shear=1, weak_scattering=0), None),
+    (dict(mag_dependency=1, momentum_dependency=1), dict(nlgc=1, kperp_kpara=0.05), None),
+    (dict(mag_dependency=1), dict(nlgc=1, kperp_kpara=0.05, dpp_wave=1, dpp_shear=1), None),
+    (dict(acc_region_flag=1), dict(), _narrow_region),
+])
+def test_3d_step_matches_numpy_restatement(conf, cli, tweak):
+    """push_particle_3d + both kappa routines + D_pp: the path of BASELINE's C5."""
+    conf = dict(conf, r1=4, r2=8, r3=12)
+    P, w, frames, before, after, u, o = _table_step("c5", 24, conf, cli, tweak=tweak)
+    fa1 = np_step.gradients32_3d(frames[0], P.dx, P.dy, P.dz)
+    fa2 = np_step.gradients32_3d(frames[1], P.dx, P.dy, P.dz)
+    F = np_step.interp32_3d(fa1, fa2, P, before["x"], before["y"], before["z"], (before["t"] - 0.0) / w.dt_out)
+    qdrift = float(np.float32(1.0) / np.float32(3 * P.pcharge))
+    want = np_step.push_3d_like(P, F, before["p"], before["mu"], P.dt_min_rel * w.dt_out, P.dt_max_rel * w.dt_out,
+                                u, before["x"], before["y"], before["z"], before["t"], qdrift, True)
+    _check(after, want, ("x", "y", "z", "p", "t", "dt"))
+    assert np.any(after["p"] != before["p"])
+
+
+@pytest.mark.parametrize("conf,cli", [
+    (dict(), dict()),
+    (dict(), dict(dpp_wave=1, dpp_shear=1)),
+    (dict(kret=0.0), dict(nlgc=1, kperp_kpara=0.05)),
+])
+def test_2d_include_3rd_step_matches_numpy_restatement(conf, cli):
+    """push_particle_2d_include_3rd: 2-D fields, 3-D motion."""
+    P, w, frames, before, after, u, o = _table_step("c1", 48, conf, dict(cli, include_3rd_dim=1))
+    fa1 = np_step.gradients32(frames[0], P.dx, P.dy)
+    fa2 = np_step.gradients32(frames[1], P.dx, P.dy)
+    F = np_step.interp32(fa1, fa2, P, before["x"], before["y"], (before["t"] - 0.0) / w.dt_out)
+    qdrift = float(np.float32(1.0) / np.float32(3 * P.pcharge))
+    want = np_step.push_3d_like(P, F, before["p"], before["mu"], P.dt_min_rel * w.dt_out, P.dt_max_rel * w.dt_out,
+                                u, before["x"], before["y"], before["z"], before["t"], qdrift, False)
+    _check(after, want, ("x", "y", "z", "p", "t", "dt"))
+    assert np.any(after["z"] != before["z"])
+
+
+@pytest.mark.parametrize("key,conf,cli,tweak", [
+    ("c4", dict(), dict(), None),                                               # C4 as configured: wave + shear
+    ("c4", dict(kret=0.0), dict(weak_scattering=0), None),
+    ("c4", dict(momentum_dependency=0, mag_dependency=0), dict(), None),
+    ("c1", dict(), dict(nlgc=1, kperp_kpara=0.05), None),
+    ("c4", dict(), dict(nlgc=1, kperp_kpara=0.05), None),
+    ("c1", dict(acc_region_flag=1), dict(), _narrow_region),
+])
+def test_2d_step_with_dpp_and_nlgc_matches_numpy_restatement(key, conf, cli, tweak):
+    """push_particle_2d with D_pp (BASELINE's C4), NLGC kappa and the acceleration region."""
+    P, w, frames, before, after, u, o = _table_step(key, 48, conf, cli, tweak=tweak)
+    fa1 = np_step.gradients32(frames[0], P.dx, P.dy)
+    fa2 = np_step.gradients32(frames[1], P.dx, P.dy)
+    F = np_step.interp32(fa1, fa2, P, before["x"], before["y"], (before["t"] - 0.0) / w.dt_out)
+    qdrift = float(np.float32(1.0) / np.float32(3 * P.pcharge))
+    want = np_step.push_2d_general(P, F, before["p"], before["mu"], P.dt_min_rel * w.dt_out, P.dt_max_rel * w.dt_out,
+                                   u, before["x"], before["y"], before["t"], qdrift)
+    _check(after, want, ("x", "y", "p", "t", "dt"))
+    if key == "c4":
+        assert P.dpp_wave == 1 and P.dpp_shear == 1
