@@ -383,12 +383,15 @@ def dpp_terms(P, F, p, k, dvx_dx, dvy_dy, dvz_dz, divv, dp_dt, geometry):
     return dp_dt, dpp
 
 
-def _finish_momentum(P, p, dp_dt, dpp, dt, sdt, ranp, inside=None):
+def _finish_momentum(P, p, dp_dt, dpp, dt, sdt, ranp, inside=None, deltas=None):
     ddp = dp_dt * dt + ranp * np.sqrt(2 * dpp) * sdt
     if inside is not None:  # acc_region_flag == 1
         ddp = np.where(inside, ddp, 0.0)
     pn = p + ddp
-    return np.where(pn < 0.25 * P.p0, 0.25 * P.p0, pn)
+    low = pn < 0.25 * P.p0
+    if deltas is not None:  # deltap as the mover's roll-back sees it (particle_module.f90:3601-3605)
+        deltas["p"] = np.where(low, 0.25 * P.p0 - (pn - ddp), ddp)
+    return np.where(low, 0.25 * P.p0, pn)
 
 
 def _acc_region(P, x, y, z, ndim):
@@ -399,8 +402,9 @@ def _acc_region(P, x, y, z, ndim):
     return inside
 
 
-def push_2d_general(P, F, p, mu, dt_min, dt_max, u, x, y, t, qdrift, aux=None):
-    """push_particle_2d with every Parker-transport switch: NLGC kappa, D_pp (wave + shear), acc region."""
+def push_2d_general(P, F, p, mu, dt_min, dt_max, u, x, y, t, qdrift, aux=None, dt_fixed=None, deltas=None):
+    """push_particle_2d with every Parker-transport switch: NLGC kappa, D_pp (wave + shear), acc region.
+    dt_fixed: the fixed_dt = .true. call of the mover's re-push; deltas: dict that receives deltax/y/p."""
     nf = NFIELDS
     k = kappa_tensor(P, F, p, mu, "2d", aux)
     bx, by, bz = F[:, 4], F[:, 5], F[:, 6]
@@ -429,13 +433,18 @@ def push_2d_general(P, F, p, mu, dt_min, dt_max, u, x, y, t, qdrift, aux=None):
     dt = np.where(ok, cand, dt_min)
     dt = np.where(dt < dt_min, dt_min, dt)
     dt = np.where(dt > dt_max, dt_max, dt)
+    if dt_fixed is not None:
+        dt = dt_fixed
     sdt = np.sqrt(dt)
     sqrt3 = np.sqrt(3.0)
     ran1, ran2, ran3, ranp = [(2.0 * u[:, c] - 1.0) * sqrt3 for c in range(4)]
-    xn = x + (dx_dt * dt + ran1 * k["skperp"] * sdt + ran3 * k["skpara_perp"] * sdt * bx * ib)
-    yn = y + (dy_dt * dt + ran2 * k["skperp"] * sdt + ran3 * k["skpara_perp"] * sdt * by * ib)
+    ddx = dx_dt * dt + ran1 * k["skperp"] * sdt + ran3 * k["skpara_perp"] * sdt * bx * ib
+    ddy = dy_dt * dt + ran2 * k["skperp"] * sdt + ran3 * k["skpara_perp"] * sdt * by * ib
+    xn, yn = x + ddx, y + ddy
+    if deltas is not None:
+        deltas["x"], deltas["y"] = ddx, ddy
     inside = _acc_region(P, xn, yn, None, 2) if P.acc_region_flag == 1 else None
-    return xn, yn, _finish_momentum(P, p, dp_dt, dpp, dt, sdt, ranp, inside), t + dt, dt
+    return xn, yn, _finish_momentum(P, p, dp_dt, dpp, dt, sdt, ranp, inside, deltas), t + dt, dt
 
 
 def push_3d_like(P, F, p, mu, dt_min, dt_max, u, x, y, z, t, qdrift, full3d, aux=None):
@@ -499,3 +508,92 @@ def push_3d_like(P, F, p, mu, dt_min, dt_max, u, x, y, z, t, qdrift, full3d, aux
     zn = z + (dz_dt * dt + (bzn * skpa * ran1 + bxyn * skpe * ran2) * sdt)
     inside = _acc_region(P, xn, yn, zn, 3 if full3d else 2) if P.acc_region_flag == 1 else None
     return xn, yn, zn, _finish_momentum(P, p, dp_dt, dpp, dt, sdt, ranp, inside), t + dt, dt
+
+
+# ------------------------------------------------------------------------------------------------
+# The mover: one MHD interval of ONE particle at a time, in plain Python (small cases only).
+#   particle_boundary_condition (single rank)         particle_module.f90:1984-2129
+#   particle_mover_one_cycle                          particle_module.f90:1481-1833
+#   particle_mover (extended bounds, final BC pass)   particle_module.f90:1846-1974
+# ------------------------------------------------------------------------------------------------
+INBOX, OTHERS = 1, 0
+
+
+def boundary_condition(P, s, e, tally):
+    """s: dict with x, y, z, weight, count_flag; e = (xmin, xmax, ymin, ymax, zmin, zmax) as passed in
+    (the step loop passes the EXTENDED bounds, so a periodic wrap shifts by L + dx)."""
+    for axis, (name, lo, hi) in enumerate((("x", e[0], e[1]), ("y", e[2], e[3]), ("z", e[4], e[5]))):
+        if axis >= P.ndim:
+            break
+        if s[name] < lo and s["count_flag"] == INBOX:
+            if P.pbc[axis]:                      # open: neighbors < 0
+                tally["leak"] += s["weight"]
+                s["count_flag"] = -(2 * axis + 1)
+            else:                                # periodic, the neighbour is this rank
+                s[name] = s[name] - lo + hi
+        elif s[name] > hi and s["count_flag"] == INBOX:
+            if P.pbc[axis]:
+                tally["leak"] += s["weight"]
+                s["count_flag"] = -(2 * axis + 2)
+            else:
+                s[name] = s[name] - hi + lo
+
+
+def _negp_or_bc(P, s, e, tally):
+    if s["p"] < 0.0:
+        s["count_flag"] = OTHERS
+        tally["leak_negp"] += s["weight"]
+    else:
+        boundary_condition(P, s, e, tally)
+
+
+def mover_one_particle(P, s, push, t0, dtf, nsteps_interval, num_fine_steps, tally):
+    """particle_mover_one_cycle for one particle.  `push(s, fixed_dt)` performs one push_particle_* call
+    on the state dict (position, p, t, dt) and returns (deltax, deltay, deltaz, deltap)."""
+    dt_fine = dtf / num_fine_steps
+    e = (P.xmin - P.dx * 0.5, P.xmax + P.dx * 0.5, P.ymin - P.dy * 0.5, P.ymax + P.dy * 0.5,
+         P.zmin - P.dz * 0.5, P.zmax + P.dz * 0.5)
+    d = (0.0, 0.0, 0.0, 0.0)
+    step = int(np.ceil((s["t"] - t0) / dt_fine))
+    dt_target = dt_fine if step <= 0 else step * dt_fine
+    if dt_target > dtf:
+        dt_target = dtf
+    if s["p"] < 0.0 and s["count_flag"] == INBOX:
+        s["count_flag"] = OTHERS
+        tally["leak_negp"] += s["weight"]
+    else:
+        boundary_condition(P, s, e, tally)
+    if s["count_flag"] != INBOX:
+        return
+    while dt_target < dtf + dt_fine * np.float64(np.float32(0.1)):
+        if s["count_flag"] != INBOX:
+            break
+        while (s["t"] - t0) < dt_target and s["count_flag"] == INBOX:
+            _negp_or_bc(P, s, e, tally)
+            if s["count_flag"] != INBOX:
+                break
+            d = push(s, False)
+            tally["steps"] += 1
+            s["nsteps_pushed"] = (s["nsteps_pushed"] + 1) % nsteps_interval
+        if (s["t"] - t0) > dt_target and s["count_flag"] == INBOX:
+            s["x"], s["y"], s["z"], s["p"] = s["x"] - d[0], s["y"] - d[1], s["z"] - d[2], s["p"] - d[3]
+            s["t"] = s["t"] - s["dt"]
+            dt_old = s["dt"]
+            s["dt"] = t0 + dt_target - s["t"]
+            if s["dt"] > 0:
+                s["nsteps_pushed"] = s["nsteps_pushed"] - 1
+                d = push(s, True)
+                tally["steps"] += 1
+                s["nsteps_pushed"] = (s["nsteps_pushed"] + 1) % nsteps_interval
+            s["dt"] = dt_old
+            _negp_or_bc(P, s, e, tally)
+        dt_target = dt_target + dt_fine
+
+
+def final_boundary_pass(P, s, tally):
+    """The pass after the cycle loop: the TRUE bounds (particle_module.f90:1955-1967)."""
+    if s["p"] < 0.0 and s["count_flag"] != INBOX:
+        s["count_flag"] = OTHERS
+        tally["leak_negp"] += s["weight"]
+    else:
+        boundary_condition(P, s, (P.xmin, P.xmax, P.ymin, P.ymax, P.zmin, P.zmax), tally)

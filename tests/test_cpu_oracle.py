@@ -971,3 +971,113 @@ def test_2d_step_with_dpp_and_nlgc_matches_numpy_restatement(key, conf, cli, twe
     _check(after, want, ("x", "y", "p", "t", "dt"))
     if key == "c4":
         assert P.dpp_wave == 1 and P.dpp_shear == 1
+
+
+# ---- the mover's control flow against a plain-Python restatement ---------------------------------
+def _python_interval(P, w, frames, ptls, t0, dtf, nsteps_interval, num_fine_steps):
+    """One MHD interval of every particle with np_step.mover_one_particle (2-D Parker), Philox uniforms
+    keyed like the library's: counter (step_lo, step_hi, tag_injected, tag_splitted), key (seed, origin)."""
+    fa1 = np_step.gradients32(frames[0], P.dx, P.dy)
+    fa2 = np_step.gradients32(frames[1], P.dx, P.dy)
+    qdrift = float(np.float32(1.0) / np.float32(3 * P.pcharge))
+    dt_min, dt_max = P.dt_min_rel * dtf, P.dt_max_rel * dtf
+    tally = dict(leak=0.0, leak_negp=0.0, steps=0)
+    one = lambda v: np.array([v], dtype=np.float64)
+    out = []
+    for rec, rng0 in zip(ptls, rng_steps(ptls)):
+        s = {k: float(rec[k]) for k in ("x", "y", "z", "p", "mu", "t", "dt", "weight")}
+        s.update(count_flag=int(rec["count_flag"]), nsteps_pushed=int(rec["nsteps_pushed"]), rng=int(rng0))
+        key = (P.seed & 0xFFFFFFFF, ((P.seed >> 32) + int(rec["origin"])) & 0xFFFFFFFF)
+        tags = (int(rec["tag_injected"]), int(rec["tag_splitted"]))
+
+        def push(s, fixed):
+            F = np_step.interp32(fa1, fa2, P, one(s["x"]), one(s["y"]), one((s["t"] - t0) / dtf))
+            blk = philox4x32_10((s["rng"] & 0xFFFFFFFF, s["rng"] >> 32) + tags, key)
+            u = np.array([[b / 4294967295.0 for b in blk]])
+            d = {}
+            x, y, p, t, dt = np_step.push_2d_general(P, F, one(s["p"]), one(s["mu"]), dt_min, dt_max, u, one(s["x"]),
+                                                     one(s["y"]), one(s["t"]), qdrift,
+                                                     dt_fixed=one(s["dt"]) if fixed else None, deltas=d)
+            s.update(x=float(x[0]), y=float(y[0]), p=float(p[0]), t=float(t[0]), dt=float(dt[0]), rng=s["rng"] + 1)
+            return float(d["x"][0]), float(d["y"][0]), 0.0, float(d["p"][0])
+
+        np_step.mover_one_particle(P, s, push, t0, dtf, nsteps_interval, num_fine_steps, tally)
+        if s["count_flag"] == np_step.INBOX:
+            np_step.final_boundary_pass(P, s, tally)
+        out.append(s)
+    return out, tally
+
+
+@pytest.mark.parametrize("key,conf,nfine", [("c1", dict(dt_min_rel=2e-3), 1), ("c1", dict(dt_min_rel=2e-3), 3),
+                                            ("c3", dict(dt_min_rel=2e-3), 2),
+                                            ("c4", dict(dt_min_rel=4e-3), 2)])
+def test_mover_interval_matches_python_restatement(key, conf, nfine):
+    """particle_mover_one_cycle + particle_mover: target times, roll-back and fixed-dt re-push, the BC test
+    at the top of every step with the extended bounds, the final pass with the true ones, remove_particles."""
+    n = 24
+    w, P, frames, _ = make_case(key, grid=48, nptl=n, conf=conf)
+    o = Oracle(P, w.nptl_max)
+    o.upload_fields(0, frames[0])
+    o.upload_fields(1, frames[1])
+    o.inject_uniform(n, 0.0, 1, w.particle_v0, 0.0, w.dt_out, box_of(P), w.power_index)
+    before = o.download_particles()
+    steps = o.particle_mover(0.0, w.dt_out, 100, nfine, 1)
+    after = sort_by_key(o.download_particles())
+    esc = sort_by_key(o.download_escaped())
+    ref, tally = _python_interval(P, w, frames, before, 0.0, w.dt_out, 100, nfine)
+    assert tally["steps"] == steps, (tally["steps"], steps)
+    order = np.lexsort((before["tag_splitted"], before["tag_injected"], before["origin"]))
+    ref = [ref[i] for i in order]
+    tags = before["tag_injected"][order]
+    inbox = [r for r in ref if r["count_flag"] == np_step.INBOX]
+    gone = [(t, r) for t, r in zip(tags, ref) if r["count_flag"] < 0]
+    assert len(inbox) == len(after) and len(gone) == len(esc)
+    for name in ("x", "y", "p", "t", "dt"):
+        got, want = after[name], np.array([r[name] for r in inbox])
+        assert np.abs(got - want).max() <= 1e-11 * max(1.0, np.abs(want).max()), name
+    assert np.array_equal(after["nsteps_pushed"], np.array([r["nsteps_pushed"] for r in inbox]))
+    assert np.array_equal(rng_steps(after), np.array([r["rng"] for r in inbox], dtype=np.uint64))
+    assert np.all(after["t"] == w.dt_out)                       # every survivor ends ON the frame time
+    assert np.array_equal(esc["count_flag"], np.array([r["count_flag"] for _, r in gone], dtype=esc["count_flag"].dtype))
+    c = o.counters()
+    assert c.leak == tally["leak"] and c.leak_negp == tally["leak_negp"]
+    if key == "c3":
+        assert len(gone) > 0, "the open-x case must lose particles"
+
+
+@pytest.mark.parametrize("key", ["c1", "c2"])
+def test_boundary_quirks_match_python_restatement(key):
+    """Particles parked around the box edges: inside the half-cell margin they are left alone by the step
+    loop (extended bounds) and wrapped by L / removed by the final pass; beyond it the loop wraps them by
+    L + dx or lets them escape (c2: open boundaries)."""
+    n = 16
+    w, P, frames, _ = make_case(key, grid=48, nptl=n, conf=dict(dt_min_rel=5e-3))
+    o = Oracle(P, w.nptl_max)
+    o.upload_fields(0, frames[0])
+    o.upload_fields(1, frames[1])
+    o.inject_uniform(n, 0.0, 1, w.particle_v0, 0.0, w.dt_out, box_of(P), w.power_index)
+    ptl = o.download_particles()
+    offs = np.array([0.3, 0.6, -0.3, -0.6])
+    ptl["x"][0:4] = np.where(offs > 0, P.xmax + offs * P.dx, P.xmin + offs * P.dx)
+    ptl["y"][4:8] = np.where(offs > 0, P.ymax + offs * P.dy, P.ymin + offs * P.dy)
+    ptl["x"][8:10] = [P.xmax + 0.7 * P.dx, P.xmin - 0.2 * P.dx]      # both axes at once
+    ptl["y"][8:10] = [P.ymin - 0.7 * P.dy, P.ymax + 0.2 * P.dy]
+    ptl["t"][:10] = 0.02                                             # a few steps each
+    o.upload_particles(ptl)
+    steps = o.particle_mover(0.0, w.dt_out, 100, 1, 1)
+    after, esc = sort_by_key(o.download_particles()), sort_by_key(o.download_escaped())
+    ref, tally = _python_interval(P, w, frames, ptl, 0.0, w.dt_out, 100, 1)
+    order = np.lexsort((ptl["tag_splitted"], ptl["tag_injected"], ptl["origin"]))
+    ref = [ref[i] for i in order]
+    inbox = [r for r in ref if r["count_flag"] == np_step.INBOX]
+    gone = [r for r in ref if r["count_flag"] < 0]
+    assert tally["steps"] == steps and len(inbox) == len(after) and len(gone) == len(esc)
+    for name in ("x", "y", "p", "t"):
+        want = np.array([r[name] for r in inbox])
+        assert np.abs(after[name] - want).max() <= 1e-11 * max(1.0, np.abs(want).max()), name
+    assert np.array_equal(esc["count_flag"], np.array([r["count_flag"] for r in gone], dtype=esc["count_flag"].dtype))
+    assert o.counters().leak == tally["leak"]
+    if key == "c2":
+        assert len(gone) >= 6          # everything parked outside the true box leaves through an open boundary
+    else:
+        assert len(gone) == 0 and np.all((after["x"] >= P.xmin) & (after["x"] <= P.xmax))
