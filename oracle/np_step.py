@@ -597,3 +597,26 @@ def final_boundary_pass(P, s, tally):
         tally["leak_negp"] += s["weight"]
     else:
         boundary_condition(P, s, (P.xmin, P.xmax, P.ymin, P.ymax, P.zmin, P.zmax), tally)
+
+
+def remove_particles(flags):
+    """remove_particles (particle_module.f90:5365-5403): swap-with-tail compaction.  flags: count_flag per
+    slot; returns (order of the surviving slots as original indices, escaped indices in the order they are
+    appended to escaped_ptls)."""
+    idx = list(range(len(flags)))
+    n = len(idx)
+    nremoved = 0
+    escaped = []
+    i = 1
+    while i <= n:
+        if (n - i) == (nremoved - 1):
+            break
+        if flags[idx[i - 1]] == INBOX:
+            i += 1
+        else:
+            if flags[idx[i - 1]] < 0:
+                escaped.append(idx[i - 1])
+            tail = n - nremoved
+            idx[tail - 1], idx[i - 1] = idx[i - 1], idx[tail - 1]
+            nremoved += 1
+    return idx[:n - nremoved], escaped

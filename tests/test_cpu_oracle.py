@@ -974,7 +974,7 @@ def test_2d_step_with_dpp_and_nlgc_matches_numpy_restatement(key, conf, cli, twe
 
 
 # ---- the mover's control flow against a plain-Python restatement ---------------------------------
-def _python_interval(P, w, frames, ptls, t0, dtf, nsteps_interval, num_fine_steps):
+def _python_interval(P, w, frames, ptls, t0, dtf, nsteps_interval, num_fine_steps, keep_cycle_flags=False):
     """One MHD interval of every particle with np_step.mover_one_particle (2-D Parker), Philox uniforms
     keyed like the library's: counter (step_lo, step_hi, tag_injected, tag_splitted), key (seed, origin)."""
     fa1 = np_step.gradients32(frames[0], P.dx, P.dy)
@@ -1002,6 +1002,8 @@ def _python_interval(P, w, frames, ptls, t0, dtf, nsteps_interval, num_fine_step
             return float(d["x"][0]), float(d["y"][0]), 0.0, float(d["p"][0])
 
         np_step.mover_one_particle(P, s, push, t0, dtf, nsteps_interval, num_fine_steps, tally)
+        if keep_cycle_flags:
+            s["flag_after_cycle"] = s["count_flag"]
         if s["count_flag"] == np_step.INBOX:
             np_step.final_boundary_pass(P, s, tally)
         out.append(s)
@@ -1065,8 +1067,14 @@ def test_boundary_quirks_match_python_restatement(key):
     ptl["t"][:10] = 0.02                                             # a few steps each
     o.upload_particles(ptl)
     steps = o.particle_mover(0.0, w.dt_out, 100, 1, 1)
-    after, esc = sort_by_key(o.download_particles()), sort_by_key(o.download_escaped())
-    ref, tally = _python_interval(P, w, frames, ptl, 0.0, w.dt_out, 100, 1)
+    raw, raw_esc = o.download_particles(), o.download_escaped()
+    after, esc = sort_by_key(raw), sort_by_key(raw_esc)
+    ref, tally = _python_interval(P, w, frames, ptl, 0.0, w.dt_out, 100, 1, keep_cycle_flags=True)
+    # remove_particles after the cycle, then again after the final pass: the ORDER of survivors and escapees
+    keep1, esc1 = np_step.remove_particles([r["flag_after_cycle"] for r in ref])
+    keep2, esc2 = np_step.remove_particles([ref[i]["count_flag"] for i in keep1])
+    assert np.array_equal(raw["tag_injected"], ptl["tag_injected"][[keep1[i] for i in keep2]])
+    assert np.array_equal(raw_esc["tag_injected"], ptl["tag_injected"][esc1 + [keep1[i] for i in esc2]])
     order = np.lexsort((ptl["tag_splitted"], ptl["tag_injected"], ptl["origin"]))
     ref = [ref[i] for i in order]
     inbox = [r for r in ref if r["count_flag"] == np_step.INBOX]
