@@ -310,6 +310,11 @@ def main():
 
     layout = {2: "L2E" if (P.dpp_wave or P.dpp_shear or P.include_3rd_dim) else "L2B",
               3: "L3E" if (P.dpp_wave or P.dpp_shear) else "L3B"}[w.ndim]
+    # packed store: 2 frames x NREC float32 per ghosted grid point; particles: 17 SoA arrays
+    nrec = {"L2B": 16, "L2E": 24, "L3B": 24, "L3E": 32}[layout]
+    npts = (w.nx + 4) * (w.ny + 4 if w.ndim > 1 else 1) * (w.nz + 4 if w.ndim > 2 else 1)
+    store_mb = npts * 2 * nrec * 4 / 1e6
+    ptl_mb = nptl_end * 102 / 1e6
     peak, peak_src = measured_peaks()
     # roofline of the push kernel on THIS rank (per launch: steps of one interval x bytes/step)
     ach = tot["steps"] * ALGO_BYTES[layout] / (tot["push_ms"] * 1e-3) / 1e9 if tot["push_ms"] > 0 else 0.0
@@ -336,8 +341,8 @@ def main():
             "field_layout": layout, "strict_math": int(args.strict),
             "step": "one MHD interval (dt_out) of the whole population",
             "parallelism": f"particles sharded over {world} GPU(s), full field per GPU, NCCL allreduce of histograms",
-            "l2": "no flush: the two-frame field store (135 MB at 1024^2) plus the particle arrays (102 MB) exceed "
-                  "the 126 MB L2, and every step uploads a new MHD frame and repacks half of the store",
+            "l2": f"no flush: the two-frame field store ({store_mb:.0f} MB) plus the particle arrays ({ptl_mb:.0f} MB) "
+                  "exceed the 126 MB L2, and every step uploads a new MHD frame and repacks half of the store",
             "source": w.source,
             "why_this_workload": "north_star states its target on the 2D reconnection config (configs[0]); configs[1] "
                                  "(C2, 1e8 particles x 2.4e4 steps per MHD interval = 2 min per step at this rate) runs "
