@@ -1089,3 +1089,101 @@ def test_boundary_quirks_match_python_restatement(key):
         assert len(gone) >= 6          # everything parked outside the true box leaves through an open boundary
     else:
         assert len(gone) == 0 and np.all((after["x"] >= P.xmin) & (after["x"] <= P.xmax))
+
+
+# ---- injection, value for value ------------------------------------------------------------------
+def _py_inject_uniform(P, n, dt, dist_flag, particle_v0, t_frame, dt_mhd, box, power_index, tag0=0):
+    """inject_particles_spatial_uniform (whole-domain branch, particle_module.f90:487-498) +
+    inject_one_particle (:385-441) in plain Python.  Uniform k of particle `tag` is word k % 4 of
+    Philox((k // 4, 0, tag, 0), (seed_lo, seed_hi + origin)) / 4294967295 (DESIGN.md section 4)."""
+    import math
+    key = (P.seed & 0xFFFFFFFF, ((P.seed >> 32) + P.mpi_rank) & 0xFFFFFFFF)
+    mu_max = float(np.float32(0.99))
+    out = []
+    for i in range(n):
+        tag = tag0 + i
+        state = dict(k=0, buf=None)
+
+        def u():
+            if state["k"] % 4 == 0:
+                state["buf"] = philox4x32_10((state["k"] // 4, 0, tag, 0), key)
+            v = state["buf"][state["k"] % 4] / 4294967295.0
+            state["k"] += 1
+            return v
+        x = u() * (box[3] - box[0]) + box[0]
+        y = u() * (box[4] - box[1]) + box[1]
+        z = u() * (box[5] - box[2]) + box[2]
+        mu = mu_max * (2.0 * u() - 1.0)
+        if dist_flag == 0:
+            ftest, fxp = 1.0, 0.5
+            while ftest > fxp:
+                ptmp = (u() * (P.pmax - P.pmin) + P.pmin) / P.p0
+                fxp = ptmp ** 2 * math.exp(-ptmp ** 2)
+                ftest = u() * float(np.float32(0.37))
+            p = ptmp * P.p0
+        elif dist_flag == 1:
+            p = P.p0
+        else:
+            r01 = u()
+            if int(power_index) == 1:
+                p = (P.pmax / P.p0) ** r01 * P.p0
+            else:
+                norm = P.pmax ** (-power_index + 1) - P.p0 ** (-power_index + 1)
+                p = (r01 * norm + P.p0 ** (-power_index + 1)) ** (1.0 / (-power_index + 1))
+        out.append(dict(x=x, y=y, z=z, mu=mu, p=p, v=particle_v0 * p / P.p0, t=t_frame + u() * dt_mhd,
+                        dt=dt, weight=1.0, tag_injected=tag, tag_splitted=1, origin=P.mpi_rank))
+    return out
+
+
+@pytest.mark.parametrize("dist_flag,power_index", [(0, 6.2), (1, 6.2), (2, 6.2), (2, 1.0)])
+def test_injection_matches_python_restatement(dist_flag, power_index):
+    w, P, _, _ = make_case("c1", grid=32, nptl=500)
+    P.mpi_rank = 3
+    o = Oracle(P, 2000)
+    box = [0.25, 0.5, 0.0, 1.5, 1.75, 0.0]                       # -ip box: a sub-volume of the domain
+    o.inject_uniform(300, 2e-6, dist_flag, 50.0, 0.4, 0.1, box, power_index)
+    o.inject_uniform(200, 2e-6, dist_flag, 50.0, 0.5, 0.1, box, power_index)   # tags continue at 300
+    a = o.download_particles()
+    ref = (_py_inject_uniform(P, 300, 2e-6, dist_flag, 50.0, 0.4, 0.1, box, power_index)
+           + _py_inject_uniform(P, 200, 2e-6, dist_flag, 50.0, 0.5, 0.1, box, power_index, tag0=300))
+    assert len(a) == 500
+    for f in ("x", "y", "z", "mu", "t", "dt", "weight"):
+        assert np.array_equal(a[f], np.array([r[f] for r in ref])), f
+    for f in ("p", "v"):                                          # exp()/pow() may differ in the last bit
+        want = np.array([r[f] for r in ref])
+        assert np.abs(a[f] - want).max() <= 4e-16 * np.abs(want).max(), f
+    for f in ("tag_injected", "tag_splitted", "origin"):
+        assert np.array_equal(a[f], np.array([r[f] for r in ref])), f
+    assert np.all(a["count_flag"] == 1) and np.all(a["split_times"] == 0) and np.all(rng_steps(a) == 0)
+    if dist_flag == 0:                                            # the rejection loop really ran
+        assert len(np.unique(a["p"])) == 500 and a["p"].min() >= P.pmin and a["p"].max() <= P.pmax
+
+
+def test_escaped_distributions_match_numpy_binning():
+    """calc_escaped_distributions, global part (diagnostics.f90:934-955): fescaped(imu, ip, |count_flag|) +=
+    weight for p in (pmin, pmax]; C2 has open boundaries, so several faces fill."""
+    w, P, frames, ts = make_case("c2", grid=32, nptl=4000, conf=dict(dt_min_rel=1e-3))
+    o = Oracle(P, w.nptl_max)
+    got = []
+    run_intervals(o, frames, ts, nptl=4000, particle_v0=w.particle_v0, dist_flag=2, dump_escaped_dist=True,
+                  on_interval=lambda tf, d: got.append((d["fescaped"].copy(), None)))
+    # the escaped list is reset after every dump: bin the last interval's escapees by hand
+    o2 = Oracle(P, w.nptl_max)
+    o2.upload_fields(0, frames[0])
+    o2.upload_fields(1, frames[1])
+    o2.inject_uniform(4000, 0.0, 2, w.particle_v0, 0.0, w.dt_out, box_of(P), w.power_index)
+    o2.particle_mover(0.0, w.dt_out, 100, 1, 1)
+    esc = o2.download_escaped()
+    assert len(esc) > 20 and set(np.unique(esc["count_flag"])) <= {-1, -2, -3, -4}
+    assert len(set(np.unique(esc["count_flag"]))) >= 2
+    pmin_log = np.log10(P.pmin)
+    dp_log = (np.log10(P.pmax) - pmin_log) / P.npp_global
+    ref = np.zeros((2 * P.ndim, P.npp_global, P.nmu_global))
+    for r in esc:
+        if r["p"] > P.pmin and r["p"] <= P.pmax and -1.0 <= r["mu"] <= 1.0:
+            ip = int(np.floor((np.log10(r["p"]) - pmin_log) / dp_log)) + 1
+            imu = int(np.floor((r["mu"] + 1.0) / float(np.float32(2.0) / np.float32(P.nmu_global)))) + 1
+            ref[abs(int(r["count_flag"])) - 1, min(ip, P.npp_global) - 1, imu - 1] += r["weight"]
+    assert np.array_equal(o2.escaped_diagnostics(), ref)
+    assert np.array_equal(got[0][0], ref)          # the same interval through run_intervals
+    assert ref.sum() == esc["weight"].sum() == o2.counters().leak
