@@ -405,17 +405,23 @@ int main(int argc, char** argv)
         return gpat_reset_tracked(h);
     };
 
+    // a missing or short input file: say which, and let CK() finalize the handle once
+    auto file_error = [](const char* what, int tframe) -> int {
+        std::fprintf(stderr, "gpat_driver: cannot read %s (frame %d)\n", what, tframe);
+        return -1;
+    };
+
     // deltab_NNNN / lc_NNNN: slab array then 2-D array (read_magnetic_fluctuation,
     // read_correlation_length, mhd_data_parallel.f90:306-497; stochastic-mhd.f90:330-346, 413-420)
     std::vector<float> maps;
     auto upload_maps = [&](int tframe, int slot) -> int {
         if (P.deltab_flag) {
-            if (!read_frame(dir_mhd, tframe, ncell * 2, maps, "deltab")) return die(h, "read deltab frame", -1);
+            if (!read_frame(dir_mhd, tframe, ncell * 2, maps, "deltab")) return file_error("deltab", tframe);
             int rc = gpat_upload_turbulence(h, 0, slot, maps.data());
             if (rc) return rc;
         }
         if (P.correlation_flag) {
-            if (!read_frame(dir_mhd, tframe, ncell * 2, maps, "lc")) return die(h, "read lc frame", -1);
+            if (!read_frame(dir_mhd, tframe, ncell * 2, maps, "lc")) return file_error("lc", tframe);
             int rc = gpat_upload_turbulence(h, 1, slot, maps.data());
             if (rc) return rc;
         }
@@ -434,10 +440,10 @@ int main(int argc, char** argv)
             std::snprintf(name, sizeof(name), "%s%s_%04d.dat", dir_mhd.c_str(), cli.s(k ? "-sf2" : "-sf1").c_str(), tframe);
             surf.resize(n);
             FILE* f = std::fopen(name, "rb");
-            if (!f) return die(h, "open acceleration surface file", -1);
+            if (!f) return file_error(name, tframe);
             const size_t got = std::fread(surf.data(), sizeof(double), n, f);
             std::fclose(f);
-            if (got != n) return die(h, "read acceleration surface file", -1);
+            if (got != n) return file_error(name, tframe);
             int rc = gpat_upload_acc_surface(h, k, slot, surf.data());
             if (rc) return rc;
         }

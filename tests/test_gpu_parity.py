@@ -551,6 +551,53 @@ def test_cpp_driver_matches_python_driver(tmp_path):
     g.close()
 
 
+def test_cpp_driver_reads_acceleration_surfaces(tmp_path):
+    """-as 1 -sn1 +z -s2e .true. -sn2 -y -ii .true. -sf1/-sf2: the C++ driver reads <name>_NNNN.dat like
+    read_acc_surface and gives the run run_intervals gives with the same arrays."""
+    import os
+    import subprocess
+    from stochastic_parker_b200 import WORKLOADS, config, mhd
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-s", "-C", os.path.join(root, "host")], check=True)
+    w = WORKLOADS["c5"].scaled(grid=32, nptl=3000)
+    w.conf = dict(w.conf, acc_region_flag=1, r1=4, r2=8, r3=16)
+    w.cli = dict(w.cli, acc_by_surface=1, surface_norm1="+z", surface2_existed=1, surface_norm2="-y", is_intersection=1)
+    nfr = 3
+    d = tmp_path / "mhd"
+    cfg = mhd.write_run(str(d), w.kind, w.nx, w.ny, w.nz, nframes=nfr, lx=w.lx, ly=w.ly, lz=w.lz, dt_out=w.dt_out)
+    P = config.build_params(w.conf_text(), mhd.read_mhd_config(str(d / "mhd_config.dat")), 3, nframes=nfr - 1, cli=w.cli)
+    for f in range(nfr):
+        for k, stem in enumerate(("surf_a", "surf_b")):
+            mhd.make_acc_surface(P, k, f).tofile(str(d / f"{stem}_{f:04d}.dat"))
+    conf = tmp_path / "conf.dat"
+    conf.write_text(w.conf_text())
+    out = tmp_path / "out"
+    out.mkdir()
+    args = [os.path.join(root, "host", "gpat_driver"), "-nl", ".false.", "-pv", repr(w.particle_v0),
+            "-dm", str(d) + "/", "-np", "3000", "-ti", "1", "-ts", "0", "-te", str(nfr - 1),
+            "-df", "1", "-pi", "6.2", "-sf", "1", "-sr", "1.05", "-ps", "1.05", "-ni", "100", "-dt", "0.0",
+            "-dd", str(out) + "/", "-cf", str(conf), "-ld", ".false.", "-nm", "30000", "-in", ".true.",
+            "-nd", "3", "-dp1", "850964.408", "-dp2", "13575468.975", "-ch", "-1",
+            "-as", "1", "-sn1", "+z", "-s2e", ".true.", "-sn2", "-y", "-ii", ".true.", "-sf1", "surf_a", "-sf2", "surf_b"]
+    r = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    g = GpatSim(P, 30000)
+    frames = [mhd.read_frame(str(d), f, dict(cfg, ndim=3)) for f in range(nfr)]
+    rec, steps = run_intervals(g, frames, [f * w.dt_out for f in range(nfr)], nptl=3000, dist_flag=1,
+                               particle_v0=w.particle_v0, power_index=6.2, split_ratio=1.05, pmin_split=1.05,
+                               local_dist=False, surfaces=surfaces_of(P))
+    assert f"Total particle steps: {steps} " in r.stdout
+    for rd in rec:
+        raw = open(out / f"fdists_{rd['frame']:04d}.bin", "rb").read()
+        nmu, npp = np.frombuffer(raw[:8], dtype=np.int32)
+        assert np.array_equal(np.frombuffer(raw[8:8 + 8 * nmu * npp], dtype=np.float64).reshape(npp, nmu), rd["fglobal"])
+    g.close()
+    # without the surface files the driver stops with an error instead of running ungated
+    os.remove(d / "surf_b_0001.dat")
+    r = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0
+
+
 def test_restart_round_trip_is_bit_exact():
     """dump_particles / read_particles + save/read_particle_module_state (diagnostics.f90:1811-1888,
     particle_module.f90:5532-5664, 5744-5816): a run that is stopped after one interval, downloaded
