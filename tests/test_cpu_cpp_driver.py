@@ -1,0 +1,225 @@
+"""CPU tests of the C++ host driver (host/gpat_driver.cpp): switches, conf.dat, frame / map / surface / tag
+files, call order and output files -- the host logic above the C ABI.
+
+The driver binary is the product's; the library underneath it is replaced, for these tests only, by the
+TEST DOUBLE in tests/abi_mock/ (LD_PRELOAD), whose entry points forward to the CPU oracle.  The same
+sequence driven from Python (run_intervals on oracle.Oracle) must then give bit-identical files.  The
+GPU counterparts of these tests (the real library under the same binary) are in test_gpu_parity.py.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle.oracle import Oracle
+from stochastic_parker_b200 import WORKLOADS, config, mhd, run_intervals
+from stochastic_parker_b200.abi import PARTICLE_DTYPE
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MOCK_DIR = os.path.join(ROOT, "tests", "abi_mock")
+MOCK = os.path.join(MOCK_DIR, "_build", "libgpat_testdouble.so")
+DRIVER = os.path.join(ROOT, "host", "gpat_driver")
+
+
+@pytest.fixture(scope="module")
+def driver():
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+    if not os.path.exists(os.path.join(ROOT, "stochastic_parker_b200", "csrc", "libgpat_cuda.so")):
+        pytest.skip("the product library is not built (the driver links against it)")
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "host")], check=True)
+    os.makedirs(os.path.dirname(MOCK), exist_ok=True)
+    subprocess.run(["gcc", "-O1", "-shared", "-fPIC", "-Wall", "-o", MOCK, os.path.join(MOCK_DIR, "gpat_mock.c"),
+                    "-L" + os.path.join(ROOT, "oracle"), "-lorc", "-Wl,-rpath," + os.path.join(ROOT, "oracle")],
+                   check=True)
+
+    def run(args, expect_ok=True):
+        env = dict(os.environ, LD_PRELOAD=MOCK, OMP_NUM_THREADS="4")
+        r = subprocess.run([DRIVER] + [str(a) for a in args], capture_output=True, text=True, timeout=600, env=env)
+        if expect_ok:
+            assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        return r
+    return run
+
+
+def _setup(tmp_path, key, grid, nptl, nfr, conf=None, cli=None):
+    w = WORKLOADS[key].scaled(grid=grid, nptl=nptl)
+    if conf:
+        w.conf = dict(w.conf, **conf)
+    if cli:
+        w.cli = dict(w.cli, **cli)
+    d = tmp_path / "mhd"
+    cfg = mhd.write_run(str(d), w.kind, w.nx, w.ny, w.nz, nframes=nfr, lx=w.lx, ly=w.ly, lz=w.lz, dt_out=w.dt_out)
+    (tmp_path / "conf.dat").write_text(w.conf_text())
+    out = tmp_path / "out"
+    out.mkdir()
+    P = config.build_params(w.conf_text(), mhd.read_mhd_config(str(d / "mhd_config.dat")), w.ndim, nframes=nfr - 1,
+                            cli=w.cli)
+    frames = [mhd.read_frame(str(d), f, dict(cfg, ndim=w.ndim)) for f in range(nfr)]
+    base = ["-nl", ".false.", "-pv", repr(w.particle_v0), "-dm", str(d) + "/", "-np", nptl, "-ti", "1", "-ts", "0",
+            "-te", nfr - 1, "-df", "1", "-pi", "6.2", "-sf", "1", "-sr", "1.05", "-ps", "1.05", "-ni", "100",
+            "-dt", "0.0", "-dd", str(out) + "/", "-cf", str(tmp_path / "conf.dat"), "-ld", ".true.", "-nm", 12 * nptl,
+            "-in", ".true.", "-nd", w.ndim, "-dp1", "850964.408", "-dp2", "13575468.975", "-ch", "-1"]
+    return w, P, frames, d, out, base
+
+
+def _spectra(out, frame):
+    raw = open(out / f"fdists_{frame:04d}.bin", "rb").read()
+    nmu, npp = np.frombuffer(raw[:8], dtype=np.int32)
+    return np.frombuffer(raw[8:8 + 8 * nmu * npp], dtype=np.float64).reshape(npp, nmu)
+
+
+def _same_run(r, out, rec, steps, nfr, local=True):
+    assert f"Total particle steps: {steps} " in r.stdout
+    for d in rec:
+        assert np.array_equal(_spectra(out, d["frame"]), d["fglobal"]), d["frame"]
+        if local and d["flocal"][1] is not None:
+            loc = open(out / f"fdists_local2_{d['frame']:04d}.bin", "rb").read()
+            shp = np.frombuffer(loc[:20], dtype=np.int32)
+            assert np.array_equal(np.frombuffer(loc[20:], dtype=np.float64).reshape(tuple(shp[::-1])), d["flocal"][1])
+    rows = open(out / "quick.dat").read().splitlines()
+    assert rows[0].split()[:3] == ["iframe", "nptl_current", "nptl_split"] and len(rows) == 1 + nfr
+    assert rows[-1][:6] == f"{nfr - 1:06d}" and float(rows[-1][6:19]) == float(f"{rec[-1]['quick'][0]:.6E}")
+    assert len(open(out / "pmax_global.dat").read().split()) == nfr
+
+
+KW = dict(dist_flag=1, power_index=6.2, split_ratio=1.05, pmin_split=1.05)
+
+
+def test_basic_2d_run_with_split_and_local_spectra(driver, tmp_path):
+    w, P, frames, d, out, base = _setup(tmp_path, "c1", 48, 800, 4)
+    r = driver(base)
+    rec, steps = run_intervals(Oracle(P, 12 * 800), frames, [f * w.dt_out for f in range(4)], nptl=800,
+                               particle_v0=w.particle_v0, **KW)
+    _same_run(r, out, rec, steps, 4)
+
+
+def test_fine_steps_part_box_and_power_law(driver, tmp_path):
+    w, P, frames, d, out, base = _setup(tmp_path, "c3", 48, 600, 3)
+    box = [P.xmin + 0.1 * P.lx, P.ymin, 0.0, P.xmin + 0.4 * P.lx, P.ymax, 0.0]
+    args = base + ["-nf", "3", "-ip", ".true.", "-xs", box[0], "-ys", box[1], "-zs", box[2], "-xe", box[3],
+                   "-ye", box[4], "-ze", box[5], "-df", "2", "-in", ".false.", "-ded", ".true."]
+    r = driver(args)
+    rec, steps = run_intervals(Oracle(P, 12 * 600), frames, [f * w.dt_out for f in range(3)], nptl=600,
+                               particle_v0=w.particle_v0, **dict(KW, dist_flag=2), num_fine_steps=3, part_box=box,
+                               inject_new_ptl=False, dump_escaped_dist=True)
+    _same_run(r, out, rec, steps, 3)
+
+
+@pytest.mark.parametrize("switch,extra,mode,vmin,norm", [
+    ("-ij", ["-jz", "0.5", "-nn", "40"], 1, 0.5, 40),
+    ("-iaj", ["-ajm", "0.5", "-naj", "40"], 2, 0.5, 40),
+    ("-iv", ["-dv", "0.2", "-nv", "40"], 4, 0.2, 40),
+])
+def test_targeted_injection_switches(driver, tmp_path, switch, extra, mode, vmin, norm):
+    w, P, frames, d, out, base = _setup(tmp_path, "c1", 48, 500, 3)
+    r = driver(base + [switch, ".true.", "-sn", ".false."] + extra)
+    rec, steps = run_intervals(Oracle(P, 12 * 500), frames, [f * w.dt_out for f in range(3)], nptl=500,
+                               particle_v0=w.particle_v0, **KW, inject_mode=mode, inject_same_nptl=False,
+                               inject_min=vmin, ncells_norm=norm)
+    _same_run(r, out, rec, steps, 3)
+
+
+def test_shock_injection_switch(driver, tmp_path):
+    w, P, frames, d, out, base = _setup(tmp_path, "c3", 48, 500, 3)
+    r = driver(base + ["-is", ".true."])
+    rec, steps = run_intervals(Oracle(P, 12 * 500), frames, [f * w.dt_out for f in range(3)], nptl=500,
+                               particle_v0=w.particle_v0, **KW, inject_mode=6)
+    _same_run(r, out, rec, steps, 3)
+
+
+def test_one_dimensional_run(driver, tmp_path):
+    w, P, frames, d, out, base = _setup(tmp_path, "s1", 256, 500, 3)
+    r = driver(base)
+    rec, steps = run_intervals(Oracle(P, 12 * 500), frames, [f * w.dt_out for f in range(3)], nptl=500,
+                               particle_v0=w.particle_v0, **KW)
+    _same_run(r, out, rec, steps, 3)
+
+
+def test_focused_transport_switches(driver, tmp_path):
+    w, P, frames, d, out, base = _setup(tmp_path, "c1", 48, 400, 3, conf=dict(dt_min_rel=1e-3),
+                                        cli=dict(focused_transport=1, duu_init=5.0))
+    r = driver(base + ["-ft", ".true.", "-du", "5.0"])
+    rec, steps = run_intervals(Oracle(P, 12 * 400), frames, [f * w.dt_out for f in range(3)], nptl=400,
+                               particle_v0=w.particle_v0, **KW)
+    assert P.nmu_global > 1
+    _same_run(r, out, rec, steps, 3)
+
+
+def test_turbulence_map_files(driver, tmp_path):
+    w, P, frames, d, out, base = _setup(tmp_path, "c1", 48, 400, 3)
+    P.deltab_flag = 1
+    P.correlation_flag = 1
+    maps = [mhd.make_turbulence_maps(w.nx, w.ny, w.nz, f, 2, w.dt_out) for f in range(3)]
+    for f, (s2s, s22, lcs, lc2) in enumerate(maps):
+        np.stack([s2s, s22]).tofile(str(d / f"deltab_{f:04d}"))
+        np.stack([lcs, lc2]).tofile(str(d / f"lc_{f:04d}"))
+    r = driver(base + ["-db", "1", "-co", "1"])
+
+    class WithMaps(Oracle):   # run_intervals has no map hook: upload them with the frames
+        def upload_fields(self, slot, f, with_grad=0):
+            super().upload_fields(slot, f, with_grad)
+            k = next(i for i, fr in enumerate(frames) if fr is f)
+            self.upload_turbulence(0, slot, maps[k][0], maps[k][1])
+            self.upload_turbulence(1, slot, maps[k][2], maps[k][3])
+    rec, steps = run_intervals(WithMaps(P, 12 * 400), frames, [f * w.dt_out for f in range(3)], nptl=400,
+                               particle_v0=w.particle_v0, **KW)
+    _same_run(r, out, rec, steps, 3)
+    os.remove(d / "lc_0002")
+    assert driver(base + ["-db", "1", "-co", "1"], expect_ok=False).returncode != 0
+
+
+def test_acceleration_surface_files(driver, tmp_path):
+    w, P, frames, d, out, base = _setup(tmp_path, "c5", 24, 400, 3, conf=dict(acc_region_flag=1, r1=4, r2=8, r3=12),
+                                        cli=dict(acc_by_surface=1, surface_norm1="+z", surface2_existed=1,
+                                                 surface_norm2="-y", is_intersection=1))
+    for f in range(3):
+        for k, stem in enumerate(("surf_a", "surf_b")):
+            mhd.make_acc_surface(P, k, f).tofile(str(d / f"{stem}_{f:04d}.dat"))
+    args = base + ["-as", "1", "-sn1", "+z", "-s2e", ".true.", "-sn2", "-y", "-ii", ".true.", "-sf1", "surf_a",
+                   "-sf2", "surf_b"]
+    r = driver(args)
+    rec, steps = run_intervals(Oracle(P, 12 * 400), frames, [f * w.dt_out for f in range(3)], nptl=400,
+                               particle_v0=w.particle_v0, **KW, surfaces=lambda k, f: mhd.make_acc_surface(P, k, f))
+    _same_run(r, out, rec, steps, 3)
+    ungated, _ = run_intervals(Oracle(config.build_params(w.conf_text(), mhd.read_mhd_config(str(d / "mhd_config.dat")),
+                                                          3, nframes=2, cli=dict(w.cli, acc_by_surface=0)), 12 * 400),
+                               frames, [f * w.dt_out for f in range(3)], nptl=400, particle_v0=w.particle_v0, **KW)
+    assert not np.array_equal(ungated[-1]["fglobal"], rec[-1]["fglobal"])   # the gate matters in this case
+    os.remove(d / "surf_b_0001.dat")
+    assert driver(args, expect_ok=False).returncode != 0
+
+
+def test_tracking_run(driver, tmp_path):
+    from stochastic_parker_b200 import tracking
+    w, P, frames, d, out, base = _setup(tmp_path, "c1", 48, 500, 3, conf=dict(dt_min_rel=1e-4))
+    ts = [f * w.dt_out for f in range(3)]
+    first = Oracle(P, 12 * 500)
+    run_intervals(first, frames, ts, nptl=500, particle_v0=w.particle_v0, **KW, inject_new_ptl=False)
+    dump = first.download_particles()
+    assert dump["split_times"].max() >= 1
+    tags = tracking.select_tags(dump, np.argsort(dump["p"])[-12:])
+    with open(tmp_path / "tags.bin", "wb") as f:
+        np.array(tags.shape, dtype=np.int32).tofile(f)
+        np.ascontiguousarray(tags, dtype=np.int32).tofile(f)
+    r = driver(base + ["-tf", ".true.", "-ptf", str(tmp_path / "tags.bin"), "-in", ".false."])
+    got = {}
+    o = Oracle(P, 12 * 500)
+    rec, steps = run_intervals(o, frames, ts, nptl=500, particle_v0=w.particle_v0, **KW, inject_new_ptl=False,
+                               track_tags=tags, on_tracked=lambda tf, a: got.__setitem__(tf, a.copy()))
+    assert f"Total particle steps: {steps} " in r.stdout
+    for tf, want in got.items():
+        raw = open(out / f"particle_tracking_particles_tracked_{tf:04d}.bin", "rb").read()
+        ntrk, nmax = np.frombuffer(raw[:16], dtype=np.int64)
+        have = np.frombuffer(raw[16:], dtype=PARTICLE_DTYPE).reshape(ntrk, nmax)
+        assert have.shape == want.shape
+        for name in PARTICLE_DTYPE.names:   # field by field: the two pad bytes of the record are not data
+            assert np.array_equal(have[name], want[name]), (tf, name)
+    assert not os.path.exists(out / "fdists_0001.bin")   # no distributions in a tracking run
+
+
+def test_bad_switches_stop_the_driver(driver, tmp_path):
+    w, P, frames, d, out, base = _setup(tmp_path, "c1", 32, 50, 2)
+    assert driver(base + ["-nosuch", "1"], expect_ok=False).returncode == 2
+    assert driver(base + ["-rf", ".true."], expect_ok=False).returncode == 2
+    assert driver(base[:4] + ["-dm", str(tmp_path / "nowhere") + "/"] + base[6:], expect_ok=False).returncode == 2
