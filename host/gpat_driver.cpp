@@ -16,6 +16,9 @@
 //   fdists_localK_NNNN.bin  i32 nmu, np, nrx, nry, nrz | f64 flocalK(nmu,np,nrx,nry,nrz)
 //
 // build: make -C host      run: host/gpat_driver -dm <mhd dir>/ -cf conf.dat -np 100000 -te 3 ...
+#include <sys/stat.h>
+
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -211,7 +214,7 @@ int main(int argc, char** argv)
         return 2;
     }
     // features outside the GPU path must stay off; the library re-checks the ones it is told about
-    for (const char* k : {"-rf", "-vdt"})
+    for (const char* k : {"-vdt"})
         if (cli.b(k)) {
             std::fprintf(stderr, "gpat_driver: switch %s is outside the GPU particle path\n", k);
             return 2;
@@ -294,6 +297,35 @@ int main(int argc, char** argv)
     gpat_handle h = nullptr;
     const long long nptl_max = cli.i("-nm"), nptl = cli.i("-np");
     CK(gpat_init(&h, (int)cli.i("-gpu"), nptl_max, &P), "gpat_init");
+
+    // restart_flag (stochastic-mhd.f90:224-239): tmin from restart/latest_restart, then read_particles(tmin)
+    // and read_particle_module_state(tmin).  The reference's HDF5 containers are raw records here (the
+    // formats are stated next to stochastic_parker_b200.driver.dump_restart, which writes the same files).
+    int tmin = t_start;
+    if (cli.b("-rf")) {
+        const std::string rdir = diag_dir + "restart/";
+        int32_t t32 = 0;
+        FILE* f = std::fopen((rdir + "latest_restart").c_str(), "rb");
+        if (!f || std::fread(&t32, sizeof(t32), 1, f) != 1) return die(h, "read restart/latest_restart", -1);
+        std::fclose(f);
+        tmin = t32;
+        char name[64];
+        std::snprintf(name, sizeof(name), "particles_%04d.bin", tmin);
+        f = std::fopen((rdir + name).c_str(), "rb");
+        int64_t n = 0;
+        if (!f || std::fread(&n, sizeof(n), 1, f) != 1 || n < 0 || n > nptl_max) return die(h, "read restart particles header", -1);
+        std::vector<gpat_particle> ptl((size_t)n);
+        if (std::fread(ptl.data(), sizeof(gpat_particle), (size_t)n, f) != (size_t)n) return die(h, "read restart particles", -1);
+        std::fclose(f);
+        std::snprintf(name, sizeof(name), "particle_module_state_%04d.bin", tmin);
+        gpat_counters rc{};
+        f = std::fopen((rdir + name).c_str(), "rb");
+        if (!f || std::fread(&rc, sizeof(rc), 1, f) != 1) return die(h, "read restart particle_module_state", -1);
+        std::fclose(f);
+        CK(gpat_upload_particles(h, ptl.data(), n), "gpat_upload_particles");
+        CK(gpat_set_counters(h, &rc), "gpat_set_counters");
+        std::printf("This is a restart of a previous simulation (frame %d, %lld particles)\n", tmin, (long long)n);
+    }
 
     // farray(:, -1:nx+2, [-1:ny+2, [-1:nz+2]]) (mhd_data_parallel.f90:77-83)
     const size_t ncell = (size_t)(mc.nx + 4) * (P.ndim >= 2 ? mc.ny + 4 : 1) * (P.ndim == 3 ? mc.nz + 4 : 1);
@@ -451,14 +483,16 @@ int main(int argc, char** argv)
     };
 
     // ---- solve_transport_equation (stochastic-mhd.f90:312-567) ----
-    if (!read_frame(dir_mhd, t_start, ncell * 8, frame)) return die(h, "read first mhd_data frame", -1);
+    if (!read_frame(dir_mhd, tmin, ncell * 8, frame)) return die(h, "read first mhd_data frame", -1);
     CK(gpat_upload_fields(h, 0, frame.data(), 8, 0), "gpat_upload_fields");
-    CK(upload_surfaces(t_start, 0), "gpat_upload_acc_surface");
-    CK(upload_maps(t_start, 0), "gpat_upload_turbulence");
+    CK(upload_surfaces(tmin, 0), "gpat_upload_acc_surface");
+    CK(upload_maps(tmin, 0), "gpat_upload_turbulence");
     uint64_t total_steps = 0;
     auto wall0 = std::chrono::steady_clock::now();
     auto step1 = wall0;
-    for (int tf = t_start + 1; tf <= t_end; ++tf) {
+    bool reached_quota = false;
+    int tf = tmin + 1;
+    for (; tf <= t_end; ++tf) {
         std::printf(" Starting step %d\n", tf);
         if (single_frame == 0 && tf <= tmax_mhd) {  // :400-447
             if (!read_frame(dir_mhd, tf, ncell * 8, frame)) return die(h, "read mhd_data frame", -1);
@@ -510,9 +544,46 @@ int main(int argc, char** argv)
         auto step2 = std::chrono::steady_clock::now();
         std::printf("Step %d takes %9.4f seconds.\n", tf, std::chrono::duration<double>(step2 - step1).count());
         step1 = step2;
+        // 30 minutes before the quota: stop and dump the restart files (:558-565)
+        if (std::chrono::duration<double>(step2 - wall0).count() > (cli.d("-qh") - 0.5) * 3600.0) {
+            reached_quota = true;
+            break;
+        }
+    }
+    // restart files, always written when the run ends (:252-271): dump_particles(t_end), save_particle_module_state(t_end)
+    // and latest_restart = the last finished frame
+    if (!reached_quota) {
+        tf = tf - 1;
+        std::printf("Dumping restart files at the end of the simulation\n");
+    } else {
+        std::printf("Reached quota time. Dumping restart files.\n");
     }
     gpat_counters c{};
     gpat_get_counters(h, &c);
+    {
+        const std::string rdir = diag_dir + "restart/";
+        ::mkdir(rdir.c_str(), 0777);
+        std::vector<gpat_particle> ptl((size_t)std::max<int64_t>(c.nptl_current, 1));
+        int64_t n = 0;
+        CK(gpat_download_particles(h, ptl.data(), c.nptl_current, &n), "gpat_download_particles");
+        char name[64];
+        std::snprintf(name, sizeof(name), "particles_%04d.bin", t_end);
+        FILE* f = std::fopen((rdir + name).c_str(), "wb");
+        if (!f) return die(h, "write restart particles", -1);
+        std::fwrite(&n, sizeof(n), 1, f);
+        std::fwrite(ptl.data(), sizeof(gpat_particle), (size_t)n, f);
+        std::fclose(f);
+        std::snprintf(name, sizeof(name), "particle_module_state_%04d.bin", t_end);
+        f = std::fopen((rdir + name).c_str(), "wb");
+        if (!f) return die(h, "write restart particle_module_state", -1);
+        std::fwrite(&c, sizeof(c), 1, f);
+        std::fclose(f);
+        const int32_t t32 = tf;
+        f = std::fopen((rdir + "latest_restart").c_str(), "wb");
+        if (!f) return die(h, "write restart/latest_restart", -1);
+        std::fwrite(&t32, sizeof(t32), 1, f);
+        std::fclose(f);
+    }
     const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
     std::printf("Total particle steps: %llu in %.3f s (%.4g steps/s); nptl_current = %lld\n",
                 (unsigned long long)total_steps, wall, total_steps / wall, (long long)c.nptl_current);

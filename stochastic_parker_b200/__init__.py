@@ -8,5 +8,5 @@ frames in the reference's on-disk format).
 """
 from .abi import LIB_PATH, PARTICLE_DTYPE, Counters, Params, Timings, load_library  # noqa: F401
 from .config import WORKLOADS, Workload, build_params  # noqa: F401
-from .driver import GpatError, GpatSim, run_intervals  # noqa: F401
+from .driver import GpatError, GpatSim, dump_restart, read_restart, run_intervals  # noqa: F401
 from .multi import bootstrap_comm, rank_info, reduce_diagnostics, shard_count  # noqa: F401

@@ -11,6 +11,7 @@ and owns the host buffers, exactly like the Fortran driver would.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -284,7 +285,7 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
                   split_ratio=2.0, pmin_split=2.0, nsteps_interval=100, num_fine_steps=1,
                   local_dist=True, dump_escaped_dist=False, dt_inject=0.0, on_interval=None,
                   inject_mode=0, inject_same_nptl=True, inject_min=0.0, ncells_norm=1,
-                  track_tags=None, on_tracked=None, surfaces=None):
+                  track_tags=None, on_tracked=None, surfaces=None, tmin=0, quota_seconds=None):
     """solve_transport_equation (stochastic-mhd.f90:312-567) for one rank.
 
     `sim` is a GpatSim (or the test oracle, which has the same methods); `frames` is a
@@ -292,7 +293,10 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
     time of frame i (tstamps_mhd, mhd_config.f90:263-271).  Returns the per-interval records
     the reference writes to quick.dat / pmax_global.dat / fdists_NNNN.h5.  With acc_by_surface,
     `surfaces(which, frame)` returns the float64 heights of acceleration surface `which` at that frame
-    (the content of <surface_filenameK>_NNNN.dat).
+    (the content of <surface_filenameK>_NNNN.dat).  `tmin` > 0 continues a run restored with
+    read_restart() (frames are still indexed from the run's t_start = 0); `quota_seconds` ends the loop after
+    the first interval that finishes beyond it (reached_quota, :558-565).  The frame the loop stopped at is
+    left in run_intervals.last_frame for dump_restart().
     """
     get = frames if callable(frames) else (lambda i: frames[i])
     P = sim.P
@@ -303,14 +307,17 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
         part_box = [P.xmin, P.ymin, P.zmin, P.xmax, P.ymax, P.zmax]
     nframes = len(tstamps)
     records = []
-    sim.upload_fields(0, get(0))                               # :320-321, :350
+    import time as _time
+    start = _time.time()
+    run_intervals.last_frame = tmin
+    sim.upload_fields(0, get(tmin))                            # :320-321, :350 (mhd_data_<tmin>)
     nsurf = (2 if P.surface2_existed else 1) if P.acc_by_surface else 0
     if nsurf and surfaces is None:
         raise ValueError("acc_by_surface needs the `surfaces` callable")
     for k in range(nsurf):                                     # :323-334 read_acc_surface(0, ...)
-        sim.upload_acc_surface(k, 0, surfaces(k, 0))
+        sim.upload_acc_surface(k, 0, surfaces(k, tmin))
     total_steps = 0
-    for tf in range(1, nframes):                               # :397
+    for tf in range(tmin + 1, nframes):                        # :397
         # read_field_data_parallel(..., var_flag=time_interp_flag): without time interpolation
         # the new frame REPLACES farray1 (:404-406, :426)
         sim.upload_fields(1 if P.time_interp else 0, get(tf))
@@ -344,6 +351,9 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
             records.append(d)
             if P.time_interp:
                 sim.swap_fields()
+            run_intervals.last_frame = tf
+            if quota_seconds is not None and _time.time() - start > quota_seconds:
+                break
             continue
         d = sim.diagnostics(local_dist)                        # :518-521
         d["frame"] = tf
@@ -356,4 +366,49 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
             on_interval(tf, d)
         if P.time_interp:
             sim.swap_fields()                                  # :538
+        run_intervals.last_frame = tf
+        if quota_seconds is not None and _time.time() - start > quota_seconds:   # :558-565
+            break
     return records, total_steps
+
+
+run_intervals.last_frame = 0
+
+
+def dump_restart(sim, diagnostics_directory: str, t_end: int, tf: int) -> None:
+    """The restart files the reference always writes when a run ends (stochastic-mhd.f90:252-271):
+    dump_particles(t_end) + save_particle_module_state(t_end) into <dir>/restart/ and latest_restart = tf.
+    (The files carry t_end in their names and latest_restart the last finished frame, as in the reference,
+    so a run cut short by its quota can only be resumed after renaming -- kept as it is there.)  The
+    reference's HDF5 containers are replaced by raw records (no HDF5 in this image):
+      particles_NNNN.bin               int64 nptl, then nptl x gpat_particle (104 B; the Philox step counter
+                                       rides in `padding`, so no separate save_prng file is needed)
+      particle_module_state_NNNN.bin   gpat_counters (nptl_current, nptl_split, nptl_escaped, nptl_max, tag_max,
+                                       leak, leak_negp)
+      latest_restart                   int32 tf (the reference's own format)"""
+    d = os.path.join(diagnostics_directory, "restart")
+    os.makedirs(d, exist_ok=True)
+    ptl = sim.download_particles()
+    with open(os.path.join(d, f"particles_{t_end:04d}.bin"), "wb") as f:
+        np.array([len(ptl)], dtype=np.int64).tofile(f)
+        ptl.tofile(f)
+    with open(os.path.join(d, f"particle_module_state_{t_end:04d}.bin"), "wb") as f:
+        f.write(bytes(sim.counters()))
+    np.array([tf], dtype=np.int32).tofile(os.path.join(d, "latest_restart"))
+
+
+def read_restart(sim, diagnostics_directory: str) -> int:
+    """restart_flag (stochastic-mhd.f90:224-236): tmin from latest_restart, then read_particles(tmin) and
+    read_particle_module_state(tmin).  Returns tmin for run_intervals(..., tmin=tmin)."""
+    d = os.path.join(diagnostics_directory, "restart")
+    tmin = int(np.fromfile(os.path.join(d, "latest_restart"), dtype=np.int32)[0])
+    with open(os.path.join(d, f"particles_{tmin:04d}.bin"), "rb") as f:
+        n = int(np.fromfile(f, dtype=np.int64, count=1)[0])
+        ptl = np.fromfile(f, dtype=PARTICLE_DTYPE, count=n)
+    if len(ptl) != n:
+        raise IOError(f"particles_{tmin:04d}.bin is truncated")
+    raw = open(os.path.join(d, f"particle_module_state_{tmin:04d}.bin"), "rb").read()
+    c = Counters.from_buffer_copy(raw)
+    sim.upload_particles(ptl)
+    sim.set_counters(c)
+    return tmin

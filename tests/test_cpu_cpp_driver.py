@@ -221,5 +221,49 @@ def test_tracking_run(driver, tmp_path):
 def test_bad_switches_stop_the_driver(driver, tmp_path):
     w, P, frames, d, out, base = _setup(tmp_path, "c1", 32, 50, 2)
     assert driver(base + ["-nosuch", "1"], expect_ok=False).returncode == 2
-    assert driver(base + ["-rf", ".true."], expect_ok=False).returncode == 2
+    assert driver(base + ["-vdt", ".true."], expect_ok=False).returncode == 2
+    assert driver(base + ["-rf", ".true."], expect_ok=False).returncode != 0      # no restart/ files to read
     assert driver(base[:4] + ["-dm", str(tmp_path / "nowhere") + "/"] + base[6:], expect_ok=False).returncode == 2
+
+
+def test_restart_files_and_restart_flag(driver, tmp_path):
+    """-te 2, then -rf .true. -te 4: the restart files the driver always writes at the end
+    (stochastic-mhd.f90:252-271) resume the run bit-identically; run_intervals' dump_restart / read_restart use
+    the same files."""
+    from stochastic_parker_b200 import dump_restart, read_restart
+    w, P, frames, d, out, base = _setup(tmp_path, "c3", 48, 500, 5)
+    ts = [f * w.dt_out for f in range(5)]
+    te = base.index("-te") + 1
+    first = list(base)
+    first[te] = 2
+    driver(first + ["-nf", "2"])
+    rdir = out / "restart"
+    assert np.fromfile(rdir / "latest_restart", dtype=np.int32)[0] == 2
+    r = driver(base + ["-nf", "2", "-rf", ".true."])
+    assert "This is a restart" in r.stdout and " Starting step 3" in r.stdout and " Starting step 2" not in r.stdout
+    full = Oracle(P, 12 * 500)
+    rec, steps = run_intervals(full, frames, ts, nptl=500, particle_v0=w.particle_v0, **KW, num_fine_steps=2)
+    for rd in rec:
+        assert np.array_equal(_spectra(out, rd["frame"]), rd["fglobal"]), rd["frame"]
+    rows = open(out / "quick.dat").read().splitlines()
+    assert len(rows) == 1 + 5 and [int(x[:6]) for x in rows[1:]] == [0, 1, 2, 3, 4]
+    # the files of the second run hold the final population of the uninterrupted run
+    assert np.fromfile(rdir / "latest_restart", dtype=np.int32)[0] == 4
+    raw = open(rdir / "particles_0004.bin", "rb").read()
+    n = np.frombuffer(raw[:8], dtype=np.int64)[0]
+    got = np.frombuffer(raw[8:], dtype=PARTICLE_DTYPE)
+    want = full.download_particles()
+    assert n == len(want) == len(got)
+    for name in PARTICLE_DTYPE.names:
+        assert np.array_equal(got[name], want[name]), name
+    # and Python reads what C++ wrote (first run's files), continuing to the same end state
+    o = Oracle(P, 12 * 500)
+    np.array([2], dtype=np.int32).tofile(rdir / "latest_restart")
+    assert read_restart(o, str(out) + "/") == 2
+    run_intervals(o, frames, ts, nptl=500, particle_v0=w.particle_v0, **KW, num_fine_steps=2, tmin=2)
+    have = o.download_particles()
+    for name in PARTICLE_DTYPE.names:
+        assert np.array_equal(have[name], want[name]), name
+    dump_restart(o, str(tmp_path / "py") + "/", 4, 4)
+    assert open(tmp_path / "py" / "restart" / "particle_module_state_0004.bin", "rb").read() == \
+        open(rdir / "particle_module_state_0004.bin", "rb").read()

@@ -1187,3 +1187,31 @@ def test_escaped_distributions_match_numpy_binning():
     assert np.array_equal(o2.escaped_diagnostics(), ref)
     assert np.array_equal(got[0][0], ref)          # the same interval through run_intervals
     assert ref.sum() == esc["weight"].sum() == o2.counters().leak
+
+
+def test_host_restart_files_continue_the_run_bit_identically(tmp_path):
+    """dump_restart / read_restart + run_intervals(tmin=): a run stopped after frame 2 (quota), dumped and
+    resumed in a fresh simulation gives the particles, counters and spectra of the uninterrupted run."""
+    from stochastic_parker_b200 import dump_restart, read_restart
+    w, P, frames, ts = make_case("c3", grid=48, nptl=600, nframes=5)
+    kw = dict(nptl=600, dist_flag=2, particle_v0=w.particle_v0, pmin_split=1.05, split_ratio=1.05, num_fine_steps=2)
+    a = Oracle(P, 20000)
+    full, _ = run_intervals(a, frames, ts, **kw)
+    b = Oracle(P, 20000)
+    part1, _ = run_intervals(b, frames[:3], ts[:3], **kw)            # -te 2
+    assert run_intervals.last_frame == 2
+    dump_restart(b, str(tmp_path) + "/", 2, run_intervals.last_frame)
+    c = Oracle(P, 20000)
+    tmin = read_restart(c, str(tmp_path) + "/")
+    assert tmin == 2
+    part2, _ = run_intervals(c, frames, ts, tmin=tmin, **kw)         # -rf .true. -te 4
+    assert [d["frame"] for d in part1 + part2] == [d["frame"] for d in full]      # no second frame-0 record
+    for x, y in zip(part1 + part2, full):
+        assert np.array_equal(x["fglobal"], y["fglobal"]) and np.array_equal(x["quick"], y["quick"])
+    assert_particles_identical(c.download_particles(), a.download_particles(), "restart")
+    ca, cc = a.counters(), c.counters()
+    assert (ca.nptl_current, ca.nptl_split, ca.tag_max, ca.leak) == (cc.nptl_current, cc.nptl_split, cc.tag_max, cc.leak)
+    # quota: the loop stops after the first interval that ends beyond it
+    d = Oracle(P, 20000)
+    rec, _ = run_intervals(d, frames, ts, quota_seconds=0.0, **kw)
+    assert run_intervals.last_frame == 1 and [r["frame"] for r in rec] == [0, 1]
