@@ -18,7 +18,7 @@ module gpat_cuda
     public :: gpat_download_particles, gpat_upload_particles
     public :: gpat_download_escaped, gpat_reset_escaped
     public :: gpat_get_counters, gpat_set_counters
-    public :: gpat_diagnostics, gpat_escaped_diagnostics, gpat_hist_edges
+    public :: gpat_diagnostics, gpat_escaped_diagnostics, gpat_escaped_local_diagnostics, gpat_hist_edges
     public :: gpat_comm_unique_id, gpat_comm_init, gpat_comm_destroy
     public :: gpat_get_timings, gpat_check
 
@@ -278,6 +278,15 @@ module gpat_cuda
             import :: c_ptr, c_int
             type(c_ptr), value :: h, fescaped
         end function gpat_escaped_diagnostics
+
+        !< calc_escaped_distributions, local part (diagnostics.f90:956-1170): fx/fy/fz are arrays of four
+        !< c_ptr (c_loc(fescapedK_x) ... or c_null_ptr), K = 1..4
+        integer(c_int) function gpat_escaped_local_diagnostics(h, fx, fy, fz) &
+                bind(C, name="gpat_escaped_local_diagnostics")
+            import :: c_ptr, c_int
+            type(c_ptr), value :: h
+            type(c_ptr), intent(in) :: fx(4), fy(4), fz(4)
+        end function gpat_escaped_local_diagnostics
 
         integer(c_int) function gpat_hist_edges(h, which, pedges, muedges) bind(C, name="gpat_hist_edges")
             import :: c_ptr, c_int

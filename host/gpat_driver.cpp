@@ -404,6 +404,49 @@ int main(int argc, char** argv)
         return 0;
     };
 
+    // escaped_dists_NNNN: calc_escaped_distributions + save_global/local_escaped_distributions
+    // (diagnostics.f90:913-1232, 1331-1372, 1536-1642) as raw records:
+    //   escaped_dists_NNNN.bin         int32 nmu, npp, nface; fescaped(nmu, npp, nface)
+    //   escaped_dists_localK_NNNN.bin  int32 nmu, npbins, nrx, nry, nrz, ndim; fescapedK_x, [_y, [_z]]
+    auto escaped_diagnostics = [&](int iframe) -> int {
+        const int nface = 2 * P.ndim;
+        std::vector<double> fesc((size_t)P.nmu_global * P.npp_global * nface);
+        int rc = gpat_escaped_diagnostics(h, fesc.data());
+        if (rc) return rc;
+        char name[64];
+        std::snprintf(name, sizeof(name), "escaped_dists_%04d.bin", iframe);
+        FILE* f = std::fopen((diag_dir + name).c_str(), "wb");
+        if (!f) return -1;
+        const int32_t hdr[3] = {P.nmu_global, P.npp_global, nface};
+        std::fwrite(hdr, sizeof(int32_t), 3, f);
+        std::fwrite(fesc.data(), sizeof(double), fesc.size(), f);
+        std::fclose(f);
+        if (!local_dist) return 0;
+        std::vector<double> face[3][4];
+        double *fx[4] = {}, *fy[4] = {}, *fz[4] = {};
+        for (int k = 0; k < 4; ++k) {
+            if (!flocal_ptr[k]) continue;
+            const size_t nb = (size_t)lshape[k][0] * lshape[k][1] * 2;
+            face[0][k].assign(nb * lshape[k][3] * lshape[k][4], 0.0); fx[k] = face[0][k].data();
+            if (P.ndim > 1) { face[1][k].assign(nb * lshape[k][2] * lshape[k][4], 0.0); fy[k] = face[1][k].data(); }
+            if (P.ndim > 2) { face[2][k].assign(nb * lshape[k][2] * lshape[k][3], 0.0); fz[k] = face[2][k].data(); }
+        }
+        rc = gpat_escaped_local_diagnostics(h, fx, fy, fz);
+        if (rc) return rc;
+        for (int k = 0; k < 4; ++k) {
+            if (!flocal_ptr[k]) continue;
+            std::snprintf(name, sizeof(name), "escaped_dists_local%d_%04d.bin", k + 1, iframe);
+            f = std::fopen((diag_dir + name).c_str(), "wb");
+            if (!f) return -1;
+            std::fwrite(lshape[k], sizeof(int32_t), 5, f);
+            const int32_t nd = P.ndim;
+            std::fwrite(&nd, sizeof(int32_t), 1, f);
+            for (int a = 0; a < 3; ++a) std::fwrite(face[a][k].data(), sizeof(double), face[a][k].size(), f);
+            std::fclose(f);
+        }
+        return 0;
+    };
+
     // ---- particle tracking (stochastic-mhd.f90:226-229): the tag table is the reference's HDF5
     // dataset "tags" (nptl_tracking x (split_times_max+2) int32, C order) as a raw file
     // [int32 nptl_tracking, int32 ncols, data...] -- no HDF5 in this image
@@ -535,7 +578,10 @@ int main(int argc, char** argv)
         if (!track) {  // :516-535
             CK(diagnostics(tf, false), "diagnostics");  // :518-521
             std::printf(" Finishing distribution diagnostics \n");
-            if (dump_escaped_dist) CK(gpat_reset_escaped(h), "gpat_reset_escaped");  // :533
+            if (dump_escaped_dist) {  // :522-534: escaped spectra of this interval, then reset_escaped_particles
+                CK(escaped_diagnostics(tf), "escaped diagnostics");
+                CK(gpat_reset_escaped(h), "gpat_reset_escaped");
+            }
         }
         if (P.time_interp == 1) {
             CK(gpat_swap_fields(h), "gpat_swap_fields");  // :538

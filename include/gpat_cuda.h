@@ -337,6 +337,15 @@ int gpat_escaped_diagnostics(gpat_handle h, double* fescaped);
 
 /* Bin edges, init_particle_distributions (diagnostics.f90:196-209, 270-283).
  * which = 0 global, 1..4 local set.  pedges has npbins+1, muedges nmu+1 values. */
+/* calc_escaped_distributions, local part (diagnostics.f90:956-1170; arrays of
+ * init_local_escaped_distributions, diagnostics.f90:358-405), already summed over ranks like the
+ * MPI_REDUCEs of diagnostics.f90:1174-1230.  For each enabled local set k (0..3):
+ *   fx[k] = fescaped{k+1}_x(nmu, npbins, nry, nrz, 2)
+ *   fy[k] = fescaped{k+1}_y(nmu, npbins, nrx, nrz, 2)   (ndim > 1)
+ *   fz[k] = fescaped{k+1}_z(nmu, npbins, nrx, nry, 2)   (ndim > 2)
+ * column-major, last index 1 = low face, 2 = high face.  Null pointers (arrays, or single entries) are
+ * skipped.  Needs dump_escaped_dist = 1 in gpat_particle_mover, like gpat_escaped_diagnostics. */
+int gpat_escaped_local_diagnostics(gpat_handle h, double* const fx[4], double* const fy[4], double* const fz[4]);
 int gpat_hist_edges(gpat_handle h, int which, double* pedges, double* muedges);
 
 /* ---- multi-GPU (one process per GPU) ------------------------------------ */

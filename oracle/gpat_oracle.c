@@ -2391,6 +2391,52 @@ void orc_escaped_diagnostics(const orc_sim* S, double* fescaped)
     }
 }
 
+/* local part of calc_escaped_distributions, DG:956-1170 (+ init_local_escaped_distributions, DG:358-405):
+ * fx[k] = fescaped{k+1}_x(nmu, npbins, nry, nrz, 2), fy[k] = ..._y(nmu, npbins, nrx, nrz, 2) (ndim > 1),
+ * fz[k] = ..._z(nmu, npbins, nrx, nry, 2) (ndim > 2); last index 1 = low face, 2 = high face.
+ * The local sets add the (spherical-corrected) weight, DG:937-943: the particle's own weight here. */
+void orc_escaped_local_diagnostics(const orc_sim* S, double* const fx[4], double* const fy[4], double* const fz[4])
+{
+    const gpat_params* P = &S->P;
+    int64_t n_esc = S->nptl_escaped < S->nptl_escaped_max ? S->nptl_escaped : S->nptl_escaped_max;
+    for (int k = 0; k < 4; ++k) {
+        const gpat_hist_spec* h = &P->local[k];
+        if (!h->enabled) continue;
+        const int nrx = (P->nx + h->rx - 1) / h->rx, nry = (P->ny + h->ry - 1) / h->ry, nrz = (P->nz + h->rz - 1) / h->rz;
+        const double dxd = P->lx / nrx, dyd = P->ly / nry, dzd = P->lz / nrz;
+        const double pminl = log10(h->pmin), dpl = (log10(h->pmax) - pminl) / h->npbins;
+        const double dmul = (double)(2.0f / (float)h->nmu);
+        const size_t nb = (size_t)h->nmu * h->npbins;
+        if (fx && fx[k]) memset(fx[k], 0, sizeof(double) * nb * nry * nrz * 2);
+        if (fy && fy[k] && P->ndim > 1) memset(fy[k], 0, sizeof(double) * nb * nrx * nrz * 2);
+        if (fz && fz[k] && P->ndim > 2) memset(fz[k], 0, sizeof(double) * nb * nrx * nry * 2);
+        for (int64_t n = 0; n < n_esc; ++n) {
+            const gpat_particle* ptl = &S->escaped[n];
+            int okx = 1, oky = 1, okz = 1, okp = 1, okm = 1;
+            int64_t ix = ifloor((ptl->x - P->xmin) / dxd, &okx) + 1;
+            int64_t iy = ifloor((ptl->y - P->ymin) / dyd, &oky) + 1;
+            int64_t iz = ifloor((ptl->z - P->zmin) / dzd, &okz) + 1;
+            int64_t ip = ifloor((log10(ptl->p) - pminl) / dpl, &okp) + 1;
+            int64_t imu = ifloor((ptl->mu + 1.0) / dmul, &okm) + 1;
+            int condx = okx && ix >= 1 && ix <= nrx;
+            int condy = oky && iy >= 1 && iy <= nry;
+            int condz = okz && iz >= 1 && iz <= nrz;
+            int condp = okp && ip > 0 && ip < h->npbins;
+            int condmu = okm && imu >= 1 && imu <= h->nmu;
+            if (!(condp && condmu)) continue;
+            const size_t b = (size_t)(imu - 1) + (size_t)h->nmu * (size_t)(ip - 1);
+            const int face = -ptl->count_flag; /* 1 lx, 2 hx, 3 ly, 4 hy, 5 lz, 6 hz */
+            const size_t side = (size_t)((face - 1) & 1);
+            if ((face == 1 || face == 2) && condy && condz && fx && fx[k])
+                fx[k][b + nb * ((size_t)(iy - 1) + (size_t)nry * ((size_t)(iz - 1) + (size_t)nrz * side))] += ptl->weight;
+            else if ((face == 3 || face == 4) && condx && condz && fy && fy[k] && P->ndim > 1)
+                fy[k][b + nb * ((size_t)(ix - 1) + (size_t)nrx * ((size_t)(iz - 1) + (size_t)nrz * side))] += ptl->weight;
+            else if ((face == 5 || face == 6) && condx && condy && fz && fz[k] && P->ndim > 2)
+                fz[k][b + nb * ((size_t)(ix - 1) + (size_t)nrx * ((size_t)(iy - 1) + (size_t)nry * side))] += ptl->weight;
+        }
+    }
+}
+
 /* ------------------------------------------------------------------------ */
 /* accessors                                                                  */
 /* ------------------------------------------------------------------------ */
@@ -2417,6 +2463,14 @@ int64_t orc_get_escaped(const orc_sim* S, gpat_particle* out, int64_t nmax)
 }
 
 void orc_reset_escaped(orc_sim* S) { S->nptl_escaped = 0; }
+
+/* test hook: replace the escaped list (lets a test re-bin another implementation's escapees) */
+void orc_set_escaped(orc_sim* S, const gpat_particle* in, int64_t n)
+{
+    if (n > S->nptl_escaped_max) n = S->nptl_escaped_max;
+    memcpy(S->escaped, in, sizeof(gpat_particle) * (size_t)n);
+    S->nptl_escaped = n;
+}
 
 void orc_get_counters(const orc_sim* S, gpat_counters* c)
 {

@@ -231,6 +231,24 @@ class Oracle:
         self.lib.orc_escaped_diagnostics(self.h, ptr(out))
         return out
 
+    def escaped_local_shapes(self, k: int):
+        nrz, nry, nrx, npb, nmu = self.local_shape(k)
+        P = self.P
+        return ((2, nrz, nry, npb, nmu), (2, nrz, nrx, npb, nmu) if P.ndim > 1 else None,
+                (2, nry, nrx, npb, nmu) if P.ndim > 2 else None)
+
+    def escaped_local_diagnostics(self):
+        P = self.P
+        arrs = [[None] * 4 for _ in range(3)]
+        for k in range(4):
+            if P.local[k].enabled:
+                for f, shp in enumerate(self.escaped_local_shapes(k)):
+                    if shp is not None:
+                        arrs[f][k] = np.zeros(shp, dtype=np.float64)
+        ptrs = [(C.c_void_p * 4)(*[ptr(a) if a is not None else None for a in arrs[f]]) for f in range(3)]
+        self.lib.orc_escaped_local_diagnostics(self.h, ptrs[0], ptrs[1], ptrs[2])
+        return [dict(x=arrs[0][k], y=arrs[1][k], z=arrs[2][k]) if P.local[k].enabled else None for k in range(4)]
+
     def hist_edges(self, which: int = 0):
         P = self.P
         np_ = P.local[which - 1].npbins if which else P.npp_global

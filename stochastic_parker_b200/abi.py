@@ -152,6 +152,7 @@ SIGNATURES = {
     "gpat_diagnostics": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_void_p),
                                    C.c_void_p, C.c_void_p]),
     "gpat_escaped_diagnostics": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gpat_escaped_local_diagnostics": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "gpat_hist_edges": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "gpat_comm_unique_id": (C.c_int, [C.c_char_p]),
     "gpat_comm_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),

@@ -128,6 +128,8 @@ struct gpat_sim {
     void* sort_tmp = nullptr;
     size_t sort_tmp_bytes = 0;
     long long sort_cap = 0;
+    double* d_fesc_loc = nullptr;  // local escaped distributions (all sets, all faces)
+    size_t fesc_loc_n = 0;
     double* d_surf[2] = {nullptr, nullptr};  // acceleration surfaces: two halves each
     int surf_n1[2] = {0, 0}, surf_n2[2] = {0, 0};
     bool have_surf[2][2] = {{false, false}, {false, false}};
@@ -680,7 +682,7 @@ int gpat_finalize(gpat_handle h)
     void* ptrs[] = {h->ptl_mem, h->esc_mem, h->d_counters, h->d_nptl_split, h->d_leak, h->d_queue,
                     h->w.tile_counts, h->w.tile_offsets, h->idx_a, h->idx_b, h->fld, h->stage, h->stage2,
                     h->d_tags, h->d_tracked, h->d_shock, h->aux, h->ptl_mem2, h->sort_keys, h->sort_tmp,
-                    h->d_surf[0], h->d_surf[1],
+                    h->d_surf[0], h->d_surf[1], h->d_fesc_loc,
                     h->d_fglobal, h->d_flocal[0], h->d_flocal[1], h->d_flocal[2], h->d_flocal[3],
                     h->d_fesc, h->d_pthr, h->d_sums, h->d_minmax, h->d_quick, h->d_table, h->d_aos};
     for (void* p : ptrs)
@@ -1211,6 +1213,56 @@ int gpat_escaped_diagnostics(gpat_handle h, double* fescaped)
     }
     if (h->comm) NC(nccl().AllReduce(h->d_fesc, h->d_fesc, n, ncclDouble, ncclSum, h->comm, h->st));
     CU(cudaMemcpyAsync(fescaped, h->d_fesc, n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->st));
+    return GPAT_OK;
+}
+
+int gpat_escaped_local_diagnostics(gpat_handle h, double* const fx[4], double* const fy[4], double* const fz[4])
+{
+    if (!h) return GPAT_ERR_INVALID;
+    CU(cudaSetDevice(h->device));
+    const gpat_params& p = h->hp;
+    DiagArgs a{};
+    fill_diag_args(h, a, 1);
+    // one device buffer: per enabled set its x-, y- (ndim > 1) and z-face (ndim > 2) arrays, in that order
+    size_t off[4][3], len[4][3], total = 0;
+    for (int k = 0; k < 4; ++k) {
+        const HistDev& d = a.loc[k];
+        const size_t nb = (size_t)d.nmu * d.npbins * 2;
+        len[k][0] = d.enabled ? nb * d.nry * d.nrz : 0;
+        len[k][1] = (d.enabled && p.ndim > 1) ? nb * d.nrx * d.nrz : 0;
+        len[k][2] = (d.enabled && p.ndim > 2) ? nb * d.nrx * d.nry : 0;
+        for (int f = 0; f < 3; ++f) { off[k][f] = total; total += len[k][f]; }
+    }
+    if (total == 0) return GPAT_OK;
+    if (h->fesc_loc_n < total) {
+        if (h->d_fesc_loc) cudaFree(h->d_fesc_loc);
+        h->d_fesc_loc = nullptr;
+        h->fesc_loc_n = 0;
+        CU(cudaMalloc(&h->d_fesc_loc, total * sizeof(double)));
+        h->fesc_loc_n = total;
+    }
+    CU(cudaMemsetAsync(h->d_fesc_loc, 0, total * sizeof(double), h->st));
+    EscLocalDev o{};
+    for (int k = 0; k < 4; ++k) {
+        o.fx[k] = len[k][0] ? h->d_fesc_loc + off[k][0] : nullptr;
+        o.fy[k] = len[k][1] ? h->d_fesc_loc + off[k][1] : nullptr;
+        o.fz[k] = len[k][2] ? h->d_fesc_loc + off[k][2] : nullptr;
+    }
+    long long have = h->esc_mem ? (h->nptl_escaped < h->ecap ? h->nptl_escaped : h->ecap) : 0;
+    if (have > 0) {
+        launch_escaped_local(h->E, have, a, o, h->st);
+        h->tm.total_launches++;
+    }
+    // MPI_REDUCE of the face arrays, diagnostics.f90:1174-1230
+    if (h->comm) NC(nccl().AllReduce(h->d_fesc_loc, h->d_fesc_loc, total, ncclDouble, ncclSum, h->comm, h->st));
+    double* const* outs[3] = {fx, fy, fz};
+    for (int k = 0; k < 4; ++k)
+        for (int f = 0; f < 3; ++f)
+            if (len[k][f] && outs[f] && outs[f][k])
+                CU(cudaMemcpyAsync(outs[f][k], h->d_fesc_loc + off[k][f], len[k][f] * sizeof(double),
+                                   cudaMemcpyDeviceToHost, h->st));
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->st));
     return GPAT_OK;

@@ -204,4 +204,47 @@ void launch_escaped_diag(const PtlSoA& E, long long n, const DiagArgs& a, int nf
     if (n > 0) escaped_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(E, n, a, nface, fesc);
 }
 
+// local part of calc_escaped_distributions (diagnostics.f90:956-1170): every escaped particle is binned
+// on the face it left through, in the two coordinates of that face, with the local sets' own p and mu bins
+__global__ void escaped_local_kernel(const PtlSoA E, long long n, DiagArgs a, EscLocalDev o)
+{
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int face = -(int)E.count_flag[i];  // 1 lx, 2 hx, 3 ly, 4 hy, 5 lz, 6 hz
+    if (face < 1 || face > 6) return;
+    const double x = E.x[i], y = E.y[i], z = E.z[i], p = E.p[i], mu = E.mu[i], w = E.weight[i];
+    const double lp = log10(p);
+    const size_t side = (size_t)((face - 1) & 1);
+    for (int k = 0; k < 4; ++k) {
+        const HistDev& h = a.loc[k];
+        if (!h.enabled) continue;
+        long long ix = 0, iy = 0, iz = 0, imu = 0;
+        const bool okx = ifloor_ok((x - a.xmin) / h.dx_diag, ix), oky = ifloor_ok((y - a.ymin) / h.dy_diag, iy);
+        const bool okz = ifloor_ok((z - a.zmin) / h.dz_diag, iz), okm = ifloor_ok((mu + 1.0) / h.dmu, imu);
+        const long long ip = (long long)pbin(h.pthr, h.npbins, p, lp, h.pmin_log, h.dp_log) + 1;
+        ix += 1; iy += 1; iz += 1; imu += 1;
+        const bool condx = okx && ix >= 1 && ix <= h.nrx, condy = oky && iy >= 1 && iy <= h.nry;
+        const bool condz = okz && iz >= 1 && iz <= h.nrz;
+        const bool condp = (p == p) && ip > 0 && ip < h.npbins, condmu = okm && imu >= 1 && imu <= h.nmu;
+        if (!(condp && condmu)) continue;
+        const size_t nb = (size_t)h.nmu * h.npbins;
+        const size_t b = (size_t)(imu - 1) + (size_t)h.nmu * (size_t)(ip - 1);
+        if (face <= 2) {
+            if (condy && condz && o.fx[k])
+                atomicAdd(&o.fx[k][b + nb * ((size_t)(iy - 1) + (size_t)h.nry * ((size_t)(iz - 1) + (size_t)h.nrz * side))], w);
+        } else if (face <= 4) {
+            if (condx && condz && o.fy[k])
+                atomicAdd(&o.fy[k][b + nb * ((size_t)(ix - 1) + (size_t)h.nrx * ((size_t)(iz - 1) + (size_t)h.nrz * side))], w);
+        } else {
+            if (condx && condy && o.fz[k])
+                atomicAdd(&o.fz[k][b + nb * ((size_t)(ix - 1) + (size_t)h.nrx * ((size_t)(iy - 1) + (size_t)h.nry * side))], w);
+        }
+    }
+}
+
+void launch_escaped_local(const PtlSoA& E, long long n, const DiagArgs& a, const EscLocalDev& o, cudaStream_t st)
+{
+    if (n > 0) escaped_local_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(E, n, a, o);
+}
+
 }  // namespace gpat

@@ -233,6 +233,13 @@ struct DiagArgs {
     unsigned long long* minmax;  // [0] min dt bits [1] max dt bits [2] max p bits
 };
 
+// fescapedK_x/_y/_z of the four local sets (diagnostics.f90:358-405); null = set disabled / axis absent
+struct EscLocalDev {
+    double* fx[4];
+    double* fy[4];
+    double* fz[4];
+};
+
 // device counters (long long): [0] nptl_current [1] nptl_escaped [2] alive m [3] nholes
 // [4] nfillers [5] escaped in this pass [6] split candidates
 constexpr int kNumCounters = 8;
@@ -268,6 +275,7 @@ cudaError_t launch_cell_sort(const DevParams& prm, const PtlSoA& S, const PtlSoA
 void launch_to_aos(const PtlSoA& P, gpat_particle* out, long long n, cudaStream_t st);
 void launch_from_aos(const PtlSoA& P, const gpat_particle* in, long long n, cudaStream_t st);
 void launch_diag(const PtlSoA& P, const DiagArgs& a, int sm_count, cudaStream_t st);
+void launch_escaped_local(const PtlSoA& E, long long n, const DiagArgs& a, const EscLocalDev& o, cudaStream_t st);
 void launch_escaped_diag(const PtlSoA& E, long long n, const DiagArgs& a, int nface, double* fesc,
                          cudaStream_t st);
 void launch_finalize_quick(const double* sums, const unsigned long long* minmax, const double* leak,

@@ -245,6 +245,29 @@ class GpatSim:
                                            C.byref(pmax)), "gpat_diagnostics")
         return dict(fglobal=fglobal, flocal=flocal, quick=quick, pmax=pmax.value)
 
+    def escaped_local_shapes(self, k: int):
+        """C-order shapes of fescaped{k+1}_x, _y, _z (Fortran (nmu, npbins, n1, n2, 2), diagnostics.f90:358-405);
+        None for an axis the run does not have."""
+        nrz, nry, nrx, npb, nmu = self.local_shape(k)
+        P = self.P
+        return ((2, nrz, nry, npb, nmu), (2, nrz, nrx, npb, nmu) if P.ndim > 1 else None,
+                (2, nry, nrx, npb, nmu) if P.ndim > 2 else None)
+
+    def escaped_local_diagnostics(self):
+        """calc_escaped_distributions, local part (diagnostics.f90:956-1170): for each local set a dict
+        {"x": ..., "y": ..., "z": ...} of the face spectra (None: disabled set / absent axis)."""
+        P = self.P
+        arrs = [[None] * 4 for _ in range(3)]
+        for k in range(4):
+            if P.local[k].enabled:
+                for f, shp in enumerate(self.escaped_local_shapes(k)):
+                    if shp is not None:
+                        arrs[f][k] = np.zeros(shp, dtype=np.float64)
+        ptrs = [(C.c_void_p * 4)(*[ptr(a) if a is not None else None for a in arrs[f]]) for f in range(3)]
+        self._ck(self.lib.gpat_escaped_local_diagnostics(self.h, ptrs[0], ptrs[1], ptrs[2]),
+                 "gpat_escaped_local_diagnostics")
+        return [dict(x=arrs[0][k], y=arrs[1][k], z=arrs[2][k]) if P.local[k].enabled else None for k in range(4)]
+
     def escaped_diagnostics(self) -> np.ndarray:
         P = self.P
         out = np.zeros((2 * P.ndim, P.npp_global, P.nmu_global), dtype=np.float64)
@@ -360,6 +383,8 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
         d["steps"] = steps
         if dump_escaped_dist:
             d["fescaped"] = sim.escaped_diagnostics()
+            if local_dist:
+                d["fescaped_local"] = sim.escaped_local_diagnostics()
             sim.reset_escaped()                                # :533
         records.append(d)
         if on_interval is not None:

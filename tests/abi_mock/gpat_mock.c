@@ -40,6 +40,7 @@ void orc_hist_edges(const orc_sim* S, int which, double* pedges, double* muedges
 void orc_diagnostics(const orc_sim* S, int local_dist, double* fglobal, double* const flocal[4], double quick[8],
                      double* pmax_out);
 void orc_escaped_diagnostics(const orc_sim* S, double* fescaped);
+void orc_escaped_local_diagnostics(const orc_sim* S, double* const fx[4], double* const fy[4], double* const fz[4]);
 int64_t orc_get_particles(const orc_sim* S, gpat_particle* out, int64_t nmax);
 void orc_set_particles(orc_sim* S, const gpat_particle* in, int64_t n);
 int64_t orc_get_escaped(const orc_sim* S, gpat_particle* out, int64_t nmax);
@@ -165,6 +166,11 @@ int gpat_diagnostics(gpat_handle h, int local_dist, double* fglobal, double* con
     return GPAT_OK;
 }
 int gpat_escaped_diagnostics(gpat_handle h, double* fescaped) { orc_escaped_diagnostics(SIM(h), fescaped); return GPAT_OK; }
+int gpat_escaped_local_diagnostics(gpat_handle h, double* const fx[4], double* const fy[4], double* const fz[4])
+{
+    orc_escaped_local_diagnostics(SIM(h), fx, fy, fz);
+    return GPAT_OK;
+}
 int gpat_hist_edges(gpat_handle h, int which, double* pedges, double* muedges)
 {
     orc_hist_edges(SIM(h), which, pedges, muedges);

@@ -96,7 +96,7 @@ def test_basic_2d_run_with_split_and_local_spectra(driver, tmp_path):
 
 def test_fine_steps_part_box_and_power_law(driver, tmp_path):
     w, P, frames, d, out, base = _setup(tmp_path, "c3", 48, 600, 3)
-    box = [P.xmin + 0.1 * P.lx, P.ymin, 0.0, P.xmin + 0.4 * P.lx, P.ymax, 0.0]
+    box = [P.xmin + 0.8 * P.lx, P.ymin, 0.0, P.xmax, P.ymax, 0.0]   # next to the open high-x boundary
     args = base + ["-nf", "3", "-ip", ".true.", "-xs", box[0], "-ys", box[1], "-zs", box[2], "-xe", box[3],
                    "-ye", box[4], "-ze", box[5], "-df", "2", "-in", ".false.", "-ded", ".true."]
     r = driver(args)
@@ -104,6 +104,20 @@ def test_fine_steps_part_box_and_power_law(driver, tmp_path):
                                particle_v0=w.particle_v0, **dict(KW, dist_flag=2), num_fine_steps=3, part_box=box,
                                inject_new_ptl=False, dump_escaped_dist=True)
     _same_run(r, out, rec, steps, 3)
+    # -ded: escaped_dists_NNNN (global) and escaped_dists_localK_NNNN (face arrays) of every interval
+    assert sum(d["fescaped"].sum() for d in rec[1:]) > 0
+    for d in rec[1:]:
+        raw = open(out / f"escaped_dists_{d['frame']:04d}.bin", "rb").read()
+        nmu, npp, nface = np.frombuffer(raw[:12], dtype=np.int32)
+        assert np.array_equal(np.frombuffer(raw[12:], dtype=np.float64).reshape(nface, npp, nmu), d["fescaped"])
+        for k, loc in enumerate(d["fescaped_local"]):
+            if loc is None:
+                assert not os.path.exists(out / f"escaped_dists_local{k + 1}_{d['frame']:04d}.bin")
+                continue
+            raw = open(out / f"escaped_dists_local{k + 1}_{d['frame']:04d}.bin", "rb").read()
+            body = np.frombuffer(raw[24:], dtype=np.float64)
+            want = np.concatenate([loc[f].ravel() for f in "xyz" if loc[f] is not None])
+            assert np.array_equal(body, want), (d["frame"], k)
 
 
 @pytest.mark.parametrize("switch,extra,mode,vmin,norm", [

@@ -1215,3 +1215,58 @@ def test_host_restart_files_continue_the_run_bit_identically(tmp_path):
     d = Oracle(P, 20000)
     rec, _ = run_intervals(d, frames, ts, quota_seconds=0.0, **kw)
     assert run_intervals.last_frame == 1 and [r["frame"] for r in rec] == [0, 1]
+
+
+@pytest.mark.parametrize("key,grid,conf", [("c2", 32, dict(dt_min_rel=1e-3)),
+                                           ("c5", 16, dict(pbcx=1, pbcy=1, pbcz=1, dt_min_rel=2e-3, r1=2, r2=4, r3=8))])
+def test_local_escaped_distributions_match_numpy_binning(key, grid, conf):
+    """calc_escaped_distributions, local part (diagnostics.f90:956-1170): every escapee lands in the array of
+    the face it left through, binned in that face's two coordinates with the set's own p and mu bins (top
+    momentum bin never filled)."""
+    w, P, frames, ts = make_case(key, grid=grid, nptl=3000, conf=conf)
+    o = Oracle(P, w.nptl_max)
+    o.upload_fields(0, frames[0])
+    o.upload_fields(1, frames[1])
+    o.inject_uniform(3000, 0.0, 2, w.particle_v0, 0.0, w.dt_out, box_of(P), w.power_index)
+    o.particle_mover(0.0, w.dt_out, 100, 1, 1)
+    esc = o.download_escaped()
+    faces = set(int(f) for f in np.unique(esc["count_flag"]))
+    assert len(esc) > 30 and len(faces) >= (4 if P.ndim == 3 else 2)
+    got = o.escaped_local_diagnostics()
+    total = 0.0
+    for k in range(4):
+        s = P.local[k]
+        if not s.enabled:
+            assert got[k] is None
+            continue
+        nrz, nry, nrx, npb, nmu = o.local_shape(k)
+        ref = {"x": np.zeros((2, nrz, nry, npb, nmu)), "y": np.zeros((2, nrz, nrx, npb, nmu)),
+               "z": np.zeros((2, nry, nrx, npb, nmu))}
+        dpl = (np.log10(s.pmax) - np.log10(s.pmin)) / s.npbins
+        dmu = float(np.float32(2.0) / np.float32(s.nmu))
+        for r in esc:
+            ix = int(np.floor((r["x"] - P.xmin) / (P.lx / nrx)))
+            iy = int(np.floor((r["y"] - P.ymin) / (P.ly / nry)))
+            iz = int(np.floor((r["z"] - P.zmin) / (P.lz / nrz)))
+            ip = int(np.floor((np.log10(r["p"]) - np.log10(s.pmin)) / dpl))        # 0-based
+            imu = int(np.floor((r["mu"] + 1.0) / dmu))
+            if not (0 <= ip < npb - 1 and 0 <= imu < nmu):
+                continue
+            cx, cy, cz = 0 <= ix < nrx, 0 <= iy < nry, 0 <= iz < nrz
+            face = -int(r["count_flag"])
+            side = (face - 1) % 2
+            if face <= 2 and cy and cz:
+                ref["x"][side, iz, iy, ip, imu] += r["weight"]
+            elif face in (3, 4) and cx and cz:
+                ref["y"][side, iz, ix, ip, imu] += r["weight"]
+            elif face >= 5 and cx and cy:
+                ref["z"][side, iy, ix, ip, imu] += r["weight"]
+        assert np.array_equal(got[k]["x"], ref["x"]), k
+        assert np.array_equal(got[k]["y"], ref["y"]), k
+        if P.ndim == 3:
+            assert np.array_equal(got[k]["z"], ref["z"]), k
+            total += got[k]["z"].sum()
+        else:
+            assert got[k]["z"] is None
+        total += got[k]["x"].sum() + got[k]["y"].sum()
+    assert total > 0.0

@@ -344,6 +344,51 @@ def test_split_and_remove_exact():
     g.close()
 
 
+@pytest.mark.parametrize("key,grid,conf", [("c2", 64, {}), ("c3", 64, {}),
+                                           ("c5", 32, dict(pbcx=1, pbcy=1, pbcz=1))])
+def test_local_escaped_distributions_bit_exact(key, grid, conf):
+    """calc_escaped_distributions, local part (diagnostics.f90:956-1170) on the SAME escaped set: the face
+    arrays of every enabled local set equal the oracle's bit for bit; an empty escaped list gives zeros."""
+    w, P, frames, ts = make_case(key, grid=grid, nptl=4000, conf=conf)
+    g, o = pair(P, w.nptl_max, 1)
+    load_fields((g, o), frames, P.time_interp)
+    empty = g.escaped_local_diagnostics()
+    assert all(e is None or all(v is None or not v.any() for v in e.values()) for e in empty)
+    _inject((g, o), w, P, 4000, dist_flag=2)
+    o.particle_mover(0.0, w.dt_out, 100, 1, 1)
+    esc = o.download_escaped()
+    assert len(esc) > 20
+    # same escaped particles on both sides: push on the oracle, then hand the GPU the pre-push population
+    # and let it produce its own escapees; compare through the particles that both sides lost
+    g.particle_mover(0.0, w.dt_out, 100, 1, 1)
+    ge = g.download_escaped()
+    assert abs(len(ge) - len(esc)) <= 2
+    a, b = g.escaped_local_diagnostics(), o.escaped_local_diagnostics()
+    if len(ge) == len(esc) and np.array_equal(sort_by_key(ge)["count_flag"], sort_by_key(esc)["count_flag"]):
+        for k in range(4):
+            assert (a[k] is None) == (b[k] is None)
+            if a[k] is None:
+                continue
+            for f in "xyz":
+                assert (a[k][f] is None) == (b[k][f] is None)
+                if a[k][f] is not None:
+                    # positions agree to 1e-9 after an interval: a bin-edge case may move one count
+                    assert np.abs(a[k][f] - b[k][f]).sum() <= 2.0, (k, f)
+                    assert a[k][f].sum() == b[k][f].sum()
+    # and the binning itself, bit for bit, on the GPU's own escapees re-binned by the oracle's routine
+    o2 = Oracle(P, w.nptl_max)
+    o2.upload_particles(np.zeros(0, dtype=PARTICLE_DTYPE))
+    o2.lib.orc_set_escaped(o2.h, ge.ctypes.data_as(__import__("ctypes").c_void_p), __import__("ctypes").c_int64(len(ge)))
+    c = o2.escaped_local_diagnostics()
+    for k in range(4):
+        if a[k] is None:
+            continue
+        for f in "xyz":
+            if a[k][f] is not None:
+                assert np.array_equal(a[k][f], c[k][f]), (k, f)
+    g.close()
+
+
 def test_edge_cases():
     """Empty population, zero-particle injection, mover before fields, bad parameters."""
     from stochastic_parker_b200 import GpatError
