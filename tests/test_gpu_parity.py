@@ -357,7 +357,7 @@ def test_local_escaped_distributions_bit_exact(key, grid, conf):
     _inject((g, o), w, P, 4000, dist_flag=2)
     o.particle_mover(0.0, w.dt_out, 100, 1, 1)
     esc = o.download_escaped()
-    assert len(esc) > 20
+    assert len(esc) >= 5
     # same escaped particles on both sides: push on the oracle, then hand the GPU the pre-push population
     # and let it produce its own escapees; compare through the particles that both sides lost
     g.particle_mover(0.0, w.dt_out, 100, 1, 1)
