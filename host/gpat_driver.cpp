@@ -214,7 +214,7 @@ int main(int argc, char** argv)
         return 2;
     }
     // features outside the GPU path must stay off; the library re-checks the ones it is told about
-    for (const char* k : {"-vdt"})
+    for (const char* k : {"-sc"})
         if (cli.b(k)) {
             std::fprintf(stderr, "gpat_driver: switch %s is outside the GPU particle path\n", k);
             return 2;
@@ -331,7 +331,24 @@ int main(int argc, char** argv)
     const size_t ncell = (size_t)(mc.nx + 4) * (P.ndim >= 2 ? mc.ny + 4 : 1) * (P.ndim == 3 ? mc.nz + 4 : 1);
     std::vector<float> frame;
     // calc_tstamps_mhd (mhd_config.f90:263-271): uniform output interval
-    auto tstamp = [&](int i) { return i * mc.dt_out; };
+    // or, with -vdt .true., load_tstamps_mhd (mhd_config.f90:221-254): time_stamps.dat = the first and last frame of
+    // the MHD run in two 8-byte slots (the first is read as a default integer), then one f64 per frame; frames past
+    // tmax_mhd continue with the last interval
+    std::vector<double> stamps((size_t)(t_end - t_start + 1));
+    for (int i = t_start; i <= t_end; ++i) stamps[(size_t)(i - t_start)] = i * mc.dt_out;
+    if (cli.b("-vdt")) {
+        FILE* f = std::fopen((dir_mhd + "time_stamps.dat").c_str(), "rb");
+        int32_t ts_mhd = 0;
+        if (!f || std::fread(&ts_mhd, sizeof(ts_mhd), 1, f) != 1) return die(h, "read time_stamps.dat", -1);
+        const long long tm = cli.i("-tm");
+        const long long nread = std::min<long long>(tm, t_end) - t_start + 1;
+        if (nread < 2 || std::fseek(f, (long)(t_start - ts_mhd + 2) * 8, SEEK_SET) != 0 ||
+            std::fread(stamps.data(), sizeof(double), (size_t)nread, f) != (size_t)nread)
+            return die(h, "read time_stamps.dat", -1);
+        std::fclose(f);
+        for (long long i = nread; i <= t_end - t_start; ++i) stamps[(size_t)i] = stamps[(size_t)i - 1] + (stamps[(size_t)nread - 1] - stamps[(size_t)nread - 2]);
+    }
+    auto tstamp = [&](int i) { return stamps[(size_t)(i - t_start)]; };
     double part_box[6] = {P.xmin, P.ymin, P.zmin, P.xmax, P.ymax, P.zmax};  // stochastic-mhd.f90:375-391
     if (cli.b("-ip")) {
         part_box[0] = cli.d("-xs"); part_box[1] = cli.d("-ys"); part_box[2] = cli.d("-zs");
@@ -534,6 +551,7 @@ int main(int argc, char** argv)
     auto wall0 = std::chrono::steady_clock::now();
     auto step1 = wall0;
     bool reached_quota = false;
+    int last_read = tmin;
     int tf = tmin + 1;
     for (; tf <= t_end; ++tf) {
         std::printf(" Starting step %d\n", tf);
@@ -542,6 +560,14 @@ int main(int argc, char** argv)
             CK(gpat_upload_fields(h, P.time_interp ? 1 : 0, frame.data(), 8, 0), "gpat_upload_fields");
             CK(upload_surfaces(tf, P.time_interp ? 1 : 0), "gpat_upload_acc_surface");
             CK(upload_maps(tf, P.time_interp ? 1 : 0), "gpat_upload_turbulence");
+            last_read = tf;
+        } else if (P.time_interp && tf > tmin + 1) {
+            // no new frame (tf > tmax_mhd): the reference's farray2 still holds the last frame it read, and
+            // copy_fields made farray1 equal to it.  gpat_swap_fields exchanges the two device halves instead of
+            // copying, so the last frame is sent to slot 1 again.
+            CK(gpat_upload_fields(h, 1, frame.data(), 8, 0), "gpat_upload_fields");
+            CK(upload_surfaces(last_read, 1), "gpat_upload_acc_surface");
+            CK(upload_maps(last_read, 1), "gpat_upload_turbulence");
         }
         const double t0 = tstamp(tf - 1), dtf = tstamp(tf) - tstamp(tf - 1);  // tstamps_mhd(tf - t_start), particle_module.f90:1868
         if (cli.b("-is")) {  // :451-454: locate_shock_xpos + inject_particles_at_shock, every frame

@@ -308,7 +308,7 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
                   split_ratio=2.0, pmin_split=2.0, nsteps_interval=100, num_fine_steps=1,
                   local_dist=True, dump_escaped_dist=False, dt_inject=0.0, on_interval=None,
                   inject_mode=0, inject_same_nptl=True, inject_min=0.0, ncells_norm=1,
-                  track_tags=None, on_tracked=None, surfaces=None, tmin=0, quota_seconds=None):
+                  track_tags=None, on_tracked=None, surfaces=None, tmin=0, quota_seconds=None, tmax_mhd=1 << 30):
     """solve_transport_equation (stochastic-mhd.f90:312-567) for one rank.
 
     `sim` is a GpatSim (or the test oracle, which has the same methods); `frames` is a
@@ -319,7 +319,9 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
     (the content of <surface_filenameK>_NNNN.dat).  `tmin` > 0 continues a run restored with
     read_restart() (frames are still indexed from the run's t_start = 0); `quota_seconds` ends the loop after
     the first interval that finishes beyond it (reached_quota, :558-565).  The frame the loop stopped at is
-    left in run_intervals.last_frame for dump_restart().
+    left in run_intervals.last_frame for dump_restart().  Past `tmax_mhd` no new frame is read (:400): the
+    last one is sent to slot 1 again, because swap_fields exchanges the two device halves where the
+    reference's copy_fields leaves farray2 in place.
     """
     get = frames if callable(frames) else (lambda i: frames[i])
     P = sim.P
@@ -343,9 +345,16 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
     for tf in range(tmin + 1, nframes):                        # :397
         # read_field_data_parallel(..., var_flag=time_interp_flag): without time interpolation
         # the new frame REPLACES farray1 (:404-406, :426)
-        sim.upload_fields(1 if P.time_interp else 0, get(tf))
-        for k in range(nsurf):                                 # :405-416 read_acc_surface(time_interp_flag, ...)
-            sim.upload_acc_surface(k, 1 if P.time_interp else 0, surfaces(k, tf))
+        if tf <= tmax_mhd or not P.time_interp:
+            fr = min(tf, tmax_mhd)
+        elif tf > tmin + 1:
+            fr = tmax_mhd
+        else:
+            fr = None
+        if fr is not None:
+            sim.upload_fields(1 if P.time_interp else 0, get(fr))
+            for k in range(nsurf):                             # :405-416 read_acc_surface(time_interp_flag, ...)
+                sim.upload_acc_surface(k, 1 if P.time_interp else 0, surfaces(k, fr))
         t0, dtf = tstamps[tf - 1], tstamps[tf] - tstamps[tf - 1]
         if (tf == 1 or inject_new_ptl) and tf <= tmax_to_inject:   # :462-485
             if inject_mode == 6:                               # :451-454 inject_at_shock

@@ -328,3 +328,27 @@ def make_acc_surface(P, which: int, frame: int) -> np.ndarray:
     mid = 0.5 + (0.2 if which else 0.0) * (1 if norm < 0 else -1)
     h = mid + 0.12 * np.sin(2 * np.pi * (U + 0.07 * frame)) * np.cos(2 * np.pi * V + 0.3 * which) + 0.01 * frame
     return np.ascontiguousarray(lo[axis] + ext[axis] * h, dtype=np.float64)
+
+
+def write_time_stamps(directory: str, ts_mhd: int, te_mhd: int, stamps) -> None:
+    """time_stamps.dat as load_tstamps_mhd reads it (mhd_config.f90:221-254): the first and last frame of the
+    MHD run in two 8-byte slots, then one float64 time per frame ts_mhd .. te_mhd."""
+    with open(os.path.join(directory, "time_stamps.dat"), "wb") as f:
+        np.array([ts_mhd, te_mhd], dtype=np.int64).tofile(f)
+        np.asarray(stamps, dtype=np.float64).tofile(f)
+
+
+def read_time_stamps(directory: str, t_start: int, t_end: int, tmax_mhd: int) -> np.ndarray:
+    """tstamps_mhd(1 : t_end - t_start + 1) with -vdt .true.; frames past tmax_mhd repeat the last interval."""
+    with open(os.path.join(directory, "time_stamps.dat"), "rb") as f:
+        ts_mhd = int(np.fromfile(f, dtype=np.int32, count=1)[0])   # a default integer read at pos = 1
+        f.seek((t_start - ts_mhd + 2) * 8)
+        nread = min(tmax_mhd, t_end) - t_start + 1
+        head = np.fromfile(f, dtype=np.float64, count=nread)
+    if len(head) != nread or nread < 2:
+        raise IOError("time_stamps.dat is too short")
+    out = np.empty(t_end - t_start + 1)
+    out[:nread] = head
+    for i in range(nread, len(out)):
+        out[i] = out[i - 1] + (head[-1] - head[-2])
+    return out

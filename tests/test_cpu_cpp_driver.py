@@ -235,7 +235,8 @@ def test_tracking_run(driver, tmp_path):
 def test_bad_switches_stop_the_driver(driver, tmp_path):
     w, P, frames, d, out, base = _setup(tmp_path, "c1", 32, 50, 2)
     assert driver(base + ["-nosuch", "1"], expect_ok=False).returncode == 2
-    assert driver(base + ["-vdt", ".true."], expect_ok=False).returncode == 2
+    assert driver(base + ["-sc", "1"], expect_ok=False).returncode == 2
+    assert driver(base + ["-vdt", ".true."], expect_ok=False).returncode != 0     # no time_stamps.dat
     assert driver(base + ["-rf", ".true."], expect_ok=False).returncode != 0      # no restart/ files to read
     assert driver(base[:4] + ["-dm", str(tmp_path / "nowhere") + "/"] + base[6:], expect_ok=False).returncode == 2
 
@@ -281,3 +282,21 @@ def test_restart_files_and_restart_flag(driver, tmp_path):
     dump_restart(o, str(tmp_path / "py") + "/", 4, 4)
     assert open(tmp_path / "py" / "restart" / "particle_module_state_0004.bin", "rb").read() == \
         open(rdir / "particle_module_state_0004.bin", "rb").read()
+
+
+def test_varying_frame_interval(driver, tmp_path):
+    """-vdt .true.: load_tstamps_mhd (mhd_config.f90:221-254) -- frame times from time_stamps.dat, frames past
+    -tm continue with the last interval."""
+    w, P, frames, d, out, base = _setup(tmp_path, "c1", 48, 500, 5)
+    stamps = np.array([0.0, 0.07, 0.19, 0.26, 0.40])
+    mhd.write_time_stamps(str(d), 0, 3, stamps[:4])                 # the MHD run has frames 0..3 only
+    r = driver(base + ["-vdt", ".true.", "-tm", "3", "-st", "0"], expect_ok=False)
+    # frame 4 does not exist as a file: with -tm 3 the driver must not try to read it
+    ts = mhd.read_time_stamps(str(d), 0, 4, 3)
+    assert np.allclose(ts, [0.0, 0.07, 0.19, 0.26, 0.33]) and ts[4] - ts[3] == ts[3] - ts[2]
+    os.remove(d / "mhd_data_0004")
+    r = driver(base + ["-vdt", ".true.", "-tm", "3"])
+
+    rec, steps = run_intervals(Oracle(P, 12 * 500), frames[:4], list(ts), nptl=500, particle_v0=w.particle_v0, **KW,
+                               tmax_mhd=3)
+    _same_run(r, out, rec, steps, 5)

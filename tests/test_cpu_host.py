@@ -233,7 +233,7 @@ def test_cpp_driver_accepts_the_reference_command_line(tmp_path):
             "-dp2", "13575468.975", "-ch", "-1", "-ug", "1", "-cd", "0"]
     r = subprocess.run(args + ["--no_such_switch", "1"], capture_output=True, text=True)
     assert r.returncode == 2 and "unknown switch" in r.stderr
-    r = subprocess.run(args[:-2] + ["-vdt", ".true."], capture_output=True, text=True)  # variable dt_mhd: tstamps file
+    r = subprocess.run(args + ["-sc", "1"], capture_output=True, text=True)  # spherical coordinates
     assert r.returncode == 2 and "outside the GPU particle path" in r.stderr
     if not _has_gpu():
         r = subprocess.run(args, capture_output=True, text=True)
