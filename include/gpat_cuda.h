@@ -205,7 +205,12 @@ int gpat_upload_acc_surface(gpat_handle h, int which, int slot, const double* he
  * gpat_upload_fields copies synchronously as before. */
 int gpat_prefetch_fields(gpat_handle h, const float* f, int nvar);
 
-/* Replaces copy_fields (mhd_data_parallel.f90:1920): farray1 = farray2. O(1). */
+/* Replaces copy_fields (mhd_data_parallel.f90:1920): farray1 = farray2.  O(1): the two halves of the
+ * device store change roles, nothing is copied.  Slot 1 therefore holds the OLD slot 0 afterwards, not a
+ * second copy of the new slot 0 as in the reference; a caller that reads no new frame before the next
+ * gpat_particle_mover (tf > tmax_mhd, stochastic-mhd.f90:400) sends the last frame to slot 1 again
+ * (both host drivers of this repository do).  The same holds for the turbulence maps and the
+ * acceleration surfaces, which swap with the fields. */
 int gpat_swap_fields(gpat_handle h);
 
 /* ---- particles --------------------------------------------------------- */
