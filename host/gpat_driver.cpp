@@ -421,6 +421,32 @@ int main(int argc, char** argv)
         return 0;
     };
 
+    // dump_particles (-pd 1, diagnostics.f90:1811-1888) and dump_escaped_particles (-de .true. with -ded,
+    // :1896-1978): int64 count + gpat_particle records, the format of the restart files
+    auto write_particles = [&](const std::string& path, bool escaped) -> int {
+        gpat_counters cc{};
+        int rc = gpat_get_counters(h, &cc);
+        if (rc) return rc;
+        const int64_t cap = escaped ? cc.nptl_escaped : cc.nptl_current;
+        std::vector<gpat_particle> buf((size_t)std::max<int64_t>(cap, 1));
+        int64_t n = 0;
+        rc = escaped ? gpat_download_escaped(h, buf.data(), cap, &n) : gpat_download_particles(h, buf.data(), cap, &n);
+        if (rc) return rc;
+        n = std::min(n, cap);
+        FILE* f = std::fopen(path.c_str(), "wb");
+        if (!f) return -1;
+        std::fwrite(&n, sizeof(n), 1, f);
+        std::fwrite(buf.data(), sizeof(gpat_particle), (size_t)n, f);
+        std::fclose(f);
+        return 0;
+    };
+    const bool particle_data_dump = cli.i("-pd") == 1, dump_escaped = cli.b("-de");
+    auto frame_name = [](const char* stem, int iframe) {
+        char name[64];
+        std::snprintf(name, sizeof(name), "%s_%04d.bin", stem, iframe);
+        return std::string(name);
+    };
+
     // escaped_dists_NNNN: calc_escaped_distributions + save_global/local_escaped_distributions
     // (diagnostics.f90:913-1232, 1331-1372, 1536-1642) as raw records:
     //   escaped_dists_NNNN.bin         int32 nmu, npp, nface; fescaped(nmu, npp, nface)
@@ -592,7 +618,10 @@ int main(int argc, char** argv)
                    "gpat_inject_uniform");
             }
         }
-        if (tf == t_start + 1 && !track) CK(diagnostics(t_start, true), "initial diagnostics");  // :488-494
+        if (tf == t_start + 1 && !track) {  // :488-494
+            CK(diagnostics(t_start, true), "initial diagnostics");
+            if (particle_data_dump) CK(write_particles(diag_dir + frame_name("particles", t_start), false), "dump_particles");
+        }
         uint64_t steps = 0;
         CK(gpat_particle_mover(h, t0, dtf, nsteps_interval, track ? 1 : num_fine_steps, dump_escaped_dist ? 1 : 0,
                                &steps),
@@ -604,8 +633,10 @@ int main(int argc, char** argv)
         if (!track) {  // :516-535
             CK(diagnostics(tf, false), "diagnostics");  // :518-521
             std::printf(" Finishing distribution diagnostics \n");
+            if (particle_data_dump) CK(write_particles(diag_dir + frame_name("particles", tf), false), "dump_particles");  // :525-527
             if (dump_escaped_dist) {  // :522-534: escaped spectra of this interval, then reset_escaped_particles
                 CK(escaped_diagnostics(tf), "escaped diagnostics");
+                if (dump_escaped) CK(write_particles(diag_dir + frame_name("escaped_particles", tf), true), "dump_escaped_particles");
                 CK(gpat_reset_escaped(h), "gpat_reset_escaped");
             }
         }

@@ -308,7 +308,8 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
                   split_ratio=2.0, pmin_split=2.0, nsteps_interval=100, num_fine_steps=1,
                   local_dist=True, dump_escaped_dist=False, dt_inject=0.0, on_interval=None,
                   inject_mode=0, inject_same_nptl=True, inject_min=0.0, ncells_norm=1,
-                  track_tags=None, on_tracked=None, surfaces=None, tmin=0, quota_seconds=None, tmax_mhd=1 << 30):
+                  track_tags=None, on_tracked=None, surfaces=None, tmin=0, quota_seconds=None, tmax_mhd=1 << 30,
+                  particle_data_dump=False, dump_escaped=False):
     """solve_transport_equation (stochastic-mhd.f90:312-567) for one rank.
 
     `sim` is a GpatSim (or the test oracle, which has the same methods); `frames` is a
@@ -321,7 +322,9 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
     the first interval that finishes beyond it (reached_quota, :558-565).  The frame the loop stopped at is
     left in run_intervals.last_frame for dump_restart().  Past `tmax_mhd` no new frame is read (:400): the
     last one is sent to slot 1 again, because swap_fields exchanges the two device halves where the
-    reference's copy_fields leaves farray2 in place.
+    reference's copy_fields leaves farray2 in place.  `particle_data_dump` / `dump_escaped` add the
+    population (dump_particles, :491, 525-527) and the interval's escapees (dump_escaped_particles, :529-531)
+    to every record as "particles" / "escaped_particles".
     """
     get = frames if callable(frames) else (lambda i: frames[i])
     P = sim.P
@@ -367,6 +370,8 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
         if tf == 1 and not track:                              # :488-494
             d0 = sim.diagnostics(local_dist)
             d0["frame"] = 0
+            if particle_data_dump:
+                d0["particles"] = sim.download_particles()
             records.append(d0)
         # a tracking run moves the particles with num_fine_steps = 1 (:497-503)
         steps = sim.particle_mover(t0, dtf, nsteps_interval, 1 if track else num_fine_steps,
@@ -390,7 +395,11 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
         d = sim.diagnostics(local_dist)                        # :518-521
         d["frame"] = tf
         d["steps"] = steps
+        if particle_data_dump:
+            d["particles"] = sim.download_particles()
         if dump_escaped_dist:
+            if dump_escaped:
+                d["escaped_particles"] = sim.download_escaped()
             d["fescaped"] = sim.escaped_diagnostics()
             if local_dist:
                 d["fescaped_local"] = sim.escaped_local_diagnostics()

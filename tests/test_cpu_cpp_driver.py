@@ -98,12 +98,25 @@ def test_fine_steps_part_box_and_power_law(driver, tmp_path):
     w, P, frames, d, out, base = _setup(tmp_path, "c3", 48, 600, 3)
     box = [P.xmin + 0.8 * P.lx, P.ymin, 0.0, P.xmax, P.ymax, 0.0]   # next to the open high-x boundary
     args = base + ["-nf", "3", "-ip", ".true.", "-xs", box[0], "-ys", box[1], "-zs", box[2], "-xe", box[3],
-                   "-ye", box[4], "-ze", box[5], "-df", "2", "-in", ".false.", "-ded", ".true."]
+                   "-ye", box[4], "-ze", box[5], "-df", "2", "-in", ".false.", "-ded", ".true.", "-pd", "1",
+                   "-de", ".true."]
     r = driver(args)
     rec, steps = run_intervals(Oracle(P, 12 * 600), frames, [f * w.dt_out for f in range(3)], nptl=600,
                                particle_v0=w.particle_v0, **dict(KW, dist_flag=2), num_fine_steps=3, part_box=box,
-                               inject_new_ptl=False, dump_escaped_dist=True)
+                               inject_new_ptl=False, dump_escaped_dist=True, particle_data_dump=True, dump_escaped=True)
     _same_run(r, out, rec, steps, 3)
+    # -pd 1 / -de .true.: particles_NNNN and escaped_particles_NNNN hold the same records, in the same order
+    for d in rec:
+        for stem, key in (("particles", "particles"), ("escaped_particles", "escaped_particles")):
+            if key not in d:
+                assert not os.path.exists(out / f"{stem}_{d['frame']:04d}.bin")
+                continue
+            raw = open(out / f"{stem}_{d['frame']:04d}.bin", "rb").read()
+            assert np.frombuffer(raw[:8], dtype=np.int64)[0] == len(d[key])
+            got = np.frombuffer(raw[8:], dtype=PARTICLE_DTYPE)
+            for name in PARTICLE_DTYPE.names:
+                assert np.array_equal(got[name], d[key][name]), (stem, d["frame"], name)
+    assert sum(len(d.get("escaped_particles", ())) for d in rec) > 0
     # -ded: escaped_dists_NNNN (global) and escaped_dists_localK_NNNN (face arrays) of every interval
     assert sum(d["fescaped"].sum() for d in rec[1:]) > 0
     for d in rec[1:]:
