@@ -443,15 +443,11 @@ def dump_restart(sim, diagnostics_directory: str, t_end: int, tf: int) -> None:
 def read_restart(sim, diagnostics_directory: str) -> int:
     """restart_flag (stochastic-mhd.f90:224-236): tmin from latest_restart, then read_particles(tmin) and
     read_particle_module_state(tmin).  Returns tmin for run_intervals(..., tmin=tmin)."""
+    from . import outputs
     d = os.path.join(diagnostics_directory, "restart")
     tmin = int(np.fromfile(os.path.join(d, "latest_restart"), dtype=np.int32)[0])
-    with open(os.path.join(d, f"particles_{tmin:04d}.bin"), "rb") as f:
-        n = int(np.fromfile(f, dtype=np.int64, count=1)[0])
-        ptl = np.fromfile(f, dtype=PARTICLE_DTYPE, count=n)
-    if len(ptl) != n:
-        raise IOError(f"particles_{tmin:04d}.bin is truncated")
-    raw = open(os.path.join(d, f"particle_module_state_{tmin:04d}.bin"), "rb").read()
-    c = Counters.from_buffer_copy(raw)
+    ptl = outputs.read_particles(os.path.join(d, f"particles_{tmin:04d}.bin"))
+    c = outputs.read_module_state(os.path.join(d, f"particle_module_state_{tmin:04d}.bin"))
     sim.upload_particles(ptl)
     sim.set_counters(c)
     return tmin

@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 
 from oracle.oracle import Oracle
-from stochastic_parker_b200 import WORKLOADS, config, mhd, run_intervals
+from stochastic_parker_b200 import WORKLOADS, config, mhd, outputs, run_intervals
 from stochastic_parker_b200.abi import PARTICLE_DTYPE
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -64,9 +64,7 @@ def _setup(tmp_path, key, grid, nptl, nfr, conf=None, cli=None):
 
 
 def _spectra(out, frame):
-    raw = open(out / f"fdists_{frame:04d}.bin", "rb").read()
-    nmu, npp = np.frombuffer(raw[:8], dtype=np.int32)
-    return np.frombuffer(raw[8:8 + 8 * nmu * npp], dtype=np.float64).reshape(npp, nmu)
+    return outputs.read_fdists(str(out), frame)["fglobal"]
 
 
 def _same_run(r, out, rec, steps, nfr, local=True):
@@ -74,13 +72,13 @@ def _same_run(r, out, rec, steps, nfr, local=True):
     for d in rec:
         assert np.array_equal(_spectra(out, d["frame"]), d["fglobal"]), d["frame"]
         if local and d["flocal"][1] is not None:
-            loc = open(out / f"fdists_local2_{d['frame']:04d}.bin", "rb").read()
-            shp = np.frombuffer(loc[:20], dtype=np.int32)
-            assert np.array_equal(np.frombuffer(loc[20:], dtype=np.float64).reshape(tuple(shp[::-1])), d["flocal"][1])
-    rows = open(out / "quick.dat").read().splitlines()
-    assert rows[0].split()[:3] == ["iframe", "nptl_current", "nptl_split"] and len(rows) == 1 + nfr
-    assert rows[-1][:6] == f"{nfr - 1:06d}" and float(rows[-1][6:19]) == float(f"{rec[-1]['quick'][0]:.6E}")
-    assert len(open(out / "pmax_global.dat").read().split()) == nfr
+            assert np.array_equal(outputs.read_fdists_local(str(out), 2, d["frame"]), d["flocal"][1])
+    q = outputs.read_quick(str(out))
+    assert list(q)[:3] == ["iframe", "nptl_current", "nptl_split"] and list(q["iframe"]) == list(range(nfr))
+    assert q["nptl_current"][-1] == float(f"{rec[-1]['quick'][0]:.5E}")
+    assert q["ntot"][-1] == float(f"{rec[-1]['quick'][2]:.5E}") and q["pdt_max"][-1] == float(f"{rec[-1]['quick'][7]:.5E}")
+    pm = outputs.read_pmax_global(str(out))
+    assert len(pm) == nfr and pm[-1] == float(f"{rec[-1]['pmax']:.5E}")
 
 
 KW = dict(dist_flag=1, power_index=6.2, split_ratio=1.05, pmin_split=1.05)
@@ -105,6 +103,31 @@ def test_fine_steps_part_box_and_power_law(driver, tmp_path):
                                particle_v0=w.particle_v0, **dict(KW, dist_flag=2), num_fine_steps=3, part_box=box,
                                inject_new_ptl=False, dump_escaped_dist=True, particle_data_dump=True, dump_escaped=True)
     _same_run(r, out, rec, steps, 3)
+    # -pd 1 / -de .true.: particles_NNNN and escaped_particles_NNNN hold the same records, in the same order
+    for d in rec:
+        for stem, key in (("particles", "particles"), ("escaped_particles", "escaped_particles")):
+            if key not in d:
+                assert not os.path.exists(out / f"{stem}_{d['frame']:04d}.bin")
+                continue
+            raw = open(out / f"{stem}_{d['frame']:04d}.bin", "rb").read()
+            assert np.frombuffer(raw[:8], dtype=np.int64)[0] == len(d[key])
+            got = np.frombuffer(raw[8:], dtype=PARTICLE_DTYPE)
+            for name in PARTICLE_DTYPE.names:
+                assert np.array_equal(got[name], d[key][name]), (stem, d["frame"], name)
+    assert sum(len(d.get("escaped_particles", ())) for d in rec) > 0
+    # -ded: escaped_dists_NNNN (global) and escaped_dists_localK_NNNN (face arrays) of every interval
+    assert sum(d["fescaped"].sum() for d in rec[1:]) > 0
+    for d in rec[1:]:
+        assert np.array_equal(outputs.read_escaped_dists(str(out), d["frame"]), d["fescaped"])
+        for k, loc in enumerate(d["fescaped_local"]):
+            if loc is None:
+                assert not os.path.exists(out / f"escaped_dists_local{k + 1}_{d['frame']:04d}.bin")
+                continue
+            got = outputs.read_escaped_dists_local(str(out), k + 1, d["frame"])
+            for f in "xyz":
+                assert (got[f] is None) == (loc[f] is None)
+                if loc[f] is not None:
+                    assert np.array_equal(got[f], loc[f]), (d["frame"], k, f)
     # -pd 1 / -de .true.: particles_NNNN and escaped_particles_NNNN hold the same records, in the same order
     for d in rec:
         for stem, key in (("particles", "particles"), ("escaped_particles", "escaped_particles")):
