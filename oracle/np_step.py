@@ -443,6 +443,15 @@ def push_2d_general(P, F, p, mu, dt_min, dt_max, u, x, y, t, qdrift, aux=None, d
     xn, yn = x + ddx, y + ddy
     if deltas is not None:
         deltas["x"], deltas["y"] = ddx, ddy
+    if deltas is not None:
+        # check_drift_2d (particle_module.f90:3448-3460, 3582-3586): the out-of-plane drift moves ptl%z inside the
+        # pusher; the mover's own deltaz stays 0 in 2-D, so a roll-back does not undo it
+        if P.check_drift_2d:
+            dbx_dy, dby_dx = F[:, nf + 13], F[:, nf + 15]
+            vdz = vdp * ((dby_dx - dbx_dy) * ib2 - 2 * (by * db_dx - bx * db_dy) * ib3)
+        else:
+            vdz = np.zeros_like(vdp)
+        deltas["z_in_pusher"] = vdz * dt
     inside = _acc_region(P, xn, yn, None, 2) if P.acc_region_flag == 1 else None
     return xn, yn, _finish_momentum(P, p, dp_dt, dpp, dt, sdt, ranp, inside, deltas), t + dt, dt
 

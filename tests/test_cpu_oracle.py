@@ -999,6 +999,7 @@ def _python_interval(P, w, frames, ptls, t0, dtf, nsteps_interval, num_fine_step
                                                      one(s["y"]), one(s["t"]), qdrift,
                                                      dt_fixed=one(s["dt"]) if fixed else None, deltas=d)
             s.update(x=float(x[0]), y=float(y[0]), p=float(p[0]), t=float(t[0]), dt=float(dt[0]), rng=s["rng"] + 1)
+            s["z"] = s["z"] + float(d["z_in_pusher"][0])   # moved inside push_particle_2d; the mover's deltaz stays 0
             return float(d["x"][0]), float(d["y"][0]), 0.0, float(d["p"][0])
 
         np_step.mover_one_particle(P, s, push, t0, dtf, nsteps_interval, num_fine_steps, tally)
@@ -1010,14 +1011,15 @@ def _python_interval(P, w, frames, ptls, t0, dtf, nsteps_interval, num_fine_step
     return out, tally
 
 
-@pytest.mark.parametrize("key,conf,nfine", [("c1", dict(dt_min_rel=2e-3), 1), ("c1", dict(dt_min_rel=2e-3), 3),
-                                            ("c3", dict(dt_min_rel=2e-3), 2),
-                                            ("c4", dict(dt_min_rel=4e-3), 2)])
-def test_mover_interval_matches_python_restatement(key, conf, nfine):
+@pytest.mark.parametrize("key,conf,nfine,cli", [("c1", dict(dt_min_rel=2e-3), 1, None), ("c1", dict(dt_min_rel=2e-3), 3, None),
+                                                ("c3", dict(dt_min_rel=2e-3), 2, None),
+                                                ("c4", dict(dt_min_rel=4e-3), 2, None),
+                                                ("c1", dict(dt_min_rel=2e-3), 2, dict(check_drift_2d=1))])
+def test_mover_interval_matches_python_restatement(key, conf, nfine, cli):
     """particle_mover_one_cycle + particle_mover: target times, roll-back and fixed-dt re-push, the BC test
     at the top of every step with the extended bounds, the final pass with the true ones, remove_particles."""
     n = 24
-    w, P, frames, _ = make_case(key, grid=48, nptl=n, conf=conf)
+    w, P, frames, _ = make_case(key, grid=48, nptl=n, conf=conf, cli=cli)
     o = Oracle(P, w.nptl_max)
     o.upload_fields(0, frames[0])
     o.upload_fields(1, frames[1])
@@ -1034,9 +1036,11 @@ def test_mover_interval_matches_python_restatement(key, conf, nfine):
     inbox = [r for r in ref if r["count_flag"] == np_step.INBOX]
     gone = [(t, r) for t, r in zip(tags, ref) if r["count_flag"] < 0]
     assert len(inbox) == len(after) and len(gone) == len(esc)
-    for name in ("x", "y", "p", "t", "dt"):
+    for name in ("x", "y", "z", "p", "t", "dt"):
         got, want = after[name], np.array([r[name] for r in inbox])
         assert np.abs(got - want).max() <= 1e-11 * max(1.0, np.abs(want).max()), name
+    if cli and cli.get("check_drift_2d"):
+        assert np.any(after["z"] != 0.0)            # the out-of-plane drift accumulated in z
     assert np.array_equal(after["nsteps_pushed"], np.array([r["nsteps_pushed"] for r in inbox]))
     assert np.array_equal(rng_steps(after), np.array([r["rng"] for r in inbox], dtype=np.uint64))
     assert np.all(after["t"] == w.dt_out)                       # every survivor ends ON the frame time
