@@ -456,7 +456,7 @@ def push_2d_general(P, F, p, mu, dt_min, dt_max, u, x, y, t, qdrift, aux=None, d
     return xn, yn, _finish_momentum(P, p, dp_dt, dpp, dt, sdt, ranp, inside, deltas), t + dt, dt
 
 
-def push_3d_like(P, F, p, mu, dt_min, dt_max, u, x, y, z, t, qdrift, full3d, aux=None):
+def push_3d_like(P, F, p, mu, dt_min, dt_max, u, x, y, z, t, qdrift, full3d, aux=None, dt_fixed=None, deltas=None):
     """push_particle_3d (full3d) or push_particle_2d_include_3rd, Cartesian uniform grid.
     Returns x, y, z, p, t, dt after the step."""
     nf = NFIELDS
@@ -508,15 +508,20 @@ def push_3d_like(P, F, p, mu, dt_min, dt_max, u, x, y, z, t, qdrift, full3d, aux
     dt = np.where(ok, cand, dt_min)
     dt = np.where(dt < dt_min, dt_min, dt)
     dt = np.where(dt > dt_max, dt_max, dt)
+    if dt_fixed is not None:
+        dt = dt_fixed
     sdt = np.sqrt(dt)
     sqrt3 = np.sqrt(3.0)
     ran1, ran2, ran3, ranp = [(2.0 * u[:, c] - 1.0) * sqrt3 for c in range(4)]
     skpa, skpe = k["skpara"], k["skperp"]
-    xn = x + (dx_dt * dt + (bxn * skpa * ran1 - bxn * bzn * skpe * ibxyn * ran2 - byn * skpe * ibxyn * ran3) * sdt)
-    yn = y + (dy_dt * dt + (byn * skpa * ran1 - byn * bzn * skpe * ibxyn * ran2 + bxn * skpe * ibxyn * ran3) * sdt)
-    zn = z + (dz_dt * dt + (bzn * skpa * ran1 + bxyn * skpe * ran2) * sdt)
+    ddx = dx_dt * dt + (bxn * skpa * ran1 - bxn * bzn * skpe * ibxyn * ran2 - byn * skpe * ibxyn * ran3) * sdt
+    ddy = dy_dt * dt + (byn * skpa * ran1 - byn * bzn * skpe * ibxyn * ran2 + bxn * skpe * ibxyn * ran3) * sdt
+    ddz = dz_dt * dt + (bzn * skpa * ran1 + bxyn * skpe * ran2) * sdt
+    xn, yn, zn = x + ddx, y + ddy, z + ddz
+    if deltas is not None:
+        deltas["x"], deltas["y"], deltas["z"] = ddx, ddy, ddz
     inside = _acc_region(P, xn, yn, zn, 3 if full3d else 2) if P.acc_region_flag == 1 else None
-    return xn, yn, zn, _finish_momentum(P, p, dp_dt, dpp, dt, sdt, ranp, inside), t + dt, dt
+    return xn, yn, zn, _finish_momentum(P, p, dp_dt, dpp, dt, sdt, ranp, inside, deltas), t + dt, dt
 
 
 # ------------------------------------------------------------------------------------------------

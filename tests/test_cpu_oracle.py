@@ -977,8 +977,13 @@ def test_2d_step_with_dpp_and_nlgc_matches_numpy_restatement(key, conf, cli, twe
 def _python_interval(P, w, frames, ptls, t0, dtf, nsteps_interval, num_fine_steps, keep_cycle_flags=False):
     """One MHD interval of every particle with np_step.mover_one_particle (2-D Parker), Philox uniforms
     keyed like the library's: counter (step_lo, step_hi, tag_injected, tag_splitted), key (seed, origin)."""
-    fa1 = np_step.gradients32(frames[0], P.dx, P.dy)
-    fa2 = np_step.gradients32(frames[1], P.dx, P.dy)
+    full3d = P.ndim == 3
+    if full3d:
+        fa1 = np_step.gradients32_3d(frames[0], P.dx, P.dy, P.dz)
+        fa2 = np_step.gradients32_3d(frames[1], P.dx, P.dy, P.dz)
+    else:
+        fa1 = np_step.gradients32(frames[0], P.dx, P.dy)
+        fa2 = np_step.gradients32(frames[1], P.dx, P.dy)
     qdrift = float(np.float32(1.0) / np.float32(3 * P.pcharge))
     dt_min, dt_max = P.dt_min_rel * dtf, P.dt_max_rel * dtf
     tally = dict(leak=0.0, leak_negp=0.0, steps=0)
@@ -991,10 +996,20 @@ def _python_interval(P, w, frames, ptls, t0, dtf, nsteps_interval, num_fine_step
         tags = (int(rec["tag_injected"]), int(rec["tag_splitted"]))
 
         def push(s, fixed):
-            F = np_step.interp32(fa1, fa2, P, one(s["x"]), one(s["y"]), one((s["t"] - t0) / dtf))
             blk = philox4x32_10((s["rng"] & 0xFFFFFFFF, s["rng"] >> 32) + tags, key)
             u = np.array([[b / 4294967295.0 for b in blk]])
             d = {}
+            if full3d or P.include_3rd_dim:   # push_particle_3d / push_particle_2d_include_3rd
+                rt = one((s["t"] - t0) / dtf)
+                F = (np_step.interp32_3d(fa1, fa2, P, one(s["x"]), one(s["y"]), one(s["z"]), rt) if full3d
+                     else np_step.interp32(fa1, fa2, P, one(s["x"]), one(s["y"]), rt))
+                x, y, z, p, t, dt = np_step.push_3d_like(P, F, one(s["p"]), one(s["mu"]), dt_min, dt_max, u, one(s["x"]),
+                                                         one(s["y"]), one(s["z"]), one(s["t"]), qdrift, full3d,
+                                                         dt_fixed=one(s["dt"]) if fixed else None, deltas=d)
+                s.update(x=float(x[0]), y=float(y[0]), z=float(z[0]), p=float(p[0]), t=float(t[0]), dt=float(dt[0]),
+                         rng=s["rng"] + 1)
+                return float(d["x"][0]), float(d["y"][0]), float(d["z"][0]), float(d["p"][0])
+            F = np_step.interp32(fa1, fa2, P, one(s["x"]), one(s["y"]), one((s["t"] - t0) / dtf))
             x, y, p, t, dt = np_step.push_2d_general(P, F, one(s["p"]), one(s["mu"]), dt_min, dt_max, u, one(s["x"]),
                                                      one(s["y"]), one(s["t"]), qdrift,
                                                      dt_fixed=one(s["dt"]) if fixed else None, deltas=d)
@@ -1014,12 +1029,16 @@ def _python_interval(P, w, frames, ptls, t0, dtf, nsteps_interval, num_fine_step
 @pytest.mark.parametrize("key,conf,nfine,cli", [("c1", dict(dt_min_rel=2e-3), 1, None), ("c1", dict(dt_min_rel=2e-3), 3, None),
                                                 ("c3", dict(dt_min_rel=2e-3), 2, None),
                                                 ("c4", dict(dt_min_rel=4e-3), 2, None),
-                                                ("c1", dict(dt_min_rel=2e-3), 2, dict(check_drift_2d=1))])
+                                                ("c1", dict(dt_min_rel=2e-3), 2, dict(check_drift_2d=1)),
+                                                ("c1", dict(dt_min_rel=2e-3), 2, dict(include_3rd_dim=1)),
+                                                ("c5", dict(dt_min_rel=4e-3, r1=4, r2=8, r3=12), 2, None),
+                                                ("c5", dict(dt_min_rel=4e-3, r1=4, r2=8, r3=12, pbcx=1, pbcy=1, pbcz=1), 1,
+                                                 None)])
 def test_mover_interval_matches_python_restatement(key, conf, nfine, cli):
     """particle_mover_one_cycle + particle_mover: target times, roll-back and fixed-dt re-push, the BC test
     at the top of every step with the extended bounds, the final pass with the true ones, remove_particles."""
     n = 24
-    w, P, frames, _ = make_case(key, grid=48, nptl=n, conf=conf, cli=cli)
+    w, P, frames, _ = make_case(key, grid=24 if key == "c5" else 48, nptl=n, conf=conf, cli=cli)
     o = Oracle(P, w.nptl_max)
     o.upload_fields(0, frames[0])
     o.upload_fields(1, frames[1])
@@ -1051,13 +1070,15 @@ def test_mover_interval_matches_python_restatement(key, conf, nfine, cli):
         assert len(gone) > 0, "the open-x case must lose particles"
 
 
-@pytest.mark.parametrize("key", ["c1", "c2"])
-def test_boundary_quirks_match_python_restatement(key):
+@pytest.mark.parametrize("key,extra", [("c1", {}), ("c2", {}), ("c5", {}), ("c5", dict(pbcx=1, pbcy=1, pbcz=1))])
+def test_boundary_quirks_match_python_restatement(key, extra):
     """Particles parked around the box edges: inside the half-cell margin they are left alone by the step
     loop (extended bounds) and wrapped by L / removed by the final pass; beyond it the loop wraps them by
     L + dx or lets them escape (c2: open boundaries)."""
     n = 16
-    w, P, frames, _ = make_case(key, grid=48, nptl=n, conf=dict(dt_min_rel=5e-3))
+    w, P, frames, _ = make_case(key, grid=24 if key == "c5" else 48, nptl=n,
+                                conf=dict(extra, dt_min_rel=5e-3, **(dict(r1=4, r2=8, r3=12) if key == "c5" else {})))
+    open_box = key == "c2" or bool(extra)
     o = Oracle(P, w.nptl_max)
     o.upload_fields(0, frames[0])
     o.upload_fields(1, frames[1])
@@ -1068,7 +1089,9 @@ def test_boundary_quirks_match_python_restatement(key):
     ptl["y"][4:8] = np.where(offs > 0, P.ymax + offs * P.dy, P.ymin + offs * P.dy)
     ptl["x"][8:10] = [P.xmax + 0.7 * P.dx, P.xmin - 0.2 * P.dx]      # both axes at once
     ptl["y"][8:10] = [P.ymin - 0.7 * P.dy, P.ymax + 0.2 * P.dy]
-    ptl["t"][:10] = 0.02                                             # a few steps each
+    if P.ndim == 3:
+        ptl["z"][10:14] = np.where(offs > 0, P.zmax + offs * P.dz, P.zmin + offs * P.dz)
+    ptl["t"][:14] = 0.02                                             # a few steps each
     o.upload_particles(ptl)
     steps = o.particle_mover(0.0, w.dt_out, 100, 1, 1)
     raw, raw_esc = o.download_particles(), o.download_escaped()
@@ -1084,13 +1107,15 @@ def test_boundary_quirks_match_python_restatement(key):
     inbox = [r for r in ref if r["count_flag"] == np_step.INBOX]
     gone = [r for r in ref if r["count_flag"] < 0]
     assert tally["steps"] == steps and len(inbox) == len(after) and len(gone) == len(esc)
-    for name in ("x", "y", "p", "t"):
+    for name in ("x", "y", "z", "p", "t"):
         want = np.array([r[name] for r in inbox])
         assert np.abs(after[name] - want).max() <= 1e-11 * max(1.0, np.abs(want).max()), name
     assert np.array_equal(esc["count_flag"], np.array([r["count_flag"] for r in gone], dtype=esc["count_flag"].dtype))
     assert o.counters().leak == tally["leak"]
-    if key == "c2":
+    if open_box:
         assert len(gone) >= 6          # everything parked outside the true box leaves through an open boundary
+        if P.ndim == 3:
+            assert {-5, -6} <= set(int(f) for f in esc["count_flag"])
     else:
         assert len(gone) == 0 and np.all((after["x"] >= P.xmin) & (after["x"] <= P.xmax))
 
