@@ -563,7 +563,7 @@ def _negp_or_bc(P, s, e, tally):
 
 def mover_one_particle(P, s, push, t0, dtf, nsteps_interval, num_fine_steps, tally):
     """particle_mover_one_cycle for one particle.  `push(s, fixed_dt)` performs one push_particle_* call
-    on the state dict (position, p, t, dt) and returns (deltax, deltay, deltaz, deltap)."""
+    on the state dict (position, p, t, dt) and returns (deltax, deltay, deltaz, deltap[, deltav, deltamu])."""
     dt_fine = dtf / num_fine_steps
     e = (P.xmin - P.dx * 0.5, P.xmax + P.dx * 0.5, P.ymin - P.dy * 0.5, P.ymax + P.dy * 0.5,
          P.zmin - P.dz * 0.5, P.zmax + P.dz * 0.5)
@@ -591,6 +591,8 @@ def mover_one_particle(P, s, push, t0, dtf, nsteps_interval, num_fine_steps, tal
             s["nsteps_pushed"] = (s["nsteps_pushed"] + 1) % nsteps_interval
         if (s["t"] - t0) > dt_target and s["count_flag"] == INBOX:
             s["x"], s["y"], s["z"], s["p"] = s["x"] - d[0], s["y"] - d[1], s["z"] - d[2], s["p"] - d[3]
+            if len(d) == 6:   # focused transport: deltav, deltamu (particle_module.f90:1712-1713)
+                s["v"], s["mu"] = s["v"] - d[4], s["mu"] - d[5]
             s["t"] = s["t"] - s["dt"]
             dt_old = s["dt"]
             s["dt"] = t0 + dt_target - s["t"]

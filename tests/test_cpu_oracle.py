@@ -484,7 +484,7 @@ def test_tracking_replays_and_records_the_selected_particles():
 
 
 # ---- focused transport, 2-D (calc_duu + push_particle_2d_ft, particle_module.f90:3116-3155, 3626-3977)
-def _np_step_2d_ft(P, F, ptl, u, dt_min, dt_max):
+def _np_step_2d_ft(P, F, ptl, u, dt_min, dt_max, dt_fixed=None):
     """Independent numpy restatement of one 2-D focused-transport step written from the Fortran."""
     f = lambda k: F[:, k - 1]
     g = lambda k: F[:, 8 + k - 1]
@@ -538,6 +538,8 @@ def _np_step_2d_ft(P, F, ptl, u, dt_min, dt_max):
     cands = [(0.5 * P.dx / s) ** 2, (0.5 * P.dy / s) ** 2, (s / dx_dt) ** 2, (s / dy_dt) ** 2,
              float(np.float32(0.1)) * p / np.abs(dp_dt), float(np.float32(0.1)) / np.abs(dmu_dt), 2.0 * duu / dmu_dt**2]
     dt = np.clip(np.minimum.reduce(cands), dt_min, dt_max)
+    if dt_fixed is not None:
+        dt = dt_fixed
     sdt, s3 = np.sqrt(dt), np.sqrt(3.0)
     r1, r2, rp, rm = [(2.0 * u[:, k] - 1.0) * s3 for k in range(4)]
     bxn, byn, bzn = bx * ib, by * ib, bz * ib
@@ -1299,3 +1301,55 @@ def test_local_escaped_distributions_match_numpy_binning(key, grid, conf):
             assert got[k]["z"] is None
         total += got[k]["x"].sum() + got[k]["y"].sum()
     assert total > 0.0
+
+
+def test_focused_transport_mover_rolls_back_speed_and_pitch_angle():
+    """The mover with the 2-D focused-transport pusher: the roll-back before the fixed-dt re-push also
+    restores v and mu (particle_module.f90:1712-1713).  Plain-Python mover + the numpy FT step against the
+    oracle's particle_mover over a whole interval with two fine steps."""
+    n = 20
+    w, P, frames, _ = make_case("c1", grid=48, nptl=n, conf=dict(dt_min_rel=2e-3),
+                                cli=dict(focused_transport=1, duu_init=5.0))
+    o = Oracle(P, w.nptl_max)
+    o.upload_fields(0, frames[0])
+    o.upload_fields(1, frames[1])
+    o.inject_uniform(n, 0.0, 0, w.particle_v0, 0.0, w.dt_out, box_of(P), w.power_index)
+    before = o.download_particles()
+    steps = o.particle_mover(0.0, w.dt_out, 100, 2, 0)
+    after = sort_by_key(o.download_particles())
+    fa1 = np_step.gradients32(frames[0], P.dx, P.dy)
+    fa2 = np_step.gradients32(frames[1], P.dx, P.dy)
+    dt_min, dt_max = P.dt_min_rel * w.dt_out, P.dt_max_rel * w.dt_out
+    tally = dict(leak=0.0, leak_negp=0.0, steps=0)
+    one = lambda v: np.array([v], dtype=np.float64)
+    out = []
+    for rec, rng0 in zip(before, rng_steps(before)):
+        s = {k: float(rec[k]) for k in ("x", "y", "z", "p", "v", "mu", "t", "dt", "weight")}
+        s.update(count_flag=int(rec["count_flag"]), nsteps_pushed=int(rec["nsteps_pushed"]), rng=int(rng0))
+        key = (P.seed & 0xFFFFFFFF, ((P.seed >> 32) + int(rec["origin"])) & 0xFFFFFFFF)
+        tags = (int(rec["tag_injected"]), int(rec["tag_splitted"]))
+
+        def push(s, fixed):
+            F = np_step.interp32(fa1, fa2, P, one(s["x"]), one(s["y"]), one((s["t"] - 0.0) / w.dt_out))
+            blk = philox4x32_10((s["rng"] & 0xFFFFFFFF, s["rng"] >> 32) + tags, key)
+            u = np.array([[b / 4294967295.0 for b in blk]])
+            st = {k: one(s[k]) for k in ("x", "y", "p", "v", "mu", "t")}
+            x, y, p, v, mu, t, dt = _np_step_2d_ft(P, F, st, u, dt_min, dt_max, dt_fixed=one(s["dt"]) if fixed else None)
+            d = (float(x[0]) - s["x"], float(y[0]) - s["y"], 0.0, float(p[0]) - s["p"], float(v[0]) - s["v"],
+                 float(mu[0]) - s["mu"])
+            s.update(x=float(x[0]), y=float(y[0]), p=float(p[0]), v=float(v[0]), mu=float(mu[0]), t=float(t[0]),
+                     dt=float(dt[0]), rng=s["rng"] + 1)
+            return d
+
+        np_step.mover_one_particle(P, s, push, 0.0, w.dt_out, 100, 2, tally)
+        if s["count_flag"] == np_step.INBOX:
+            np_step.final_boundary_pass(P, s, tally)
+        out.append(s)
+    assert tally["steps"] == steps, (tally["steps"], steps)
+    order = np.lexsort((before["tag_splitted"], before["tag_injected"], before["origin"]))
+    ref = [out[i] for i in order if out[i]["count_flag"] == np_step.INBOX]
+    assert len(ref) == len(after)
+    for name in ("x", "y", "p", "v", "mu", "t", "dt"):
+        want = np.array([r[name] for r in ref])
+        assert np.abs(after[name] - want).max() <= 1e-10 * max(1.0, np.abs(want).max()), name
+    assert np.all(after["t"] == w.dt_out) and np.any(after["mu"] != sort_by_key(before)["mu"])
