@@ -1353,3 +1353,73 @@ def test_focused_transport_mover_rolls_back_speed_and_pitch_angle():
         want = np.array([r[name] for r in ref])
         assert np.abs(after[name] - want).max() <= 1e-10 * max(1.0, np.abs(want).max()), name
     assert np.all(after["t"] == w.dt_out) and np.any(after["mu"] != sort_by_key(before)["mu"])
+
+
+@pytest.mark.parametrize("key,grid,dist_flag", [("c3", 48, 1), ("c3", 48, 0), ("c5", 16, 2)])
+def test_shock_injection_matches_python_restatement(key, grid, dist_flag):
+    """locate_shock_xpos + interp_shock_location + inject_particles_at_shock (mhd_data_parallel.f90:1988-2045,
+    particle_module.f90:542-633) value for value, quirks included: only the LATER frame's shock positions
+    survive rt = 0 (swapped time weights), rz is computed from dpy, the weights of the z pair therefore do
+    not sum to one in 3-D, x = (sx + 2) * lx / nxg, the Maxwellian envelope is 0.75 with exp(-p^2/2), t is
+    the frame time itself."""
+    import math
+    conf = dict(r1=2, r2=4, r3=8) if key == "c5" else None
+    w, P, frames, _ = make_case(key, grid=grid, nptl=300, conf=conf)
+    o = Oracle(P, w.nptl_max)
+    o.upload_fields(0, frames[0])
+    o.upload_fields(1, frames[1])
+    o.inject_at_shock(300, 1e-6, dist_flag, w.particle_v0, 0.3, 6.2)
+    a = o.download_particles()
+    assert len(a) == 300
+    if P.ndim == 2:
+        fa2 = np_step.gradients32(frames[1], P.dx, P.dy)[None]          # (1, ny+4, nx+4, 32)
+    else:
+        fa2 = np_step.gradients32_3d(frames[1], P.dx, P.dy, P.dz)
+    sx2 = np.argmax(np.abs(fa2[..., 8]), axis=-1) + 1                     # maxloc(abs(dvx_dx), dim=1), 1-based
+    key_ = (P.seed & 0xFFFFFFFF, ((P.seed >> 32) + P.mpi_rank) & 0xFFFFFFFF)
+    mu_max = float(np.float32(0.99))
+    nxg = P.nx + 4
+    for tag in range(300):
+        st = dict(k=0, buf=None)
+
+        def u():
+            if st["k"] % 4 == 0:
+                st["buf"] = philox4x32_10((st["k"] // 4, 0, tag, 0), key_)
+            v = st["buf"][st["k"] % 4] / 4294967295.0
+            st["k"] += 1
+            return v
+        y = u() * (P.ymax - P.ymin) + P.ymin
+        dpy = y / P.dy
+        iy = math.floor(dpy)
+        z = u() * (P.zmax - P.zmin) + P.zmin
+        iz = math.floor(z / P.dz)
+        ry = dpy - iy
+        rz = dpy - iy
+        wts = [(1 - ry) * (1 - rz), ry * (1 - rz), (1 - ry) * rz, ry * rz]
+        sx = 0.0
+        if P.ndim == 2:
+            for j in (0, 1):
+                sx = sx + sx2[0, iy + j] * wts[j]                     # Fortran index iy+j-1, lower bound -1
+        else:
+            for k in (0, 1):
+                for j in (0, 1):
+                    sx = sx + sx2[iz + k, iy + j] * wts[k * 2 + j]
+        x = ((sx * (1.0 - 0.0) + 0.0 * 0.0) + 2) * (P.xmax - P.xmin) / nxg
+        if dist_flag == 0:
+            ftest, fxp = 1.0, 0.5
+            while ftest > fxp:
+                ptmp = (u() * (P.pmax - P.pmin) + P.pmin) / P.p0
+                fxp = ptmp ** 2 * math.exp(-0.5 * ptmp ** 2)
+                ftest = u() * float(np.float32(0.75))
+            p = ptmp * P.p0
+        elif dist_flag == 1:
+            p = P.p0
+        else:
+            r01 = u()
+            norm = P.pmax ** (-6.2 + 1) - P.p0 ** (-6.2 + 1)
+            p = (r01 * norm + P.p0 ** (-6.2 + 1)) ** (1.0 / (-6.2 + 1))
+        mu = mu_max * (2.0 * u() - 1.0)
+        r = a[tag]
+        assert (r["x"], r["y"], r["z"], r["mu"], r["t"], r["dt"]) == (x, y, z, mu, 0.3, 1e-6), tag
+        assert abs(r["p"] - p) <= 4e-16 * p and r["tag_injected"] == tag and r["weight"] == 1.0
+    assert len(np.unique(a["x"])) > 3 or P.ndim == 2
