@@ -253,3 +253,56 @@ def test_fortran_interface_binds_every_entry_point():
     # the derived types carry the fields added to gpat_params in this round
     for field in ("keep_rho", "duu0", "focused_transport", "deltab_flag"):
         assert field in text, field
+
+
+# ---- parameter validation: runs before the device is touched, so it is testable here ------------------
+@pytest.mark.parametrize("change,message", [
+    (dict(spherical_coord=1), "spherical coordinates are outside the GPU path"),
+    (dict(nonuniform_grid=1), "non-uniform grids are outside the GPU path"),
+    (dict(nz=2), "2-D runs need nz = 1"),
+    (dict(ndim=4), "ndim must be 1, 2 or 3"),
+    (dict(pcharge=0), "pcharge must be non-zero"),
+    (dict(npp_global=0), "npp_global/nmu_global"),
+    (dict(acc_by_surface=1, surface_norm1=3), "acc_by_surface needs ndim = 3"),
+    (dict(focused_transport=1, include_3rd_dim=1, rng_mode=1), "draw five uniforms per step"),
+    (dict(local0_rx=5), "Wrong factor 'rx/ry/rz'"),
+    (dict(local0_npbins=0), "bad local histogram spec"),
+])
+def test_gpat_init_rejects_what_the_path_cannot_do(change, message):
+    """validate() in csrc/abi.cu: GPAT_ERR_INVALID (1) with the reason, before any CUDA call -- the library
+    never computes something other than what the switches ask for."""
+    from helpers import make_case
+    from stochastic_parker_b200 import GpatError, GpatSim
+    w, P, _, _ = make_case("c1", grid=16, nptl=8)
+    for k, v in change.items():
+        if k.startswith("local0_"):
+            setattr(P.local[0], k[7:], v)
+        else:
+            setattr(P, k, v)
+    with pytest.raises(GpatError) as e:
+        GpatSim(P, 64)
+    assert "(1)" in str(e.value) and message in str(e.value), str(e.value)
+
+
+def test_gpat_init_rejects_undefined_1d_and_3d_combinations():
+    from helpers import make_case
+    from stochastic_parker_b200 import GpatError, GpatSim
+    w, P, _, _ = make_case("s1", grid=64, nptl=8)
+    for change, message in ((dict(mag_dependency=1), "uninitialised db_dx"), (dict(focused_transport=1), "never assigns"),
+                            (dict(ny=2), "1-D runs need ny = nz = 1")):
+        Q = P.copy()
+        for k, v in change.items():
+            setattr(Q, k, v)
+        with pytest.raises(GpatError) as e:
+            GpatSim(Q, 64)
+        assert "(1)" in str(e.value) and message in str(e.value), str(e.value)
+    w, P3, _, _ = make_case("c5", grid=16, nptl=8, conf=dict(r1=2, r2=4, r3=8))
+    for change, message in ((dict(acc_by_surface=1, surface_norm1=0), "surface_norm must be"),
+                            (dict(acc_by_surface=1, surface_norm1=2, surface2_existed=1, surface_norm2=7), "surface_norm must be"),
+                            (dict(include_3rd_dim=1), "include_3rd_dim needs ndim = 2")):
+        Q = P3.copy()
+        for k, v in change.items():
+            setattr(Q, k, v)
+        with pytest.raises(GpatError) as e:
+            GpatSim(Q, 64)
+        assert "(1)" in str(e.value) and message in str(e.value), str(e.value)
