@@ -319,8 +319,8 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
     `surfaces(which, frame)` returns the float64 heights of acceleration surface `which` at that frame
     (the content of <surface_filenameK>_NNNN.dat).  `tmin` > 0 continues a run restored with
     read_restart() (frames are still indexed from the run's t_start = 0); `quota_seconds` ends the loop after
-    the first interval that finishes beyond it (reached_quota, :558-565).  The frame the loop stopped at is
-    left in run_intervals.last_frame for dump_restart().  Past `tmax_mhd` no new frame is read (:400): the
+    the first interval that finishes beyond it (reached_quota, :558-565); the last record's "frame" is the
+    frame to hand to dump_restart().  Past `tmax_mhd` no new frame is read (:400): the
     last one is sent to slot 1 again, because swap_fields exchanges the two device halves where the
     reference's copy_fields leaves farray2 in place.  `particle_data_dump` / `dump_escaped` add the
     population (dump_particles, :491, 525-527) and the interval's escapees (dump_escaped_particles, :529-531)
@@ -337,7 +337,6 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
     records = []
     import time as _time
     start = _time.time()
-    run_intervals.last_frame = tmin
     sim.upload_fields(0, get(tmin))                            # :320-321, :350 (mhd_data_<tmin>)
     nsurf = (2 if P.surface2_existed else 1) if P.acc_by_surface else 0
     if nsurf and surfaces is None:
@@ -388,7 +387,6 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
             records.append(d)
             if P.time_interp:
                 sim.swap_fields()
-            run_intervals.last_frame = tf
             if quota_seconds is not None and _time.time() - start > quota_seconds:
                 break
             continue
@@ -409,13 +407,10 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
             on_interval(tf, d)
         if P.time_interp:
             sim.swap_fields()                                  # :538
-        run_intervals.last_frame = tf
         if quota_seconds is not None and _time.time() - start > quota_seconds:   # :558-565
             break
     return records, total_steps
 
-
-run_intervals.last_frame = 0
 
 
 def dump_restart(sim, diagnostics_directory: str, t_end: int, tf: int) -> None:
