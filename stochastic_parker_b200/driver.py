@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import time
 
 import numpy as np
 
@@ -335,8 +336,7 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
         part_box = [P.xmin, P.ymin, P.zmin, P.xmax, P.ymax, P.zmax]
     nframes = len(tstamps)
     records = []
-    import time as _time
-    start = _time.time()
+    start = time.time()
     sim.upload_fields(0, get(tmin))                            # :320-321, :350 (mhd_data_<tmin>)
     nsurf = (2 if P.surface2_existed else 1) if P.acc_by_surface else 0
     if nsurf and surfaces is None:
@@ -387,7 +387,7 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
             records.append(d)
             if P.time_interp:
                 sim.swap_fields()
-            if quota_seconds is not None and _time.time() - start > quota_seconds:
+            if quota_seconds is not None and time.time() - start > quota_seconds:
                 break
             continue
         d = sim.diagnostics(local_dist)                        # :518-521
@@ -407,7 +407,7 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
             on_interval(tf, d)
         if P.time_interp:
             sim.swap_fields()                                  # :538
-        if quota_seconds is not None and _time.time() - start > quota_seconds:   # :558-565
+        if quota_seconds is not None and time.time() - start > quota_seconds:   # :558-565
             break
     return records, total_steps
 
