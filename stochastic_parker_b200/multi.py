@@ -59,4 +59,8 @@ def reduce_diagnostics(d: dict, dist) -> dict:
     out["pmax"] = float(red(np.array([d["pmax"]]), dist.ReduceOp.MAX)[0])
     if "fescaped" in d:
         out["fescaped"] = red(d["fescaped"], dist.ReduceOp.SUM)
+    if "fescaped_local" in d:  # the per-face arrays, diagnostics.f90:1174-1230
+        out["fescaped_local"] = [None if s is None else
+                                 {f: (None if a is None else red(a, dist.ReduceOp.SUM)) for f, a in s.items()}
+                                 for s in d["fescaped_local"]]
     return out

@@ -61,3 +61,29 @@ def test_two_ranks_reduce_to_the_union(tmp_path):
     assert red["quick"][2] == d["quick"][2]                       # sum of weights
     assert red["quick"][6] == d["quick"][6] and red["quick"][7] == d["quick"][7]  # min / max dt
     assert float(red["pmax"]) == d["pmax"]
+
+
+def test_reduce_diagnostics_covers_the_escaped_face_arrays():
+    """reduce_diagnostics walks every array the MPI_REDUCEs of diagnostics.f90:881-905 and 1174-1230 touch;
+    a stand-in communicator of two identical ranks (SUM doubles, MIN / MAX keep) makes that visible."""
+    from stochastic_parker_b200 import reduce_diagnostics
+
+    class TwoEqualRanks:
+        class ReduceOp:
+            SUM, MIN, MAX = "sum", "min", "max"
+
+        @staticmethod
+        def all_reduce(t, op):
+            if op == "sum":
+                t.mul_(2)
+
+    d = dict(fglobal=np.ones((4, 1)), flocal=[np.ones((1, 2, 2, 3, 1)), None, None, None],
+             quick=np.arange(1.0, 9.0), pmax=3.0, fescaped=np.ones((4, 4, 1)),
+             fescaped_local=[dict(x=np.ones((2, 1, 2, 3, 1)), y=np.full((2, 1, 2, 3, 1), 0.5), z=None), None, None, None])
+    r = reduce_diagnostics(d, TwoEqualRanks)
+    assert r["fglobal"].sum() == 8 and r["flocal"][0].sum() == 24 and r["flocal"][1] is None
+    assert list(r["quick"]) == [2, 4, 6, 8, 10, 12, 7, 8] and r["pmax"] == 3.0
+    assert r["fescaped"].sum() == 32
+    assert r["fescaped_local"][0]["x"].sum() == 24 and r["fescaped_local"][0]["y"].sum() == 12
+    assert r["fescaped_local"][0]["z"] is None and r["fescaped_local"][1] is None
+    assert d["fescaped_local"][0]["x"].sum() == 12          # the input record is left alone
