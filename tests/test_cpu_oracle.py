@@ -1423,3 +1423,64 @@ def test_shock_injection_matches_python_restatement(key, grid, dist_flag):
         assert (r["x"], r["y"], r["z"], r["mu"], r["t"], r["dt"]) == (x, y, z, mu, 0.3, 1e-6), tag
         assert abs(r["p"] - p) <= 4e-16 * p and r["tag_injected"] == tag and r["weight"] == 1.0
     assert len(np.unique(a["x"])) > 3 or P.ndim == 2
+
+
+def test_random_switch_combinations_match_numpy_restatement():
+    """24 seeded random combinations of the Parker-transport switches (geometry, both dependencies, kret,
+    NLGC, D_pp wave / shear, weak or strong scattering, acceleration region, time interpolation) -- one step of
+    the C oracle against the numpy restatement each, so that switch INTERACTIONS are pinned too."""
+    rng = np.random.default_rng(2024)
+    seen = set()
+    for trial in range(24):
+        geom = ["2d", "2d3", "3d"][trial % 3]
+        conf = dict(mag_dependency=int(rng.integers(0, 2)), momentum_dependency=int(rng.integers(0, 2)),
+                    kret=float(rng.choice([0.0, 0.01, 0.3])), acc_region_flag=int(rng.integers(0, 2)))
+        cli = dict(nlgc=int(rng.integers(0, 2)), kperp_kpara=0.05, dpp_wave=int(rng.integers(0, 2)),
+                   dpp_shear=int(rng.integers(0, 2)), weak_scattering=int(rng.integers(0, 2)),
+                   time_interp=int(rng.integers(0, 2)))
+        if geom == "2d3":
+            cli["include_3rd_dim"] = 1
+        if geom == "3d":
+            conf.update(r1=4, r2=8, r3=12)
+        seen.add((geom, conf["mag_dependency"], cli["nlgc"], cli["dpp_wave"], cli["dpp_shear"]))
+        key, grid = ("c5", 24) if geom == "3d" else ("c1", 48)
+        tweak = _narrow_region if conf["acc_region_flag"] else None
+        w, P, frames, _ = make_case(key, grid=grid, nptl=120, conf=conf, cli=cli)
+        if tweak:
+            tweak(P)
+        P.rng_mode = RNG_TABLE
+        o = Oracle(P, w.nptl_max)
+        u = np.random.default_rng(100 + trial).uniform(0, 1, (120, 2, 4))
+        o.set_rng_table(u)
+        o.upload_fields(0, frames[0])
+        if P.time_interp:
+            o.upload_fields(1, frames[1])
+        o.inject_uniform(120, 0.0, 0, w.particle_v0, 0.0, w.dt_out, box_of(P), w.power_index)
+        before = o.download_particles()
+        assert o.debug_push_n(0.0, w.dt_out, 1) == 120
+        after = o.download_particles()
+        uu = u[before["tag_injected"], 0]
+        rt = (before["t"] - 0.0) / w.dt_out
+        if geom == "3d":
+            fa1 = np_step.gradients32_3d(frames[0], P.dx, P.dy, P.dz)
+            fa2 = np_step.gradients32_3d(frames[1], P.dx, P.dy, P.dz) if P.time_interp else None
+            F = np_step.interp32_3d(fa1, fa2, P, before["x"], before["y"], before["z"], rt)
+        else:
+            fa1 = np_step.gradients32(frames[0], P.dx, P.dy)
+            fa2 = np_step.gradients32(frames[1], P.dx, P.dy) if P.time_interp else None
+            F = np_step.interp32(fa1, fa2, P, before["x"], before["y"], rt)
+        qdrift = float(np.float32(1.0) / np.float32(3 * P.pcharge))
+        dt_min, dt_max = P.dt_min_rel * w.dt_out, P.dt_max_rel * w.dt_out
+        if geom == "2d":
+            want = np_step.push_2d_general(P, F, before["p"], before["mu"], dt_min, dt_max, uu, before["x"], before["y"],
+                                           before["t"], qdrift)
+            names = ("x", "y", "p", "t", "dt")
+        else:
+            want = np_step.push_3d_like(P, F, before["p"], before["mu"], dt_min, dt_max, uu, before["x"], before["y"],
+                                        before["z"], before["t"], qdrift, geom == "3d")
+            names = ("x", "y", "z", "p", "t", "dt")
+        for name, ref in zip(names, want):
+            scale = np.maximum(np.abs(ref), 1.0) if name in "xyz" else np.abs(ref)
+            err = np.abs(after[name] - ref) / scale
+            assert err.max() < 4e-15, (trial, geom, conf, cli, name, err.max())
+    assert len(seen) >= 15
