@@ -336,3 +336,18 @@ def test_varying_frame_interval(driver, tmp_path):
     rec, steps = run_intervals(Oracle(P, 12 * 500), frames[:4], list(ts), nptl=500, particle_v0=w.particle_v0, **KW,
                                tmax_mhd=3)
     _same_run(r, out, rec, steps, 5)
+
+
+def test_single_time_frame_without_time_interpolation(driver, tmp_path):
+    """-st 1 -ti 0: the first frame is the only one read (stochastic-mhd.f90:400); every interval uses it."""
+    w, P, frames, d, out, base = _setup(tmp_path, "c1", 48, 400, 4, cli=dict(time_interp=0))
+    ti = base.index("-ti") + 1
+    args = list(base)
+    args[ti] = "0"
+    for f in (1, 2, 3):
+        os.remove(d / f"mhd_data_{f:04d}")          # must not be needed
+    r = driver(args + ["-st", "1"])
+    assert P.time_interp == 0
+    rec, steps = run_intervals(Oracle(P, 12 * 400), [frames[0]] * 4, [f * w.dt_out for f in range(4)], nptl=400,
+                               particle_v0=w.particle_v0, **KW)
+    _same_run(r, out, rec, steps, 4)
