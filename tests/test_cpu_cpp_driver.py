@@ -160,6 +160,7 @@ def test_fine_steps_part_box_and_power_law(driver, tmp_path):
     ("-ij", ["-jz", "0.5", "-nn", "40"], 1, 0.5, 40),
     ("-iaj", ["-ajm", "0.5", "-naj", "40"], 2, 0.5, 40),
     ("-iv", ["-dv", "0.2", "-nv", "40"], 4, 0.2, 40),
+    ("-ir", ["-rm", "1.05", "-nr", "40"], 5, 1.05, 40),
 ])
 def test_targeted_injection_switches(driver, tmp_path, switch, extra, mode, vmin, norm):
     w, P, frames, d, out, base = _setup(tmp_path, "c1", 48, 500, 3)
@@ -351,3 +352,24 @@ def test_single_time_frame_without_time_interpolation(driver, tmp_path):
     rec, steps = run_intervals(Oracle(P, 12 * 400), [frames[0]] * 4, [f * w.dt_out for f in range(4)], nptl=400,
                                particle_v0=w.particle_v0, **KW)
     _same_run(r, out, rec, steps, 4)
+
+
+def test_third_dimension_dpp_and_nlgc_switches(driver, tmp_path):
+    """-i3 1 -dw 1 -ds 1 -ws 0 -nl .true. -kk 0.05 -cd 0: the switch-to-parameter mapping of the physics options."""
+    cli = dict(include_3rd_dim=1, dpp_wave=1, dpp_shear=1, weak_scattering=0, nlgc=1, kperp_kpara=0.05, tau0=1e-3)
+    w, P, frames, d, out, base = _setup(tmp_path, "c1", 48, 400, 3, conf=dict(dt_min_rel=1e-3), cli=cli)
+    args = list(base)
+    args[args.index("-nl") + 1] = ".true."
+    r = driver(args + ["-i3", "1", "-dw", "1", "-ds", "1", "-ws", "0", "-kk", "0.05", "-t0", "1e-3"])
+    rec, steps = run_intervals(Oracle(P, 12 * 400), frames, [f * w.dt_out for f in range(3)], nptl=400,
+                               particle_v0=w.particle_v0, **KW)
+    assert P.nlgc == 1 and P.include_3rd_dim == 1 and P.dpp_wave == 1 and P.weak_scattering == 0 and P.tau0 == 1e-3
+    _same_run(r, out, rec, steps, 3)
+
+
+def test_three_dimensional_run(driver, tmp_path):
+    w, P, frames, d, out, base = _setup(tmp_path, "c5", 24, 300, 3, conf=dict(r1=4, r2=8, r3=12))
+    r = driver(base)
+    rec, steps = run_intervals(Oracle(P, 12 * 300), frames, [f * w.dt_out for f in range(3)], nptl=300,
+                               particle_v0=w.particle_v0, **KW)
+    _same_run(r, out, rec, steps, 3)
