@@ -373,3 +373,25 @@ def test_three_dimensional_run(driver, tmp_path):
     rec, steps = run_intervals(Oracle(P, 12 * 300), frames, [f * w.dt_out for f in range(3)], nptl=300,
                                particle_v0=w.particle_v0, **KW)
     _same_run(r, out, rec, steps, 3)
+
+
+def test_large_db2_injection_with_map_files(driver, tmp_path):
+    """-ib .true. -db2 ... -nb ... with -db 1: inject_particles_at_large_db2 reads the uploaded dB^2 map."""
+    w, P, frames, d, out, base = _setup(tmp_path, "c1", 48, 400, 3)
+    P.deltab_flag = 1
+    maps = [mhd.make_turbulence_maps(w.nx, w.ny, w.nz, f, 2, w.dt_out) for f in range(3)]
+    for f, (s2s, s22, lcs, lc2) in enumerate(maps):
+        np.stack([s2s, s22]).tofile(str(d / f"deltab_{f:04d}"))
+    vmin = float(np.median(maps[0][0]))
+    r = driver(base + ["-db", "1", "-ib", ".true.", "-db2", repr(vmin), "-nb", "40", "-sn", ".false."])
+
+    class WithMaps(Oracle):
+        def upload_fields(self, slot, f, with_grad=0):
+            super().upload_fields(slot, f, with_grad)
+            k = next(i for i, fr in enumerate(frames) if fr is f)
+            self.upload_turbulence(0, slot, maps[k][0], maps[k][1])
+    rec, steps = run_intervals(WithMaps(P, 12 * 400), frames, [f * w.dt_out for f in range(3)], nptl=400,
+                               particle_v0=w.particle_v0, **KW, inject_mode=3, inject_same_nptl=False, inject_min=vmin,
+                               ncells_norm=40)
+    _same_run(r, out, rec, steps, 3)
+    assert rec[-1]["quick"][0] > 0
