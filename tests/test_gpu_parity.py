@@ -6,6 +6,8 @@ FP64; integer/index work (histogram counts, tags, compaction order, RNG counters
 difference from the oracle is CUDA's libdevice pow/log10 vs glibc's (<= 2 ulp); the fast build
 (FMA contraction, fused time blend) is held to the same 1e-12 per step.
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -377,7 +379,7 @@ def test_local_escaped_distributions_bit_exact(key, grid, conf):
     # and the binning itself, bit for bit, on the GPU's own escapees re-binned by the oracle's routine
     o2 = Oracle(P, w.nptl_max)
     o2.upload_particles(np.zeros(0, dtype=PARTICLE_DTYPE))
-    o2.lib.orc_set_escaped(o2.h, ge.ctypes.data_as(__import__("ctypes").c_void_p), __import__("ctypes").c_int64(len(ge)))
+    o2.lib.orc_set_escaped(o2.h, ge.ctypes.data_as(C.c_void_p), C.c_int64(len(ge)))
     c = o2.escaped_local_diagnostics()
     for k in range(4):
         if a[k] is None:
