@@ -1484,3 +1484,52 @@ def test_random_switch_combinations_match_numpy_restatement():
             err = np.abs(after[name] - ref) / scale
             assert err.max() < 4e-15, (trial, geom, conf, cli, name, err.max())
     assert len(seen) >= 15
+
+
+@pytest.mark.parametrize("nlgc,third,flags", [(1, 0, (1, 1)), (1, 0, (1, 0)), (1, 0, (0, 1)), (1, 1, (1, 1)), (0, 1, (1, 1))])
+def test_turbulence_maps_with_nlgc_and_third_dimension_match_numpy_restatement(nlgc, third, flags):
+    """The map terms of calc_spatial_diffusion_coefficients_nlgc (particle_module.f90:2486-2500, 2588-2604:
+    db2_2d and lc_2d enter k_perp) and of the include_3rd branches, which the plain 2-D test above does not reach."""
+    from stochastic_parker_b200 import mhd
+    cli = dict(nlgc=nlgc, kperp_kpara=0.05)
+    if third:
+        cli["include_3rd_dim"] = 1
+    w, P, frames, _ = make_case("c1", grid=48, nptl=300, cli=cli)
+    P.deltab_flag, P.correlation_flag = flags
+    P.rng_mode = RNG_TABLE
+    o = Oracle(P, w.nptl_max)
+    u = np.random.default_rng(31).uniform(0, 1, (300, 2, 4))
+    o.set_rng_table(u)
+    maps = [mhd.make_turbulence_maps(P.nx, P.ny, 1, f) for f in (0, 1)]
+    for slot in (0, 1):
+        o.upload_fields(slot, frames[slot])
+        if flags[0]:
+            o.upload_turbulence(0, slot, maps[slot][0], maps[slot][1])
+        if flags[1]:
+            o.upload_turbulence(1, slot, maps[slot][2], maps[slot][3])
+    o.inject_uniform(300, 0.0, 0, w.particle_v0, 0.0, w.dt_out, box_of(P), w.power_index)
+    before = o.download_particles()
+    assert o.debug_push_n(0.0, w.dt_out, 1) == 300
+    after = o.download_particles()
+    rt = (before["t"] - 0.0) / w.dt_out
+    fa1 = np_step.gradients32(frames[0], P.dx, P.dy)
+    fa2 = np_step.gradients32(frames[1], P.dx, P.dy)
+    F = np_step.interp32(fa1, fa2, P, before["x"], before["y"], rt)
+    g = [[np_step.turbulence_grad(m, P.dx, P.dy) for m in maps[s]] for s in (0, 1)]
+    aux = np_step.interp_aux(g[0], g[1], P, before["x"], before["y"], rt)
+    if not flags[0]:
+        aux[:, 0:8] = 1.0          # interp_* is not called: the locals keep their initial 1.0 (particle_module.f90:1546)
+    if not flags[1]:
+        aux[:, 8:16] = 1.0
+    qdrift = float(np.float32(1.0) / np.float32(3 * P.pcharge))
+    uu = u[before["tag_injected"], 0]
+    dt_min, dt_max = P.dt_min_rel * w.dt_out, P.dt_max_rel * w.dt_out
+    if third:
+        want = np_step.push_3d_like(P, F, before["p"], before["mu"], dt_min, dt_max, uu, before["x"], before["y"],
+                                    before["z"], before["t"], qdrift, False, aux=aux)
+        names = ("x", "y", "z", "p", "t", "dt")
+    else:
+        want = np_step.push_2d_general(P, F, before["p"], before["mu"], dt_min, dt_max, uu, before["x"], before["y"],
+                                       before["t"], qdrift, aux=aux)
+        names = ("x", "y", "p", "t", "dt")
+    _check(after, want, names, tol=1e-14)
