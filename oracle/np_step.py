@@ -636,3 +636,39 @@ def remove_particles(flags):
             idx[tail - 1], idx[i - 1] = idx[i - 1], idx[tail - 1]
             nremoved += 1
     return idx[:n - nremoved], escaped
+
+
+def turbulence_grad_3d(a, dx, dy, dz):
+    """3-D version of turbulence_grad: (nz+4, ny+4, nx+4) float32 -> (..., 4) float32 = value, d/dx, d/dy, d/dz
+    (calc_grad_sigma2_slab and its siblings, mhd_data_parallel.f90:771-1604, d/dz part included)."""
+    out = np.zeros(a.shape + (4,), dtype=np.float32)
+    out[..., 0] = a
+    for comp, (axis, h) in enumerate(((2, dx), (1, dy), (0, dz)), start=1):
+        b = np.moveaxis(a, axis, 0)
+        g = np.zeros_like(b)
+        g[1:-1] = b[2:] - b[:-2]
+        g[0] = (np.float32(-3) * b[0] + np.float32(4) * b[1]) - b[2]
+        g[-1] = (np.float32(3) * b[-1] - np.float32(4) * b[-2]) + b[-3]
+        out[..., comp] = np.moveaxis((g.astype(np.float64) * (0.5 / h)).astype(np.float32), 0, axis)
+    return out
+
+
+def interp_aux_3d(maps1, maps2, P, x, y, z, rt):
+    """interp_magnetic_fluctuation / interp_correlation_length with the eight trilinear weights: (n, 16)."""
+    pc = [(x - P.xmin) / P.dx, (y - P.ymin) / P.dy, (z - P.zmin) / P.dz]
+    idx = [np.floor(c).astype(np.int64) + 1 for c in pc]
+    r = [c - i + 1 for c, i in zip(pc, idx)]
+    r1 = [1.0 - v for v in r]
+    out = []
+    for m1, m2 in zip(maps1, maps2):
+        f1 = np.zeros((len(x), 4))
+        f2 = np.zeros((len(x), 4))
+        for k in (0, 1):
+            for j in (0, 1):
+                for i in (0, 1):
+                    w = (r[0] if i else r1[0]) * (r[1] if j else r1[1]) * (r[2] if k else r1[2])
+                    sl = (idx[2] + k + 1, idx[1] + j + 1, idx[0] + i + 1)
+                    f1 = f1 + m1[sl].astype(np.float64) * w[:, None]
+                    f2 = f2 + m2[sl].astype(np.float64) * w[:, None]
+        out.append(f1 * (1.0 - rt[:, None]) + f2 * rt[:, None])
+    return np.concatenate(out, axis=1)

@@ -1533,3 +1533,41 @@ def test_turbulence_maps_with_nlgc_and_third_dimension_match_numpy_restatement(n
                                        before["t"], qdrift, aux=aux)
         names = ("x", "y", "p", "t", "dt")
     _check(after, want, names, tol=1e-14)
+
+
+@pytest.mark.parametrize("nlgc", [0, 1])
+def test_3d_turbulence_maps_match_numpy_restatement(nlgc):
+    """3-D maps: the d/dz gradients, the eight-corner gather and the dk/dz map terms of both kappa routines."""
+    from stochastic_parker_b200 import mhd
+    w, P, frames, _ = make_case("c5", grid=24, nptl=300, conf=dict(r1=4, r2=8, r3=12, mag_dependency=1),
+                                cli=dict(nlgc=nlgc, kperp_kpara=0.05))
+    P.deltab_flag, P.correlation_flag = 1, 1
+    P.rng_mode = RNG_TABLE
+    o = Oracle(P, w.nptl_max)
+    u = np.random.default_rng(41).uniform(0, 1, (300, 2, 4))
+    o.set_rng_table(u)
+    maps = [mhd.make_turbulence_maps(P.nx, P.ny, P.nz, f, 3) for f in (0, 1)]
+    for slot in (0, 1):
+        o.upload_fields(slot, frames[slot])
+        o.upload_turbulence(0, slot, maps[slot][0], maps[slot][1])
+        o.upload_turbulence(1, slot, maps[slot][2], maps[slot][3])
+    o.inject_uniform(300, 0.0, 0, w.particle_v0, 0.0, w.dt_out, box_of(P), w.power_index)
+    before = o.download_particles()
+    assert o.debug_push_n(0.0, w.dt_out, 1) == 300
+    after = o.download_particles()
+    rt = (before["t"] - 0.0) / w.dt_out
+    fa1 = np_step.gradients32_3d(frames[0], P.dx, P.dy, P.dz)
+    fa2 = np_step.gradients32_3d(frames[1], P.dx, P.dy, P.dz)
+    F = np_step.interp32_3d(fa1, fa2, P, before["x"], before["y"], before["z"], rt)
+    g = [[np_step.turbulence_grad_3d(m, P.dx, P.dy, P.dz) for m in maps[s]] for s in (0, 1)]
+    assert np.any(g[0][0][..., 3] != 0)                       # the maps do vary along z
+    aux = np_step.interp_aux_3d(g[0], g[1], P, before["x"], before["y"], before["z"], rt)
+    qdrift = float(np.float32(1.0) / np.float32(3 * P.pcharge))
+    want = np_step.push_3d_like(P, F, before["p"], before["mu"], P.dt_min_rel * w.dt_out, P.dt_max_rel * w.dt_out,
+                                u[before["tag_injected"], 0], before["x"], before["y"], before["z"], before["t"], qdrift,
+                                True, aux=aux)
+    _check(after, want, ("x", "y", "z", "p", "t", "dt"), tol=1e-14)
+    flat = np_step.push_3d_like(P, F, before["p"], before["mu"], P.dt_min_rel * w.dt_out, P.dt_max_rel * w.dt_out,
+                                u[before["tag_injected"], 0], before["x"], before["y"], before["z"], before["t"], qdrift,
+                                True, aux=np.ones_like(aux) * np.array([1, 0, 0, 0] * 4))
+    assert np.max(np.abs(flat[2] - want[2])) > 1e-7           # the maps matter for the z motion
