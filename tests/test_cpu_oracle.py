@@ -484,7 +484,7 @@ def test_tracking_replays_and_records_the_selected_particles():
 
 
 # ---- focused transport, 2-D (calc_duu + push_particle_2d_ft, particle_module.f90:3116-3155, 3626-3977)
-def _np_step_2d_ft(P, F, ptl, u, dt_min, dt_max, dt_fixed=None):
+def _np_step_2d_ft(P, F, ptl, u, dt_min, dt_max, dt_fixed=None, aux=None):
     """Independent numpy restatement of one 2-D focused-transport step written from the Fortran."""
     f = lambda k: F[:, k - 1]
     g = lambda k: F[:, 8 + k - 1]
@@ -497,12 +497,21 @@ def _np_step_2d_ft(P, F, ptl, u, dt_min, dt_max, dt_fixed=None):
     dbz_dx, dbz_dy, db_dx, db_dy = g(19), g(20), g(22), g(23)
     # kappa with kpp = -kperp (particle_module.f90:2372-2376)
     knp = b ** (P.gamma_turb - 2.0) if P.mag_dependency == 1 else np.ones_like(b)
+    if P.deltab_flag:
+        knp = knp / aux[:, 0]
+    if P.correlation_flag:
+        knp = knp * aux[:, 8] ** (P.gamma_turb - 1.0)
     knorm = knp * (p / P.p0) ** P.pindex if P.momentum_dependency == 1 else knp
     kpara = P.kpara0 * knorm
     kperp = kpara * P.kret
     skpara, skperp = np.sqrt(2 * kpara), np.sqrt(2 * kperp)
     dkdx = db_dx * ib * (P.gamma_turb - 2.0) if P.mag_dependency == 1 else 0.0 * b
     dkdy = db_dy * ib * (P.gamma_turb - 2.0) if P.mag_dependency == 1 else 0.0 * b
+    if P.deltab_flag:
+        dkdx, dkdy = dkdx - aux[:, 1] / aux[:, 0], dkdy - aux[:, 2] / aux[:, 0]
+    if P.correlation_flag:
+        dkdx = dkdx + (P.gamma_turb - 1.0) * aux[:, 9] / aux[:, 8]
+        dkdy = dkdy + (P.gamma_turb - 1.0) * aux[:, 10] / aux[:, 8]
     kpp = -kperp
     dkxx_dx = kperp * dkdx + kpp * dkdx * bx**2 * ib2 + 2.0 * kpp * bx * (dbx_dx * b - bx * db_dx) * ib3
     dkyy_dy = kperp * dkdy + kpp * dkdy * by**2 * ib2 + 2.0 * kpp * by * (dby_dy * b - by * db_dy) * ib3
@@ -529,6 +538,10 @@ def _np_step_2d_ft(P, F, ptl, u, dt_min, dt_max, dt_fixed=None):
     norm = np.ones_like(b)
     if P.mag_dependency == 1:
         norm = norm * b ** (2.0 - P.gamma_turb)
+    if P.deltab_flag:            # calc_duu, particle_module.f90:3143-3148
+        norm = norm * aux[:, 0]
+    if P.correlation_flag:
+        norm = norm * aux[:, 8] ** (1.0 - P.gamma_turb)
     if P.momentum_dependency == 1:
         norm = norm * (p / P.p0) ** (P.gamma_turb - 1)
     duu = P.duu0 * (1 - mu2) * dtmp * norm
@@ -1571,3 +1584,37 @@ def test_3d_turbulence_maps_match_numpy_restatement(nlgc):
                                 u[before["tag_injected"], 0], before["x"], before["y"], before["z"], before["t"], qdrift,
                                 True, aux=np.ones_like(aux) * np.array([1, 0, 0, 0] * 4))
     assert np.max(np.abs(flat[2] - want[2])) > 1e-7           # the maps matter for the z motion
+
+
+def test_focused_transport_with_turbulence_maps_matches_numpy_restatement():
+    """calc_duu's map factors (particle_module.f90:3143-3148: D_mumu ~ dB^2 * lc^(1 - gamma)) and the map terms
+    of kappa under focused transport."""
+    from stochastic_parker_b200 import mhd
+    w, P, frames, _ = make_case("c1", grid=48, nptl=300, cli=dict(focused_transport=1, duu_init=5.0))
+    P.deltab_flag, P.correlation_flag = 1, 1
+    P.rng_mode = RNG_TABLE
+    o = Oracle(P, w.nptl_max)
+    u = np.random.default_rng(51).uniform(0, 1, (300, 2, 4))
+    o.set_rng_table(u)
+    maps = [mhd.make_turbulence_maps(P.nx, P.ny, 1, f) for f in (0, 1)]
+    for slot in (0, 1):
+        o.upload_fields(slot, frames[slot])
+        o.upload_turbulence(0, slot, maps[slot][0], maps[slot][1])
+        o.upload_turbulence(1, slot, maps[slot][2], maps[slot][3])
+    o.inject_uniform(300, 0.0, 0, w.particle_v0, 0.0, w.dt_out, box_of(P), w.power_index)
+    before = o.download_particles()
+    assert o.debug_push_n(0.0, w.dt_out, 1) == 300
+    after = o.download_particles()
+    rt = (before["t"] - 0.0) / w.dt_out
+    F = o.interp(before["x"], before["y"], before["z"], rt)
+    g = [[np_step.turbulence_grad(m, P.dx, P.dy) for m in maps[s]] for s in (0, 1)]
+    aux = np_step.interp_aux(g[0], g[1], P, before["x"], before["y"], rt)
+    args = (P, F, before, u[before["tag_injected"], 0], P.dt_min_rel * w.dt_out, P.dt_max_rel * w.dt_out)
+    x, y, p, v, mu, t, dt = _np_step_2d_ft(*args, aux=aux)
+    for name, ref in (("x", x), ("y", y), ("p", p), ("v", v), ("mu", mu), ("t", t), ("dt", dt)):
+        scale = np.maximum(np.abs(ref), 1.0 if name in "xy" else 1e-300)
+        assert (np.abs(after[name] - ref) / scale).max() < 1e-13, name
+    P0 = P.copy()
+    P0.deltab_flag, P0.correlation_flag = 0, 0
+    mu0 = _np_step_2d_ft(P0, *args[1:])[4]
+    assert np.max(np.abs(mu0 - mu)) > 1e-6          # the maps change the pitch-angle scattering
