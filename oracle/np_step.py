@@ -251,7 +251,7 @@ def interp32_3d(fa1, fa2, P, x, y, z, rt):
     return f1
 
 
-def kappa_tensor(P, F, p, mu, geometry, aux=None):
+def kappa_tensor(P, F, p, mu, geometry, aux=None, focused=False):
     """kappa_type for geometry '2d' (ndim_field = 2), '2d3' (2-D + include_3rd_dim) or '3d'.
     Returns a dict of arrays named as the Fortran components."""
     nf = NFIELDS
@@ -318,7 +318,8 @@ def kappa_tensor(P, F, p, mu, geometry, aux=None):
             a = a + g1 * aux[:, 9 + n] / aux[:, 8]
             e = e + g1 * aux[:, 9 + n] / aux[:, 8] / 3.0 + 2.0 * aux[:, 13 + n] / aux[:, 12] / 3.0
         dpa[d], dpe[d] = a, e
-    kpp = kpara - kperp  # Parker transport (focused transport is restated in the tests that cover it)
+    # focused transport keeps the perpendicular part only (particle_module.f90:2372-2376, 2606-2610)
+    kpp = -kperp if focused else kpara - kperp
     for d in axes:       # dk_dd_dd
         if P.nlgc:
             iso, ani = kperp * dpe[d], kpara * dpa[d] - kperp * dpe[d]

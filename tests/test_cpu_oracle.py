@@ -517,6 +517,10 @@ def _np_step_2d_ft(P, F, ptl, u, dt_min, dt_max, dt_fixed=None, aux=None):
     dkyy_dy = kperp * dkdy + kpp * dkdy * by**2 * ib2 + 2.0 * kpp * by * (dby_dy * b - by * db_dy) * ib3
     dkxy_dx = kpp * dkdx * bx * by * ib2 + kpp * ((dbx_dx * by + bx * dby_dx) * ib2 - 2.0 * bx * by * db_dx * ib3)
     dkxy_dy = kpp * dkdy * bx * by * ib2 + kpp * ((dbx_dy * by + bx * dby_dy) * ib2 - 2.0 * bx * by * db_dy * ib3)
+    if P.nlgc:   # calc_spatial_diffusion_coefficients_nlgc with focused_transport = .true.
+        kt = np_step.kappa_tensor(P, F, p, mu, "2d", aux, focused=True)
+        kpara, kperp, skpara, skperp = kt["kpara"], kt["kperp"], kt["skpara"], kt["skperp"]
+        dkxx_dx, dkyy_dy, dkxy_dx, dkxy_dy = kt["dkxx_dx"], kt["dkyy_dy"], kt["dkxy_dx"], kt["dkxy_dy"]
     vdp = float(np.float32(1.0) / np.float32(P.pcharge)) / np.sqrt((P.drift1 * P.p0 / p) ** 2 + (P.drift2 * P.p0**2 / p**2) ** 2)
     mu2 = mu**2
     muf1, muf2 = 0.5 * (1.0 - mu2), 0.5 * (3.0 * mu2 - 1.0)
@@ -1618,3 +1622,35 @@ def test_focused_transport_with_turbulence_maps_matches_numpy_restatement():
     P0.deltab_flag, P0.correlation_flag = 0, 0
     mu0 = _np_step_2d_ft(P0, *args[1:])[4]
     assert np.max(np.abs(mu0 - mu)) > 1e-6          # the maps change the pitch-angle scattering
+
+
+@pytest.mark.parametrize("maps_on", [0, 1])
+def test_focused_transport_with_nlgc_matches_numpy_restatement(maps_on):
+    """push_particle_2d_ft fed by calc_spatial_diffusion_coefficients_nlgc(focused_transport = .true.):
+    k_perp ~ mu^2, kpp = -k_perp, separate d ln k_para and d ln k_perp."""
+    from stochastic_parker_b200 import mhd
+    w, P, frames, _ = make_case("c1", grid=48, nptl=300, cli=dict(focused_transport=1, duu_init=5.0, nlgc=1, kperp_kpara=0.05))
+    P.deltab_flag = P.correlation_flag = maps_on
+    P.rng_mode = RNG_TABLE
+    o = Oracle(P, w.nptl_max)
+    u = np.random.default_rng(61).uniform(0, 1, (300, 2, 4))
+    o.set_rng_table(u)
+    maps = [mhd.make_turbulence_maps(P.nx, P.ny, 1, f) for f in (0, 1)]
+    for slot in (0, 1):
+        o.upload_fields(slot, frames[slot])
+        if maps_on:
+            o.upload_turbulence(0, slot, maps[slot][0], maps[slot][1])
+            o.upload_turbulence(1, slot, maps[slot][2], maps[slot][3])
+    o.inject_uniform(300, 0.0, 0, w.particle_v0, 0.0, w.dt_out, box_of(P), w.power_index)
+    before = o.download_particles()
+    assert o.debug_push_n(0.0, w.dt_out, 1) == 300
+    after = o.download_particles()
+    rt = (before["t"] - 0.0) / w.dt_out
+    F = o.interp(before["x"], before["y"], before["z"], rt)
+    g = [[np_step.turbulence_grad(m, P.dx, P.dy) for m in maps[s]] for s in (0, 1)]
+    aux = np_step.interp_aux(g[0], g[1], P, before["x"], before["y"], rt) if maps_on else None
+    x, y, p, v, mu, t, dt = _np_step_2d_ft(P, F, before, u[before["tag_injected"], 0], P.dt_min_rel * w.dt_out,
+                                           P.dt_max_rel * w.dt_out, aux=aux)
+    for name, ref in (("x", x), ("y", y), ("p", p), ("v", v), ("mu", mu), ("t", t), ("dt", dt)):
+        scale = np.maximum(np.abs(ref), 1.0 if name in "xy" else 1e-300)
+        assert (np.abs(after[name] - ref) / scale).max() < 1e-13, name
