@@ -719,6 +719,12 @@ def _np_step_ft_3d_like(P, F, ptl, u, u5, dt_min, dt_max):
     dkxz_dz = dk(0.0, dkdz, bx, bz, dbx_dz, dbz_dz, db_dz)
     dkyz_dy = dk(0.0, dkdy, by, bz, dby_dy, dbz_dy, db_dy)
     dkyz_dz = dk(0.0, dkdz, by, bz, dby_dz, dbz_dz, db_dz)
+    if P.nlgc:   # calc_spatial_diffusion_coefficients_nlgc with focused_transport = .true.
+        kt = np_step.kappa_tensor(P, F, p, mu, "3d" if full3d else "2d3", None, focused=True)
+        kpara, kperp, skpara, skperp = kt["kpara"], kt["kperp"], kt["skpara"], kt["skperp"]
+        dkxx_dx, dkyy_dy, dkzz_dz = kt["dkxx_dx"], kt["dkyy_dy"], kt["dkzz_dz"]
+        dkxy_dx, dkxy_dy, dkxz_dx, dkxz_dz = kt["dkxy_dx"], kt["dkxy_dy"], kt["dkxz_dx"], kt["dkxz_dz"]
+        dkyz_dy, dkyz_dz = kt["dkyz_dy"], kt["dkyz_dz"]
     vdp = float(np.float32(1.0) / np.float32(P.pcharge)) / np.sqrt((P.drift1 * P.p0 / p) ** 2 + (P.drift2 * P.p0**2 / p**2) ** 2)
     mu2 = mu**2
     muf1, muf2 = 0.5 * (1.0 - mu2), 0.5 * (3.0 * mu2 - 1.0)
@@ -775,7 +781,9 @@ def _np_step_ft_3d_like(P, F, ptl, u, u5, dt_min, dt_max):
     return x, y, z, pn, vn, mun, ptl["t"] + dt, dt
 
 
-@pytest.mark.parametrize("key,grid,cli", [("c1", 48, dict(include_3rd_dim=1)), ("c5", 24, {})])
+@pytest.mark.parametrize("key,grid,cli", [("c1", 48, dict(include_3rd_dim=1)), ("c5", 24, {}),
+                                          ("c1", 48, dict(include_3rd_dim=1, nlgc=1, kperp_kpara=0.05)),
+                                          ("c5", 24, dict(nlgc=1, kperp_kpara=0.05))])
 def test_focused_transport_3d_like_step_matches_numpy_restatement(key, grid, cli):
     w, P, frames, _ = make_case(key, grid=grid, nptl=300, cli=dict(cli, focused_transport=1, duu_init=5.0),
                                 conf=dict(r1=4, r2=8, r3=12) if key == "c5" else None)
