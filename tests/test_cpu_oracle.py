@@ -344,9 +344,29 @@ def _np_step_1d(P, frames, before, u, t0, dtf):
     knorm = (p / P.p0) ** P.pindex if P.momentum_dependency == 1 else np.ones_like(p)
     kpara = P.kpara0 * knorm
     kperp = kpara * P.kret
+    if P.nlgc:  # particle_module.f90:2497-2509 with mag_dependency = 0 and no maps
+        nperp = (p / P.p0) ** ((5.0 - P.gamma_turb) / 3.0) if P.momentum_dependency == 1 else np.ones_like(p)
+        kperp = P.kpara0 * P.kperp_kpara * nperp * before["mu"] ** 2
     skpara, skperp = np.sqrt(2.0 * kpara), np.sqrt(2.0 * kperp)
     dx_dt = Fi["vx"] + kpara * 0.0
     dp_dt = -p * Fi["dvx"] / 3.0
+    dpp = np.zeros_like(p)
+    b = np.sqrt(Fi["bx"] ** 2 + Fi["by"] ** 2 + Fi["bz"] ** 2)
+    if P.dpp_wave:   # calc_dpp_wave_scattering
+        va = b / np.sqrt(Fi["rho"])
+        dp_dt = dp_dt + ((8 * p / (27 * kpara)) if P.momentum_dependency == 1 else (4 * p / (9 * kpara))) * va ** 2
+        dpp = dpp + (p * va) ** 2 / (9 * kpara)
+    if P.dpp_shear:  # push_particle_1d's shear tensor (:3048-3053) + calc_dpp_flow_shear
+        divv = Fi["dvx"]
+        sxx, syy, szz = Fi["dvx"] - divv / 3, -divv / 3, -divv / 3
+        if P.weak_scattering:
+            bbs = (sxx * Fi["bx"] ** 2 + syy * Fi["by"] ** 2 + szz * Fi["bz"] ** 2) * (1.0 / b) * (1.0 / b)
+            gsh = bbs ** 2 / 5
+        else:
+            gsh = 2 * (sxx ** 2 + syy ** 2 + szz ** 2) / 15
+        on = gsh > 0
+        dp_dt = np.where(on, dp_dt + (2 + P.pindex) * gsh * P.tau0 * 1.0 * p ** (P.pindex - 1) * P.p0 ** (2.0 - P.pindex), dp_dt)
+        dpp = np.where(on, dpp + gsh * P.tau0 * 1.0 * p ** P.pindex * P.p0 ** (2.0 - P.pindex), dpp)
     s = np.where(skperp > 0, skperp, skpara)
     dt = np.minimum(np.minimum((0.5 * P.dx / skpara) ** 2, (s / dx_dt) ** 2),
                     float(np.float32(0.1)) * p / np.abs(dp_dt))
@@ -355,13 +375,15 @@ def _np_step_1d(P, frames, before, u, t0, dtf):
     sdt = np.sqrt(dt)
     ran1 = (2.0 * u[:, 0] - 1.0) * np.sqrt(3.0)
     xn = x + (dx_dt * dt + ran1 * skpara * sdt)
-    pn = p + dp_dt * dt  # dpp = 0: the momentum noise term is exactly zero
+    pn = p + (dp_dt * dt + (2.0 * u[:, 1] - 1.0) * np.sqrt(3.0) * np.sqrt(2 * dpp) * sdt)
     pn = np.maximum(pn, 0.25 * P.p0)  # particle_module.f90:3105-3109
     return xn, pn, t + dt, dt
 
 
-def test_1d_step_matches_numpy_restatement():
-    w, P, frames, _ = make_case("s1", grid=256, nptl=300)
+@pytest.mark.parametrize("cli", [None, dict(dpp_wave=1, dpp_shear=1), dict(dpp_wave=1, dpp_shear=1, weak_scattering=0),
+                                 dict(nlgc=1, kperp_kpara=0.05), dict(nlgc=1, kperp_kpara=0.05, dpp_wave=1, dpp_shear=1)])
+def test_1d_step_matches_numpy_restatement(cli):
+    w, P, frames, _ = make_case("s1", grid=256, nptl=300, cli=cli)
     assert P.ndim == 1 and frames[0].shape == (260, 8)
     P.rng_mode = RNG_TABLE
     o = Oracle(P, w.nptl_max)
@@ -376,7 +398,7 @@ def test_1d_step_matches_numpy_restatement():
     x, p, t, dt = _np_step_1d(P, frames[:2], before, u[before["tag_injected"], 0], 0.0, w.dt_out)
     for name, ref in (("x", x), ("p", p), ("t", t), ("dt", dt)):
         err = np.abs(after[name] - ref) / np.maximum(np.abs(ref), 1.0 if name == "x" else 1e-300)
-        assert err.max() < 2e-15, (name, err.max())
+        assert err.max() < 4e-15, (name, err.max())
     assert np.array_equal(after["y"], before["y"]) and np.array_equal(after["z"], before["z"])
 
 
