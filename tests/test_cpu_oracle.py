@@ -1684,3 +1684,52 @@ def test_focused_transport_with_nlgc_matches_numpy_restatement(maps_on):
     for name, ref in (("x", x), ("y", y), ("p", p), ("v", v), ("mu", mu), ("t", t), ("dt", dt)):
         scale = np.maximum(np.abs(ref), 1.0 if name in "xy" else 1e-300)
         assert (np.abs(after[name] - ref) / scale).max() < 1e-13, name
+
+
+def test_large_jz_injection_matches_python_restatement():
+    """inject_particles_at_large_jz (particle_module.f90:785-905) value for value: per particle a rejection
+    loop over uniform positions in the WHOLE domain (three draws per trial; outside the part box counts as a
+    rejection), |jz| = |dby_dx - dbx_dy| interpolated at rt = 0, then mu and inject_one_particle."""
+    w, P, frames, _ = make_case("c1", grid=48, nptl=8)
+    o = Oracle(P, 4000)
+    o.upload_fields(0, frames[0])
+    o.upload_fields(1, frames[1])
+    fa1 = np_step.gradients32(frames[0], P.dx, P.dy)
+    fa2 = np_step.gradients32(frames[1], P.dx, P.dy)
+    jz_grid = np.abs(fa1[2:-2, 2:-2, 8 + 15] - fa1[2:-2, 2:-2, 8 + 13])
+    box = box_of(P)
+    box[0] += 0.2 * P.lx
+    box[4] -= 0.3 * P.ly
+    vmin = float(np.quantile(jz_grid, 0.7))
+    ninj, ncells = o.inject_targeted(1, 300, 1e-6, 1, w.particle_v0, 0.2, 0.1, box, 6.2, False, vmin, 2 * 48 * 48)
+    a = o.download_particles()
+    assert ninj == len(a) and ninj == int(300 * ncells / (2 * 48 * 48)) and ninj > 20
+    key = (P.seed & 0xFFFFFFFF, ((P.seed >> 32) + P.mpi_rank) & 0xFFFFFFFF)
+    mu_max = float(np.float32(0.99))
+    one = lambda v: np.array([v])
+    trials = 0
+    for tag in range(ninj):
+        st = dict(k=0, buf=None)
+
+        def u():
+            if st["k"] % 4 == 0:
+                st["buf"] = philox4x32_10((st["k"] // 4, 0, tag, 0), key)
+            v = st["buf"][st["k"] % 4] / 4294967295.0
+            st["k"] += 1
+            return v
+        jz = -2.0
+        while jz < vmin:
+            trials += 1
+            x = u() * (P.xmax - P.xmin) + P.xmin
+            y = u() * (P.ymax - P.ymin) + P.ymin
+            z = u() * (P.zmax - P.zmin) + P.zmin
+            if box[0] <= x <= box[3] and box[1] <= y <= box[4] and box[2] <= z <= box[5]:
+                F = np_step.interp32(fa1, fa2, P, one(x), one(y), one(0.0))
+                jz = abs(F[0, 8 + 15] - F[0, 8 + 13])
+            else:
+                jz = -3.0
+        mu = mu_max * (2.0 * u() - 1.0)
+        t = 0.2 + u() * 0.1
+        r = a[tag]
+        assert (r["x"], r["y"], r["z"], r["mu"], r["t"], r["p"]) == (x, y, z, mu, t, P.p0), tag
+    assert trials > 2 * ninj            # the rejection loop really rejected
