@@ -1733,3 +1733,92 @@ def test_large_jz_injection_matches_python_restatement():
         r = a[tag]
         assert (r["x"], r["y"], r["z"], r["mu"], r["t"], r["p"]) == (x, y, z, mu, t, P.p0), tag
     assert trials > 2 * ninj            # the rejection loop really rejected
+
+
+def _py_is_selected(tags, split_times_max, origin, tag_inj, tag_spl, nsplit):
+    """is_particle_selected (particle_module.f90:5911-5952); tags: (nptl_tracking, ncols) = Fortran (ncols, n).
+    Returns (selected, lo, hi) with 1-based column indices."""
+    def findloc(vals, v, back=False):
+        idx = np.flatnonzero(vals == v)
+        return 0 if len(idx) == 0 else int(idx[-1 if back else 0]) + 1
+    if nsplit > split_times_max:
+        return False, -1, -1
+    i1 = findloc(tags[:, 0], origin)
+    if i1 <= 0:
+        return False, -1, -1
+    i2 = findloc(tags[:, 0], origin, True)
+    i3 = findloc(tags[i1 - 1:i2, 1], abs(tag_inj))
+    if i3 <= 0:
+        return False, -1, -1
+    i4 = findloc(tags[i1 - 1:i2, 1], abs(tag_inj), True)
+    i3, i4 = i3 + i1 - 1, i4 + i1 - 1
+    if nsplit > 0:
+        i5 = findloc(tags[i3 - 1:i4, nsplit + 1], abs(tag_spl))
+        if i5 <= 0:
+            return False, -1, -1
+        i6 = findloc(tags[i3 - 1:i4, nsplit + 1], abs(tag_spl), True)
+        return True, i5 + i3 - 1, i6 + i3 - 1
+    return True, i3, i4
+
+
+def test_split_of_tracked_particles_matches_python_restatement():
+    """split_particle's tracking branch (particle_module.f90:5452-5473): the child of a tracked particle gets
+    tag_splitted - 2**(split_times - 1); parent and child each keep their negative tag only while the tag
+    table still lists them at their new split level, and are sampled into particles_tracked when
+    nsteps_pushed == 0."""
+    w, P, _, _ = make_case("c1", grid=16, nptl=8, conf=dict(dt_min_rel=1e-2))
+    tags = np.array([[0, 5, 1, 3], [0, 5, 2, 2], [0, 9, 1, 1], [1, 5, 1, 1]], dtype=np.int32)
+    ptl = np.zeros(6, dtype=PARTICLE_DTYPE)
+    ptl["origin"] = [0, 0, 0, 0, 1, 0]
+    ptl["tag_injected"] = [-5, -9, 7, -5, 5, -9]
+    ptl["tag_splitted"] = [-1, -1, 1, -1, 1, -1]
+    ptl["split_times"] = [0, 0, 0, 1, 0, 2]
+    ptl["p"] = P.p0 * np.array([3.0, 3.0, 3.0, 5.0, 3.0, 1.0])     # the last one is below its threshold
+    ptl["weight"] = 0.5 ** ptl["split_times"].astype(float)
+    ptl["count_flag"] = 1
+    ptl["nsteps_pushed"] = [0, 0, 0, 0, 0, 0]
+    ptl["nsteps_tracked"] = [3, 3, 0, 3, 0, 3]
+    ptl["x"] = np.arange(6) * 0.1
+    o = Oracle(P, 32)
+    o.init_tracking(tags, 10)
+    o.upload_particles(ptl)
+    o.split(2.0, 2.0, 10)
+    got = o.download_particles()
+    rec = o.download_tracked()
+    # ---- restatement ----
+    split_times_max = tags.shape[1] - 2
+    out = [dict((n, ptl[n][i].item()) for n in PARTICLE_DTYPE.names) for i in range(len(ptl))]
+    want_rec = {}
+    for i in range(len(ptl)):
+        q = dict(out[i])
+        if not (q["p"] > 2.0 * P.p0 * 2.0 ** q["split_times"] and q["p"] <= P.pmax):
+            continue
+        q["weight"] = float(np.float32(0.5) ** np.float32(1.0 + q["split_times"]))
+        q["split_times"] += 1
+        child = dict(q)
+        if q["tag_splitted"] < 0:
+            child["tag_splitted"] = q["tag_splitted"] - 2 ** (q["split_times"] - 1)
+            for who in (child, q):
+                sel, lo, hi = _py_is_selected(tags, split_times_max, who["origin"], who["tag_injected"],
+                                              who["tag_splitted"], who["split_times"])
+                if sel:
+                    if q["nsteps_pushed"] == 0:
+                        who["nsteps_tracked"] += 1
+                        for c in range(lo, hi + 1):
+                            want_rec[(c - 1, who["nsteps_tracked"] - 1)] = dict(who)
+                else:
+                    who["tag_splitted"] = -who["tag_splitted"]
+        else:
+            child["tag_splitted"] = q["tag_splitted"] + 2 ** (q["split_times"] - 1)
+        out.append(child)
+        out[i] = q
+    assert len(got) == len(out) == 11
+    for name in ("origin", "tag_injected", "tag_splitted", "split_times", "weight", "p", "x", "nsteps_tracked"):
+        assert [g.item() for g in got[name]] == [q[name] for q in out], name
+    # who is still tracked: A and its child, B only (its child is not in the table), D's child only
+    assert [q["tag_splitted"] for q in out] == [-1, -1, 1, 1, 1, -1, -2, 2, 2, -3, 2]
+    filled = {(r, c) for r in range(rec.shape[0]) for c in range(rec.shape[1]) if rec[r, c]["tag_splitted"] != 0}
+    assert filled == set(want_rec)
+    for (r, c), q in want_rec.items():
+        for name in ("tag_injected", "tag_splitted", "split_times", "nsteps_tracked", "x", "weight"):
+            assert rec[r, c][name].item() == q[name], (r, c, name)
