@@ -53,3 +53,34 @@ def test_random_switch_combination(trial, strict):
         assert_particles_close(g.download_particles(), o.download_particles(), 1e-12 * max(1, nsteps // 4),
                                f"{geom} {conf} {cli} strict={strict} n={nsteps}", frac_outliers=0.004)
     g.close()
+
+
+def test_split_of_tracked_particles_hand_made_population():
+    """GPU twin of tests/test_cpu_oracle.py::test_split_of_tracked_particles_matches_python_restatement: the same
+    six particles and tag table through gpat_init_tracking + gpat_split, against the oracle, field by field."""
+    from stochastic_parker_b200.abi import PARTICLE_DTYPE
+    w, P, _, _ = make_case("c1", grid=16, nptl=8, conf=dict(dt_min_rel=1e-2))
+    tags = np.array([[0, 5, 1, 3], [0, 5, 2, 2], [0, 9, 1, 1], [1, 5, 1, 1]], dtype=np.int32)
+    ptl = np.zeros(6, dtype=PARTICLE_DTYPE)
+    ptl["origin"] = [0, 0, 0, 0, 1, 0]
+    ptl["tag_injected"] = [-5, -9, 7, -5, 5, -9]
+    ptl["tag_splitted"] = [-1, -1, 1, -1, 1, -1]
+    ptl["split_times"] = [0, 0, 0, 1, 0, 2]
+    ptl["p"] = P.p0 * np.array([3.0, 3.0, 3.0, 5.0, 3.0, 1.0])
+    ptl["weight"] = 0.5 ** ptl["split_times"].astype(float)
+    ptl["count_flag"] = 1
+    ptl["nsteps_tracked"] = [3, 3, 0, 3, 0, 3]
+    ptl["x"] = np.arange(6) * 0.1
+    g, o = GpatSim(P, 32), Oracle(P, 32)
+    for s in (g, o):
+        s.init_tracking(tags, 10)
+        s.upload_particles(ptl)
+        s.split(2.0, 2.0, 10)
+    a, b = g.download_particles(), o.download_particles()
+    assert len(a) == len(b) == 11
+    for name in PARTICLE_DTYPE.names:
+        assert np.array_equal(a[name], b[name]), name
+    ra, rb = g.download_tracked(), o.download_tracked()
+    for name in PARTICLE_DTYPE.names:
+        assert np.array_equal(ra[name], rb[name]), name
+    g.close()
