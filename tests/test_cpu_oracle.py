@@ -1686,27 +1686,40 @@ def test_focused_transport_with_nlgc_matches_numpy_restatement(maps_on):
         assert (np.abs(after[name] - ref) / scale).max() < 1e-13, name
 
 
-def test_large_jz_injection_matches_python_restatement():
-    """inject_particles_at_large_jz (particle_module.f90:785-905) value for value: per particle a rejection
-    loop over uniform positions in the WHOLE domain (three draws per trial; outside the part box counts as a
-    rejection), |jz| = |dby_dx - dbx_dy| interpolated at rt = 0, then mu and inject_one_particle."""
+@pytest.mark.parametrize("mode", [1, 2, 4, 5])
+def test_targeted_injection_matches_python_restatement(mode):
+    """inject_particles_at_large_jz / _absj / _divv / _rho (particle_module.f90:785-905, 919-1061, 1250-1341,
+    1356-1468) value for value: per particle a rejection loop over uniform positions in the WHOLE domain (three
+    draws per trial; outside the part box counts as a rejection), the criterion interpolated at rt = 0, then mu
+    and inject_one_particle."""
     w, P, frames, _ = make_case("c1", grid=48, nptl=8)
     o = Oracle(P, 4000)
     o.upload_fields(0, frames[0])
     o.upload_fields(1, frames[1])
     fa1 = np_step.gradients32(frames[0], P.dx, P.dy)
     fa2 = np_step.gradients32(frames[1], P.dx, P.dy)
-    jz_grid = np.abs(fa1[2:-2, 2:-2, 8 + 15] - fa1[2:-2, 2:-2, 8 + 13])
+    g = lambda F, k: F[..., 8 + k - 1]            # fields(nfields + k)
+
+    def criterion(F):                             # the quantity the loop compares with its threshold
+        if mode == 1:
+            return np.abs(g(F, 16) - g(F, 14))
+        if mode == 2:
+            return np.sqrt((g(F, 18) - g(F, 20)) ** 2 + (g(F, 19) - g(F, 15)) ** 2 + (g(F, 14) - g(F, 16)) ** 2)
+        if mode == 4:
+            return -(g(F, 1) + g(F, 5))
+        return F[..., 3]
+    grid_vals = criterion(fa1[2:-2, 2:-2].astype(np.float64))
     box = box_of(P)
     box[0] += 0.2 * P.lx
     box[4] -= 0.3 * P.ly
-    vmin = float(np.quantile(jz_grid, 0.7))
-    ninj, ncells = o.inject_targeted(1, 300, 1e-6, 1, w.particle_v0, 0.2, 0.1, box, 6.2, False, vmin, 2 * 48 * 48)
+    vmin = float(np.quantile(grid_vals, 0.7))
+    ninj, ncells = o.inject_targeted(mode, 300, 1e-6, 1, w.particle_v0, 0.2, 0.1, box, 6.2, False, vmin, 2 * 48 * 48)
     a = o.download_particles()
-    assert ninj == len(a) and ninj == int(300 * ncells / (2 * 48 * 48)) and ninj > 20
+    assert ninj == len(a) and ninj == int(300 * ncells / (2 * 48 * 48)) and ninj > 10
     key = (P.seed & 0xFFFFFFFF, ((P.seed >> 32) + P.mpi_rank) & 0xFFFFFFFF)
     mu_max = float(np.float32(0.99))
     one = lambda v: np.array([v])
+    outside = {1: -3.0, 2: -3.0, 4: -3.0, 5: 0.0}[mode]     # divv = 3.0 outside the box, compared as -divv
     trials = 0
     for tag in range(ninj):
         st = dict(k=0, buf=None)
@@ -1717,17 +1730,16 @@ def test_large_jz_injection_matches_python_restatement():
             v = st["buf"][st["k"] % 4] / 4294967295.0
             st["k"] += 1
             return v
-        jz = -2.0
-        while jz < vmin:
+        crit = {1: -2.0, 2: -2.0, 4: -2.0, 5: 0.0}[mode]     # jz = absj = -2, divv = +2, rho = 0 before the loop
+        while crit < vmin:
             trials += 1
             x = u() * (P.xmax - P.xmin) + P.xmin
             y = u() * (P.ymax - P.ymin) + P.ymin
             z = u() * (P.zmax - P.zmin) + P.zmin
             if box[0] <= x <= box[3] and box[1] <= y <= box[4] and box[2] <= z <= box[5]:
-                F = np_step.interp32(fa1, fa2, P, one(x), one(y), one(0.0))
-                jz = abs(F[0, 8 + 15] - F[0, 8 + 13])
+                crit = float(criterion(np_step.interp32(fa1, fa2, P, one(x), one(y), one(0.0)))[0])
             else:
-                jz = -3.0
+                crit = outside
         mu = mu_max * (2.0 * u() - 1.0)
         t = 0.2 + u() * 0.1
         r = a[tag]
