@@ -2496,3 +2496,14 @@ int orc_num_threads(void)
     return 1;
 #endif
 }
+
+/* bench.py's reference arm: torchrun exports OMP_NUM_THREADS=1 to every rank, which would time the
+ * CPU path on one core; the arm asks for the host's cores explicitly. */
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

@@ -261,6 +261,10 @@ class Oracle:
     def num_threads(self) -> int:
         return int(self.lib.orc_num_threads())
 
+    def set_num_threads(self, n: int):
+        """OpenMP team size of the mover (bench.py's reference arm: all host cores, whatever OMP_NUM_THREADS says)"""
+        self.lib.orc_set_num_threads(C.c_int(int(n)))
+
 
 def philox4x32_10(ctr, key):
     lib = _load(False)

@@ -1,0 +1,292 @@
+"""The oracle pinned to the reference's OWN Fortran.
+
+tests/golden/ref_f90/<case>.npz were computed by executing the unmodified procedures of
+/root/reference/src/modules/*.f90 (inject_particles_spatial_uniform, inject_one_particle, particle_mover,
+particle_mover_one_cycle, particle_boundary_condition, get_interp_paramters, interp_fields,
+calc_fields_gradients, calc_spatial_diffusion_coefficients[_nlgc], calc_dpp_*, every push_particle_*,
+remove_particles, split_particle, calc_particle_distributions, calc_escaped_distributions, quick_check,
+get_pmax_global, init_particle_distributions ...) with oracle/f90/f90run.py -- there is no Fortran compiler in
+this image or on the B200 box (profiles/r02a_fortran_probe.log).  Three layers:
+
+  1. oracle/gpat_oracle.c == golden, BIT FOR BIT, for every case (always runs; no /root/reference needed);
+  2. the golden files are what the reference computes: regenerated live from /root/reference for a subset of
+     the cases (skipped where the reference tree is absent, e.g. on the GPU box);
+  3. the translator obeys Fortran's rules: literal kinds, mixed-kind promotion, integer division, real**integer,
+     assignment conversion, derived-type copies, array sections and bounds, intent(out) copy-back, DO semantics --
+     checked on small Fortran sources written for the purpose.
+"""
+import os
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from helpers import REF_GOLDEN_CASES, assert_particles_identical, golden_collect, unpack_sparse
+from oracle.oracle import Oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle", "f90"))
+import f90run as F  # noqa: E402
+import refsim  # noqa: E402
+
+GOLD = os.path.join(HERE, "golden", "ref_f90")
+LIVE_CASES = ["c1_2d", "c3_shock_open", "c4_dpp_wave_shear", "c5_3d", "s1_shock_1d"]
+
+
+def assert_same_as_golden(got, z, what):
+    """bit-for-bit: float arrays are compared through their bit patterns"""
+    assert sorted(got) == sorted(z.files), (what, set(got) ^ set(z.files))
+    for k in z.files:
+        a, b = np.asarray(got[k]), z[k]
+        if a.dtype.names:
+            assert_particles_identical(a, b, f"{what}:{k}")
+            continue
+        assert a.shape == b.shape, (what, k, a.shape, b.shape)
+        if a.dtype.kind == "f":
+            a, b = np.ascontiguousarray(a, dtype=np.float64).view(np.uint64), np.ascontiguousarray(b, dtype=np.float64).view(np.uint64)
+        bad = np.flatnonzero(a.reshape(-1) != b.reshape(-1))
+        assert len(bad) == 0, f"{what}: {k} differs at {len(bad)} of {a.size} elements, first {bad[:4]}"
+
+
+@pytest.mark.parametrize("name", REF_GOLDEN_CASES)
+def test_oracle_equals_the_reference_golden_bit_for_bit(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    got = golden_collect(lambda P, n: Oracle(P, n), name)
+    assert_same_as_golden(got, z, name)
+    # the run must have exercised what it claims to pin
+    assert int(z["run_steps"]) > 1000 and int(z["steps41_count"]) > 40 * 40
+
+
+def test_golden_runs_cover_escapes_splits_and_every_histogram():
+    tot_escaped = tot_split = 0
+    for name in REF_GOLDEN_CASES:
+        z = np.load(os.path.join(GOLD, name + ".npz"))
+        tot_split += int(z["run_counters_int"][1])
+        tot_escaped += sum(len(z[k]) for k in z.files if k.endswith("escaped_particles"))
+        assert any(k.endswith("flocal1.val") and len(z[k]) for k in z.files), name
+    assert tot_split >= 50 and tot_escaped >= 40
+    z = np.load(os.path.join(GOLD, "c3_shock_open.npz"))
+    assert unpack_sparse(z, "run_f2_fescaped1_x").sum() >= 4 and z["run_f2_fescaped"].sum() >= 4
+
+
+@pytest.mark.skipif(not refsim.available(), reason="/root/reference is not present on this box")
+@pytest.mark.parametrize("name", LIVE_CASES)
+def test_golden_is_what_the_reference_fortran_computes(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    got = golden_collect(lambda P, n: refsim.RefSim(P, n), name)
+    assert_same_as_golden(got, z, name)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the translator itself
+# ---------------------------------------------------------------------------------------------------
+def run_f90(tmp_path, source, proc, *args, module="m"):
+    p = tmp_path / "m.f90"
+    p.write_text(textwrap.dedent(source))
+    prog = F.Program()
+    prog.ext_values.update(real32=4, real64=8)
+    prog.load_file(str(p))
+    prog.init_module_data()
+    return prog, prog.get(module, proc)(*args)
+
+
+HEAD = """
+module m
+    implicit none
+    integer, parameter :: sp = kind(1.0), dp = kind(1.0d0)
+    type pt
+        integer :: n
+        real(dp) :: x
+    end type pt
+    real(dp) :: acc = 0.0_dp
+    type(pt), allocatable, dimension(:) :: arr
+    real(sp), allocatable, dimension(:, :) :: g
+contains
+"""
+
+
+def test_f90run_literal_kinds_and_promotion(tmp_path):
+    src = HEAD + """
+    subroutine s(p, a, b, c, d, e)
+        real(dp), intent(in) :: p
+        real(dp), intent(out) :: a, b, c, d, e
+        integer :: q
+        q = 3
+        a = 0.1 * p                 ! default-real literal: single precision 0.1, promoted
+        b = 0.1_dp * p
+        c = 1.0 / (3 * q) / p       ! real(sp) / integer stays single precision, then promotes
+        d = 2 / 3 + 7 / 2 + (-7) / 2  ! integer division truncates toward zero
+        e = 0.5**(1.0 + q)          ! real(sp) ** real(sp)
+    end subroutine s
+    end module m
+    """
+    _, (a, b, c, d, e) = run_f90(tmp_path, src, "s", np.float64(3.0), None, None, None, None, None)
+    assert a == np.float64(np.float32(0.1)) * 3.0 and a != 0.1 * 3.0
+    assert b == np.float64(0.1) * 3.0
+    assert c == np.float64(np.float32(1.0) / np.float32(9.0)) / 3.0
+    assert d == 0.0 and isinstance(d, np.float64)
+    assert e == 0.0625
+
+
+def test_f90run_integer_powers_follow_libgcc_powi(tmp_path):
+    src = HEAD + """
+    subroutine s(x, n, a, b, c)
+        real(dp), intent(in) :: x
+        integer, intent(in) :: n
+        real(dp), intent(out) :: a, b, c
+        a = x**n
+        b = x**(-2)
+        c = x**2.0_dp
+    end subroutine s
+    end module m
+    """
+    x = np.float64(1.0000001234567)
+    _, (a, b, c) = run_f90(tmp_path, src, "s", x, 5, None, None, None)
+    x2 = x * x
+    assert a == x * (x2 * x2)            # square-and-multiply: r = x; a = x^2; a = x^4; r = r * a
+    assert b == 1.0 / (x * x)
+    import math
+    assert c == math.pow(x, 2.0)
+
+
+def test_f90run_assignment_converts_and_structs_copy(tmp_path):
+    src = HEAD + """
+    subroutine s(r, i, y)
+        real(dp), intent(in) :: r
+        integer, intent(out) :: i
+        real(dp), intent(out) :: y
+        type(pt) :: a, b
+        real(sp) :: h
+        i = r                ! truncation toward zero
+        h = r                ! rounding to single
+        a%n = 1
+        a%x = h
+        b = a                ! a copy, not an alias
+        b%x = 2.0
+        allocate(arr(3))
+        arr(2) = a
+        a%n = 7
+        y = arr(2)%x + b%x + arr(2)%n
+    end subroutine s
+    end module m
+    """
+    _, (i, y) = run_f90(tmp_path, src, "s", np.float64(-2.7), None, None)
+    assert i == -2 and isinstance(i, int)
+    assert y == np.float64(np.float32(-2.7)) + 2.0 + 1
+
+
+def test_f90run_sections_bounds_and_mixed_kind_array_arithmetic(tmp_path):
+    src = HEAD + """
+    subroutine s(scale, out)
+        real(dp), intent(in) :: scale
+        real(dp), dimension(4), intent(out) :: out
+        integer :: i, j
+        allocate(g(4, -1:6))
+        do j = -1, 6
+            do i = 1, 4
+                g(i, j) = 0.1 * i + j
+            enddo
+        enddo
+        ! strided section on the left, single-precision difference times a double on the right
+        g(2::2, 0:5) = (g(:2, 1:6) - g(:2, -1:4)) * scale
+        out(1) = g(2, 0)
+        out(2) = g(4, 5)
+        out(3) = ubound(g, 2) + lbound(g, 2)
+        out(4) = sum(g(1, :))
+    end subroutine s
+    end module m
+    """
+    out = F.FArray.alloc(np.float64, [(1, 4)])
+    run_f90(tmp_path, src, "s", np.float64(1.0) / 3.0, out)
+    f4 = np.float32
+    g = lambda i, j: f4(f4(f4(0.1) * f4(i)) + f4(j))  # noqa: E731
+    assert out[1] == f4(np.float64(g(1, 1) - g(1, -1)) * (np.float64(1.0) / 3.0))
+    assert out[2] == f4(np.float64(g(2, 6) - g(2, 4)) * (np.float64(1.0) / 3.0))
+    assert out[3] == 5.0
+    s = f4(0)
+    for j in range(-1, 7):
+        s = f4(s + g(1, j))
+    assert out[4] == s
+
+
+def test_f90run_calls_copy_back_and_do_loops(tmp_path):
+    src = HEAD + """
+    subroutine bump(x, k, t)
+        real(dp), intent(inout) :: x
+        integer, intent(out) :: k
+        type(pt), intent(inout) :: t
+        x = x + 1.0
+        k = 5
+        t%n = t%n + 1
+        acc = acc + x
+    end subroutine bump
+
+    function twice(v) result(w)
+        real(dp), intent(in) :: v
+        real(dp) :: w
+        w = 2 * v
+    end function twice
+
+    subroutine s(res)
+        real(dp), dimension(6), intent(out) :: res
+        real(dp) :: x
+        integer :: k, i, n
+        type(pt) :: t
+        t%n = 0
+        x = 1.0
+        call bump(x, k, t)
+        call bump(res(2), k, t)          ! array element as an intent(inout) actual
+        res(1) = x
+        res(3) = k + t%n
+        n = 0
+        do i = 10, 1, -3
+            if (i == 4) cycle
+            n = n + i
+        enddo
+        res(4) = n + 100 * i             ! i = -2 after completion
+        do while (n > 0)
+            n = n - 7
+            if (n < 5) exit
+        enddo
+        res(5) = n
+        res(6) = twice(acc)
+    end subroutine s
+    end module m
+    """
+    res = F.FArray.alloc(np.float64, [(1, 6)])
+    res.a[:] = 0.0
+    run_f90(tmp_path, src, "s", res)
+    assert list(res.a) == [2.0, 1.0, 7.0, 10 + 7 + 1 + 100 * -2, 4.0, 2 * (2.0 + 1.0)]
+
+
+def test_f90run_reading_an_unassigned_variable_is_an_error(tmp_path):
+    src = HEAD + """
+    subroutine s(y)
+        real(dp), intent(out) :: y
+        real(dp) :: never_set
+        y = never_set * 2.0
+    end subroutine s
+    end module m
+    """
+    with pytest.raises(RuntimeError, match="before assigning"):
+        run_f90(tmp_path, src, "s", None)
+
+
+def test_f90run_cpp_conditionals_and_continuations(tmp_path):
+    src = HEAD + """
+    subroutine s(y)
+        integer, intent(out) :: y
+        y = 1
+#if (defined USE_OPENMP)
+        y = 2
+#endif
+        !$OMP PARALLEL
+        y = y + &
+            10 * &   ! a comment after the continuation mark
+            3
+    end subroutine s
+    end module m
+    """
+    _, (y,) = run_f90(tmp_path, src, "s", None)
+    assert y == 31

@@ -130,40 +130,7 @@ def test_1d_gradients_and_interp_bit_exact():
     g.close()
 
 
-CASES = {
-    "c1_2d": dict(key="c1", grid=64),
-    "c1_2d_no_time_interp": dict(key="c1", grid=64, cli=dict(time_interp=0)),
-    "c1_2d_check_drift": dict(key="c1", grid=64, cli=dict(check_drift_2d=1)),
-    "c1_2d_nlgc": dict(key="c1", grid=64, conf=dict(dt_min_rel=1e-3), cli=dict(nlgc=1, kperp_kpara=0.05)),
-    "c1_2d_acc_region": dict(key="c1", grid=64, conf=dict(acc_region_flag=1)),
-    "c1_2d_include_3rd": dict(key="c1", grid=64, cli=dict(include_3rd_dim=1)),
-    "c2_flare_open": dict(key="c2", grid=64),
-    "c3_shock_open": dict(key="c3", grid=64),
-    "c4_dpp_wave_shear": dict(key="c4", grid=64),
-    "c4_dpp_strong_kret0": dict(key="c4", grid=64, conf=dict(kret=0.0), cli=dict(weak_scattering=0)),
-    "c1_2d_focused_transport": dict(key="c1", grid=64, conf=dict(dt_min_rel=1e-4),
-                                    cli=dict(focused_transport=1, duu_init=5.0)),
-    "c4_2d_focused_transport_dpp": dict(key="c4", grid=64, conf=dict(dt_min_rel=1e-3),
-                                        cli=dict(focused_transport=1, duu_init=5.0, nlgc=1, kperp_kpara=0.05)),
-    "c1_2d_ft_include_3rd": dict(key="c1", grid=64, conf=dict(dt_min_rel=1e-3),
-                                 cli=dict(focused_transport=1, duu_init=5.0, include_3rd_dim=1)),
-    "c5_3d_ft": dict(key="c5", grid=32, conf=dict(dt_min_rel=1e-3), cli=dict(focused_transport=1, duu_init=5.0)),
-    "s1_shock_1d": dict(key="s1", grid=256),
-    "s1_shock_1d_dpp_nlgc": dict(key="s1", grid=256, conf=dict(dt_min_rel=1e-3),
-                                 cli=dict(dpp_wave=1, dpp_shear=1, nlgc=1, kperp_kpara=0.05)),
-    "c5_3d": dict(key="c5", grid=32),
-    "c5_3d_acc_surfaces_union": dict(key="c5", grid=32, conf=dict(acc_region_flag=1),
-                                     cli=dict(acc_by_surface=1, surface_norm1="+z", surface2_existed=1,
-                                              surface_norm2="-y")),
-    "c5_3d_acc_surface_no_time_interp": dict(key="c5", grid=32, conf=dict(acc_region_flag=1),
-                                             cli=dict(acc_by_surface=1, surface_norm1="-x", time_interp=0)),
-    "c5_3d_ft_acc_surfaces_intersection": dict(key="c5", grid=32, conf=dict(acc_region_flag=1, dt_min_rel=1e-3),
-                                               cli=dict(focused_transport=1, duu_init=5.0, acc_by_surface=1,
-                                                        surface_norm1="+y", surface2_existed=1,
-                                                        surface_norm2="-z", is_intersection=1)),
-    "c5_3d_dpp_nlgc": dict(key="c5", grid=32, conf=dict(kpara0=0.02, dt_min_rel=1e-3),
-                           cli=dict(dpp_wave=1, dpp_shear=1, nlgc=1, kperp_kpara=0.05)),
-}
+from helpers import CASES  # noqa: E402  (shared with the reference-golden tests)
 
 
 def _inject(sims, w, P, n, t0=0.0, dist_flag=1):
