@@ -291,6 +291,20 @@ def _raw(x):
     return x.a if isinstance(x, FArray) else x
 
 
+def realloc_assign(cur, val, dtype):
+    """whole-array assignment to an ALLOCATABLE array (Fortran 2003 semantics)"""
+    raw = val.a if isinstance(val, FArray) else val
+    if isinstance(raw, np.ndarray) and (cur is None or cur.a.shape != raw.shape):
+        lb = val.lb if isinstance(val, FArray) else (1,) * raw.ndim
+        new = FArray(np.empty(raw.shape, dtype=dtype, order="F"), lb)
+        new.assign(val)
+        return new
+    if cur is None:
+        raise RuntimeError("scalar assigned to an unallocated array")
+    cur.assign(val)
+    return cur
+
+
 class FStruct:
     """Base of generated derived-type classes.  _fields: name -> converter."""
     __slots__ = ()
@@ -534,6 +548,27 @@ def i_dot_product(a, b):
     return s
 
 
+def i_findloc(array, value, dim=None, mask=None, kind=None, back=False):
+    a = _raw(array)
+    if a.ndim != 1:
+        raise NotImplementedError("findloc of a rank > 1 array")
+    hit = np.flatnonzero(a == value)
+    if len(hit) == 0:
+        return 0
+    return int(hit[-1] if back else hit[0]) + 1
+
+
+def i_maxloc(array, dim=None, mask=None, kind=None, back=False):
+    """first location of the maximum (1-based, relative to the section: lower bound 1)"""
+    a = _raw(array)
+    if dim is None:
+        if a.ndim != 1:
+            raise NotImplementedError("maxloc without dim on a rank > 1 array")
+        return np.array([int(np.argmax(a)) + 1], dtype=np.int64)
+    r = np.argmax(a, axis=dim - 1) + 1   # numpy returns the first occurrence, like Fortran without back=
+    return int(r) if a.ndim == 1 else r.astype(np.int64)
+
+
 def i_merge(t, f, mask):
     return t if mask else f
 
@@ -576,7 +611,7 @@ INTRINSICS = {
     "mod": i_mod, "modulo": i_modulo, "sign": i_sign, "epsilon": i_epsilon, "huge": i_huge, "tiny": i_tiny,
     "sum": i_sum, "maxval": i_maxval, "minval": i_minval, "size": i_size, "ubound": i_ubound,
     "lbound": i_lbound, "dot_product": i_dot_product, "merge": i_merge, "allocated": i_allocated,
-    "present": i_present, "trim": i_trim, "kind": i_kind,
+    "present": i_present, "trim": i_trim, "kind": i_kind, "findloc": i_findloc, "maxloc": i_maxloc,
 }
 for _n in ("sqrt", "exp", "log", "log10", "sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", "erf"):
     INTRINSICS[_n] = _mk_unary(_n)
@@ -951,7 +986,7 @@ class Program:
         self.glob = {"f4": f4, "f8": f8, "f_div": f_div, "f_pow": f_pow, "DoRange": DoRange, "FArray": FArray,
                      "Undefined": Undefined, "cv_int": cv_int, "cv_r4": cv_r4, "cv_r8": cv_r8, "cv_bool": cv_bool,
                      "cv_any": cv_any, "cv_struct": cv_struct, "I": INTRINSICS, "i_arrcons": i_arrcons,
-                     "FortranStop": FortranStop, "np": np, "_prog": self}
+                     "FortranStop": FortranStop, "np": np, "_prog": self, "realloc_assign": realloc_assign}
 
     def const(self, value):
         """pooled literal: built once, referenced by name from the generated code"""
@@ -1446,7 +1481,23 @@ class ExprCompiler:
                         args = self.map_keywords(info, pos, kw)
                         code = f"{code}({', '.join(args)})"
                         if info.kind == "function" and info.out_scalars:
-                            pass  # value-result of functions is not copied back (not needed on this path)
+                            # a function that also sets scalar dummies returns (result, out1, ...): copy the
+                            # outs back into the actuals (local scalars only) inside the expression
+                            self.prog._tmp = getattr(self.prog, "_tmp", 0) + 1
+                            t = f"_t{self.prog._tmp}"
+                            parts = [f"({t} := {code})"]
+                            for k, ai in enumerate(info.out_scalars):
+                                src = args[ai] if ai < len(args) else "None"
+                                m = re.fullmatch(r"v_(\w+)", src)
+                                if m and m.group(1) in self.scope.locals:
+                                    conv = _CONV.get(self.scope.locals[m.group(1)].base, "cv_any")
+                                    parts.append(f"({src} := {conv}({t}[{k + 1}]))")
+                                elif src != "None" and info.decls[info.args[ai]].intent != "in":
+                                    if not re.fullmatch(r"[\w.()\[\]' ,+-]*", src) or "v_" in src or "M_" in src:
+                                        raise NotImplementedError(
+                                            f"function {info.name}: actual {src} of a non-intent(in) scalar dummy")
+                            parts.append(f"{t}[0]")
+                            code = "(" + ", ".join(parts) + ")[-1]"
                     else:
                         args = pos + [f"{k}={c}" for k, c in kw.items()]
                         code = f"{code}({', '.join(args)})"
@@ -1500,6 +1551,8 @@ class ProcCompiler:
     def ret_stmt(self):
         p = self.proc
         if p.kind == "function":
+            if p.out_scalars:
+                return f"return (v_{p.result}, " + "".join(f"v_{p.args[i]}, " for i in p.out_scalars) + ")"
             return f"return v_{p.result}"
         return "return (" + "".join(f"v_{p.args[i]}, " for i in p.out_scalars) + ")"
 
@@ -1820,7 +1873,15 @@ class ProcCompiler:
                 raise NameError(f"assignment to unknown variable {name}")
             ts, base, is_local = self.prog.modules[sym[1]].decls[sym[2]], f"M_{sym[1]}.{sym[2]}", False
         if not parts:
-            if ts.is_array:
+            if ts.is_array and ts.allocatable:
+                # Fortran 2003 (re)allocation on assignment, gfortran's default: a shape mismatch gives the
+                # left-hand side the shape of the right-hand side, lower bounds 1 for an expression
+                dt = {"int": "np.int64", "r4": "np.float32", "r8": "np.float64", "bool": "bool"}.get(ts.base, "object")
+                if is_local:
+                    self.emit(f"{base} = realloc_assign({base}, {rhs_code}, {dt})")
+                else:
+                    self.emit(f"object.__setattr__(M_{sym[1]}, {sym[2]!r}, realloc_assign({base}, {rhs_code}, {dt}))")
+            elif ts.is_array:
                 self.emit(f"{base}.assign({rhs_code})")
             elif is_local:
                 conv = _CONV.get(ts.base, "cv_struct")

@@ -104,6 +104,14 @@ class RefSim:
             return (send,)
         E["mpi_reduce"] = mpi_reduce
         self.prog.ext_out["mpi_reduce"] = [1]
+
+        def mpi_allreduce(send, recv, count, dtype, op, comm, ierr):
+            if isinstance(send, F.FArray):
+                recv.assign(send)
+                return (None,)
+            return (send,)
+        E["mpi_allreduce"] = mpi_allreduce
+        self.prog.ext_out["mpi_allreduce"] = [1]
         E["omp_get_thread_num"] = lambda: 0
         E["omp_get_num_threads"] = lambda: 1
         E["__write__"] = lambda unit, items: self.written.append((unit, items))
@@ -188,6 +196,8 @@ class RefSim:
         self.call("simulation_setup_module", "set_field_configuration", int(P.ndim))
         self.call("simulation_setup_module", "set_neighbors")
         self.call("mhd_data_parallel", "init_field_data", int(P.time_interp))
+        self.call("mhd_data_parallel", "init_grid_positions")            # MAIN:198-199
+        self.call("mhd_data_parallel", "set_local_grid_positions", "")
         if not P.time_interp:  # farray2 is referenced by name only when time_interp is true
             pass
         pm = M["particle_module"]
@@ -298,6 +308,44 @@ class RefSim:
         box = F.FArray(np.array(part_box, dtype=np.float64))
         self.call("particle_module", "inject_particles_spatial_uniform", int(nptl), f8(dt), int(dist_flag),
                   f8(particle_v0), 1, box, f8(power_index))
+        for i in range(n0 + 1, int(pm.nptl_current) + 1):
+            pm.ptls[i].padding = 0.0
+
+    INJECTORS = {1: ("inject_particles_at_large_jz", "get_ncells_large_jz"),
+                 2: ("inject_particles_at_large_absj", "get_ncells_large_absj"),
+                 3: ("inject_particles_at_large_db2", "get_ncells_large_db2"),
+                 4: ("inject_particles_at_large_divv", "get_ncells_large_divv"),
+                 5: ("inject_particles_at_large_rho", "get_ncells_large_rho")}
+
+    def inject_targeted(self, mode, nptl, dt, dist_flag, particle_v0, t_frame, dt_mhd, part_box, power_index,
+                        inject_same_nptl=True, vmin=0.0, ncells_norm=1):
+        """inject_particles_at_large_jz / _absj / _db2 / _divv / _rho (PM:785-1468) and their cell counters
+        (MD:2211-2498), whole-field decomposition; returns (nptl_inject, ncells) like the C ABI"""
+        pm = self.M["particle_module"]
+        self._set_tstamps(t_frame, dt_mhd)
+        inj, cnt = self.INJECTORS[mode]
+        box = F.FArray(np.array(part_box, dtype=np.float64))
+        n0 = int(pm.nptl_current)
+        nargs = len(self.prog.modules["mhd_data_parallel"].procs[cnt].args)
+        cargs = (f8(vmin), bool(self.P.spherical_coord), box) if nargs == 3 else (f8(vmin), box)
+        ncells = self.call("mhd_data_parallel", cnt, *cargs)
+        self.call("particle_module", inj, int(nptl), f8(dt), int(dist_flag), f8(particle_v0), 1,
+                  bool(inject_same_nptl), f8(vmin), int(ncells_norm), box, f8(power_index))
+        for i in range(n0 + 1, int(pm.nptl_current) + 1):
+            pm.ptls[i].padding = 0.0
+        return int(pm.nptl_inject), int(ncells)
+
+    def inject_at_shock(self, nptl, dt, dist_flag, particle_v0, t_frame, power_index):
+        """locate_shock_xpos (MD:1988-2006) + inject_particles_at_shock (PM:542-633), as MAIN:451-454 calls them"""
+        pm, md = self.M["particle_module"], self.M["mhd_data_parallel"]
+        if md.__dict__.get("shock_xpos1") is None:
+            self.call("mhd_data_parallel", "init_shock_xpos")
+        ts = self.M["mhd_config_module"].tstamps_mhd
+        ts[1] = f8(t_frame)
+        n0 = int(pm.nptl_current)
+        self.call("mhd_data_parallel", "locate_shock_xpos")
+        self.call("particle_module", "inject_particles_at_shock", int(nptl), f8(dt), int(dist_flag), f8(particle_v0), 1,
+                  f8(power_index))
         for i in range(n0 + 1, int(pm.nptl_current) + 1):
             pm.ptls[i].padding = 0.0
 
@@ -417,6 +465,33 @@ class RefSim:
 
     def reset_escaped(self):
         self.M["particle_module"].nptl_escaped = 0
+
+    # ---- particle tracking (PM:5825-5990; the HDF5 read of init_particle_tracking is the harness's) -------------
+    def init_tracking(self, tags: np.ndarray, nsteps_interval: int):
+        pm = self.M["particle_module"]
+        tags = np.ascontiguousarray(tags, dtype=np.int32)  # (ntrack, ncols) C == (ncols, ntrack) Fortran
+        ntrack, ncols = tags.shape
+        pm.track_particle_flag = True
+        pm.split_times_max, pm.nptl_tracking = ncols - 2, ntrack
+        t = self.prog.allocate("particle_module", "tags_tracking", [(1, ncols), (1, ntrack)])
+        t.a[...] = tags.T
+        # nsteps_tracking_max = ceiling((1.0 / dt_min_rel) / nsteps_interval) + 1      (PM:5876)
+        pm.nsteps_tracking_max = int(math.ceil((np.float32(1.0) / pm.dt_min_rel) / int(nsteps_interval))) + 1
+        self.prog.allocate("particle_module", "particles_tracked", [(1, int(pm.nsteps_tracking_max)), (1, ntrack)])
+        for e in pm.particles_tracked.a.reshape(-1):
+            e.padding = 0.0
+        self.call("particle_module", "reset_tracked_particles")
+
+    def download_tracked(self) -> np.ndarray:
+        pm = self.M["particle_module"]
+        a = pm.particles_tracked.a  # (nsteps_tracking_max, nptl_tracking)
+        out = np.zeros((a.shape[1], a.shape[0]), dtype=PARTICLE_DTYPE)
+        for j in range(a.shape[1]):
+            out[j] = self._to_records(list(a[:, j]))
+        return out
+
+    def reset_tracked(self):
+        self.call("particle_module", "reset_tracked_particles")
 
     def counters(self) -> Counters:
         pm = self.M["particle_module"]

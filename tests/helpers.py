@@ -208,3 +208,21 @@ def golden_collect(make_sim, name):
                             _pack_sparse(out, f + f"fescaped{k + 1}_{ax}", d[ax])
     s.close()
     return out
+
+
+def tracked_split_population(P):
+    """Six hand-made particles + a tag table for split_particle's tracking branch (PM:5452-5473).  Every tracked
+    chain is distinct, as in a real run -- two particles that map to the SAME particles_tracked slot would make the
+    result depend on the serial loop order of the reference, which a parallel split does not reproduce."""
+    tags = np.array([[0, 5, 1, 3], [0, 5, 2, 2], [0, 9, 1, 1], [1, 5, 1, 3]], dtype=np.int32)
+    ptl = np.zeros(6, dtype=PARTICLE_DTYPE)
+    ptl["origin"] = [0, 0, 0, 1, 1, 0]
+    ptl["tag_injected"] = [-5, -9, 7, -5, 6, -9]
+    ptl["tag_splitted"] = [-1, -1, 1, -1, 1, -1]
+    ptl["split_times"] = [0, 0, 0, 1, 0, 2]
+    ptl["p"] = P.p0 * np.array([3.0, 3.0, 3.0, 5.0, 3.0, 1.0])     # the last one is below its threshold
+    ptl["weight"] = 0.5 ** ptl["split_times"].astype(float)
+    ptl["count_flag"] = 1
+    ptl["nsteps_tracked"] = [3, 3, 0, 3, 0, 3]
+    ptl["x"] = np.arange(6) * 0.1
+    return tags, ptl

@@ -1779,18 +1779,8 @@ def test_split_of_tracked_particles_matches_python_restatement():
     table still lists them at their new split level, and are sampled into particles_tracked when
     nsteps_pushed == 0."""
     w, P, _, _ = make_case("c1", grid=16, nptl=8, conf=dict(dt_min_rel=1e-2))
-    tags = np.array([[0, 5, 1, 3], [0, 5, 2, 2], [0, 9, 1, 1], [1, 5, 1, 1]], dtype=np.int32)
-    ptl = np.zeros(6, dtype=PARTICLE_DTYPE)
-    ptl["origin"] = [0, 0, 0, 0, 1, 0]
-    ptl["tag_injected"] = [-5, -9, 7, -5, 5, -9]
-    ptl["tag_splitted"] = [-1, -1, 1, -1, 1, -1]
-    ptl["split_times"] = [0, 0, 0, 1, 0, 2]
-    ptl["p"] = P.p0 * np.array([3.0, 3.0, 3.0, 5.0, 3.0, 1.0])     # the last one is below its threshold
-    ptl["weight"] = 0.5 ** ptl["split_times"].astype(float)
-    ptl["count_flag"] = 1
-    ptl["nsteps_pushed"] = [0, 0, 0, 0, 0, 0]
-    ptl["nsteps_tracked"] = [3, 3, 0, 3, 0, 3]
-    ptl["x"] = np.arange(6) * 0.1
+    from helpers import tracked_split_population
+    tags, ptl = tracked_split_population(P)
     o = Oracle(P, 32)
     o.init_tracking(tags, 10)
     o.upload_particles(ptl)

@@ -290,3 +290,111 @@ def test_f90run_cpp_conditionals_and_continuations(tmp_path):
     """
     _, (y,) = run_f90(tmp_path, src, "s", None)
     assert y == 31
+
+
+@pytest.mark.skipif(not refsim.available(), reason="/root/reference is not present on this box")
+def test_tracked_split_equals_the_reference_split_particle():
+    """split_particle + is_particle_selected (PM:5430-5480, 5920-5959) executed from the reference's source on the
+    hand-made tracked population, against the C oracle: particles and particles_tracked, field by field."""
+    from helpers import make_case, tracked_split_population
+    from stochastic_parker_b200.abi import PARTICLE_DTYPE
+    w, P, _, _ = make_case("c1", grid=16, nptl=8, conf=dict(dt_min_rel=1e-2))
+    tags, ptl = tracked_split_population(P)
+    r, o = refsim.RefSim(P, 32), Oracle(P, 32)
+    for s in (r, o):
+        s.init_tracking(tags, 10)
+        s.upload_particles(ptl)
+        s.split(2.0, 2.0, 10)
+    a, b = r.download_particles(), o.download_particles()
+    assert len(a) == len(b) == 11
+    assert_particles_identical(a, b, "split")
+    ra, rb = r.download_tracked(), o.download_tracked()
+    assert ra.shape == rb.shape
+    for name in PARTICLE_DTYPE.names:
+        if name != "padding":
+            assert np.array_equal(ra[name], rb[name]), name
+    assert (ra["tag_splitted"] != 0).sum() == 4
+
+
+@pytest.mark.skipif(not refsim.available(), reason="/root/reference is not present on this box")
+def test_tracking_run_equals_the_reference():
+    """The reference's two-run tracking workflow (hooks in inject_one_particle PM:434-440, the mover PM:1697-1724 /
+    1806-1812 and split_particle PM:5452-5473, locate_particle / is_particle_selected with findloc) from its own
+    source against the C oracle: final population bit for bit, particles_tracked record by record."""
+    from helpers import make_case
+    from stochastic_parker_b200.abi import PARTICLE_DTYPE
+    from stochastic_parker_b200.driver import run_intervals
+    from stochastic_parker_b200.tracking import select_tags
+    nptl, nsel = 40, 6
+    w, P, frames, ts = make_case("c1", grid=24, nptl=nptl, nframes=3, conf=dict(dt_min_rel=1e-3))
+    P.strict_math = 1
+    kw = dict(nptl=nptl, dist_flag=2, particle_v0=w.particle_v0, inject_new_ptl=False, split_flag=1,
+              pmin_split=1.02, split_ratio=1.02, nsteps_interval=20)
+    a = Oracle(P, 8 * nptl)
+    run_intervals(a, frames, ts, **kw)
+    first = a.download_particles()
+    assert first["split_times"].max() >= 2
+    tags = select_tags(first, np.argsort(first["p"])[-nsel:])
+    out = []
+    for cls in (Oracle, refsim.RefSim):
+        recs = []
+        b = cls(P, 8 * nptl)
+        run_intervals(b, frames, ts, track_tags=tags, on_tracked=lambda tf, rec: recs.append(rec.copy()), **kw)
+        out.append((b.download_particles(), recs))
+    (pa, ra), (pb, rb) = out
+    assert_particles_identical(pa, pb, "tracking run")
+    assert len(ra) == len(rb) == 2
+    for x, y in zip(ra, rb):
+        assert x.shape == y.shape and (x["tag_splitted"] < 0).sum() >= 10
+        for n in PARTICLE_DTYPE.names:
+            if n != "padding":
+                assert np.array_equal(x[n], y[n]), n
+
+
+@pytest.mark.skipif(not refsim.available(), reason="/root/reference is not present on this box")
+@pytest.mark.parametrize("key,grid,mode,same", [("c1", 32, 1, True), ("c1", 32, 2, False), ("c3", 32, 4, True),
+                                                ("c4", 32, 5, True), ("c5", 16, 1, True)])
+def test_targeted_injectors_equal_the_reference(key, grid, mode, same):
+    """inject_particles_at_large_jz / _absj / _divv / _rho + get_ncells_large_* (PM:785-1468, MD:2211-2498) from the
+    reference's source (including get_ncells_large_divv's reallocation-on-assignment shift, MD:2423) against the
+    C oracle: same cell count, same number of particles, same accepted positions and momenta, bit for bit."""
+    from helpers import box_of, make_case
+    w, P, frames, _ = make_case(key, grid=grid, nptl=8)
+    r, o = refsim.RefSim(P, 600), Oracle(P, 600)
+    for s in (r, o):
+        s.upload_fields(0, frames[0])
+        s.upload_fields(1, frames[1])
+    box = box_of(P)
+    box[0] += 0.1 * (P.xmax - P.xmin)
+    box[4] -= 0.15 * (P.ymax - P.ymin)
+    fa = o.get_fields(0).reshape(-1, 32)
+    crit = {1: np.abs(fa[:, 8 + 15] - fa[:, 8 + 13]),
+            2: np.sqrt((fa[:, 8 + 17] - fa[:, 8 + 19]) ** 2 + (fa[:, 8 + 18] - fa[:, 8 + 14]) ** 2
+                       + (fa[:, 8 + 13] - fa[:, 8 + 15]) ** 2),
+            4: -(fa[:, 8] + fa[:, 8 + 4] + (fa[:, 8 + 8] if P.ndim == 3 else 0.0)), 5: fa[:, 3]}[mode]
+    vmin = float(np.quantile(crit, 0.7))
+    rr = r.inject_targeted(mode, 60, 1e-4, 0, w.particle_v0, 0.0, 0.1, box, 6.2, same, vmin, 3 * grid)
+    ro = o.inject_targeted(mode, 60, 1e-4, 0, w.particle_v0, 0.0, 0.1, box, 6.2, same, vmin, 3 * grid)
+    assert rr == ro and rr[0] > 0 and rr[1] > 0
+    assert_particles_identical(r.download_particles(), o.download_particles(), f"{key} mode {mode}")
+
+
+@pytest.mark.skipif(not refsim.available(), reason="/root/reference is not present on this box")
+def test_shock_injection_equals_the_reference_in_1d_and_is_undefined_beyond():
+    """locate_shock_xpos + inject_particles_at_shock (MD:1988-2006, PM:542-633).  1-D: bit for bit.  2-D / 3-D:
+    interp_shock_location sums into sx1 / sx2 without ever initialising them (MD:2037-2049) -- executing the
+    reference's statements proves it; the library and the oracle start them at zero."""
+    from helpers import make_case
+    w, P, frames, _ = make_case("s1", grid=64, nptl=8)
+    r, o = refsim.RefSim(P, 600), Oracle(P, 600)
+    for s in (r, o):
+        s.upload_fields(0, frames[0])
+        s.upload_fields(1, frames[1])
+        s.inject_at_shock(50, 1e-4, 2, w.particle_v0, 0.0, 6.2)
+    assert_particles_identical(r.download_particles(), o.download_particles(), "1-D shock injection")
+    w, P, frames, _ = make_case("c3", grid=32, nptl=8)
+    r = refsim.RefSim(P, 600)
+    r.upload_fields(0, frames[0])
+    r.upload_fields(1, frames[1])
+    with pytest.raises(RuntimeError, match="sx1' before assigning"):
+        r.inject_at_shock(50, 1e-4, 2, w.particle_v0, 0.0, 6.2)
