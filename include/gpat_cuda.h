@@ -201,8 +201,10 @@ int gpat_upload_acc_surface(gpat_handle h, int which, int slot, const double* he
  * stream and returns at once, so the copy overlaps the next gpat_particle_mover.  A later
  * gpat_upload_fields with the same host pointer and nvar finds the bytes on the device and
  * only runs the gradient/pack kernel.  The host buffer must stay unchanged (and should be
- * page-locked) until that gpat_upload_fields call returns.  Optional: without it
- * gpat_upload_fields copies synchronously as before. */
+ * page-locked) until that gpat_upload_fields call returns.  A prefetch is consumed by the NEXT
+ * gpat_upload_fields call only: an upload with another pointer or nvar discards it (a caller that
+ * reuses one buffer for every frame must not rewrite it between the prefetch and its upload).
+ * Optional: without it gpat_upload_fields copies synchronously as before. */
 int gpat_prefetch_fields(gpat_handle h, const float* f, int nvar);
 
 /* Replaces copy_fields (mhd_data_parallel.f90:1920): farray1 = farray2.  O(1): the two halves of the
@@ -306,7 +308,11 @@ int gpat_download_particles(gpat_handle h, gpat_particle* out, int64_t nmax, int
 int gpat_upload_particles(gpat_handle h, const gpat_particle* in, int64_t n);
 
 /* Escaped particles of the current interval (escaped_ptls, particle_module.f90:134-135)
- * and reset_escaped_particles (diagnostics.f90, called at stochastic-mhd.f90:533). */
+ * and reset_escaped_particles (diagnostics.f90, called at stochastic-mhd.f90:533).  The device
+ * array grows like resize_escaped_particles (particle_module.f90:5329-5358) when a caller does not
+ * reset it every interval.  ORDER: escapees of one remove pass are stored in ascending particle-
+ * array index, the reference stores them in the encounter order of its swap-with-tail loop; the
+ * set is the same, records are identified by (origin, tag_injected, tag_splitted). */
 int gpat_download_escaped(gpat_handle h, gpat_particle* out, int64_t nmax, int64_t* n);
 int gpat_reset_escaped(gpat_handle h);
 

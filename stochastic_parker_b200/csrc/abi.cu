@@ -438,12 +438,40 @@ int ensure_aos(gpat_sim* h, long long n)
     return GPAT_OK;
 }
 
+// escaped_ptls with the reference's growth rule (resize_escaped_particles, particle_module.f90:5329-5358,
+// called from remove_particles :5372-5376): when the escapees so far plus every current particle would not
+// fit, the array grows to max(int(1.25 * cap), cap + nptl_current) and keeps its content.
 int ensure_escaped(gpat_sim* h)
 {
-    if (h->esc_mem) return GPAT_OK;
-    CU(cudaMalloc(&h->esc_mem, soa_bytes(h->nptl_max)));
-    carve_soa(h->esc_mem, h->nptl_max, h->E);
-    h->ecap = h->nptl_max;
+    if (!h->esc_mem) {
+        CU(cudaMalloc(&h->esc_mem, soa_bytes(h->nptl_max)));
+        carve_soa(h->esc_mem, h->nptl_max, h->E);
+        h->ecap = h->nptl_max;
+    }
+    if (h->nptl_escaped + h->nptl_current <= h->ecap) return GPAT_OK;
+    long long ncap = (long long)(1.25 * (double)h->ecap);
+    if (ncap < h->ecap + h->nptl_current) ncap = h->ecap + h->nptl_current;
+    void* mem = nullptr;
+    CU(cudaMalloc(&mem, soa_bytes(ncap)));
+    PtlSoA N;
+    carve_soa(mem, ncap, N);
+    const long long keep = h->nptl_escaped < h->ecap ? h->nptl_escaped : h->ecap;
+    if (keep > 0) {
+        const size_t n8 = (size_t)keep * 8, n4 = (size_t)keep * 4, n1 = (size_t)keep;
+        double* const src8[10] = {h->E.x, h->E.y, h->E.z, h->E.p, h->E.v, h->E.mu, h->E.weight, h->E.t, h->E.dt, (double*)h->E.rng};
+        double* const dst8[10] = {N.x, N.y, N.z, N.p, N.v, N.mu, N.weight, N.t, N.dt, (double*)N.rng};
+        for (int k = 0; k < 10; ++k) CU(cudaMemcpyAsync(dst8[k], src8[k], n8, cudaMemcpyDeviceToDevice, h->st));
+        int* const src4[5] = {h->E.origin, h->E.nsteps_tracked, h->E.nsteps_pushed, h->E.tag_injected, h->E.tag_splitted};
+        int* const dst4[5] = {N.origin, N.nsteps_tracked, N.nsteps_pushed, N.tag_injected, N.tag_splitted};
+        for (int k = 0; k < 5; ++k) CU(cudaMemcpyAsync(dst4[k], src4[k], n4, cudaMemcpyDeviceToDevice, h->st));
+        CU(cudaMemcpyAsync(N.split_times, h->E.split_times, n1, cudaMemcpyDeviceToDevice, h->st));
+        CU(cudaMemcpyAsync(N.count_flag, h->E.count_flag, n1, cudaMemcpyDeviceToDevice, h->st));
+    }
+    CU(cudaStreamSynchronize(h->st));
+    cudaFree(h->esc_mem);
+    h->esc_mem = mem;
+    h->E = N;
+    h->ecap = ncap;
     return GPAT_OK;
 }
 
@@ -714,6 +742,9 @@ int gpat_upload_fields(gpat_handle h, int slot, const float* f, int nvar, int wi
         src = h->stage2;
         h->pf_ptr = nullptr;
     } else {
+        // a prefetch is good for the NEXT upload only: an upload of anything else drops it, so that a frame whose
+        // upload was skipped (error path, quota break) can never be packed later from a stale device copy
+        h->pf_ptr = nullptr;
         if (bytes > h->stage_bytes) {
             if (h->stage) cudaFree(h->stage);
             h->stage = nullptr;

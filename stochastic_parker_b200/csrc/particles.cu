@@ -658,7 +658,7 @@ __global__ void split_apply_kernel(PtlSoA P, const long long* idx, long long* co
     long long child = n + k;
     int st = P.split_times[i];
     // particle_module.f90:5449: 0.5**(1.0 + split_times) in default real -- exact power of two
-    double wgt = (double)exp2f(-(1.0f + (float)st));
+    double wgt = ldexp(1.0, -(1 + st));
     P.weight[i] = wgt;
     P.split_times[i] = (signed char)(st + 1);
     copy_particle(P, child, P, i);

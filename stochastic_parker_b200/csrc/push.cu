@@ -1343,7 +1343,9 @@ __device__ __forceinline__ int after_push(const DevParams& prm, const PushArgs& 
         q.nsteps_pushed = (n1 < a.nsteps_interval) ? n1 : (n1 == a.nsteps_interval ? 0 : n1 % a.nsteps_interval);
     }
     if (TRACK && q.tag_spl < 0 && q.nsteps_pushed == 0) track_sample(a, P, idx, q);
-    if (!(SPEC & 1) && a.debug_nsteps > 0) return (--remaining == 0) ? ST_IDLE : ST_ADAPT;  // SPEC: never the debug mode
+    // gpat_debug_push_n: a uniform branch on a kernel argument, kept in the switch-specialised instantiations too so
+    // that the per-step parity tests run the very kernels bench.py times
+    if (a.debug_nsteps > 0) return (--remaining == 0) ? ST_IDLE : ST_ADAPT;
     return next_state<TRACK>(prm, a, q, state == ST_FIX ? AFTER_FIXED_PUSH : AT_INNER_HEAD);
 }
 
@@ -1716,7 +1718,7 @@ void launch_one(const DevParams& prm, const PtlSoA& P, const float* fld, const P
         // (profiles/README.md).  Tracking runs pick the same SPEC so that they replay the run their
         // particles were selected from with identical arithmetic.
         int spec = 0;
-        if (a.debug_nsteps == 0 && !prm.nlgc && prm.rng_mode != GPAT_RNG_TABLE && !prm.check_drift_2d &&
+        if (!prm.nlgc && prm.rng_mode != GPAT_RNG_TABLE && !prm.check_drift_2d &&
             prm.acc_region_flag != 1 && prm.time_interp && !a.generic) {
             const int want = 1 | (prm.mag_dependency == 1 ? 2 : 0) | (prm.momentum_dependency == 1 ? 4 : 0);
             if (Rec<L>::NDIM == 2 && (want == kSpec11 || (L == L2B && want == kSpec01))) spec = want;

@@ -309,7 +309,7 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
                   split_ratio=2.0, pmin_split=2.0, nsteps_interval=100, num_fine_steps=1,
                   local_dist=True, dump_escaped_dist=False, dt_inject=0.0, on_interval=None,
                   inject_mode=0, inject_same_nptl=True, inject_min=0.0, ncells_norm=1,
-                  track_tags=None, on_tracked=None, surfaces=None, tmin=0, quota_seconds=None, tmax_mhd=1 << 30,
+                  track_tags=None, on_tracked=None, surfaces=None, maps=None, tmin=0, quota_seconds=None, tmax_mhd=1 << 30,
                   particle_data_dump=False, dump_escaped=False):
     """solve_transport_equation (stochastic-mhd.f90:312-567) for one rank.
 
@@ -343,6 +343,14 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
         raise ValueError("acc_by_surface needs the `surfaces` callable")
     for k in range(nsurf):                                     # :323-334 read_acc_surface(0, ...)
         sim.upload_acc_surface(k, 0, surfaces(k, tmin))
+    # turbulence maps (:336-347, 413-420): `maps(which, frame)` -> (slab, two_d) of deltab_NNNN (which = 0) /
+    # lc_NNNN (which = 1).  They swap with the fields, so they must be re-sent every frame like them.
+    which_maps = [w for w, on in ((0, P.deltab_flag), (1, P.correlation_flag)) if on]
+    if which_maps and maps is None:
+        raise ValueError("deltab_flag / correlation_flag need the `maps` callable (the maps swap with the fields "
+                         "every interval and would go stale)")
+    for wm in which_maps:
+        sim.upload_turbulence(wm, 0, *maps(wm, tmin))
     total_steps = 0
     for tf in range(tmin + 1, nframes):                        # :397
         # read_field_data_parallel(..., var_flag=time_interp_flag): without time interpolation
@@ -357,11 +365,13 @@ def run_intervals(sim, frames, tstamps, *, nptl, dist_flag=1, particle_v0=1.0, p
             sim.upload_fields(1 if P.time_interp else 0, get(fr))
             for k in range(nsurf):                             # :405-416 read_acc_surface(time_interp_flag, ...)
                 sim.upload_acc_surface(k, 1 if P.time_interp else 0, surfaces(k, fr))
+            for wm in which_maps:                              # :413-420 read_magnetic_fluctuation / _correlation_length
+                sim.upload_turbulence(wm, 1 if P.time_interp else 0, *maps(wm, fr))
         t0, dtf = tstamps[tf - 1], tstamps[tf] - tstamps[tf - 1]
-        if (tf == 1 or inject_new_ptl) and tf <= tmax_to_inject:   # :462-485
-            if inject_mode == 6:                               # :451-454 inject_at_shock
-                sim.inject_at_shock(nptl, dt_inject, dist_flag, particle_v0, t0, power_index)
-            elif inject_mode:                                  # :464-480 (inject_large_jz ... _rho)
+        if inject_mode == 6:                                   # :451-454 inject_at_shock: EVERY frame, whatever
+            sim.inject_at_shock(nptl, dt_inject, dist_flag, particle_v0, t0, power_index)   # -in / tmax_to_inject say
+        elif (tf == 1 or inject_new_ptl) and tf <= tmax_to_inject:   # :462-485
+            if inject_mode:                                    # :464-480 (inject_large_jz ... _rho)
                 sim.inject_targeted(inject_mode, nptl, dt_inject, dist_flag, particle_v0, t0, dtf, part_box,
                                     power_index, inject_same_nptl, inject_min, ncells_norm)
             else:

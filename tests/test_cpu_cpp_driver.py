@@ -179,6 +179,17 @@ def test_shock_injection_switch(driver, tmp_path):
     _same_run(r, out, rec, steps, 3)
 
 
+def test_shock_injection_ignores_the_inject_new_ptl_switch(driver, tmp_path):
+    """stochastic-mhd.f90:451-454 calls locate_shock_xpos + inject_particles_at_shock on EVERY frame, before and
+    outside the `tf == 1 .or. inject_new_ptl` gate: with -in .false. both host drivers still inject each frame."""
+    w, P, frames, d, out, base = _setup(tmp_path, "c3", 48, 300, 3)
+    r = driver(base + ["-is", ".true.", "-in", ".false."])
+    rec, steps = run_intervals(Oracle(P, 12 * 300), frames, [f * w.dt_out for f in range(3)], nptl=300,
+                               particle_v0=w.particle_v0, **KW, inject_mode=6, inject_new_ptl=False)
+    _same_run(r, out, rec, steps, 3)
+    assert rec[-1]["quick"][0] > 1.5 * 300     # two injections, not one
+
+
 def test_one_dimensional_run(driver, tmp_path):
     w, P, frames, d, out, base = _setup(tmp_path, "s1", 256, 500, 3)
     r = driver(base)
@@ -207,14 +218,9 @@ def test_turbulence_map_files(driver, tmp_path):
         np.stack([lcs, lc2]).tofile(str(d / f"lc_{f:04d}"))
     r = driver(base + ["-db", "1", "-co", "1"])
 
-    class WithMaps(Oracle):   # run_intervals has no map hook: upload them with the frames
-        def upload_fields(self, slot, f, with_grad=0):
-            super().upload_fields(slot, f, with_grad)
-            k = next(i for i, fr in enumerate(frames) if fr is f)
-            self.upload_turbulence(0, slot, maps[k][0], maps[k][1])
-            self.upload_turbulence(1, slot, maps[k][2], maps[k][3])
-    rec, steps = run_intervals(WithMaps(P, 12 * 400), frames, [f * w.dt_out for f in range(3)], nptl=400,
-                               particle_v0=w.particle_v0, **KW)
+    rec, steps = run_intervals(Oracle(P, 12 * 400), frames, [f * w.dt_out for f in range(3)], nptl=400,
+                               particle_v0=w.particle_v0, **KW,
+                               maps=lambda which, f: (maps[f][2 * which], maps[f][2 * which + 1]))
     _same_run(r, out, rec, steps, 3)
     os.remove(d / "lc_0002")
     assert driver(base + ["-db", "1", "-co", "1"], expect_ok=False).returncode != 0
@@ -385,13 +391,9 @@ def test_large_db2_injection_with_map_files(driver, tmp_path):
     vmin = float(np.median(maps[0][0]))
     r = driver(base + ["-db", "1", "-ib", ".true.", "-db2", repr(vmin), "-nb", "40", "-sn", ".false."])
 
-    class WithMaps(Oracle):
-        def upload_fields(self, slot, f, with_grad=0):
-            super().upload_fields(slot, f, with_grad)
-            k = next(i for i, fr in enumerate(frames) if fr is f)
-            self.upload_turbulence(0, slot, maps[k][0], maps[k][1])
-    rec, steps = run_intervals(WithMaps(P, 12 * 400), frames, [f * w.dt_out for f in range(3)], nptl=400,
-                               particle_v0=w.particle_v0, **KW, inject_mode=3, inject_same_nptl=False, inject_min=vmin,
+    rec, steps = run_intervals(Oracle(P, 12 * 400), frames, [f * w.dt_out for f in range(3)], nptl=400,
+                               particle_v0=w.particle_v0, **KW, maps=lambda which, f: (maps[f][0], maps[f][1]),
+                               inject_mode=3, inject_same_nptl=False, inject_min=vmin,
                                ncells_norm=40)
     _same_run(r, out, rec, steps, 3)
     assert rec[-1]["quick"][0] > 0
