@@ -236,12 +236,18 @@ int validate(const gpat_params* p, std::string& why)
     return 0;
 }
 
-bool Rec_has_rho(int layout) { return layout == L2E || layout == L3E; }
+bool Rec_has_rho(int layout) { return layout == L2E || layout == L3E || layout == L2D; }
 
 int pick_layout(const gpat_params& p)
 {
     // focused transport reads vz and all six in-plane velocity gradients (particle_module.f90:3764-3789)
     bool ext = p.dpp_wave || p.dpp_shear || (p.ndim == 2 && p.include_3rd_dim) || p.keep_rho || p.focused_transport;
+    // production build, 2-D momentum diffusion without the third dimension (config C4): the L2B line with rho in
+    // its pad slot + a side plane for the two shear-only gradients (gpat_internal.cuh, Rec<L2D>).  Everything the
+    // reference-order kernels serve (strict_math, 1-D, focused transport, turbulence maps) keeps L2E.
+    if (p.ndim == 2 && (p.dpp_wave || p.dpp_shear) && !p.include_3rd_dim && !p.focused_transport && !p.strict_math &&
+        !p.deltab_flag && !p.correlation_flag && !getenv("GPAT_NO_L2D"))
+        return L2D;
     // 1-D runs live in the 2-D record layouts (one physical row + one zero row, fill_dev_params)
     if (p.ndim <= 2) return ext ? L2E : L2B;
     return ext ? L3E : L3B;
@@ -329,7 +335,8 @@ void carve_soa(void* mem, long long n, PtlSoA& P)
 
 size_t field_floats(const gpat_sim* h)
 {
-    return (size_t)h->dp.nxg * h->dp.nyg * h->dp.nzg * nrec_of(h->layout) * 2;  // both halves, always
+    // both halves, always; + the side plane of L2D
+    return (size_t)h->dp.nxg * h->dp.nyg * h->dp.nzg * (nrec_of(h->layout) * 2 + side_floats_of(h->layout));
 }
 
 // The smallest positive double p with floor((log10(p) - pmin_log)/dp_log) >= k, found by

@@ -80,6 +80,27 @@ __global__ void pack_kernel(const float* __restrict__ src, int nvar, int with_gr
     }
 }
 
+// Side plane of L2D (gpat_internal.cuh): one float4 per grid point, [s0, s1 of half 0 | s0, s1 of half 1];
+// this frame half owns two of the four floats.  Same gradient arithmetic as the record plane.
+__global__ void pack_side_kernel(const float* __restrict__ src, int nvar, int with_grad, GridDims g, int s0, int s1,
+                                 float* __restrict__ side, int half)
+{
+    const long long ncell = (long long)g.nxg * g.nyg * g.nzg;
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < ncell;
+         c += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(c % g.nxg);
+        const int j = (int)((c / g.nxg) % g.nyg);
+        const int k = (int)(c / ((long long)g.nxg * g.nyg));
+        float2 v;
+        if (with_grad) { v.x = src[c * nvar + (s0 - 1)]; v.y = src[c * nvar + (s1 - 1)]; }
+        else {
+            v.x = grad_one(src, nvar, g, (s0 - 9) / 3, (s0 - 9) % 3, i, j, k);
+            v.y = grad_one(src, nvar, g, (s1 - 9) / 3, (s1 - 9) % 3, i, j, k);
+        }
+        *reinterpret_cast<float2*>(side + c * 4 + 2 * half) = v;
+    }
+}
+
 // debug: the full 32-slot reference layout from an 8-variable frame
 __global__ void grad32_kernel(const float* __restrict__ src, GridDims g, float* __restrict__ out32)
 {
@@ -106,6 +127,12 @@ void launch_pack(const float* src, int nvar, int with_grad, const DevParams& prm
     const long long stride = 2LL * map.nrec;
     const int half_off = (prm.time_interp ? half : 0) * 4;
     pack_kernel<<<sm_count * 8, 256, 0, st>>>(src, nvar, with_grad, g, map, dst, stride, half_off);
+    if (side_floats_of(layout)) {
+        const long long nstore = (long long)prm.nxg * prm.nyg * prm.nzg;  // the side plane starts behind the records
+        pack_side_kernel<<<sm_count * 8, 256, 0, st>>>(src, nvar, with_grad, g, side_slot_of(layout, 0),
+                                                       side_slot_of(layout, 1), dst + nstore * stride,
+                                                       prm.time_interp ? half : 0);
+    }
 }
 
 // Turbulence maps: consumer side of read_magnetic_fluctuation / read_correlation_length

@@ -22,27 +22,40 @@ namespace gpat {
 // ---- packed field record layouts ---------------------------------------------------
 // Reference slot numbers (1-based, mhd_data_parallel.f90:77-81): 1 vx 2 vy 3 vz 4 rho 5 bx
 // 6 by 7 bz 8 |B|; gradient of primary k along d (1..3) is slot 8 + 3(k-1) + d.
-enum Layout : int { L2B = 0, L2E = 1, L3B = 2, L3E = 3 };
+enum Layout : int { L2B = 0, L2E = 1, L3B = 2, L3E = 3, L2D = 4 };
 
+// NREC/NUSED: floats per frame in the record / slots in use; EXT: momentum-diffusion slots present;
+// NSIDE: slots kept in the SIDE PLANE (see L2D); THIRD: 0 = no resolved z axis, 1 = always (3-D),
+// 2 = decided at run time by include_3rd_dim; NF = doubles of an interpolated record (record + side slots).
 template <int L> struct Rec;
 // 2-D Parker without momentum diffusion: 15 slots (particle_module.f90:3392-3399, 3430-3433,
 // 2352-2357) + 1 pad = 64 B per frame
 template <> struct Rec<L2B> {
-    static constexpr int NREC = 16, NUSED = 15, NDIM = 2;
+    static constexpr int NREC = 16, NUSED = 15, NDIM = 2, NSIDE = 0, THIRD = 0, NF = NREC;
     static constexpr bool EXT = false;
 };
 // + vz (include_3rd_dim), rho (D_pp wave), dvx_dy dvy_dx dvz_dx dvz_dy (D_pp shear)
 template <> struct Rec<L2E> {
-    static constexpr int NREC = 24, NUSED = 21, NDIM = 2;
+    static constexpr int NREC = 24, NUSED = 21, NDIM = 2, NSIDE = 0, THIRD = 2, NF = NREC;
     static constexpr bool EXT = true;
 };
 // 3-D Parker: 21 slots (particle_module.f90:4665-4670, 4686-4688, 2390-2401)
 template <> struct Rec<L3B> {
-    static constexpr int NREC = 24, NUSED = 21, NDIM = 3;
+    static constexpr int NREC = 24, NUSED = 21, NDIM = 3, NSIDE = 0, THIRD = 1, NF = NREC;
     static constexpr bool EXT = false;
 };
 template <> struct Rec<L3E> {
-    static constexpr int NREC = 32, NUSED = 28, NDIM = 3;
+    static constexpr int NREC = 32, NUSED = 28, NDIM = 3, NSIDE = 0, THIRD = 1, NF = NREC;
+    static constexpr bool EXT = true;
+};
+// 2-D Parker + momentum diffusion WITHOUT the third dimension (BASELINE config C4, production build):
+// 18 slots.  The record is the L2B line with rho in its pad slot -- one 128-byte line per grid point,
+// both frames, gathered by four lanes exactly like L2B -- and the two shear-only gradients dvx_dy,
+// dvy_dx live in a side plane behind the record plane: one float4 per grid point
+// [dvx_dy, dvy_dx of half 0 | the same of half 1].  144 B per grid point instead of L2E's 192 B, and
+// the gather keeps L2B's four lanes per particle instead of L2E's two.
+template <> struct Rec<L2D> {
+    static constexpr int NREC = 16, NUSED = 16, NDIM = 2, NSIDE = 2, THIRD = 0, NF = NREC + 4;
     static constexpr bool EXT = true;
 };
 
@@ -54,19 +67,26 @@ __host__ __device__ constexpr int slot_of(int layout, int k)
     constexpr int l3[32] = {1, 2, 3, 5, 6, 7, 9, 13, 17, 21, 22, 23, 24, 25, 26, 27, 28, 29,
                             30, 31, 32, /*21*/ 4, 10, 11, 12, 14, 15, 16, 0, 0, 0, 0};
     return (layout == L2B) ? (k < 15 ? l2[k] : 0)
+         : (layout == L2D) ? (k < 15 ? l2[k] : 4)
          : (layout == L2E) ? l2[k]
          : (layout == L3B) ? (k < 21 ? l3[k] : 0)
                            : l3[k];
 }
 __host__ __device__ constexpr int nrec_of(int layout)
 {
-    return layout == L2B ? 16 : layout == L3E ? 32 : 24;
+    return (layout == L2B || layout == L2D) ? 16 : layout == L3E ? 32 : 24;
 }
+// side plane: floats per grid point (both frames) behind the record plane, and the reference slots it holds
+__host__ __device__ constexpr int side_floats_of(int layout) { return layout == L2D ? 4 : 0; }
+__host__ __device__ constexpr int side_slot_of(int layout, int i) { return layout == L2D ? (i == 0 ? 10 : 12) : 0; }  // dvx_dy, dvy_dx
 
 // named positions inside a record
 namespace s2 {  // 2-D layouts
 enum { vx = 0, vy, bx, by, bz, dvx_dx, dvy_dy, dbx_dx, dbx_dy, dby_dx, dby_dy, dbz_dx, dbz_dy,
        db_dx, db_dy, vz, rho, dvx_dy, dvy_dx, dvz_dx, dvz_dy };
+}
+namespace s2d {  // L2D: interpolated record F[NF]: the 15 base slots, rho, then the side slots
+enum { rho = 15, dvx_dy = 16, dvy_dx = 17 };
 }
 namespace s3 {  // 3-D layouts
 enum { vx = 0, vy, vz, bx, by, bz, dvx_dx, dvy_dy, dvz_dz, dbx_dx, dbx_dy, dbx_dz, dby_dx, dby_dy,

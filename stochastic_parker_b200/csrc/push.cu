@@ -184,7 +184,7 @@ __device__ __forceinline__ long long locate(const DevParams& prm, double x, doub
 template <int L>
 __device__ __forceinline__ void gather(const DevParams& prm, const float* __restrict__ fld,
                                        int sel, double x, double y, double z, double rt,
-                                       double (&F)[Rec<L>::NREC])
+                                       double (&F)[Rec<L>::NF])
 {
     constexpr int NREC = Rec<L>::NREC;
     constexpr int NQ = (Rec<L>::NUSED + 3) / 4;
@@ -231,6 +231,21 @@ __device__ __forceinline__ void gather(const DevParams& prm, const float* __rest
         for (int e = 0; e < 4; ++e)
             F[4 * qd + e] = prm.time_interp ? (a[e] * rt1 + b[e] * rt) : a[e];
     }
+    if constexpr (Rec<L>::NSIDE > 0) {  // side plane (L2D): [s0 s1 of half 0 | s0 s1 of half 1] per grid point
+        const float* side = fld + (long long)prm.nxg * prm.nyg * prm.nzg * stride;
+        const int sA = prm.time_interp ? sel : 0, sB = sel ^ 1;
+        double a[2] = {0.0, 0.0}, b[2] = {0.0, 0.0};
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const float4 e = __ldg(reinterpret_cast<const float4*>(side + (off[c] / stride) * 4));
+            const float ea[2] = {sA ? e.z : e.x, sA ? e.w : e.y}, eb[2] = {sB ? e.z : e.x, sB ? e.w : e.y};
+            a[0] = a[0] + (double)ea[0] * w[c]; a[1] = a[1] + (double)ea[1] * w[c];
+            if (prm.time_interp) { b[0] = b[0] + (double)eb[0] * w[c]; b[1] = b[1] + (double)eb[1] * w[c]; }
+        }
+        F[NREC] = prm.time_interp ? (a[0] * rt1 + b[0] * rt) : a[0];
+        F[NREC + 1] = prm.time_interp ? (a[1] * rt1 + b[1] * rt) : a[1];
+        F[NREC + 2] = F[NREC + 3] = 0.0;
+    }
 #else
     // fast: fold the time blend into the corner weights, one FMA per loaded value; w0/w1 are the
     // weights of half 0 / half 1 of each chunk
@@ -257,6 +272,19 @@ __device__ __forceinline__ void gather(const DevParams& prm, const float* __rest
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) F[4 * qd + e] = a[e];
+    }
+    if constexpr (Rec<L>::NSIDE > 0) {
+        const float* side = fld + (long long)prm.nxg * prm.nyg * prm.nzg * stride;
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const float4 e = __ldg(reinterpret_cast<const float4*>(side + (off[c] / stride) * 4));
+            const float a0f = sel == 0 ? e.x : e.z, a1f = sel == 0 ? e.y : e.w;  // farray1 lives in half `sel`
+            const float b0f = sel == 0 ? e.z : e.x, b1f = sel == 0 ? e.w : e.y;  // farray2
+            a0 = fma((double)a0f, w0[c], a0); a1 = fma((double)a1f, w0[c], a1);
+            a0 = fma((double)b0f, w1[c], a0); a1 = fma((double)b1f, w1[c], a1);
+        }
+        F[NREC] = a0; F[NREC + 1] = a1; F[NREC + 2] = F[NREC + 3] = 0.0;
     }
 #endif
 }
@@ -1458,7 +1486,11 @@ template <int L> struct Coop {
     // rows (160 B apart in 2-D) still tile the 32 banks on the read side
     // (profiles/r01e_push_coop_ncu.txt: 3.2e9 shared-memory bank conflicts before this).
     static constexpr bool SKEW = (G == 4);                        // G = 2 rows (NREC = 24) are conflict-free at +16 B
-    static constexpr int ROW = SKEW ? NREC + 4 : NREC + 2;
+    // side plane (L2D): in round r lane gq of the group loads corner gq's float4 of particle r and parks its two
+    // weighted partial sums behind the record part of the owner's row; the owner adds the four corners up
+    static constexpr int NSIDE = Rec<L>::NSIDE;
+    static constexpr int SIDEROW = NSIDE ? 2 * G : 0;             // doubles: G corners x 2 side slots
+    static constexpr int ROW = (SKEW ? NREC + 4 : NREC + 2) + SIDEROW;
     // parameter rows.  2-D: the owner publishes its eight finished corner weights (time blend and
     // conversion scale folded in) + the cell, 80 B; the other lanes of the group load them instead
     // of recomputing 16 products per round.  3-D: rx ry t0 t1 cell rz, 48 B, weights per round.
@@ -1473,7 +1505,7 @@ template <int L> struct Coop {
 template <int L> struct MinBlocks { static constexpr int V = GPAT_MINBLOCKS; };
 #else
 // 3-D Parker at 4 CTAs spills 32 bytes and is still 6 % faster than 3 CTAs on C5 (profiles/README.md)
-template <int L> struct MinBlocks { static constexpr int V = (L == L2B || L == L3B) ? 4 : 3; };
+template <int L> struct MinBlocks { static constexpr int V = (L == L2B || L == L3B || L == L2D) ? 4 : 3; };
 #endif
 // SEL = which half of the store is farray1 (PushArgs::sel).  It is a template parameter because
 // the two frames must enter every sum in the order (farray1, farray2) whatever half they live in:
@@ -1511,7 +1543,7 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
         }
         // top of the inner while body, particle_module.f90:1602-1612.  One combined test keeps the
         // common case (inside the extended box, p >= 0) to a single untaken branch.
-        if (state == ST_ADAPT && outside_or_negp<(Rec<L>::NDIM == 3) || Rec<L>::EXT>(prm, q)) {
+        if (state == ST_ADAPT && outside_or_negp<(Rec<L>::THIRD != 0)>(prm, q)) {
             negp_or_bc(prm, q, a.leak);
             if (q.count_flag != GPAT_COUNT_FLAG_INBOX) {
                 store_lane(a, P, idx, q);
@@ -1556,9 +1588,16 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
             constexpr int NLD = C::NC * C::CPL;  // 256-bit loads per lane per round
             constexpr int DEPTH = (GPAT_COOP_DEPTH < C::G) ? GPAT_COOP_DEPTH : C::G;
             float4 lo[DEPTH][NLD], hi[DEPTH][NLD];
+            float4 sd[DEPTH];  // side plane (L2D): corner gq of the round's particle
             auto issue = [&](int r, int slot) {
                 const long long cell = __double_as_longlong(par[(gbase + r) * C::PAR + (C::PUBW ? 8 : 4)]);
                 const float* base = fld + cell * stride + (gq * C::CPL) * 8;
+                if constexpr (C::NSIDE > 0) {
+                    static_assert(C::G == 4 && C::NC == 4 && C::PUBW, "side plane: one corner per lane of the group");
+                    const float* side = fld + (long long)prm.nxg * prm.nyg * prm.nzg * stride;
+                    sd[slot] = __ldg(reinterpret_cast<const float4*>(
+                        side + (cell + (gq & 1) + (long long)(gq >> 1) * prm.nxg) * 4));
+                }
 #pragma unroll
                 for (int c = 0; c < C::NC; ++c) {
                     const float* pc_ = base + ((c & 1) + (long long)((c >> 1) & 1) * prm.nxg +
@@ -1615,8 +1654,25 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                         }
                     }
                 }
+                double2 sidep = make_double2(0.0, 0.0);
+                if constexpr (C::NSIDE > 0) {
+                    // this lane's corner: weights of half 0 / half 1 from the owner's published row (w0[gq], w1[gq])
+                    static_assert(cvt_weight_scale(0, 0) == cvt_weight_scale(1, 0) && cvt_weight_scale(0, 1) == cvt_weight_scale(1, 1),
+                                  "the side gather assumes a conversion mask that does not depend on the row");
+                    const double wa = par[owner * C::PAR + gq], wb = par[owner * C::PAR + 4 + gq];
+                    const float4 e = sd[slot];
+                    if constexpr (SEL == 0) {
+                        sidep.x = fma(cvt_sel<0, 1>(e.z), wb, cvt_sel<0, 0>(e.x) * wa);
+                        sidep.y = fma(cvt_sel<0, 1>(e.w), wb, cvt_sel<0, 0>(e.y) * wa);
+                    } else {
+                        sidep.x = fma(cvt_sel<0, 0>(e.x), wa, cvt_sel<0, 1>(e.z) * wb);
+                        sidep.y = fma(cvt_sel<0, 0>(e.y), wa, cvt_sel<0, 1>(e.w) * wb);
+                    }
+                }
                 if (r + DEPTH < C::G) issue(r + DEPTH, slot);
                 double2* out = reinterpret_cast<double2*>(res + C::row_off(owner) + (gq * C::CPL) * 4);
+                if constexpr (C::NSIDE > 0)
+                    *reinterpret_cast<double2*>(res + C::row_off(owner) + C::NREC + 2 * gq) = sidep;
 #pragma unroll
                 for (int j = 0; j < C::CPL; ++j) {
                     out[2 * j] = make_double2(acc[j][0], acc[j][1]);
@@ -1628,7 +1684,7 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
 
         // ---- phase C: the owner lane finishes its push ----
         if (state != ST_IDLE) {
-            double F[C::NREC];
+            double F[Rec<L>::NF];
             const double2* row = reinterpret_cast<const double2*>(res + C::row_off((int)lane));
 #pragma unroll
             for (int k = 0; k < C::NREC / 2; ++k) {
@@ -1636,7 +1692,13 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                 F[2 * k] = v.x;
                 F[2 * k + 1] = v.y;
             }
-            physics_fast<L, double[C::NREC], TRACK, SPEC>(prm, a, F, q, state == ST_FIX);
+            if constexpr (C::NSIDE > 0) {  // the four corners' partial sums, always in corner order
+                const double2 c0 = row[C::NREC / 2], c1 = row[C::NREC / 2 + 1], c2 = row[C::NREC / 2 + 2], c3 = row[C::NREC / 2 + 3];
+                F[C::NREC] = ((c0.x + c1.x) + c2.x) + c3.x;
+                F[C::NREC + 1] = ((c0.y + c1.y) + c2.y) + c3.y;
+                F[C::NREC + 2] = F[C::NREC + 3] = 0.0;
+            }
+            physics_fast<L, double[Rec<L>::NF], TRACK, SPEC>(prm, a, F, q, state == ST_FIX);
             nsteps++;
             state = after_push<TRACK, SPEC>(prm, a, q, state, remaining, P, idx);
             if (state == ST_IDLE) store_lane(a, P, idx, q);
@@ -1656,11 +1718,13 @@ __global__ void interp_kernel(const __grid_constant__ DevParams prm, const float
 {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double F[Rec<L>::NREC];
+    double F[Rec<L>::NF];
     gather<L>(prm, fld, sel, x[i], y[i], z[i], rt[i], F);
     for (int s = 0; s < 32; ++s) out32[i * 32 + s] = 0.0;
 #pragma unroll
     for (int k = 0; k < Rec<L>::NUSED; ++k) out32[i * 32 + slot_of(L, k) - 1] = F[k];
+#pragma unroll
+    for (int k = 0; k < Rec<L>::NSIDE; ++k) out32[i * 32 + side_slot_of(L, k) - 1] = F[Rec<L>::NREC + k];
 }
 
 template <int L> constexpr int C_NC() { return (Rec<L>::NDIM == 3) ? 8 : 4; }
@@ -1768,6 +1832,9 @@ void GPAT_LAUNCH(int layout, const DevParams& prm, const PtlSoA& P, const float*
         case L2B: launch_one<L2B>(prm, P, fld, a, sm_count, st); break;
         case L2E: launch_one<L2E>(prm, P, fld, a, sm_count, st); break;
         case L3B: launch_one<L3B>(prm, P, fld, a, sm_count, st); break;
+#if !GPAT_STRICT
+        case L2D: launch_one<L2D>(prm, P, fld, a, sm_count, st); break;  // production build only (abi.cu: pick_layout)
+#endif
         default: launch_one<L3E>(prm, P, fld, a, sm_count, st); break;
     }
 }
@@ -1783,6 +1850,7 @@ void launch_interp_debug(int layout, const DevParams& prm, const float* fld, int
         case L2B: interp_kernel<L2B><<<grid, 128, 0, st>>>(prm, fld, sel, n, x, y, z, rt, out32); break;
         case L2E: interp_kernel<L2E><<<grid, 128, 0, st>>>(prm, fld, sel, n, x, y, z, rt, out32); break;
         case L3B: interp_kernel<L3B><<<grid, 128, 0, st>>>(prm, fld, sel, n, x, y, z, rt, out32); break;
+        case L2D: interp_kernel<L2D><<<grid, 128, 0, st>>>(prm, fld, sel, n, x, y, z, rt, out32); break;
         default: interp_kernel<L3E><<<grid, 128, 0, st>>>(prm, fld, sel, n, x, y, z, rt, out32); break;
     }
 }

@@ -89,7 +89,9 @@ __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArg
         dbx_dx = F[s2::dbx_dx]; dbx_dy = F[s2::dbx_dy]; dby_dx = F[s2::dby_dx]; dby_dy = F[s2::dby_dy];
         dbz_dx = F[s2::dbz_dx]; dbz_dy = F[s2::dbz_dy]; db_dx = F[s2::db_dx]; db_dy = F[s2::db_dy];
         dvx_dx = F[s2::dvx_dx]; dvy_dy = F[s2::dvy_dy];
-        if constexpr (EXT) {
+        if constexpr (L == L2D) {  // rho in the pad slot of the base line, the shear gradients from the side plane
+            rho = F[s2d::rho]; dvx_dy = F[s2d::dvx_dy]; dvy_dx = F[s2d::dvy_dx];
+        } else if constexpr (EXT) {
             vz = F[s2::vz]; rho = F[s2::rho];
             dvx_dy = F[s2::dvx_dy]; dvy_dx = F[s2::dvy_dx]; dvz_dx = F[s2::dvz_dx]; dvz_dy = F[s2::dvz_dy];
         }
@@ -107,7 +109,7 @@ __device__ __forceinline__ void physics_fast(const DevParams& prm, const PushArg
             dvy_dz = F[s3::dvy_dz]; dvz_dx = F[s3::dvz_dx]; dvz_dy = F[s3::dvz_dy];
         }
     }
-    const bool third = D3 || (EXT && prm.include_3rd_dim);
+    const bool third = (Rec<L>::THIRD == 1) || (Rec<L>::THIRD == 2 && prm.include_3rd_dim);
 
     // ---- |B|, 1/|B| from one rsqrt ----
     const double b2 = bx * bx + by * by + bz * bz;
@@ -312,14 +314,14 @@ template <int L, bool TRACK = false>
 __device__ __forceinline__ void push_once_fast(const DevParams& prm, const PushArgs& a,
                                                const float* __restrict__ fld, Lane& q, bool fixed_dt)
 {
-    double F[Rec<L>::NREC];
+    double F[Rec<L>::NF];
     const double rt = (q.t - a.t0) * a.idtf;
     gather<L>(prm, fld, a.sel, q.x, q.y, q.z, rt, F);
     if constexpr (Rec<L>::NDIM == 3) {
         if (prm.acc_by_surface) {
-            physics_fast<L, double[Rec<L>::NREC], TRACK, kSpecSurf>(prm, a, F, q, fixed_dt);
+            physics_fast<L, double[Rec<L>::NF], TRACK, kSpecSurf>(prm, a, F, q, fixed_dt);
             return;
         }
     }
-    physics_fast<L, double[Rec<L>::NREC], TRACK>(prm, a, F, q, fixed_dt);
+    physics_fast<L, double[Rec<L>::NF], TRACK>(prm, a, F, q, fixed_dt);
 }
