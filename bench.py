@@ -38,7 +38,7 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-ALGO_BYTES = {"L2B": 480, "L2E": 576, "L2D": 576, "L3B": 1344, "L3E": 1344 + 7 * 8 * 4 * 2}
+ALGO_BYTES = {"L2B": 480, "L2E": 576, "L2D": 576, "L3B": 1344, "L3D": 1344, "L3E": 1344 + 7 * 8 * 4 * 2}
 
 
 def parse_args():
@@ -151,7 +151,7 @@ def host_threads() -> int:
 def workload_config(w, P, world, nptl_end=None, strict=0):
     """the `config` object: identical for both arms"""
     layout = field_layout(P, w, strict)
-    floats = {"L2B": 32, "L2E": 48, "L2D": 36, "L3B": 48, "L3E": 64}[layout]   # per grid point, both frames
+    floats = {"L2B": 32, "L2E": 48, "L2D": 36, "L3B": 48, "L3D": 48, "L3E": 64}[layout]   # per grid point, both frames
     npts = (w.nx + 4) * (w.ny + 4 if w.ndim > 1 else 1) * (w.nz + 4 if w.ndim > 2 else 1)
     store_mb = npts * floats * 4 / 1e6
     return {
@@ -173,6 +173,8 @@ def field_layout(P, w, strict=0):
     """mirror of pick_layout (csrc/abi.cu)"""
     if w.ndim == 2 and (P.dpp_wave or P.dpp_shear) and not P.include_3rd_dim and not strict:
         return "L2D"
+    if w.ndim == 3 and not (P.dpp_wave or P.dpp_shear) and not strict:
+        return "L3D"
     return {1: "L2B", 2: "L2E" if (P.dpp_wave or P.dpp_shear or P.include_3rd_dim) else "L2B",
             3: "L3E" if (P.dpp_wave or P.dpp_shear) else "L3B"}[w.ndim]
 

@@ -5,13 +5,26 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may build, load or call it.  The product (stochastic_parker_b200/) never does.
  *
- * PARITY UNPINNED: the reference (xiaocanli/stochastic-parker) ships no tests,
- * golden vectors or known-answer files for this path, and it cannot be built in
- * this image (needs gfortran + MPI + HDF5 + FoBiS/FLAP + mt_stream_f90-1.11, none
- * present).  This file restates the cited Fortran line by line: FP64 throughout,
- * the same operation order (Fortran left-to-right association), the same
- * default-real (FP32) literals.  Build the parity copy with
- * `-O2 -ffp-contract=off` so the compiler keeps that order.
+ * PARITY: PINNED TO THE REFERENCE'S OWN FORTRAN, EXECUTED -- NOT COMPILED.  The reference
+ * (xiaocanli/stochastic-parker) ships no tests, golden vectors or known-answer files for this
+ * path and cannot be built here or on the B200 box (no Fortran front-end on either:
+ * profiles/r02a_fortran_probe.log; it also needs MPI + HDF5 + FoBiS/FLAP + mt_stream_f90-1.11),
+ * so there is no oracle/_ref binary.  Instead oracle/f90/f90run.py executes the UNMODIFIED text
+ * of the reference's procedures (particle_mover, particle_mover_one_cycle, every push_particle_*,
+ * both kappa routines, calc_dpp_*, interp_fields, calc_fields_gradients, the injectors,
+ * remove_particles, split_particle, the tracking hooks, calc_particle_distributions,
+ * calc_escaped_distributions, quick_check ...) with Fortran's kind / promotion / literal /
+ * evaluation-order rules, and tests/golden/ref_f90/*.npz hold what they compute for 18 switch
+ * combinations (1-D, 2-D, 3-D, NLGC, D_pp, focused transport, open boundaries with escapes,
+ * splitting).  tests/test_cpu_reference_f90.py holds THIS FILE to those vectors BIT FOR BIT
+ * (particles, counters, every histogram), live against /root/reference where it exists.
+ * What that does not cover: a compiler's freedom to contract a*b+c into an FMA or to vectorise
+ * a reduction (the interpreter evaluates strictly, like gfortran -O2 without -ffast-math on a
+ * target without FMA contraction), and the 2-D / 3-D shock injector, which reads uninitialised
+ * variables in the reference (tests/test_cpu_reference_f90.py proves it by execution).
+ * This file restates the cited Fortran line by line: FP64 throughout, the same operation order
+ * (Fortran left-to-right association), the same default-real (FP32) literals.  Build the parity
+ * copy with `-O2 -ffp-contract=off` so the compiler keeps that order.
  *
  * Third-party arithmetic that is NOT restated: mt_stream_f90-1.11 (multiple-stream
  * MT19937, random_number_generator.f90:9,35-44,100).  north_star defines parity

@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and
 bench.py's cpu_baseline / --impl reference legs; never by the product package.
-Parity is unpinned (no reference golden vectors exist; see gpat_oracle.c header).
+Pinned bit for bit to golden vectors computed by executing the reference's own Fortran
+(oracle/f90/, tests/golden/ref_f90/, tests/test_cpu_reference_f90.py; see gpat_oracle.c header).
 
 The method names mirror stochastic_parker_b200.driver.GpatSim so parity tests
 read the same on both sides.

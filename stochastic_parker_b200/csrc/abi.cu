@@ -248,6 +248,9 @@ int pick_layout(const gpat_params& p)
     if (p.ndim == 2 && (p.dpp_wave || p.dpp_shear) && !p.include_3rd_dim && !p.focused_transport && !p.strict_math &&
         !p.deltab_flag && !p.correlation_flag && !getenv("GPAT_NO_L2D"))
         return L2D;
+    // production build, 3-D Parker without momentum diffusion (config C5): the L3B record split at the 128-byte line
+    if (p.ndim == 3 && !ext && !p.strict_math && !p.deltab_flag && !p.correlation_flag && !getenv("GPAT_NO_L3D"))
+        return L3D;
     // 1-D runs live in the 2-D record layouts (one physical row + one zero row, fill_dev_params)
     if (p.ndim <= 2) return ext ? L2E : L2B;
     return ext ? L3E : L3B;

@@ -94,28 +94,40 @@ __global__ void __launch_bounds__(256) diag_kernel(const PtlSoA P, const __grid_
                 else atomicAdd(&a.fglobal[gbin], acc);
             }
         }
-        // local distributions (diagnostics.f90:782-870)
-        if (live && a.local_dist) {
+        // local distributions (diagnostics.f90:782-870).  Same warp aggregation as the global spectrum: the lanes of
+        // a warp that fall into the same (mu, p, x, y, z) bin are merged with __match_any_sync and their leader
+        // issues ONE no-return FP64 reduction (REDG.F64).  The particle arrays are cell-ordered in the production
+        // build, so neighbouring lanes share bins (at C1's r = 4 set a warp of 32 particles lands in a handful of
+        // bins); the 5-D arrays themselves are MBs (C1: 6.3 + 4.2 + 0.5 MB) and cannot be staged in shared memory.
+        if (a.local_dist) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const HistDev& h = a.loc[k];
-                if (!h.enabled || !h.data) continue;
-                long long ix, iy, iz, ip, imu;
-                bool ok = ifloor_ok((x - a.xmin) / h.dx_diag, ix) &&
-                          ifloor_ok((y - a.ymin) / h.dy_diag, iy) &&
-                          ifloor_ok((z - a.zmin) / h.dz_diag, iz) &&
-                          ifloor_ok((mu + 1.0) / h.dmu, imu);
-                if (!ok) continue;
-                ip = pbin(h.pthr, h.npbins, p, lp, h.pmin_log, h.dp_log);
-                ix += 1; iy += 1; iz += 1; ip += 1; imu += 1;
-                if (ix >= 1 && ix <= h.nrx && iy >= 1 && iy <= h.nry && iz >= 1 && iz <= h.nrz &&
-                    ip > 0 && ip < h.npbins /* top bin never filled, diagnostics.f90:799 */ &&
-                    imu >= 1 && imu <= h.nmu) {
-                    size_t lin = (size_t)(imu - 1) + (size_t)h.nmu * ((size_t)(ip - 1) +
-                                 (size_t)h.npbins * ((size_t)(ix - 1) + (size_t)h.nrx *
-                                 ((size_t)(iy - 1) + (size_t)h.nry * (size_t)(iz - 1))));
-                    atomicAdd(&h.data[lin], w);
+                if (!h.enabled || !h.data) continue;   // uniform: kernel argument
+                long long lin = -1;
+                if (live) {
+                    long long ix, iy, iz, ip, imu;
+                    const bool ok = ifloor_ok((x - a.xmin) / h.dx_diag, ix) &&
+                                    ifloor_ok((y - a.ymin) / h.dy_diag, iy) &&
+                                    ifloor_ok((z - a.zmin) / h.dz_diag, iz) &&
+                                    ifloor_ok((mu + 1.0) / h.dmu, imu);
+                    if (ok) {
+                        ip = pbin(h.pthr, h.npbins, p, lp, h.pmin_log, h.dp_log);
+                        ix += 1; iy += 1; iz += 1; ip += 1; imu += 1;
+                        if (ix >= 1 && ix <= h.nrx && iy >= 1 && iy <= h.nry && iz >= 1 && iz <= h.nrz &&
+                            ip > 0 && ip < h.npbins /* top bin never filled, diagnostics.f90:799 */ &&
+                            imu >= 1 && imu <= h.nmu)
+                            lin = (long long)((size_t)(imu - 1) + (size_t)h.nmu * ((size_t)(ip - 1) +
+                                  (size_t)h.npbins * ((size_t)(ix - 1) + (size_t)h.nrx *
+                                  ((size_t)(iy - 1) + (size_t)h.nry * (size_t)(iz - 1)))));
+                    }
                 }
+                const unsigned peers = __match_any_sync(0xffffffffu, lin);
+                const int leader = __ffs(peers) - 1;
+                double acc = 0.0;
+                for (unsigned mm = peers; mm; mm &= mm - 1)   // dyadic weights: the sum is exact in any order
+                    acc += __shfl_sync(peers, w, __ffs(mm) - 1);
+                if (lin >= 0 && (int)(threadIdx.x & 31u) == leader) atomicAdd(&h.data[lin], acc);
             }
         }
     }

@@ -127,7 +127,13 @@ void launch_pack(const float* src, int nvar, int with_grad, const DevParams& prm
     const long long stride = 2LL * map.nrec;
     const int half_off = (prm.time_interp ? half : 0) * 4;
     pack_kernel<<<sm_count * 8, 256, 0, st>>>(src, nvar, with_grad, g, map, dst, stride, half_off);
-    if (side_floats_of(layout)) {
+    if (layout == L3D) {  // side plane in chunk format: the same kernel over the side slots, 16 floats per grid point
+        SlotMap sm;
+        sm.nrec = 8;
+        for (int k = 0; k < 32; ++k) sm.slot[k] = (k < 8) ? side_slot_of(layout, k) : 0;
+        const long long nstore = (long long)prm.nxg * prm.nyg * prm.nzg;
+        pack_kernel<<<sm_count * 8, 256, 0, st>>>(src, nvar, with_grad, g, sm, dst + nstore * stride, 16, half_off);
+    } else if (side_floats_of(layout)) {
         const long long nstore = (long long)prm.nxg * prm.nyg * prm.nzg;  // the side plane starts behind the records
         pack_side_kernel<<<sm_count * 8, 256, 0, st>>>(src, nvar, with_grad, g, side_slot_of(layout, 0),
                                                        side_slot_of(layout, 1), dst + nstore * stride,

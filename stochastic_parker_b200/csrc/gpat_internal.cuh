@@ -22,7 +22,7 @@ namespace gpat {
 // ---- packed field record layouts ---------------------------------------------------
 // Reference slot numbers (1-based, mhd_data_parallel.f90:77-81): 1 vx 2 vy 3 vz 4 rho 5 bx
 // 6 by 7 bz 8 |B|; gradient of primary k along d (1..3) is slot 8 + 3(k-1) + d.
-enum Layout : int { L2B = 0, L2E = 1, L3B = 2, L3E = 3, L2D = 4 };
+enum Layout : int { L2B = 0, L2E = 1, L3B = 2, L3E = 3, L2D = 4, L3D = 5 };
 
 // NREC/NUSED: floats per frame in the record / slots in use; EXT: momentum-diffusion slots present;
 // NSIDE: slots kept in the SIDE PLANE (see L2D); THIRD: 0 = no resolved z axis, 1 = always (3-D),
@@ -31,21 +31,21 @@ template <int L> struct Rec;
 // 2-D Parker without momentum diffusion: 15 slots (particle_module.f90:3392-3399, 3430-3433,
 // 2352-2357) + 1 pad = 64 B per frame
 template <> struct Rec<L2B> {
-    static constexpr int NREC = 16, NUSED = 15, NDIM = 2, NSIDE = 0, THIRD = 0, NF = NREC;
+    static constexpr int NREC = 16, NUSED = 15, NDIM = 2, NSIDE = 0, SIDE_CHUNKS = 0, THIRD = 0, NF = NREC;
     static constexpr bool EXT = false;
 };
 // + vz (include_3rd_dim), rho (D_pp wave), dvx_dy dvy_dx dvz_dx dvz_dy (D_pp shear)
 template <> struct Rec<L2E> {
-    static constexpr int NREC = 24, NUSED = 21, NDIM = 2, NSIDE = 0, THIRD = 2, NF = NREC;
+    static constexpr int NREC = 24, NUSED = 21, NDIM = 2, NSIDE = 0, SIDE_CHUNKS = 0, THIRD = 2, NF = NREC;
     static constexpr bool EXT = true;
 };
 // 3-D Parker: 21 slots (particle_module.f90:4665-4670, 4686-4688, 2390-2401)
 template <> struct Rec<L3B> {
-    static constexpr int NREC = 24, NUSED = 21, NDIM = 3, NSIDE = 0, THIRD = 1, NF = NREC;
+    static constexpr int NREC = 24, NUSED = 21, NDIM = 3, NSIDE = 0, SIDE_CHUNKS = 0, THIRD = 1, NF = NREC;
     static constexpr bool EXT = false;
 };
 template <> struct Rec<L3E> {
-    static constexpr int NREC = 32, NUSED = 28, NDIM = 3, NSIDE = 0, THIRD = 1, NF = NREC;
+    static constexpr int NREC = 32, NUSED = 28, NDIM = 3, NSIDE = 0, SIDE_CHUNKS = 0, THIRD = 1, NF = NREC;
     static constexpr bool EXT = true;
 };
 // 2-D Parker + momentum diffusion WITHOUT the third dimension (BASELINE config C4, production build):
@@ -55,8 +55,19 @@ template <> struct Rec<L3E> {
 // [dvx_dy, dvy_dx of half 0 | the same of half 1].  144 B per grid point instead of L2E's 192 B, and
 // the gather keeps L2B's four lanes per particle instead of L2E's two.
 template <> struct Rec<L2D> {
-    static constexpr int NREC = 16, NUSED = 16, NDIM = 2, NSIDE = 2, THIRD = 0, NF = NREC + 4;
+    static constexpr int NREC = 16, NUSED = 16, NDIM = 2, NSIDE = 2, SIDE_CHUNKS = 0, THIRD = 0, NF = NREC + 4;
     static constexpr bool EXT = true;
+};
+
+// 3-D Parker, production build (BASELINE config C5): the 24-slot record split at the 128-byte line.  Record
+// plane = the first 16 slots of L3B (one line per grid point, both frames, four lanes per particle like L2B);
+// side plane = the remaining 5 slots (+3 pad) as two 32-byte chunks per grid point, same chunk format.  The
+// 192-byte L3B record straddles lines and only splits two ways (six chunks), which costs twice the L1
+// wavefronts per load instruction (profiles/r02b_push_coop_c5_ncu.txt: L1 data pipe 75 % busy).
+// SIDE_CHUNKS: side plane in chunk format (0: L2D's float4 format).
+template <> struct Rec<L3D> {
+    static constexpr int NREC = 16, NUSED = 16, NDIM = 3, NSIDE = 5, SIDE_CHUNKS = 2, THIRD = 1, NF = NREC + 8;
+    static constexpr bool EXT = false;
 };
 
 // packed position -> reference slot (1-based); 0 marks padding
@@ -70,15 +81,21 @@ __host__ __device__ constexpr int slot_of(int layout, int k)
          : (layout == L2D) ? (k < 15 ? l2[k] : 4)
          : (layout == L2E) ? l2[k]
          : (layout == L3B) ? (k < 21 ? l3[k] : 0)
+         : (layout == L3D) ? (k < 16 ? l3[k] : 0)
                            : l3[k];
 }
 __host__ __device__ constexpr int nrec_of(int layout)
 {
-    return (layout == L2B || layout == L2D) ? 16 : layout == L3E ? 32 : 24;
+    return (layout == L2B || layout == L2D || layout == L3D) ? 16 : layout == L3E ? 32 : 24;
 }
 // side plane: floats per grid point (both frames) behind the record plane, and the reference slots it holds
-__host__ __device__ constexpr int side_floats_of(int layout) { return layout == L2D ? 4 : 0; }
-__host__ __device__ constexpr int side_slot_of(int layout, int i) { return layout == L2D ? (i == 0 ? 10 : 12) : 0; }  // dvx_dy, dvy_dx
+__host__ __device__ constexpr int side_floats_of(int layout) { return layout == L2D ? 4 : layout == L3D ? 16 : 0; }
+__host__ __device__ constexpr int side_slot_of(int layout, int i)
+{
+    constexpr int l3s[8] = {28, 29, 30, 31, 32, 0, 0, 0};  // dbz_dy dbz_dz db_dx db_dy db_dz (positions 16..20 of L3B)
+    return layout == L2D ? (i == 0 ? 10 : i == 1 ? 12 : 0)  // dvx_dy, dvy_dx
+         : layout == L3D ? (i < 8 ? l3s[i] : 0) : 0;
+}
 
 // named positions inside a record
 namespace s2 {  // 2-D layouts

@@ -231,7 +231,29 @@ __device__ __forceinline__ void gather(const DevParams& prm, const float* __rest
         for (int e = 0; e < 4; ++e)
             F[4 * qd + e] = prm.time_interp ? (a[e] * rt1 + b[e] * rt) : a[e];
     }
-    if constexpr (Rec<L>::NSIDE > 0) {  // side plane (L2D): [s0 s1 of half 0 | s0 s1 of half 1] per grid point
+    if constexpr (Rec<L>::SIDE_CHUNKS > 0) {  // side plane in chunk format (L3D): same sums over the side chunks
+        const float* side = fld + (long long)prm.nxg * prm.nyg * prm.nzg * stride;
+        constexpr int SS = 8 * Rec<L>::SIDE_CHUNKS;
+#pragma unroll
+        for (int qd = 0; qd < Rec<L>::SIDE_CHUNKS; ++qd) {
+            double a[4] = {0.0, 0.0, 0.0, 0.0}, b[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const float* pc_ = side + (off[c] / stride) * SS + 8 * qd;
+                float4 fa = __ldg(reinterpret_cast<const float4*>(pc_ + hA));
+                a[0] = a[0] + (double)fa.x * w[c]; a[1] = a[1] + (double)fa.y * w[c];
+                a[2] = a[2] + (double)fa.z * w[c]; a[3] = a[3] + (double)fa.w * w[c];
+                if (prm.time_interp) {
+                    float4 fb = __ldg(reinterpret_cast<const float4*>(pc_ + hB));
+                    b[0] = b[0] + (double)fb.x * w[c]; b[1] = b[1] + (double)fb.y * w[c];
+                    b[2] = b[2] + (double)fb.z * w[c]; b[3] = b[3] + (double)fb.w * w[c];
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                F[NREC + 4 * qd + e] = prm.time_interp ? (a[e] * rt1 + b[e] * rt) : a[e];
+        }
+    } else if constexpr (Rec<L>::NSIDE > 0) {  // side plane (L2D): [s0 s1 of half 0 | s0 s1 of half 1] per grid point
         const float* side = fld + (long long)prm.nxg * prm.nyg * prm.nzg * stride;
         const int sA = prm.time_interp ? sel : 0, sB = sel ^ 1;
         double a[2] = {0.0, 0.0}, b[2] = {0.0, 0.0};
@@ -273,7 +295,26 @@ __device__ __forceinline__ void gather(const DevParams& prm, const float* __rest
 #pragma unroll
         for (int e = 0; e < 4; ++e) F[4 * qd + e] = a[e];
     }
-    if constexpr (Rec<L>::NSIDE > 0) {
+    if constexpr (Rec<L>::SIDE_CHUNKS > 0) {
+        const float* side = fld + (long long)prm.nxg * prm.nyg * prm.nzg * stride;
+        constexpr int SS = 8 * Rec<L>::SIDE_CHUNKS;
+#pragma unroll
+        for (int qd = 0; qd < Rec<L>::SIDE_CHUNKS; ++qd) {
+            double a[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                float4 f0, f1;
+                if (sel == 0) ldg256(side + (off[c] / stride) * SS + 8 * qd, f0, f1);
+                else ldg256(side + (off[c] / stride) * SS + 8 * qd, f1, f0);
+                a[0] = fma((double)f0.x, w0[c], a[0]); a[1] = fma((double)f0.y, w0[c], a[1]);
+                a[2] = fma((double)f0.z, w0[c], a[2]); a[3] = fma((double)f0.w, w0[c], a[3]);
+                a[0] = fma((double)f1.x, w1[c], a[0]); a[1] = fma((double)f1.y, w1[c], a[1]);
+                a[2] = fma((double)f1.z, w1[c], a[2]); a[3] = fma((double)f1.w, w1[c], a[3]);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) F[NREC + 4 * qd + e] = a[e];
+        }
+    } else if constexpr (Rec<L>::NSIDE > 0) {
         const float* side = fld + (long long)prm.nxg * prm.nyg * prm.nzg * stride;
         double a0 = 0.0, a1 = 0.0;
 #pragma unroll
@@ -1488,8 +1529,12 @@ template <int L> struct Coop {
     static constexpr bool SKEW = (G == 4);                        // G = 2 rows (NREC = 24) are conflict-free at +16 B
     // side plane (L2D): in round r lane gq of the group loads corner gq's float4 of particle r and parks its two
     // weighted partial sums behind the record part of the owner's row; the owner adds the four corners up
+    // Chunk-format side plane (L3D, two chunks per grid point): one load instruction brings the 128 contiguous
+    // bytes of an x-adjacent corner PAIR to the four lanes (lane gq: chunk gq & 1 of the corner with x-bit gq >> 1);
+    // over the four (y, z) pairs every lane ends with four partial sums, parked behind the record part.
     static constexpr int NSIDE = Rec<L>::NSIDE;
-    static constexpr int SIDEROW = NSIDE ? 2 * G : 0;             // doubles: G corners x 2 side slots
+    static constexpr int SCH = Rec<L>::SIDE_CHUNKS;
+    static constexpr int SIDEROW = SCH ? 4 * G : (NSIDE ? 2 * G : 0);   // doubles parked per owner row
     static constexpr int ROW = (SKEW ? NREC + 4 : NREC + 2) + SIDEROW;
     // parameter rows.  2-D: the owner publishes its eight finished corner weights (time blend and
     // conversion scale folded in) + the cell, 80 B; the other lanes of the group load them instead
@@ -1505,7 +1550,7 @@ template <int L> struct Coop {
 template <int L> struct MinBlocks { static constexpr int V = GPAT_MINBLOCKS; };
 #else
 // 3-D Parker at 4 CTAs spills 32 bytes and is still 6 % faster than 3 CTAs on C5 (profiles/README.md)
-template <int L> struct MinBlocks { static constexpr int V = (L == L2B || L == L3B || L == L2D) ? 4 : 3; };
+template <int L> struct MinBlocks { static constexpr int V = (L == L2B || L == L3B || L == L2D || L == L3D) ? 4 : 3; };
 #endif
 // SEL = which half of the store is farray1 (PushArgs::sel).  It is a template parameter because
 // the two frames must enter every sum in the order (farray1, farray2) whatever half they live in:
@@ -1589,10 +1634,19 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
             constexpr int DEPTH = (GPAT_COOP_DEPTH < C::G) ? GPAT_COOP_DEPTH : C::G;
             float4 lo[DEPTH][NLD], hi[DEPTH][NLD];
             float4 sd[DEPTH];  // side plane (L2D): corner gq of the round's particle
+            float4 slo[DEPTH][C::SCH ? 4 : 1], shi[DEPTH][C::SCH ? 4 : 1];  // side plane (L3D): the four (y, z) corner pairs
             auto issue = [&](int r, int slot) {
                 const long long cell = __double_as_longlong(par[(gbase + r) * C::PAR + (C::PUBW ? 8 : 4)]);
                 const float* base = fld + cell * stride + (gq * C::CPL) * 8;
-                if constexpr (C::NSIDE > 0) {
+                if constexpr (C::SCH > 0) {
+                    static_assert(C::G == 4 && C::NC == 8 && C::SCH == 2, "chunk-format side plane: 3-D, two chunks, four lanes");
+                    const float* side = fld + (long long)prm.nxg * prm.nyg * prm.nzg * stride;
+                    const float* sb = side + (cell + (gq >> 1)) * 16 + (gq & 1) * 8;
+#pragma unroll
+                    for (int pr = 0; pr < 4; ++pr)
+                        ldg256(sb + ((long long)(pr & 1) * prm.nxg + (long long)(pr >> 1) * prm.nxg * prm.nyg) * 16,
+                               slo[slot][pr], shi[slot][pr]);
+                } else if constexpr (C::NSIDE > 0) {
                     static_assert(C::G == 4 && C::NC == 4 && C::PUBW, "side plane: one corner per lane of the group");
                     const float* side = fld + (long long)prm.nxg * prm.nyg * prm.nzg * stride;
                     sd[slot] = __ldg(reinterpret_cast<const float4*>(
@@ -1655,11 +1709,29 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                     }
                 }
                 double2 sidep = make_double2(0.0, 0.0);
-                if constexpr (C::NSIDE > 0) {
+                double sacc[4] = {0.0, 0.0, 0.0, 0.0};
+                if constexpr (C::SCH > 0) {
+                    const bool xb = (gq >> 1) != 0;
+#pragma unroll
+                    for (int pr = 0; pr < 4; ++pr) {  // corner = x-bit | pr << 1: same weights as the record part
+                        const double wa = xb ? w0[2 * pr + 1] : w0[2 * pr], wb = xb ? w1[2 * pr + 1] : w1[2 * pr];
+                        if constexpr (SEL == 0) {
+                            fma_chunk<0, 0>(2 * pr, slo[slot][pr], wa, sacc);
+                            fma_chunk<0, 1>(2 * pr, shi[slot][pr], wb, sacc);
+                        } else {
+                            fma_chunk<0, 1>(2 * pr, shi[slot][pr], wb, sacc);
+                            fma_chunk<0, 0>(2 * pr, slo[slot][pr], wa, sacc);
+                        }
+                    }
+                } else if constexpr (C::NSIDE > 0) {
                     // this lane's corner: weights of half 0 / half 1 from the owner's published row (w0[gq], w1[gq])
                     static_assert(cvt_weight_scale(0, 0) == cvt_weight_scale(1, 0) && cvt_weight_scale(0, 1) == cvt_weight_scale(1, 1),
                                   "the side gather assumes a conversion mask that does not depend on the row");
-                    const double wa = par[owner * C::PAR + gq], wb = par[owner * C::PAR + 4 + gq];
+                    // (selected from the registers the record part already loaded: a second trip to the parameter
+                    // row costs two 4-wavefront LDS.64 per round, profiles/r02c_push_coop_c4_l2d_ncu.txt)
+                    const bool g1 = (gq & 1) != 0, g2 = (gq & 2) != 0;
+                    const double wa = g2 ? (g1 ? w0[3] : w0[2]) : (g1 ? w0[1] : w0[0]);
+                    const double wb = g2 ? (g1 ? w1[3] : w1[2]) : (g1 ? w1[1] : w1[0]);
                     const float4 e = sd[slot];
                     if constexpr (SEL == 0) {
                         sidep.x = fma(cvt_sel<0, 1>(e.z), wb, cvt_sel<0, 0>(e.x) * wa);
@@ -1671,7 +1743,11 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                 }
                 if (r + DEPTH < C::G) issue(r + DEPTH, slot);
                 double2* out = reinterpret_cast<double2*>(res + C::row_off(owner) + (gq * C::CPL) * 4);
-                if constexpr (C::NSIDE > 0)
+                if constexpr (C::SCH > 0) {
+                    double2* so = reinterpret_cast<double2*>(res + C::row_off(owner) + C::NREC + 4 * gq);
+                    so[0] = make_double2(sacc[0], sacc[1]);
+                    so[1] = make_double2(sacc[2], sacc[3]);
+                } else if constexpr (C::NSIDE > 0)
                     *reinterpret_cast<double2*>(res + C::row_off(owner) + C::NREC + 2 * gq) = sidep;
 #pragma unroll
                 for (int j = 0; j < C::CPL; ++j) {
@@ -1692,7 +1768,15 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                 F[2 * k] = v.x;
                 F[2 * k + 1] = v.y;
             }
-            if constexpr (C::NSIDE > 0) {  // the four corners' partial sums, always in corner order
+            if constexpr (C::SCH > 0) {  // lanes (0, 2) hold chunk 0 at x-bit 0 / 1, lanes (1, 3) chunk 1
+                const double2* sr = row + C::NREC / 2;
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    const double2 a0 = sr[2 * ch], a1 = sr[2 * ch + 1], b0 = sr[2 * (ch + 2)], b1 = sr[2 * (ch + 2) + 1];
+                    F[C::NREC + 4 * ch] = a0.x + b0.x; F[C::NREC + 4 * ch + 1] = a0.y + b0.y;
+                    F[C::NREC + 4 * ch + 2] = a1.x + b1.x; F[C::NREC + 4 * ch + 3] = a1.y + b1.y;
+                }
+            } else if constexpr (C::NSIDE > 0) {  // the four corners' partial sums, always in corner order
                 const double2 c0 = row[C::NREC / 2], c1 = row[C::NREC / 2 + 1], c2 = row[C::NREC / 2 + 2], c3 = row[C::NREC / 2 + 3];
                 F[C::NREC] = ((c0.x + c1.x) + c2.x) + c3.x;
                 F[C::NREC + 1] = ((c0.y + c1.y) + c2.y) + c3.y;
@@ -1764,7 +1848,7 @@ void launch_one(const DevParams& prm, const PtlSoA& P, const float* fld, const P
                 cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, dev);
                 if (l2_bytes <= 0) l2_bytes = 64 << 20;
             }
-            const double per_cta = (double)sm_count * kBlock * C_NC<L>() * (2.0 * Rec<L>::NREC * 4.0);
+            const double per_cta = (double)sm_count * kBlock * C_NC<L>() * ((2.0 * Rec<L>::NREC + side_floats_of(L)) * 4.0);
             int cap = (int)(0.5 * (double)l2_bytes / per_cta + 0.5);
             if (cap < 1) cap = 1;
             // Cell-sorted particles (sort.cu) share their records across the lanes of a warp: the working
@@ -1834,6 +1918,7 @@ void GPAT_LAUNCH(int layout, const DevParams& prm, const PtlSoA& P, const float*
         case L3B: launch_one<L3B>(prm, P, fld, a, sm_count, st); break;
 #if !GPAT_STRICT
         case L2D: launch_one<L2D>(prm, P, fld, a, sm_count, st); break;  // production build only (abi.cu: pick_layout)
+        case L3D: launch_one<L3D>(prm, P, fld, a, sm_count, st); break;
 #endif
         default: launch_one<L3E>(prm, P, fld, a, sm_count, st); break;
     }
@@ -1851,6 +1936,7 @@ void launch_interp_debug(int layout, const DevParams& prm, const float* fld, int
         case L2E: interp_kernel<L2E><<<grid, 128, 0, st>>>(prm, fld, sel, n, x, y, z, rt, out32); break;
         case L3B: interp_kernel<L3B><<<grid, 128, 0, st>>>(prm, fld, sel, n, x, y, z, rt, out32); break;
         case L2D: interp_kernel<L2D><<<grid, 128, 0, st>>>(prm, fld, sel, n, x, y, z, rt, out32); break;
+        case L3D: interp_kernel<L3D><<<grid, 128, 0, st>>>(prm, fld, sel, n, x, y, z, rt, out32); break;
         default: interp_kernel<L3E><<<grid, 128, 0, st>>>(prm, fld, sel, n, x, y, z, rt, out32); break;
     }
 }

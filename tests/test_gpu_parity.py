@@ -956,7 +956,8 @@ def test_gpu_against_reference_golden(name):
     got = golden_collect(lambda P, n: _GpuForGolden(P, n), name)
     assert np.array_equal(got["grad_sha256"], z["grad_sha256"]), "calc_fields_gradients differs from the reference"
     used = np.any(got["interp"] != 0.0, axis=0)
-    assert used.sum() >= 15 and np.array_equal(got["interp"][:, used], z["interp"][:, used])
+    # (a slot of a synthetic field can be identically zero, e.g. vz of the flare sheet: it then counts as unused)
+    assert used.sum() >= 12 and np.array_equal(got["interp"][:, used], z["interp"][:, used])
     # injection order: 16 particles each with dist_flag 1 (delta: no transcendental), 0 (Maxwellian: exp), 2 (power law:
     # pow) -- the first group bit for bit, the others to the ulps of libdevice's exp / pow
     assert_particles_identical(got["inject"][:16], z["inject"][:16], name + " inject (delta)")
@@ -979,22 +980,25 @@ def test_gpu_against_reference_golden(name):
             assert rel_err(got[k], z[k]) < 1e-6, k
 
 
-def test_side_plane_layout_matches_the_extended_record(monkeypatch):
-    """Config C4's production layout (L2D: the 2-D Parker line with rho in its pad slot + a side plane for
-    dvx_dy / dvy_dx, four lanes per particle) against the 24-slot extended record (L2E, GPAT_NO_L2D=1) it
-    replaces: interpolated fields bit for bit, 30 pushes to 1e-12, and a whole interval with histograms."""
-    w, P, frames, ts = make_case("c4", grid=64, nptl=512)
+@pytest.mark.parametrize("key,grid,env,nslots,absent", [("c4", 64, "GPAT_NO_L2D", 18, 2), ("c5", 32, "GPAT_NO_L3D", 21, 3)])
+def test_side_plane_layouts_match_the_one_plane_records(monkeypatch, key, grid, env, nslots, absent):
+    """The production layouts with a side plane -- L2D (config C4: the 2-D Parker line with rho in its pad slot +
+    dvx_dy / dvy_dx behind it) and L3D (config C5: the 3-D record split at the 128-byte line), both gathered by
+    four lanes per particle -- against the one-plane records they replace (L2E / L3B, selected by GPAT_NO_L2D /
+    GPAT_NO_L3D): interpolated fields bit for bit, 30 pushes to 1e-12, and whole intervals with histograms."""
+    w, P, frames, ts = make_case(key, grid=grid, nptl=512)
     P.strict_math = 0
     n = 300
     rng = np.random.default_rng(5)
     x, y = rng.uniform(P.xmin, P.xmax, n), rng.uniform(P.ymin, P.ymax, n)
-    z, rt = np.zeros(n), rng.uniform(0, 1, n)
+    z = rng.uniform(P.zmin, P.zmax, n) if P.ndim == 3 else np.zeros(n)
+    rt = rng.uniform(0, 1, n)
     out = {}
-    for tag, env in (("side", None), ("ext", "1")):
-        if env:
-            monkeypatch.setenv("GPAT_NO_L2D", env)
+    for tag, val in (("side", None), ("one", "1")):
+        if val:
+            monkeypatch.setenv(env, val)
         else:
-            monkeypatch.delenv("GPAT_NO_L2D", raising=False)
+            monkeypatch.delenv(env, raising=False)
         g = GpatSim(P, w.nptl_max)
         load_fields((g,), frames, P.time_interp)
         fi = g.interp(x, y, z, rt)
@@ -1006,13 +1010,14 @@ def test_side_plane_layout_matches_the_extended_record(monkeypatch):
         rec, steps = run_intervals(g, frames, ts, nptl=512, particle_v0=w.particle_v0, split_flag=0)
         out[tag] = (fi, s, a, rec, steps, sort_by_key(g.download_particles()))
         g.close()
-    fs, fe = out["side"][0], out["ext"][0]
+    fs, fe = out["side"][0], out["one"][0]
     used = np.any(fs != 0.0, axis=0)
-    assert used.sum() == 18 and not np.any(fs[:, 2] != 0.0)          # 18 slots, no vz
+    assert used.sum() == nslots and not np.any(fs[:, absent] != 0.0)   # C4: no vz; C5: no rho
     assert np.array_equal(fs[:, used], fe[:, used])
-    assert out["side"][1] == out["ext"][1]
-    assert_particles_close(out["side"][2], out["ext"][2], STEP_RTOL * 8, "L2D vs L2E, 30 pushes", frac_outliers=0.004)
-    assert abs(out["side"][4] - out["ext"][4]) <= 2e-3 * out["ext"][4]
-    assert_particles_close(out["side"][5], out["ext"][5], FRAME_RTOL, "L2D vs L2E, intervals", int_exact=False,
-                           frac_outliers=0.01)
-    assert np.abs(out["side"][3][-1]["fglobal"] - out["ext"][3][-1]["fglobal"]).sum() <= 4.0
+    assert out["side"][1] == out["one"][1]
+    assert_particles_close(out["side"][2], out["one"][2], STEP_RTOL * 8, "side plane vs one plane, 30 pushes",
+                           frac_outliers=0.004)
+    assert abs(out["side"][4] - out["one"][4]) <= 2e-3 * out["one"][4]
+    assert_particles_close(out["side"][5], out["one"][5], FRAME_RTOL, "side plane vs one plane, intervals",
+                           int_exact=False, frac_outliers=0.01)
+    assert np.abs(out["side"][3][-1]["fglobal"] - out["one"][3][-1]["fglobal"]).sum() <= 4.0
