@@ -759,7 +759,7 @@ class TypeSpec:
         return self.base.startswith("type:")
 
 
-_KIND_NAMES = {"sp": 4, "dp": 8, "real32": 4, "real64": 8, "4": 4, "8": 8, "fp": 4}
+_KIND_NAMES = {"sp": 4, "dp": 8, "real32": 4, "real64": 8, "4": 4, "8": 8, "fp": 4, "c_double": 8, "c_float": 4}
 
 
 def split_top(s, sep=","):
@@ -855,11 +855,11 @@ def parse_declaration(text):
             intent = re.sub(r"\s", "", al[al.index("(") + 1:al.rindex(")")])
         elif al == "parameter":
             parameter = True
-        elif al == "allocatable":
+        elif al in ("allocatable", "pointer"):
             allocatable = True
         elif al == "optional":
             optional = True
-        elif al in ("save", "target", "private", "public", "value", "volatile", "contiguous"):
+        elif al in ("save", "target", "private", "public", "value", "volatile", "contiguous") or al.startswith("bind"):
             pass
         else:
             raise NotImplementedError(f"attribute {a!r} in {text!r}")

@@ -1357,7 +1357,7 @@ __device__ __forceinline__ void store_lane(const PushArgs& a, const PtlSoA& P, l
 }
 
 // idle lanes take the next particles of the work counter (one warp-aggregated atomic)
-template <bool TRACK = false>
+template <bool TRACK = false, bool PERM4 = false>
 __device__ __forceinline__ void refill(const DevParams& prm, const PushArgs& a, const PtlSoA& P,
                                        unsigned lane, Lane& q, int& state, long long& idx,
                                        bool& exhausted, int& remaining)
@@ -1371,7 +1371,27 @@ __device__ __forceinline__ void refill(const DevParams& prm, const PushArgs& a, 
     if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)__popc(m));
     base = __shfl_sync(0xffffffffu, base, leader);
     if (want) {
-        idx = (long long)(base + __popc(m & ((1u << lane) - 1u)));
+        unsigned rank;
+        if (PERM4) {
+            // Lane-group kernels with four lanes per particle serve, in round r, the particles of lanes r, 4 + r, 8 + r ...
+            // Hand consecutive queue entries to exactly those lanes (virtual position (lane & 3) * 8 + lane / 4): with
+            // cell-sorted particles the eight gathers of one load instruction then touch NEIGHBOURING grid points, and
+            // the x + 1 corner of one particle is the x corner of the next -- an L1 hit a few instructions later.
+            unsigned mp = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                unsigned t = (m >> k) & 0x11111111u;         // lanes 4g + k -> bit 4g
+                t = (t | (t >> 3)) & 0x03030303u;
+                t = (t | (t >> 6)) & 0x000F000Fu;
+                t = (t | (t >> 12)) & 0x000000FFu;           // -> bit g
+                mp |= t << (8 * k);
+            }
+            const unsigned v = (lane & 3u) * 8u + (lane >> 2);
+            rank = __popc(mp & ((1u << v) - 1u));
+        } else {
+            rank = __popc(m & ((1u << lane) - 1u));
+        }
+        idx = (long long)(base + rank);
         if (idx >= a.nptl) {
             exhausted = true;
         } else {
@@ -1473,6 +1493,9 @@ push_kernel(const __grid_constant__ DevParams prm, const PtlSoA P, const float* 
 // with final values of the slots of its chunks, parked in shared memory for the owner lane.
 #ifndef GPAT_COOP_DEPTH
 #define GPAT_COOP_DEPTH 1
+#endif
+#ifndef GPAT_NO_PERM
+#define GPAT_NO_PERM 0   // 1: A/B build without the neighbour-preserving lane assignment of refill()
 #endif
 // FP32 -> FP64 on the integer pipe.  F2F.F64.F32 runs on the XU at 16 lanes/clk/SM (2 cycles per
 // warp instruction, scripts/micro/pipes.cu) and the 128 conversions of a 2-D step were the busiest
@@ -1581,7 +1604,7 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
     unsigned long long nsteps = 0;
 
     for (;;) {
-        refill<TRACK>(prm, a, P, lane, q, state, idx, exhausted, remaining);
+        refill<TRACK, (C::G == 4) && !GPAT_NO_PERM>(prm, a, P, lane, q, state, idx, exhausted, remaining);
         if (__all_sync(0xffffffffu, state == ST_IDLE)) {
             if (__all_sync(0xffffffffu, exhausted)) break;
             continue;

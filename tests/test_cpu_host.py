@@ -255,6 +255,69 @@ def test_fortran_interface_binds_every_entry_point():
         assert field in text, field
 
 
+def test_fortran_interface_parses_and_matches_the_c_layouts():
+    """No Fortran compiler exists in this image or on the B200 box (profiles/r02a_fortran_probe.log), so the interface
+    module cannot be compiled.  Next best: the Fortran front-end this repository does have (oracle/f90/f90run.py, the
+    one that executes the reference) reads it -- the module must parse, `gpat_check` must translate, every bind(C)
+    derived type must list the C struct's fields in the same order with the same kinds and extents, and every
+    interface must have as many dummy arguments as its C prototype."""
+    import ctypes as C
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "f90"))
+    import f90run as F
+    from stochastic_parker_b200 import abi
+    path = os.path.join(ROOT, "fortran", "gpat_cuda_iface.f90")
+    prog = F.Program()
+    prog.load_file(path)
+    mod = prog.modules["gpat_cuda"]
+    assert not [n for n, p in mod.procs.items() if isinstance(p, Exception)]
+    prog.externals.update(mpi_finalize=lambda *a: (), c_f_pointer=lambda *a, **k: ())
+    assert "gpat_check" in mod.procs and prog.sources is not None
+    kinds = {"c_int8_t": C.c_int8, "c_int32_t": C.c_int32, "c_int64_t": C.c_int64, "c_int": C.c_int, "c_double": C.c_double,
+             "c_float": C.c_float}
+    structs = {"gpat_params": abi.Params, "gpat_hist_spec": abi.HistSpec, "gpat_counters": abi.Counters,
+               "gpat_timings": abi.Timings}
+    for tname, cstruct in structs.items():
+        f_fields = mod.types[tname]
+        c_fields = [(n, t) for n, t in cstruct._fields_]
+        assert len(f_fields) == len(c_fields), (tname, len(f_fields), len(c_fields))
+        for (fn, ts), (cn, ct) in zip(f_fields, c_fields):
+            assert fn.rstrip("_") == cn.rstrip("_"), (tname, fn, cn)
+            n = 1
+            if ts.dims:
+                n = int(ts.dims[0][1])
+            if ts.is_struct:
+                base = structs[ts.base[5:]]
+            else:
+                base = kinds[(ts.kind_src or "").strip().lower()]
+                assert (ts.base == "int") == (base not in (C.c_double, C.c_float)), (tname, fn)
+            want = base * n if n > 1 else base
+            got_size, want_size = C.sizeof(ct), C.sizeof(want)
+            assert got_size == want_size, (tname, fn, got_size, want_size)
+            if cn == "seed":
+                continue  # uint64_t in C, integer(c_int64_t) in Fortran (no unsigned kinds)
+            assert (ct._type_ if hasattr(ct, "_length_") else ct) in (base, getattr(base, "_type_", None)) or \
+                C.sizeof(ct._type_ if hasattr(ct, "_length_") else ct) == C.sizeof(base), (tname, fn)
+    # particle record: 104 bytes, same order
+    pf = [n.rstrip("_") for n, _ in mod.types["gpat_particle"]]
+    assert pf == ["split_times", "count_flag", "pad", "origin", "nsteps_tracked", "nsteps_pushed", "tag_injected",
+                  "tag_splitted", "x", "y", "z", "p", "v", "mu", "weight", "t", "dt", "padding"]
+    # arity of every interface against the C prototypes
+    lines = [t for _, t in F.read_logical_lines(path)]
+    f_arity = {}
+    for t in lines:
+        m = re.match(r'^(?:[\w()]+\s+)?(?:function|subroutine)\s+(gpat_\w+)\s*\((.*?)\)\s*bind\(C', t, re.I)
+        if m:
+            f_arity[m.group(1).lower()] = len([a for a in m.group(2).split(",") if a.strip()])
+    htext = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    c_arity = {}
+    for m in re.finditer(r"\b(gpat_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", htext):
+        args = m.group(2).strip()
+        c_arity[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    assert len(f_arity) >= 30
+    for name, n in f_arity.items():
+        assert c_arity[name] == n, (name, n, c_arity[name])
+
+
 # ---- parameter validation: runs before the device is touched, so it is testable here ------------------
 @pytest.mark.parametrize("change,message", [
     (dict(spherical_coord=1), "spherical coordinates are outside the GPU path"),

@@ -957,7 +957,7 @@ def test_gpu_against_reference_golden(name):
     assert np.array_equal(got["grad_sha256"], z["grad_sha256"]), "calc_fields_gradients differs from the reference"
     used = np.any(got["interp"] != 0.0, axis=0)
     # (a slot of a synthetic field can be identically zero, e.g. vz of the flare sheet: it then counts as unused)
-    assert used.sum() >= 12 and np.array_equal(got["interp"][:, used], z["interp"][:, used])
+    assert used.sum() >= (8 if name.startswith("s1") else 12) and np.array_equal(got["interp"][:, used], z["interp"][:, used])
     # injection order: 16 particles each with dist_flag 1 (delta: no transcendental), 0 (Maxwellian: exp), 2 (power law:
     # pow) -- the first group bit for bit, the others to the ulps of libdevice's exp / pow
     assert_particles_identical(got["inject"][:16], z["inject"][:16], name + " inject (delta)")
