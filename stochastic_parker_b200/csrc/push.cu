@@ -1893,6 +1893,7 @@ void launch_one(const DevParams& prm, const PtlSoA& P, const float* fld, const P
             prm.acc_region_flag != 1 && prm.time_interp && !a.generic) {
             const int want = 1 | (prm.mag_dependency == 1 ? 2 : 0) | (prm.momentum_dependency == 1 ? 4 : 0);
             if (Rec<L>::NDIM == 2 && (want == kSpec11 || (L == L2B && want == kSpec01))) spec = want;
+            if (L == L3D && want == kSpec10 && !prm.acc_by_surface && !getenv("GPAT_NO_SPEC3D")) spec = want;
         }
         auto go = [&](auto sel_c, auto trk_c, auto spec_c) {
             push_kernel_coop<L, decltype(sel_c)::value, decltype(trk_c)::value, decltype(spec_c)::value>
@@ -1908,6 +1909,9 @@ void launch_one(const DevParams& prm, const PtlSoA& P, const float* fld, const P
             }
             if constexpr (Rec<L>::NDIM == 3) {  // run-time switches + the acceleration-surface gate
                 if (prm.acc_by_surface) { go(sel_c, trk_c, std::integral_constant<int, kSpecSurf>{}); return; }
+            }
+            if constexpr (L == L3D) {
+                if (spec == kSpec10) { go(sel_c, trk_c, std::integral_constant<int, kSpec10>{}); return; }
             }
             go(sel_c, trk_c, I{});
         };

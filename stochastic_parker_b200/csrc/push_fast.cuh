@@ -30,6 +30,7 @@ __device__ __forceinline__ double min2f(double a, double b) { return (a < b) ? a
 // instructions on C1, profiles/r01f_push_coop_spec_ncu.txt).  SPEC = 0 reads every switch at run time.
 constexpr int kSpec11 = 1 | 2 | 4;  // mag_dependency = 1, momentum_dependency = 1 (C1, C2, C4)
 constexpr int kSpec01 = 1 | 4;      // mag_dependency = 0, momentum_dependency = 1 (C3)
+constexpr int kSpec10 = 1 | 2;      // mag_dependency = 1, momentum_dependency = 0 (C5; instantiated for L3D only)
 // bit 0 clear: every switch is read at run time.  kSpecSurf adds the acc_by_surface gate of the 3-D
 // pusher (particle_module.f90:4887-4892) to that generic code, so runs without surfaces never carry it.
 constexpr int kSpecSurf = 8;
