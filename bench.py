@@ -435,6 +435,10 @@ def main():
             with open(tpath) as f:
                 tj = json.load(f)
             traffic = tj.get(f"{args.workload}_dram_bytes_per_launch")
+            if traffic is None:  # per-step DRAM bytes measured on this config's full-size grid x the steps of one launch
+                per_step = tj.get("dram_bytes_per_step", {}).get(args.workload, {}).get("dram_bytes_per_step")
+                if per_step is not None:
+                    traffic = per_step * tot["steps"] / max(1, args.steps)
             pipes = tj.get(f"{args.workload}_pipes")
         except Exception:
             traffic = None

@@ -1705,12 +1705,25 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                         const double rz = par[owner * C::PAR + 5];
                         const double rz1 = 1.0 - rz;
                         const double wxy[4] = {rx1 * ry1, rx * ry1, rx1 * ry, rx * ry};
-                        const double z00 = rz1 * t0, z10 = rz * t0, z01 = rz1 * t1, z11 = rz * t1;
+                        if constexpr (cvt_weight_scale(0, 0) == cvt_weight_scale(1, 0) &&
+                                      cvt_weight_scale(0, 1) == cvt_weight_scale(1, 1)) {
+                            // the conversion scale does not depend on the row: fold it into the four z x time factors
+                            // (a power of two: bit-identical to scaling each of the sixteen weights)
+                            const double s0 = cvt_weight_scale(0, 0), s1 = cvt_weight_scale(0, 1);
+                            const double z00 = rz1 * t0 * s0, z10 = rz * t0 * s0, z01 = rz1 * t1 * s1, z11 = rz * t1 * s1;
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const double s0 = cvt_weight_scale(c >> 1, 0), s1 = cvt_weight_scale(c >> 1, 1);
-                            w0[c] = wxy[c] * z00 * s0; w0[c + 4] = wxy[c] * z10 * s0;
-                            w1[c] = wxy[c] * z01 * s1; w1[c + 4] = wxy[c] * z11 * s1;
+                            for (int c = 0; c < 4; ++c) {
+                                w0[c] = wxy[c] * z00; w0[c + 4] = wxy[c] * z10;
+                                w1[c] = wxy[c] * z01; w1[c + 4] = wxy[c] * z11;
+                            }
+                        } else {
+                            const double z00 = rz1 * t0, z10 = rz * t0, z01 = rz1 * t1, z11 = rz * t1;
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const double s0 = cvt_weight_scale(c >> 1, 0), s1 = cvt_weight_scale(c >> 1, 1);
+                                w0[c] = wxy[c] * z00 * s0; w0[c + 4] = wxy[c] * z10 * s0;
+                                w1[c] = wxy[c] * z01 * s1; w1[c + 4] = wxy[c] * z11 * s1;
+                            }
                         }
                     }
                 }
