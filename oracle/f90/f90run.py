@@ -361,6 +361,29 @@ def cv_any(v):
     return v
 
 
+class FStr(str):
+    """A Fortran character value: substring s(i:j) is 1-based with an inclusive end, comparison ignores trailing blanks"""
+
+    def __getitem__(self, key):
+        if isinstance(key, slice):
+            lo = 1 if key.start is None else int(key.start)
+            hi = len(self) if key.stop is None else int(key.stop)
+            return FStr(str.__getitem__(self, slice(lo - 1, hi)))
+        return FStr(str.__getitem__(self, int(key) - 1))
+
+    def __eq__(self, other):
+        return str(self).rstrip() == str(other).rstrip()
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    __hash__ = str.__hash__
+
+
+def cv_char(v):
+    return v if isinstance(v, (FStr, Undefined)) or v is None else FStr(v)
+
+
 def cv_struct(v):
     return v.copy()
 
@@ -985,7 +1008,7 @@ class Program:
         self._consts = {}
         self.glob = {"f4": f4, "f8": f8, "f_div": f_div, "f_pow": f_pow, "DoRange": DoRange, "FArray": FArray,
                      "Undefined": Undefined, "cv_int": cv_int, "cv_r4": cv_r4, "cv_r8": cv_r8, "cv_bool": cv_bool,
-                     "cv_any": cv_any, "cv_struct": cv_struct, "I": INTRINSICS, "i_arrcons": i_arrcons,
+                     "cv_any": cv_any, "cv_char": cv_char, "cv_struct": cv_struct, "I": INTRINSICS, "i_arrcons": i_arrcons,
                      "FortranStop": FortranStop, "np": np, "_prog": self, "realloc_assign": realloc_assign}
 
     def const(self, value):
@@ -1137,7 +1160,7 @@ class Program:
         return self.struct_class(r[1], r[2])
 
     def converter(self, ts, modname=None):
-        return {"int": cv_int, "r4": cv_r4, "r8": cv_r8, "bool": cv_bool, "char": cv_any}.get(ts.base, cv_struct)
+        return {"int": cv_int, "r4": cv_r4, "r8": cv_r8, "bool": cv_bool, "char": cv_char}.get(ts.base, cv_struct)
 
     def np_dtype(self, ts):
         return {"int": np.int64, "r4": np.float32, "r8": np.float64, "bool": bool}.get(ts.base, object)
@@ -1530,7 +1553,7 @@ class ExprCompiler:
 # ------------------------------------------------------------------------------------------------
 # procedure compiler
 # ------------------------------------------------------------------------------------------------
-_CONV = {"int": "cv_int", "r4": "cv_r4", "r8": "cv_r8", "bool": "cv_bool", "char": "cv_any"}
+_CONV = {"int": "cv_int", "r4": "cv_r4", "r8": "cv_r8", "bool": "cv_bool", "char": "cv_char"}
 
 
 class ProcCompiler:
@@ -1565,6 +1588,8 @@ class ProcCompiler:
             if ts.is_array:
                 lbs = ", ".join(self.ec.compile(lb) if lb is not None else "1" for lb, _ in ts.dims)
                 self.emit(f"v_{a} = _prog.as_dummy(v_{a}, ({lbs},), {len(ts.dims)})")
+            elif ts.base == "char":
+                self.emit(f"v_{a} = cv_char(v_{a})")
         for name, ts in p.decls.items():
             if name in p.args:
                 continue

@@ -269,7 +269,45 @@ class RefSim:
         return self._farray(slot).a.transpose(3, 2, 1, 0).copy(order='C')
 
     def swap_fields(self):
+        """what MAIN:537-547 does at the end of an interval: copy_fields (+ surfaces, maps)"""
         self.call("mhd_data_parallel", "copy_fields")
+        if self.P.acc_by_surface:
+            self.call("acc_region_surface", "copy_acc_surface")
+        if self.P.deltab_flag:
+            self.call("mhd_data_parallel", "copy_magnetic_fluctuation")
+        if self.P.correlation_flag:
+            self.call("mhd_data_parallel", "copy_correlation_length")
+
+    # ---- turbulence maps (MD:107-182, 306-497, 771-1604) and acceleration surfaces (acc_region_surface.f90) -------------
+    def upload_turbulence(self, which: int, slot: int, slab: np.ndarray, two_d: np.ndarray):
+        """read_magnetic_fluctuation (which = 0) / read_correlation_length (1): the file content goes into component 1
+        of the slab / 2-D arrays, then the reference's own gradient passes fill components 2..4"""
+        md = self.M["mhd_data_parallel"]
+        names = (("sigma2_slab", "sigma2_2d", "init_magnetic_fluctuation", "calc_grad_sigma2_slab", "calc_grad_sigma2_2d"),
+                 ("lc_slab", "lc_2d", "init_correlation_length", "calc_grad_lc_slab", "calc_grad_lc_2d"))[which]
+        if md.__dict__.get(names[0] + "_1") is None:
+            self.call("mhd_data_parallel", names[2])
+        suffix = "_1" if slot == 0 else "_2"
+        for nm, data in ((names[0], slab), (names[1], two_d)):
+            arr = getattr(md, nm + suffix)
+            arr.a[0] = np.ascontiguousarray(data, dtype=np.float32).reshape(self.grid_shape).transpose(2, 1, 0)
+        self.call("mhd_data_parallel", names[3], slot)
+        self.call("mhd_data_parallel", names[4], slot)
+
+    def upload_acc_surface(self, which: int, slot: int, heights: np.ndarray):
+        """read_acc_surface, whole-plane branch: heights (n2, n1) C-order == acc_surfaceK{1,2}(-1:n1+2, -1:n2+2)"""
+        P, ar = self.P, self.M["acc_region_surface"]
+        if ar.__dict__.get("acc_surface11") is None:
+            def norm(v):
+                return ("+" if v > 0 else "-") + "xyz"[abs(v) - 1]
+            if P.surface2_existed:
+                self.call("acc_region_surface", "init_acc_surface", int(P.time_interp), norm(P.surface_norm1),
+                          norm(P.surface_norm2), bool(P.is_intersection))
+            else:
+                self.call("acc_region_surface", "init_acc_surface", int(P.time_interp), norm(P.surface_norm1))
+        arr = getattr(ar, f"acc_surface{which + 1}{slot + 1}")
+        h = np.ascontiguousarray(heights, dtype=np.float64)
+        arr.a[...] = h.reshape(arr.a.shape[1], arr.a.shape[0]).T
 
     def interp(self, x, y, z, rt) -> np.ndarray:
         """get_interp_paramters + interp_fields at given points (the px/py/pz arithmetic of PM:1622-1624)"""

@@ -398,3 +398,48 @@ def test_shock_injection_equals_the_reference_in_1d_and_is_undefined_beyond():
     r.upload_fields(1, frames[1])
     with pytest.raises(RuntimeError, match="sx1' before assigning"):
         r.inject_at_shock(50, 1e-4, 2, w.particle_v0, 0.0, 6.2)
+
+
+@pytest.mark.skipif(not refsim.available(), reason="/root/reference is not present on this box")
+@pytest.mark.parametrize("key,grid,cli", [("c1", 24, {}), ("c1", 24, dict(nlgc=1, kperp_kpara=0.05)), ("c5", 12, {})])
+def test_turbulence_maps_equal_the_reference(key, grid, cli):
+    """deltab_flag + correlation_flag: init_magnetic_fluctuation / init_correlation_length, calc_grad_sigma2_slab/_2d,
+    calc_grad_lc_slab/_2d, interp_magnetic_fluctuation, interp_correlation_length, copy_* and their terms in both kappa
+    routines (MD:107-182, 771-1604, 1806-1941; PM:2246-2254, 2505-2517), two intervals from the reference's source
+    against the C oracle, bit for bit."""
+    from helpers import make_case
+    from stochastic_parker_b200 import mhd
+    from stochastic_parker_b200.driver import run_intervals
+    w, P, frames, ts = make_case(key, grid=grid, nptl=16, conf=dict(dt_min_rel=1e-3), cli=cli)
+    P.deltab_flag, P.correlation_flag, P.strict_math = 1, 1, 1
+    maps = [mhd.make_turbulence_maps(w.nx, w.ny, w.nz, f, P.ndim, w.dt_out) for f in range(3)]
+    out = []
+    for cls in (refsim.RefSim, Oracle):
+        s = cls(P, w.nptl_max)
+        rec, steps = run_intervals(s, frames, ts, nptl=16, particle_v0=w.particle_v0, split_flag=1, pmin_split=1.05,
+                                   split_ratio=1.05, maps=lambda which, f: (maps[f][2 * which], maps[f][2 * which + 1]))
+        out.append((s.download_particles(), steps, rec))
+    assert out[0][1] == out[1][1] > 2000
+    assert_particles_identical(out[0][0], out[1][0], "turbulence maps")
+    assert np.array_equal(out[0][2][-1]["fglobal"], out[1][2][-1]["fglobal"])
+
+
+@pytest.mark.skipif(not refsim.available(), reason="/root/reference is not present on this box")
+@pytest.mark.parametrize("name", ["c5_3d_acc_surfaces_union", "c5_3d_acc_surface_no_time_interp",
+                                  "c5_3d_ft_acc_surfaces_intersection"])
+def test_acceleration_surfaces_equal_the_reference(name):
+    """acc_by_surface: init_acc_surface, interp_acc_surface, check_above_acc_surface, copy_acc_surface
+    (acc_region_surface.f90) and the gate in push_particle_3d / _3d_ft, from the reference's source, bit for bit."""
+    from helpers import CASES, make_case
+    from stochastic_parker_b200 import mhd
+    from stochastic_parker_b200.driver import run_intervals
+    w, P, frames, ts = make_case(**dict(CASES[name], grid=12), nptl=12)
+    P.strict_math = 1
+    out = []
+    for cls in (refsim.RefSim, Oracle):
+        s = cls(P, w.nptl_max)
+        rec, steps = run_intervals(s, frames, ts, nptl=12, particle_v0=w.particle_v0, split_flag=1, pmin_split=1.05,
+                                   split_ratio=1.05, surfaces=lambda which, f: mhd.make_acc_surface(P, which, f))
+        out.append((s.download_particles(), steps))
+    assert out[0][1] == out[1][1] > 2000
+    assert_particles_identical(out[0][0], out[1][0], name)
