@@ -159,13 +159,14 @@ def workload_config(w, P, world, nptl_end=None, strict=0):
         "particles_per_gpu": w.nptl, "split": w.split_flag, "field_layout": layout, "strict_math": int(strict),
         "step": "one MHD interval (dt_out) of the whole population",
         "parallelism": f"particles sharded over {world} GPU(s), full field per GPU, NCCL allreduce of histograms",
-        "l2": f"no flush: the two-frame field store ({store_mb:.0f} MB) plus the particle arrays ({w.nptl * 102 / 1e6:.0f} MB) "
-              "exceed the 126 MB L2, and every step uploads a new MHD frame and repacks half of the store",
+        "l2": (f"no flush: the two-frame field store ({store_mb:.0f} MB) plus the particle arrays ({w.nptl * 102 / 1e6:.0f} MB) "
+               + ("exceed" if store_mb + w.nptl * 102 / 1e6 > 126 else "are below") +
+               " the 126 MB L2, and every step uploads a new MHD frame and repacks half of the store"),
         "source": w.source,
         "why_this_workload": "north_star states its target on the 2D reconnection config (configs[0]); configs[1] "
                              "(C2, 1e8 particles x 1.7e4 steps per MHD interval = 75 s per step at this rate) is run "
-                             "at full size by scripts/r02/gpu_fullsize.sh (lines kept in profiles/, summarised under "
-                             "`extra.configs`)",
+                             "at full size by scripts/r02/gpu_b.sh / gpu_c.sh / gpu_k.sh / gpu_j8.sh (lines kept in profiles/, "
+                             "summarised under `extra.configs`)",
     }
 
 
