@@ -43,19 +43,23 @@ __global__ void __launch_bounds__(256) read_kernel(const float* __restrict__ buf
             }
         }
     } else {
-        const size_t nlines = nchunks / 4;
+        // random 128-byte lines: the line count is rounded down to a power of two so that the index is a mask (a 64-bit
+        // modulo would make the loop compute-bound), eight independent loads in flight per lane
+        size_t nlines = 1;
+        while (nlines * 2 <= nchunks / 4) nlines *= 2;
+        const size_t mask = nlines - 1;
         const unsigned q = threadIdx.x & 3u;
         uint64_t s = (tid >> 2) * 0x9E3779B97F4A7C15ull + 12345u;
         const size_t per_thread = (nchunks * (size_t)passes) / nthreads;
-        for (size_t i = 0; i + 3 < per_thread; i += 4) {
-            float4 a[4], b[4];
+        for (size_t i = 0; i + 7 < per_thread; i += 8) {
+            float4 a[8], b[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 8; ++j) {
                 s = s * 6364136223846793005ull + 1442695040888963407ull;
-                const size_t line = (size_t)((s >> 20) % nlines);
+                const size_t line = (size_t)(s >> 24) & mask;
                 ldg256(buf + 32 * line + 8 * q, a[j], b[j]);
             }
-            acc += a[0].x + b[1].y + a[2].z + b[3].w;
+            acc += a[0].x + b[1].y + a[2].z + b[3].w + a[4].x + b[5].y + a[6].z + b[7].w;
         }
     }
     if (acc == 123.456f) sink[0] = acc;
@@ -91,7 +95,7 @@ extern "C" int membw_read_gbs(size_t bytes, int passes, int mode, double* gbs)
     if (mode == 0) moved = bytes * (size_t)passes;
     else {
         const size_t nthreads = (size_t)grid * 256;
-        moved = ((nchunks * (size_t)passes) / nthreads / 4 * 4) * nthreads * 32;
+        moved = ((nchunks * (size_t)passes) / nthreads / 8 * 8) * nthreads * 32;
     }
     *gbs = (double)moved / (best * 1e-3) / 1e9;
     cudaEventDestroy(e0);

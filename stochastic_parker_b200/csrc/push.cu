@@ -1494,6 +1494,10 @@ push_kernel(const __grid_constant__ DevParams prm, const PtlSoA P, const float* 
 #ifndef GPAT_COOP_DEPTH
 #define GPAT_COOP_DEPTH 1
 #endif
+#ifndef GPAT_UNROLL_3D
+#define GPAT_UNROLL_3D 0   // 1: A/B build with the four rounds of the 3-D kernels unrolled like the 2-D ones
+#endif
+#define GPAT_ROUNDS_UNROLL(NC, G) ((GPAT_UNROLL_3D || (NC) != 8) ? (G) : 1)
 #ifndef GPAT_NO_PERM
 #define GPAT_NO_PERM 0   // 1: A/B build without the neighbour-preserving lane assignment of refill()
 #endif
@@ -1684,12 +1688,20 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                         ldg256(pc_ + 8 * j, lo[slot][c * C::CPL + j], hi[slot][c * C::CPL + j]);
                 }
             };
+            constexpr bool ROLLED = (GPAT_ROUNDS_UNROLL(C::NC, C::G) == 1);  // rolled: loads at the top of every round,
+            if constexpr (!ROLLED) {                                         // no buffers carried across the back-edge
 #pragma unroll
-            for (int r = 0; r < DEPTH; ++r) issue(r, r);
-#pragma unroll
+                for (int r = 0; r < DEPTH; ++r) issue(r, r);
+            }
+            // 2-D: the four rounds are unrolled (2700-instruction body, no instruction-fetch stalls).  3-D: a rolled loop --
+            // unrolled, the body is 4096 instructions = 64 KB and "no instruction" is the second largest stall reason
+            // (2.0 per issue at 512^3, 1.15 at 256^3: profiles/r02n_push_coop_c5_512_ncu.txt)
+            constexpr int kRoundsUnroll = GPAT_ROUNDS_UNROLL(C::NC, C::G);
+#pragma unroll kRoundsUnroll
             for (int r = 0; r < C::G; ++r) {
                 const int owner = gbase + r;
-                const int slot = r % DEPTH;
+                const int slot = ROLLED ? 0 : r % DEPTH;
+                if constexpr (ROLLED) issue(r, 0);
                 const double2* row = reinterpret_cast<const double2*>(par + owner * C::PAR);
                 // weights of half 0 / half 1 at each corner (time blend folded in)
                 double w0[C::NC], w1[C::NC];
@@ -1777,7 +1789,9 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                         sidep.y = fma(cvt_sel<0, 0>(e.y), wa, cvt_sel<0, 1>(e.w) * wb);
                     }
                 }
-                if (r + DEPTH < C::G) issue(r + DEPTH, slot);
+                if constexpr (!ROLLED) {
+                    if (r + DEPTH < C::G) issue(r + DEPTH, slot);
+                }
                 double2* out = reinterpret_cast<double2*>(res + C::row_off(owner) + (gq * C::CPL) * 4);
                 if constexpr (C::SCH > 0) {
                     double2* so = reinterpret_cast<double2*>(res + C::row_off(owner) + C::NREC + 4 * gq);
