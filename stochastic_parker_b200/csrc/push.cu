@@ -1494,6 +1494,9 @@ push_kernel(const __grid_constant__ DevParams prm, const PtlSoA P, const float* 
 #ifndef GPAT_COOP_DEPTH
 #define GPAT_COOP_DEPTH 1
 #endif
+#ifndef GPAT_PUB_FACTORS
+#define GPAT_PUB_FACTORS 0   // 1: A/B build publishing y x time factors instead of finished weights (measured: -1 %)
+#endif
 #ifndef GPAT_UNROLL_3D
 #define GPAT_UNROLL_3D 0   // 1: A/B build with the four rounds of the 3-D kernels unrolled like the 2-D ones
 #endif
@@ -1567,7 +1570,14 @@ template <int L> struct Coop {
     // conversion scale folded in) + the cell, 80 B; the other lanes of the group load them instead
     // of recomputing 16 products per round.  3-D: rx ry t0 t1 cell rz, 48 B, weights per round.
     static constexpr bool PUBW = (NC == 4);
-    static constexpr int PAR = PUBW ? 10 : 6;
+    // PUBF (2-D): publish the four y x time factors + rx + the cell (48 B, three LDS.128 per round) and let every lane
+    // form the eight weights with the owner's own products (bit-identical: rx1 * a0 ...), instead of the eight finished
+    // weights (80 B, four LDS.128 + one LDS.64 per round): 40 fewer shared-memory wavefronts per warp-step for 36 more
+    // FP64 instructions.  MEASURED AND REJECTED (profiles/README.md, call R): 1 % slower on C1, C2, C3 and C4 -- trading
+    // L1-pipe wavefronts for issue slots does not pay although the L1 data pipe is the busiest unit (80 % vs 65 %).
+    static constexpr bool PUBF = PUBW && (GPAT_PUB_FACTORS != 0);
+    static constexpr int PAR = PUBF ? 6 : (PUBW ? 10 : 6);
+    static constexpr int CELL_AT = PUBF ? 5 : (PUBW ? 8 : 4);
     __device__ static __forceinline__ int row_off(int owner) { return owner * ROW + (SKEW ? ((owner / G) & 1) * 2 : 0); }
 };
 
@@ -1641,11 +1651,17 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                 const double rx1 = 1.0 - rx, ry1 = 1.0 - ry;
                 const double a0 = ry1 * t0 * cvt_weight_scale(0, 0), b0 = ry * t0 * cvt_weight_scale(1, 0);
                 const double a1 = ry1 * t1 * cvt_weight_scale(0, 1), b1 = ry * t1 * cvt_weight_scale(1, 1);
-                row[0] = make_double2(rx1 * a0, rx * a0);  // w0[0..3]: half 0 at the four corners
-                row[1] = make_double2(rx1 * b0, rx * b0);
-                row[2] = make_double2(rx1 * a1, rx * a1);  // w1[0..3]: half 1
-                row[3] = make_double2(rx1 * b1, rx * b1);
-                row[4] = make_double2(__longlong_as_double(cell), 0.0);
+                if constexpr (C::PUBF) {
+                    row[0] = make_double2(a0, b0);
+                    row[1] = make_double2(a1, b1);
+                    row[2] = make_double2(rx, __longlong_as_double(cell));
+                } else {
+                    row[0] = make_double2(rx1 * a0, rx * a0);  // w0[0..3]: half 0 at the four corners
+                    row[1] = make_double2(rx1 * b0, rx * b0);
+                    row[2] = make_double2(rx1 * a1, rx * a1);  // w1[0..3]: half 1
+                    row[3] = make_double2(rx1 * b1, rx * b1);
+                    row[4] = make_double2(__longlong_as_double(cell), 0.0);
+                }
             } else {
                 row[0] = make_double2(rx, ry);
                 row[1] = make_double2(t0, t1);
@@ -1663,7 +1679,7 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
             float4 sd[DEPTH];  // side plane (L2D): corner gq of the round's particle
             float4 slo[DEPTH][C::SCH ? 4 : 1], shi[DEPTH][C::SCH ? 4 : 1];  // side plane (L3D): the four (y, z) corner pairs
             auto issue = [&](int r, int slot) {
-                const long long cell = __double_as_longlong(par[(gbase + r) * C::PAR + (C::PUBW ? 8 : 4)]);
+                const long long cell = __double_as_longlong(par[(gbase + r) * C::PAR + C::CELL_AT]);
                 const float* base = fld + cell * stride + (gq * C::CPL) * 8;
                 if constexpr (C::SCH > 0) {
                     static_assert(C::G == 4 && C::NC == 8 && C::SCH == 2, "chunk-format side plane: 3-D, two chunks, four lanes");
@@ -1705,7 +1721,12 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                 const double2* row = reinterpret_cast<const double2*>(par + owner * C::PAR);
                 // weights of half 0 / half 1 at each corner (time blend folded in)
                 double w0[C::NC], w1[C::NC];
-                if constexpr (C::PUBW) {
+                if constexpr (C::PUBF) {
+                    const double2 f0 = row[0], f1 = row[1];
+                    const double rx = row[2].x, rx1 = 1.0 - rx;
+                    w0[0] = rx1 * f0.x; w0[1] = rx * f0.x; w0[2] = rx1 * f0.y; w0[3] = rx * f0.y;
+                    w1[0] = rx1 * f1.x; w1[1] = rx * f1.x; w1[2] = rx1 * f1.y; w1[3] = rx * f1.y;
+                } else if constexpr (C::PUBW) {
                     const double2 q0 = row[0], q1 = row[1], q2 = row[2], q3 = row[3];
                     w0[0] = q0.x; w0[1] = q0.y; w0[2] = q1.x; w0[3] = q1.y;
                     w1[0] = q2.x; w1[1] = q2.y; w1[2] = q3.x; w1[3] = q3.y;
