@@ -517,8 +517,7 @@ int push_counters(gpat_sim* h)
 // off).  Never in the reference-order build, whose tests check the reference's own particle order.
 int sort_before_push(gpat_sim* h)
 {
-    const bool strict = h->hp.strict_math || h->hp.ndim == 1 || h->hp.focused_transport || h->hp.deltab_flag ||
-                        h->hp.correlation_flag;
+    const bool strict = h->hp.strict_math;
     // Default: sort when the packed field store is larger than the L2 (+4 % on C1/C2, +10 % on C4, 2x
     // on C5).  A store that is L2-resident as a whole has no locality left to gain, and clustering
     // particles with similar step counts into the same warps costs load balance (C3: -4.5 %).
@@ -598,10 +597,13 @@ int run_push(gpat_sim* h, double t0, double dtf, int nsteps_interval, int num_fi
     CU(cudaMemsetAsync(h->d_queue, 0, 2 * sizeof(unsigned long long), h->st));
     CU(cudaEventRecord(h->ev[0], h->st));
     if (a.nptl > 0) {
-        // 1-D (push_particle_1d), focused transport (push_particle_2d_ft) and the turbulence maps
-        // (deltab / correlation) exist in the reference-order build only: not throughput paths yet
-        if (h->hp.strict_math || h->hp.ndim == 1 || h->hp.focused_transport || h->hp.deltab_flag ||
-            h->hp.correlation_flag) launch_push_strict(h->layout, h->dp, h->P, h->fld, a, h->sm_count, h->st);
+        // 1-D (push_particle_1d), focused transport (push_particle_*_ft) and the turbulence maps (deltab /
+        // correlation) run the general pushers behind the lane-group gather in the production build
+        // (push.cu: kSpecAlt); GPAT_ALT_STRICT=1 sends them back to the reference-order kernels (A/B switch)
+        const bool alt_strict = getenv("GPAT_ALT_STRICT") && atoi(getenv("GPAT_ALT_STRICT")) != 0;
+        const bool alt = h->hp.ndim == 1 || h->hp.focused_transport || h->hp.deltab_flag || h->hp.correlation_flag;
+        if (h->hp.strict_math || (alt && (alt_strict || h->push_variant != 1)))
+            launch_push_strict(h->layout, h->dp, h->P, h->fld, a, h->sm_count, h->st);
         else launch_push_fast(h->layout, h->dp, h->P, h->fld, a, h->sm_count, h->st);
         h->tm.total_launches++;
     }

@@ -36,6 +36,28 @@ constexpr int kBlock = 128;
 __device__ __forceinline__ double sq(double v) { return v * v; }
 __device__ __forceinline__ double min2(double a, double b) { return (b < a) ? b : a; }
 
+// Elementary operations of the general pushers (push_physics and what it calls).  Reference-order build: the plain
+// IEEE operations in the reference's order.  Production build: the straight-line versions of fastmath.cuh (<= 2 ulp each;
+// pow as exp(y log x)), which is what turns the ~2000 FP64-pipe instructions of a focused-transport step's libdevice
+// pow / sqrt / division sequences into ~500.  Arguments are what the pushers guarantee: normal, positive where a
+// root or a logarithm is taken; pow(0, y) keeps its IEEE value.
+constexpr double kThird = 1.0 / 3.0, kTwoThirds = 2.0 / 3.0;
+#if GPAT_STRICT
+__device__ __forceinline__ double pm_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ double pm_pow(double x, double y) { return pow(x, y); }
+__device__ __forceinline__ double pm_div(double a, double b) { return a / b; }
+__device__ __forceinline__ double pm_divc(double a, double c) { return a / c; }
+#else
+__device__ __forceinline__ double pm_sqrt(double x) { return fm::sqrt_pos(x); }
+__device__ __forceinline__ double pm_pow(double x, double y)
+{
+    const double r = fm::exp_mid(y * fm::log_pos(x > 0.0 ? x : 1.0));
+    return (x > 0.0) ? r : ((y > 0.0) ? 0.0 : (y == 0.0 ? 1.0 : __longlong_as_double(0x7ff0000000000000LL)));
+}
+__device__ __forceinline__ double pm_div(double a, double b) { return a * fm::rcp(b); }
+__device__ __forceinline__ double pm_divc(double a, double c) { return a * (1.0 / c); }  // c: a literal
+#endif
+
 // ---- Philox4x32-10 (Salmon et al. 2011) -------------------------------------------
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, unsigned k0, unsigned k1)
 {
@@ -69,13 +91,20 @@ struct Lane {
     int nsteps_pushed;
     int count_flag;
     int nsteps_tracked;  // used by the tracking instantiations only
-#if GPAT_STRICT
+    // Touched only by the reference-order build and by the ALT instantiations of the production build (1-D, focused
+    // transport, turbulence maps); every other instantiation never reads or writes them, so they cost no registers there.
     double v, dvl, dmul;  // focused transport: particle speed, last step's delta v / delta mu
     double sh1, sh2;      // acc_by_surface: surface heights at this step's starting position
-#endif
 };
 
+constexpr bool kStrict = (GPAT_STRICT != 0);
+// SPEC value of the production-build instantiations that run the general pushers (push_physics: 1-D, focused transport,
+// turbulence maps, every switch at run time) behind the lane-group gather
+constexpr int kSpecAlt = 16;
+
 // particle_boundary_condition for a single rank (neighbours are self or -1)
+// ALT: the run may be 1-D (reference-order build: always checked)
+template <bool ALT = false>
 __device__ __forceinline__ void boundary(const DevParams& prm, Lane& q, const double* e,
                                          double* leak)
 {
@@ -86,10 +115,8 @@ __device__ __forceinline__ void boundary(const DevParams& prm, Lane& q, const do
         if (prm.pbc[0]) { atomicAdd(leak, q.weight); q.count_flag = GPAT_COUNT_FLAG_ESCAPE_HX; }
         else q.x = q.x - e[1] + e[0];
     }
-#if GPAT_STRICT
-    if (prm.ndim > 1)  // particle_module.f90:2036 (1-D runs use the reference-order build only)
-#endif
-    if (q.y < e[2] && q.count_flag == GPAT_COUNT_FLAG_INBOX) {
+    if ((kStrict || ALT) && prm.ndim == 1) {  // particle_module.f90:2036
+    } else if (q.y < e[2] && q.count_flag == GPAT_COUNT_FLAG_INBOX) {
         if (prm.pbc[1]) { atomicAdd(leak, q.weight); q.count_flag = GPAT_COUNT_FLAG_ESCAPE_LY; }
         else q.y = q.y - e[2] + e[3];
     } else if (q.y > e[3] && q.count_flag == GPAT_COUNT_FLAG_INBOX) {
@@ -110,25 +137,24 @@ __device__ __forceinline__ void boundary(const DevParams& prm, Lane& q, const do
 // true when negp_or_bc() would change anything
 // MAYZ = false: the layout rules out a resolved z axis (base 2-D record: ndim = 2 and no
 // include_3rd_dim, which needs the extended record), so the z test is not even compiled
-template <bool MAYZ = true>
+template <bool MAYZ = true, bool ALT = false>
 __device__ __forceinline__ bool outside_or_negp(const DevParams& prm, const Lane& q)
 {
     bool o = (q.p < 0.0) | (q.x < prm.ext[0]) | (q.x > prm.ext[1]) | (q.y < prm.ext[2]) | (q.y > prm.ext[3]);
-#if GPAT_STRICT
-    if (prm.ndim == 1) o = (q.p < 0.0) | (q.x < prm.ext[0]) | (q.x > prm.ext[1]);
-#endif
+    if ((kStrict || ALT) && prm.ndim == 1) o = (q.p < 0.0) | (q.x < prm.ext[0]) | (q.x > prm.ext[1]);
     if (MAYZ && (prm.ndim == 3 || prm.include_3rd_dim)) o = o | (q.z < prm.ext[4]) | (q.z > prm.ext[5]);
     return o;
 }
 
 // particle_module.f90:1602-1609
+template <bool ALT = false>
 __device__ __forceinline__ void negp_or_bc(const DevParams& prm, Lane& q, double* leak)
 {
     if (q.p < 0.0) {
         q.count_flag = GPAT_COUNT_FLAG_OTHERS;
         atomicAdd(leak + 1, q.weight);
     } else {
-        boundary(prm, q, prm.ext, leak);
+        boundary<ALT>(prm, q, prm.ext, leak);
     }
 }
 
@@ -144,7 +170,7 @@ __device__ __forceinline__ void ldg256(const float* __restrict__ p, float4& lo, 
 
 // cell index + in-cell offsets of a position (get_interp_paramters, particle_module.f90:642-674);
 // the cell is clamped so that a runaway particle cannot fault.
-template <int NDIM>
+template <int NDIM, bool ALT = false>
 __device__ __forceinline__ long long locate(const DevParams& prm, double x, double y, double z,
                                             double& rx, double& ry, double& rz)
 {
@@ -162,9 +188,7 @@ __device__ __forceinline__ long long locate(const DevParams& prm, double x, doub
     // Fortran index -> storage index is +1 (lower bound -1, mhd_data_parallel.f90:82)
     int cx = min(max(ix + 1, 0), prm.nxg - 2);
     int cy = min(max(iy + 1, 0), prm.nyg - 2);
-#if GPAT_STRICT
-    if (prm.ndim == 1) { cy = 0; ry = 0.0; }  // pos(2) = 1, ry = 0 (particle_module.f90:649-652)
-#endif
+    if ((kStrict || ALT) && prm.ndim == 1) { cy = 0; ry = 0.0; }  // pos(2) = 1, ry = 0 (particle_module.f90:649-652)
     long long cell = (long long)cy * prm.nxg + cx;
     rz = 0.0;
     if (NDIM == 3) {
@@ -330,7 +354,6 @@ __device__ __forceinline__ void gather(const DevParams& prm, const float* __rest
 #endif
 }
 
-#if GPAT_STRICT
 // interp_magnetic_fluctuation + interp_correlation_length (mhd_data_parallel.f90:1806-1915): the
 // sixteen values db2_slab(1:4) db2_2d(1:4) lc_slab(1:4) lc_2d(1:4), reference summation order
 template <int NDIM>
@@ -339,7 +362,7 @@ __device__ __forceinline__ void gather_aux(const DevParams& prm, const float* __
 {
     constexpr int NC = (NDIM == 3) ? 8 : 4;
     double rx, ry, rz;
-    const long long cell = locate<NDIM>(prm, x, y, z, rx, ry, rz);
+    const long long cell = locate<NDIM, true>(prm, x, y, z, rx, ry, rz);
     const double rx1 = 1.0 - rx, ry1 = 1.0 - ry, rz1 = 1.0 - rz;
     double w[NC];
     if (NC == 4) {
@@ -370,7 +393,6 @@ __device__ __forceinline__ void gather_aux(const DevParams& prm, const float* __
         for (int e = 0; e < 4; ++e) A[4 * q + e] = prm.time_interp ? (a[e] * rt1 + b[e] * rt) : a[e];
     }
 }
-#endif
 
 // ---- kappa (particle_module.f90:93-104) --------------------------------------------
 struct Kappa {
@@ -391,49 +413,43 @@ __device__ __forceinline__ void calc_kappa(const DevParams& prm, const BField& B
                                            double mu, Kappa& k, const double* aux = nullptr)
 {
     const double bx = B.bx, by = B.by, bz = B.bz, b = B.b;
-    const double ib1 = (b < kEps) ? 1.0 : 1.0 / b;  // particle_module.f90:2230-2234
+    const double ib1 = (b < kEps) ? 1.0 : pm_div(1.0, b);  // particle_module.f90:2230-2234
     const double ib2 = ib1 * ib1;
     const double ib3 = ib1 * ib2;
     double knp = 1.0, knperp = 1.0;
     if (prm.mag_dependency == 1) {
-        knp = knp * pow(b, prm.gm2);
-        if (prm.nlgc) knperp = knperp * pow(b, prm.gm2_3);
+        knp = knp * pm_pow(b, prm.gm2);
+        if (prm.nlgc) knperp = knperp * pm_pow(b, prm.gm2_3);
     }
-#if GPAT_STRICT
     const bool dbf = aux && prm.deltab_flag, cof = aux && prm.correlation_flag;
     if (dbf) {  // particle_module.f90:2246-2248 / 2505-2509
-        knp = knp / aux[0];
-        if (prm.nlgc) knperp = knperp * pow(aux[0], -1.0 / 3.0) * pow(aux[4], 2.0 / 3.0);
+        knp = pm_div(knp, aux[0]);
+        if (prm.nlgc) knperp = knperp * pm_pow(aux[0], -kThird) * pm_pow(aux[4], kTwoThirds);
     }
     if (cof) {  // particle_module.f90:2252-2254 / 2513-2517
-        knp = knp * pow(aux[8], prm.gamma_turb - 1.0);
-        if (prm.nlgc) knperp = knperp * pow(aux[8], (prm.gamma_turb - 1.0) / 3.0) * pow(aux[12], 2.0 / 3.0);
+        knp = knp * pm_pow(aux[8], prm.gamma_turb - 1.0);
+        if (prm.nlgc) knperp = knperp * pm_pow(aux[8], pm_divc(prm.gamma_turb - 1.0, 3.0)) * pm_pow(aux[12], kTwoThirds);
     }
-#endif
     k.knorm_para = knp;
     double ax = 0.0, ay = 0.0, az = 0.0;  // coefficients multiplying the b_i b_j terms
     if (!prm.nlgc) {
-        double knorm = (prm.momentum_dependency == 1) ? knp * pow(p / prm.p0, prm.pindex) : knp;
+        double knorm = (prm.momentum_dependency == 1) ? knp * pm_pow(pm_div(p, prm.p0), prm.pindex) : knp;
         k.kpara = prm.kpara0 * knorm;
         k.kperp = k.kpara * prm.kret;
     } else {
         double kn_para = knp, kn_perp = knperp;
         if (prm.momentum_dependency == 1) {
-            kn_para = knp * pow(p / prm.p0, prm.pindex);
-            kn_perp = knperp * pow(p / prm.p0, prm.pidx_perp);
+            kn_para = knp * pm_pow(pm_div(p, prm.p0), prm.pindex);
+            kn_perp = knperp * pm_pow(pm_div(p, prm.p0), prm.pidx_perp);
         }
         k.kpara = prm.kpara0 * kn_para;
         k.kperp = prm.kpara0 * prm.kperp_kpara * kn_perp * sq(mu);
     }
-    k.skpara = sqrt(2.0 * k.kpara);
-    k.skperp = sqrt(2.0 * k.kperp);
-    k.skpara_perp = sqrt(2.0 * (k.kpara - k.kperp));
-#if GPAT_STRICT
+    k.skpara = pm_sqrt(2.0 * k.kpara);
+    k.skperp = pm_sqrt(2.0 * k.kperp);
+    k.skpara_perp = pm_sqrt(2.0 * (k.kpara - k.kperp));
     // particle_module.f90:2372-2376: focused transport carries the parallel streaming itself
     const double kpp = prm.focused_transport ? -k.kperp : k.kpara - k.kperp;
-#else
-    const double kpp = k.kpara - k.kperp;
-#endif
     double px_, py_, pz_ = 0.0;  // the "kperp*dkdx" leading terms
     if (!prm.nlgc) {
         double dkdx = 0.0, dkdy = 0.0, dkdz = 0.0;
@@ -444,47 +460,43 @@ __device__ __forceinline__ void calc_kappa(const DevParams& prm, const BField& B
                 dkdx = B.db_dx * ib1 * prm.gm2; dkdy = B.db_dy * ib1 * prm.gm2;
             }
         }
-#if GPAT_STRICT
         if (dbf) {  // particle_module.f90:2314-2317, 2364-2367, 2410-2414
-            dkdx = dkdx - aux[1] / aux[0]; dkdy = dkdy - aux[2] / aux[0];
-            if (FULL3D) dkdz = dkdz - aux[3] / aux[0];
+            dkdx = dkdx - pm_div(aux[1], aux[0]); dkdy = dkdy - pm_div(aux[2], aux[0]);
+            if (FULL3D) dkdz = dkdz - pm_div(aux[3], aux[0]);
         }
         if (cof) {  // particle_module.f90:2318-2321, 2368-2371, 2415-2419
             const double g1 = prm.gamma_turb - 1.0;
-            dkdx = dkdx + g1 * aux[9] / aux[8]; dkdy = dkdy + g1 * aux[10] / aux[8];
-            if (FULL3D) dkdz = dkdz + g1 * aux[11] / aux[8];
+            dkdx = dkdx + pm_div(g1 * aux[9], aux[8]); dkdy = dkdy + pm_div(g1 * aux[10], aux[8]);
+            if (FULL3D) dkdz = dkdz + pm_div(g1 * aux[11], aux[8]);
         }
-#endif
         px_ = k.kperp * dkdx; py_ = k.kperp * dkdy; pz_ = k.kperp * dkdz;
         ax = kpp * dkdx; ay = kpp * dkdy; az = kpp * dkdz;
     } else {
         double dpa_x = 0.0, dpa_y = 0.0, dpa_z = 0.0, dpe_x = 0.0, dpe_y = 0.0, dpe_z = 0.0;
         if (prm.mag_dependency == 1) {
             dpa_x = B.db_dx * ib1 * prm.gm2; dpa_y = B.db_dy * ib1 * prm.gm2;
-            dpe_x = B.db_dx * ib1 * prm.gm2 / 3.0; dpe_y = B.db_dy * ib1 * prm.gm2 / 3.0;
-            if (FULL3D) { dpa_z = B.db_dz * ib1 * prm.gm2; dpe_z = B.db_dz * ib1 * prm.gm2 / 3.0; }
+            dpe_x = pm_divc(B.db_dx * ib1 * prm.gm2, 3.0); dpe_y = pm_divc(B.db_dy * ib1 * prm.gm2, 3.0);
+            if (FULL3D) { dpa_z = B.db_dz * ib1 * prm.gm2; dpe_z = pm_divc(B.db_dz * ib1 * prm.gm2, 3.0); }
         }
-#if GPAT_STRICT
         if (dbf) {  // particle_module.f90:2589-2596 and the 2-D+3rd / 3-D twins
-            dpa_x = dpa_x - aux[1] / aux[0]; dpa_y = dpa_y - aux[2] / aux[0];
-            dpe_x = dpe_x - aux[1] / aux[0] / 3.0 + 2.0 * aux[5] / aux[4] / 3.0;
-            dpe_y = dpe_y - aux[2] / aux[0] / 3.0 + 2.0 * aux[6] / aux[4] / 3.0;
+            dpa_x = dpa_x - pm_div(aux[1], aux[0]); dpa_y = dpa_y - pm_div(aux[2], aux[0]);
+            dpe_x = dpe_x - pm_divc(pm_div(aux[1], aux[0]), 3.0) + pm_divc(pm_div(2.0 * aux[5], aux[4]), 3.0);
+            dpe_y = dpe_y - pm_divc(pm_div(aux[2], aux[0]), 3.0) + pm_divc(pm_div(2.0 * aux[6], aux[4]), 3.0);
             if (FULL3D) {
-                dpa_z = dpa_z - aux[3] / aux[0];
-                dpe_z = dpe_z - aux[3] / aux[0] / 3.0 + 2.0 * aux[7] / aux[4] / 3.0;
+                dpa_z = dpa_z - pm_div(aux[3], aux[0]);
+                dpe_z = dpe_z - pm_divc(pm_div(aux[3], aux[0]), 3.0) + pm_divc(pm_div(2.0 * aux[7], aux[4]), 3.0);
             }
         }
         if (cof) {  // particle_module.f90:2597-2604
             const double g1 = prm.gamma_turb - 1.0;
-            dpa_x = dpa_x + g1 * aux[9] / aux[8]; dpa_y = dpa_y + g1 * aux[10] / aux[8];
-            dpe_x = dpe_x + g1 * aux[9] / aux[8] / 3.0 + 2.0 * aux[13] / aux[12] / 3.0;
-            dpe_y = dpe_y + g1 * aux[10] / aux[8] / 3.0 + 2.0 * aux[14] / aux[12] / 3.0;
+            dpa_x = dpa_x + pm_div(g1 * aux[9], aux[8]); dpa_y = dpa_y + pm_div(g1 * aux[10], aux[8]);
+            dpe_x = dpe_x + pm_divc(pm_div(g1 * aux[9], aux[8]), 3.0) + pm_divc(pm_div(2.0 * aux[13], aux[12]), 3.0);
+            dpe_y = dpe_y + pm_divc(pm_div(g1 * aux[10], aux[8]), 3.0) + pm_divc(pm_div(2.0 * aux[14], aux[12]), 3.0);
             if (FULL3D) {
-                dpa_z = dpa_z + g1 * aux[11] / aux[8];
-                dpe_z = dpe_z + g1 * aux[11] / aux[8] / 3.0 + 2.0 * aux[15] / aux[12] / 3.0;
+                dpa_z = dpa_z + pm_div(g1 * aux[11], aux[8]);
+                dpe_z = dpe_z + pm_divc(pm_div(g1 * aux[11], aux[8]), 3.0) + pm_divc(pm_div(2.0 * aux[15], aux[12]), 3.0);
             }
         }
-#endif
         px_ = k.kperp * dpe_x; py_ = k.kperp * dpe_y; pz_ = k.kperp * dpe_z;
         ax = k.kpara * dpa_x - k.kperp * dpe_x;
         ay = k.kpara * dpa_y - k.kperp * dpe_y;
@@ -521,30 +533,30 @@ __device__ __forceinline__ void momentum_diffusion(const DevParams& prm, const B
                                                    double& dpp)
 {
     if (prm.dpp_wave) {
-        double va = B.b / sqrt(rho);
-        if (prm.momentum_dependency == 1) dp_dt = dp_dt + (8.0 * p / (27.0 * k.kpara)) * sq(va);
-        else dp_dt = dp_dt + (4.0 * p / (9.0 * k.kpara)) * sq(va);
-        dpp = dpp + sq(p * va) / (9.0 * k.kpara);
+        double va = pm_div(B.b, pm_sqrt(rho));
+        if (prm.momentum_dependency == 1) dp_dt = dp_dt + pm_div(8.0 * p, 27.0 * k.kpara) * sq(va);
+        else dp_dt = dp_dt + pm_div(4.0 * p, 9.0 * k.kpara) * sq(va);
+        dpp = dpp + pm_div(sq(p * va), 9.0 * k.kpara);
     }
     if (prm.dpp_shear) {
-        double sxx = V.dvx_dx - divv / 3.0, syy = V.dvy_dy - divv / 3.0, szz = V.dvz_dz - divv / 3.0;
+        double sxx = V.dvx_dx - pm_divc(divv, 3.0), syy = V.dvy_dy - pm_divc(divv, 3.0), szz = V.dvz_dz - pm_divc(divv, 3.0);
         double sxy = (V.dvx_dy + V.dvy_dx) / 2.0;
         double sxz = (V.dvx_dz + V.dvz_dx) / 2.0;
         double syz = (V.dvy_dz + V.dvz_dy) / 2.0;
         double gshear;
         if (prm.weak_scattering) {
-            double ib = (B.b < kEps) ? 0.0 : 1.0 / B.b;
+            double ib = (B.b < kEps) ? 0.0 : pm_div(1.0, B.b);
             double bbs = sxx * sq(B.bx) + syy * sq(B.by) + szz * sq(B.bz) +
                          2.0 * (sxy * B.bx * B.by + sxz * B.bx * B.bz + syz * B.by * B.bz);
             bbs = bbs * ib * ib;
-            gshear = sq(bbs) / 5.0;
+            gshear = pm_divc(sq(bbs), 5.0);
         } else {
-            gshear = 2.0 * (sq(sxx) + sq(syy) + sq(szz) + 2.0 * (sq(sxy) + sq(sxz) + sq(syz))) / 15.0;
+            gshear = pm_divc(2.0 * (sq(sxx) + sq(syy) + sq(szz) + 2.0 * (sq(sxy) + sq(sxz) + sq(syz))), 15.0);
         }
         if (gshear > 0.0) {
             dp_dt = dp_dt + (2.0 + prm.pindex) * gshear * prm.tau0 * k.knorm_para *
-                                pow(p, prm.pindex - 1.0) * prm.p0_pow;
-            dpp = dpp + gshear * prm.tau0 * k.knorm_para * pow(p, prm.pindex) * prm.p0_pow;
+                                pm_pow(p, prm.pindex - 1.0) * prm.p0_pow;
+            dpp = dpp + gshear * prm.tau0 * k.knorm_para * pm_pow(p, prm.pindex) * prm.p0_pow;
         }
     }
 }
@@ -631,7 +643,6 @@ __device__ __forceinline__ bool above_surface(const DevParams& prm, const Lane& 
     return in;
 }
 
-#if GPAT_STRICT
 // push_particle_1d (particle_module.f90:2993-3111) on a 2-D record whose second row is zero.
 // Two uniforms per step: ran1 for x, then one for p (particle_module.f90:3085-3088).
 template <int L>
@@ -642,7 +653,7 @@ __device__ __forceinline__ void push_1d(const DevParams& prm, const PushArgs& a,
     BField B;
     VGrad V;
     B.bx = F[s2::bx]; B.by = F[s2::by]; B.bz = F[s2::bz];
-    B.b = sqrt(sq(B.bx) + sq(B.by) + sq(B.bz));
+    B.b = pm_sqrt(sq(B.bx) + sq(B.by) + sq(B.bz));
     B.dbx_dx = B.dbx_dy = B.dbx_dz = B.dby_dx = B.dby_dy = B.dby_dz = 0.0;
     B.dbz_dx = B.dbz_dy = B.dbz_dz = B.db_dx = B.db_dy = B.db_dz = 0.0;
     V.dvx_dx = F[s2::dvx_dx];
@@ -654,21 +665,21 @@ __device__ __forceinline__ void push_1d(const DevParams& prm, const PushArgs& a,
     // particle_module.f90:2271-2292: dkdx has no magnetic term here (mag_dependency = 1 is rejected by
     // gpat_init because the reference would multiply by an unassigned db_dx)
     double dkdx = 0.0;
-    if (aux && prm.deltab_flag) dkdx = dkdx - aux[1] / aux[0];
-    if (aux && prm.correlation_flag) dkdx = dkdx + (prm.gamma_turb - 1.0) * aux[9] / aux[8];
+    if (aux && prm.deltab_flag) dkdx = dkdx - pm_div(aux[1], aux[0]);
+    if (aux && prm.correlation_flag) dkdx = dkdx + pm_div((prm.gamma_turb - 1.0) * aux[9], aux[8]);
     k.dkxx_dx = k.kpara * dkdx;
     const double dx_dt = F[s2::vx] + k.dkxx_dx;
     const double divv = V.dvx_dx;
-    double dp_dt = -q.p * divv / 3.0;
+    double dp_dt = pm_divc(-q.p * divv, 3.0);
     double dpp = 0.0;
     if (Rec<L>::EXT) momentum_diffusion(prm, B, V, rho, divv, k, q.p, dp_dt, dpp);
     if (!fixed_dt) {
         double d;
         if (dx_dt != 0.0 && dp_dt != 0.0) {  // particle_module.f90:3060-3072
             const double s = (k.skperp > 0.0) ? k.skperp : k.skpara;
-            d = sq(0.5 * prm.dx / k.skpara);
-            d = min2(d, sq(s / dx_dt));
-            d = min2(d, (double)0.1f * q.p / fabs(dp_dt));
+            d = sq(pm_div(0.5 * prm.dx, k.skpara));
+            d = min2(d, sq(pm_div(s, dx_dt)));
+            d = min2(d, pm_div((double)0.1f * q.p, fabs(dp_dt)));
         } else {
             d = a.dt_min;
         }
@@ -676,7 +687,7 @@ __device__ __forceinline__ void push_1d(const DevParams& prm, const PushArgs& a,
         if (d > a.dt_max) d = a.dt_max;
         q.dt = d;
     }
-    const double sdt = sqrt(q.dt);
+    const double sdt = pm_sqrt(q.dt);
     const double sqrt3 = 1.7320508075688772;
     const double ran1 = (2.0 * u0 - 1.0) * sqrt3;
     const double ddx = dx_dt * q.dt + ran1 * k.skpara * sdt;
@@ -686,7 +697,7 @@ __device__ __forceinline__ void push_1d(const DevParams& prm, const PushArgs& a,
     q.dyl = 0.0;
     q.dzl = 0.0;
     const double ranp = (2.0 * u1 - 1.0) * sqrt3;
-    double ddp = dp_dt * q.dt + ranp * sqrt(2.0 * dpp) * sdt;
+    double ddp = dp_dt * q.dt + ranp * pm_sqrt(2.0 * dpp) * sdt;
     if (prm.acc_region_flag == 1) {
         if (in_acc_region(prm, q)) q.p = q.p + ddp;
         else ddp = 0.0;
@@ -701,9 +712,7 @@ __device__ __forceinline__ void push_1d(const DevParams& prm, const PushArgs& a,
     }
     q.dpl = ddp;
 }
-#endif
 
-#if GPAT_STRICT
 // calc_duu (particle_module.f90:3116-3155) + push_particle_2d_ft (particle_module.f90:3626-3977),
 // Cartesian uniform grid.  Uniforms: u0, u1 perpendicular displacement, u2 momentum, u3 pitch angle.
 template <int L>
@@ -727,15 +736,15 @@ __device__ __forceinline__ void push_2d_ft(const DevParams& prm, const PushArgs&
         const double dvz_dx = F[s2::dvz_dx], dvz_dy = F[s2::dvz_dy];
         const double rho = F[s2::rho];
         const double bx = B.bx, by = B.by, bz = B.bz;
-        B.b = sqrt(sq(bx) + sq(by) + sq(bz));
+        B.b = pm_sqrt(sq(bx) + sq(by) + sq(bz));
         const double b = B.b;
         Kappa k;
         calc_kappa<false, false>(prm, B, q.p, q.mu, k, aux);
-        const double ib = (b < kEps) ? 0.0 : 1.0 / b;
+        const double ib = (b < kEps) ? 0.0 : pm_div(1.0, b);
         const double ib2 = ib * ib, ib3 = ib * ib2;
         // `1.0 / pcharge` is a default-real quotient (particle_module.f90:3716); qdrift holds 1/(3 q)
-        const double vdp = (double)(1.0f / (float)prm.pcharge) /
-                           sqrt(sq(prm.drift1 * prm.p0 / q.p) + sq(prm.drift2 * sq(prm.p0) / sq(q.p)));
+        const double vdp = pm_div((double)(1.0f / (float)prm.pcharge),
+                           pm_sqrt(sq(pm_div(prm.drift1 * prm.p0, q.p)) + sq(pm_div(prm.drift2 * sq(prm.p0), sq(q.p)))));
         const double mu2 = sq(q.mu);
         const double muf1 = 0.5 * (1.0 - mu2), muf2 = 0.5 * (3.0 * mu2 - 1.0);
         const double kx = bx * B.dbx_dx + by * B.dbx_dy;
@@ -761,26 +770,26 @@ __device__ __forceinline__ void push_2d_ft(const DevParams& prm, const PushArgs&
                                  bz * (bx * dvz_dx + by * dvz_dy)) * ib2;
         const double bv_gradv = (bx * (vx * V.dvx_dx + vy * V.dvx_dy) + by * (vx * V.dvy_dx + vy * V.dvy_dy) +
                                  bz * (vx * dvz_dx + vy * dvz_dy)) * ib;
-        const double acc_rate = -(muf1 * divv + muf2 * bb_gradv + q.mu * bv_gradv / q.v);
+        const double acc_rate = -(muf1 * divv + muf2 * bb_gradv + pm_div(q.mu * bv_gradv, q.v));
         double dp_dt = q.p * acc_rate;
         double dpp = 0.0;
         momentum_diffusion(prm, B, V, rho, divv, k, q.p, dp_dt, dpp);  // sigma_xz = sigma_yz = 0 (V.dvz_* = 0)
         // calc_duu
         const double div_bnorm = -(bx * B.db_dx + by * B.db_dy) * ib2;
-        double dmu_dt = q.v * div_bnorm + q.mu * divv - 3 * q.mu * bb_gradv - 2 * bv_gradv / q.v;
+        double dmu_dt = q.v * div_bnorm + q.mu * divv - 3 * q.mu * bb_gradv - pm_div(2 * bv_gradv, q.v);
         dmu_dt = dmu_dt * (1 - mu2) * 0.5;
         const double h0 = (double)0.2f;
-        const double dtmp = pow(fabs(q.mu), prm.gamma_turb - 1) + h0;
+        const double dtmp = pm_pow(fabs(q.mu), prm.gamma_turb - 1) + h0;
         double duu = prm.duu0 * (1 - mu2) * dtmp;
         double duu_du;
-        if (q.mu > 0.0) duu_du = prm.duu0 * (-2 * q.mu * dtmp + (1 - mu2) * pow(fabs(q.mu), prm.gamma_turb - 2));
-        else if (q.mu < 0.0) duu_du = prm.duu0 * (-2 * q.mu * dtmp - (1 - mu2) * pow(fabs(q.mu), prm.gamma_turb - 2));
+        if (q.mu > 0.0) duu_du = prm.duu0 * (-2 * q.mu * dtmp + (1 - mu2) * pm_pow(fabs(q.mu), prm.gamma_turb - 2));
+        else if (q.mu < 0.0) duu_du = prm.duu0 * (-2 * q.mu * dtmp - (1 - mu2) * pm_pow(fabs(q.mu), prm.gamma_turb - 2));
         else duu_du = 0.0;
         double duu_norm = 1.0;
-        if (prm.mag_dependency == 1) duu_norm = duu_norm * pow(b, 2.0 - prm.gamma_turb);
+        if (prm.mag_dependency == 1) duu_norm = duu_norm * pm_pow(b, 2.0 - prm.gamma_turb);
         if (aux && prm.deltab_flag) duu_norm = duu_norm * aux[0];                                    // :3143-3145
-        if (aux && prm.correlation_flag) duu_norm = duu_norm * pow(aux[8], 1.0 - prm.gamma_turb);   // :3146-3148
-        if (prm.momentum_dependency == 1) duu_norm = duu_norm * pow(q.p / prm.p0, prm.gamma_turb - 1);
+        if (aux && prm.correlation_flag) duu_norm = duu_norm * pm_pow(aux[8], 1.0 - prm.gamma_turb);   // :3146-3148
+        if (prm.momentum_dependency == 1) duu_norm = duu_norm * pm_pow(pm_div(q.p, prm.p0), prm.gamma_turb - 1);
         duu_du = duu_du * duu_norm;
         duu = duu * duu_norm;
         dmu_dt = dmu_dt + duu_du;
@@ -789,13 +798,13 @@ __device__ __forceinline__ void push_2d_ft(const DevParams& prm, const PushArgs&
             double d;
             if (dx_dt != 0.0 && dy_dt != 0.0 && dp_dt != 0.0 && dmu_dt != 0.0) {
                 const double s = (k.skperp > 0.0) ? k.skperp : k.skpara;  // particle_module.f90:3847-3864
-                d = sq(0.5 * prm.dx / s);
-                d = min2(d, sq(0.5 * prm.dy / s));
-                d = min2(d, sq(s / dx_dt));
-                d = min2(d, sq(s / dy_dt));
-                d = min2(d, (double)0.1f * q.p / fabs(dp_dt));
-                d = min2(d, (double)0.1f / fabs(dmu_dt));
-                d = min2(d, 2.0 * duu / sq(dmu_dt));
+                d = sq(pm_div(0.5 * prm.dx, s));
+                d = min2(d, sq(pm_div(0.5 * prm.dy, s)));
+                d = min2(d, sq(pm_div(s, dx_dt)));
+                d = min2(d, sq(pm_div(s, dy_dt)));
+                d = min2(d, pm_div((double)0.1f * q.p, fabs(dp_dt)));
+                d = min2(d, pm_div((double)0.1f, fabs(dmu_dt)));
+                d = min2(d, pm_div(2.0 * duu, sq(dmu_dt)));
             } else {
                 d = a.dt_min;
             }
@@ -803,21 +812,21 @@ __device__ __forceinline__ void push_2d_ft(const DevParams& prm, const PushArgs&
             if (d > a.dt_max) d = a.dt_max;
             q.dt = d;
         }
-        const double sdt = sqrt(q.dt);
+        const double sdt = pm_sqrt(q.dt);
         const double sqrt3 = 1.7320508075688772;
         double ran1 = (2.0 * u0 - 1.0) * sqrt3;
         const double ran2 = (2.0 * u1 - 1.0) * sqrt3;
         const double bxn = bx * ib, byn = by * ib, bzn = bz * ib;
-        const double ibxyn = 1.0 / sqrt(sq(bxn) + sq(byn));
+        const double ibxyn = pm_div(1.0, pm_sqrt(sq(bxn) + sq(byn)));
         // the second term uses the UN-normalised by / bx (particle_module.f90:3912-3913): kept
         const double ddx = dx_dt * q.dt + k.skperp * ibxyn * sdt * (-bxn * bzn * ran1 - by * ran2);
         const double ddy = dy_dt * q.dt + k.skperp * ibxyn * sdt * (-byn * bzn * ran1 + bx * ran2);
         const double ddz = dz_dt * q.dt;
         ran1 = (2.0 * u2 - 1.0) * sqrt3;
-        double ddp = dp_dt * q.dt + ran1 * sqrt(2 * dpp) * sdt;
-        double ddv = q.v * ddp / q.p;
+        double ddp = dp_dt * q.dt + ran1 * pm_sqrt(2 * dpp) * sdt;
+        double ddv = pm_div(q.v * ddp, q.p);
         ran1 = (2.0 * u3 - 1.0) * sqrt3;
-        double ddmu = dmu_dt * q.dt + ran1 * sqrt(2 * duu) * sdt;
+        double ddmu = dmu_dt * q.dt + ran1 * pm_sqrt(2 * duu) * sdt;
         q.x = q.x + ddx;
         q.y = q.y + ddy;
         q.z = q.z + ddz;
@@ -835,7 +844,7 @@ __device__ __forceinline__ void push_2d_ft(const DevParams& prm, const PushArgs&
         const double pfloor = 0.25 * prm.p0;
         if (q.p < pfloor) {  // particle_module.f90:3967-3974
             q.v = q.v - ddv;
-            ddv = q.v * 0.25 * prm.p0 / q.p - q.v;
+            ddv = pm_div(q.v * 0.25 * prm.p0, q.p) - q.v;
             q.v = q.v + ddv;
             q.p = q.p - ddp;
             ddp = pfloor - q.p;
@@ -845,9 +854,7 @@ __device__ __forceinline__ void push_2d_ft(const DevParams& prm, const PushArgs&
         q.dpl = ddp; q.dvl = ddv; q.dmul = ddmu;
     }
 }
-#endif
 
-#if GPAT_STRICT
 // push_particle_2d_include_3rd_ft (particle_module.f90:4267-4623) and push_particle_3d_ft (:4930-5320),
 // Cartesian, no acc_by_surface: one body, the 2-D variant with every d/dz equal to zero (x - 0, x + 0
 // and 0 * x are exact).  Uniforms: u0 u1 (u2 = ran3 is drawn and unused in Cartesian runs), u3 for p,
@@ -885,18 +892,18 @@ __device__ __forceinline__ void push_ft_3d_like(const DevParams& prm, const Push
             V.dvy_dz = F[s3::dvy_dz]; V.dvz_dx = F[s3::dvz_dx]; V.dvz_dy = F[s3::dvz_dy];
         }
         const double bx = B.bx, by = B.by, bz = B.bz;
-        B.b = sqrt(sq(bx) + sq(by) + sq(bz));
+        B.b = pm_sqrt(sq(bx) + sq(by) + sq(bz));
         const double b = B.b;
         Kappa k;
         if (D3) calc_kappa<true, true>(prm, B, q.p, q.mu, k, aux);
         else calc_kappa<true, false>(prm, B, q.p, q.mu, k, aux);
-        const double ib = (b < kEps) ? 0.0 : 1.0 / b;
+        const double ib = (b < kEps) ? 0.0 : pm_div(1.0, b);
         const double bxn = bx * ib, byn = by * ib, bzn = bz * ib;
-        const double bxyn = sqrt(sq(bxn) + sq(byn));
-        const double ibxyn = (bxyn < kEps) ? 0.0 : 1.0 / bxyn;
+        const double bxyn = pm_sqrt(sq(bxn) + sq(byn));
+        const double ibxyn = (bxyn < kEps) ? 0.0 : pm_div(1.0, bxyn);
         const double ib2 = ib * ib, ib3 = ib * ib2;
-        const double vdp = (double)(1.0f / (float)prm.pcharge) /
-                           sqrt(sq(prm.drift1 * prm.p0 / q.p) + sq(prm.drift2 * sq(prm.p0) / sq(q.p)));
+        const double vdp = pm_div((double)(1.0f / (float)prm.pcharge),
+                           pm_sqrt(sq(pm_div(prm.drift1 * prm.p0, q.p)) + sq(pm_div(prm.drift2 * sq(prm.p0), sq(q.p)))));
         const double mu2 = sq(q.mu);
         const double muf1 = 0.5 * (1.0 - mu2), muf2 = 0.5 * (3.0 * mu2 - 1.0);
         double kx, ky, kz, bdot_curvb, vdx, vdy;
@@ -947,26 +954,26 @@ __device__ __forceinline__ void push_ft_3d_like(const DevParams& prm, const Push
             bv_gradv = (bx * (vx * V.dvx_dx + vy * V.dvx_dy) + by * (vx * V.dvy_dx + vy * V.dvy_dy) +
                         bz * (vx * V.dvz_dx + vy * V.dvz_dy)) * ib;
         }
-        const double acc_rate = -(muf1 * divv + muf2 * bb_gradv + q.mu * bv_gradv / q.v);
+        const double acc_rate = -(muf1 * divv + muf2 * bb_gradv + pm_div(q.mu * bv_gradv, q.v));
         double dp_dt = q.p * acc_rate;
         double dpp = 0.0;
         momentum_diffusion(prm, B, V, rho, divv, k, q.p, dp_dt, dpp);
         const double div_bnorm = D3 ? -(bx * B.db_dx + by * B.db_dy + bz * B.db_dz) * ib2
                                     : -(bx * B.db_dx + by * B.db_dy) * ib2;
-        double dmu_dt = q.v * div_bnorm + q.mu * divv - 3 * q.mu * bb_gradv - 2 * bv_gradv / q.v;
+        double dmu_dt = q.v * div_bnorm + q.mu * divv - 3 * q.mu * bb_gradv - pm_div(2 * bv_gradv, q.v);
         dmu_dt = dmu_dt * (1 - mu2) * 0.5;
         const double h0 = (double)0.2f;
-        const double dtmp = pow(fabs(q.mu), prm.gamma_turb - 1) + h0;
+        const double dtmp = pm_pow(fabs(q.mu), prm.gamma_turb - 1) + h0;
         double duu = prm.duu0 * (1 - mu2) * dtmp;
         double duu_du;
-        if (q.mu > 0.0) duu_du = prm.duu0 * (-2 * q.mu * dtmp + (1 - mu2) * pow(fabs(q.mu), prm.gamma_turb - 2));
-        else if (q.mu < 0.0) duu_du = prm.duu0 * (-2 * q.mu * dtmp - (1 - mu2) * pow(fabs(q.mu), prm.gamma_turb - 2));
+        if (q.mu > 0.0) duu_du = prm.duu0 * (-2 * q.mu * dtmp + (1 - mu2) * pm_pow(fabs(q.mu), prm.gamma_turb - 2));
+        else if (q.mu < 0.0) duu_du = prm.duu0 * (-2 * q.mu * dtmp - (1 - mu2) * pm_pow(fabs(q.mu), prm.gamma_turb - 2));
         else duu_du = 0.0;
         double duu_norm = 1.0;
-        if (prm.mag_dependency == 1) duu_norm = duu_norm * pow(b, 2.0 - prm.gamma_turb);
+        if (prm.mag_dependency == 1) duu_norm = duu_norm * pm_pow(b, 2.0 - prm.gamma_turb);
         if (aux && prm.deltab_flag) duu_norm = duu_norm * aux[0];
-        if (aux && prm.correlation_flag) duu_norm = duu_norm * pow(aux[8], 1.0 - prm.gamma_turb);
-        if (prm.momentum_dependency == 1) duu_norm = duu_norm * pow(q.p / prm.p0, prm.gamma_turb - 1);
+        if (aux && prm.correlation_flag) duu_norm = duu_norm * pm_pow(aux[8], 1.0 - prm.gamma_turb);
+        if (prm.momentum_dependency == 1) duu_norm = duu_norm * pm_pow(pm_div(q.p, prm.p0), prm.gamma_turb - 1);
         duu_du = duu_du * duu_norm;
         duu = duu * duu_norm;
         dmu_dt = dmu_dt + duu_du;
@@ -976,15 +983,15 @@ __device__ __forceinline__ void push_ft_3d_like(const DevParams& prm, const Push
             if (D3) ok = ok && dz_dt != 0.0;  // particle_module.f90:5156-5160; the 2-D variant does not test dz_dt
             if (ok) {
                 const double s = (k.skperp > 0.0) ? k.skperp : k.skpara;
-                d = sq(0.5 * prm.dx / s);
-                d = min2(d, sq(0.5 * prm.dy / s));
-                if (D3) d = min2(d, sq(0.5 * prm.dz / s));
-                d = min2(d, sq(s / dx_dt));
-                d = min2(d, sq(s / dy_dt));
-                if (D3) d = min2(d, sq(s / dz_dt));
-                d = min2(d, (double)0.1f * q.p / fabs(dp_dt));
-                d = min2(d, (double)0.1f / fabs(dmu_dt));
-                d = min2(d, 2.0 * duu / sq(dmu_dt));
+                d = sq(pm_div(0.5 * prm.dx, s));
+                d = min2(d, sq(pm_div(0.5 * prm.dy, s)));
+                if (D3) d = min2(d, sq(pm_div(0.5 * prm.dz, s)));
+                d = min2(d, sq(pm_div(s, dx_dt)));
+                d = min2(d, sq(pm_div(s, dy_dt)));
+                if (D3) d = min2(d, sq(pm_div(s, dz_dt)));
+                d = min2(d, pm_div((double)0.1f * q.p, fabs(dp_dt)));
+                d = min2(d, pm_div((double)0.1f, fabs(dmu_dt)));
+                d = min2(d, pm_div(2.0 * duu, sq(dmu_dt)));
             } else {
                 d = a.dt_min;
             }
@@ -992,7 +999,7 @@ __device__ __forceinline__ void push_ft_3d_like(const DevParams& prm, const Push
             if (d > a.dt_max) d = a.dt_max;
             q.dt = d;
         }
-        const double sdt = sqrt(q.dt);
+        const double sdt = pm_sqrt(q.dt);
         const double sqrt3 = 1.7320508075688772;
         double ran1 = (2.0 * u0 - 1.0) * sqrt3;
         const double ran2 = (2.0 * u1 - 1.0) * sqrt3;
@@ -1000,10 +1007,10 @@ __device__ __forceinline__ void push_ft_3d_like(const DevParams& prm, const Push
         const double ddy = dy_dt * q.dt + (-byn * bzn * k.skperp * ibxyn * ran1 + bxn * k.skperp * ibxyn * ran2) * sdt;
         const double ddz = dz_dt * q.dt + bxyn * k.skperp * ran1 * sdt;
         ran1 = (2.0 * u3 - 1.0) * sqrt3;
-        double ddp = dp_dt * q.dt + ran1 * sqrt(2 * dpp) * sdt;
-        double ddv = q.v * ddp / q.p;
+        double ddp = dp_dt * q.dt + ran1 * pm_sqrt(2 * dpp) * sdt;
+        double ddv = pm_div(q.v * ddp, q.p);
         ran1 = (2.0 * u4 - 1.0) * sqrt3;
-        double ddmu = dmu_dt * q.dt + ran1 * sqrt(2 * duu) * sdt;
+        double ddmu = dmu_dt * q.dt + ran1 * pm_sqrt(2 * duu) * sdt;
         q.x = q.x + ddx;
         q.y = q.y + ddy;
         q.z = q.z + ddz;
@@ -1023,7 +1030,7 @@ __device__ __forceinline__ void push_ft_3d_like(const DevParams& prm, const Push
         const double pfloor = 0.25 * prm.p0;
         if (q.p < pfloor) {
             q.v = q.v - ddv;
-            ddv = q.v * 0.25 * prm.p0 / q.p - q.v;
+            ddv = pm_div(q.v * 0.25 * prm.p0, q.p) - q.v;
             q.v = q.v + ddv;
             q.p = q.p - ddp;
             ddp = pfloor - q.p;
@@ -1033,21 +1040,21 @@ __device__ __forceinline__ void push_ft_3d_like(const DevParams& prm, const Push
         q.dpl = ddp; q.dvl = ddv; q.dmul = ddmu;
     }
 }
-#endif
 
 // One call of push_particle_*: everything between the BC test and the step counter.
+// One push_particle_* call on the interpolated record F, every model switch read at run time, reference operation
+// order.  Reference-order build: called by push_once() below.  Production build: phase C of the kSpecAlt
+// instantiations of push_kernel_coop (1-D, focused transport, turbulence maps) -- same statements, compiled with FMA
+// contraction and the production locate() / u01(); held to 1e-12 per step like the other production kernels.
 template <int L, bool TRACK = false>
-__device__ __forceinline__ void push_once(const DevParams& prm, const PushArgs& a,
-                                          const float* __restrict__ fld, Lane& q, bool fixed_dt)
+__device__ __forceinline__ void push_physics(const DevParams& prm, const PushArgs& a,
+                                             const double (&F)[Rec<L>::NREC], Lane& q, bool fixed_dt, double rt)
 {
     // tracked particles carry negated tags; the streams are keyed by the magnitudes so that a
     // tracking run replays the run its particles were selected from
     const int tag_inj = TRACK ? abs(q.tag_inj) : q.tag_inj, tag_spl = TRACK ? abs(q.tag_spl) : q.tag_spl;
     constexpr bool D3 = (Rec<L>::NDIM == 3);
     constexpr bool EXT = Rec<L>::EXT;
-    double F[Rec<L>::NREC];
-    const double rt = (q.t - a.t0) / a.dtf;
-    gather<L>(prm, fld, a.sel, q.x, q.y, q.z, rt, F);
 
     // uniforms of this step: ran1, ran2, ran3, ran_p
     double u0, u1, u2, u3;
@@ -1068,7 +1075,6 @@ __device__ __forceinline__ void push_once(const DevParams& prm, const PushArgs& 
     q.rng += 1;
 
     const double* auxp = nullptr;
-#if GPAT_STRICT
     double A[16];
     if (a.aux && (prm.deltab_flag || prm.correlation_flag)) {  // particle_module.f90:1634-1639
         gather_aux<Rec<L>::NDIM>(prm, a.aux, a.sel, q.x, q.y, q.z, rt, A);
@@ -1096,7 +1102,6 @@ __device__ __forceinline__ void push_once(const DevParams& prm, const PushArgs& 
         }
         return;
     }
-#endif
 
     BField B;
     VGrad V;
@@ -1133,7 +1138,7 @@ __device__ __forceinline__ void push_once(const DevParams& prm, const PushArgs& 
             V.dvx_dy = V.dvx_dz = V.dvy_dx = V.dvy_dz = V.dvz_dx = V.dvz_dy = 0.0;
         }
     }
-    B.b = sqrt(sq(B.bx) + sq(B.by) + sq(B.bz));
+    B.b = pm_sqrt(sq(B.bx) + sq(B.by) + sq(B.bz));
     const bool third = D3 || (EXT && prm.include_3rd_dim);  // push_particle_3d-like path
 
     Kappa k;
@@ -1141,12 +1146,12 @@ __device__ __forceinline__ void push_once(const DevParams& prm, const PushArgs& 
     else if (EXT && prm.include_3rd_dim) calc_kappa<true, false>(prm, B, q.p, q.mu, k, auxp);
     else calc_kappa<false, false>(prm, B, q.p, q.mu, k, auxp);
 
-    const double ib = (B.b < kEps) ? 0.0 : 1.0 / B.b;  // particle_module.f90:3414-3418
+    const double ib = (B.b < kEps) ? 0.0 : pm_div(1.0, B.b);  // particle_module.f90:3414-3418
     const double ib2 = ib * ib;
     const double ib3 = ib * ib2;
     // particle_module.f90:3436: 1.0/(3*pcharge) is an FP32 quotient
-    const double vdp = prm.qdrift / sqrt(sq(prm.drift1 * prm.p0 / q.p) +
-                                         sq(prm.drift2 * sq(prm.p0) / sq(q.p)));
+    const double vdp = pm_div(prm.qdrift, pm_sqrt(sq(pm_div(prm.drift1 * prm.p0, q.p)) +
+                                         sq(pm_div(prm.drift2 * sq(prm.p0), sq(q.p)))));
     double vdx, vdy, vdz;
     if (!third) {
         vdx = vdp * (B.dbz_dy * ib2 - 2.0 * B.bz * B.db_dy * ib3);
@@ -1172,7 +1177,7 @@ __device__ __forceinline__ void push_once(const DevParams& prm, const PushArgs& 
         dz_dt = vz + vdz + k.dkxz_dx + k.dkyz_dy + k.dkzz_dz;
         divv = V.dvx_dx + V.dvy_dy + V.dvz_dz;
     }
-    double dp_dt = -q.p * divv / 3.0;
+    double dp_dt = pm_divc(-q.p * divv, 3.0);
     double dpp = 0.0;
     if (EXT) {
         if (!third) { V.dvz_dx = 0.0; V.dvz_dy = 0.0; }  // push_particle_2d: sigma_xz = sigma_yz = 0
@@ -1183,13 +1188,13 @@ __device__ __forceinline__ void push_once(const DevParams& prm, const PushArgs& 
         double d;
         if (dx_dt != 0.0 && dy_dt != 0.0 && dp_dt != 0.0) {
             const double s = (k.skperp > 0.0) ? k.skperp : k.skpara;
-            d = sq(0.5 * prm.dx / k.skpara);
-            d = min2(d, sq(0.5 * prm.dy / k.skpara));
-            if (D3) d = min2(d, sq(0.5 * prm.dz / k.skpara));
-            d = min2(d, sq(s / dx_dt));
-            d = min2(d, sq(s / dy_dt));
-            if (D3) d = min2(d, sq(s / dz_dt));
-            d = min2(d, (double)0.1f * q.p / fabs(dp_dt));
+            d = sq(pm_div(0.5 * prm.dx, k.skpara));
+            d = min2(d, sq(pm_div(0.5 * prm.dy, k.skpara)));
+            if (D3) d = min2(d, sq(pm_div(0.5 * prm.dz, k.skpara)));
+            d = min2(d, sq(pm_div(s, dx_dt)));
+            d = min2(d, sq(pm_div(s, dy_dt)));
+            if (D3) d = min2(d, sq(pm_div(s, dz_dt)));
+            d = min2(d, pm_div((double)0.1f * q.p, fabs(dp_dt)));
         } else {
             d = a.dt_min;
         }
@@ -1197,7 +1202,7 @@ __device__ __forceinline__ void push_once(const DevParams& prm, const PushArgs& 
         if (d > a.dt_max) d = a.dt_max;
         q.dt = d;
     }
-    const double sdt = sqrt(q.dt);
+    const double sdt = pm_sqrt(q.dt);
     const double sqrt3 = 1.7320508075688772;  // dsqrt(3.0d0), correctly rounded
     const double ran1 = (2.0 * u0 - 1.0) * sqrt3;
     const double ran2 = (2.0 * u1 - 1.0) * sqrt3;
@@ -1210,8 +1215,8 @@ __device__ __forceinline__ void push_once(const DevParams& prm, const PushArgs& 
         q.dzl = 0.0;  // the mover's own deltaz stays 0 in plain 2-D (particle_module.f90:1564)
     } else {
         const double bxn = B.bx * ib, byn = B.by * ib, bzn = B.bz * ib;
-        const double bxyn = sqrt(sq(bxn) + sq(byn));
-        const double ibxyn = (bxyn < kEps) ? 0.0 : 1.0 / bxyn;
+        const double bxyn = pm_sqrt(sq(bxn) + sq(byn));
+        const double ibxyn = (bxyn < kEps) ? 0.0 : pm_div(1.0, bxyn);
         ddx = dx_dt * q.dt + (bxn * k.skpara * ran1 - bxn * bzn * k.skperp * ibxyn * ran2 -
                               byn * k.skperp * ibxyn * ran3) * sdt;
         ddy = dy_dt * q.dt + (byn * k.skpara * ran1 - byn * bzn * k.skperp * ibxyn * ran2 +
@@ -1227,12 +1232,10 @@ __device__ __forceinline__ void push_once(const DevParams& prm, const PushArgs& 
     q.dyl = ddy;
 
     const double ranp = (2.0 * u3 - 1.0) * sqrt3;
-    double ddp = dp_dt * q.dt + ranp * sqrt(2.0 * dpp) * sdt;
+    double ddp = dp_dt * q.dt + ranp * pm_sqrt(2.0 * dpp) * sdt;
     if (prm.acc_region_flag == 1) {
         bool in = in_acc_region(prm, q);
-#if GPAT_STRICT
         if (prm.acc_by_surface) in = in && above_surface(prm, q, q.sh1, q.sh2);  // particle_module.f90:4887-4892
-#endif
         if (in) q.p = q.p + ddp;
         else ddp = 0.0;
     } else {
@@ -1245,6 +1248,16 @@ __device__ __forceinline__ void push_once(const DevParams& prm, const PushArgs& 
         q.p = pfloor;
     }
     q.dpl = ddp;
+}
+
+template <int L, bool TRACK = false>
+__device__ __forceinline__ void push_once(const DevParams& prm, const PushArgs& a,
+                                          const float* __restrict__ fld, Lane& q, bool fixed_dt)
+{
+    double F[Rec<L>::NREC];
+    const double rt = (q.t - a.t0) / a.dtf;
+    gather<L>(prm, fld, a.sel, q.x, q.y, q.z, rt, F);
+    push_physics<L, TRACK>(prm, a, F, q, fixed_dt, rt);
 }
 
 #if !GPAT_STRICT
@@ -1264,7 +1277,7 @@ enum : int { AT_OUTER_HEAD = 0, AT_INNER_HEAD = 1, AFTER_FIXED_PUSH = 2 };
 //        then dt = dt_old; BC                             <- AFTER_FIXED_PUSH
 //     dt_target += dt_fine
 // Returns ST_IDLE when the particle is done for this interval.
-template <bool TRACK = false>
+template <bool TRACK = false, bool ALT = false>
 __device__ __forceinline__ int next_state(const DevParams& prm, const PushArgs& a, Lane& q,
                                           int entry)
 {
@@ -1275,9 +1288,9 @@ __device__ __forceinline__ int next_state(const DevParams& prm, const PushArgs& 
             if ((q.t - a.t0) > q.dt_target && inbox) {  // particle_module.f90:1707-1716
                 q.x = q.x - q.dxl; q.y = q.y - q.dyl; q.z = q.z - q.dzl;
                 q.p = q.p - q.dpl;
-#if GPAT_STRICT
-                if (prm.focused_transport) { q.v = q.v - q.dvl; q.mu = q.mu - q.dmul; }  // particle_module.f90:1712-1713
-#endif
+                if constexpr (kStrict || ALT) {
+                    if (prm.focused_transport) { q.v = q.v - q.dvl; q.mu = q.mu - q.dmul; }  // particle_module.f90:1712-1713
+                }
                 q.t = q.t - q.dt;
                 q.dt_old = q.dt;
                 q.dt = a.t0 + q.dt_target - q.t;
@@ -1291,12 +1304,12 @@ __device__ __forceinline__ int next_state(const DevParams& prm, const PushArgs& 
                     return ST_FIX;
                 }
                 q.dt = q.dt_old;  // particle_module.f90:1816-1825
-                negp_or_bc(prm, q, a.leak);
+                negp_or_bc<ALT>(prm, q, a.leak);
             }
             q.dt_target = q.dt_target + a.dt_fine;
         } else if (entry == AFTER_FIXED_PUSH) {
             q.dt = q.dt_old;
-            negp_or_bc(prm, q, a.leak);
+            negp_or_bc<ALT>(prm, q, a.leak);
             q.dt_target = q.dt_target + a.dt_fine;
         }
         if (!(q.dt_target < a.dt_target_limit) || q.count_flag != GPAT_COUNT_FLAG_INBOX)
@@ -1307,7 +1320,7 @@ __device__ __forceinline__ int next_state(const DevParams& prm, const PushArgs& 
 
 // particle record -> lane registers, and the initial state of its loop nest
 // (particle_module.f90:1561-1592)
-template <bool TRACK = false>
+template <bool TRACK = false, bool ALT = false>
 __device__ __forceinline__ int load_lane(const DevParams& prm, const PushArgs& a, const PtlSoA& P,
                                          long long idx, Lane& q, int& remaining)
 {
@@ -1318,10 +1331,10 @@ __device__ __forceinline__ int load_lane(const DevParams& prm, const PushArgs& a
     q.tag_spl = P.tag_splitted[idx]; q.origin = P.origin[idx];
     q.nsteps_pushed = P.nsteps_pushed[idx]; q.count_flag = P.count_flag[idx];
     q.dxl = q.dyl = q.dzl = q.dpl = 0.0;
-#if GPAT_STRICT
-    q.v = P.v[idx]; q.dvl = 0.0; q.dmul = 0.0;
-    q.sh1 = 0.0; q.sh2 = 0.0;
-#endif
+    if constexpr (kStrict || ALT) {
+        q.v = P.v[idx]; q.dvl = 0.0; q.dmul = 0.0;
+        q.sh1 = 0.0; q.sh2 = 0.0;
+    }
     q.dt_old = q.dt;
     if (a.debug_nsteps > 0) {
         remaining = a.debug_nsteps;
@@ -1337,19 +1350,18 @@ __device__ __forceinline__ int load_lane(const DevParams& prm, const PushArgs& a
         q.count_flag = GPAT_COUNT_FLAG_OTHERS;
         atomicAdd(a.leak + 1, q.weight);
     } else {
-        boundary(prm, q, prm.ext, a.leak);
+        boundary<ALT>(prm, q, prm.ext, a.leak);
     }
-    return (q.count_flag == GPAT_COUNT_FLAG_INBOX) ? next_state<TRACK>(prm, a, q, AT_OUTER_HEAD) : ST_IDLE;
+    return (q.count_flag == GPAT_COUNT_FLAG_INBOX) ? next_state<TRACK, ALT>(prm, a, q, AT_OUTER_HEAD) : ST_IDLE;
 }
 
+template <bool ALT = false>
 __device__ __forceinline__ void store_lane(const PushArgs& a, const PtlSoA& P, long long idx,
                                            const Lane& q)
 {
     P.x[idx] = q.x; P.y[idx] = q.y; P.z[idx] = q.z; P.p[idx] = q.p;
     P.t[idx] = q.t; P.dt[idx] = q.dt; P.rng[idx] = q.rng;
-#if GPAT_STRICT
-    P.v[idx] = q.v; P.mu[idx] = q.mu;  // changed by focused transport only
-#endif
+    if constexpr (kStrict || ALT) { P.v[idx] = q.v; P.mu[idx] = q.mu; }  // changed by focused transport only
     P.nsteps_pushed[idx] = q.nsteps_pushed;
     P.count_flag[idx] = (signed char)q.count_flag;
     // particle_module.f90:1913 sets 1 at the start of the interval; tracked particles count up from it
@@ -1357,7 +1369,7 @@ __device__ __forceinline__ void store_lane(const PushArgs& a, const PtlSoA& P, l
 }
 
 // idle lanes take the next particles of the work counter (one warp-aggregated atomic)
-template <bool TRACK = false, bool PERM4 = false>
+template <bool TRACK = false, bool PERM4 = false, bool ALT = false>
 __device__ __forceinline__ void refill(const DevParams& prm, const PushArgs& a, const PtlSoA& P,
                                        unsigned lane, Lane& q, int& state, long long& idx,
                                        bool& exhausted, int& remaining)
@@ -1395,8 +1407,8 @@ __device__ __forceinline__ void refill(const DevParams& prm, const PushArgs& a, 
         if (idx >= a.nptl) {
             exhausted = true;
         } else {
-            state = load_lane<TRACK>(prm, a, P, idx, q, remaining);
-            if (state == ST_IDLE) store_lane(a, P, idx, q);
+            state = load_lane<TRACK, ALT>(prm, a, P, idx, q, remaining);
+            if (state == ST_IDLE) store_lane<ALT>(a, P, idx, q);
         }
     }
 }
@@ -1435,7 +1447,7 @@ __device__ __forceinline__ int after_push(const DevParams& prm, const PushArgs& 
     // gpat_debug_push_n: a uniform branch on a kernel argument, kept in the switch-specialised instantiations too so
     // that the per-step parity tests run the very kernels bench.py times
     if (a.debug_nsteps > 0) return (--remaining == 0) ? ST_IDLE : ST_ADAPT;
-    return next_state<TRACK>(prm, a, q, state == ST_FIX ? AFTER_FIXED_PUSH : AT_INNER_HEAD);
+    return next_state<TRACK, SPEC == kSpecAlt>(prm, a, q, state == ST_FIX ? AFTER_FIXED_PUSH : AT_INNER_HEAD);
 }
 
 template <int L, bool TRACK = false>
@@ -1594,7 +1606,7 @@ template <int L> struct MinBlocks { static constexpr int V = (L == L2B || L == L
 // a run restarted from a dump starts with sel = 0 again and has to continue bit-identically
 // (tests/test_gpu_parity.py::test_restart_round_trip_is_bit_exact).
 template <int L, int SEL, bool TRACK = false, int SPEC = 0>
-__global__ void __launch_bounds__(kBlock, MinBlocks<L>::V)
+__global__ void __launch_bounds__(kBlock, (SPEC == kSpecAlt ? 3 : MinBlocks<L>::V))
 push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                  const float* __restrict__ fld, const __grid_constant__ PushArgs a)
 {
@@ -1617,18 +1629,19 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
     int remaining = 0;
     unsigned long long nsteps = 0;
 
+    constexpr bool ALT = (SPEC == kSpecAlt);
     for (;;) {
-        refill<TRACK, (C::G == 4) && !GPAT_NO_PERM>(prm, a, P, lane, q, state, idx, exhausted, remaining);
+        refill<TRACK, (C::G == 4) && !GPAT_NO_PERM, ALT>(prm, a, P, lane, q, state, idx, exhausted, remaining);
         if (__all_sync(0xffffffffu, state == ST_IDLE)) {
             if (__all_sync(0xffffffffu, exhausted)) break;
             continue;
         }
         // top of the inner while body, particle_module.f90:1602-1612.  One combined test keeps the
         // common case (inside the extended box, p >= 0) to a single untaken branch.
-        if (state == ST_ADAPT && outside_or_negp<(Rec<L>::THIRD != 0)>(prm, q)) {
-            negp_or_bc(prm, q, a.leak);
+        if (state == ST_ADAPT && outside_or_negp<(Rec<L>::THIRD != 0), ALT>(prm, q)) {
+            negp_or_bc<ALT>(prm, q, a.leak);
             if (q.count_flag != GPAT_COUNT_FLAG_INBOX) {
-                store_lane(a, P, idx, q);
+                store_lane<ALT>(a, P, idx, q);
                 state = ST_IDLE;
             }
         }
@@ -1639,7 +1652,7 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
             double rx = 0.0, ry = 0.0, rz = 0.0, t0 = 0.0, t1 = 0.0;
             long long cell = 0;
             if (state != ST_IDLE) {
-                cell = locate<Rec<L>::NDIM>(prm, q.x, q.y, q.z, rx, ry, rz);
+                cell = locate<Rec<L>::NDIM, (SPEC == kSpecAlt)>(prm, q.x, q.y, q.z, rx, ry, rz);
                 const double rt = (q.t - a.t0) * a.idtf;
                 const bool ti = (SPEC & 1) || prm.time_interp;  // SPEC: time interpolation on
                 const double tA = ti ? 1.0 - rt : 1.0, tB = ti ? rt : 0.0;
@@ -1853,10 +1866,15 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                 F[C::NREC + 1] = ((c0.y + c1.y) + c2.y) + c3.y;
                 F[C::NREC + 2] = F[C::NREC + 3] = 0.0;
             }
-            physics_fast<L, double[Rec<L>::NF], TRACK, SPEC>(prm, a, F, q, state == ST_FIX);
+            if constexpr (ALT) {
+                static_assert(!ALT || Rec<L>::NF == Rec<L>::NREC, "the general pushers read one-plane records");
+                push_physics<L, TRACK>(prm, a, F, q, state == ST_FIX, (q.t - a.t0) * a.idtf);
+            } else {
+                physics_fast<L, double[Rec<L>::NF], TRACK, SPEC>(prm, a, F, q, state == ST_FIX);
+            }
             nsteps++;
             state = after_push<TRACK, SPEC>(prm, a, q, state, remaining, P, idx);
-            if (state == ST_IDLE) store_lane(a, P, idx, q);
+            if (state == ST_IDLE) store_lane<ALT>(a, P, idx, q);
         }
     }
 #pragma unroll
@@ -1947,8 +1965,13 @@ void launch_one(const DevParams& prm, const PtlSoA& P, const float* fld, const P
             push_kernel_coop<L, decltype(sel_c)::value, decltype(trk_c)::value, decltype(spec_c)::value>
                 <<<(unsigned)grid, kBlock, pad, st>>>(prm, P, fld, a);
         };
+        // 1-D, focused transport, turbulence maps: the general pushers behind the lane-group gather (one-plane records)
+        const bool alt = prm.ndim == 1 || prm.focused_transport || prm.deltab_flag || prm.correlation_flag;
         auto by_spec = [&](auto sel_c, auto trk_c) {
             using I = std::integral_constant<int, 0>;
+            if constexpr (Rec<L>::NF == Rec<L>::NREC) {
+                if (alt) { go(sel_c, trk_c, std::integral_constant<int, kSpecAlt>{}); return; }
+            }
             if constexpr (Rec<L>::NDIM == 2) {
                 if (spec == kSpec11) { go(sel_c, trk_c, std::integral_constant<int, kSpec11>{}); return; }
                 if constexpr (L == L2B) {
