@@ -24,6 +24,40 @@
 
 namespace fm {
 
+// Polynomial coefficients and magic numbers of log_pos / exp_mid.  As literals every FP64 constant costs two UMOV
+// (uniform-register immediates) right before its use -- 50 of the 1070 warp-instructions of a C1 step
+// (profiles/r02w_c1_by_line.txt); from a __constant__ table (FM_CONST_TABLE=1) one LDCU.128 brings two of them.
+// MEASURED, NO GAIN (profiles/README.md, call X: C1 +0.2 %, C3 +1.3 %, C4 -2.3 %, C5 +0.4 %): the default keeps the
+// literals; the host build (tests/fastmath_host_check.cpp) always uses them.
+#ifndef FM_CONST_TABLE
+#define FM_CONST_TABLE 0
+#endif
+#define FM_TABLE_VALUES                                                                                         \
+    1.531383769920937332e-01, 2.222219843214978396e-01, 3.999999999940941908e-01, 1.479819860511658591e-01,     \
+    1.818357216161805012e-01, 2.857142874366239149e-01, 6.666666666666735130e-01, 4503601774854144.0,           \
+    6.93147180369123816490e-01, 1.90821492927058770002e-10, 1.4426950408889634074, 6755399441055744.0,          \
+    1.0 / 479001600.0, 1.0 / 3628800.0, 1.0 / 6227020800.0, 1.0 / 39916800.0, 1.0 / 40320.0, 1.0 / 362880.0,    \
+    1.0 / 720.0, 1.0 / 5040.0, 1.0 / 24.0, 1.0 / 120.0, 0.5, 1.0 / 6.0
+enum : int { K_LG6 = 0, K_LG4, K_LG2, K_LG7, K_LG5, K_LG3, K_LG1, K_TWO52B, K_LN2HI, K_LN2LO, K_LOG2E, K_MAGIC,
+             K_E12, K_E10, K_E13, K_E11, K_E8, K_E9, K_E6, K_E7, K_E4, K_E5, K_E2, K_E3, K_COUNT };
+FM_HD constexpr double kval(int i)
+{
+    constexpr double t[K_COUNT] = {FM_TABLE_VALUES};
+    return t[i];
+}
+#if defined(__CUDACC__) && FM_CONST_TABLE
+static __constant__ double ktab_dev[K_COUNT] = {FM_TABLE_VALUES};
+#endif
+template <int I> FM_HD double K()
+{
+#if defined(__CUDA_ARCH__) && FM_CONST_TABLE
+    return ktab_dev[I];
+#else
+    constexpr double v = kval(I);
+    return v;
+#endif
+}
+
 FM_HD int hi_word(double x)
 {
 #ifdef __CUDA_ARCH__
@@ -118,40 +152,37 @@ FM_HD double log_pos(double x)
     const double s = f * rcp(2.0 + f);
     const double z = s * s;
     const double w = z * z;
-    const double t1 = w * fma_(w, fma_(w, 1.531383769920937332e-01, 2.222219843214978396e-01),
-                               3.999999999940941908e-01);
-    const double t2 = z * fma_(w, fma_(w, fma_(w, 1.479819860511658591e-01, 1.818357216161805012e-01),
-                                       2.857142874366239149e-01),
-                               6.666666666666735130e-01);
+    const double t1 = w * fma_(w, fma_(w, K<K_LG6>(), K<K_LG4>()), K<K_LG2>());
+    const double t2 = z * fma_(w, fma_(w, fma_(w, K<K_LG7>(), K<K_LG5>()), K<K_LG3>()), K<K_LG1>());
     const double R = t2 + t1;
     const double hfsq = 0.5 * f * f;
     // k as a double without an integer->float conversion: 2^52 + 2^31 + k, minus the bias
-    const double dk = make_double(0x43300000, k ^ (int)0x80000000) - 4503601774854144.0;
+    const double dk = make_double(0x43300000, k ^ (int)0x80000000) - K<K_TWO52B>();
     const double l1p = f - (hfsq - s * (hfsq + R));
-    return fma_(dk, 6.93147180369123816490e-01, fma_(dk, 1.90821492927058770002e-10, l1p));
+    return fma_(dk, K<K_LN2HI>(), fma_(dk, K<K_LN2LO>(), l1p));
 }
 
 // exp(x) for |x| < 700 (result normal)
 FM_HD double exp_mid(double x)
 {
-    const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: t's low word is round(x log2 e)
-    const double t = fma_(x, 1.4426950408889634074, kMagic);
+    const double kMagic = K<K_MAGIC>();  // 1.5 * 2^52: t's low word is round(x log2 e)
+    const double t = fma_(x, K<K_LOG2E>(), kMagic);
     const int k = lo_word(t);
     const double kd = t - kMagic;
-    double r = fma_(-kd, 6.93147180369123816490e-01, x);
-    r = fma_(-kd, 1.90821492927058770002e-10, r);  // |r| <= 0.3466
+    double r = fma_(-kd, K<K_LN2HI>(), x);
+    r = fma_(-kd, K<K_LN2LO>(), r);  // |r| <= 0.3466
     const double r2 = r * r;
     // Taylor to r^13, even and odd parts as two short Horner chains
-    double pe = fma_(r2, 1.0 / 479001600.0, 1.0 / 3628800.0);
-    double po = fma_(r2, 1.0 / 6227020800.0, 1.0 / 39916800.0);
-    pe = fma_(r2, pe, 1.0 / 40320.0);
-    po = fma_(r2, po, 1.0 / 362880.0);
-    pe = fma_(r2, pe, 1.0 / 720.0);
-    po = fma_(r2, po, 1.0 / 5040.0);
-    pe = fma_(r2, pe, 1.0 / 24.0);
-    po = fma_(r2, po, 1.0 / 120.0);
-    pe = fma_(r2, pe, 0.5);
-    po = fma_(r2, po, 1.0 / 6.0);
+    double pe = fma_(r2, K<K_E12>(), K<K_E10>());
+    double po = fma_(r2, K<K_E13>(), K<K_E11>());
+    pe = fma_(r2, pe, K<K_E8>());
+    po = fma_(r2, po, K<K_E9>());
+    pe = fma_(r2, pe, K<K_E6>());
+    po = fma_(r2, po, K<K_E7>());
+    pe = fma_(r2, pe, K<K_E4>());
+    po = fma_(r2, po, K<K_E5>());
+    pe = fma_(r2, pe, K<K_E2>());
+    po = fma_(r2, po, K<K_E3>());
     // exp(r) = 1 + r + r^2 (pe + r po)
     const double p = fma_(r2, fma_(r, po, pe), r) + 1.0;
     return make_double(hi_word(p) + (k << 20), lo_word(p));

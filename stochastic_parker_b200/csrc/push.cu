@@ -1524,6 +1524,9 @@ push_kernel(const __grid_constant__ DevParams prm, const PtlSoA P, const float* 
 // interpolation weight, so the FMA sees the same exact product f*w as with a real conversion.
 // GPAT_CVT_ALU_MASK picks which (row cy, frame half h) quarter of the corner values goes this
 // way: bit 2*cy + h.
+#ifndef GPAT_CVT_WIDE
+#define GPAT_CVT_WIDE 0
+#endif
 #ifndef GPAT_CVT_ALU_MASK
 #define GPAT_CVT_ALU_MASK 10  // the second frame half on the integer pipe: XU 60 % -> 33 %, +1.8 % steps/s on C1
 #endif
@@ -1532,7 +1535,19 @@ __device__ __forceinline__ double cvt(float f) { return (double)f; }
 __device__ __forceinline__ double cvt_scaled(float f)  // f * 2^-896
 {
     const int b = __float_as_int(f);
-    return __hiloint2double((b >> 3) & 0x8fffffff, b << 29);
+#if !GPAT_CVT_WIDE
+    return __hiloint2double((b >> 3) & 0x8fffffff, b << 29);  // SHF + LOP3 + IMAD.SHL: three ALU instructions
+#else
+    // A/B build, MEASURED AND REJECTED (profiles/README.md, call X): one signed 32 x 32 -> 64 multiply by 2^29 produces both
+    // words (high word = b >> 3 arithmetic, low word = b << 29), i.e. IMAD.WIDE + one LOP3 instead of three ALU
+    // instructions (these conversions are 18.9 % of the executed instructions of the C1 kernel).  64 fewer instructions per
+    // warp-step and 1.3 % SLOWER on C1, 1.6 % on C5: IMAD.WIDE is a multi-cycle instruction of the FMA pipe, the three
+    // single-cycle ALU instructions were not the limit.  (PTX with an immediate: the compiler turns the C++
+    // multiplication back into the two shifts.)
+    long long p;
+    asm("mul.wide.s32 %0, %1, 0x20000000;" : "=l"(p) : "r"(b));
+    return __hiloint2double(__double2hiint(__longlong_as_double(p)) & 0x8fffffff, __double2loint(__longlong_as_double(p)));
+#endif
 }
 template <int CY, int H> __device__ __forceinline__ double cvt_sel(float f)
 {
