@@ -89,7 +89,7 @@ typedef struct gpat_hist_spec {
  * (simulation_setup.f90:171-253), particle BCs (simulation_setup.f90:107-123). */
 typedef struct gpat_params {
     /* grid */
-    int32_t ndim;        /* ndim_field: 1, 2 or 3 (1-D: ny = nz = 1, reference-order build only) */
+    int32_t ndim;        /* ndim_field: 1, 2 or 3 (1-D: ny = nz = 1) */
     int32_t nx, ny, nz;  /* mhd_config%nx.. without ghost cells (nz=1 in 2-D) */
     int32_t time_interp; /* time_interp_flag */
     int32_t pbc[3];      /* pbcx,pbcy,pbcz: 0 periodic, 1 open */

@@ -244,7 +244,7 @@ int pick_layout(const gpat_params& p)
     bool ext = p.dpp_wave || p.dpp_shear || (p.ndim == 2 && p.include_3rd_dim) || p.keep_rho || p.focused_transport;
     // production build, 2-D momentum diffusion without the third dimension (config C4): the L2B line with rho in
     // its pad slot + a side plane for the two shear-only gradients (gpat_internal.cuh, Rec<L2D>).  Everything the
-    // reference-order kernels serve (strict_math, 1-D, focused transport, turbulence maps) keeps L2E.
+    // general pushers serve (strict_math, 1-D, focused transport, turbulence maps) keeps the one-plane record L2E.
     if (p.ndim == 2 && (p.dpp_wave || p.dpp_shear) && !p.include_3rd_dim && !p.focused_transport && !p.strict_math &&
         !p.deltab_flag && !p.correlation_flag && !getenv("GPAT_NO_L2D"))
         return L2D;

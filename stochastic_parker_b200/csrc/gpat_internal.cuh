@@ -146,8 +146,8 @@ struct DevParams {
     double acc_region[6];
     int momentum_dependency, mag_dependency, acc_region_flag;
     int dpp_wave, dpp_shear, weak_scattering, check_drift_2d, include_3rd_dim, nlgc;
-    int focused_transport;  // 2-D Cartesian push_particle_2d_ft, reference-order build only
-    int deltab_flag, correlation_flag;  // turbulence maps (reference-order build only)
+    int focused_transport;  // Cartesian push_particle_*_ft (production build: kSpecAlt instantiations)
+    int deltab_flag, correlation_flag;  // turbulence maps (production build: kSpecAlt instantiations)
     // acceleration surfaces (3-D, reference-order build only): normal = sign * (axis + 1)
     int acc_by_surface, surface_norm1, surface_norm2, surface2_existed, is_intersection;
     int pcharge;
