@@ -35,7 +35,7 @@ for name, kw, nptl, maps in CASES:
         P.deltab_flag = 1
         P.correlation_flag = 1
     line = f"{name:34s}"
-    for route in ("1", "0"):
+    for route in os.environ.get("ALT_PROBE_ROUTES", "1,0").split(","):
         os.environ["GPAT_ALT_STRICT"] = route
         g = GpatSim(P, w.nptl_max)
         g.upload_fields(0, frames[0])

@@ -101,6 +101,11 @@ constexpr bool kStrict = (GPAT_STRICT != 0);
 // SPEC value of the production-build instantiations that run the general pushers (push_physics: 1-D, focused transport,
 // turbulence maps, every switch at run time) behind the lane-group gather
 constexpr int kSpecAlt = 16;
+// ... and the same with the lane-group gather of the turbulence-map record compiled in (deltab_flag / correlation_flag):
+// a separate instantiation, because carrying the map code costs runs without maps 10 % (profiles/README.md, calls Y, Z)
+constexpr int kSpecAltMaps = 16 | 32;
+__host__ __device__ constexpr bool spec_is_alt(int spec) { return (spec & 16) != 0; }
+__host__ __device__ constexpr bool spec_has_maps(int spec) { return (spec & 32) != 0; }
 
 // particle_boundary_condition for a single rank (neighbours are self or -1)
 // ALT: the run may be 1-D (reference-order build: always checked)
@@ -1046,9 +1051,11 @@ __device__ __forceinline__ void push_ft_3d_like(const DevParams& prm, const Push
 // order.  Reference-order build: called by push_once() below.  Production build: phase C of the kSpecAlt
 // instantiations of push_kernel_coop (1-D, focused transport, turbulence maps) -- same statements, compiled with FMA
 // contraction and the production locate() / u01(); held to 1e-12 per step like the other production kernels.
-template <int L, bool TRACK = false>
+// PRE: the caller gathered the map record already (aux_pre, or nullptr in a run without maps)
+template <int L, bool TRACK = false, bool PRE = false>
 __device__ __forceinline__ void push_physics(const DevParams& prm, const PushArgs& a,
-                                             const double (&F)[Rec<L>::NREC], Lane& q, bool fixed_dt, double rt)
+                                             const double (&F)[Rec<L>::NREC], Lane& q, bool fixed_dt, double rt,
+                                             const double* aux_pre = nullptr)
 {
     // tracked particles carry negated tags; the streams are keyed by the magnitudes so that a
     // tracking run replays the run its particles were selected from
@@ -1074,11 +1081,13 @@ __device__ __forceinline__ void push_physics(const DevParams& prm, const PushArg
     }
     q.rng += 1;
 
-    const double* auxp = nullptr;
-    double A[16];
-    if (a.aux && (prm.deltab_flag || prm.correlation_flag)) {  // particle_module.f90:1634-1639
-        gather_aux<Rec<L>::NDIM>(prm, a.aux, a.sel, q.x, q.y, q.z, rt, A);
-        auxp = A;
+    const double* auxp = aux_pre;  // production build: the lane group gathered the map record with the fields
+    double A[PRE ? 1 : 16];
+    if constexpr (!PRE) {
+        if (a.aux && (prm.deltab_flag || prm.correlation_flag)) {  // particle_module.f90:1634-1639
+            gather_aux<Rec<L>::NDIM>(prm, a.aux, a.sel, q.x, q.y, q.z, rt, A);
+            auxp = A;
+        }
     }
     if constexpr (D3) {  // particle_module.f90:1662-1665, 1683-1686
         if (prm.acc_by_surface) surface_heights(prm, a, q.x, q.y, q.z, rt, q.sh1, q.sh2);
@@ -1447,7 +1456,7 @@ __device__ __forceinline__ int after_push(const DevParams& prm, const PushArgs& 
     // gpat_debug_push_n: a uniform branch on a kernel argument, kept in the switch-specialised instantiations too so
     // that the per-step parity tests run the very kernels bench.py times
     if (a.debug_nsteps > 0) return (--remaining == 0) ? ST_IDLE : ST_ADAPT;
-    return next_state<TRACK, SPEC == kSpecAlt>(prm, a, q, state == ST_FIX ? AFTER_FIXED_PUSH : AT_INNER_HEAD);
+    return next_state<TRACK, spec_is_alt(SPEC)>(prm, a, q, state == ST_FIX ? AFTER_FIXED_PUSH : AT_INNER_HEAD);
 }
 
 template <int L, bool TRACK = false>
@@ -1524,6 +1533,12 @@ push_kernel(const __grid_constant__ DevParams prm, const PtlSoA P, const float* 
 // interpolation weight, so the FMA sees the same exact product f*w as with a real conversion.
 // GPAT_CVT_ALU_MASK picks which (row cy, frame half h) quarter of the corner values goes this
 // way: bit 2*cy + h.
+#ifndef GPAT_ALT_MINBLOCKS
+#define GPAT_ALT_MINBLOCKS 3   // resident CTAs per SM the 2-D kSpecAlt instantiations are compiled for (168 registers)
+#endif
+#ifndef GPAT_ALT_MINBLOCKS_3D
+#define GPAT_ALT_MINBLOCKS_3D 2  // 3-D: 255 registers, no spills: focused transport +9 %, maps +21 % over 3 CTAs (call Z)
+#endif
 #ifndef GPAT_CVT_WIDE
 #define GPAT_CVT_WIDE 0
 #endif
@@ -1569,7 +1584,7 @@ __device__ __forceinline__ void fma_chunk(int c, const float4& f, double w, doub
     }
 }
 
-template <int L> struct Coop {
+template <int L, bool AUX = false> struct Coop {
     static constexpr int NREC = Rec<L>::NREC;
     static constexpr int NCH = NREC / 4;                          // 32-byte chunks per grid point
 #ifdef GPAT_COOP_G
@@ -1592,6 +1607,13 @@ template <int L> struct Coop {
     static constexpr int NSIDE = Rec<L>::NSIDE;
     static constexpr int SCH = Rec<L>::SIDE_CHUNKS;
     static constexpr int SIDEROW = SCH ? 4 * G : (NSIDE ? 2 * G : 0);   // doubles parked per owner row
+    // AUX (kSpecAlt instantiations): the 16 interpolated values of the turbulence-map record (128 B per grid point, four
+    // chunks in the fields' own chunk format) are gathered by the same lanes with the same weights -- 4 / G map chunks
+    // per lane -- and parked behind the record part of the owner's row.
+    // They live in rows of their own (AROW doubles per owner) so that the record rows keep the pitch and the skew
+    // measured above whether a run has maps or not.
+    static constexpr int ACPL = AUX ? 4 / G : 0;
+    static constexpr int AROW = AUX ? 18 : 0;
     static constexpr int ROW = (SKEW ? NREC + 4 : NREC + 2) + SIDEROW;
     // parameter rows.  2-D: the owner publishes its eight finished corner weights (time blend and
     // conversion scale folded in) + the cell, 80 B; the other lanes of the group load them instead
@@ -1621,18 +1643,23 @@ template <int L> struct MinBlocks { static constexpr int V = (L == L2B || L == L
 // a run restarted from a dump starts with sel = 0 again and has to continue bit-identically
 // (tests/test_gpu_parity.py::test_restart_round_trip_is_bit_exact).
 template <int L, int SEL, bool TRACK = false, int SPEC = 0>
-__global__ void __launch_bounds__(kBlock, (SPEC == kSpecAlt ? 3 : MinBlocks<L>::V))
+__global__ void __launch_bounds__(kBlock, (spec_is_alt(SPEC) ? (Rec<L>::NDIM == 3 ? GPAT_ALT_MINBLOCKS_3D : GPAT_ALT_MINBLOCKS)
+                                                               : MinBlocks<L>::V))
 push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                  const float* __restrict__ fld, const __grid_constant__ PushArgs a)
 {
-    using C = Coop<L>;
+    using C = Coop<L, spec_has_maps(SPEC)>;
     constexpr int NW = kBlock / 32;
-    __shared__ __align__(16) double sm_par[NW][32 * C::PAR];
-    __shared__ __align__(16) double sm_res[NW][32 * C::ROW];
     const unsigned lane = threadIdx.x & 31u;
     const unsigned wid = threadIdx.x >> 5;
-    double* const par = sm_par[wid];
-    double* const res = sm_res[wid];
+    // rows of the kSpecAlt instantiations carry the 16 map values too and exceed the 48 KB of static shared memory with the
+    // wide records: those instantiations take their rows from dynamic shared memory (coop_smem_bytes, launch_one)
+    extern __shared__ __align__(16) double coop_dyn[];
+    __shared__ __align__(16) double sm_par[spec_is_alt(SPEC) ? 1 : NW][spec_is_alt(SPEC) ? 2 : 32 * C::PAR];
+    __shared__ __align__(16) double sm_res[spec_is_alt(SPEC) ? 1 : NW][spec_is_alt(SPEC) ? 2 : 32 * C::ROW];
+    double* const par = spec_is_alt(SPEC) ? coop_dyn + wid * (32 * C::PAR) : sm_par[wid];
+    double* const res = spec_is_alt(SPEC) ? coop_dyn + NW * (32 * C::PAR) + wid * (32 * C::ROW) : sm_res[wid];
+    double* const ares = coop_dyn + NW * (32 * (C::PAR + C::ROW)) + wid * (32 * C::AROW);  // kSpecAltMaps only
     const int gq = (int)(lane & (C::G - 1));
     const int gbase = (int)(lane & ~(unsigned)(C::G - 1));
     constexpr long long stride = 2LL * C::NREC;
@@ -1644,7 +1671,8 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
     int remaining = 0;
     unsigned long long nsteps = 0;
 
-    constexpr bool ALT = (SPEC == kSpecAlt);
+    constexpr bool ALT = spec_is_alt(SPEC);
+    constexpr bool has_aux = spec_has_maps(SPEC);  // launch_one picks kSpecAltMaps exactly when the run has maps
     for (;;) {
         refill<TRACK, (C::G == 4) && !GPAT_NO_PERM, ALT>(prm, a, P, lane, q, state, idx, exhausted, remaining);
         if (__all_sync(0xffffffffu, state == ST_IDLE)) {
@@ -1667,7 +1695,7 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
             double rx = 0.0, ry = 0.0, rz = 0.0, t0 = 0.0, t1 = 0.0;
             long long cell = 0;
             if (state != ST_IDLE) {
-                cell = locate<Rec<L>::NDIM, (SPEC == kSpecAlt)>(prm, q.x, q.y, q.z, rx, ry, rz);
+                cell = locate<Rec<L>::NDIM, spec_is_alt(SPEC)>(prm, q.x, q.y, q.z, rx, ry, rz);
                 const double rt = (q.t - a.t0) * a.idtf;
                 const bool ti = (SPEC & 1) || prm.time_interp;  // SPEC: time interpolation on
                 const double tA = ti ? 1.0 - rt : 1.0, tB = ti ? rt : 0.0;
@@ -1853,6 +1881,44 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                     out[2 * j] = make_double2(acc[j][0], acc[j][1]);
                     out[2 * j + 1] = make_double2(acc[j][2], acc[j][3]);
                 }
+                if constexpr (C::ACPL > 0) {
+                    // turbulence maps (interp_magnetic_fluctuation + interp_correlation_length, mhd_data_parallel.f90:
+                    // 1806-1915): a second, smaller gather of this round's particle with the weights already in registers
+                    {
+                        const long long cell = __double_as_longlong(par[owner * C::PAR + C::CELL_AT]);
+                        const float* ab = a.aux + cell * 32 + (gq * C::ACPL) * 8;
+                        float4 alo[C::NC * C::ACPL], ahi[C::NC * C::ACPL];
+#pragma unroll
+                        for (int c = 0; c < C::NC; ++c) {
+                            const float* pc_ = ab + ((c & 1) + (long long)((c >> 1) & 1) * prm.nxg +
+                                                     (long long)(c >> 2) * prm.nxg * prm.nyg) * 32;
+#pragma unroll
+                            for (int j = 0; j < C::ACPL; ++j) ldg256(pc_ + 8 * j, alo[c * C::ACPL + j], ahi[c * C::ACPL + j]);
+                        }
+                        double aacc[C::ACPL][4];
+#pragma unroll
+                        for (int j = 0; j < C::ACPL; ++j) aacc[j][0] = aacc[j][1] = aacc[j][2] = aacc[j][3] = 0.0;
+#pragma unroll
+                        for (int c = 0; c < C::NC; ++c) {
+#pragma unroll
+                            for (int j = 0; j < C::ACPL; ++j) {
+                                if constexpr (SEL == 0) {
+                                    fma_chunk<0, 0>(c, alo[c * C::ACPL + j], w0[c], aacc[j]);
+                                    fma_chunk<0, 1>(c, ahi[c * C::ACPL + j], w1[c], aacc[j]);
+                                } else {
+                                    fma_chunk<0, 1>(c, ahi[c * C::ACPL + j], w1[c], aacc[j]);
+                                    fma_chunk<0, 0>(c, alo[c * C::ACPL + j], w0[c], aacc[j]);
+                                }
+                            }
+                        }
+                        double2* ao = reinterpret_cast<double2*>(ares + owner * C::AROW + (gq * C::ACPL) * 4);
+#pragma unroll
+                        for (int j = 0; j < C::ACPL; ++j) {
+                            ao[2 * j] = make_double2(aacc[j][0], aacc[j][1]);
+                            ao[2 * j + 1] = make_double2(aacc[j][2], aacc[j][3]);
+                        }
+                    }
+                }
             }
         }
         __syncwarp();
@@ -1883,7 +1949,21 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
             }
             if constexpr (ALT) {
                 static_assert(!ALT || Rec<L>::NF == Rec<L>::NREC, "the general pushers read one-plane records");
-                push_physics<L, TRACK>(prm, a, F, q, state == ST_FIX, (q.t - a.t0) * a.idtf);
+                // Always a valid array (registers, constant indices): the pushers read it only under deltab_flag /
+                // correlation_flag, and gpat_particle_mover refuses to run with a flag set and no maps uploaded.
+                double A[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) A[k] = 1.0;
+                if constexpr (has_aux) {
+                    const double2* ar = reinterpret_cast<const double2*>(ares + (int)lane * C::AROW);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const double2 v = ar[k];
+                        A[2 * k] = v.x;
+                        A[2 * k + 1] = v.y;
+                    }
+                }
+                push_physics<L, TRACK, true>(prm, a, F, q, state == ST_FIX, (q.t - a.t0) * a.idtf, A);
             } else {
                 physics_fast<L, double[Rec<L>::NF], TRACK, SPEC>(prm, a, F, q, state == ST_FIX);
             }
@@ -1931,12 +2011,35 @@ void launch_one(const DevParams& prm, const PtlSoA& P, const float* fld, const P
     if (a.variant == 1) {
         // GPAT_PUSH_SMEM_PAD: occupancy experiments (unused dynamic shared memory per CTA)
         size_t pad = 0;
+        // 1-D, focused transport, turbulence maps: the general pushers behind the lane-group gather (one-plane records)
+        const bool alt = (Rec<L>::NF == Rec<L>::NREC) &&
+                         (prm.ndim == 1 || prm.focused_transport || prm.deltab_flag || prm.correlation_flag);
+        const bool maps = a.aux && (prm.deltab_flag || prm.correlation_flag);
         if (const char* e = getenv("GPAT_PUSH_SMEM_PAD")) {
             pad = (size_t)atol(e);
             cudaFuncSetAttribute(push_kernel_coop<L, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
             cudaFuncSetAttribute(push_kernel_coop<L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
         }
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel_coop<L, 0>, kBlock, pad);
+        if constexpr (Rec<L>::NF == Rec<L>::NREC) {
+            if (alt) {  // the kSpecAlt instantiations keep their rows in dynamic shared memory
+                using CA = Coop<L, true>;
+                pad = (size_t)(kBlock / 32) * 32 * (CA::PAR + CA::ROW + (maps ? CA::AROW : 0)) * sizeof(double);
+                auto set = [&](auto k) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad); };
+                if (maps) {
+                    set(push_kernel_coop<L, 0, false, kSpecAltMaps>); set(push_kernel_coop<L, 1, false, kSpecAltMaps>);
+                    set(push_kernel_coop<L, 0, true, kSpecAltMaps>); set(push_kernel_coop<L, 1, true, kSpecAltMaps>);
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel_coop<L, 0, false, kSpecAltMaps>, kBlock, pad);
+                } else {
+                    set(push_kernel_coop<L, 0, false, kSpecAlt>); set(push_kernel_coop<L, 1, false, kSpecAlt>);
+                    set(push_kernel_coop<L, 0, true, kSpecAlt>); set(push_kernel_coop<L, 1, true, kSpecAlt>);
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel_coop<L, 0, false, kSpecAlt>, kBlock, pad);
+                }
+            } else {
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel_coop<L, 0>, kBlock, pad);
+            }
+        } else {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel_coop<L, 0>, kBlock, pad);
+        }
         if (per_sm < 1) per_sm = 1;
         {
             // Size residency to the L2, not to the register file.  A lane re-reads the same NC records
@@ -1980,11 +2083,10 @@ void launch_one(const DevParams& prm, const PtlSoA& P, const float* fld, const P
             push_kernel_coop<L, decltype(sel_c)::value, decltype(trk_c)::value, decltype(spec_c)::value>
                 <<<(unsigned)grid, kBlock, pad, st>>>(prm, P, fld, a);
         };
-        // 1-D, focused transport, turbulence maps: the general pushers behind the lane-group gather (one-plane records)
-        const bool alt = prm.ndim == 1 || prm.focused_transport || prm.deltab_flag || prm.correlation_flag;
         auto by_spec = [&](auto sel_c, auto trk_c) {
             using I = std::integral_constant<int, 0>;
             if constexpr (Rec<L>::NF == Rec<L>::NREC) {
+                if (alt && maps) { go(sel_c, trk_c, std::integral_constant<int, kSpecAltMaps>{}); return; }
                 if (alt) { go(sel_c, trk_c, std::integral_constant<int, kSpecAlt>{}); return; }
             }
             if constexpr (Rec<L>::NDIM == 2) {
