@@ -322,6 +322,11 @@ void launch_push_fast(int layout, const DevParams& prm, const PtlSoA& P, const f
                       const PushArgs& a, int sm_count, cudaStream_t st);
 void launch_push_strict(int layout, const DevParams& prm, const PtlSoA& P, const float* fld,
                         const PushArgs& a, int sm_count, cudaStream_t st);
+// production build, translation units of their own: the kSpecAlt instantiations of the 2-D / 3-D one-plane records
+void launch_push_alt2d(int layout, const DevParams& prm, const PtlSoA& P, const float* fld,
+                       const PushArgs& a, int sm_count, cudaStream_t st);
+void launch_push_alt3d(int layout, const DevParams& prm, const PtlSoA& P, const float* fld,
+                       const PushArgs& a, int sm_count, cudaStream_t st);
 void launch_interp_debug(int layout, const DevParams& prm, const float* fld, int sel, long long n,
                          const double* x, const double* y, const double* z, const double* rt,
                          double* out32, cudaStream_t st);

@@ -26,6 +26,11 @@
 #ifndef GPAT_STRICT
 #define GPAT_STRICT 0
 #endif
+// The production build is three translation units of this file (compile time): GPAT_TU_PART 0 = the kernels of the named
+// configs + every generic instantiation, 1 / 2 = the 2-D / 3-D kSpecAlt instantiations (1-D, focused transport, maps).
+#ifndef GPAT_TU_PART
+#define GPAT_TU_PART 0
+#endif
 
 namespace gpat {
 namespace {
@@ -1997,6 +2002,78 @@ __global__ void interp_kernel(const __grid_constant__ DevParams prm, const float
 
 template <int L> constexpr int C_NC() { return (Rec<L>::NDIM == 3) ? 8 : 4; }
 
+#if !GPAT_STRICT
+// Size residency to the L2, not to the register file.  A lane re-reads the same NC records step after step, so the
+// live working set is resident lanes x NC x record bytes; it is served by L2 only while it fits about half of it (the
+// 126 MB L2 of a B200 is two partitions).  2-D records: 39-58 MB at full occupancy, no cap.  3-D Parker: 29 MB per
+// resident CTA per SM -> 2 CTAs; measured on C5: 1/2/3/4 CTAs per SM = 2.61/3.45/3.17/2.84e9 steps/s
+// (profiles/README.md).  GPAT_PUSH_MAXCTAS overrides.
+template <int L>
+int l2_cap(int sm_count, int per_sm, const PushArgs& a)
+{
+    static int l2_bytes = 0;
+    if (!l2_bytes) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, dev);
+        if (l2_bytes <= 0) l2_bytes = 64 << 20;
+    }
+    const double per_cta = (double)sm_count * kBlock * C_NC<L>() * ((2.0 * Rec<L>::NREC + side_floats_of(L)) * 4.0);
+    int cap = (int)(0.5 * (double)l2_bytes / per_cta + 0.5);
+    if (cap < 1) cap = 1;
+    // Cell-sorted particles (sort.cu) share their records across the lanes of a warp: the working
+    // set per lane shrinks and full occupancy wins again (C5 sorted: 2/3/4 CTAs = 4.8/5.6/5.7e9).
+    if (a.sorted) cap = per_sm;
+    if (const char* e = getenv("GPAT_PUSH_MAXCTAS")) cap = atoi(e) > 0 ? atoi(e) : cap;
+    return per_sm > cap ? cap : per_sm;
+}
+#endif
+
+#if !GPAT_STRICT && GPAT_TU_PART != 0
+// The kSpecAlt / kSpecAltMaps instantiations (1-D, focused transport, turbulence maps): rows in dynamic shared memory
+// (the map rows only when the run has maps), grid sized from the occupancy of the instantiation that runs.
+template <int L>
+void launch_alt(const DevParams& prm, const PtlSoA& P, const float* fld, const PushArgs& a,
+                int sm_count, cudaStream_t st)
+{
+    static_assert(Rec<L>::NF == Rec<L>::NREC, "the general pushers read one-plane records");
+    const bool maps = a.aux && (prm.deltab_flag || prm.correlation_flag);
+    using CA = Coop<L, true>;
+    const size_t smem = (size_t)(kBlock / 32) * 32 * (CA::PAR + CA::ROW + (maps ? CA::AROW : 0)) * sizeof(double);
+    int per_sm = 0;
+    auto set = [&](auto k) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); };
+    if (maps) {
+        set(push_kernel_coop<L, 0, false, kSpecAltMaps>); set(push_kernel_coop<L, 1, false, kSpecAltMaps>);
+        set(push_kernel_coop<L, 0, true, kSpecAltMaps>); set(push_kernel_coop<L, 1, true, kSpecAltMaps>);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel_coop<L, 0, false, kSpecAltMaps>, kBlock, smem);
+    } else {
+        set(push_kernel_coop<L, 0, false, kSpecAlt>); set(push_kernel_coop<L, 1, false, kSpecAlt>);
+        set(push_kernel_coop<L, 0, true, kSpecAlt>); set(push_kernel_coop<L, 1, true, kSpecAlt>);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel_coop<L, 0, false, kSpecAlt>, kBlock, smem);
+    }
+    if (per_sm < 1) per_sm = 1;
+    per_sm = l2_cap<L>(sm_count, per_sm, a);
+    const long long want = (a.nptl + kBlock - 1) / kBlock;
+    long long grid = (long long)sm_count * per_sm;  // persistent: a multiple of the SM count
+    if (want < grid) grid = want > 0 ? want : 1;
+    auto go = [&](auto sel_c, auto trk_c, auto spec_c) {
+        push_kernel_coop<L, decltype(sel_c)::value, decltype(trk_c)::value, decltype(spec_c)::value>
+            <<<(unsigned)grid, kBlock, smem, st>>>(prm, P, fld, a);
+    };
+    auto by_maps = [&](auto sel_c, auto trk_c) {
+        if (maps) go(sel_c, trk_c, std::integral_constant<int, kSpecAltMaps>{});
+        else go(sel_c, trk_c, std::integral_constant<int, kSpecAlt>{});
+    };
+    auto by_trk = [&](auto sel_c) {
+        if (a.trk.enabled) by_maps(sel_c, std::true_type{});
+        else by_maps(sel_c, std::false_type{});
+    };
+    if (a.sel == 0) by_trk(std::integral_constant<int, 0>{});
+    else by_trk(std::integral_constant<int, 1>{});
+}
+#endif
+
+#if GPAT_STRICT || GPAT_TU_PART == 0
 template <int L>
 void launch_one(const DevParams& prm, const PtlSoA& P, const float* fld, const PushArgs& a,
                 int sm_count, cudaStream_t st)
@@ -2011,59 +2088,23 @@ void launch_one(const DevParams& prm, const PtlSoA& P, const float* fld, const P
     if (a.variant == 1) {
         // GPAT_PUSH_SMEM_PAD: occupancy experiments (unused dynamic shared memory per CTA)
         size_t pad = 0;
-        // 1-D, focused transport, turbulence maps: the general pushers behind the lane-group gather (one-plane records)
-        const bool alt = (Rec<L>::NF == Rec<L>::NREC) &&
-                         (prm.ndim == 1 || prm.focused_transport || prm.deltab_flag || prm.correlation_flag);
-        const bool maps = a.aux && (prm.deltab_flag || prm.correlation_flag);
+        // 1-D, focused transport, turbulence maps: the general pushers behind the lane-group gather (one-plane records);
+        // their instantiations live in translation units of their own (GPAT_TU_PART 1 and 2, see the Makefile)
+        if constexpr (Rec<L>::NF == Rec<L>::NREC) {
+            if (prm.ndim == 1 || prm.focused_transport || prm.deltab_flag || prm.correlation_flag) {
+                if (Rec<L>::NDIM == 2) launch_push_alt2d(L, prm, P, fld, a, sm_count, st);
+                else launch_push_alt3d(L, prm, P, fld, a, sm_count, st);
+                return;
+            }
+        }
         if (const char* e = getenv("GPAT_PUSH_SMEM_PAD")) {
             pad = (size_t)atol(e);
             cudaFuncSetAttribute(push_kernel_coop<L, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
             cudaFuncSetAttribute(push_kernel_coop<L, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad);
         }
-        if constexpr (Rec<L>::NF == Rec<L>::NREC) {
-            if (alt) {  // the kSpecAlt instantiations keep their rows in dynamic shared memory
-                using CA = Coop<L, true>;
-                pad = (size_t)(kBlock / 32) * 32 * (CA::PAR + CA::ROW + (maps ? CA::AROW : 0)) * sizeof(double);
-                auto set = [&](auto k) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pad); };
-                if (maps) {
-                    set(push_kernel_coop<L, 0, false, kSpecAltMaps>); set(push_kernel_coop<L, 1, false, kSpecAltMaps>);
-                    set(push_kernel_coop<L, 0, true, kSpecAltMaps>); set(push_kernel_coop<L, 1, true, kSpecAltMaps>);
-                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel_coop<L, 0, false, kSpecAltMaps>, kBlock, pad);
-                } else {
-                    set(push_kernel_coop<L, 0, false, kSpecAlt>); set(push_kernel_coop<L, 1, false, kSpecAlt>);
-                    set(push_kernel_coop<L, 0, true, kSpecAlt>); set(push_kernel_coop<L, 1, true, kSpecAlt>);
-                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel_coop<L, 0, false, kSpecAlt>, kBlock, pad);
-                }
-            } else {
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel_coop<L, 0>, kBlock, pad);
-            }
-        } else {
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel_coop<L, 0>, kBlock, pad);
-        }
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel_coop<L, 0>, kBlock, pad);
         if (per_sm < 1) per_sm = 1;
-        {
-            // Size residency to the L2, not to the register file.  A lane re-reads the same NC records
-            // step after step, so the live working set is resident lanes x NC x record bytes; it is
-            // served by L2 only while it fits about half of it (the 126 MB L2 of a B200 is two
-            // partitions).  2-D records: 39-58 MB at full occupancy, no cap.  3-D Parker: 29 MB per
-            // resident CTA per SM -> 2 CTAs; measured on C5: 1/2/3/4 CTAs per SM = 2.61/3.45/3.17/2.84e9
-            // steps/s (profiles/README.md).  GPAT_PUSH_MAXCTAS overrides.
-            static int l2_bytes = 0;
-            if (!l2_bytes) {
-                int dev = 0;
-                cudaGetDevice(&dev);
-                cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, dev);
-                if (l2_bytes <= 0) l2_bytes = 64 << 20;
-            }
-            const double per_cta = (double)sm_count * kBlock * C_NC<L>() * ((2.0 * Rec<L>::NREC + side_floats_of(L)) * 4.0);
-            int cap = (int)(0.5 * (double)l2_bytes / per_cta + 0.5);
-            if (cap < 1) cap = 1;
-            // Cell-sorted particles (sort.cu) share their records across the lanes of a warp: the working
-            // set per lane shrinks and full occupancy wins again (C5 sorted: 2/3/4 CTAs = 4.8/5.6/5.7e9).
-            if (a.sorted) cap = per_sm;
-            if (const char* e = getenv("GPAT_PUSH_MAXCTAS")) cap = atoi(e) > 0 ? atoi(e) : cap;
-            if (per_sm > cap) per_sm = cap;
-        }
+        per_sm = l2_cap<L>(sm_count, per_sm, a);
         grid = (long long)sm_count * per_sm;
         if (want < grid) grid = want > 0 ? want : 1;
         // tracking runs use their own instantiations: the production kernels carry no tracking code
@@ -2085,10 +2126,6 @@ void launch_one(const DevParams& prm, const PtlSoA& P, const float* fld, const P
         };
         auto by_spec = [&](auto sel_c, auto trk_c) {
             using I = std::integral_constant<int, 0>;
-            if constexpr (Rec<L>::NF == Rec<L>::NREC) {
-                if (alt && maps) { go(sel_c, trk_c, std::integral_constant<int, kSpecAltMaps>{}); return; }
-                if (alt) { go(sel_c, trk_c, std::integral_constant<int, kSpecAlt>{}); return; }
-            }
             if constexpr (Rec<L>::NDIM == 2) {
                 if (spec == kSpec11) { go(sel_c, trk_c, std::integral_constant<int, kSpec11>{}); return; }
                 if constexpr (L == L2B) {
@@ -2115,8 +2152,25 @@ void launch_one(const DevParams& prm, const PtlSoA& P, const float* fld, const P
     if (a.trk.enabled) push_kernel<L, true><<<(unsigned)grid, kBlock, 0, st>>>(prm, P, fld, a);
     else push_kernel<L><<<(unsigned)grid, kBlock, 0, st>>>(prm, P, fld, a);
 }
+#endif
 
 }  // namespace
+
+#if !GPAT_STRICT && GPAT_TU_PART == 1
+void launch_push_alt2d(int layout, const DevParams& prm, const PtlSoA& P, const float* fld,
+                       const PushArgs& a, int sm_count, cudaStream_t st)
+{
+    if (layout == L2B) launch_alt<L2B>(prm, P, fld, a, sm_count, st);
+    else launch_alt<L2E>(prm, P, fld, a, sm_count, st);
+}
+#elif !GPAT_STRICT && GPAT_TU_PART == 2
+void launch_push_alt3d(int layout, const DevParams& prm, const PtlSoA& P, const float* fld,
+                       const PushArgs& a, int sm_count, cudaStream_t st)
+{
+    if (layout == L3B) launch_alt<L3B>(prm, P, fld, a, sm_count, st);
+    else launch_alt<L3E>(prm, P, fld, a, sm_count, st);
+}
+#else
 
 #if GPAT_STRICT
 #define GPAT_LAUNCH launch_push_strict
@@ -2156,5 +2210,7 @@ void launch_interp_debug(int layout, const DevParams& prm, const float* fld, int
     }
 }
 #endif
+
+#endif  // GPAT_TU_PART
 
 }  // namespace gpat
