@@ -1544,6 +1544,9 @@ push_kernel(const __grid_constant__ DevParams prm, const PtlSoA P, const float* 
 #ifndef GPAT_ALT_MINBLOCKS_3D
 #define GPAT_ALT_MINBLOCKS_3D 2  // 3-D: 255 registers, no spills: focused transport +9 %, maps +21 % over 3 CTAs (call Z)
 #endif
+#ifndef GPAT_SKIP_ROUNDS
+#define GPAT_SKIP_ROUNDS 0
+#endif
 #ifndef GPAT_CVT_WIDE
 #define GPAT_CVT_WIDE 0
 #endif
@@ -1765,10 +1768,20 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                         ldg256(pc_ + 8 * j, lo[slot][c * C::CPL + j], hi[slot][c * C::CPL + j]);
                 }
             };
+            // GPAT_SKIP_ROUNDS=1 (A/B build, MEASURED AND REJECTED, profiles/README.md call T3): skip the rounds whose owner
+            // lanes are all idle (warp-uniform test), so that at the end of a launch, when the queue is empty and a warp holds
+            // one or two unfinished particles, an iteration costs one or two L2 round trips instead of four.  The uniform
+            // branches around the loads stop the compiler from overlapping the rounds: C1 -8 % (2.23e10 -> 2.06e10), and even
+            // the tail-dominated 125 000-particle run loses 6 %.  Four-lane groups only: with two lanes per particle the
+            // conditional prefetch of 96 load registers spills 400 bytes.
+            constexpr bool kSkip = (GPAT_SKIP_ROUNDS != 0) && (C::G == 4);
+            const unsigned act = kSkip ? __ballot_sync(0xffffffffu, state != ST_IDLE) : 0xffffffffu;
+            auto need = [&](int r) { return !kSkip || (act & (0x11111111u << r)) != 0u; };
             constexpr bool ROLLED = (GPAT_ROUNDS_UNROLL(C::NC, C::G) == 1);  // rolled: loads at the top of every round,
             if constexpr (!ROLLED) {                                         // no buffers carried across the back-edge
 #pragma unroll
-                for (int r = 0; r < DEPTH; ++r) issue(r, r);
+                for (int r = 0; r < DEPTH; ++r)
+                    if (need(r)) issue(r, r);
             }
             // 2-D: the four rounds are unrolled (2700-instruction body, no instruction-fetch stalls).  3-D: a rolled loop --
             // unrolled, the body is 4096 instructions = 64 KB and "no instruction" is the second largest stall reason
@@ -1778,6 +1791,12 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
             for (int r = 0; r < C::G; ++r) {
                 const int owner = gbase + r;
                 const int slot = ROLLED ? 0 : r % DEPTH;
+                if (!need(r)) {
+                    if constexpr (!ROLLED) {
+                        if (r + DEPTH < C::G && need(r + DEPTH)) issue(r + DEPTH, slot);
+                    }
+                    continue;
+                }
                 if constexpr (ROLLED) issue(r, 0);
                 const double2* row = reinterpret_cast<const double2*>(par + owner * C::PAR);
                 // weights of half 0 / half 1 at each corner (time blend folded in)
@@ -1872,7 +1891,7 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                     }
                 }
                 if constexpr (!ROLLED) {
-                    if (r + DEPTH < C::G) issue(r + DEPTH, slot);
+                    if (r + DEPTH < C::G && need(r + DEPTH)) issue(r + DEPTH, slot);
                 }
                 double2* out = reinterpret_cast<double2*>(res + C::row_off(owner) + (gq * C::CPL) * 4);
                 if constexpr (C::SCH > 0) {
