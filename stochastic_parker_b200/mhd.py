@@ -293,11 +293,14 @@ def make_turbulence_maps(nx: int, ny: int, nz: int, frame: int, ndim: int = 2, d
     """Synthetic deltab_NNNN / lc_NNNN content (read_magnetic_fluctuation, read_correlation_length,
     mhd_data_parallel.f90:306-497: each file holds the slab array then the 2-D array over the ghosted
     grid, float32).  Smooth, strictly positive, time-dependent: returns
-    (sigma2_slab, sigma2_2d, lc_slab, lc_2d), each (ny+4, nx+4) or (nz+4, ny+4, nx+4)."""
+    (sigma2_slab, sigma2_2d, lc_slab, lc_2d), each (nx+4,), (ny+4, nx+4) or (nz+4, ny+4, nx+4)."""
     t = frame * dt_out
     xs = (np.arange(nx + 4, dtype=np.float64) - 2.0) / max(nx - 1, 1)
     ys = (np.arange(ny + 4, dtype=np.float64) - 2.0) / max(ny - 1, 1)
-    if ndim == 2:
+    if ndim == 1:   # one row, no ghost rows in y (the 1-D files hold nx + 4 values per array)
+        X = xs
+        Y = Z = 0.0 * X
+    elif ndim == 2:
         X, Y = np.meshgrid(xs, ys)
         Z = 0.0 * X
     else:
