@@ -183,8 +183,8 @@ int gpat_upload_fields(gpat_handle h, int slot, const float* f, int nvar, int wi
  * the content of the reference's deltab_NNNN / lc_NNNN file.  slot as in gpat_upload_fields;
  * gpat_swap_fields also stands for copy_magnetic_fluctuation / copy_correlation_length
  * (:1928-1941).  The maps enter kappa (particle_module.f90:2246-2254, 2314-2321, 2505-2517,
- * 2589-2604), D_mumu (:3143-3148) and inject_large_db2; runs that use them take the
- * reference-order build of the push kernel. */
+ * 2589-2604), D_mumu (:3143-3148) and inject_large_db2; both builds gather them (production build:
+ * by the lane group that gathers the particle's field record). */
 int gpat_upload_turbulence(gpat_handle h, int which, int slot, const float* data);
 
 /* Acceleration surfaces (`-as 1`, 3-D).  Replaces read_acc_surface (acc_region_surface.f90:121-243):
@@ -192,7 +192,7 @@ int gpat_upload_turbulence(gpat_handle h, int which, int slot, const float* data
  * grid sizes of the two axes other than the surface normal, in x < y < z order; which = 0/1 for
  * surface 1/2, slot as in gpat_upload_fields (gpat_swap_fields also stands for copy_acc_surface,
  * :390-396).  interp_acc_surface (:255-334) and check_above_acc_surface (:342-388) run inside the
- * 3-D pushers (particle_module.f90:4887-4892, 5297-5303), reference-order build. */
+ * 3-D pushers (particle_module.f90:4887-4892, 5297-5303), both builds. */
 int gpat_upload_acc_surface(gpat_handle h, int which, int slot, const double* heights);
 
 /* Frame pipeline (stochastic-mhd.f90:401-447 reads frame tf at the top of every iteration,
