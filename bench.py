@@ -524,6 +524,13 @@ def main():
                                      "C4 take minutes per MHD interval)"}
             except Exception:
                 pass
+        gpath = os.path.join(ROOT, "profiles", "r02_general_pushers.json")
+        if os.path.exists(gpath):   # builder-run lines of the pushers outside the named configs (not re-run here)
+            try:
+                with open(gpath) as f:
+                    line.setdefault("extra", {})["general_pushers"] = json.load(f)
+            except Exception:
+                pass
         if world == 1 and not args.no_cpu_baseline:
             try:
                 base, _ = cpu_rate(w, P, cfg, args.cpu_seconds)
