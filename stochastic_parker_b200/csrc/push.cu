@@ -111,6 +111,13 @@ constexpr int kSpecAlt = 16;
 constexpr int kSpecAltMaps = 16 | 32;
 __host__ __device__ constexpr bool spec_is_alt(int spec) { return (spec & 16) != 0; }
 __host__ __device__ constexpr bool spec_has_maps(int spec) { return (spec & 32) != 0; }
+// ... and one instantiation per pusher (bits 6-7 of SPEC), so that a focused-transport kernel does not carry push_1d and
+// the Parker pushers and vice versa (the kernel that held all of them was 12 900 instructions, "no instruction" 0.4-0.7
+// stalls per issue, profiles/r02n2_push_coop_*_ncu.txt).  PATH_ANY reads ndim / focused_transport at run time: the
+// reference-order build.
+enum : int { PATH_ANY = 0, PATH_1D = 1, PATH_FT = 2, PATH_PARKER = 3 };
+__host__ __device__ constexpr int spec_path(int spec) { return (spec >> 6) & 3; }
+__host__ __device__ constexpr int alt_spec(int path, bool maps) { return 16 | (maps ? 32 : 0) | (path << 6); }
 
 // particle_boundary_condition for a single rank (neighbours are self or -1)
 // ALT: the run may be 1-D (reference-order build: always checked)
@@ -1057,7 +1064,7 @@ __device__ __forceinline__ void push_ft_3d_like(const DevParams& prm, const Push
 // instantiations of push_kernel_coop (1-D, focused transport, turbulence maps) -- same statements, compiled with FMA
 // contraction and the production locate() / u01(); held to 1e-12 per step like the other production kernels.
 // PRE: the caller gathered the map record already (aux_pre, or nullptr in a run without maps)
-template <int L, bool TRACK = false, bool PRE = false>
+template <int L, bool TRACK = false, bool PRE = false, int PATH = PATH_ANY>
 __device__ __forceinline__ void push_physics(const DevParams& prm, const PushArgs& a,
                                              const double (&F)[Rec<L>::NREC], Lane& q, bool fixed_dt, double rt,
                                              const double* aux_pre = nullptr)
@@ -1097,13 +1104,15 @@ __device__ __forceinline__ void push_physics(const DevParams& prm, const PushArg
     if constexpr (D3) {  // particle_module.f90:1662-1665, 1683-1686
         if (prm.acc_by_surface) surface_heights(prm, a, q.x, q.y, q.z, rt, q.sh1, q.sh2);
     }
+    const bool is_1d = (PATH == PATH_ANY) ? (prm.ndim == 1) : (PATH == PATH_1D);
+    const bool is_ft = (PATH == PATH_ANY) ? (prm.focused_transport != 0) : (PATH == PATH_FT);
     if constexpr (!D3) {
-        if (prm.ndim == 1) {
+        if (is_1d) {
             push_1d<L>(prm, a, F, u0, u1, q, fixed_dt, auxp);
             return;
         }
     }
-    if (prm.focused_transport) {
+    if (is_ft) {
         if (D3 || (EXT && prm.include_3rd_dim)) {
             // fifth uniform: first word of a second Philox block of this step (counter word 1, top bit flipped)
             const unsigned long long step = q.rng - 1;
@@ -1987,7 +1996,7 @@ push_kernel_coop(const __grid_constant__ DevParams prm, const PtlSoA P,
                         A[2 * k + 1] = v.y;
                     }
                 }
-                push_physics<L, TRACK, true>(prm, a, F, q, state == ST_FIX, (q.t - a.t0) * a.idtf, A);
+                push_physics<L, TRACK, true, spec_path(SPEC)>(prm, a, F, q, state == ST_FIX, (q.t - a.t0) * a.idtf, A);
             } else {
                 physics_fast<L, double[Rec<L>::NF], TRACK, SPEC>(prm, a, F, q, state == ST_FIX);
             }
@@ -2049,46 +2058,56 @@ int l2_cap(int sm_count, int per_sm, const PushArgs& a)
 #endif
 
 #if !GPAT_STRICT && GPAT_TU_PART != 0
-// The kSpecAlt / kSpecAltMaps instantiations (1-D, focused transport, turbulence maps): rows in dynamic shared memory
-// (the map rows only when the run has maps), grid sized from the occupancy of the instantiation that runs.
+// The kSpecAlt instantiations (1-D, focused transport, turbulence maps; one per pusher, with or without the map gather):
+// rows in dynamic shared memory (the map rows only when the run has maps), grid sized from the occupancy of the
+// instantiation that runs.
+template <int L, int SPEC>
+void launch_alt_spec(const DevParams& prm, const PtlSoA& P, const float* fld, const PushArgs& a,
+                     int sm_count, cudaStream_t st)
+{
+    using CA = Coop<L, spec_has_maps(SPEC)>;
+    const size_t smem = (size_t)(kBlock / 32) * 32 * (CA::PAR + CA::ROW + CA::AROW) * sizeof(double);
+    int per_sm = 0;
+    auto set = [&](auto k) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); };
+    set(push_kernel_coop<L, 0, false, SPEC>); set(push_kernel_coop<L, 1, false, SPEC>);
+    set(push_kernel_coop<L, 0, true, SPEC>); set(push_kernel_coop<L, 1, true, SPEC>);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel_coop<L, 0, false, SPEC>, kBlock, smem);
+    if (per_sm < 1) per_sm = 1;
+    per_sm = l2_cap<L>(sm_count, per_sm, a);
+    const long long want = (a.nptl + kBlock - 1) / kBlock;
+    long long grid = (long long)sm_count * per_sm;  // persistent: a multiple of the SM count
+    if (want < grid) grid = want > 0 ? want : 1;
+    auto go = [&](auto sel_c, auto trk_c) {
+        push_kernel_coop<L, decltype(sel_c)::value, decltype(trk_c)::value, SPEC>
+            <<<(unsigned)grid, kBlock, smem, st>>>(prm, P, fld, a);
+    };
+    auto by_trk = [&](auto sel_c) {
+        if (a.trk.enabled) go(sel_c, std::true_type{});
+        else go(sel_c, std::false_type{});
+    };
+    if (a.sel == 0) by_trk(std::integral_constant<int, 0>{});
+    else by_trk(std::integral_constant<int, 1>{});
+}
+
 template <int L>
 void launch_alt(const DevParams& prm, const PtlSoA& P, const float* fld, const PushArgs& a,
                 int sm_count, cudaStream_t st)
 {
     static_assert(Rec<L>::NF == Rec<L>::NREC, "the general pushers read one-plane records");
     const bool maps = a.aux && (prm.deltab_flag || prm.correlation_flag);
-    using CA = Coop<L, true>;
-    const size_t smem = (size_t)(kBlock / 32) * 32 * (CA::PAR + CA::ROW + (maps ? CA::AROW : 0)) * sizeof(double);
-    int per_sm = 0;
-    auto set = [&](auto k) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); };
-    if (maps) {
-        set(push_kernel_coop<L, 0, false, kSpecAltMaps>); set(push_kernel_coop<L, 1, false, kSpecAltMaps>);
-        set(push_kernel_coop<L, 0, true, kSpecAltMaps>); set(push_kernel_coop<L, 1, true, kSpecAltMaps>);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel_coop<L, 0, false, kSpecAltMaps>, kBlock, smem);
-    } else {
-        set(push_kernel_coop<L, 0, false, kSpecAlt>); set(push_kernel_coop<L, 1, false, kSpecAlt>);
-        set(push_kernel_coop<L, 0, true, kSpecAlt>); set(push_kernel_coop<L, 1, true, kSpecAlt>);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel_coop<L, 0, false, kSpecAlt>, kBlock, smem);
+    auto with_maps = [&](auto path_c) {
+        constexpr int PATH = decltype(path_c)::value;
+        if (maps) launch_alt_spec<L, alt_spec(PATH, true)>(prm, P, fld, a, sm_count, st);
+        else launch_alt_spec<L, alt_spec(PATH, false)>(prm, P, fld, a, sm_count, st);
+    };
+    if constexpr (Rec<L>::NDIM == 2) {   // 1-D runs live in the 2-D records
+        if (prm.ndim == 1) { with_maps(std::integral_constant<int, PATH_1D>{}); return; }
     }
-    if (per_sm < 1) per_sm = 1;
-    per_sm = l2_cap<L>(sm_count, per_sm, a);
-    const long long want = (a.nptl + kBlock - 1) / kBlock;
-    long long grid = (long long)sm_count * per_sm;  // persistent: a multiple of the SM count
-    if (want < grid) grid = want > 0 ? want : 1;
-    auto go = [&](auto sel_c, auto trk_c, auto spec_c) {
-        push_kernel_coop<L, decltype(sel_c)::value, decltype(trk_c)::value, decltype(spec_c)::value>
-            <<<(unsigned)grid, kBlock, smem, st>>>(prm, P, fld, a);
-    };
-    auto by_maps = [&](auto sel_c, auto trk_c) {
-        if (maps) go(sel_c, trk_c, std::integral_constant<int, kSpecAltMaps>{});
-        else go(sel_c, trk_c, std::integral_constant<int, kSpecAlt>{});
-    };
-    auto by_trk = [&](auto sel_c) {
-        if (a.trk.enabled) by_maps(sel_c, std::true_type{});
-        else by_maps(sel_c, std::false_type{});
-    };
-    if (a.sel == 0) by_trk(std::integral_constant<int, 0>{});
-    else by_trk(std::integral_constant<int, 1>{});
+    if constexpr (Rec<L>::EXT) {         // focused transport reads the extended records only (abi.cu: pick_layout)
+        if (prm.focused_transport) { with_maps(std::integral_constant<int, PATH_FT>{}); return; }
+    }
+    // Parker pushers: only runs with maps come here (without maps they are the named-config kernels of part 0)
+    launch_alt_spec<L, alt_spec(PATH_PARKER, true)>(prm, P, fld, a, sm_count, st);
 }
 #endif
 
