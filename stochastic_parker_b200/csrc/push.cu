@@ -47,18 +47,26 @@ __device__ __forceinline__ double min2(double a, double b) { return (b < a) ? b 
 // pow / sqrt / division sequences into ~500.  Arguments are what the pushers guarantee: normal, positive where a
 // root or a logarithm is taken; pow(0, y) keeps its IEEE value.
 constexpr double kThird = 1.0 / 3.0, kTwoThirds = 2.0 / 3.0;
+// PowBase: a base of several powers.  Production build: its logarithm is taken once (a focused-transport step raises
+// b, p/p0, |mu| and p to ten exponents; as separate pow calls that was ten logarithms, the compiler cannot merge them
+// across the run-time switches).  Reference-order build: just the value, every power is its own pow().
+struct PowBase { double x, lx; };
 #if GPAT_STRICT
 __device__ __forceinline__ double pm_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ PowBase pm_base(double x) { return PowBase{x, 0.0}; }
+__device__ __forceinline__ double pm_powb(const PowBase& b, double y) { return pow(b.x, y); }
 __device__ __forceinline__ double pm_pow(double x, double y) { return pow(x, y); }
 __device__ __forceinline__ double pm_div(double a, double b) { return a / b; }
 __device__ __forceinline__ double pm_divc(double a, double c) { return a / c; }
 #else
 __device__ __forceinline__ double pm_sqrt(double x) { return fm::sqrt_pos(x); }
-__device__ __forceinline__ double pm_pow(double x, double y)
+__device__ __forceinline__ PowBase pm_base(double x) { return PowBase{x, fm::log_pos(x > 0.0 ? x : 1.0)}; }
+__device__ __forceinline__ double pm_powb(const PowBase& b, double y)
 {
-    const double r = fm::exp_mid(y * fm::log_pos(x > 0.0 ? x : 1.0));
-    return (x > 0.0) ? r : ((y > 0.0) ? 0.0 : (y == 0.0 ? 1.0 : __longlong_as_double(0x7ff0000000000000LL)));
+    const double r = fm::exp_mid(y * b.lx);
+    return (b.x > 0.0) ? r : ((y > 0.0) ? 0.0 : (y == 0.0 ? 1.0 : __longlong_as_double(0x7ff0000000000000LL)));
 }
+__device__ __forceinline__ double pm_pow(double x, double y) { return pm_powb(pm_base(x), y); }
 __device__ __forceinline__ double pm_div(double a, double b) { return a * fm::rcp(b); }
 __device__ __forceinline__ double pm_divc(double a, double c) { return a * (1.0 / c); }  // c: a literal
 #endif
@@ -414,6 +422,7 @@ __device__ __forceinline__ void gather_aux(const DevParams& prm, const float* __
 // ---- kappa (particle_module.f90:93-104) --------------------------------------------
 struct Kappa {
     double knorm_para, kpara, kperp, skpara, skperp, skpara_perp;
+    PowBase pb_b, pb_p, pb_lc;  // bases b, p/p0, lc_slab of calc_kappa's powers (set under the switches that use them)
     double dkxx_dx, dkyy_dy, dkzz_dz, dkxy_dx, dkxy_dy, dkxz_dx, dkxz_dz, dkyz_dy, dkyz_dz;
 };
 
@@ -435,8 +444,9 @@ __device__ __forceinline__ void calc_kappa(const DevParams& prm, const BField& B
     const double ib3 = ib1 * ib2;
     double knp = 1.0, knperp = 1.0;
     if (prm.mag_dependency == 1) {
-        knp = knp * pm_pow(b, prm.gm2);
-        if (prm.nlgc) knperp = knperp * pm_pow(b, prm.gm2_3);
+        k.pb_b = pm_base(b);
+        knp = knp * pm_powb(k.pb_b, prm.gm2);
+        if (prm.nlgc) knperp = knperp * pm_powb(k.pb_b, prm.gm2_3);
     }
     const bool dbf = aux && prm.deltab_flag, cof = aux && prm.correlation_flag;
     if (dbf) {  // particle_module.f90:2246-2248 / 2505-2509
@@ -444,20 +454,22 @@ __device__ __forceinline__ void calc_kappa(const DevParams& prm, const BField& B
         if (prm.nlgc) knperp = knperp * pm_pow(aux[0], -kThird) * pm_pow(aux[4], kTwoThirds);
     }
     if (cof) {  // particle_module.f90:2252-2254 / 2513-2517
-        knp = knp * pm_pow(aux[8], prm.gamma_turb - 1.0);
-        if (prm.nlgc) knperp = knperp * pm_pow(aux[8], pm_divc(prm.gamma_turb - 1.0, 3.0)) * pm_pow(aux[12], kTwoThirds);
+        k.pb_lc = pm_base(aux[8]);
+        knp = knp * pm_powb(k.pb_lc, prm.gamma_turb - 1.0);
+        if (prm.nlgc) knperp = knperp * pm_powb(k.pb_lc, pm_divc(prm.gamma_turb - 1.0, 3.0)) * pm_pow(aux[12], kTwoThirds);
     }
     k.knorm_para = knp;
     double ax = 0.0, ay = 0.0, az = 0.0;  // coefficients multiplying the b_i b_j terms
+    if (prm.momentum_dependency == 1) k.pb_p = pm_base(pm_div(p, prm.p0));
     if (!prm.nlgc) {
-        double knorm = (prm.momentum_dependency == 1) ? knp * pm_pow(pm_div(p, prm.p0), prm.pindex) : knp;
+        double knorm = (prm.momentum_dependency == 1) ? knp * pm_powb(k.pb_p, prm.pindex) : knp;
         k.kpara = prm.kpara0 * knorm;
         k.kperp = k.kpara * prm.kret;
     } else {
         double kn_para = knp, kn_perp = knperp;
         if (prm.momentum_dependency == 1) {
-            kn_para = knp * pm_pow(pm_div(p, prm.p0), prm.pindex);
-            kn_perp = knperp * pm_pow(pm_div(p, prm.p0), prm.pidx_perp);
+            kn_para = knp * pm_powb(k.pb_p, prm.pindex);
+            kn_perp = knperp * pm_powb(k.pb_p, prm.pidx_perp);
         }
         k.kpara = prm.kpara0 * kn_para;
         k.kperp = prm.kpara0 * prm.kperp_kpara * kn_perp * sq(mu);
@@ -571,9 +583,10 @@ __device__ __forceinline__ void momentum_diffusion(const DevParams& prm, const B
             gshear = pm_divc(2.0 * (sq(sxx) + sq(syy) + sq(szz) + 2.0 * (sq(sxy) + sq(sxz) + sq(syz))), 15.0);
         }
         if (gshear > 0.0) {
+            const PowBase pbp = pm_base(p);
             dp_dt = dp_dt + (2.0 + prm.pindex) * gshear * prm.tau0 * k.knorm_para *
-                                pm_pow(p, prm.pindex - 1.0) * prm.p0_pow;
-            dpp = dpp + gshear * prm.tau0 * k.knorm_para * pm_pow(p, prm.pindex) * prm.p0_pow;
+                                pm_powb(pbp, prm.pindex - 1.0) * prm.p0_pow;
+            dpp = dpp + gshear * prm.tau0 * k.knorm_para * pm_powb(pbp, prm.pindex) * prm.p0_pow;
         }
     }
 }
@@ -796,17 +809,18 @@ __device__ __forceinline__ void push_2d_ft(const DevParams& prm, const PushArgs&
         double dmu_dt = q.v * div_bnorm + q.mu * divv - 3 * q.mu * bb_gradv - pm_div(2 * bv_gradv, q.v);
         dmu_dt = dmu_dt * (1 - mu2) * 0.5;
         const double h0 = (double)0.2f;
-        const double dtmp = pm_pow(fabs(q.mu), prm.gamma_turb - 1) + h0;
+        const PowBase pbm = pm_base(fabs(q.mu));
+        const double dtmp = pm_powb(pbm, prm.gamma_turb - 1) + h0;
         double duu = prm.duu0 * (1 - mu2) * dtmp;
         double duu_du;
-        if (q.mu > 0.0) duu_du = prm.duu0 * (-2 * q.mu * dtmp + (1 - mu2) * pm_pow(fabs(q.mu), prm.gamma_turb - 2));
-        else if (q.mu < 0.0) duu_du = prm.duu0 * (-2 * q.mu * dtmp - (1 - mu2) * pm_pow(fabs(q.mu), prm.gamma_turb - 2));
+        if (q.mu > 0.0) duu_du = prm.duu0 * (-2 * q.mu * dtmp + (1 - mu2) * pm_powb(pbm, prm.gamma_turb - 2));
+        else if (q.mu < 0.0) duu_du = prm.duu0 * (-2 * q.mu * dtmp - (1 - mu2) * pm_powb(pbm, prm.gamma_turb - 2));
         else duu_du = 0.0;
         double duu_norm = 1.0;
-        if (prm.mag_dependency == 1) duu_norm = duu_norm * pm_pow(b, 2.0 - prm.gamma_turb);
+        if (prm.mag_dependency == 1) duu_norm = duu_norm * pm_powb(k.pb_b, 2.0 - prm.gamma_turb);
         if (aux && prm.deltab_flag) duu_norm = duu_norm * aux[0];                                    // :3143-3145
-        if (aux && prm.correlation_flag) duu_norm = duu_norm * pm_pow(aux[8], 1.0 - prm.gamma_turb);   // :3146-3148
-        if (prm.momentum_dependency == 1) duu_norm = duu_norm * pm_pow(pm_div(q.p, prm.p0), prm.gamma_turb - 1);
+        if (aux && prm.correlation_flag) duu_norm = duu_norm * pm_powb(k.pb_lc, 1.0 - prm.gamma_turb);   // :3146-3148
+        if (prm.momentum_dependency == 1) duu_norm = duu_norm * pm_powb(k.pb_p, prm.gamma_turb - 1);
         duu_du = duu_du * duu_norm;
         duu = duu * duu_norm;
         dmu_dt = dmu_dt + duu_du;
@@ -980,17 +994,18 @@ __device__ __forceinline__ void push_ft_3d_like(const DevParams& prm, const Push
         double dmu_dt = q.v * div_bnorm + q.mu * divv - 3 * q.mu * bb_gradv - pm_div(2 * bv_gradv, q.v);
         dmu_dt = dmu_dt * (1 - mu2) * 0.5;
         const double h0 = (double)0.2f;
-        const double dtmp = pm_pow(fabs(q.mu), prm.gamma_turb - 1) + h0;
+        const PowBase pbm = pm_base(fabs(q.mu));
+        const double dtmp = pm_powb(pbm, prm.gamma_turb - 1) + h0;
         double duu = prm.duu0 * (1 - mu2) * dtmp;
         double duu_du;
-        if (q.mu > 0.0) duu_du = prm.duu0 * (-2 * q.mu * dtmp + (1 - mu2) * pm_pow(fabs(q.mu), prm.gamma_turb - 2));
-        else if (q.mu < 0.0) duu_du = prm.duu0 * (-2 * q.mu * dtmp - (1 - mu2) * pm_pow(fabs(q.mu), prm.gamma_turb - 2));
+        if (q.mu > 0.0) duu_du = prm.duu0 * (-2 * q.mu * dtmp + (1 - mu2) * pm_powb(pbm, prm.gamma_turb - 2));
+        else if (q.mu < 0.0) duu_du = prm.duu0 * (-2 * q.mu * dtmp - (1 - mu2) * pm_powb(pbm, prm.gamma_turb - 2));
         else duu_du = 0.0;
         double duu_norm = 1.0;
-        if (prm.mag_dependency == 1) duu_norm = duu_norm * pm_pow(b, 2.0 - prm.gamma_turb);
+        if (prm.mag_dependency == 1) duu_norm = duu_norm * pm_powb(k.pb_b, 2.0 - prm.gamma_turb);
         if (aux && prm.deltab_flag) duu_norm = duu_norm * aux[0];
-        if (aux && prm.correlation_flag) duu_norm = duu_norm * pm_pow(aux[8], 1.0 - prm.gamma_turb);
-        if (prm.momentum_dependency == 1) duu_norm = duu_norm * pm_pow(pm_div(q.p, prm.p0), prm.gamma_turb - 1);
+        if (aux && prm.correlation_flag) duu_norm = duu_norm * pm_powb(k.pb_lc, 1.0 - prm.gamma_turb);
+        if (prm.momentum_dependency == 1) duu_norm = duu_norm * pm_powb(k.pb_p, prm.gamma_turb - 1);
         duu_du = duu_du * duu_norm;
         duu = duu * duu_norm;
         dmu_dt = dmu_dt + duu_du;
