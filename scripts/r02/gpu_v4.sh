@@ -1,7 +1,7 @@
 #!/bin/bash
-# Round 2, call V3: final state of the round -- full GPU suite, smoke, default bench (both arms), C4 and C3 lines.
+# Round 2, call V4: final state of the round -- full GPU suite, smoke, default bench (both arms), C4 and C3 lines.
 mkdir -p gpurun_out
-T=r02v3
+T=r02v4
 python -m pytest tests -m gpu -q > gpurun_out/${T}_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${T}_pytest_gpu.log
 tail -3 gpurun_out/${T}_pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2>&1; tail -1 gpurun_out/${T}_smoke.log
