@@ -407,7 +407,21 @@ def main():
                 os.remove(path)
         frames.append(t)
     tstamps = [f * w.dt_out for f in range(nint + 1)]
-    out = sim.alloc_diagnostics()
+    # histogram arrays in pinned memory too (the Fortran driver's fglobal / flocalK after cudaHostRegister):
+    # gpat_diagnostics copies the reduced histograms straight into them
+    pinned_keep = []
+
+    def pinned_diagnostics(s):
+        def pin(a):
+            if a is None:
+                return None
+            t = torch.zeros(a.shape, dtype=torch.float64, pin_memory=True)
+            pinned_keep.append(t)
+            return t.numpy()
+        fg, fl = s.alloc_diagnostics()
+        return pin(fg), [pin(a) for a in fl]
+
+    out = pinned_diagnostics(sim)
     frame_bytes = frames[0].numel() * 4
     hist_bytes = out[0].nbytes + sum(a.nbytes for a in out[1] if a is not None) + 9 * 8
 
@@ -504,7 +518,7 @@ def main():
             sim2 = spb.GpatSim(P, ws.nptl_max, device=local_rank)
             if world > 1:
                 spb.bootstrap_comm(sim2, dist)
-            out2 = sim2.alloc_diagnostics()
+            out2 = pinned_diagnostics(sim2)
             t2 = run_intervals_timed(sim2, ws, P, args, frames, tstamps, world, dist, torch, dev, out2, local_rank)
             m2, p2, e2, s2 = reduce_over_ranks(t2, world, dist, torch, dev)
             line["strong_scaling"] = {"particles_total": ws.nptl * world, "particles_per_gpu": ws.nptl,
