@@ -27,8 +27,10 @@ namespace fm {
 // Polynomial coefficients and magic numbers of log_pos / exp_mid.  As literals every FP64 constant costs two UMOV
 // (uniform-register immediates) right before its use -- 50 of the 1070 warp-instructions of a C1 step
 // (profiles/r02w_c1_by_line.txt); from a __constant__ table (FM_CONST_TABLE=1) one LDCU.128 brings two of them.
-// MEASURED, NO GAIN (profiles/README.md, call X: C1 +0.2 %, C3 +1.3 %, C4 -2.3 %, C5 +0.4 %): the default keeps the
-// literals; the host build (tests/fastmath_host_check.cpp) always uses them.
+// MEASURED: no gain in the kernels of the named configs (profiles/README.md, call X: C1 +0.2 %, C3 +1.3 %, C4 -2.3 %,
+// C5 +0.4 %), +1-1.5 % in the general-pusher kernels, whose steps take ten powers (call K2).  The default keeps the
+// literals, the Makefile turns the table on for the two general-pusher translation units; the host build
+// (tests/fastmath_host_check.cpp) always uses the literals.
 #ifndef FM_CONST_TABLE
 #define FM_CONST_TABLE 0
 #endif
